@@ -1,0 +1,46 @@
+// Error reporting and device queries shared by every rb200 entry point.
+#include <stdarg.h>
+
+#include "common.cuh"
+
+static thread_local char g_err[1024] = "";
+
+int rb_set_error(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+struct DevInfo { int sm = 0, smem = 0; bool ok = false; };
+static DevInfo& dev_info() {
+    static thread_local DevInfo d[64];
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) { static thread_local DevInfo none; return none; }
+    if (!d[dev].ok) {
+        cudaDeviceGetAttribute(&d[dev].sm, cudaDevAttrMultiProcessorCount, dev);
+        cudaDeviceGetAttribute(&d[dev].smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+        d[dev].ok = d[dev].sm > 0;
+    }
+    return d[dev];
+}
+int rb_sm_count() { int s = dev_info().sm; return s > 0 ? s : 148; }
+int rb_max_smem_optin() { int s = dev_info().smem; return s > 0 ? s : 232448; }
+
+extern "C" int rb200_version(void) { return RB200_VERSION; }
+extern "C" const char* rb200_last_error(void) { return g_err; }
+extern "C" int rb200_sm_count(void) { return rb_sm_count(); }
+
+// sizeof() of the ABI structs, so that foreign-language bindings can verify their mirrors.
+extern "C" size_t rb200_sizeof(int which) {
+    switch (which) {
+        case 0: return sizeof(rb200_tower_job);
+        case 1: return sizeof(rb200_tower_bwd_job);
+        case 2: return sizeof(rb200_opt_state);
+        case 3: return sizeof(rb200_step_params);
+        case 4: return sizeof(rb200_step_views);
+        case 5: return sizeof(rb200_sumsq_seg);
+        default: return 0;
+    }
+}

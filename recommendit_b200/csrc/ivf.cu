@@ -1,0 +1,805 @@
+// IVFFlat / flat inner-product retrieval (sm_100a), fp32 FFMA path.
+//
+// Restates on the GPU what the reference gets from faiss.IndexIVFFlat (src/models/faiss_index.py:
+// 68-74 build, :113/:145 search; algorithm per SURVEY.md Appendix B):
+//
+//   build   normalise rows → assign to argmax-IP centroid → stable counting sort into CSR lists
+//           (offsets / list_ids / list_vecs contiguous per list)
+//   train   spherical k-means: assign + deterministic segment mean + renormalise
+//   search  (1) coarse scores q·Cᵀ  (2) top-nprobe lists per query, descending
+//           (3) LIST-MAJOR scan: (list, query) pairs are radix-sorted by list so that one CTA
+//               stages a 64-vector tile of a list in shared memory ONCE and scores it against every
+//               query that probes the list — the database is read from HBM once per batch instead
+//               of once per probing query
+//           (4) per-query radix-select of the k best candidates + bitonic sort, ties by scan order
+//   flat    exhaustive search = the same score/select kernels over row chunks with a running top-k
+#include <cub/cub.cuh>
+#include <float.h>
+
+#include "common.cuh"
+
+namespace {
+
+constexpr int NT = 256;
+constexpr int TT = 64;          // score tile: 64 queries × 64 vectors
+
+// ------------------------------------------------------------------------------------------ //
+// small utilities
+// ------------------------------------------------------------------------------------------ //
+__global__ void __launch_bounds__(NT) normalize_rows_kernel(const float* __restrict__ x, long long n, int D, float eps,
+                                                            float* __restrict__ out) {
+    const long long row = ((long long)blockIdx.x * NT + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (row >= n) return;
+    float ss = 0.f;
+    for (int d = lane; d < D; d += 32) { const float v = x[row * D + d]; ss = fmaf(v, v, ss); }
+    ss = rb_warp_sum(ss);
+    const float den = fmaxf(sqrtf(ss), eps);
+    for (int d = lane; d < D; d += 32) out[row * D + d] = x[row * D + d] / den;
+}
+
+// load a 64-row tile of row-major [*, D] data (rows given by an optional index list) into smem
+template <int D, typename IdxT>
+__device__ __forceinline__ void load_tile(float* __restrict__ S, int ld, const float* __restrict__ src, long long row0,
+                                          long long row_end, const IdxT* __restrict__ index, int index_div) {
+    for (int idx = threadIdx.x; idx < TT * (D / 4); idx += NT) {
+        const int r = idx / (D / 4), c = idx - r * (D / 4);
+        const long long g = row0 + r;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (g < row_end) {
+            const long long srow = index ? (long long)(index[g] / index_div) : g;
+            v = __ldg(reinterpret_cast<const float4*>(src + srow * D) + c);
+        }
+        *reinterpret_cast<float4*>(S + r * ld + c * 4) = v;
+    }
+}
+
+// acc[r][c] = Σ_k A[ty*4+r][k] · W[tx+16c][k]
+template <int D, int LD>
+__device__ __forceinline__ void score_tile(const float* __restrict__ As, const float* __restrict__ Ws, int tx, int ty,
+                                           float (&acc)[4][4]) {
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) acc[r][c] = 0.f;
+    const float* a_base = As + (ty * 4) * LD;
+    const float* w_base = Ws + tx * LD;
+#pragma unroll 2
+    for (int k = 0; k < D; k += 4) {
+        float4 b[4];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) b[c] = *reinterpret_cast<const float4*>(w_base + c * 16 * LD + k);
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            const float4 a = *reinterpret_cast<const float4*>(a_base + r * LD + k);
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                float v = acc[r][c];
+                v = fmaf(a.x, b[c].x, v); v = fmaf(a.y, b[c].y, v);
+                v = fmaf(a.z, b[c].z, v); v = fmaf(a.w, b[c].w, v);
+                acc[r][c] = v;
+            }
+        }
+    }
+}
+
+template <int D> struct Ld { static constexpr int v = ((D / 4) & 1) ? D : D + 4; };
+template <int D> constexpr size_t tile_pair_bytes() { return sizeof(float) * 2 * TT * Ld<D>::v; }
+// opt in to > 48 KB of dynamic shared memory (D = 128) once per kernel instantiation
+template <typename K>
+int allow_smem(K kernel, size_t bytes, bool& done) {
+    if (!done && bytes > 48 * 1024) RB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    done = true;
+    return RB200_OK;
+}
+#define RB_TILE_LAUNCH(KERNEL, DD, GRID, ST, ...)                                   \
+    do {                                                                            \
+        static bool done__ = false;                                                 \
+        int rc__ = allow_smem(KERNEL<DD>, tile_pair_bytes<DD>(), done__);           \
+        if (rc__) return rc__;                                                      \
+        KERNEL<DD><<<GRID, NT, tile_pair_bytes<DD>(), ST>>>(__VA_ARGS__);           \
+    } while (0)
+
+// ------------------------------------------------------------------------------------------ //
+// dense scores: out[a][col0 + b] = A[a]·Bm[b]   (coarse quantizer, flat-search chunks)
+// ------------------------------------------------------------------------------------------ //
+template <int D>
+__global__ void __launch_bounds__(NT) dense_scores_kernel(const float* __restrict__ A, long long na, const float* __restrict__ Bm,
+                                                          long long nb, float* __restrict__ out, long long ld_out,
+                                                          long long col0) {
+    constexpr int LD = Ld<D>::v;
+    extern __shared__ __align__(16) float tile_smem[];
+    float* As = tile_smem;
+    float* Bs = tile_smem + TT * LD;
+    const long long a0 = (long long)blockIdx.y * TT, b0 = (long long)blockIdx.x * TT;
+    load_tile<D, int>(As, LD, A, a0, na, nullptr, 1);
+    load_tile<D, int>(Bs, LD, Bm, b0, nb, nullptr, 1);
+    __syncthreads();
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+    float acc[4][4];
+    score_tile<D, LD>(As, Bs, tx, ty, acc);
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        const long long a = a0 + ty * 4 + r;
+        if (a >= na) continue;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            const long long b = b0 + tx + 16 * c;
+            if (b < nb) out[a * ld_out + col0 + b] = acc[r][c];
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------ //
+// assignment: argmax_c x·centroid_c  (lowest index on ties)
+// ------------------------------------------------------------------------------------------ //
+template <int D>
+__global__ void __launch_bounds__(NT) assign_kernel(const float* __restrict__ x, long long n, const float* __restrict__ C,
+                                                    int nlist, int* __restrict__ assign, float* __restrict__ best_score) {
+    constexpr int LD = Ld<D>::v;
+    extern __shared__ __align__(16) float tile_smem[];
+    float* Xs = tile_smem;
+    float* Cs = tile_smem + TT * LD;
+    const long long r0 = (long long)blockIdx.x * TT;
+    load_tile<D, int>(Xs, LD, x, r0, n, nullptr, 1);
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+    float bv[4]; int bi[4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) { bv[r] = -FLT_MAX; bi[r] = 0x7fffffff; }
+    for (int c0 = 0; c0 < nlist; c0 += TT) {
+        __syncthreads();
+        load_tile<D, int>(Cs, LD, C, c0, nlist, nullptr, 1);
+        __syncthreads();
+        float acc[4][4];
+        score_tile<D, LD>(Xs, Cs, tx, ty, acc);
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                const int ci = c0 + tx + 16 * c;
+                if (ci < nlist && (acc[r][c] > bv[r] || (acc[r][c] == bv[r] && ci < bi[r]))) { bv[r] = acc[r][c]; bi[r] = ci; }
+            }
+    }
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+#pragma unroll
+        for (int o = 8; o > 0; o >>= 1) {
+            const float ov = __shfl_xor_sync(RB_FULL_MASK, bv[r], o);
+            const int oi = __shfl_xor_sync(RB_FULL_MASK, bi[r], o);
+            if (ov > bv[r] || (ov == bv[r] && oi < bi[r])) { bv[r] = ov; bi[r] = oi; }
+        }
+        const long long row = r0 + ty * 4 + r;
+        if (tx == 0 && row < n) {
+            assign[row] = bi[r];
+            if (best_score) best_score[row] = bv[r];
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------ //
+// CSR construction / k-means update (shared: stable sort of rows by list)
+// ------------------------------------------------------------------------------------------ //
+__global__ void iota_kernel(int* __restrict__ v, long long n) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) v[i] = (int)i;
+}
+__global__ void histogram_kernel(const int* __restrict__ keys, long long n, int nbins, int* __restrict__ counts) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) { const int k = keys[i]; if ((unsigned)k < (unsigned)nbins) atomicAdd(counts + k, 1); }
+}
+__global__ void offsets_to_i64_kernel(const int* __restrict__ excl, const int* __restrict__ counts, int nlist,
+                                      int64_t* __restrict__ offsets) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < nlist) offsets[i] = excl[i];
+    if (i == nlist - 1) offsets[nlist] = (int64_t)excl[i] + counts[i];
+}
+__global__ void __launch_bounds__(NT) gather_rows_kernel(const float* __restrict__ x, const int* __restrict__ order, long long n,
+                                                         int D, int64_t* __restrict__ list_ids, float* __restrict__ list_vecs) {
+    const long long i = ((long long)blockIdx.x * NT + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (i >= n) return;
+    const long long src = order[i];
+    if (lane == 0) list_ids[i] = src;
+    for (int c = lane; c < D / 4; c += 32)
+        reinterpret_cast<float4*>(list_vecs + i * D)[c] = __ldg(reinterpret_cast<const float4*>(x + src * D) + c);
+}
+// one warp per list: mean of member rows in ascending row order, then L2 renormalise
+__global__ void __launch_bounds__(NT) centroid_update_kernel(const float* __restrict__ x, const int* __restrict__ order,
+                                                             const int* __restrict__ excl, const int* __restrict__ counts,
+                                                             int nlist, int D, float* __restrict__ centroids) {
+    const int l = (blockIdx.x * NT + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (l >= nlist) return;
+    const int cnt = counts[l], beg = excl[l];
+    if (cnt == 0) return;   // empty list keeps its centroid (host-side split policy decides what to do)
+    float ss = 0.f;
+    for (int d = lane; d < D; d += 32) {
+        float s = 0.f;
+        for (int j = 0; j < cnt; ++j) s += __ldg(x + (long long)order[beg + j] * D + d);
+        s /= (float)cnt;
+        centroids[(long long)l * D + d] = s;
+        ss = fmaf(s, s, ss);
+    }
+    ss = rb_warp_sum(ss);
+    const float den = fmaxf(sqrtf(ss), 1e-30f);
+    for (int d = lane; d < D; d += 32) centroids[(long long)l * D + d] /= den;
+}
+
+struct SortWs {
+    int* iota; int* order; int* keys_sorted; int* counts; int* excl; char* temp; size_t temp_bytes;
+};
+size_t sort_ws_temp(long long n, int nlist) {
+    size_t a = 0, b = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, a, (const int*)nullptr, (int*)nullptr, (const int*)nullptr, (int*)nullptr, (int)n);
+    cub::DeviceScan::ExclusiveSum(nullptr, b, (const int*)nullptr, (int*)nullptr, nlist);
+    return a > b ? a : b;
+}
+size_t sort_ws_bytes(long long n, int nlist) {
+    return 256 * 8 + sizeof(int) * (3 * (size_t)n + 2 * (size_t)nlist) + sort_ws_temp(n, nlist);
+}
+bool carve_sort_ws(RbArena& ar, long long n, int nlist, SortWs& w) {
+    w.iota = ar.take<int>(n); w.order = ar.take<int>(n); w.keys_sorted = ar.take<int>(n);
+    w.counts = ar.take<int>(nlist); w.excl = ar.take<int>(nlist);
+    w.temp_bytes = sort_ws_temp(n, nlist);
+    w.temp = ar.take<char>(w.temp_bytes);
+    return ar.ok();
+}
+int key_bits_i32(int nlist) { int b = 1; while (b < 31 && (1 << b) < nlist) ++b; return b; }
+
+int sort_rows_by_list(const int* assign, long long n, int nlist, SortWs& w, cudaStream_t st) {
+    iota_kernel<<<(unsigned)((n + NT - 1) / NT), NT, 0, st>>>(w.iota, n);
+    RB_LAUNCH_CHECK("iota_kernel");
+    size_t tb = w.temp_bytes;
+    RB_CUDA(cub::DeviceRadixSort::SortPairs(w.temp, tb, assign, w.keys_sorted, (const int*)w.iota, w.order, (int)n, 0,
+                                            key_bits_i32(nlist), st));
+    RB_CUDA(cudaMemsetAsync(w.counts, 0, sizeof(int) * nlist, st));
+    histogram_kernel<<<(unsigned)((n + NT - 1) / NT), NT, 0, st>>>(assign, n, nlist, w.counts);
+    RB_LAUNCH_CHECK("histogram_kernel");
+    tb = w.temp_bytes;
+    RB_CUDA(cub::DeviceScan::ExclusiveSum(w.temp, tb, (const int*)w.counts, w.excl, nlist, st));
+    return RB200_OK;
+}
+
+// ------------------------------------------------------------------------------------------ //
+// search, step 2: top-nprobe lists per query (one CTA per query) + candidate bookkeeping
+// ------------------------------------------------------------------------------------------ //
+__global__ void __launch_bounds__(NT) probe_select_kernel(const float* __restrict__ coarse, int nlist, int nprobe,
+                                                          const int64_t* __restrict__ offsets, int* __restrict__ probes,
+                                                          int* __restrict__ cand_base, long long* __restrict__ totals,
+                                                          int* __restrict__ list_qcount) {
+    extern __shared__ float sc[];                  // [nlist]
+    __shared__ float wv[NT / 32];
+    __shared__ int wi[NT / 32];
+    const int q = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    for (int i = tid; i < nlist; i += NT) sc[i] = coarse[(long long)q * nlist + i];
+    __syncthreads();
+    long long total = 0;
+    for (int p = 0; p < nprobe; ++p) {
+        float bv = -FLT_MAX; int bi = 0x7fffffff;
+        for (int i = tid; i < nlist; i += NT) {
+            const float v = sc[i];
+            if (v > bv || (v == bv && i < bi)) { bv = v; bi = i; }   // i ascending per thread: strict > keeps lowest
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const float ov = __shfl_xor_sync(RB_FULL_MASK, bv, o);
+            const int oi = __shfl_xor_sync(RB_FULL_MASK, bi, o);
+            if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+        }
+        if (lane == 0) { wv[warp] = bv; wi[warp] = bi; }
+        __syncthreads();
+        if (tid == 0) {
+            for (int w = 1; w < NT / 32; ++w)
+                if (wv[w] > bv || (wv[w] == bv && wi[w] < bi)) { bv = wv[w]; bi = wi[w]; }
+            if (bi >= nlist) bi = -1;                                  // fewer than nprobe scorable lists
+            probes[(long long)q * nprobe + p] = bi;
+            cand_base[(long long)q * nprobe + p] = (int)total;
+            if (bi >= 0) {
+                total += offsets[bi + 1] - offsets[bi];
+                sc[bi] = -INFINITY;                                    // never picked again (-inf < -FLT_MAX)
+                atomicAdd(list_qcount + bi, 1);
+            }
+        }
+        __syncthreads();
+        }
+    if (tid == 0) totals[q] = total;
+}
+
+__global__ void pair_keys_kernel(const int* __restrict__ probes, long long n_pairs, int nlist, int* __restrict__ keys,
+                                 int* __restrict__ vals) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_pairs) return;
+    const int l = probes[i];
+    keys[i] = l >= 0 ? l : nlist;     // invalid probes sort to the end
+    vals[i] = (int)i;
+}
+
+__global__ void reduce_totals_kernel(const long long* __restrict__ totals, int nq, long long* __restrict__ out2) {
+    if (threadIdx.x || blockIdx.x) return;
+    long long s = 0, m = 0;
+    for (int i = 0; i < nq; ++i) { s += totals[i]; if (totals[i] > m) m = totals[i]; }
+    out2[0] = s; out2[1] = m;
+}
+
+// ------------------------------------------------------------------------------------------ //
+// search, step 3: list-major scan.  grid = (vector tiles, lists)
+// ------------------------------------------------------------------------------------------ //
+template <int D>
+__global__ void __launch_bounds__(NT) list_scan_kernel(const float* __restrict__ q, const float* __restrict__ list_vecs,
+                                                       const int64_t* __restrict__ offsets, const int* __restrict__ pair_qp,
+                                                       const int* __restrict__ list_qstart, int nprobe,
+                                                       const int* __restrict__ cand_base, const long long* __restrict__ cand_off,
+                                                       float* __restrict__ cand) {
+    constexpr int LD = Ld<D>::v;
+    extern __shared__ __align__(16) float tile_smem[];
+    float* Vs = tile_smem;
+    float* Qs = tile_smem + TT * LD;
+    __shared__ long long dst[TT];
+    const int l = blockIdx.y;
+    const long long lbeg = offsets[l], lend = offsets[l + 1];
+    const long long v0 = lbeg + (long long)blockIdx.x * TT;
+    if (v0 >= lend) return;
+    const int qs = list_qstart[l], qe = list_qstart[l + 1];
+    if (qs == qe) return;
+    load_tile<D, int>(Vs, LD, list_vecs, v0, lend, nullptr, 1);
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+    const int nv = (int)min((long long)TT, lend - v0);
+    for (int p0 = qs; p0 < qe; p0 += TT) {
+        __syncthreads();
+        load_tile<D, int>(Qs, LD, q, p0, qe, pair_qp, nprobe);
+        if (threadIdx.x < TT) {
+            const int pi = p0 + threadIdx.x;
+            long long d = -1;
+            if (pi < qe) {
+                const int qp = pair_qp[pi];
+                d = cand_off[qp / nprobe] + cand_base[qp] + (v0 - lbeg);
+            }
+            dst[threadIdx.x] = d;
+        }
+        __syncthreads();
+        float acc[4][4];
+        score_tile<D, LD>(Qs, Vs, tx, ty, acc);
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            const long long d = dst[ty * 4 + r];
+            if (d < 0) continue;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                const int vj = tx + 16 * c;
+                if (vj < nv) cand[d + vj] = acc[r][c];
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------ //
+// step 4: per-query top-k.  Radix select (4 × 8 bit, MSB first) of the k-th largest key, ordered
+// compaction (ties by candidate position), bitonic sort of the winners.
+// ------------------------------------------------------------------------------------------ //
+__device__ __forceinline__ uint32_t f2key(float f) {
+    const uint32_t u = __float_as_uint(f);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float key2f(uint32_t k) {
+    return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);
+}
+
+// id resolution modes for the winners
+struct ResolveIvf {      // candidate position → (probe, offset in list) → list_ids
+    const int* probes; const int* cand_base; const int64_t* offsets; const int64_t* list_ids; int nprobe;
+};
+struct ResolveFlat {     // [running top-k (kprev entries) | chunk rows]
+    const int64_t* prev_ids; int kprev; long long row_base;
+};
+
+template <typename R> __device__ long long resolve_id(const R& r, int q, int c);
+template <> __device__ long long resolve_id<ResolveIvf>(const ResolveIvf& r, int q, int c) {
+    const int* base = r.cand_base + (long long)q * r.nprobe;
+    int lo = 0, hi = r.nprobe - 1;           // last probe p with base[p] <= c  (empty lists share a base: take the last)
+    while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (base[mid] <= c) lo = mid; else hi = mid - 1; }
+    // step back over probes whose list is too short to contain c (only possible for empty/invalid ones after lo)
+    int p = lo;
+    while (p > 0) {
+        const int l = r.probes[(long long)q * r.nprobe + p];
+        if (l >= 0 && c - base[p] < r.offsets[l + 1] - r.offsets[l]) break;
+        --p;
+    }
+    const int l = r.probes[(long long)q * r.nprobe + p];
+    return r.list_ids[r.offsets[l] + (c - base[p])];
+}
+template <> __device__ long long resolve_id<ResolveFlat>(const ResolveFlat& r, int q, int c) {
+    if (c < r.kprev) return r.prev_ids[(long long)q * r.kprev + c];
+    return r.row_base + (c - r.kprev);
+}
+
+template <typename R>
+__global__ void __launch_bounds__(NT) select_topk_kernel(const float* __restrict__ cand, const long long* __restrict__ cand_off,
+                                                         long long fixed_stride, const long long* __restrict__ counts,
+                                                         int fixed_count, int k, int sort_n, int cache_cap, R res,
+                                                         float* __restrict__ out_scores, int64_t* __restrict__ out_ids) {
+    extern __shared__ __align__(16) unsigned char sm_raw[];
+    uint32_t* skey = reinterpret_cast<uint32_t*>(sm_raw);           // [sort_n]
+    int* sidx = reinterpret_cast<int*>(skey + sort_n);              // [sort_n]
+    float* cache = reinterpret_cast<float*>(sidx + sort_n);         // [cache_cap]
+    __shared__ int hist[256];
+    __shared__ int wsum[2][NT / 32];
+    __shared__ uint32_t s_prefix;
+    __shared__ int s_krem;
+    const int q = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const float* src = cand + (cand_off ? cand_off[q] : (long long)q * fixed_stride);
+    const int n = counts ? (int)counts[q] : fixed_count;
+
+    if (n <= cache_cap) {
+        for (int i = tid; i < n; i += NT) cache[i] = src[i];
+        __syncthreads();
+        src = cache;
+    }
+    for (int i = tid; i < sort_n; i += NT) { skey[i] = 0u; sidx[i] = 0x7fffffff; }
+
+    uint32_t T = 0u;
+    int n_gt = 0, k_eq = 0;
+    if (n <= k) {
+        T = 0u; n_gt = 0; k_eq = n;     // take everything (all keys >= 0)
+        __syncthreads();
+    } else {
+        uint32_t prefix = 0u, mask = 0u;
+        int krem = k;
+        for (int shift = 24; shift >= 0; shift -= 8) {
+            hist[tid] = 0;
+            __syncthreads();
+            for (int i = tid; i < n; i += NT) {
+                const uint32_t key = f2key(src[i]);
+                if ((key & mask) == prefix) atomicAdd(&hist[(key >> shift) & 255u], 1);
+            }
+            __syncthreads();
+            if (tid == 0) {
+                int cum = 0, d = 255;
+                for (; d > 0; --d) { if (cum + hist[d] >= krem) break; cum += hist[d]; }
+                s_prefix = prefix | ((uint32_t)d << shift);
+                s_krem = krem - cum;
+            }
+            __syncthreads();
+            prefix = s_prefix; krem = s_krem; mask |= 255u << shift;
+            __syncthreads();
+        }
+        T = prefix; k_eq = krem; n_gt = k - krem;
+    }
+
+    // ordered compaction: keys > T go to [0, n_gt) (any order is fine, they are sorted below — but we
+    // keep position order anyway), keys == T take the first k_eq positions → [n_gt, n_gt + k_eq)
+    int run_gt = 0, run_eq = 0;
+    for (int base = 0; base < n; base += NT) {
+        const int i = base + tid;
+        uint32_t key = 0u; bool gt = false, eq = false;
+        if (i < n) {
+            key = f2key(src[i]);
+            if (n <= k) eq = true; else { gt = key > T; eq = key == T; }
+        }
+        const uint32_t bg = __ballot_sync(RB_FULL_MASK, gt), be = __ballot_sync(RB_FULL_MASK, eq);
+        if (lane == 0) { wsum[0][warp] = __popc(bg); wsum[1][warp] = __popc(be); }
+        __syncthreads();
+        int og = run_gt, oe = run_eq, tg = 0, te = 0;
+        for (int w = 0; w < NT / 32; ++w) {
+            if (w < warp) { og += wsum[0][w]; oe += wsum[1][w]; }
+            tg += wsum[0][w]; te += wsum[1][w];
+        }
+        const uint32_t lt = (1u << lane) - 1u;
+        if (gt) { const int p = og + __popc(bg & lt); skey[p] = key; sidx[p] = i; }
+        if (eq) { const int e = oe + __popc(be & lt); if (e < k_eq) { skey[n_gt + e] = key; sidx[n_gt + e] = i; } }
+        run_gt += tg; run_eq += te;
+        __syncthreads();
+    }
+
+    // bitonic sort, descending by (key, then ascending idx)
+    for (int size = 2; size <= sort_n; size <<= 1) {
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+            __syncthreads();
+            for (int t = tid; t < sort_n / 2; t += NT) {
+                const int lo = (t / stride) * (stride << 1) + (t % stride), hi = lo + stride;
+                const bool desc = ((lo & size) == 0);
+                const uint32_t ka = skey[lo], kb = skey[hi];
+                const int ia = sidx[lo], ib = sidx[hi];
+                const bool a_first = ka > kb || (ka == kb && ia < ib);    // a ranks before b
+                if (a_first != desc) { skey[lo] = kb; skey[hi] = ka; sidx[lo] = ib; sidx[hi] = ia; }
+            }
+        }
+    }
+    __syncthreads();
+    const int n_out = n < k ? n : k;
+    for (int j = tid; j < k; j += NT) {
+        if (j < n_out) {
+            out_scores[(long long)q * k + j] = key2f(skey[j]);
+            out_ids[(long long)q * k + j] = resolve_id<R>(res, q, sidx[j]);
+        } else {
+            out_scores[(long long)q * k + j] = -FLT_MAX;
+            out_ids[(long long)q * k + j] = -1;
+        }
+    }
+}
+
+int next_pow2(int v) { int p = 2; while (p < v) p <<= 1; return p; }
+
+template <typename R>
+int launch_select(const float* cand, const long long* cand_off, long long fixed_stride, const long long* counts,
+                  int fixed_count, long long max_count, int nq, int k, const R& res, float* out_scores, int64_t* out_ids,
+                  cudaStream_t st) {
+    const int sort_n = next_pow2(k);
+    int cache_cap = (int)(max_count < 24576 ? max_count : 24576);
+    if (cache_cap < 0) cache_cap = 0;
+    const size_t smem = (size_t)sort_n * 8 + (size_t)cache_cap * 4 + 16;
+    static size_t attr_smem = 0;
+    if (smem > attr_smem) {
+        RB_CUDA(cudaFuncSetAttribute(select_topk_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem > 48 * 1024 ? smem : 48 * 1024)));
+        attr_smem = smem;
+    }
+    select_topk_kernel<R><<<nq, NT, smem, st>>>(cand, cand_off, fixed_stride, counts, fixed_count, k, sort_n, cache_cap, res,
+                                                out_scores, out_ids);
+    RB_LAUNCH_CHECK("select_topk_kernel");
+    return RB200_OK;
+}
+
+// k-way merge of `parts` sorted lists per query: treat the concatenation as candidates
+struct ResolveMerge { const int64_t* ids; int parts; int nq; int k; };
+template <> __device__ long long resolve_id<ResolveMerge>(const ResolveMerge& r, int q, int c) {
+    const int part = c / r.k, j = c - part * r.k;
+    return r.ids[((long long)part * r.nq + q) * r.k + j];
+}
+__global__ void __launch_bounds__(NT) merge_gather_kernel(const float* __restrict__ scores, int parts, int nq, int k,
+                                                          float* __restrict__ cand) {
+    const long long i = (long long)blockIdx.x * NT + threadIdx.x;
+    const long long total = (long long)nq * parts * k;
+    if (i >= total) return;
+    const int q = (int)(i / ((long long)parts * k));
+    const int rem = (int)(i - (long long)q * parts * k);
+    const int part = rem / k, j = rem - part * k;
+    cand[i] = scores[((long long)part * nq + q) * k + j];
+}
+
+struct PlanLayout {
+    float* coarse; int* probes; int* cand_base; long long* totals; long long* cand_off; long long* tot2;
+    int* list_qcount; int* list_qstart; int* pair_keys; int* pair_vals; int* pair_keys_sorted; int* pair_qp;
+    char* temp; size_t temp_bytes;
+};
+size_t plan_temp_bytes(int nq, int nlist, int nprobe) {
+    size_t a = 0, b = 0, c = 0;
+    const long long np = (long long)nq * nprobe;
+    cub::DeviceRadixSort::SortPairs(nullptr, a, (const int*)nullptr, (int*)nullptr, (const int*)nullptr, (int*)nullptr, (int)np);
+    cub::DeviceScan::ExclusiveSum(nullptr, b, (const int*)nullptr, (int*)nullptr, nlist + 1);
+    cub::DeviceScan::ExclusiveSum(nullptr, c, (const long long*)nullptr, (long long*)nullptr, nq + 1);
+    size_t m = a > b ? a : b;
+    return m > c ? m : c;
+}
+bool carve_plan(RbArena& ar, int nq, int nlist, int nprobe, PlanLayout& L) {
+    const size_t np = (size_t)nq * nprobe;
+    L.coarse = ar.take<float>((size_t)nq * nlist);
+    L.probes = ar.take<int>(np); L.cand_base = ar.take<int>(np);
+    L.totals = ar.take<long long>((size_t)nq + 1); L.cand_off = ar.take<long long>((size_t)nq + 1);
+    L.tot2 = ar.take<long long>(2);
+    L.list_qcount = ar.take<int>((size_t)nlist + 2); L.list_qstart = ar.take<int>((size_t)nlist + 2);
+    L.pair_keys = ar.take<int>(np); L.pair_vals = ar.take<int>(np);
+    L.pair_keys_sorted = ar.take<int>(np); L.pair_qp = ar.take<int>(np);
+    L.temp_bytes = plan_temp_bytes(nq, nlist, nprobe);
+    L.temp = ar.take<char>(L.temp_bytes);
+    return ar.ok();
+}
+
+#define RB_DISPATCH_D(D, CALL)                                            \
+    switch (D) {                                                          \
+        case 32: { constexpr int DD = 32; CALL; } break;                  \
+        case 64: { constexpr int DD = 64; CALL; } break;                  \
+        case 128: { constexpr int DD = 128; CALL; } break;                \
+        default: return rb_set_error(RB200_ERR_INVALID, "unsupported D=%d (32, 64 or 128)", D); \
+    }
+
+}  // namespace
+
+extern "C" int rb200_normalize_rows(const float* x, int64_t n, int D, float eps, float* out, void* stream) {
+    RB_REQUIRE(x && out && n >= 0 && D >= 1, "normalize_rows: bad arguments");
+    if (n == 0) return RB200_OK;
+    normalize_rows_kernel<<<(unsigned)((n * 32 + NT - 1) / NT), NT, 0, (cudaStream_t)stream>>>(x, n, D, eps, out);
+    RB_LAUNCH_CHECK("normalize_rows_kernel");
+    return RB200_OK;
+}
+
+extern "C" int rb200_ivf_assign(const float* x, int64_t n, int D, const float* centroids, int nlist, int32_t* assign_out,
+                                float* best_score, void* stream) {
+    RB_REQUIRE(x && centroids && assign_out && n >= 0 && nlist >= 1, "ivf_assign: bad arguments");
+    if (n == 0) return RB200_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    RB_DISPATCH_D(D, RB_TILE_LAUNCH(assign_kernel, DD, (unsigned)((n + TT - 1) / TT), st, x, n, centroids, nlist, assign_out, best_score));
+    RB_LAUNCH_CHECK("assign_kernel");
+    return RB200_OK;
+}
+
+extern "C" size_t rb200_kmeans_update_workspace_bytes(int64_t n, int nlist) { return sort_ws_bytes(n, nlist); }
+
+extern "C" int rb200_kmeans_update(const float* x, int64_t n, int D, const int32_t* assign, int nlist, float* centroids,
+                                   int32_t* counts, void* workspace, size_t workspace_bytes, void* stream) {
+    RB_REQUIRE(x && assign && centroids && n >= 1 && nlist >= 1 && n < (1ll << 31), "kmeans_update: bad arguments");
+    cudaStream_t st = (cudaStream_t)stream;
+    RbArena ar(workspace, workspace_bytes);
+    SortWs w;
+    if (!workspace || !carve_sort_ws(ar, n, nlist, w)) return rb_set_error(RB200_ERR_WORKSPACE, "kmeans_update: workspace too small");
+    int rc = sort_rows_by_list(assign, n, nlist, w, st);
+    if (rc) return rc;
+    centroid_update_kernel<<<(nlist * 32 + NT - 1) / NT, NT, 0, st>>>(x, w.order, w.excl, w.counts, nlist, D, centroids);
+    RB_LAUNCH_CHECK("centroid_update_kernel");
+    if (counts) RB_CUDA(cudaMemcpyAsync(counts, w.counts, sizeof(int) * nlist, cudaMemcpyDeviceToDevice, st));
+    return RB200_OK;
+}
+
+extern "C" size_t rb200_ivf_build_workspace_bytes(int64_t n, int nlist) { return sort_ws_bytes(n, nlist); }
+
+extern "C" int rb200_ivf_build(const float* x, int64_t n, int D, const int32_t* assign, int nlist, int64_t* offsets,
+                               int64_t* list_ids, float* list_vecs, void* workspace, size_t workspace_bytes, void* stream) {
+    RB_REQUIRE(x && assign && offsets && list_ids && list_vecs && n >= 1 && nlist >= 1 && n < (1ll << 31) && D % 4 == 0,
+               "ivf_build: bad arguments");
+    cudaStream_t st = (cudaStream_t)stream;
+    RbArena ar(workspace, workspace_bytes);
+    SortWs w;
+    if (!workspace || !carve_sort_ws(ar, n, nlist, w)) return rb_set_error(RB200_ERR_WORKSPACE, "ivf_build: workspace too small");
+    int rc = sort_rows_by_list(assign, n, nlist, w, st);
+    if (rc) return rc;
+    offsets_to_i64_kernel<<<(nlist + NT - 1) / NT, NT, 0, st>>>(w.excl, w.counts, nlist, offsets);
+    RB_LAUNCH_CHECK("offsets_to_i64_kernel");
+    gather_rows_kernel<<<(unsigned)((n * 32 + NT - 1) / NT), NT, 0, st>>>(x, w.order, n, D, list_ids, list_vecs);
+    RB_LAUNCH_CHECK("gather_rows_kernel");
+    return RB200_OK;
+}
+
+extern "C" size_t rb200_ivf_plan_workspace_bytes(int nq, int nlist, int nprobe) {
+    const size_t np = (size_t)nq * nprobe;
+    return 256 * 16 + sizeof(float) * (size_t)nq * nlist + sizeof(int) * (6 * np + 2 * ((size_t)nlist + 2)) +
+           sizeof(long long) * (2 * ((size_t)nq + 1) + 2) + plan_temp_bytes(nq, nlist, nprobe);
+}
+
+extern "C" int rb200_ivf_search_plan(const float* q, int nq, int D, const float* centroids, int nlist, int nprobe,
+                                     const int64_t* offsets, void* plan_ws, size_t plan_ws_bytes,
+                                     int64_t* total_candidates_host, int64_t* max_candidates_host, void* stream) {
+    RB_REQUIRE(q && centroids && offsets && nq >= 1 && nlist >= 1 && nprobe >= 1 && nprobe <= nlist, "ivf_search_plan: bad arguments");
+    RB_REQUIRE(total_candidates_host && max_candidates_host, "ivf_search_plan: NULL host outputs");
+    RB_REQUIRE((size_t)nlist * 4 <= 200 * 1024, "ivf_search_plan: nlist=%d too large for the probe-select kernel", nlist);
+    cudaStream_t st = (cudaStream_t)stream;
+    RbArena ar(plan_ws, plan_ws_bytes);
+    PlanLayout L;
+    if (!plan_ws || !carve_plan(ar, nq, nlist, nprobe, L)) return rb_set_error(RB200_ERR_WORKSPACE, "ivf_search_plan: workspace too small");
+    const dim3 g((nlist + TT - 1) / TT, (nq + TT - 1) / TT);
+    RB_DISPATCH_D(D, RB_TILE_LAUNCH(dense_scores_kernel, DD, g, st, q, nq, centroids, nlist, L.coarse, nlist, 0));
+    RB_LAUNCH_CHECK("dense_scores_kernel");
+    RB_CUDA(cudaMemsetAsync(L.list_qcount, 0, sizeof(int) * ((size_t)nlist + 2), st));
+    const size_t ps_smem = sizeof(float) * (size_t)nlist;
+    static size_t ps_attr = 0;
+    if (ps_smem > 48 * 1024 && ps_smem > ps_attr) {
+        RB_CUDA(cudaFuncSetAttribute(probe_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ps_smem));
+        ps_attr = ps_smem;
+    }
+    probe_select_kernel<<<nq, NT, ps_smem, st>>>(L.coarse, nlist, nprobe, offsets, L.probes, L.cand_base, L.totals, L.list_qcount);
+    RB_LAUNCH_CHECK("probe_select_kernel");
+    const long long np = (long long)nq * nprobe;
+    pair_keys_kernel<<<(unsigned)((np + NT - 1) / NT), NT, 0, st>>>(L.probes, np, nlist, L.pair_keys, L.pair_vals);
+    RB_LAUNCH_CHECK("pair_keys_kernel");
+    size_t tb = L.temp_bytes;
+    RB_CUDA(cub::DeviceRadixSort::SortPairs(L.temp, tb, (const int*)L.pair_keys, L.pair_keys_sorted, (const int*)L.pair_vals,
+                                            L.pair_qp, (int)np, 0, key_bits_i32(nlist + 1), st));
+    tb = L.temp_bytes;
+    RB_CUDA(cub::DeviceScan::ExclusiveSum(L.temp, tb, (const int*)L.list_qcount, L.list_qstart, nlist + 1, st));
+    RB_CUDA(cudaMemsetAsync(L.totals + nq, 0, sizeof(long long), st));
+    tb = L.temp_bytes;
+    RB_CUDA(cub::DeviceScan::ExclusiveSum(L.temp, tb, (const long long*)L.totals, L.cand_off, nq + 1, st));
+    reduce_totals_kernel<<<1, 32, 0, st>>>(L.totals, nq, L.tot2);
+    RB_LAUNCH_CHECK("reduce_totals_kernel");
+    long long h[2] = {0, 0};
+    RB_CUDA(cudaMemcpyAsync(h, L.tot2, sizeof(h), cudaMemcpyDeviceToHost, st));
+    RB_CUDA(cudaStreamSynchronize(st));
+    *total_candidates_host = h[0];
+    *max_candidates_host = h[1];
+    return RB200_OK;
+}
+
+extern "C" size_t rb200_ivf_search_workspace_bytes(int64_t total_candidates) {
+    return 256 + sizeof(float) * (size_t)(total_candidates > 0 ? total_candidates : 1);
+}
+
+extern "C" int rb200_ivf_search_run(const float* q, int nq, int D, int nlist, int nprobe, const int64_t* offsets,
+                                    const int64_t* list_ids, const float* list_vecs, int64_t max_list_len, int k,
+                                    void* plan_ws, size_t plan_ws_bytes, int64_t total_candidates, int64_t max_candidates,
+                                    float* out_scores, int64_t* out_ids, void* workspace, size_t workspace_bytes,
+                                    void* stream) {
+    RB_REQUIRE(q && offsets && list_ids && list_vecs && out_scores && out_ids, "ivf_search_run: NULL pointer");
+    RB_REQUIRE(nq >= 1 && k >= 1 && k <= 2048 && nprobe >= 1 && max_list_len >= 0, "ivf_search_run: bad sizes (k must be 1..2048)");
+    cudaStream_t st = (cudaStream_t)stream;
+    RbArena pa(plan_ws, plan_ws_bytes);
+    PlanLayout L;
+    if (!plan_ws || !carve_plan(pa, nq, nlist, nprobe, L)) return rb_set_error(RB200_ERR_WORKSPACE, "ivf_search_run: plan workspace too small");
+    RbArena ar(workspace, workspace_bytes);
+    float* cand = ar.take<float>((size_t)(total_candidates > 0 ? total_candidates : 1));
+    if (!workspace || !ar.ok()) return rb_set_error(RB200_ERR_WORKSPACE, "ivf_search_run: workspace too small");
+    if (total_candidates > 0 && max_list_len > 0) {
+        const dim3 g((unsigned)((max_list_len + TT - 1) / TT), nlist);
+        RB_REQUIRE(nlist <= 65535, "ivf_search_run: nlist must be <= 65535");
+        RB_DISPATCH_D(D, RB_TILE_LAUNCH(list_scan_kernel, DD, g, st, q, list_vecs, offsets, L.pair_qp, L.list_qstart, nprobe,
+                                        L.cand_base, L.cand_off, cand));
+        RB_LAUNCH_CHECK("list_scan_kernel");
+    }
+    ResolveIvf res{L.probes, L.cand_base, offsets, list_ids, nprobe};
+    return launch_select<ResolveIvf>(cand, L.cand_off, 0, L.totals, 0, max_candidates, nq, k, res, out_scores, out_ids, st);
+}
+
+// ------------------------------------------------------------------------------------------ //
+// flat (exhaustive) search: chunks of rows, running top-k carried as the first k candidates
+// ------------------------------------------------------------------------------------------ //
+static long long flat_chunk_rows(int nq, int64_t n) {
+    long long c = (256ll << 20) / ((long long)nq * 4);        // ~256 MB of chunk scores
+    c = c / TT * TT;
+    if (c < 4096) c = 4096;
+    if (c > 1 << 20) c = 1 << 20;
+    if (c > n) c = (n + TT - 1) / TT * TT;
+    return c;
+}
+
+extern "C" size_t rb200_flat_search_workspace_bytes(int nq, int64_t n, int k) {
+    const long long chunk = flat_chunk_rows(nq, n);
+    return 256 * 4 + sizeof(float) * (size_t)nq * (size_t)(chunk + k) + (sizeof(float) + sizeof(int64_t)) * (size_t)nq * k;
+}
+
+__global__ void copy_prev_kernel(const float* __restrict__ prev_scores, int nq, int k, float* __restrict__ cand, long long stride) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (long long)nq * k) return;
+    const int q = (int)(i / k), j = (int)(i - (long long)q * k);
+    cand[q * stride + j] = prev_scores[i];
+}
+
+extern "C" int rb200_flat_search(const float* q, int nq, const float* x, int64_t n, int D, int k, int64_t id_base,
+                                 float* out_scores, int64_t* out_ids, void* workspace, size_t workspace_bytes, void* stream) {
+    RB_REQUIRE(q && x && out_scores && out_ids && nq >= 1 && n >= 1 && k >= 1 && k <= 2048, "flat_search: bad arguments (k must be 1..2048)");
+    cudaStream_t st = (cudaStream_t)stream;
+    const long long chunk = flat_chunk_rows(nq, n);
+    const long long stride = chunk + k;
+    RbArena ar(workspace, workspace_bytes);
+    float* cand = ar.take<float>((size_t)nq * stride);
+    float* tmp_scores = ar.take<float>((size_t)nq * k);
+    int64_t* tmp_ids = ar.take<int64_t>((size_t)nq * k);
+    if (!workspace || !ar.ok()) return rb_set_error(RB200_ERR_WORKSPACE, "flat_search: workspace too small");
+    const long long n_chunks = (n + chunk - 1) / chunk;
+    // ping-pong between (out) and (tmp) so that the last chunk lands in out_*
+    float* cur_s = (n_chunks % 2) ? out_scores : tmp_scores;
+    int64_t* cur_i = (n_chunks % 2) ? out_ids : tmp_ids;
+    float* prev_s = nullptr; int64_t* prev_i = nullptr;
+    for (long long ci = 0; ci < n_chunks; ++ci) {
+        const long long r0 = ci * chunk, rows = (n - r0 < chunk) ? n - r0 : chunk;
+        const int kprev = ci == 0 ? 0 : k;
+        if (kprev) {
+            copy_prev_kernel<<<(unsigned)(((long long)nq * k + NT - 1) / NT), NT, 0, st>>>(prev_s, nq, k, cand, stride);
+            RB_LAUNCH_CHECK("copy_prev_kernel");
+        }
+        const dim3 g((unsigned)((rows + TT - 1) / TT), (nq + TT - 1) / TT);
+        RB_DISPATCH_D(D, RB_TILE_LAUNCH(dense_scores_kernel, DD, g, st, q, nq, x + r0 * D, rows, cand, stride, kprev));
+        RB_LAUNCH_CHECK("dense_scores_kernel");
+        ResolveFlat res{prev_i, kprev, id_base + r0};
+        // previous winners may contain -FLT_MAX padding (when fewer than k rows so far): they carry id -1
+        int rc = launch_select<ResolveFlat>(cand, nullptr, stride, nullptr, (int)(rows + kprev), rows + kprev, nq, k, res, cur_s, cur_i, st);
+        if (rc) return rc;
+        prev_s = cur_s; prev_i = cur_i;
+        cur_s = (cur_s == out_scores) ? tmp_scores : out_scores;
+        cur_i = (cur_i == out_ids) ? tmp_ids : out_ids;
+    }
+    return RB200_OK;
+}
+
+extern "C" size_t rb200_topk_merge_workspace_bytes(int parts, int nq, int k) {
+    return 256 + sizeof(float) * (size_t)parts * nq * k;
+}
+
+extern "C" int rb200_topk_merge(const float* scores, const int64_t* ids, int parts, int nq, int k, float* out_scores,
+                                int64_t* out_ids, void* workspace, size_t workspace_bytes, void* stream) {
+    RB_REQUIRE(scores && ids && out_scores && out_ids && parts >= 1 && nq >= 1 && k >= 1 && k <= 2048, "topk_merge: bad arguments");
+    cudaStream_t st = (cudaStream_t)stream;
+    RbArena ar(workspace, workspace_bytes);
+    float* cand = ar.take<float>((size_t)parts * nq * k);
+    if (!workspace || !ar.ok()) return rb_set_error(RB200_ERR_WORKSPACE, "topk_merge: workspace too small");
+    const long long total = (long long)parts * nq * k;
+    merge_gather_kernel<<<(unsigned)((total + NT - 1) / NT), NT, 0, st>>>(scores, parts, nq, k, cand);
+    RB_LAUNCH_CHECK("merge_gather_kernel");
+    ResolveMerge res{ids, parts, nq, k};
+    return launch_select<ResolveMerge>(cand, nullptr, (long long)parts * k, nullptr, parts * k, (long long)parts * k, nq, k, res,
+                                       out_scores, out_ids, st);
+}

@@ -1,0 +1,192 @@
+// One-call fused training step (src/training/train_embeddings.py:183-192 of the reference).
+// Pure orchestration: carves the workspace and enqueues the kernels of tower.cu / loss.cu /
+// scatter_adam.cu on one stream.  No synchronisation, no allocation → CUDA-graph capturable.
+#include "common.cuh"
+
+namespace {
+
+struct StepWs {
+    float *u, *p, *n;              // tower outputs [B,D] each (p,n contiguous)
+    float *hid_u, *hid_pn;         // [B,H], [2B,H]
+    float *den_u, *den_pn;         // [B], [2B]
+    float *du, *dpn;               // loss gradients [B,D], [2B,D]
+    float *dpre_u, *dpre_pn, *dact_u, *dact_pn, *drows_u, *drows_pn;
+    int64_t* ids_pn;               // [2B]
+    float *g_user_mlp, *g_item_mlp;   // contiguous
+    int64_t *uniq_u, *uniq_i; float *ug_u, *ug_i; int *n_uniq;   // n_uniq[0]=user, [1]=item
+    void *ws_bwd, *ws_loss, *ws_scatter, *ws_sumsq;
+    size_t b_bwd, b_loss, b_scatter, b_sumsq;
+    int P_user, P_item;
+};
+
+bool carve(RbArena& ar, const rb200_step_params& s, StepWs& w) {
+    const size_t B = s.B, D = s.D, H = s.H;
+    const int items = s.loss_kind == 0 ? 2 : 1;
+    w.u = ar.take<float>(B * D);
+    w.p = ar.take<float>(items * B * D); w.n = w.p + B * D;
+    w.hid_u = ar.take<float>(B * H); w.hid_pn = ar.take<float>(items * B * H);
+    w.den_u = ar.take<float>(B); w.den_pn = ar.take<float>(items * B);
+    w.du = ar.take<float>(B * D); w.dpn = ar.take<float>(items * B * D);
+    w.dpre_u = ar.take<float>(B * D); w.dpre_pn = ar.take<float>(items * B * D);
+    w.dact_u = ar.take<float>(B * H); w.dact_pn = ar.take<float>(items * B * H);
+    w.drows_u = ar.take<float>(B * D); w.drows_pn = ar.take<float>(items * B * D);
+    w.ids_pn = ar.take<int64_t>(items * B);
+    w.P_user = s.H * s.D + s.H + s.D * s.H + s.D;
+    w.P_item = s.H * (s.D + s.extra_dim) + s.H + s.D * s.H + s.D;
+    w.g_user_mlp = ar.take<float>((size_t)w.P_user + w.P_item);
+    w.g_item_mlp = w.g_user_mlp + w.P_user;
+    w.uniq_u = ar.take<int64_t>(B); w.uniq_i = ar.take<int64_t>(items * B);
+    w.ug_u = ar.take<float>(B * D); w.ug_i = ar.take<float>(items * B * D);
+    w.n_uniq = ar.take<int>(2);
+    w.b_bwd = rb200_tower_bwd_workspace_bytes(s.D, s.H, s.extra_dim);
+    w.ws_bwd = ar.take<char>(w.b_bwd);
+    const size_t l0 = rb200_bpr_pair_workspace_bytes(s.B), l1 = s.loss_kind == 1 ? rb200_bpr_inbatch_workspace_bytes(s.B, s.D) : 0;
+    w.b_loss = l0 > l1 ? l0 : l1;
+    w.ws_loss = ar.take<char>(w.b_loss);
+    const size_t s0 = rb200_scatter_workspace_bytes(s.B, s.n_user_rows), s1 = rb200_scatter_workspace_bytes(items * s.B, s.n_item_rows);
+    w.b_scatter = s0 > s1 ? s0 : s1;
+    w.ws_scatter = ar.take<char>(w.b_scatter);
+    w.b_sumsq = rb200_sumsq_workspace_bytes();
+    w.ws_sumsq = ar.take<char>(w.b_sumsq);
+    return ar.ok();
+}
+
+__global__ void copy_loss_kernel(const float* loss, rb200_opt_state* st) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) st->loss = loss[0];
+}
+
+int check(const rb200_step_params* s) {
+    RB_REQUIRE(s, "bpr_step: NULL params");
+    RB_REQUIRE(s->B >= 1 && s->extra_dim >= 0, "bpr_step: bad B/extra_dim");
+    RB_REQUIRE(s->user_table && s->user_table_m && s->user_table_v && s->item_table && s->item_table_m && s->item_table_v,
+               "bpr_step: NULL table pointer");
+    RB_REQUIRE(s->user_mlp && s->user_mlp_m && s->user_mlp_v && s->item_mlp && s->item_mlp_m && s->item_mlp_v,
+               "bpr_step: NULL MLP pointer");
+    RB_REQUIRE(s->opt && s->loss && s->user_ids && s->pos_ids, "bpr_step: NULL opt/loss/ids");
+    RB_REQUIRE(s->loss_kind == 1 || s->neg_ids, "bpr_step: neg_ids required for the pairwise loss");
+    RB_REQUIRE(s->extra_dim == 0 || (s->pos_extra && (s->loss_kind == 1 || s->neg_extra)), "bpr_step: NULL extra");
+    RB_REQUIRE(s->adam_mode == 1 || (s->user_row_slot && s->item_row_slot), "bpr_step: dense Adam needs row_slot buffers");
+    RB_REQUIRE(s->workspace, "bpr_step: NULL workspace");
+    return RB200_OK;
+}
+
+}  // namespace
+
+extern "C" size_t rb200_bpr_step_workspace_bytes(int B, int D, int H, int extra_dim, int64_t n_user_rows, int64_t n_item_rows,
+                                                 int loss_kind) {
+    rb200_step_params s{};
+    s.B = B; s.D = D; s.H = H; s.extra_dim = extra_dim; s.n_user_rows = n_user_rows; s.n_item_rows = n_item_rows;
+    s.loss_kind = loss_kind;
+    RbArena ar(nullptr, ~(size_t)0);
+    StepWs w;
+    carve(ar, s, w);
+    return ar.off + 256;
+}
+
+extern "C" int rb200_bpr_step_views(const rb200_step_params* s, rb200_step_views* out) {
+    int rc = check(s);
+    if (rc) return rc;
+    RB_REQUIRE(out, "bpr_step_views: NULL out");
+    RbArena ar(s->workspace, s->workspace_bytes);
+    StepWs w;
+    if (!carve(ar, *s, w)) return rb_set_error(RB200_ERR_WORKSPACE, "bpr_step_views: workspace too small");
+    out->user_mlp_grad = w.g_user_mlp; out->item_mlp_grad = w.g_item_mlp;
+    out->user_uniq_ids = w.uniq_u; out->item_uniq_ids = w.uniq_i;
+    out->user_uniq_grads = w.ug_u; out->item_uniq_grads = w.ug_i;
+    out->user_n_uniq = w.n_uniq; out->item_n_uniq = w.n_uniq + 1;
+    out->user_emb = w.u; out->pos_emb = w.p; out->neg_emb = s->loss_kind == 0 ? w.n : nullptr;
+    return RB200_OK;
+}
+
+extern "C" int rb200_bpr_step(const rb200_step_params* s, void* stream) {
+    int rc = check(s);
+    if (rc) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    RbArena ar(s->workspace, s->workspace_bytes);
+    StepWs w;
+    if (!carve(ar, *s, w)) return rb_set_error(RB200_ERR_WORKSPACE, "bpr_step: workspace too small (%zu given, %zu needed)",
+                                               s->workspace_bytes, ar.off);
+    const int B = s->B, D = s->D, H = s->H, E = s->extra_dim;
+    const bool pair = s->loss_kind == 0;
+    const int items = pair ? 2 : 1;
+    const int Pu = w.P_user, Pi = w.P_item;
+    const int Din_i = D + E;
+
+    if ((rc = rb200_opt_begin_step(s->opt, st))) return rc;
+
+    // ---- forward: user / positive / negative towers in one launch -------------------------- //
+    rb200_tower_job fj[3] = {};
+    fj[0].table = s->user_table; fj[0].ids = s->user_ids; fj[0].extra = nullptr; fj[0].extra_dim = 0;
+    fj[0].W1 = s->user_mlp; fj[0].b1 = s->user_mlp + H * D; fj[0].W2 = s->user_mlp + H * D + H; fj[0].b2 = s->user_mlp + H * D + H + D * H;
+    fj[0].out = w.u; fj[0].hid = w.hid_u; fj[0].denom = w.den_u; fj[0].keep_mask = s->keep_mask_user;
+    fj[0].n_rows = s->n_user_rows; fj[0].B = B;
+    for (int t = 0; t < items; ++t) {
+        rb200_tower_job& j = fj[1 + t];
+        j.table = s->item_table; j.ids = t == 0 ? s->pos_ids : s->neg_ids; j.extra = t == 0 ? s->pos_extra : s->neg_extra;
+        j.extra_dim = E; j.extra_by_id = s->extra_by_id;
+        j.W1 = s->item_mlp; j.b1 = s->item_mlp + H * Din_i; j.W2 = s->item_mlp + H * Din_i + H; j.b2 = s->item_mlp + H * Din_i + H + D * H;
+        j.out = w.p + (size_t)t * B * D; j.hid = w.hid_pn + (size_t)t * B * H; j.denom = w.den_pn + (size_t)t * B;
+        j.keep_mask = t == 0 ? s->keep_mask_pos : s->keep_mask_neg;
+        j.n_rows = s->n_item_rows; j.B = B;
+    }
+    if ((rc = rb200_tower_fwd(fj, 1 + items, D, H, s->dropout_p, s->seed, 0, &s->opt->step, s->err_flag, st))) return rc;
+
+    // ---- loss + gradient w.r.t. the tower outputs ------------------------------------------- //
+    if (pair) rc = rb200_bpr_pair(w.u, w.p, w.n, B, D, s->loss, w.du, w.dpn, w.dpn + (size_t)B * D, 1.f, w.ws_loss, w.b_loss, st);
+    else rc = rb200_bpr_inbatch(w.u, w.p, B, D, s->inbatch_mode, s->loss, w.du, w.dpn, 1.f, w.ws_loss, w.b_loss, st);
+    if (rc) return rc;
+    copy_loss_kernel<<<1, 32, 0, st>>>(s->loss, s->opt);
+    RB_LAUNCH_CHECK("copy_loss_kernel");
+
+    // ---- backward through the towers ----------------------------------------------------------- //
+    rb200_tower_bwd_job bj[2] = {};
+    bj[0].table = s->user_table; bj[0].ids = s->user_ids; bj[0].extra = nullptr; bj[0].n_rows = s->n_user_rows; bj[0].B = B;
+    bj[0].extra_dim = 0; bj[0].W1 = fj[0].W1; bj[0].W2 = fj[0].W2; bj[0].dY = w.du; bj[0].y = w.u; bj[0].denom = w.den_u;
+    bj[0].hid = w.hid_u; bj[0].dpre = w.dpre_u; bj[0].dact = w.dact_u; bj[0].dRows = w.drows_u;
+    if ((rc = rb200_tower_bwd(bj, 1, D, H, s->dropout_p, w.g_user_mlp, 0, w.ws_bwd, w.b_bwd, st))) return rc;
+    for (int t = 0; t < items; ++t) {
+        rb200_tower_bwd_job& j = bj[t];
+        j = rb200_tower_bwd_job{};
+        j.table = s->item_table; j.ids = fj[1 + t].ids; j.extra = fj[1 + t].extra; j.n_rows = s->n_item_rows; j.B = B;
+        j.extra_dim = E; j.extra_by_id = s->extra_by_id; j.W1 = fj[1].W1; j.W2 = fj[1].W2;
+        j.dY = w.dpn + (size_t)t * B * D; j.y = w.p + (size_t)t * B * D; j.denom = w.den_pn + (size_t)t * B;
+        j.hid = w.hid_pn + (size_t)t * B * H; j.dpre = w.dpre_pn + (size_t)t * B * D; j.dact = w.dact_pn + (size_t)t * B * H;
+        j.dRows = w.drows_pn + (size_t)t * B * D;
+    }
+    if ((rc = rb200_tower_bwd(bj, items, D, H, s->dropout_p, w.g_item_mlp, 0, w.ws_bwd, w.b_bwd, st))) return rc;
+
+    // ---- sparse embedding gradients: deterministic sorted-segment sums ---------------------- //
+    const bool dense = s->adam_mode == 0;
+    RB_CUDA(cudaMemcpyAsync(w.ids_pn, s->pos_ids, sizeof(int64_t) * B, cudaMemcpyDeviceToDevice, st));
+    if (pair) RB_CUDA(cudaMemcpyAsync(w.ids_pn + B, s->neg_ids, sizeof(int64_t) * B, cudaMemcpyDeviceToDevice, st));
+    if ((rc = rb200_scatter_rows(s->user_ids, w.drows_u, B, D, s->n_user_rows, s->padding_idx, nullptr, w.uniq_u, w.ug_u,
+                                 w.n_uniq, dense ? s->user_row_slot : nullptr, w.ws_scatter, w.b_scatter, st))) return rc;
+    if ((rc = rb200_scatter_rows(w.ids_pn, w.drows_pn, items * B, D, s->n_item_rows, s->padding_idx, nullptr, w.uniq_i, w.ug_i,
+                                 w.n_uniq + 1, dense ? s->item_row_slot : nullptr, w.ws_scatter, w.b_scatter, st))) return rc;
+
+    // ---- clip_grad_norm_(all parameters, 1.0) ---------------------------------------------------- //
+    rb200_sumsq_seg segs[3] = {
+        {w.g_user_mlp, (int64_t)Pu + Pi, nullptr, 0},
+        {w.ug_u, (int64_t)B * D, w.n_uniq, D},
+        {w.ug_i, (int64_t)items * B * D, w.n_uniq + 1, D},
+    };
+    if ((rc = rb200_sumsq_accumulate(s->opt, segs, 3, w.ws_sumsq, w.b_sumsq, st))) return rc;
+    if ((rc = rb200_grad_norm_clip(s->opt, st))) return rc;
+
+    // ---- Adam ---------------------------------------------------------------------------------- //
+    if ((rc = rb200_adam_dense(s->user_mlp, w.g_user_mlp, s->user_mlp_m, s->user_mlp_v, Pu, s->opt, st))) return rc;
+    if ((rc = rb200_adam_dense(s->item_mlp, w.g_item_mlp, s->item_mlp_m, s->item_mlp_v, Pi, s->opt, st))) return rc;
+    if (dense) {
+        if ((rc = rb200_adam_table_dense(s->user_table, s->user_table_m, s->user_table_v, s->n_user_rows, D, s->user_row_slot,
+                                         w.ug_u, s->opt, st))) return rc;
+        if ((rc = rb200_adam_table_dense(s->item_table, s->item_table_m, s->item_table_v, s->n_item_rows, D, s->item_row_slot,
+                                         w.ug_i, s->opt, st))) return rc;
+        if ((rc = rb200_scatter_reset_slots(w.uniq_u, w.n_uniq, B, s->user_row_slot, st))) return rc;
+        if ((rc = rb200_scatter_reset_slots(w.uniq_i, w.n_uniq + 1, items * B, s->item_row_slot, st))) return rc;
+    } else {
+        if ((rc = rb200_adam_rows(s->user_table, s->user_table_m, s->user_table_v, D, w.uniq_u, w.ug_u, w.n_uniq, B, s->opt, st))) return rc;
+        if ((rc = rb200_adam_rows(s->item_table, s->item_table_m, s->item_table_v, D, w.uniq_i, w.ug_i, w.n_uniq + 1, items * B,
+                                  s->opt, st))) return rc;
+    }
+    return RB200_OK;
+}

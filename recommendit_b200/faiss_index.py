@@ -1,0 +1,312 @@
+"""B200 drop-in for the reference's ``src/models/faiss_index.py`` — no FAISS involved.
+
+``FAISSIndex`` keeps the reference's name and call surface (``build_ivf_index`` / ``search`` /
+``batch_search`` / ``save`` / ``load`` / ``stats`` / ``set_n_probe``; attributes ``index.ntotal``,
+``index.nprobe``, ``item_ids``, ``embed_dim``, ``n_lists``, ``n_probe``) so ``build_index.py:128-138``,
+``serving/recommender.py:155-156,311-313`` and ``run_pipeline.py:146-178`` use it unchanged.  What FAISS's
+``IndexIVFFlat(IndexFlatIP, METRIC_INNER_PRODUCT)`` did on the CPU is done by ``librb200.so``:
+
+=============================  ==========================================================
+reference call                 replaced by
+=============================  ==========================================================
+``index.train`` (:73)          spherical k-means: ``rb200_ivf_assign`` + ``rb200_kmeans_update``
+``index.add`` (:74)            ``rb200_ivf_assign`` + ``rb200_ivf_build`` (CSR inverted lists in HBM)
+``index.search`` (:113,:145)   ``rb200_ivf_search_plan`` + ``rb200_ivf_search_run``
+numpy renormalisation          ``rb200_normalize_rows``
+=============================  ==========================================================
+
+The database, the centroids and the inverted lists stay resident in HBM; queries come in and results
+go out as host NumPy arrays exactly as in the reference.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import logging
+import pickle
+from pathlib import Path
+from typing import Dict, List, Optional, Tuple
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import RB200Error, check, ptr, stream_ptr, workspace
+
+logger = logging.getLogger(__name__)
+
+KMEANS_ITERS = 10          # faiss::ClusteringParameters default niter for the IVF coarse quantizer
+KMEANS_SEED = 1234         # faiss default seed
+MAX_POINTS_PER_CENTROID = 256
+_MAGIC = b"RB200IVF1"
+
+
+def _device() -> torch.device:
+    if not torch.cuda.is_available():
+        raise RB200Error("FAISSIndex (recommendit_b200) needs a CUDA device: the IVF kernels are sm_100a only, "
+                         "there is no CPU fallback.")
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+class _IVFState:
+    """What ``FAISSIndex.index`` points at: device-resident IVFFlat state with the two attributes the
+    reference touches on a faiss index (``ntotal``, ``nprobe``)."""
+
+    def __init__(self, d: int, nlist: int, nprobe: int):
+        self.d = d
+        self.nlist = nlist
+        self.nprobe = nprobe
+        self.ntotal = 0
+        self.centroids: Optional[torch.Tensor] = None   # [nlist, d] f32
+        self.offsets: Optional[torch.Tensor] = None     # [nlist+1] i64
+        self.list_ids: Optional[torch.Tensor] = None    # [ntotal] i64 internal row numbers, list-contiguous
+        self.list_vecs: Optional[torch.Tensor] = None   # [ntotal, d] f32, list-contiguous
+        self.max_list_len = 0
+        self.is_trained = False
+
+    # ---- kernels -------------------------------------------------------------------------- #
+    def assign(self, x: torch.Tensor) -> torch.Tensor:
+        lib = _lib.load()
+        out = torch.empty(x.shape[0], dtype=torch.int32, device=x.device)
+        check(lib.rb200_ivf_assign(ptr(x), x.shape[0], self.d, ptr(self.centroids), self.nlist, ptr(out), None,
+                                   stream_ptr()), "rb200_ivf_assign")
+        return out
+
+    def train(self, x: torch.Tensor, niter: int = KMEANS_ITERS, seed: int = KMEANS_SEED) -> None:
+        """Spherical k-means (metric = inner product ⇒ centroids renormalised every iteration)."""
+        lib = _lib.load()
+        n = x.shape[0]
+        if n > MAX_POINTS_PER_CENTROID * self.nlist:     # FAISS sub-samples large training sets
+            sel = np.random.default_rng(seed + 1).permutation(n)[: MAX_POINTS_PER_CENTROID * self.nlist]
+            x = x[torch.as_tensor(sel, device=x.device)].contiguous()
+            n = x.shape[0]
+        init = np.random.default_rng(seed).permutation(n)[: self.nlist]
+        if len(init) < self.nlist:                       # fewer points than lists: repeat (degenerate case)
+            init = np.resize(init, self.nlist)
+        self.centroids = x[torch.as_tensor(init, device=x.device)].contiguous().clone()
+        counts = torch.empty(self.nlist, dtype=torch.int32, device=x.device)
+        wsb = lib.rb200_kmeans_update_workspace_bytes(n, self.nlist)
+        ws = workspace(wsb, x.device)
+        rng = np.random.default_rng(seed + 7)
+        for _ in range(niter):
+            a = self.assign(x)
+            check(lib.rb200_kmeans_update(ptr(x), n, self.d, ptr(a), self.nlist, ptr(self.centroids), ptr(counts),
+                                          ptr(ws), wsb, stream_ptr()), "rb200_kmeans_update")
+            cnt = counts.cpu().numpy().astype(np.float64)
+            empty = np.nonzero(cnt == 0)[0]
+            if len(empty):                               # FAISS split_clusters: clone a big list, perturb ±1/1024
+                cen = self.centroids.cpu().numpy()
+                sign = np.where(np.arange(self.d) % 2 == 0, 1.0, -1.0).astype(np.float32)
+                for ci in empty:
+                    p = np.maximum(cnt - 1, 0)
+                    if p.sum() <= 0:
+                        break
+                    cj = int(rng.choice(self.nlist, p=p / p.sum()))
+                    cen[ci] = cen[cj] * (1 + sign / 1024)
+                    cen[cj] = cen[cj] * (1 - sign / 1024)
+                    cnt[ci] = cnt[cj] / 2
+                    cnt[cj] -= cnt[ci]
+                self.centroids = torch.as_tensor(cen, device=x.device)
+                check(lib.rb200_normalize_rows(ptr(self.centroids), self.nlist, self.d, 1e-30, ptr(self.centroids),
+                                               stream_ptr()), "rb200_normalize_rows")
+        self.is_trained = True
+
+    def add(self, x: torch.Tensor) -> None:
+        lib = _lib.load()
+        n = x.shape[0]
+        a = self.assign(x)
+        self.offsets = torch.empty(self.nlist + 1, dtype=torch.int64, device=x.device)
+        self.list_ids = torch.empty(n, dtype=torch.int64, device=x.device)
+        self.list_vecs = torch.empty(n, self.d, dtype=torch.float32, device=x.device)
+        wsb = lib.rb200_ivf_build_workspace_bytes(n, self.nlist)
+        ws = workspace(wsb, x.device)
+        check(lib.rb200_ivf_build(ptr(x), n, self.d, ptr(a), self.nlist, ptr(self.offsets), ptr(self.list_ids),
+                                  ptr(self.list_vecs), ptr(ws), wsb, stream_ptr()), "rb200_ivf_build")
+        self.ntotal = n
+        self.max_list_len = int((self.offsets[1:] - self.offsets[:-1]).max().item())
+
+    def search_device(self, q: torch.Tensor, k: int) -> Tuple[torch.Tensor, torch.Tensor]:
+        """q: normalised [nq, d] f32 on the device → (scores [nq,k] f32, rows [nq,k] i64), -FLT_MAX / -1 padded."""
+        lib = _lib.load()
+        nq = q.shape[0]
+        nprobe = max(1, min(int(self.nprobe), self.nlist))
+        pb = lib.rb200_ivf_plan_workspace_bytes(nq, self.nlist, nprobe)
+        plan = workspace(pb, q.device)
+        total, mx = C.c_int64(0), C.c_int64(0)
+        check(lib.rb200_ivf_search_plan(ptr(q), nq, self.d, ptr(self.centroids), self.nlist, nprobe, ptr(self.offsets),
+                                        ptr(plan), pb, C.byref(total), C.byref(mx), stream_ptr()), "rb200_ivf_search_plan")
+        wb = lib.rb200_ivf_search_workspace_bytes(total.value)
+        ws = workspace(wb, q.device)
+        scores = torch.empty(nq, k, dtype=torch.float32, device=q.device)
+        rows = torch.empty(nq, k, dtype=torch.int64, device=q.device)
+        check(lib.rb200_ivf_search_run(ptr(q), nq, self.d, self.nlist, nprobe, ptr(self.offsets), ptr(self.list_ids),
+                                       ptr(self.list_vecs), self.max_list_len, k, ptr(plan), pb, total.value, mx.value,
+                                       ptr(scores), ptr(rows), ptr(ws), wb, stream_ptr()), "rb200_ivf_search_run")
+        return scores, rows
+
+    def search(self, queries: np.ndarray, k: int) -> Tuple[np.ndarray, np.ndarray]:
+        """faiss-style ``index.search(x, k)`` on host arrays (already normalised)."""
+        q = torch.as_tensor(np.ascontiguousarray(queries, dtype=np.float32), device=self.centroids.device)
+        s, r = self.search_device(q, k)
+        return s.cpu().numpy(), r.cpu().numpy()
+
+
+def _normalize_device(x: torch.Tensor, eps: float = 1e-8) -> torch.Tensor:
+    lib = _lib.load()
+    out = torch.empty_like(x)
+    check(lib.rb200_normalize_rows(ptr(x), x.shape[0], x.shape[1], eps, ptr(out), stream_ptr()), "rb200_normalize_rows")
+    return out
+
+
+class FAISSIndex:
+    """IVFFlat inner-product index over L2-normalised vectors; scores are cosine similarities."""
+
+    def __init__(self, embed_dim: int = 64, n_lists: int = 100, n_probe: int = 10):
+        self.embed_dim = embed_dim
+        self.n_lists = n_lists
+        self.n_probe = n_probe
+        self.index: Optional[_IVFState] = None
+        self.item_ids: Optional[np.ndarray] = None            # internal row → item id
+        self._item_id_to_faiss_idx: Dict[int, int] = {}
+
+    # ---- construction (faiss_index.py:45-82) ----------------------------------------------- #
+    def build_ivf_index(self, embeddings: np.ndarray, item_ids: List[int], centroids: Optional[np.ndarray] = None) -> None:
+        """``centroids`` (optional, [n_lists, embed_dim]) skips k-means and uses the given coarse quantizer —
+        parity runs feed the same centroids to this index and to the CPU oracle."""
+        assert embeddings.dtype == np.float32, "Embeddings must be float32"
+        assert embeddings.shape[1] == self.embed_dim, f"Expected embed_dim={self.embed_dim}, got {embeddings.shape[1]}"
+        dev = _device()
+        n = embeddings.shape[0]
+        with torch.cuda.device(dev):
+            x = _normalize_device(torch.as_tensor(np.ascontiguousarray(embeddings), device=dev))   # :64-65
+            st = _IVFState(self.embed_dim, self.n_lists, self.n_probe)
+            if centroids is not None:
+                assert centroids.shape == (self.n_lists, self.embed_dim)
+                st.centroids = torch.as_tensor(np.ascontiguousarray(centroids, dtype=np.float32), device=dev)
+                st.is_trained = True
+            else:
+                logger.info("Training IVF coarse quantizer on %d vectors (n_lists=%d)...", n, self.n_lists)
+                st.train(x)
+            st.add(x)
+        self.index = st
+        self.item_ids = np.array(item_ids, dtype=np.int64)
+        self._item_id_to_faiss_idx = {int(iid): idx for idx, iid in enumerate(item_ids)}
+        logger.info("IVF index built: %d vectors, %d lists, probe=%d", st.ntotal, self.n_lists, self.n_probe)
+
+    # ---- search (faiss_index.py:88-153) ------------------------------------------------------ #
+    def _search_normalised(self, queries: np.ndarray, k: int):
+        st = self.index
+        dev = st.centroids.device
+        with torch.cuda.device(dev):
+            q = _normalize_device(torch.as_tensor(np.ascontiguousarray(queries, dtype=np.float32), device=dev))
+            s, r = st.search_device(q, k)
+            return s.cpu().numpy(), r.cpu().numpy()
+
+    def search(self, query_vector: np.ndarray, k: int = 500) -> Tuple[np.ndarray, np.ndarray]:
+        if self.index is None:
+            raise RuntimeError("Index not built. Call build_ivf_index() first.")
+        query = np.atleast_2d(query_vector).astype(np.float32)
+        k = min(k, self.index.ntotal)
+        distances, rows = self._search_normalised(query[:1], k)     # like the reference, only row 0 is used (:115-116)
+        distances, rows = distances[0], rows[0]
+        valid = rows >= 0
+        return distances[valid], self.item_ids[rows[valid]]
+
+    def batch_search(self, query_vectors: np.ndarray, k: int = 500) -> Tuple[np.ndarray, np.ndarray]:
+        if self.index is None:
+            raise RuntimeError("Index not built.")
+        k = min(k, self.index.ntotal)
+        distances, rows = self._search_normalised(query_vectors.astype(np.float32), k)
+        mapped = np.where(rows >= 0, self.item_ids[np.clip(rows, 0, len(self.item_ids) - 1)], -1)
+        return distances, mapped
+
+    # ---- persistence (faiss_index.py:159-205) ---------------------------------------------- #
+    def save(self, path: str) -> None:
+        """``path`` holds the index (own binary format: magic + npz of centroids / offsets / list ids /
+        list vectors); ``path.with_suffix('.meta.pkl')`` is the same pickle sidecar the reference writes."""
+        if self.index is None:
+            raise RuntimeError("Index not built.")
+        save_path = Path(path)
+        save_path.parent.mkdir(parents=True, exist_ok=True)
+        st = self.index
+        with open(save_path, "wb") as f:
+            f.write(_MAGIC)
+            np.savez(f, centroids=st.centroids.cpu().numpy(), offsets=st.offsets.cpu().numpy(),
+                     list_ids=st.list_ids.cpu().numpy(), list_vecs=st.list_vecs.cpu().numpy(),
+                     dims=np.array([st.d, st.nlist, st.ntotal, st.max_list_len], dtype=np.int64))
+        with open(save_path.with_suffix(".meta.pkl"), "wb") as f:
+            pickle.dump({"item_ids": self.item_ids, "item_id_to_faiss_idx": self._item_id_to_faiss_idx,
+                         "embed_dim": self.embed_dim, "n_lists": self.n_lists, "n_probe": self.n_probe}, f)
+        logger.info("Saved IVF index to %s", save_path)
+
+    @classmethod
+    def load(cls, path: str) -> "FAISSIndex":
+        load_path = Path(path)
+        if not load_path.exists():
+            raise FileNotFoundError(f"FAISS index not found at {load_path}")
+        with open(load_path.with_suffix(".meta.pkl"), "rb") as f:
+            meta = pickle.load(f)
+        obj = cls(embed_dim=meta["embed_dim"], n_lists=meta["n_lists"], n_probe=meta["n_probe"])
+        dev = _device()
+        with open(load_path, "rb") as f:
+            if f.read(len(_MAGIC)) != _MAGIC:
+                raise RB200Error(f"{load_path} is not a recommendit_b200 IVF index file")
+            z = np.load(f)
+            d, nlist, ntotal, mx = (int(v) for v in z["dims"])
+            st = _IVFState(d, nlist, meta["n_probe"])
+            st.centroids = torch.as_tensor(z["centroids"], device=dev)
+            st.offsets = torch.as_tensor(z["offsets"], device=dev)
+            st.list_ids = torch.as_tensor(z["list_ids"], device=dev)
+            st.list_vecs = torch.as_tensor(z["list_vecs"], device=dev)
+            st.ntotal, st.max_list_len, st.is_trained = ntotal, mx, True
+        obj.index = st
+        obj.item_ids = meta["item_ids"]
+        obj._item_id_to_faiss_idx = meta["item_id_to_faiss_idx"]
+        logger.info("Loaded IVF index from %s: %d vectors, dim=%d", load_path, st.ntotal, obj.embed_dim)
+        return obj
+
+    # ---- utilities (faiss_index.py:211-228) --------------------------------------------------- #
+    def stats(self) -> Dict:
+        if self.index is None:
+            return {"status": "not built"}
+        return {"n_vectors": int(self.index.ntotal), "embed_dim": self.embed_dim, "n_lists": self.n_lists,
+                "n_probe": self.n_probe, "metric": "inner_product",
+                "n_item_ids": len(self.item_ids) if self.item_ids is not None else 0}
+
+    def set_n_probe(self, n_probe: int) -> None:
+        self.n_probe = n_probe
+        if self.index is not None:
+            self.index.nprobe = n_probe
+
+
+def flat_search(queries: torch.Tensor, database: torch.Tensor, k: int, id_base: int = 0
+                ) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Exhaustive inner-product top-k on device tensors (``faiss.IndexFlatIP.search`` semantics; BASELINE cfg 5).
+    Returns (scores [nq,k], ids [nq,k] = id_base + row), -FLT_MAX / -1 padded when k > rows."""
+    lib = _lib.load()
+    _lib.require_cuda(queries, database)
+    nq, D = queries.shape
+    n = database.shape[0]
+    wb = lib.rb200_flat_search_workspace_bytes(nq, n, k)
+    ws = workspace(wb, queries.device)
+    scores = torch.empty(nq, k, dtype=torch.float32, device=queries.device)
+    ids = torch.empty(nq, k, dtype=torch.int64, device=queries.device)
+    with torch.cuda.device(queries.device):
+        check(lib.rb200_flat_search(ptr(queries), nq, ptr(database), n, D, k, id_base, ptr(scores), ptr(ids), ptr(ws), wb,
+                                    stream_ptr()), "rb200_flat_search")
+    return scores, ids
+
+
+def topk_merge(scores: torch.Tensor, ids: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Merge per-shard sorted top-k lists: scores/ids are [parts, nq, k] → ([nq,k], [nq,k])."""
+    lib = _lib.load()
+    _lib.require_cuda(scores, ids)
+    parts, nq, k = scores.shape
+    scores, ids = scores.contiguous(), ids.contiguous()
+    wb = lib.rb200_topk_merge_workspace_bytes(parts, nq, k)
+    ws = workspace(wb, scores.device)
+    out_s = torch.empty(nq, k, dtype=torch.float32, device=scores.device)
+    out_i = torch.empty(nq, k, dtype=torch.int64, device=scores.device)
+    with torch.cuda.device(scores.device):
+        check(lib.rb200_topk_merge(ptr(scores), ptr(ids), parts, nq, k, ptr(out_s), ptr(out_i), ptr(ws), wb, stream_ptr()),
+              "rb200_topk_merge")
+    return out_s, out_i

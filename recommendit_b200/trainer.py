@@ -1,0 +1,290 @@
+"""Fused BPR training step: the body of the reference's hot loop (``src/training/train_embeddings.py:183-192``)
+as ONE call into ``librb200.so`` (``rb200_bpr_step``), replayed as a CUDA graph.
+
+    trainer = FusedBPRTrainer(model, lr=1e-3, weight_decay=1e-5)        # == Adam(...) + clip_grad_norm_(1.0)
+    loss = trainer.step_host(user_ids, pos_ids, pos_genres, neg_ids, neg_genres)   # host (pinned) batch in, float out
+
+Per step the graph runs: 3 tower evaluations (1 launch) → pairwise ``bpr_loss`` (or ``in_batch_bpr_loss``) with its
+gradient → tower backward → deterministic sorted-segment scatter of the row gradients → global-norm clip → Adam.
+``adam_mode='dense'`` reproduces the reference trajectory exactly (every table row moves each step because of the
+coupled weight decay); ``adam_mode='rows'`` updates only the rows the batch touched.
+
+The unchanged reference caller cannot reach this entry point (it owns its own ``torch.optim.Adam``); it goes through
+the autograd path in ``two_tower.py``.  This class is the alternative trainer for users who can change two lines.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from typing import Dict, Optional
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import OptState, RB200Error, StepParams, StepViews, check, ptr, require_cuda, stream_ptr
+from .two_tower import INBATCH_MODE, TwoTowerModel
+
+
+def _flat_len(tower) -> int:
+    return sum(p.numel() for p in tower.mlp.parameters())
+
+
+class FusedBPRTrainer:
+    def __init__(self, model: TwoTowerModel, lr: float = 1e-3, betas=(0.9, 0.999), eps: float = 1e-8,
+                 weight_decay: float = 1e-5, max_norm: float = 1.0, adam_mode: str = "dense", loss: str = "bpr",
+                 inbatch_mode: Optional[int] = None, item_extra_table: Optional[torch.Tensor] = None,
+                 use_cuda_graph: bool = True, seed: Optional[int] = None):
+        self.lib = _lib.load()
+        self.model = model
+        self.dev = require_cuda(*list(model.parameters()))
+        if adam_mode not in ("dense", "rows"):
+            raise ValueError("adam_mode must be 'dense' (reference-exact) or 'rows' (touched rows only)")
+        if loss not in ("bpr", "in_batch"):
+            raise ValueError("loss must be 'bpr' or 'in_batch'")
+        self.adam_mode, self.loss_kind = adam_mode, (0 if loss == "bpr" else 1)
+        self.inbatch_mode = INBATCH_MODE if inbatch_mode is None else int(inbatch_mode)
+        self.use_graph = use_cuda_graph
+        self.seed = (torch.initial_seed() if seed is None else seed) & 0x7FFFFFFFFFFFFFFF
+        self.D, self.H = model.embed_dim, model.user_tower.mlp[0].out_features
+        self.E = model.item_tower.extra_dim
+        self.item_extra_table = None
+        if item_extra_table is not None:
+            t = item_extra_table.to(self.dev, torch.float32).contiguous()
+            if t.shape != (model.n_items + 1, self.E):
+                raise ValueError(f"item_extra_table must be [{model.n_items + 1}, {self.E}]")
+            self.item_extra_table = t
+        self._flatten()
+        f32 = dict(dtype=torch.float32, device=self.dev)
+        ut, it = model.user_tower.embedding.weight, model.item_tower.embedding.weight
+        self.state = {
+            "user_table_m": torch.zeros_like(ut), "user_table_v": torch.zeros_like(ut),
+            "item_table_m": torch.zeros_like(it), "item_table_v": torch.zeros_like(it),
+            "user_mlp_m": torch.zeros(self._user_flat.numel(), **f32), "user_mlp_v": torch.zeros(self._user_flat.numel(), **f32),
+            "item_mlp_m": torch.zeros(self._item_flat.numel(), **f32), "item_mlp_v": torch.zeros(self._item_flat.numel(), **f32),
+        }
+        self.user_slot = torch.full((ut.shape[0],), -1, dtype=torch.int32, device=self.dev)
+        self.item_slot = torch.full((it.shape[0],), -1, dtype=torch.int32, device=self.dev)
+        self.opt_dev = torch.zeros(128, dtype=torch.uint8, device=self.dev)
+        self._opt_host = OptState()
+        h = self._opt_host
+        h.lr, h.beta1, h.beta2, h.eps, h.weight_decay, h.max_norm = lr, betas[0], betas[1], eps, weight_decay, max_norm
+        h.one_minus_beta1, h.one_minus_beta2, h.beta2_f = 1 - betas[0], 1 - betas[1], betas[1]
+        h.clip_coef, h.step = 1.0, 0
+        self._push_opt()
+        self.loss_dev = torch.zeros(1, **f32)
+        self.err_flag = torch.zeros(1, dtype=torch.int32, device=self.dev)
+        self._B = None
+        self._graph = None
+        self._steps_done = 0
+
+    # ---- parameter plumbing ------------------------------------------------------------------- #
+    def _flatten(self) -> None:
+        """Make the 4 MLP tensors of each tower views of ONE flat block [W1 | b1 | W2 | b2] (what the step kernel and
+        the fused Adam walk); the nn.Parameters keep working because only ``.data`` is re-pointed."""
+        flats = []
+        for tower in (self.model.user_tower, self.model.item_tower):
+            ps = [tower.mlp[0].weight, tower.mlp[0].bias, tower.mlp[3].weight, tower.mlp[3].bias]
+            flat = torch.cat([p.detach().reshape(-1).float() for p in ps]).contiguous()
+            o = 0
+            for p in ps:
+                p.data = flat[o:o + p.numel()].view(p.shape)
+                o += p.numel()
+            flats.append(flat)
+        self._user_flat, self._item_flat = flats
+        for emb in (self.model.user_tower.embedding, self.model.item_tower.embedding):
+            if not emb.weight.is_contiguous() or emb.weight.dtype != torch.float32:
+                emb.weight.data = emb.weight.data.float().contiguous()
+
+    def _is_flat(self) -> bool:
+        return (self.model.user_tower.mlp[0].weight.data_ptr() == self._user_flat.data_ptr()
+                and self.model.item_tower.mlp[0].weight.data_ptr() == self._item_flat.data_ptr())
+
+    def _push_opt(self) -> None:
+        host = torch.frombuffer(bytearray(bytes(self._opt_host)), dtype=torch.uint8)
+        self.opt_dev.copy_(host)
+
+    def _pull_opt(self) -> OptState:
+        raw = bytes(self.opt_dev.cpu().numpy().tobytes())
+        return OptState.from_buffer_copy(raw)
+
+    def set_lr(self, lr: float) -> None:
+        """For ``CosineAnnealingLR``-style schedules (the reference steps it once per epoch)."""
+        cur = self._pull_opt()
+        cur.lr = lr
+        self._opt_host = cur
+        self._push_opt()
+
+    @property
+    def opt_state(self) -> OptState:
+        return self._pull_opt()
+
+    # ---- batch buffers ---------------------------------------------------------------------------- #
+    def _alloc(self, B: int) -> None:
+        self._B = B
+        E = 0 if self.item_extra_table is not None else self.E
+        n_i64 = 3 * B
+        self.batch_bytes = n_i64 * 8 + 2 * B * E * 4
+        # one packed staging buffer: [user_ids | pos_ids | neg_ids | pos_extra | neg_extra]
+        self.batch_dev = torch.zeros(self.batch_bytes, dtype=torch.uint8, device=self.dev)
+        self.batch_pinned = torch.zeros(self.batch_bytes, dtype=torch.uint8).pin_memory()
+        ids = self.batch_dev[: n_i64 * 8].view(torch.int64)
+        self.user_ids, self.pos_ids, self.neg_ids = ids[:B], ids[B:2 * B], ids[2 * B:]
+        if E:
+            ex = self.batch_dev[n_i64 * 8:].view(torch.float32)
+            self.pos_extra, self.neg_extra = ex[: B * E].view(B, E), ex[B * E:].view(B, E)
+        else:
+            self.pos_extra = self.neg_extra = self.item_extra_table
+        wsb = self.lib.rb200_bpr_step_workspace_bytes(B, self.D, self.H, self.E, self.model.n_users + 1,
+                                                      self.model.n_items + 1, self.loss_kind)
+        self.ws = torch.empty(wsb, dtype=torch.uint8, device=self.dev)
+        self._graph = None
+        self._params = None
+
+    def pack_host(self, user_ids, pos_ids, pos_genres, neg_ids, neg_genres, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """Pack one batch (NumPy arrays or CPU tensors) into the staging layout; returns a pinned uint8 tensor."""
+        B = len(user_ids)
+        if self._B != B:
+            self._alloc(B)
+        buf = self.batch_pinned if out is None else out
+        nb = buf.numpy()
+        ids = nb[: 3 * B * 8].view(np.int64)
+        ids[:B], ids[B:2 * B], ids[2 * B:] = np.asarray(user_ids), np.asarray(pos_ids), np.asarray(neg_ids)
+        if self.item_extra_table is None and self.E:
+            ex = nb[3 * B * 8:].view(np.float32)
+            ex[: B * self.E] = np.asarray(pos_genres, dtype=np.float32).reshape(-1)
+            ex[B * self.E:] = np.asarray(neg_genres, dtype=np.float32).reshape(-1)
+        return buf
+
+    # ---- the step ------------------------------------------------------------------------------------ #
+    def _make_params(self) -> StepParams:
+        m, s = self.model, self.state
+        p = StepParams()
+        p.D, p.H, p.extra_dim, p.B = self.D, self.H, self.E, self._B
+        p.n_user_rows, p.n_item_rows = m.n_users + 1, m.n_items + 1
+        p.user_table, p.user_table_m, p.user_table_v = ptr(m.user_tower.embedding.weight), ptr(s["user_table_m"]), ptr(s["user_table_v"])
+        p.item_table, p.item_table_m, p.item_table_v = ptr(m.item_tower.embedding.weight), ptr(s["item_table_m"]), ptr(s["item_table_v"])
+        p.user_mlp, p.user_mlp_m, p.user_mlp_v = ptr(self._user_flat), ptr(s["user_mlp_m"]), ptr(s["user_mlp_v"])
+        p.item_mlp, p.item_mlp_m, p.item_mlp_v = ptr(self._item_flat), ptr(s["item_mlp_m"]), ptr(s["item_mlp_v"])
+        p.user_row_slot, p.item_row_slot, p.opt = ptr(self.user_slot), ptr(self.item_slot), ptr(self.opt_dev)
+        p.user_ids, p.pos_ids, p.neg_ids = ptr(self.user_ids), ptr(self.pos_ids), ptr(self.neg_ids)
+        p.pos_extra, p.neg_extra = ptr(self.pos_extra), ptr(self.neg_extra)
+        p.extra_by_id = 1 if self.item_extra_table is not None else 0
+        p.loss_kind, p.inbatch_mode = self.loss_kind, self.inbatch_mode
+        p.adam_mode = 0 if self.adam_mode == "dense" else 1
+        p.dropout_p = m.user_tower.dropout_p if m.training else 0.0
+        p.seed = self.seed
+        p.keep_mask_user = p.keep_mask_pos = p.keep_mask_neg = None
+        p.padding_idx = 0
+        p.loss, p.err_flag = ptr(self.loss_dev), ptr(self.err_flag)
+        p.workspace, p.workspace_bytes = ptr(self.ws), self.ws.numel()
+        return p
+
+    def _launch(self, masks=None) -> None:
+        if not self._is_flat():
+            self._flatten()
+            self._graph = None
+        p = self._make_params()
+        if masks is not None:
+            self._mask_keep = [None if t is None else t.to(self.dev, torch.uint8).contiguous() for t in masks]
+            p.keep_mask_user, p.keep_mask_pos, p.keep_mask_neg = (ptr(t) for t in self._mask_keep)
+        self._params = p
+        check(self.lib.rb200_bpr_step(C.byref(p), stream_ptr()), "rb200_bpr_step")
+
+    def step(self, masks=None) -> torch.Tensor:
+        """One optimiser step on the batch currently in the staging buffers (``user_ids`` … ``neg_extra``).
+        Returns the device scalar holding the loss (no synchronisation)."""
+        if self._B is None:
+            raise RB200Error("no batch staged: call load_batch()/step_host() first")
+        with torch.cuda.device(self.dev):
+            training_p = self.model.user_tower.dropout_p if self.model.training else 0.0
+            key = (self._B, training_p)
+            if not self.use_graph or masks is not None:
+                self._launch(masks)
+            elif self._warm_key != key:
+                self._launch()                          # first step of a shape runs eagerly: sets kernel attributes
+                self._warm_key, self._graph = key, None
+            elif self._graph is None or not self._is_flat():
+                if not self._is_flat():
+                    self._flatten()
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):               # capture enqueues nothing; replay() below runs the step
+                    self._launch()
+                self._graph = g
+                g.replay()
+            else:
+                self._graph.replay()
+        self._steps_done += 1
+        return self.loss_dev
+
+    _warm_key = None
+
+    def load_batch(self, user_ids, pos_ids, pos_genres=None, neg_ids=None, neg_genres=None) -> None:
+        """Stage a batch that already lives on the device (device→device copies into the static buffers)."""
+        B = user_ids.numel()
+        if self._B != B:
+            self._alloc(B)
+        self.user_ids.copy_(user_ids)
+        self.pos_ids.copy_(pos_ids)
+        if neg_ids is not None:
+            self.neg_ids.copy_(neg_ids)
+        if self.item_extra_table is None and self.E:
+            self.pos_extra.copy_(pos_genres)
+            if neg_genres is not None:
+                self.neg_extra.copy_(neg_genres)
+
+    def load_packed(self, packed: torch.Tensor) -> None:
+        """Stage a packed batch (``pack_host`` layout) from pinned host or device memory with one async copy."""
+        self.batch_dev.copy_(packed, non_blocking=True)
+
+    def step_host(self, user_ids, pos_ids, pos_genres, neg_ids, neg_genres) -> float:
+        """End-to-end step on a host batch: pack → one H2D copy → graph replay → D2H of the loss (synchronises,
+        like ``loss.item()`` at train_embeddings.py:194)."""
+        self.load_packed(self.pack_host(user_ids, pos_ids, pos_genres, neg_ids, neg_genres))
+        return float(self.step().item())
+
+    def check_ids(self) -> None:
+        if int(self.err_flag.item()) != 0:
+            raise IndexError("an id in a previous batch was outside its embedding table (torch would raise "
+                             "'index out of range in self')")
+
+    def views(self) -> Dict[str, torch.Tensor]:
+        """Gradients of the last step (for tests): flat MLP grads and compact unique-row gradients."""
+        v = StepViews()
+        check(self.lib.rb200_bpr_step_views(C.byref(self._params), C.byref(v)), "rb200_bpr_step_views")
+        torch.cuda.synchronize(self.dev)
+
+        def wrap(addr, n, dtype):
+            out = torch.empty(n, dtype=dtype, device=self.dev)
+            size = n * out.element_size()
+            off = addr - self.ws.data_ptr()
+            out.view(torch.uint8).copy_(self.ws[off:off + size])
+            return out
+
+        B, D = self._B, self.D
+        items = 2 if self.loss_kind == 0 else 1
+        nu = int(wrap(v.user_n_uniq, 1, torch.int32).item())
+        ni = int(wrap(v.item_n_uniq, 1, torch.int32).item())
+        return {
+            "user_mlp_grad": wrap(v.user_mlp_grad, self._user_flat.numel(), torch.float32),
+            "item_mlp_grad": wrap(v.item_mlp_grad, self._item_flat.numel(), torch.float32),
+            "user_uniq_ids": wrap(v.user_uniq_ids, B, torch.int64)[:nu],
+            "item_uniq_ids": wrap(v.item_uniq_ids, items * B, torch.int64)[:ni],
+            "user_uniq_grads": wrap(v.user_uniq_grads, B * D, torch.float32).view(B, D)[:nu],
+            "item_uniq_grads": wrap(v.item_uniq_grads, items * B * D, torch.float32).view(items * B, D)[:ni],
+            "user_emb": wrap(v.user_emb, B * D, torch.float32).view(B, D),
+            "pos_emb": wrap(v.pos_emb, B * D, torch.float32).view(B, D),
+        }
+
+    # ---- checkpointing of the optimiser (the reference saves none; offered for resume) ------------ #
+    def state_dict(self) -> Dict:
+        st = self._pull_opt()
+        return {"moments": {k: v.detach().cpu() for k, v in self.state.items()}, "step": int(st.step), "lr": float(st.lr)}
+
+    def load_state_dict(self, sd: Dict) -> None:
+        for k, v in sd["moments"].items():
+            self.state[k].copy_(v)
+        st = self._pull_opt()
+        st.step, st.lr = int(sd["step"]), float(sd["lr"])
+        self._opt_host = st
+        self._push_opt()
