@@ -108,6 +108,27 @@ def coarse_probe(q: np.ndarray, centroids: np.ndarray, nprobe: int) -> np.ndarra
     return np.argsort(-s, axis=1, kind="stable")[:, :nprobe]
 
 
+def coarse_probe_margin(q: np.ndarray, centroids: np.ndarray, nprobe: int) -> np.ndarray:
+    """fp64 score gap between the nprobe-th and (nprobe+1)-th centroid per query: queries whose margin is
+    below fp32 rounding (~1e-6) may legitimately probe a different list set in another implementation."""
+    s = np.sort(q.astype(np.float64) @ centroids.astype(np.float64).T, axis=1)[:, ::-1]
+    if nprobe >= s.shape[1]:
+        return np.full(s.shape[0], np.inf)
+    return s[:, nprobe - 1] - s[:, nprobe]
+
+
+def assign_margin(x: np.ndarray, centroids: np.ndarray, block: int = 65536) -> np.ndarray:
+    """fp64 gap between the best and second-best centroid score per row (∞ with a single centroid)."""
+    out = np.empty(x.shape[0])
+    if centroids.shape[0] < 2:
+        out[:] = np.inf
+        return out
+    for s0 in range(0, x.shape[0], block):
+        sc = np.partition(x[s0:s0 + block].astype(np.float64) @ centroids.astype(np.float64).T, -2, axis=1)
+        out[s0:s0 + block] = sc[:, -1] - sc[:, -2]
+    return out
+
+
 def ivf_search(q, centroids, offsets, order, xn, nprobe: int, k: int, dtype=np.float32):
     """Returns (scores[nq,k] f32, idx[nq,k] i64 internal row numbers; −1 / −FLT_MAX padding)."""
     q = np.asarray(q, dtype=np.float32)

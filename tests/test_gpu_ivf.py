@@ -1,0 +1,194 @@
+"""GPU parity of the IVFFlat / flat retrieval kernels against oracle/ivf_oracle.py on shared centroids
+("IVF candidate IDs identical except exact-score ties", BASELINE.json)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import ivf_oracle as V
+
+pytestmark = pytest.mark.gpu
+
+
+def _data(n, d, nlist, seed, skew=False):
+    rng = np.random.default_rng(seed)
+    if skew:
+        cen = V.normalize_rows(rng.standard_normal((nlist, d)).astype(np.float32))
+        z = rng.zipf(1.3, n) % nlist
+        x = V.normalize_rows(cen[z] + 0.35 * rng.standard_normal((n, d)).astype(np.float32))
+    else:
+        x = V.normalize_rows(rng.standard_normal((n, d)).astype(np.float32))
+    return x, rng
+
+
+def _oracle_index(x, nlist, seed=1234):
+    c = V.spherical_kmeans(x, nlist, seed=seed)
+    off, order = V.build_lists(V.assign(x, c), nlist)
+    return c, off, order
+
+
+def _check_build(st, xn, c, nlist):
+    """index.add parity: the GPU assignment equals the oracle's except where two centroids tie within fp32
+    rounding; given that assignment the CSR layout (offsets, order inside lists, vectors) is bit-identical.
+    Returns the oracle CSR built from the GPU assignment."""
+    list_ids = st.list_ids.cpu().numpy()
+    off_g = st.offsets.cpu().numpy()
+    a_gpu = np.empty(xn.shape[0], dtype=np.int64)
+    a_gpu[list_ids] = np.repeat(np.arange(nlist), np.diff(off_g))
+    a_ref = V.assign(xn, c)
+    diff = a_gpu != a_ref
+    if diff.any():
+        assert (V.assign_margin(xn[diff], c) < 1e-5).all(), "assignment differs away from a tie"
+    off, order = V.build_lists(a_gpu, nlist)
+    assert np.array_equal(off_g, off) and np.array_equal(list_ids, order)
+    np.testing.assert_allclose(st.list_vecs.cpu().numpy(), xn[order], rtol=0, atol=2e-7)
+    return off, order
+
+
+def _stable_queries(q, c, nprobe):
+    """queries whose probed list set is unambiguous in fp32"""
+    return V.coarse_probe_margin(q, c, nprobe) > 1e-5
+
+
+@pytest.mark.parametrize("n,d,nlist,nprobe,k,nq", [
+    (500, 32, 10, 5, 20, 7),          # the reference fixture
+    (3883, 64, 100, 10, 500, 64),     # BASELINE config C1 (catalog 3883, nlist 100, nprobe 10, top-500)
+    (20000, 64, 256, 16, 500, 130),
+    (5000, 128, 50, 50, 100, 33),     # nprobe = nlist → exhaustive
+    (1000, 64, 40, 3, 500, 9),        # k larger than the probed lists → -1 padding
+])
+def test_ivf_search_matches_oracle(n, d, nlist, nprobe, k, nq):
+    import recommendit_b200 as R
+    x, rng = _data(n, d, nlist, seed=n + d, skew=(n == 20000))
+    c, off, order = _oracle_index(x, nlist)
+    q = V.normalize_rows(x[rng.integers(0, n, nq)] + 0.2 * rng.standard_normal((nq, d)).astype(np.float32))
+    idx = R.FAISSIndex(d, nlist, nprobe)
+    item_ids = (np.arange(n) * 3 + 7).tolist()
+    idx.build_ivf_index(x, item_ids, centroids=c)
+    off, order = _check_build(idx.index, x, c, nlist)
+    ok = _stable_queries(q, c, nprobe)
+    assert ok.mean() > 0.9
+    s_ref, i_ref = V.ivf_search(q, c, off, order, x, nprobe, min(k, n))
+    s, ids = idx.batch_search(q, k)
+    assert s.shape == (nq, min(k, n)) and (np.diff(s, axis=1) <= 0).all()
+    ids_ref = np.where(i_ref >= 0, np.asarray(item_ids)[np.clip(i_ref, 0, n - 1)], -1)
+    V.assert_topk_equivalent(s[ok], ids[ok], s_ref[ok], ids_ref[ok])
+    if not ok[0]:
+        return
+    # single-query wrapper drops the padding
+    d1, id1 = idx.search(q[0], k)
+    valid = i_ref[0] >= 0
+    assert len(id1) == valid.sum() and (np.diff(d1) <= 0).all()
+    V.assert_topk_equivalent(d1[None], id1[None], s_ref[:1, :len(id1)], ids_ref[:1, :len(id1)])
+
+
+def test_unnormalised_inputs_are_renormalised():
+    import recommendit_b200 as R
+    x, rng = _data(800, 32, 8, seed=5)
+    c, off, order = _oracle_index(x, 8)
+    scale = rng.uniform(0.1, 50, (800, 1)).astype(np.float32)
+    idx = R.FAISSIndex(32, 8, 4)
+    idx.build_ivf_index((x * scale).astype(np.float32), list(range(800)), centroids=c)
+    q = rng.standard_normal((5, 32)).astype(np.float32) * 100
+    s, ids = idx.batch_search(q, 30)
+    xn = V.normalize_rows(x * scale)
+    off, order = _check_build(idx.index, xn, c, 8)
+    ok = _stable_queries(V.normalize_rows(q), c, 4)
+    s_ref, i_ref = V.ivf_search(V.normalize_rows(q), c, off, order, xn, 4, 30)
+    V.assert_topk_equivalent(s[ok], ids[ok], s_ref[ok], i_ref[ok], rtol=1e-5, atol=1e-5)
+    assert np.abs(s).max() <= 1.0 + 1e-5
+
+
+def test_exact_ties_follow_scan_order():
+    import recommendit_b200 as R
+    x = np.zeros((64, 32), np.float32); x[:, 0] = 1.0; x[40:, 1] = 1.0     # two groups of identical vectors
+    c = V.normalize_rows(np.stack([x[0], x[63]]))
+    idx = R.FAISSIndex(32, 2, 2)
+    idx.build_ivf_index(x, list(range(64)), centroids=c)
+    s, ids = idx.batch_search(x[:1], 50)
+    xn = V.normalize_rows(x)
+    off, order = V.build_lists(V.assign(xn, c), 2)
+    s_ref, i_ref = V.ivf_search(xn[:1], c, off, order, xn, 2, 50)
+    assert ids[0].tolist() == i_ref[0].tolist()                            # bit-identical, ties included
+    np.testing.assert_array_equal(s, s_ref)
+
+
+def test_gpu_kmeans_trains_a_usable_quantizer():
+    """index.train is not bit-reproducible against FAISS (nor required to be); check the objective instead."""
+    import recommendit_b200 as R
+    x, rng = _data(6000, 64, 32, seed=9, skew=True)
+    idx = R.FAISSIndex(64, 32, 8)
+    idx.build_ivf_index(x, list(range(6000)))
+    cg = idx.index.centroids.cpu().numpy()
+    assert np.allclose(np.linalg.norm(cg, axis=1), 1.0, atol=1e-5)
+    co = V.spherical_kmeans(x, 32)
+    obj_g = (x @ cg.T).max(1).mean()
+    obj_o = (x @ co.T).max(1).mean()
+    assert obj_g >= obj_o - 5e-3, (obj_g, obj_o)
+    assert idx.index.ntotal == 6000 and int(idx.index.offsets[-1].item()) == 6000
+    # same initialisation + same algorithm ⇒ nearly the same partition as the oracle
+    agree = (V.assign(x, cg) == V.assign(x, co)).mean()
+    assert agree > 0.98, agree
+
+
+@pytest.mark.parametrize("n,d,k,nq", [(1000, 64, 500, 5), (70000, 64, 500, 33), (300, 32, 500, 3), (5000, 128, 17, 64)])
+def test_flat_search_matches_oracle(n, d, k, nq):
+    import recommendit_b200 as R
+    x, rng = _data(n, d, 1, seed=n)
+    q = V.normalize_rows(rng.standard_normal((nq, d)).astype(np.float32))
+    s, ids = R.flat_search(torch.from_numpy(q).cuda(), torch.from_numpy(x).cuda(), k, id_base=1000)
+    s_ref, i_ref = V.flat_search(q, x, k)
+    V.assert_topk_equivalent(s.cpu().numpy(), ids.cpu().numpy(), s_ref, np.where(i_ref >= 0, i_ref + 1000, -1))
+
+
+def test_sharded_flat_search_merge_equals_unsharded():
+    """BASELINE config C5 in miniature: per-shard top-k + merge == global top-k."""
+    import recommendit_b200 as R
+    x, rng = _data(40000, 64, 1, seed=2)
+    q = V.normalize_rows(rng.standard_normal((16, 64)).astype(np.float32))
+    xd, qd = torch.from_numpy(x).cuda(), torch.from_numpy(q).cuda()
+    parts_s, parts_i = [], []
+    for sh in range(4):
+        s, i = R.flat_search(qd, xd[sh * 10000:(sh + 1) * 10000].contiguous(), 500, id_base=sh * 10000)
+        parts_s.append(s); parts_i.append(i)
+    ms, mi = R.topk_merge(torch.stack(parts_s), torch.stack(parts_i))
+    s_ref, i_ref = V.flat_search(q, x, 500)
+    V.assert_topk_equivalent(ms.cpu().numpy(), mi.cpu().numpy(), s_ref, i_ref)
+
+
+def test_full_size_ivf_properties():
+    """BASELINE config C3 (1 M × 64, nlist 4096, nprobe 32, top-500, 4096 queries): properties that do not need
+    the oracle at full size, plus an oracle check on a query sample."""
+    import recommendit_b200 as R
+    n, d, nlist, nprobe, k, nq = 1_000_000, 64, 4096, 32, 500, 4096
+    g = torch.Generator(device="cuda").manual_seed(7)
+    cen = torch.nn.functional.normalize(torch.randn(nlist, d, device="cuda", generator=g), dim=-1)
+    z = (torch.rand(n, device="cuda", generator=g) ** 2 * nlist).long().clamp_(max=nlist - 1)
+    x = torch.nn.functional.normalize(cen[z] + 0.35 * torch.randn(n, d, device="cuda", generator=g), dim=-1)
+    xq = x[torch.randint(0, n, (nq,), device="cuda", generator=g)]
+    q = torch.nn.functional.normalize(xq + 0.2 * torch.randn(nq, d, device="cuda", generator=g), dim=-1)
+    xh, ch, qh = x.cpu().numpy(), cen.cpu().numpy(), q.cpu().numpy()
+    idx = R.FAISSIndex(d, nlist, nprobe)
+    idx.build_ivf_index(xh, list(range(n)), centroids=ch)
+    s, ids = idx.batch_search(qh, k)
+    assert s.shape == (nq, k) and ids.shape == (nq, k)
+    assert (np.diff(s, axis=1) <= 0).all()                                 # sorted
+    assert (ids >= 0).all()                                                # ≥ 500 candidates per query here
+    assert all(len(set(r.tolist())) == k for r in ids[:64])                # no duplicates
+    xn = V.normalize_rows(xh)
+    got = np.einsum("qkd,qd->qk", xn[ids[:32]], qh[:32])
+    np.testing.assert_allclose(got, s[:32], rtol=2e-6, atol=2e-6)          # scores are the real inner products
+    st = idx.index
+    off, order = st.offsets.cpu().numpy(), st.list_ids.cpu().numpy()
+    assert off[-1] == n and np.array_equal(np.sort(order), np.arange(n))   # a permutation: every row in one list
+    sample = np.arange(0, n, 50)                                           # assignment parity on a 20 k-row sample
+    a_gpu = np.empty(n, dtype=np.int64); a_gpu[order] = np.repeat(np.arange(nlist), np.diff(off))
+    a_ref = V.assign(xn[sample], ch)
+    bad = a_gpu[sample] != a_ref
+    assert bad.mean() < 1e-3 and (V.assign_margin(xn[sample][bad], ch) < 1e-5).all()
+    sel = np.arange(0, nq, 128)
+    sel = sel[_stable_queries(qh[sel], ch, nprobe)]
+    s_ref, i_ref = V.ivf_search(qh[sel], ch, off, order, xn, nprobe, k)
+    V.assert_topk_equivalent(s[sel], ids[sel], s_ref, i_ref)
+    # idempotence: same call, same answer
+    s2, ids2 = idx.batch_search(qh, k)
+    assert np.array_equal(ids, ids2) and np.array_equal(s, s2)

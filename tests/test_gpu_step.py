@@ -1,0 +1,203 @@
+"""GPU parity of the fused one-call training step (rb200_bpr_step) against the reference trajectory."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import two_tower_oracle as O
+from tests.parity import (batch_from_golden, dev, flat_mlp, grad_tol, masks_from_golden, model_from_golden,
+                          params_from_golden, rel_l2)
+
+pytestmark = pytest.mark.gpu
+CASES = ["tt_small", "tt_dup", "tt_dropout", "tt_d128"]
+
+
+def _trainer(model, g, **kw):
+    import recommendit_b200 as R
+    return R.FusedBPRTrainer(model, lr=float(g["lr"]), weight_decay=1e-5, max_norm=1.0, **kw)
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_fused_step_matches_reference_trajectory(golden, case):
+    g = golden(case)
+    model = model_from_golden(g).train()
+    tr = _trainer(model, g, use_cuda_graph=False)
+    lr = float(g["lr"])
+    for s in range(int(g["meta"][5])):
+        pre = f"step{s}/"
+        b = batch_from_golden(g, s)
+        tr.load_packed(tr.pack_host(*b))
+        masks = masks_from_golden(g, s)
+        loss = tr.step(masks=None if masks is None else [torch.from_numpy(m) for m in masks]).item()
+        assert abs(loss - float(g[pre + "loss"])) <= 1e-6 + 4e-5 * s, (case, s, loss)
+        if s == 0:
+            # gradients of the first step against the fp64 oracle
+            P = params_from_golden(g)
+            _, G64, _ = O.loss_and_grads(P, *b, masks=masks, drop_p=float(g["dropout"]))
+            v = tr.views()
+            assert rel_l2(v["user_mlp_grad"].cpu().numpy(), flat_mlp(G64, "user")) <= 1e-5
+            gi = v["item_mlp_grad"].cpu().numpy()
+            ref = flat_mlp(G64, "item")
+            nb2 = G64["item_tower.mlp.3.bias"].size
+            assert rel_l2(gi[:-nb2], ref[:-nb2]) <= 1e-5
+            assert rel_l2(gi[-nb2:], ref[-nb2:]) <= 1e-4
+            for tower in ("user", "item"):
+                dense = G64[f"{tower}_tower.embedding.weight"]
+                ids = v[f"{tower}_uniq_ids"].cpu().numpy()
+                bids = b[0] if tower == "user" else np.concatenate([b[1], b[3]])
+                assert np.array_equal(ids, np.unique(bids[bids != 0]))
+                assert 0 not in ids                                   # padding row never shows up
+                assert np.all(np.diff(ids) > 0)                       # ascending, unique
+                assert rel_l2(v[f"{tower}_uniq_grads"].cpu().numpy(), dense[ids]) <= 1e-5
+            st = tr.opt_state
+            assert abs(st.total_norm - float(g[pre + "total_norm"])) <= 1e-5 * st.total_norm
+            assert st.step == 1
+        # parameters after the step: every element moves by ~lr (coupled weight decay + Adam normalisation, F5);
+        # tolerance 2 % of lr absolute (Adam amplifies 1e-9 gradient noise on near-zero gradients)
+        for k, prm in model.state_dict().items():
+            ref = g[pre + "after/" + k]
+            err = np.abs(prm.detach().cpu().numpy() - ref).max()
+            assert err <= 0.25 * lr * (s + 1), (case, s, k, err)
+            moved = np.abs(ref - g["init/" + k])
+            if k.endswith("embedding.weight"):
+                assert (moved > 0).mean() > 0.99                      # dense mode: untouched rows move too
+    tr.check_ids()
+
+
+def test_adam_on_reference_gradients_is_exact(golden):
+    """Isolates clip+Adam from gradient rounding: feed the reference's own gradients through the device Adam."""
+    import ctypes as C
+    import recommendit_b200 as R
+    from recommendit_b200 import _lib
+    lib = _lib.load()
+    g = golden("tt_dup")
+    model = model_from_golden(g)
+    tr = _trainer(model, g, use_cuda_graph=False)
+    ws = _lib.workspace(lib.rb200_sumsq_workspace_bytes(), "cuda")
+    moments = {k: (torch.zeros_like(p), torch.zeros_like(p)) for k, p in model.named_parameters()}
+    for s in range(2):
+        grads = {k: dev(g[f"step{s}/grad/{k}"]) for k, _ in model.named_parameters()}
+        _lib.check(lib.rb200_opt_begin_step(tr.opt_dev.data_ptr(), _lib.stream_ptr()))
+        items = list(grads.items())
+        for i in range(0, len(items), 4):
+            segs = (_lib.SumsqSeg * 4)()
+            chunk = items[i:i + 4]
+            for j, (k, t) in enumerate(chunk):
+                segs[j] = _lib.SumsqSeg(t.data_ptr(), t.numel(), None, 0)
+            _lib.check(lib.rb200_sumsq_accumulate(tr.opt_dev.data_ptr(), segs, len(chunk), ws.data_ptr(), ws.numel(), _lib.stream_ptr()))
+        _lib.check(lib.rb200_grad_norm_clip(tr.opt_dev.data_ptr(), _lib.stream_ptr()))
+        st = tr.opt_state
+        assert abs(st.total_norm - float(g[f"step{s}/total_norm"])) <= 2e-6 * st.total_norm
+        for k, prm in model.named_parameters():
+            m, v = moments[k]
+            _lib.check(lib.rb200_adam_dense(prm.data_ptr(), grads[k].data_ptr(), m.data_ptr(), v.data_ptr(), prm.numel(),
+                                            tr.opt_dev.data_ptr(), _lib.stream_ptr()))
+            err = (prm.detach().cpu() - torch.from_numpy(g[f"step{s}/after/{k}"])).abs().max().item()
+            assert err <= 2e-3 * float(g["lr"]) + 2e-7, (s, k, err)
+            prm.data.copy_(dev(g[f"step{s}/after/{k}"]))
+
+
+def test_rows_mode_updates_only_touched_rows(golden):
+    g = golden("tt_dup")
+    model = model_from_golden(g).train()
+    before = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    tr = _trainer(model, g, adam_mode="rows", use_cuda_graph=False)
+    b = batch_from_golden(g, 0)
+    tr.load_packed(tr.pack_host(*b))
+    tr.step()
+    after = model.state_dict()
+    for tower, ids in (("user", b[0]), ("item", np.concatenate([b[1], b[3]]))):
+        k = f"{tower}_tower.embedding.weight"
+        changed = (after[k] != before[k]).any(dim=1).cpu().numpy()
+        touched = np.zeros_like(changed); touched[np.unique(ids[ids != 0])] = True
+        assert np.array_equal(changed, touched)
+        # the touched rows get exactly the dense-mode update
+    dense_model = model_from_golden(g).train()
+    tr2 = _trainer(dense_model, g, adam_mode="dense", use_cuda_graph=False)
+    tr2.load_packed(tr2.pack_host(*b)); tr2.step()
+    for tower, ids in (("user", b[0]), ("item", np.concatenate([b[1], b[3]]))):
+        k = f"{tower}_tower.embedding.weight"
+        rows = dev(np.unique(ids[ids != 0]))
+        assert torch.equal(after[k][rows], dense_model.state_dict()[k][rows])
+    for k in after:
+        if "mlp" in k:
+            assert torch.equal(after[k], dense_model.state_dict()[k])
+
+
+def test_cuda_graph_replay_equals_eager_and_is_deterministic(golden):
+    g = golden("tt_dup")
+    runs = []
+    for use_graph in (False, True, True):
+        model = model_from_golden(g).train()
+        tr = _trainer(model, g, use_cuda_graph=use_graph)
+        losses = []
+        for it in range(6):
+            b = batch_from_golden(g, it % 2)
+            losses.append(tr.step_host(*b))
+        runs.append((losses, {k: v.detach().clone() for k, v in model.state_dict().items()}))
+        if use_graph:
+            assert tr._graph is not None
+    for losses, sd in runs[1:]:
+        assert losses == runs[0][0]
+        for k in sd:
+            assert torch.equal(sd[k], runs[0][1][k]), k
+
+
+def test_in_batch_step_matches_oracle(golden):
+    g = golden("tt_dup")
+    model = model_from_golden(g).train()
+    tr = _trainer(model, g, loss="in_batch", inbatch_mode=0, use_cuda_graph=False)
+    b = batch_from_golden(g, 0)
+    tr.load_packed(tr.pack_host(*b))
+    loss = tr.step().item()
+    P = params_from_golden(g)
+    l64, G64, _ = O.loss_and_grads(P, *b, in_batch=True)
+    assert abs(loss - float(l64)) <= 1e-6
+    v = tr.views()
+    assert rel_l2(v["user_mlp_grad"].cpu().numpy(), flat_mlp(G64, "user")) <= 1e-5
+    P32 = params_from_golden(g, dtype=np.float32)
+    S = O.AdamState()
+    O.train_step(P32, S, b, lr=float(g["lr"]), in_batch=True)
+    for k, prm in model.state_dict().items():
+        assert np.abs(prm.detach().cpu().numpy() - P32[k]).max() <= 0.25 * float(g["lr"]), k
+
+
+def test_item_extra_table_mode_equals_per_sample_genres(golden):
+    import recommendit_b200 as R
+    g = golden("tt_dup")
+    u, p, pg, n, ng = batch_from_golden(g, 0)
+    ni = int(g["meta"][1])
+    rng = np.random.default_rng(3)
+    table = (rng.random((ni + 1, 18)) < 0.2).astype(np.float32)
+    m1, m2 = model_from_golden(g).train(), model_from_golden(g).train()
+    t1 = _trainer(m1, g, use_cuda_graph=False)
+    t2 = _trainer(m2, g, use_cuda_graph=False, item_extra_table=torch.from_numpy(table))
+    l1 = t1.step_host(u, p, table[p], n, table[n])
+    l2 = t2.step_host(u, p, None, n, None)
+    assert l1 == l2
+    for k in m1.state_dict():
+        assert torch.equal(m1.state_dict()[k], m2.state_dict()[k])
+    assert t2.batch_bytes == 3 * len(u) * 8
+
+
+def test_full_size_step_properties():
+    """BASELINE config C2 (B = 8192, ML-1M-shape tables, D = 64, H = 128): size-independent properties."""
+    import recommendit_b200 as R
+    torch.manual_seed(0)
+    nu, ni, B = 6040, 3952, 8192
+    model = R.TwoTowerModel(nu, ni, 64, 128, dropout=0.0).cuda().train()
+    rng = np.random.default_rng(1)
+    u, p, n = rng.integers(1, nu + 1, B), rng.integers(1, ni + 1, B), rng.integers(1, ni + 1, B)
+    table = (rng.random((ni + 1, 18)) < 0.1).astype(np.float32)
+    P = {k: v.detach().cpu().numpy().copy() for k, v in model.state_dict().items()}
+    tr = R.FusedBPRTrainer(model, use_cuda_graph=True)
+    losses = [tr.step_host(u, p, table[p], n, table[n]) for _ in range(4)]
+    assert abs(losses[0] - np.log(2)) < 0.02                      # cosine scores of random towers ≈ 0
+    assert losses[3] < losses[0]                                  # same batch repeatedly ⇒ loss goes down
+    S = O.AdamState()
+    ref = [float(O.train_step(P, S, (u, p, table[p], n, table[n]))[0]) for _ in range(4)]
+    assert np.allclose(losses, ref, atol=5e-5), (losses, ref)
+    v = tr.views()
+    assert len(v["user_uniq_ids"]) == len(np.unique(u)) and len(v["item_uniq_ids"]) == len(np.unique(np.concatenate([p, n])))
+    st = tr.opt_state
+    assert st.step == 4 and 0 < st.clip_coef <= 1.0
+    tr.check_ids()
