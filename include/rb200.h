@@ -40,6 +40,9 @@ int rb200_sm_count(void);
 /* sizeof() of the ABI structs (0 tower_job, 1 tower_bwd_job, 2 opt_state, 3 step_params,
  * 4 step_views, 5 sumsq_seg) so that bindings can verify their mirrors */
 size_t rb200_sizeof(int which);
+/* kernels of this library launched so far by this process (host-side count; cub's internal launches
+ * and graph replays are not included) */
+uint64_t rb200_launch_count(void);
 
 /* ------------------------------------------------------------------------------------------ *
  * Towers — src/models/two_tower.py:39-42 (UserTower.forward) and :68-72 (ItemTower.forward)
@@ -216,6 +219,8 @@ typedef struct rb200_step_params {
     float* loss;        /* device scalar, also copied to opt->loss                               */
     int* err_flag;      /* optional                                                              */
     void* workspace; size_t workspace_bytes;
+    void* const* stage_events_host;   /* optional: 7 cudaEvent_t recorded at the stage boundaries
+                                         start | towers fwd | loss | towers bwd | scatter | clip | adam */
 } rb200_step_params;
 
 size_t rb200_bpr_step_workspace_bytes(int B, int D, int H, int extra_dim, int64_t n_user_rows,

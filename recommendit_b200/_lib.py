@@ -61,7 +61,7 @@ class StepParams(C.Structure):
                 ("dropout_p", C.c_float), ("seed", C.c_uint64),
                 ("keep_mask_user", c_f), ("keep_mask_pos", c_f), ("keep_mask_neg", c_f),
                 ("padding_idx", C.c_int64), ("loss", c_f), ("err_flag", c_f),
-                ("workspace", c_f), ("workspace_bytes", C.c_size_t)]
+                ("workspace", c_f), ("workspace_bytes", C.c_size_t), ("stage_events_host", c_f)]
 
 
 class StepViews(C.Structure):
@@ -78,6 +78,7 @@ SIGNATURES = {
     "rb200_last_error": (C.c_char_p, []),
     "rb200_sm_count": (I, []),
     "rb200_sizeof": (SZ, [I]),
+    "rb200_launch_count": (U64, []),
     "rb200_tower_fwd": (I, [C.POINTER(TowerJob), I, I, I, F, U64, U64, P, P, P]),
     "rb200_tower_bwd_workspace_bytes": (SZ, [I, I, I]),
     "rb200_tower_bwd": (I, [C.POINTER(TowerBwdJob), I, I, I, F, P, I, P, SZ, P]),

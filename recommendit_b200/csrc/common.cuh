@@ -21,8 +21,11 @@ int rb_set_error(int code, const char* fmt, ...);
                                 cudaGetErrorString(e__));                                         \
     } while (0)
 
+extern unsigned long long g_rb_launches;   // kernels of this library launched by this process (not cub's)
+
 #define RB_LAUNCH_CHECK(name)                                                                     \
     do {                                                                                          \
+        ++g_rb_launches;                                                                          \
         cudaError_t e__ = cudaGetLastError();                                                     \
         if (e__ != cudaSuccess)                                                                   \
             return rb_set_error(RB200_ERR_CUDA, "launch of %s failed: %s", name,                  \

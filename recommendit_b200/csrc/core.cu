@@ -4,6 +4,7 @@
 #include "common.cuh"
 
 static thread_local char g_err[1024] = "";
+unsigned long long g_rb_launches = 0;
 
 int rb_set_error(int code, const char* fmt, ...) {
     va_list ap;
@@ -31,6 +32,7 @@ int rb_max_smem_optin() { int s = dev_info().smem; return s > 0 ? s : 232448; }
 extern "C" int rb200_version(void) { return RB200_VERSION; }
 extern "C" const char* rb200_last_error(void) { return g_err; }
 extern "C" int rb200_sm_count(void) { return rb_sm_count(); }
+extern "C" uint64_t rb200_launch_count(void) { return g_rb_launches; }
 
 // sizeof() of the ABI structs, so that foreign-language bindings can verify their mirrors.
 extern "C" size_t rb200_sizeof(int which) {

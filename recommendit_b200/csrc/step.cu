@@ -112,6 +112,13 @@ extern "C" int rb200_bpr_step(const rb200_step_params* s, void* stream) {
     const int Pu = w.P_user, Pi = w.P_item;
     const int Din_i = D + E;
 
+    int ev_i = 0;
+#define RB_STAGE_EVENT()                                                                   \
+    do {                                                                                   \
+        if (s->stage_events_host) RB_CUDA(cudaEventRecord((cudaEvent_t)s->stage_events_host[ev_i], st)); \
+        ++ev_i;                                                                            \
+    } while (0)
+    RB_STAGE_EVENT();
     if ((rc = rb200_opt_begin_step(s->opt, st))) return rc;
 
     // ---- forward: user / positive / negative towers in one launch -------------------------- //
@@ -131,6 +138,7 @@ extern "C" int rb200_bpr_step(const rb200_step_params* s, void* stream) {
     }
     if ((rc = rb200_tower_fwd(fj, 1 + items, D, H, s->dropout_p, s->seed, 0, &s->opt->step, s->err_flag, st))) return rc;
 
+    RB_STAGE_EVENT();
     // ---- loss + gradient w.r.t. the tower outputs ------------------------------------------- //
     if (pair) rc = rb200_bpr_pair(w.u, w.p, w.n, B, D, s->loss, w.du, w.dpn, w.dpn + (size_t)B * D, 1.f, w.ws_loss, w.b_loss, st);
     else rc = rb200_bpr_inbatch(w.u, w.p, B, D, s->inbatch_mode, s->loss, w.du, w.dpn, 1.f, w.ws_loss, w.b_loss, st);
@@ -138,6 +146,7 @@ extern "C" int rb200_bpr_step(const rb200_step_params* s, void* stream) {
     copy_loss_kernel<<<1, 32, 0, st>>>(s->loss, s->opt);
     RB_LAUNCH_CHECK("copy_loss_kernel");
 
+    RB_STAGE_EVENT();
     // ---- backward through the towers ----------------------------------------------------------- //
     rb200_tower_bwd_job bj[2] = {};
     bj[0].table = s->user_table; bj[0].ids = s->user_ids; bj[0].extra = nullptr; bj[0].n_rows = s->n_user_rows; bj[0].B = B;
@@ -155,6 +164,7 @@ extern "C" int rb200_bpr_step(const rb200_step_params* s, void* stream) {
     }
     if ((rc = rb200_tower_bwd(bj, items, D, H, s->dropout_p, w.g_item_mlp, 0, w.ws_bwd, w.b_bwd, st))) return rc;
 
+    RB_STAGE_EVENT();
     // ---- sparse embedding gradients: deterministic sorted-segment sums ---------------------- //
     const bool dense = s->adam_mode == 0;
     RB_CUDA(cudaMemcpyAsync(w.ids_pn, s->pos_ids, sizeof(int64_t) * B, cudaMemcpyDeviceToDevice, st));
@@ -164,6 +174,7 @@ extern "C" int rb200_bpr_step(const rb200_step_params* s, void* stream) {
     if ((rc = rb200_scatter_rows(w.ids_pn, w.drows_pn, items * B, D, s->n_item_rows, s->padding_idx, nullptr, w.uniq_i, w.ug_i,
                                  w.n_uniq + 1, dense ? s->item_row_slot : nullptr, w.ws_scatter, w.b_scatter, st))) return rc;
 
+    RB_STAGE_EVENT();
     // ---- clip_grad_norm_(all parameters, 1.0) ---------------------------------------------------- //
     rb200_sumsq_seg segs[3] = {
         {w.g_user_mlp, (int64_t)Pu + Pi, nullptr, 0},
@@ -173,6 +184,7 @@ extern "C" int rb200_bpr_step(const rb200_step_params* s, void* stream) {
     if ((rc = rb200_sumsq_accumulate(s->opt, segs, 3, w.ws_sumsq, w.b_sumsq, st))) return rc;
     if ((rc = rb200_grad_norm_clip(s->opt, st))) return rc;
 
+    RB_STAGE_EVENT();
     // ---- Adam ---------------------------------------------------------------------------------- //
     if ((rc = rb200_adam_dense(s->user_mlp, w.g_user_mlp, s->user_mlp_m, s->user_mlp_v, Pu, s->opt, st))) return rc;
     if ((rc = rb200_adam_dense(s->item_mlp, w.g_item_mlp, s->item_mlp_m, s->item_mlp_v, Pi, s->opt, st))) return rc;
@@ -188,5 +200,7 @@ extern "C" int rb200_bpr_step(const rb200_step_params* s, void* stream) {
         if ((rc = rb200_adam_rows(s->item_table, s->item_table_m, s->item_table_v, D, w.uniq_i, w.ug_i, w.n_uniq + 1, items * B,
                                   s->opt, st))) return rc;
     }
+    RB_STAGE_EVENT();
+#undef RB_STAGE_EVENT
     return RB200_OK;
 }

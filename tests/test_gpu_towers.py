@@ -125,7 +125,7 @@ def test_inbatch_loss_ragged_sizes_vs_oracle(B, D):
 
 
 @pytest.mark.parametrize("B", [1, 5, 64, 77, 1024])
-@pytest.mark.parametrize("D,H", [(32, 64), (64, 128), (128, 128), (64, 256)])
+@pytest.mark.parametrize("D,H", [(32, 64), (64, 128), (128, 128), (32, 256)])
 def test_tower_shapes_vs_oracle(B, D, H):
     import recommendit_b200 as R
     torch.manual_seed(B + D + H)
@@ -186,3 +186,11 @@ def test_out_of_range_and_cpu_inputs_raise():
         model.user_tower(torch.tensor([1, 2]))                 # CPU ids on a CUDA model
     with pytest.raises(R.RB200Error):
         R.TwoTowerModel(10, 10, 48, 64).cuda().user_tower(torch.tensor([1], device="cuda"))   # unsupported width
+
+
+def test_width_outside_the_shared_memory_budget_is_refused():
+    """D=64, H=256 item tower needs 242 KB of shared memory (> 227 KB): a clear error, not a wrong answer."""
+    import recommendit_b200 as R
+    m = R.TwoTowerModel(10, 10, 64, 256).cuda()
+    with pytest.raises(R.RB200Error, match="shared memory"):
+        m.item_tower(torch.tensor([1], device="cuda"), torch.zeros(1, 18, device="cuda"))

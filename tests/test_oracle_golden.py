@@ -132,3 +132,20 @@ def test_clamped_normalize_backward():
     assert np.all(y == 0)
     dW1, db1, dW2, db2, dr = O.tower_backward(c, np.ones((2, 4), np.float32))
     assert np.allclose(db2, 2.0 / 1e-12)
+
+
+@pytest.mark.parametrize("case", ["tt_small", "tt_d128"])
+def test_torch_step_matches_reference_golden(golden, case):
+    """oracle/torch_step.py (the CPU-baseline arm) reproduces the reference trajectory bit-for-bit-ish: it issues the
+    same ATen calls."""
+    import torch
+    from oracle import torch_step as TS
+    g = golden(case)
+    T = TS.make_params({k: g["init/" + k] for k in O.PARAM_KEYS})
+    opt = TS.make_optimizer(T, lr=float(g["lr"]))
+    for s in range(int(g["meta"][5])):
+        b = tuple(torch.from_numpy(a) for a in _batch(g, s))
+        loss = TS.step(T, opt, b, dropout=0.0)
+        assert abs(loss - float(g[f"step{s}/loss"])) < 1e-6
+        for k in O.PARAM_KEYS:
+            np.testing.assert_allclose(T[k].detach().numpy(), g[f"step{s}/after/" + k], rtol=0, atol=1e-6)
