@@ -29,12 +29,12 @@ __device__ __forceinline__ double block_sum(double v, double* scratch /*[NT/32]*
     return t;   // valid on thread 0
 }
 
+// one warp: lane-strided sums + fixed shuffle tree (deterministic)
 __global__ void finalize_sum_kernel(const double* __restrict__ partials, int n, double scale, float* __restrict__ out) {
-    if (threadIdx.x == 0 && blockIdx.x == 0) {
-        double t = 0.0;
-        for (int i = 0; i < n; ++i) t += partials[i];
-        out[0] = (float)(t * scale);
-    }
+    double t = 0.0;
+    for (int i = threadIdx.x; i < n; i += 32) t += partials[i];
+    t = rb_warp_sum_d(t);
+    if (threadIdx.x == 0) out[0] = (float)(t * scale);
 }
 
 // ---------------------------------------------------------------------------------------- //

@@ -72,6 +72,135 @@ __global__ void reset_slots_kernel(const int64_t* __restrict__ uniq_ids, const i
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) row_slot[uniq_ids[i]] = -1;
 }
 
+
+// ---------------------------------------------------------------------------------------- //
+// Fast path (≤ 16384 sample-rows per table, i.e. every batch of BASELINE configs C1/C2/C4): ONE CTA per table
+// radix-sorts the (id, sample) pairs in shared memory (cub::BlockRadixSort), finds the segment heads, scans them and
+// emits [sorted sample positions | segment starts | unique ids | row slots] — 1 launch instead of 9.
+// ---------------------------------------------------------------------------------------- //
+constexpr int BS_THREADS = 1024;
+constexpr unsigned KEY_SENTINEL = 0xFFFFFFFFu;
+
+struct SortJob {
+    const int64_t* ids_a; const int64_t* ids_b; int n_a, n_b;   // the id list is the concatenation a ++ b
+    long long n_rows, padding_idx; int key_bits;
+    int* pos; int* seg_start; int64_t* uniq_ids; int* n_uniq; int* row_slot;
+};
+struct SortParams { SortJob job[2]; };
+
+template <int ITEMS>
+__global__ void __launch_bounds__(BS_THREADS, 1) block_sort_segments_kernel(const SortParams p) {
+    using Sort = cub::BlockRadixSort<unsigned, BS_THREADS, ITEMS, int>;
+    using Scan = cub::BlockScan<int, BS_THREADS>;
+    extern __shared__ __align__(16) unsigned char bs_smem[];
+    typename Sort::TempStorage& sort_tmp = *reinterpret_cast<typename Sort::TempStorage*>(bs_smem);
+    __shared__ typename Scan::TempStorage scan_tmp;
+    __shared__ unsigned last_key[BS_THREADS];
+    const SortJob& J = p.job[blockIdx.x];
+    const int n = J.n_a + J.n_b, tid = threadIdx.x;
+    unsigned keys[ITEMS];
+    int vals[ITEMS];
+#pragma unroll
+    for (int i = 0; i < ITEMS; ++i) {
+        const int idx = tid * ITEMS + i;
+        unsigned key = KEY_SENTINEL;
+        if (idx < n) {
+            const long long id = idx < J.n_a ? J.ids_a[idx] : J.ids_b[idx - J.n_a];
+            if (id != J.padding_idx && (unsigned long long)id < (unsigned long long)J.n_rows) key = (unsigned)id;
+        }
+        keys[i] = key;
+        vals[i] = idx;
+    }
+    // 2^key_bits > n_rows, so the sentinel's low bits (all ones) sort strictly after every valid id;
+    // the sort is stable ⇒ equal ids keep ascending sample order
+    Sort(sort_tmp).Sort(keys, vals, 0, J.key_bits);
+    last_key[tid] = keys[ITEMS - 1];
+    __syncthreads();
+    int heads = 0, valid = 0;
+    bool is_head[ITEMS];
+#pragma unroll
+    for (int i = 0; i < ITEMS; ++i) {
+        const unsigned prev = i > 0 ? keys[i - 1] : (tid > 0 ? last_key[tid - 1] : KEY_SENTINEL);
+        const bool v = keys[i] != KEY_SENTINEL;
+        is_head[i] = v && ((tid == 0 && i == 0) || keys[i] != prev);
+        heads += is_head[i];
+        valid += v;
+    }
+    int base, total, vbase, vtotal;
+    Scan(scan_tmp).ExclusiveSum(heads, base, total);
+    __syncthreads();
+    Scan(scan_tmp).ExclusiveSum(valid, vbase, vtotal);
+    (void)vbase;
+#pragma unroll
+    for (int i = 0; i < ITEMS; ++i) {
+        const int gi = tid * ITEMS + i;
+        if (gi < n) J.pos[gi] = vals[i];
+        if (is_head[i]) {
+            J.seg_start[base] = gi;
+            J.uniq_ids[base] = (int64_t)keys[i];
+            if (J.row_slot) J.row_slot[keys[i]] = base;
+            ++base;
+        }
+    }
+    if (tid == 0) {
+        J.seg_start[total] = vtotal;
+        J.n_uniq[0] = total;
+    }
+}
+
+struct SegJob {
+    const int* pos; const int* seg_start; const int64_t* uniq_ids; const int* n_uniq;
+    const float* rows; float* uniq_grads; float* dense; int cap;   // cap = upper bound of n_uniq (launch sizing)
+};
+struct SegParams { SegJob job[2]; int n_jobs; int D4; };
+
+// one warp per unique id: rows added in ascending sample order (deterministic)
+__global__ void __launch_bounds__(NT) segment_sum2_kernel(const SegParams p) {
+    int w = (blockIdx.x * NT + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    int j = 0;
+    if (p.n_jobs > 1 && w >= p.job[0].cap) { w -= p.job[0].cap; j = 1; }
+    const SegJob& J = p.job[j];
+    if (w >= J.n_uniq[0]) return;
+    const int beg = J.seg_start[w], end = J.seg_start[w + 1];
+    const int D4 = p.D4;
+    for (int c = lane; c < D4; c += 32) {
+        float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int k = beg; k < end; ++k) {
+            const float4 v = __ldg(reinterpret_cast<const float4*>(J.rows) + (long long)J.pos[k] * D4 + c);
+            s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+        }
+        if (J.uniq_grads) reinterpret_cast<float4*>(J.uniq_grads)[(long long)w * D4 + c] = s;
+        if (J.dense) {
+            float4* dp = reinterpret_cast<float4*>(J.dense) + J.uniq_ids[w] * D4 + c;
+            float4 o = *dp;
+            o.x += s.x; o.y += s.y; o.z += s.z; o.w += s.w;
+            *dp = o;
+        }
+    }
+}
+
+int key_bits_strict(long long n_rows) {     // smallest b with 2^b > n_rows
+    int b = 1;
+    while (b < 32 && (1ll << b) <= n_rows) ++b;
+    return b;
+}
+
+template <int ITEMS>
+int launch_block_sort(const SortParams& sp, int n_jobs, cudaStream_t st) {
+    using Sort = cub::BlockRadixSort<unsigned, BS_THREADS, ITEMS, int>;
+    const size_t smem = sizeof(typename Sort::TempStorage);
+    static bool attr_set = false;
+    if (!attr_set) {
+        if (smem > 48 * 1024)
+            RB_CUDA(cudaFuncSetAttribute(block_sort_segments_kernel<ITEMS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_set = true;
+    }
+    block_sort_segments_kernel<ITEMS><<<n_jobs, BS_THREADS, smem, st>>>(sp);
+    RB_LAUNCH_CHECK("block_sort_segments_kernel");
+    return RB200_OK;
+}
+
 int key_bits(long long n_rows) {
     int b = 1;
     while (b < 63 && (1ll << b) < n_rows) ++b;
@@ -133,11 +262,22 @@ __global__ void __launch_bounds__(NT) sumsq_kernel(const SumsqSegs segs, double*
     }
 }
 
-__global__ void sumsq_finalize_kernel(const double* __restrict__ partials, int n, rb200_opt_state* st) {
-    if (threadIdx.x || blockIdx.x) return;
-    double t = st->sumsq;
-    for (int i = 0; i < n; ++i) t += partials[i];
-    st->sumsq = t;
+// one warp: lane-strided partial sums, then a fixed shuffle tree (deterministic); optionally also the clip coefficient
+__global__ void sumsq_finalize_kernel(const double* __restrict__ partials, int n, rb200_opt_state* st, int do_clip) {
+    const int lane = threadIdx.x;
+    double t = 0.0;
+    for (int i = lane; i < n; i += 32) t += partials[i];
+    t = rb_warp_sum_d(t);
+    if (lane == 0) {
+        t += st->sumsq;
+        st->sumsq = t;
+        if (do_clip) {
+            const float total = (float)sqrt(t);
+            st->total_norm = total;
+            const float coef = st->max_norm / (total + 1e-6f);
+            st->clip_coef = coef < 1.f ? coef : 1.f;
+        }
+    }
 }
 
 __global__ void grad_norm_clip_kernel(rb200_opt_state* st) {
@@ -235,10 +375,52 @@ int stream_grid(long long work_items) {
 
 }  // namespace
 
+
+// Scratch needed by the fast path for one table of n sample-rows.
+static size_t fast_scratch_bytes(int n) { return 256 * 3 + sizeof(int) * (2 * (size_t)n + 2); }
+
+// Internal: up to two tables in two launches (sort+segments, then sums).  ids of a table may be the concatenation of
+// two arrays (positive ++ negative item ids).  Requires n ≤ 16384 and n_rows < 2^31 per table.
+int rb_scatter_tables(int n_tables, const int64_t* const ids_a[2], const int64_t* const ids_b[2], const int n_a[2],
+                      const int n_b[2], const float* const rows[2], int D, const long long n_rows[2], long long padding_idx,
+                      float* const dense[2], int64_t* const uniq_ids[2], float* const uniq_grads[2], int* const n_uniq[2],
+                      int* const row_slot[2], void* workspace, size_t workspace_bytes, cudaStream_t st) {
+    RbArena ar(workspace, workspace_bytes);
+    SortParams sp{};
+    SegParams gp{};
+    gp.n_jobs = n_tables; gp.D4 = D / 4;
+    int max_n = 0;
+    for (int t = 0; t < n_tables; ++t) {
+        const int n = n_a[t] + n_b[t];
+        if (n > max_n) max_n = n;
+        SortJob& J = sp.job[t];
+        J.ids_a = ids_a[t]; J.ids_b = ids_b[t]; J.n_a = n_a[t]; J.n_b = n_b[t];
+        J.n_rows = n_rows[t]; J.padding_idx = padding_idx; J.key_bits = key_bits_strict(n_rows[t]);
+        J.pos = ar.take<int>(n); J.seg_start = ar.take<int>((size_t)n + 1);
+        J.uniq_ids = uniq_ids[t]; J.n_uniq = n_uniq[t]; J.row_slot = row_slot[t];
+        SegJob& G = gp.job[t];
+        G.pos = J.pos; G.seg_start = J.seg_start; G.uniq_ids = J.uniq_ids; G.n_uniq = J.n_uniq;
+        G.rows = rows[t]; G.uniq_grads = uniq_grads[t]; G.dense = dense[t]; G.cap = n;
+    }
+    if (!workspace || !ar.ok()) return rb_set_error(RB200_ERR_WORKSPACE, "scatter: workspace too small (%zu given)", workspace_bytes);
+    int rc;
+    if (max_n <= BS_THREADS * 4) rc = launch_block_sort<4>(sp, n_tables, st);
+    else if (max_n <= BS_THREADS * 8) rc = launch_block_sort<8>(sp, n_tables, st);
+    else rc = launch_block_sort<16>(sp, n_tables, st);
+    if (rc) return rc;
+    long long warps = 0;
+    for (int t = 0; t < n_tables; ++t) warps += gp.job[t].cap;
+    segment_sum2_kernel<<<(unsigned)((warps * 32 + NT - 1) / NT), NT, 0, st>>>(gp);
+    RB_LAUNCH_CHECK("segment_sum2_kernel");
+    return RB200_OK;
+}
+
 extern "C" size_t rb200_scatter_workspace_bytes(int B, int64_t n_rows) {
     if (B < 1) B = 1;
-    return 256 * 6 + sizeof(int64_t) * (size_t)B + sizeof(int) * ((size_t)3 * B + 2 * ((size_t)B + 1)) +
-           sort_temp_bytes(B, key_bits(n_rows));
+    // (fast path additionally needs an int64 scratch for unique ids and an int for the count when the caller
+    //  asks only for the dense output)
+    return 256 * 8 + sizeof(int64_t) * (size_t)2 * B + sizeof(int) * ((size_t)3 * B + 2 * ((size_t)B + 1) + 2) +
+           fast_scratch_bytes(B) + sort_temp_bytes(B, key_bits(n_rows));
 }
 
 extern "C" int rb200_scatter_rows(const int64_t* ids, const float* rows, int B, int D, int64_t n_rows, int64_t padding_idx,
@@ -251,6 +433,20 @@ extern "C" int rb200_scatter_rows(const int64_t* ids, const float* rows, int B, 
     if (B == 0) {
         if (n_uniq) RB_CUDA(cudaMemsetAsync(n_uniq, 0, sizeof(int), st));
         return RB200_OK;
+    }
+    if (B <= BS_THREADS * 16 && n_rows < (1ll << 31)) {
+        // single-CTA sort fast path
+        RbArena fa(workspace, workspace_bytes);
+        int64_t* u_ids = uniq_ids ? uniq_ids : fa.take<int64_t>(B);
+        int* n_u = n_uniq ? n_uniq : fa.take<int>(1);
+        char* rest = fa.take<char>(fast_scratch_bytes(B));
+        if (!workspace || !fa.ok()) return rb_set_error(RB200_ERR_WORKSPACE, "scatter_rows: workspace too small (%zu given)", workspace_bytes);
+        const int64_t* ia[2] = {ids, nullptr}; const int64_t* ib[2] = {nullptr, nullptr};
+        const int na[2] = {B, 0}, nb[2] = {0, 0};
+        const float* rw[2] = {rows, nullptr}; const long long nr[2] = {n_rows, 0};
+        float* dn[2] = {dense_grad, nullptr}; int64_t* ui[2] = {u_ids, nullptr}; float* ug[2] = {uniq_grads, nullptr};
+        int* nu[2] = {n_u, nullptr}; int* rs[2] = {row_slot, nullptr};
+        return rb_scatter_tables(1, ia, ib, na, nb, rw, D, nr, padding_idx, dn, ui, ug, nu, rs, rest, fast_scratch_bytes(B), st);
     }
     const int bits = key_bits(n_rows);
     RbArena ar(workspace, workspace_bytes);
@@ -293,8 +489,17 @@ extern "C" int rb200_opt_begin_step(rb200_opt_state* st, void* stream) {
 
 extern "C" size_t rb200_sumsq_workspace_bytes(void) { return 256 + sizeof(double) * (size_t)rb_sm_count() * 4; }
 
+int rb_sumsq_accumulate(rb200_opt_state* st, const rb200_sumsq_seg* segs, int n_segs, int do_clip, void* workspace,
+                        size_t workspace_bytes, cudaStream_t s);
+
 extern "C" int rb200_sumsq_accumulate(rb200_opt_state* st, const rb200_sumsq_seg* segs, int n_segs, void* workspace,
                                       size_t workspace_bytes, void* stream) {
+    return rb_sumsq_accumulate(st, segs, n_segs, 0, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+// do_clip != 0 also finalises total_norm / clip_coef in the same launch (this must then be the last accumulate call)
+int rb_sumsq_accumulate(rb200_opt_state* st, const rb200_sumsq_seg* segs, int n_segs, int do_clip, void* workspace,
+                        size_t workspace_bytes, cudaStream_t s) {
     RB_REQUIRE(st && segs && n_segs >= 1 && n_segs <= 4, "sumsq_accumulate: 1..4 segments");
     RbArena ar(workspace, workspace_bytes);
     const int cap = rb_sm_count() * 4;
@@ -307,10 +512,9 @@ extern "C" int rb200_sumsq_accumulate(rb200_opt_state* st, const rb200_sumsq_seg
     int grid = (int)((n / 4 + NT - 1) / NT);
     if (grid > cap) grid = cap;
     if (grid < 1) grid = 1;
-    cudaStream_t s = (cudaStream_t)stream;
     sumsq_kernel<<<grid, NT, 0, s>>>(k, partials);
     RB_LAUNCH_CHECK("sumsq_kernel");
-    sumsq_finalize_kernel<<<1, 32, 0, s>>>(partials, grid, st);
+    sumsq_finalize_kernel<<<1, 32, 0, s>>>(partials, grid, st, do_clip);
     RB_LAUNCH_CHECK("sumsq_finalize_kernel");
     return RB200_OK;
 }

@@ -3,6 +3,13 @@
 // scatter_adam.cu on one stream.  No synchronisation, no allocation → CUDA-graph capturable.
 #include "common.cuh"
 
+int rb_scatter_tables(int n_tables, const int64_t* const ids_a[2], const int64_t* const ids_b[2], const int n_a[2],
+                      const int n_b[2], const float* const rows[2], int D, const long long n_rows[2], long long padding_idx,
+                      float* const dense[2], int64_t* const uniq_ids[2], float* const uniq_grads[2], int* const n_uniq[2],
+                      int* const row_slot[2], void* workspace, size_t workspace_bytes, cudaStream_t st);
+int rb_sumsq_accumulate(rb200_opt_state* st, const rb200_sumsq_seg* segs, int n_segs, int do_clip, void* workspace,
+                        size_t workspace_bytes, cudaStream_t s);
+
 namespace {
 
 struct StepWs {
@@ -44,7 +51,7 @@ bool carve(RbArena& ar, const rb200_step_params& s, StepWs& w) {
     w.b_loss = l0 > l1 ? l0 : l1;
     w.ws_loss = ar.take<char>(w.b_loss);
     const size_t s0 = rb200_scatter_workspace_bytes(s.B, s.n_user_rows), s1 = rb200_scatter_workspace_bytes(items * s.B, s.n_item_rows);
-    w.b_scatter = s0 > s1 ? s0 : s1;
+    w.b_scatter = s0 + s1;
     w.ws_scatter = ar.take<char>(w.b_scatter);
     w.b_sumsq = rb200_sumsq_workspace_bytes();
     w.ws_sumsq = ar.take<char>(w.b_sumsq);
@@ -167,12 +174,29 @@ extern "C" int rb200_bpr_step(const rb200_step_params* s, void* stream) {
     RB_STAGE_EVENT();
     // ---- sparse embedding gradients: deterministic sorted-segment sums ---------------------- //
     const bool dense = s->adam_mode == 0;
-    RB_CUDA(cudaMemcpyAsync(w.ids_pn, s->pos_ids, sizeof(int64_t) * B, cudaMemcpyDeviceToDevice, st));
-    if (pair) RB_CUDA(cudaMemcpyAsync(w.ids_pn + B, s->neg_ids, sizeof(int64_t) * B, cudaMemcpyDeviceToDevice, st));
-    if ((rc = rb200_scatter_rows(s->user_ids, w.drows_u, B, D, s->n_user_rows, s->padding_idx, nullptr, w.uniq_u, w.ug_u,
-                                 w.n_uniq, dense ? s->user_row_slot : nullptr, w.ws_scatter, w.b_scatter, st))) return rc;
-    if ((rc = rb200_scatter_rows(w.ids_pn, w.drows_pn, items * B, D, s->n_item_rows, s->padding_idx, nullptr, w.uniq_i, w.ug_i,
-                                 w.n_uniq + 1, dense ? s->item_row_slot : nullptr, w.ws_scatter, w.b_scatter, st))) return rc;
+    {
+        const int64_t* ia[2] = {s->user_ids, s->pos_ids};
+        const int64_t* ib[2] = {nullptr, pair ? s->neg_ids : nullptr};
+        const int na[2] = {B, B}, nb[2] = {0, pair ? B : 0};
+        const float* rw[2] = {w.drows_u, w.drows_pn};
+        const long long nr[2] = {s->n_user_rows, s->n_item_rows};
+        float* dn[2] = {nullptr, nullptr};
+        int64_t* ui[2] = {w.uniq_u, w.uniq_i};
+        float* ug[2] = {w.ug_u, w.ug_i};
+        int* nu[2] = {w.n_uniq, w.n_uniq + 1};
+        int* rs[2] = {dense ? s->user_row_slot : nullptr, dense ? s->item_row_slot : nullptr};
+        if (items * B <= 16384 && s->n_user_rows < (1ll << 31) && s->n_item_rows < (1ll << 31)) {
+            if ((rc = rb_scatter_tables(2, ia, ib, na, nb, rw, D, nr, s->padding_idx, dn, ui, ug, nu, rs, w.ws_scatter, w.b_scatter, st)))
+                return rc;
+        } else {
+            RB_CUDA(cudaMemcpyAsync(w.ids_pn, s->pos_ids, sizeof(int64_t) * B, cudaMemcpyDeviceToDevice, st));
+            if (pair) RB_CUDA(cudaMemcpyAsync(w.ids_pn + B, s->neg_ids, sizeof(int64_t) * B, cudaMemcpyDeviceToDevice, st));
+            if ((rc = rb200_scatter_rows(s->user_ids, w.drows_u, B, D, s->n_user_rows, s->padding_idx, nullptr, w.uniq_u, w.ug_u,
+                                         w.n_uniq, rs[0], w.ws_scatter, w.b_scatter, st))) return rc;
+            if ((rc = rb200_scatter_rows(w.ids_pn, w.drows_pn, items * B, D, s->n_item_rows, s->padding_idx, nullptr, w.uniq_i,
+                                         w.ug_i, w.n_uniq + 1, rs[1], w.ws_scatter, w.b_scatter, st))) return rc;
+        }
+    }
 
     RB_STAGE_EVENT();
     // ---- clip_grad_norm_(all parameters, 1.0) ---------------------------------------------------- //
@@ -181,8 +205,7 @@ extern "C" int rb200_bpr_step(const rb200_step_params* s, void* stream) {
         {w.ug_u, (int64_t)B * D, w.n_uniq, D},
         {w.ug_i, (int64_t)items * B * D, w.n_uniq + 1, D},
     };
-    if ((rc = rb200_sumsq_accumulate(s->opt, segs, 3, w.ws_sumsq, w.b_sumsq, st))) return rc;
-    if ((rc = rb200_grad_norm_clip(s->opt, st))) return rc;
+    if ((rc = rb_sumsq_accumulate(s->opt, segs, 3, 1, w.ws_sumsq, w.b_sumsq, st))) return rc;
 
     RB_STAGE_EVENT();
     // ---- Adam ---------------------------------------------------------------------------------- //

@@ -478,7 +478,8 @@ __global__ void reduce_partials_kernel(const float* __restrict__ part, int nspli
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= P) return;
     float s = 0.f;
-    for (int k = 0; k < nsplit; ++k) s += __ldg(part + (long long)k * P + i);
+#pragma unroll 8
+    for (int k = 0; k < nsplit; ++k) s += __ldg(part + (long long)k * P + i);   // fixed order; loads issued 8 deep
     out[i] = accumulate ? out[i] + s : s;
 }
 

@@ -124,9 +124,13 @@ class _IVFState:
         self.ntotal = n
         self.max_list_len = int((self.offsets[1:] - self.offsets[:-1]).max().item())
 
-    def search_device(self, q: torch.Tensor, k: int) -> Tuple[torch.Tensor, torch.Tensor]:
-        """q: normalised [nq, d] f32 on the device → (scores [nq,k] f32, rows [nq,k] i64), -FLT_MAX / -1 padded."""
+    def search_device(self, q: torch.Tensor, k: int, id_table: Optional[torch.Tensor] = None
+                      ) -> Tuple[torch.Tensor, torch.Tensor]:
+        """q: normalised [nq, d] f32 on the device → (scores [nq,k] f32, rows [nq,k] i64), -FLT_MAX / -1 padded.
+        ``id_table`` (list-contiguous, same order as ``list_ids``) makes the kernel emit those ids instead of
+        internal row numbers."""
         lib = _lib.load()
+        ids_src = self.list_ids if id_table is None else id_table
         nq = q.shape[0]
         nprobe = max(1, min(int(self.nprobe), self.nlist))
         pb = lib.rb200_ivf_plan_workspace_bytes(nq, self.nlist, nprobe)
@@ -138,7 +142,7 @@ class _IVFState:
         ws = workspace(wb, q.device)
         scores = torch.empty(nq, k, dtype=torch.float32, device=q.device)
         rows = torch.empty(nq, k, dtype=torch.int64, device=q.device)
-        check(lib.rb200_ivf_search_run(ptr(q), nq, self.d, self.nlist, nprobe, ptr(self.offsets), ptr(self.list_ids),
+        check(lib.rb200_ivf_search_run(ptr(q), nq, self.d, self.nlist, nprobe, ptr(self.offsets), ptr(ids_src),
                                        ptr(self.list_vecs), self.max_list_len, k, ptr(plan), pb, total.value, mx.value,
                                        ptr(scores), ptr(rows), ptr(ws), wb, stream_ptr()), "rb200_ivf_search_run")
         return scores, rows
@@ -190,34 +194,47 @@ class FAISSIndex:
         self.index = st
         self.item_ids = np.array(item_ids, dtype=np.int64)
         self._item_id_to_faiss_idx = {int(iid): idx for idx, iid in enumerate(item_ids)}
+        self._bind_item_ids()
         logger.info("IVF index built: %d vectors, %d lists, probe=%d", st.ntotal, self.n_lists, self.n_probe)
+
+    def _bind_item_ids(self) -> None:
+        """internal row → item id (faiss_index.py:76, :118-123, :147-152) folded into the index: the list entries carry the
+        item id, so the top-k kernel emits catalog ids directly and no per-search host mapping is needed."""
+        st = self.index
+        ids_dev = torch.as_tensor(np.asarray(self.item_ids, dtype=np.int64), device=st.list_ids.device)
+        self._list_item_ids = ids_dev[st.list_ids].contiguous()
 
     # ---- search (faiss_index.py:88-153) ------------------------------------------------------ #
     def _search_normalised(self, queries: np.ndarray, k: int):
+        """host queries → (scores, item ids) as host arrays; -FLT_MAX / -1 padded.  Results come back through pinned
+        buffers from torch's pinned caching allocator (one async D2H each)."""
         st = self.index
         dev = st.centroids.device
         with torch.cuda.device(dev):
             q = _normalize_device(torch.as_tensor(np.ascontiguousarray(queries, dtype=np.float32), device=dev))
-            s, r = st.search_device(q, k)
-            return s.cpu().numpy(), r.cpu().numpy()
+            s, r = st.search_device(q, k, id_table=self._list_item_ids)
+            hs = torch.empty(s.shape, dtype=s.dtype, pin_memory=True)
+            hr = torch.empty(r.shape, dtype=r.dtype, pin_memory=True)
+            hs.copy_(s, non_blocking=True)
+            hr.copy_(r, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+            return hs.numpy(), hr.numpy()
 
     def search(self, query_vector: np.ndarray, k: int = 500) -> Tuple[np.ndarray, np.ndarray]:
         if self.index is None:
             raise RuntimeError("Index not built. Call build_ivf_index() first.")
         query = np.atleast_2d(query_vector).astype(np.float32)
         k = min(k, self.index.ntotal)
-        distances, rows = self._search_normalised(query[:1], k)     # like the reference, only row 0 is used (:115-116)
-        distances, rows = distances[0], rows[0]
-        valid = rows >= 0
-        return distances[valid], self.item_ids[rows[valid]]
+        distances, ids = self._search_normalised(query[:1], k)      # like the reference, only row 0 is used (:115-116)
+        distances, ids = distances[0], ids[0]
+        valid = ids >= 0 if (self.item_ids >= 0).all() else distances > -3e38
+        return distances[valid].copy(), ids[valid].copy()
 
     def batch_search(self, query_vectors: np.ndarray, k: int = 500) -> Tuple[np.ndarray, np.ndarray]:
         if self.index is None:
             raise RuntimeError("Index not built.")
         k = min(k, self.index.ntotal)
-        distances, rows = self._search_normalised(query_vectors.astype(np.float32), k)
-        mapped = np.where(rows >= 0, self.item_ids[np.clip(rows, 0, len(self.item_ids) - 1)], -1)
-        return distances, mapped
+        return self._search_normalised(query_vectors, k)                # padding slots already carry id -1
 
     # ---- persistence (faiss_index.py:159-205) ---------------------------------------------- #
     def save(self, path: str) -> None:
@@ -261,6 +278,7 @@ class FAISSIndex:
         obj.index = st
         obj.item_ids = meta["item_ids"]
         obj._item_id_to_faiss_idx = meta["item_id_to_faiss_idx"]
+        obj._bind_item_ids()
         logger.info("Loaded IVF index from %s: %d vectors, dim=%d", load_path, st.ntotal, obj.embed_dim)
         return obj
 
