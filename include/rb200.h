@@ -142,6 +142,13 @@ int rb200_scatter_rows(const int64_t* ids, const float* rows, int B, int D, int6
                        void* stream);
 int rb200_scatter_reset_slots(const int64_t* uniq_ids, const int* n_uniq, int max_uniq, int* row_slot,
                               void* stream);
+/* row_slot[uniq_ids[i]] = i for i < n_uniq[0] (when the compact list was produced without a slot map) */
+int rb200_scatter_set_slots(const int64_t* uniq_ids, const int* n_uniq, int max_uniq, int* row_slot,
+                            void* stream);
+/* out[i,:] = table[rows[i],:] — the owner-side row gather of row-sharded tables; rows outside
+ * [0, n_table_rows) yield zeros */
+int rb200_gather_rows(const float* table, const int64_t* rows, int64_t n, int D, int64_t n_table_rows,
+                      float* out, void* stream);
 
 /* ------------------------------------------------------------------------------------------ *
  * clip_grad_norm_ + Adam — src/training/train_embeddings.py:160,191-192

@@ -89,6 +89,8 @@ SIGNATURES = {
     "rb200_scatter_workspace_bytes": (SZ, [I, I64]),
     "rb200_scatter_rows": (I, [P, P, I, I, I64, I64, P, P, P, P, P, P, SZ, P]),
     "rb200_scatter_reset_slots": (I, [P, P, I, P, P]),
+    "rb200_scatter_set_slots": (I, [P, P, I, P, P]),
+    "rb200_gather_rows": (I, [P, P, I64, I, I64, P, P]),
     "rb200_opt_begin_step": (I, [P, P]),
     "rb200_sumsq_accumulate": (I, [P, C.POINTER(SumsqSeg), I, P, SZ, P]),
     "rb200_sumsq_workspace_bytes": (SZ, []),

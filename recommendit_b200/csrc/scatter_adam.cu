@@ -67,6 +67,25 @@ __global__ void __launch_bounds__(NT) segment_sum_kernel(const int64_t* __restri
     }
 }
 
+__global__ void set_slots_kernel(const int64_t* __restrict__ uniq_ids, const int* __restrict__ n_uniq, int* __restrict__ row_slot) {
+    const int n = n_uniq[0];
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) row_slot[uniq_ids[i]] = i;
+}
+
+// out[i] = table[rows[i]] — plain coalesced 128-bit row gather (row-sharded tables: owners serve the requested rows)
+__global__ void __launch_bounds__(NT) gather_rows_kernel(const float* __restrict__ table, const int64_t* __restrict__ rows,
+                                                         long long n, int D4, long long n_table_rows, float* __restrict__ out) {
+    const long long total = n * D4, stride = (long long)gridDim.x * NT;
+    for (long long i = (long long)blockIdx.x * NT + threadIdx.x; i < total; i += stride) {
+        const long long r = i / D4;
+        const int c = (int)(i - r * D4);
+        long long src = rows[r];
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if ((unsigned long long)src < (unsigned long long)n_table_rows) v = __ldg(reinterpret_cast<const float4*>(table) + src * D4 + c);
+        reinterpret_cast<float4*>(out)[i] = v;
+    }
+}
+
 __global__ void reset_slots_kernel(const int64_t* __restrict__ uniq_ids, const int* __restrict__ n_uniq, int* __restrict__ row_slot) {
     const int n = n_uniq[0];
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) row_slot[uniq_ids[i]] = -1;
@@ -379,39 +398,63 @@ int stream_grid(long long work_items) {
 // Scratch needed by the fast path for one table of n sample-rows.
 static size_t fast_scratch_bytes(int n) { return 256 * 3 + sizeof(int) * (2 * (size_t)n + 2); }
 
-// Internal: up to two tables in two launches (sort+segments, then sums).  ids of a table may be the concatenation of
-// two arrays (positive ++ negative item ids).  Requires n ≤ 16384 and n_rows < 2^31 per table.
-int rb_scatter_tables(int n_tables, const int64_t* const ids_a[2], const int64_t* const ids_b[2], const int n_a[2],
-                      const int n_b[2], const float* const rows[2], int D, const long long n_rows[2], long long padding_idx,
-                      float* const dense[2], int64_t* const uniq_ids[2], float* const uniq_grads[2], int* const n_uniq[2],
-                      int* const row_slot[2], void* workspace, size_t workspace_bytes, cudaStream_t st) {
+// Internal: up to two tables.  Phase 1 (rb_scatter_sort) depends only on the ids, so the fused step runs it on a side
+// stream concurrently with the towers; phase 2 (rb_scatter_sum) needs the row gradients.  ids of a table may be the
+// concatenation of two arrays (positive ++ negative item ids).  Requires n ≤ 16384 and n_rows < 2^31 per table.
+struct ScatterPlan { SortParams sp; SegParams gp; int max_n; };
+
+static int scatter_plan(ScatterPlan& pl, int n_tables, const int64_t* const ids_a[2], const int64_t* const ids_b[2],
+                        const int n_a[2], const int n_b[2], const float* const rows[2], int D, const long long n_rows[2],
+                        long long padding_idx, float* const dense[2], int64_t* const uniq_ids[2], float* const uniq_grads[2],
+                        int* const n_uniq[2], int* const row_slot[2], void* workspace, size_t workspace_bytes) {
     RbArena ar(workspace, workspace_bytes);
-    SortParams sp{};
-    SegParams gp{};
-    gp.n_jobs = n_tables; gp.D4 = D / 4;
-    int max_n = 0;
+    pl.sp = SortParams{};
+    pl.gp = SegParams{};
+    pl.gp.n_jobs = n_tables; pl.gp.D4 = D / 4;
+    pl.max_n = 0;
     for (int t = 0; t < n_tables; ++t) {
         const int n = n_a[t] + n_b[t];
-        if (n > max_n) max_n = n;
-        SortJob& J = sp.job[t];
+        if (n > pl.max_n) pl.max_n = n;
+        SortJob& J = pl.sp.job[t];
         J.ids_a = ids_a[t]; J.ids_b = ids_b[t]; J.n_a = n_a[t]; J.n_b = n_b[t];
         J.n_rows = n_rows[t]; J.padding_idx = padding_idx; J.key_bits = key_bits_strict(n_rows[t]);
         J.pos = ar.take<int>(n); J.seg_start = ar.take<int>((size_t)n + 1);
         J.uniq_ids = uniq_ids[t]; J.n_uniq = n_uniq[t]; J.row_slot = row_slot[t];
-        SegJob& G = gp.job[t];
+        SegJob& G = pl.gp.job[t];
         G.pos = J.pos; G.seg_start = J.seg_start; G.uniq_ids = J.uniq_ids; G.n_uniq = J.n_uniq;
         G.rows = rows[t]; G.uniq_grads = uniq_grads[t]; G.dense = dense[t]; G.cap = n;
     }
     if (!workspace || !ar.ok()) return rb_set_error(RB200_ERR_WORKSPACE, "scatter: workspace too small (%zu given)", workspace_bytes);
-    int rc;
-    if (max_n <= BS_THREADS * 4) rc = launch_block_sort<4>(sp, n_tables, st);
-    else if (max_n <= BS_THREADS * 8) rc = launch_block_sort<8>(sp, n_tables, st);
-    else rc = launch_block_sort<16>(sp, n_tables, st);
-    if (rc) return rc;
+    return RB200_OK;
+}
+
+static int scatter_sort(const ScatterPlan& pl, cudaStream_t st) {
+    const int nt = pl.gp.n_jobs;
+    if (pl.max_n <= BS_THREADS * 4) return launch_block_sort<4>(pl.sp, nt, st);
+    if (pl.max_n <= BS_THREADS * 8) return launch_block_sort<8>(pl.sp, nt, st);
+    return launch_block_sort<16>(pl.sp, nt, st);
+}
+
+static int scatter_sum(const ScatterPlan& pl, cudaStream_t st) {
     long long warps = 0;
-    for (int t = 0; t < n_tables; ++t) warps += gp.job[t].cap;
-    segment_sum2_kernel<<<(unsigned)((warps * 32 + NT - 1) / NT), NT, 0, st>>>(gp);
+    for (int t = 0; t < pl.gp.n_jobs; ++t) warps += pl.gp.job[t].cap;
+    segment_sum2_kernel<<<(unsigned)((warps * 32 + NT - 1) / NT), NT, 0, st>>>(pl.gp);
     RB_LAUNCH_CHECK("segment_sum2_kernel");
+    return RB200_OK;
+}
+
+// sort_stream == sum_stream ⇒ plain sequential execution.  Otherwise the caller has already made sort_stream wait for
+// the ids and must make sum_stream wait for the sort (see csrc/step.cu).
+int rb_scatter_tables(int phase, int n_tables, const int64_t* const ids_a[2], const int64_t* const ids_b[2], const int n_a[2],
+                      const int n_b[2], const float* const rows[2], int D, const long long n_rows[2], long long padding_idx,
+                      float* const dense[2], int64_t* const uniq_ids[2], float* const uniq_grads[2], int* const n_uniq[2],
+                      int* const row_slot[2], void* workspace, size_t workspace_bytes, cudaStream_t st) {
+    ScatterPlan pl;
+    int rc = scatter_plan(pl, n_tables, ids_a, ids_b, n_a, n_b, rows, D, n_rows, padding_idx, dense, uniq_ids, uniq_grads, n_uniq,
+                          row_slot, workspace, workspace_bytes);
+    if (rc) return rc;
+    if (phase == 0 || phase == 1) { if ((rc = scatter_sort(pl, st))) return rc; }
+    if (phase == 0 || phase == 2) { if ((rc = scatter_sum(pl, st))) return rc; }
     return RB200_OK;
 }
 
@@ -446,7 +489,7 @@ extern "C" int rb200_scatter_rows(const int64_t* ids, const float* rows, int B, 
         const float* rw[2] = {rows, nullptr}; const long long nr[2] = {n_rows, 0};
         float* dn[2] = {dense_grad, nullptr}; int64_t* ui[2] = {u_ids, nullptr}; float* ug[2] = {uniq_grads, nullptr};
         int* nu[2] = {n_u, nullptr}; int* rs[2] = {row_slot, nullptr};
-        return rb_scatter_tables(1, ia, ib, na, nb, rw, D, nr, padding_idx, dn, ui, ug, nu, rs, rest, fast_scratch_bytes(B), st);
+        return rb_scatter_tables(0, 1, ia, ib, na, nb, rw, D, nr, padding_idx, dn, ui, ug, nu, rs, rest, fast_scratch_bytes(B), st);
     }
     const int bits = key_bits(n_rows);
     RbArena ar(workspace, workspace_bytes);
@@ -477,6 +520,23 @@ extern "C" int rb200_scatter_reset_slots(const int64_t* uniq_ids, const int* n_u
     if (max_uniq <= 0) return RB200_OK;
     reset_slots_kernel<<<stream_grid(max_uniq), NT, 0, (cudaStream_t)stream>>>(uniq_ids, n_uniq, row_slot);
     RB_LAUNCH_CHECK("reset_slots_kernel");
+    return RB200_OK;
+}
+
+extern "C" int rb200_scatter_set_slots(const int64_t* uniq_ids, const int* n_uniq, int max_uniq, int* row_slot, void* stream) {
+    RB_REQUIRE(uniq_ids && n_uniq && row_slot, "scatter_set_slots: NULL pointer");
+    if (max_uniq <= 0) return RB200_OK;
+    set_slots_kernel<<<stream_grid(max_uniq), NT, 0, (cudaStream_t)stream>>>(uniq_ids, n_uniq, row_slot);
+    RB_LAUNCH_CHECK("set_slots_kernel");
+    return RB200_OK;
+}
+
+extern "C" int rb200_gather_rows(const float* table, const int64_t* rows, int64_t n, int D, int64_t n_table_rows, float* out,
+                                 void* stream) {
+    RB_REQUIRE(table && rows && out && n >= 0 && D >= 4 && D % 4 == 0, "gather_rows: bad arguments");
+    if (n == 0) return RB200_OK;
+    gather_rows_kernel<<<stream_grid(n * (D / 4)), NT, 0, (cudaStream_t)stream>>>(table, rows, n, D / 4, n_table_rows, out);
+    RB_LAUNCH_CHECK("gather_rows_kernel");
     return RB200_OK;
 }
 

@@ -3,7 +3,7 @@
 // scatter_adam.cu on one stream.  No synchronisation, no allocation → CUDA-graph capturable.
 #include "common.cuh"
 
-int rb_scatter_tables(int n_tables, const int64_t* const ids_a[2], const int64_t* const ids_b[2], const int n_a[2],
+int rb_scatter_tables(int phase, int n_tables, const int64_t* const ids_a[2], const int64_t* const ids_b[2], const int n_a[2],
                       const int n_b[2], const float* const rows[2], int D, const long long n_rows[2], long long padding_idx,
                       float* const dense[2], int64_t* const uniq_ids[2], float* const uniq_grads[2], int* const n_uniq[2],
                       int* const row_slot[2], void* workspace, size_t workspace_bytes, cudaStream_t st);
@@ -56,6 +56,24 @@ bool carve(RbArena& ar, const rb200_step_params& s, StepWs& w) {
     w.b_sumsq = rb200_sumsq_workspace_bytes();
     w.ws_sumsq = ar.take<char>(w.b_sumsq);
     return ar.ok();
+}
+
+// Library-owned side stream + events for the fork/join inside the step (capturable: the side stream joins the capture
+// through the event dependencies).
+struct SideStream { cudaStream_t s = nullptr; cudaEvent_t fork = nullptr, join = nullptr; };
+int side_stream(SideStream** out) {
+    static thread_local SideStream per_dev[64];
+    int dev = 0;
+    RB_CUDA(cudaGetDevice(&dev));
+    RB_REQUIRE(dev >= 0 && dev < 64, "bad device index");
+    SideStream& ss = per_dev[dev];
+    if (!ss.s) {
+        RB_CUDA(cudaStreamCreateWithFlags(&ss.s, cudaStreamNonBlocking));
+        RB_CUDA(cudaEventCreateWithFlags(&ss.fork, cudaEventDisableTiming));
+        RB_CUDA(cudaEventCreateWithFlags(&ss.join, cudaEventDisableTiming));
+    }
+    *out = &ss;
+    return RB200_OK;
 }
 
 __global__ void copy_loss_kernel(const float* loss, rb200_opt_state* st) {
@@ -128,6 +146,29 @@ extern "C" int rb200_bpr_step(const rb200_step_params* s, void* stream) {
     RB_STAGE_EVENT();
     if ((rc = rb200_opt_begin_step(s->opt, st))) return rc;
 
+    // ---- fork: the (id, sample) sort needs only the ids, so it runs on a side stream under the towers ------- //
+    const bool dense = s->adam_mode == 0;
+    const int64_t* sc_ia[2] = {s->user_ids, s->pos_ids};
+    const int64_t* sc_ib[2] = {nullptr, pair ? s->neg_ids : nullptr};
+    const int sc_na[2] = {B, B}, sc_nb[2] = {0, pair ? B : 0};
+    const float* sc_rw[2] = {w.drows_u, w.drows_pn};
+    const long long sc_nr[2] = {s->n_user_rows, s->n_item_rows};
+    float* sc_dn[2] = {nullptr, nullptr};
+    int64_t* sc_ui[2] = {w.uniq_u, w.uniq_i};
+    float* sc_ug[2] = {w.ug_u, w.ug_i};
+    int* sc_nu[2] = {w.n_uniq, w.n_uniq + 1};
+    int* sc_rs[2] = {dense ? s->user_row_slot : nullptr, dense ? s->item_row_slot : nullptr};
+    const bool fast_scatter = items * B <= 16384 && s->n_user_rows < (1ll << 31) && s->n_item_rows < (1ll << 31);
+    SideStream* side = nullptr;
+    if (fast_scatter) {
+        if ((rc = side_stream(&side))) return rc;
+        RB_CUDA(cudaEventRecord(side->fork, st));
+        RB_CUDA(cudaStreamWaitEvent(side->s, side->fork, 0));
+        if ((rc = rb_scatter_tables(1, 2, sc_ia, sc_ib, sc_na, sc_nb, sc_rw, D, sc_nr, s->padding_idx, sc_dn, sc_ui, sc_ug, sc_nu,
+                                    sc_rs, w.ws_scatter, w.b_scatter, side->s))) return rc;
+        RB_CUDA(cudaEventRecord(side->join, side->s));
+    }
+
     // ---- forward: user / positive / negative towers in one launch -------------------------- //
     rb200_tower_job fj[3] = {};
     fj[0].table = s->user_table; fj[0].ids = s->user_ids; fj[0].extra = nullptr; fj[0].extra_dim = 0;
@@ -173,29 +214,17 @@ extern "C" int rb200_bpr_step(const rb200_step_params* s, void* stream) {
 
     RB_STAGE_EVENT();
     // ---- sparse embedding gradients: deterministic sorted-segment sums ---------------------- //
-    const bool dense = s->adam_mode == 0;
-    {
-        const int64_t* ia[2] = {s->user_ids, s->pos_ids};
-        const int64_t* ib[2] = {nullptr, pair ? s->neg_ids : nullptr};
-        const int na[2] = {B, B}, nb[2] = {0, pair ? B : 0};
-        const float* rw[2] = {w.drows_u, w.drows_pn};
-        const long long nr[2] = {s->n_user_rows, s->n_item_rows};
-        float* dn[2] = {nullptr, nullptr};
-        int64_t* ui[2] = {w.uniq_u, w.uniq_i};
-        float* ug[2] = {w.ug_u, w.ug_i};
-        int* nu[2] = {w.n_uniq, w.n_uniq + 1};
-        int* rs[2] = {dense ? s->user_row_slot : nullptr, dense ? s->item_row_slot : nullptr};
-        if (items * B <= 16384 && s->n_user_rows < (1ll << 31) && s->n_item_rows < (1ll << 31)) {
-            if ((rc = rb_scatter_tables(2, ia, ib, na, nb, rw, D, nr, s->padding_idx, dn, ui, ug, nu, rs, w.ws_scatter, w.b_scatter, st)))
-                return rc;
-        } else {
-            RB_CUDA(cudaMemcpyAsync(w.ids_pn, s->pos_ids, sizeof(int64_t) * B, cudaMemcpyDeviceToDevice, st));
-            if (pair) RB_CUDA(cudaMemcpyAsync(w.ids_pn + B, s->neg_ids, sizeof(int64_t) * B, cudaMemcpyDeviceToDevice, st));
-            if ((rc = rb200_scatter_rows(s->user_ids, w.drows_u, B, D, s->n_user_rows, s->padding_idx, nullptr, w.uniq_u, w.ug_u,
-                                         w.n_uniq, rs[0], w.ws_scatter, w.b_scatter, st))) return rc;
-            if ((rc = rb200_scatter_rows(w.ids_pn, w.drows_pn, items * B, D, s->n_item_rows, s->padding_idx, nullptr, w.uniq_i,
-                                         w.ug_i, w.n_uniq + 1, rs[1], w.ws_scatter, w.b_scatter, st))) return rc;
-        }
+    if (fast_scatter) {
+        RB_CUDA(cudaStreamWaitEvent(st, side->join, 0));      // join: sorted positions / segment starts are ready
+        if ((rc = rb_scatter_tables(2, 2, sc_ia, sc_ib, sc_na, sc_nb, sc_rw, D, sc_nr, s->padding_idx, sc_dn, sc_ui, sc_ug, sc_nu,
+                                    sc_rs, w.ws_scatter, w.b_scatter, st))) return rc;
+    } else {
+        RB_CUDA(cudaMemcpyAsync(w.ids_pn, s->pos_ids, sizeof(int64_t) * B, cudaMemcpyDeviceToDevice, st));
+        if (pair) RB_CUDA(cudaMemcpyAsync(w.ids_pn + B, s->neg_ids, sizeof(int64_t) * B, cudaMemcpyDeviceToDevice, st));
+        if ((rc = rb200_scatter_rows(s->user_ids, w.drows_u, B, D, s->n_user_rows, s->padding_idx, nullptr, w.uniq_u, w.ug_u,
+                                     w.n_uniq, sc_rs[0], w.ws_scatter, w.b_scatter, st))) return rc;
+        if ((rc = rb200_scatter_rows(w.ids_pn, w.drows_pn, items * B, D, s->n_item_rows, s->padding_idx, nullptr, w.uniq_i,
+                                     w.ug_i, w.n_uniq + 1, sc_rs[1], w.ws_scatter, w.b_scatter, st))) return rc;
     }
 
     RB_STAGE_EVENT();

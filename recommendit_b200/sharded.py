@@ -1,0 +1,374 @@
+"""Row-sharded two-tower training and sharded retrieval over one NVLink/NVSwitch box (BASELINE configs C4 and C5).
+
+The reference is single-process; this is the scaled form of the same step: one process per GPU,
+``torch.distributed`` (NCCL) for the plumbing, the kernels of ``librb200.so`` for the arithmetic.
+
+Training step on rank r, local batch of B samples, tables sharded by ``owner(id) = id % world``,
+``local_row(id) = id // world`` (modulo sharding flattens Zipf-skewed id popularity):
+
+  1. bucket the batch's ids by owner (stable)                         → all-to-all: ids to their owners
+  2. owners gather the requested rows (``rb200_gather_rows``)          → all-to-all: rows back
+  3. towers fwd → ``bpr_loss`` → towers bwd on the local batch; the received row buffer acts as the "embedding
+     table" and the inverse bucket permutation as the "ids", so no un-permute copy is needed
+  4. row gradients in bucket order                                    → all-to-all: gradients to the owners
+  5. owners: deterministic sorted-segment sum per local row; MLP gradients all-reduced (sum; every rank scales its
+     loss gradient by 1/world so the sum is the gradient of the global-batch mean)
+  6. Σg² partials + loss all-reduced → global clip coefficient → Adam on the local shards and on the replicated MLPs
+
+The global result is independent of ``world`` up to fp32 summation order (tests/test_sharded_gloo.py checks it against
+the single-process oracle on the concatenated batch).
+
+Retrieval (C5): database rows sharded contiguously, queries replicated, per-shard ``rb200_flat_search`` top-k,
+all-gather of ``(score, id)[nq, k]``, ``rb200_topk_merge``.
+
+``ops`` is the arithmetic back end.  The product uses ``CudaOps`` (C ABI).  It is a parameter only so that the
+host-side exchange logic can be exercised on CPU/gloo in the tests with a stand-in built on the oracle.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from dataclasses import dataclass
+from typing import Dict, List, Optional, Tuple
+
+import torch
+import torch.distributed as dist
+
+from . import _lib
+from ._lib import OptState, SumsqSeg, TowerBwdJob, TowerJob, check, ptr, stream_ptr, workspace
+
+
+# --------------------------------------------------------------------------------------------------------- #
+# exchange plan (pure index arithmetic: runs wherever the tensors live)
+# --------------------------------------------------------------------------------------------------------- #
+@dataclass
+class Route:
+    perm: torch.Tensor          # [n] bucket order → sample index (stable by owner)
+    inv: torch.Tensor           # [n] sample index → position in bucket order
+    local_rows: torch.Tensor    # [n] local row of each request, bucket order
+    send_counts: List[int]      # requests per owner
+    recv_counts: List[int] = None
+    recv_rows: torch.Tensor = None   # local rows requested from this rank, grouped by source
+
+
+def make_route(ids: torch.Tensor, world: int) -> Route:
+    owner = ids % world
+    perm = torch.argsort(owner, stable=True)
+    inv = torch.empty_like(perm)
+    inv[perm] = torch.arange(ids.numel(), device=ids.device, dtype=perm.dtype)
+    counts = torch.bincount(owner, minlength=world)
+    return Route(perm=perm, inv=inv, local_rows=torch.div(ids, world, rounding_mode="floor")[perm].contiguous(),
+                 send_counts=[int(c) for c in counts.tolist()])
+
+
+def shard_rows(n_rows: int, world: int, rank: int) -> int:
+    """rows of a table with global ids 0..n_rows-1 owned by ``rank`` under modulo sharding"""
+    return (n_rows - rank + world - 1) // world if n_rows > rank else 0
+
+
+def all_to_all_counts(send_counts: List[int], group, device) -> List[int]:
+    s = torch.tensor(send_counts, dtype=torch.int64, device=device)
+    r = torch.empty_like(s)
+    dist.all_to_all_single(r, s, group=group)
+    return [int(c) for c in r.tolist()]
+
+
+def all_to_all_var(send: torch.Tensor, send_counts: List[int], recv_counts: List[int], group) -> torch.Tensor:
+    out = torch.empty((sum(recv_counts),) + tuple(send.shape[1:]), dtype=send.dtype, device=send.device)
+    dist.all_to_all_single(out, send.contiguous(), output_split_sizes=recv_counts, input_split_sizes=send_counts, group=group)
+    return out
+
+
+# --------------------------------------------------------------------------------------------------------- #
+# arithmetic back end over the C ABI
+# --------------------------------------------------------------------------------------------------------- #
+class CudaOps:
+    """Thin, allocation-only wrappers over ``librb200.so`` (device tensors in, device tensors out)."""
+
+    def __init__(self):
+        self.lib = _lib.load()
+
+    def gather_rows(self, table: torch.Tensor, rows: torch.Tensor) -> torch.Tensor:
+        out = torch.empty(rows.numel(), table.shape[1], dtype=torch.float32, device=table.device)
+        if rows.numel():
+            check(self.lib.rb200_gather_rows(ptr(table), ptr(rows), rows.numel(), table.shape[1], table.shape[0], ptr(out),
+                                             stream_ptr()), "rb200_gather_rows")
+        return out
+
+    def towers_fwd(self, jobs: List[dict], D: int, H: int, drop_p: float, seed: int, offset: int) -> None:
+        arr = (TowerJob * len(jobs))()
+        for i, j in enumerate(jobs):
+            arr[i] = TowerJob(ptr(j["table"]), ptr(j["ids"]), ptr(j.get("extra")), ptr(j["W1"]), ptr(j["b1"]), ptr(j["W2"]),
+                              ptr(j["b2"]), ptr(j["out"]), ptr(j["hid"]), ptr(j["denom"]), None, j["table"].shape[0],
+                              j["ids"].numel(), 0 if j.get("extra") is None else j["extra"].shape[1], 0)
+        check(self.lib.rb200_tower_fwd(arr, len(jobs), D, H, drop_p, seed, offset, None, None, stream_ptr()), "rb200_tower_fwd")
+
+    def bpr_pair(self, u, p, n, grad_scale: float):
+        B, D = u.shape
+        loss = torch.empty(1, dtype=torch.float32, device=u.device)
+        du, dp, dn = torch.empty_like(u), torch.empty_like(p), torch.empty_like(n)
+        wsb = self.lib.rb200_bpr_pair_workspace_bytes(B)
+        ws = workspace(wsb, u.device)
+        check(self.lib.rb200_bpr_pair(ptr(u), ptr(p), ptr(n), B, D, ptr(loss), ptr(du), ptr(dp), ptr(dn), grad_scale, ptr(ws), wsb,
+                                      stream_ptr()), "rb200_bpr_pair")
+        return loss, du, dp, dn
+
+    def towers_bwd(self, jobs: List[dict], D: int, H: int, drop_p: float, grads_out: torch.Tensor) -> None:
+        arr = (TowerBwdJob * len(jobs))()
+        E = 0 if jobs[0].get("extra") is None else jobs[0]["extra"].shape[1]
+        for i, j in enumerate(jobs):
+            arr[i] = TowerBwdJob(ptr(j["table"]), ptr(j["ids"]), ptr(j.get("extra")), j["table"].shape[0], j["ids"].numel(), E, 0,
+                                 ptr(j["W1"]), ptr(j["W2"]), ptr(j["dY"]), ptr(j["out"]), ptr(j["denom"]), ptr(j["hid"]),
+                                 ptr(j["dpre"]), ptr(j["dact"]), ptr(j["dRows"]))
+        wsb = self.lib.rb200_tower_bwd_workspace_bytes(D, H, E)
+        ws = workspace(wsb, grads_out.device)
+        check(self.lib.rb200_tower_bwd(arr, len(jobs), D, H, drop_p, ptr(grads_out), 0, ptr(ws), wsb, stream_ptr()), "rb200_tower_bwd")
+
+    def scatter_rows(self, ids: torch.Tensor, rows: torch.Tensor, n_rows: int, padding_row: int):
+        """→ (uniq_ids [cap], uniq_grads [cap, D], n_uniq [1] int32), deterministic; ``padding_row`` < 0 ⇒ none"""
+        B, D = rows.shape
+        cap = max(B, 1)
+        uniq = torch.empty(cap, dtype=torch.int64, device=rows.device)
+        ug = torch.empty(cap, D, dtype=torch.float32, device=rows.device)
+        nu = torch.zeros(1, dtype=torch.int32, device=rows.device)
+        if B:
+            wsb = self.lib.rb200_scatter_workspace_bytes(B, n_rows)
+            ws = workspace(wsb, rows.device)
+            check(self.lib.rb200_scatter_rows(ptr(ids), ptr(rows), B, D, n_rows, padding_row, None, ptr(uniq), ptr(ug), ptr(nu), None,
+                                              ptr(ws), wsb, stream_ptr()), "rb200_scatter_rows")
+        return uniq, ug, nu
+
+    def sumsq(self, opt: torch.Tensor, segs: List[Tuple[torch.Tensor, Optional[torch.Tensor], int]]) -> None:
+        """opt.sumsq += Σ x² ; a segment is (tensor, count tensor or None, row_len)"""
+        wsb = self.lib.rb200_sumsq_workspace_bytes()
+        ws = workspace(wsb, opt.device)
+        for i in range(0, len(segs), 4):
+            chunk = segs[i:i + 4]
+            arr = (SumsqSeg * 4)()
+            for k, (t, cnt, rl) in enumerate(chunk):
+                arr[k] = SumsqSeg(ptr(t), t.numel(), ptr(cnt), rl)
+            check(self.lib.rb200_sumsq_accumulate(ptr(opt), arr, len(chunk), ptr(ws), wsb, stream_ptr()), "rb200_sumsq_accumulate")
+
+    def begin_step(self, opt: torch.Tensor) -> None:
+        check(self.lib.rb200_opt_begin_step(ptr(opt), stream_ptr()), "rb200_opt_begin_step")
+
+    def adam_dense(self, w, g, m, v, opt) -> None:
+        check(self.lib.rb200_adam_dense(ptr(w), ptr(g), ptr(m), ptr(v), w.numel(), ptr(opt), stream_ptr()), "rb200_adam_dense")
+
+    def adam_rows(self, w, m, v, uniq, ug, nu, opt) -> None:
+        check(self.lib.rb200_adam_rows(ptr(w), ptr(m), ptr(v), w.shape[1], ptr(uniq), ptr(ug), ptr(nu), uniq.numel(), ptr(opt),
+                                       stream_ptr()), "rb200_adam_rows")
+
+    def adam_table_dense(self, w, m, v, uniq, ug, nu, slot, opt) -> None:
+        """dense (reference-exact) mode: slots are set from the compact list, every row updated, slots reset"""
+        check(self.lib.rb200_scatter_set_slots(ptr(uniq), ptr(nu), uniq.numel(), ptr(slot), stream_ptr()), "rb200_scatter_set_slots")
+        check(self.lib.rb200_adam_table_dense(ptr(w), ptr(m), ptr(v), w.shape[0], w.shape[1], ptr(slot), ptr(ug), ptr(opt),
+                                              stream_ptr()), "rb200_adam_table_dense")
+        check(self.lib.rb200_scatter_reset_slots(ptr(uniq), ptr(nu), uniq.numel(), ptr(slot), stream_ptr()), "rb200_scatter_reset_slots")
+
+    # host <-> device mirror of rb200_opt_state
+    def read_opt(self, opt: torch.Tensor) -> OptState:
+        return OptState.from_buffer_copy(bytes(opt.cpu().numpy().tobytes()))
+
+    def write_opt(self, opt: torch.Tensor, st: OptState) -> None:
+        opt.copy_(torch.frombuffer(bytearray(bytes(st)), dtype=torch.uint8))
+
+
+# --------------------------------------------------------------------------------------------------------- #
+# the sharded trainer
+# --------------------------------------------------------------------------------------------------------- #
+class ShardedBPRTrainer:
+    """Two-tower BPR training with row-sharded embedding tables (BASELINE config C4)."""
+
+    def __init__(self, n_users: int, n_items: int, embed_dim: int = 128, hidden_dim: int = 128, n_genres: int = 18,
+                 lr: float = 1e-3, betas=(0.9, 0.999), eps: float = 1e-8, weight_decay: float = 1e-5, max_norm: float = 1.0,
+                 adam_mode: str = "rows", device=None, group=None, ops=None, seed: int = 0, init: Optional[Dict] = None):
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.dev = torch.device(device if device is not None else ("cuda", torch.cuda.current_device()))
+        self.ops = ops if ops is not None else CudaOps()
+        self.D, self.H, self.E = embed_dim, hidden_dim, n_genres
+        self.n_user_rows, self.n_item_rows = n_users + 1, n_items + 1
+        self.adam_mode = adam_mode
+        f32 = dict(dtype=torch.float32, device=self.dev)
+        W, r = self.world, self.rank
+        nu, ni = shard_rows(self.n_user_rows, W, r), shard_rows(self.n_item_rows, W, r)
+        if init is not None:
+            # parity runs: slice a full (single-process) state dict
+            self.user_table = init["user_tower.embedding.weight"][r::W].to(**f32).contiguous()
+            self.item_table = init["item_tower.embedding.weight"][r::W].to(**f32).contiguous()
+            flat = lambda t: torch.cat([init[f"{t}_tower.mlp.0.weight"].reshape(-1), init[f"{t}_tower.mlp.0.bias"].reshape(-1),
+                                        init[f"{t}_tower.mlp.3.weight"].reshape(-1), init[f"{t}_tower.mlp.3.bias"].reshape(-1)])
+            self.user_mlp, self.item_mlp = flat("user").to(**f32).contiguous(), flat("item").to(**f32).contiguous()
+        else:
+            # counter-based init on the device, same bounds as the reference (xavier-uniform tables incl. row 0,
+            # U(±1/√fan_in) Linear layers); MLPs use one seed on every rank (replicated), tables a per-rank seed
+            g = torch.Generator(device=self.dev).manual_seed(seed * 1000 + 17 + r)
+            a_u, a_i = math.sqrt(6.0 / (self.n_user_rows + embed_dim)), math.sqrt(6.0 / (self.n_item_rows + embed_dim))
+            self.user_table = (torch.rand(nu, embed_dim, generator=g, **f32) * 2 - 1) * a_u
+            self.item_table = (torch.rand(ni, embed_dim, generator=g, **f32) * 2 - 1) * a_i
+            g2 = torch.Generator(device=self.dev).manual_seed(seed * 1000 + 3)
+
+            def mlp(din):
+                parts = [(torch.rand(hidden_dim * din, generator=g2, **f32) * 2 - 1) / math.sqrt(din),
+                         (torch.rand(hidden_dim, generator=g2, **f32) * 2 - 1) / math.sqrt(din),
+                         (torch.rand(embed_dim * hidden_dim, generator=g2, **f32) * 2 - 1) / math.sqrt(hidden_dim),
+                         (torch.rand(embed_dim, generator=g2, **f32) * 2 - 1) / math.sqrt(hidden_dim)]
+                return torch.cat(parts).contiguous()
+            self.user_mlp, self.item_mlp = mlp(embed_dim), mlp(embed_dim + n_genres)
+        self.state = {k: torch.zeros_like(getattr(self, k)) for k in ("user_table", "item_table", "user_mlp", "item_mlp")}
+        self.state_v = {k: torch.zeros_like(getattr(self, k)) for k in ("user_table", "item_table", "user_mlp", "item_mlp")}
+        self.user_slot = torch.full((max(nu, 1),), -1, dtype=torch.int32, device=self.dev) if adam_mode == "dense" else None
+        self.item_slot = torch.full((max(ni, 1),), -1, dtype=torch.int32, device=self.dev) if adam_mode == "dense" else None
+        st = OptState()
+        st.lr, st.beta1, st.beta2, st.eps, st.weight_decay, st.max_norm = lr, betas[0], betas[1], eps, weight_decay, max_norm
+        st.one_minus_beta1, st.one_minus_beta2, st.beta2_f, st.clip_coef = 1 - betas[0], 1 - betas[1], betas[1], 1.0
+        self.opt = torch.zeros(128, dtype=torch.uint8, device=self.dev)
+        self._opt_host = st
+        self.ops.write_opt(self.opt, st)
+        self.steps = 0
+        self.max_norm = max_norm
+
+    # views of the flat MLP blocks
+    def _mlp_views(self, flat: torch.Tensor, din: int):
+        H, D = self.H, self.D
+        o = 0
+        W1 = flat[o:o + H * din]; o += H * din
+        b1 = flat[o:o + H]; o += H
+        W2 = flat[o:o + D * H]; o += D * H
+        b2 = flat[o:o + D]
+        return W1, b1, W2, b2
+
+    def _fetch(self, table: torch.Tensor, ids: torch.Tensor):
+        """steps 1-2: route ids to owners, gather there, bring the rows back (bucket order)"""
+        rt = make_route(ids, self.world)
+        if self.world == 1:
+            rt.recv_counts, rt.recv_rows = rt.send_counts, rt.local_rows
+            return rt, self.ops.gather_rows(table, rt.local_rows)
+        rt.recv_counts = all_to_all_counts(rt.send_counts, self.group, ids.device)
+        rt.recv_rows = all_to_all_var(rt.local_rows, rt.send_counts, rt.recv_counts, self.group)
+        served = self.ops.gather_rows(table, rt.recv_rows)
+        return rt, all_to_all_var(served, rt.recv_counts, rt.send_counts, self.group)
+
+    def _return_grads(self, rt: Route, drows: torch.Tensor) -> torch.Tensor:
+        """step 4: row gradients (sample order) → bucket order → owners"""
+        sorted_rows = self.ops.gather_rows(drows, rt.perm)
+        if self.world == 1:
+            return sorted_rows
+        return all_to_all_var(sorted_rows, rt.send_counts, rt.recv_counts, self.group)
+
+    def step(self, user_ids, pos_ids, pos_genres, neg_ids, neg_genres) -> torch.Tensor:
+        """One optimiser step on this rank's local batch (device tensors).  Returns the global mean loss (device scalar)."""
+        ops, D, H, E, W = self.ops, self.D, self.H, self.E, self.world
+        B = user_ids.numel()
+        dev = user_ids.device
+        f32 = dict(dtype=torch.float32, device=dev)
+        item_ids = torch.cat([pos_ids, neg_ids])
+        rt_u, rows_u = self._fetch(self.user_table, user_ids)
+        rt_i, rows_i = self._fetch(self.item_table, item_ids)
+        ops.begin_step(self.opt)
+
+        uW1, ub1, uW2, ub2 = self._mlp_views(self.user_mlp, D)
+        iW1, ib1, iW2, ib2 = self._mlp_views(self.item_mlp, D + E)
+        out = torch.empty(3 * B, D, **f32)
+        hid = torch.empty(3 * B, H, **f32)
+        den = torch.empty(3 * B, **f32)
+        inv_p, inv_n = rt_i.inv[:B].contiguous(), rt_i.inv[B:].contiguous()
+        jobs = [
+            dict(table=rows_u, ids=rt_u.inv, extra=None, W1=uW1, b1=ub1, W2=uW2, b2=ub2, out=out[:B], hid=hid[:B], denom=den[:B]),
+            dict(table=rows_i, ids=inv_p, extra=pos_genres, W1=iW1, b1=ib1, W2=iW2, b2=ib2, out=out[B:2 * B], hid=hid[B:2 * B], denom=den[B:2 * B]),
+            dict(table=rows_i, ids=inv_n, extra=neg_genres, W1=iW1, b1=ib1, W2=iW2, b2=ib2, out=out[2 * B:], hid=hid[2 * B:], denom=den[2 * B:]),
+        ]
+        ops.towers_fwd(jobs, D, H, 0.0, 0, self.steps)
+        loss, du, dp, dn = ops.bpr_pair(out[:B], out[B:2 * B], out[2 * B:], 1.0 / W)
+
+        dpre, dact, drows = torch.empty(3 * B, D, **f32), torch.empty(3 * B, H, **f32), torch.empty(3 * B, D, **f32)
+        Pu, Pi = self.user_mlp.numel(), self.item_mlp.numel()
+        g_mlp = torch.empty(Pu + Pi, **f32)
+        for j, dY, sl in ((jobs[0], du, slice(0, B)), (jobs[1], dp, slice(B, 2 * B)), (jobs[2], dn, slice(2 * B, 3 * B))):
+            j.update(dY=dY, dpre=dpre[sl], dact=dact[sl], dRows=drows[sl])
+        ops.towers_bwd(jobs[:1], D, H, 0.0, g_mlp[:Pu])
+        ops.towers_bwd(jobs[1:], D, H, 0.0, g_mlp[Pu:])
+
+        # step 4-5: gradients back to the owning shards, deterministic segment sums there
+        gu = self._return_grads(rt_u, drows[:B])
+        gi = self._return_grads(rt_i, drows[B:])
+        pad_u = 0 if self.rank == 0 else -1          # global padding id 0 lives on rank 0 as local row 0
+        uq_u, ug_u, nu_u = ops.scatter_rows(rt_u.recv_rows, gu, max(self.user_table.shape[0], 1), pad_u)
+        uq_i, ug_i, nu_i = ops.scatter_rows(rt_i.recv_rows, gi, max(self.item_table.shape[0], 1), pad_u)
+        if W > 1:
+            dist.all_reduce(g_mlp, group=self.group)                       # Σ over ranks of (1/W)-scaled local gradients
+        # step 6: global gradient norm.  Table shards are disjoint → their Σg² add up; the MLP gradient is replicated →
+        # counted once (on rank 0).
+        segs = [(ug_u, nu_u, D), (ug_i, nu_i, D)]
+        if self.rank == 0:
+            segs.append((g_mlp, None, 0))
+        ops.sumsq(self.opt, segs)
+        st = ops.read_opt(self.opt)                                            # (host sync; scalars only)
+        red = torch.tensor([st.sumsq, float(loss.item()) / W], dtype=torch.float64, device=dev)
+        if W > 1:
+            dist.all_reduce(red, group=self.group)
+        total = math.sqrt(float(red[0].item()))
+        st.sumsq, st.total_norm = float(red[0].item()), total
+        st.clip_coef = min(1.0, self.max_norm / (total + 1e-6))
+        st.loss = float(red[1].item())
+        ops.write_opt(self.opt, st)
+
+        ops.adam_dense(self.user_mlp, g_mlp[:Pu], self.state["user_mlp"], self.state_v["user_mlp"], self.opt)
+        ops.adam_dense(self.item_mlp, g_mlp[Pu:], self.state["item_mlp"], self.state_v["item_mlp"], self.opt)
+        if self.adam_mode == "dense":
+            ops.adam_table_dense(self.user_table, self.state["user_table"], self.state_v["user_table"], uq_u, ug_u, nu_u, self.user_slot, self.opt)
+            ops.adam_table_dense(self.item_table, self.state["item_table"], self.state_v["item_table"], uq_i, ug_i, nu_i, self.item_slot, self.opt)
+        else:
+            ops.adam_rows(self.user_table, self.state["user_table"], self.state_v["user_table"], uq_u, ug_u, nu_u, self.opt)
+            ops.adam_rows(self.item_table, self.state["item_table"], self.state_v["item_table"], uq_i, ug_i, nu_i, self.opt)
+        self.steps += 1
+        return torch.tensor(st.loss, **f32)
+
+    def full_state(self) -> Dict[str, torch.Tensor]:
+        """Gather the shards into a single-process ``state_dict`` layout on every rank (tests / checkpoints)."""
+        W, D = self.world, self.D
+        out = {}
+        for name, local, n_rows in (("user", self.user_table, self.n_user_rows), ("item", self.item_table, self.n_item_rows)):
+            full = torch.zeros(n_rows, D, dtype=torch.float32, device=self.dev)
+            if W == 1:
+                full.copy_(local)
+            else:
+                rows_max = shard_rows(n_rows, W, 0)
+                pad = torch.zeros(rows_max, D, dtype=torch.float32, device=self.dev)
+                pad[: local.shape[0]] = local
+                parts = [torch.empty_like(pad) for _ in range(W)]
+                dist.all_gather(parts, pad, group=self.group)
+                for r in range(W):
+                    full[r::W] = parts[r][: shard_rows(n_rows, W, r)]
+            out[f"{name}_tower.embedding.weight"] = full
+        for name, flat, din in (("user", self.user_mlp, D), ("item", self.item_mlp, D + self.E)):
+            W1, b1, W2, b2 = self._mlp_views(flat, din)
+            out[f"{name}_tower.mlp.0.weight"] = W1.view(self.H, din).clone()
+            out[f"{name}_tower.mlp.0.bias"] = b1.clone()
+            out[f"{name}_tower.mlp.3.weight"] = W2.view(D, self.H).clone()
+            out[f"{name}_tower.mlp.3.bias"] = b2.clone()
+        return out
+
+
+# --------------------------------------------------------------------------------------------------------- #
+# sharded exhaustive retrieval (C5)
+# --------------------------------------------------------------------------------------------------------- #
+def sharded_flat_search(queries: torch.Tensor, local_db: torch.Tensor, k: int, id_base: int, group=None, search=None, merge=None
+                        ) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Per-shard top-k + all-gather + merge.  ``local_db`` holds rows [id_base, id_base + n_local); every rank passes
+    the same queries and gets the same global top-k.  Shards must be ordered by rank (rank r's ids below rank r+1's)
+    so that ties resolve to the lower id, as in the unsharded search."""
+    from .faiss_index import flat_search, topk_merge
+    search = search or flat_search
+    merge = merge or topk_merge
+    s, i = search(queries, local_db, k, id_base)
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    if world == 1:
+        return s, i
+    ss = [torch.empty_like(s) for _ in range(world)]
+    ii = [torch.empty_like(i) for _ in range(world)]
+    dist.all_gather(ss, s.contiguous(), group=group)
+    dist.all_gather(ii, i.contiguous(), group=group)
+    return merge(torch.stack(ss), torch.stack(ii))
