@@ -262,46 +262,25 @@ int sort_rows_by_list(const int* assign, long long n, int nlist, SortWs& w, cuda
 // ------------------------------------------------------------------------------------------ //
 // search, step 2: top-nprobe lists per query (one CTA per query) + candidate bookkeeping
 // ------------------------------------------------------------------------------------------ //
-__global__ void __launch_bounds__(NT) probe_select_kernel(const float* __restrict__ coarse, int nlist, int nprobe,
+// After the generic top-k kernel picked the nprobe best lists per query (score desc, list id asc): candidate
+// bookkeeping, one thread per query.
+__global__ void __launch_bounds__(NT) probe_finish_kernel(const int64_t* __restrict__ probe_ids, int nq, int nprobe,
                                                           const int64_t* __restrict__ offsets, int* __restrict__ probes,
                                                           int* __restrict__ cand_base, long long* __restrict__ totals,
                                                           int* __restrict__ list_qcount) {
-    extern __shared__ float sc[];                  // [nlist]
-    __shared__ float wv[NT / 32];
-    __shared__ int wi[NT / 32];
-    const int q = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    for (int i = tid; i < nlist; i += NT) sc[i] = coarse[(long long)q * nlist + i];
-    __syncthreads();
+    const int q = blockIdx.x * NT + threadIdx.x;
+    if (q >= nq) return;
     long long total = 0;
     for (int p = 0; p < nprobe; ++p) {
-        float bv = -FLT_MAX; int bi = 0x7fffffff;
-        for (int i = tid; i < nlist; i += NT) {
-            const float v = sc[i];
-            if (v > bv || (v == bv && i < bi)) { bv = v; bi = i; }   // i ascending per thread: strict > keeps lowest
+        const long long l = probe_ids[(long long)q * nprobe + p];
+        probes[(long long)q * nprobe + p] = (int)l;
+        cand_base[(long long)q * nprobe + p] = (int)total;
+        if (l >= 0) {
+            total += offsets[l + 1] - offsets[l];
+            atomicAdd(list_qcount + l, 1);
         }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            const float ov = __shfl_xor_sync(RB_FULL_MASK, bv, o);
-            const int oi = __shfl_xor_sync(RB_FULL_MASK, bi, o);
-            if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
-        }
-        if (lane == 0) { wv[warp] = bv; wi[warp] = bi; }
-        __syncthreads();
-        if (tid == 0) {
-            for (int w = 1; w < NT / 32; ++w)
-                if (wv[w] > bv || (wv[w] == bv && wi[w] < bi)) { bv = wv[w]; bi = wi[w]; }
-            if (bi >= nlist) bi = -1;                                  // fewer than nprobe scorable lists
-            probes[(long long)q * nprobe + p] = bi;
-            cand_base[(long long)q * nprobe + p] = (int)total;
-            if (bi >= 0) {
-                total += offsets[bi + 1] - offsets[bi];
-                sc[bi] = -INFINITY;                                    // never picked again (-inf < -FLT_MAX)
-                atomicAdd(list_qcount + bi, 1);
-            }
-        }
-        __syncthreads();
-        }
-    if (tid == 0) totals[q] = total;
+    }
+    totals[q] = total;
 }
 
 __global__ void pair_keys_kernel(const int* __restrict__ probes, long long n_pairs, int nlist, int* __restrict__ keys,
@@ -387,6 +366,7 @@ __device__ __forceinline__ float key2f(uint32_t k) {
 struct ResolveIvf {      // candidate position → (probe, offset in list) → list_ids
     const int* probes; const int* cand_base; const int64_t* offsets; const int64_t* list_ids; int nprobe;
 };
+struct ResolveIdentity { int unused; };   // candidate position is the id (coarse quantizer: list number)
 struct ResolveFlat {     // [running top-k (kprev entries) | chunk rows]
     const int64_t* prev_ids; int kprev; long long row_base;
 };
@@ -406,6 +386,7 @@ template <> __device__ long long resolve_id<ResolveIvf>(const ResolveIvf& r, int
     const int l = r.probes[(long long)q * r.nprobe + p];
     return r.list_ids[r.offsets[l] + (c - base[p])];
 }
+template <> __device__ long long resolve_id<ResolveIdentity>(const ResolveIdentity&, int, int c) { return c; }
 template <> __device__ long long resolve_id<ResolveFlat>(const ResolveFlat& r, int q, int c) {
     if (c < r.kprev) return r.prev_ids[(long long)q * r.kprev + c];
     return r.row_base + (c - r.kprev);
@@ -446,9 +427,17 @@ __global__ void __launch_bounds__(NT) select_topk_kernel(const float* __restrict
         for (int shift = 24; shift >= 0; shift -= 8) {
             hist[tid] = 0;
             __syncthreads();
-            for (int i = tid; i < n; i += NT) {
-                const uint32_t key = f2key(src[i]);
-                if ((key & mask) == prefix) atomicAdd(&hist[(key >> shift) & 255u], 1);
+            // warp-aggregated: the leading digits of cosine scores are heavily skewed (a few exponent values), so
+            // lanes holding the same digit elect one leader that adds their count — no same-bin atomic storms
+            for (int base = 0; base < n; base += NT) {
+                const int i = base + tid;
+                uint32_t digit = 0xFFFFFFFFu;
+                if (i < n) {
+                    const uint32_t key = f2key(src[i]);
+                    if ((key & mask) == prefix) digit = (key >> shift) & 255u;
+                }
+                const uint32_t peers = __match_any_sync(RB_FULL_MASK, digit);
+                if (digit != 0xFFFFFFFFu && lane == __ffs(peers) - 1) atomicAdd(&hist[digit], __popc(peers));
             }
             __syncthreads();
             if (tid == 0) {
@@ -557,6 +546,7 @@ __global__ void __launch_bounds__(NT) merge_gather_kernel(const float* __restric
 struct PlanLayout {
     float* coarse; int* probes; int* cand_base; long long* totals; long long* cand_off; long long* tot2;
     int* list_qcount; int* list_qstart; int* pair_keys; int* pair_vals; int* pair_keys_sorted; int* pair_qp;
+    float* probe_scores; int64_t* probe_ids;
     char* temp; size_t temp_bytes;
 };
 size_t plan_temp_bytes(int nq, int nlist, int nprobe) {
@@ -577,6 +567,7 @@ bool carve_plan(RbArena& ar, int nq, int nlist, int nprobe, PlanLayout& L) {
     L.list_qcount = ar.take<int>((size_t)nlist + 2); L.list_qstart = ar.take<int>((size_t)nlist + 2);
     L.pair_keys = ar.take<int>(np); L.pair_vals = ar.take<int>(np);
     L.pair_keys_sorted = ar.take<int>(np); L.pair_qp = ar.take<int>(np);
+    L.probe_scores = ar.take<float>(np); L.probe_ids = ar.take<int64_t>(np);
     L.temp_bytes = plan_temp_bytes(nq, nlist, nprobe);
     L.temp = ar.take<char>(L.temp_bytes);
     return ar.ok();
@@ -648,7 +639,7 @@ extern "C" int rb200_ivf_build(const float* x, int64_t n, int D, const int32_t* 
 
 extern "C" size_t rb200_ivf_plan_workspace_bytes(int nq, int nlist, int nprobe) {
     const size_t np = (size_t)nq * nprobe;
-    return 256 * 16 + sizeof(float) * (size_t)nq * nlist + sizeof(int) * (6 * np + 2 * ((size_t)nlist + 2)) +
+    return 256 * 18 + sizeof(float) * ((size_t)nq * nlist + np) + sizeof(int64_t) * np + sizeof(int) * (6 * np + 2 * ((size_t)nlist + 2)) +
            sizeof(long long) * (2 * ((size_t)nq + 1) + 2) + plan_temp_bytes(nq, nlist, nprobe);
 }
 
@@ -657,7 +648,7 @@ extern "C" int rb200_ivf_search_plan(const float* q, int nq, int D, const float*
                                      int64_t* total_candidates_host, int64_t* max_candidates_host, void* stream) {
     RB_REQUIRE(q && centroids && offsets && nq >= 1 && nlist >= 1 && nprobe >= 1 && nprobe <= nlist, "ivf_search_plan: bad arguments");
     RB_REQUIRE(total_candidates_host && max_candidates_host, "ivf_search_plan: NULL host outputs");
-    RB_REQUIRE((size_t)nlist * 4 <= 200 * 1024, "ivf_search_plan: nlist=%d too large for the probe-select kernel", nlist);
+    RB_REQUIRE(nprobe <= 2048, "ivf_search_plan: nprobe must be <= 2048");
     cudaStream_t st = (cudaStream_t)stream;
     RbArena ar(plan_ws, plan_ws_bytes);
     PlanLayout L;
@@ -666,14 +657,15 @@ extern "C" int rb200_ivf_search_plan(const float* q, int nq, int D, const float*
     RB_DISPATCH_D(D, RB_TILE_LAUNCH(dense_scores_kernel, DD, g, st, q, nq, centroids, nlist, L.coarse, nlist, 0));
     RB_LAUNCH_CHECK("dense_scores_kernel");
     RB_CUDA(cudaMemsetAsync(L.list_qcount, 0, sizeof(int) * ((size_t)nlist + 2), st));
-    const size_t ps_smem = sizeof(float) * (size_t)nlist;
-    static size_t ps_attr = 0;
-    if (ps_smem > 48 * 1024 && ps_smem > ps_attr) {
-        RB_CUDA(cudaFuncSetAttribute(probe_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ps_smem));
-        ps_attr = ps_smem;
+    {
+        ResolveIdentity res{0};
+        int rc = launch_select<ResolveIdentity>(L.coarse, nullptr, nlist, nullptr, nlist, nlist, nq, nprobe, res, L.probe_scores,
+                                                L.probe_ids, st);
+        if (rc) return rc;
     }
-    probe_select_kernel<<<nq, NT, ps_smem, st>>>(L.coarse, nlist, nprobe, offsets, L.probes, L.cand_base, L.totals, L.list_qcount);
-    RB_LAUNCH_CHECK("probe_select_kernel");
+    probe_finish_kernel<<<(nq + NT - 1) / NT, NT, 0, st>>>(L.probe_ids, nq, nprobe, offsets, L.probes, L.cand_base, L.totals,
+                                                         L.list_qcount);
+    RB_LAUNCH_CHECK("probe_finish_kernel");
     const long long np = (long long)nq * nprobe;
     pair_keys_kernel<<<(unsigned)((np + NT - 1) / NT), NT, 0, st>>>(L.probes, np, nlist, L.pair_keys, L.pair_vals);
     RB_LAUNCH_CHECK("pair_keys_kernel");
