@@ -246,6 +246,16 @@ typedef struct rb200_step_views {
 int rb200_bpr_step_views(const rb200_step_params* params_host, rb200_step_views* out_host);
 
 /* ------------------------------------------------------------------------------------------ *
+ * Tensor-core score product: C[M,N] (row stride ldc) = A[M,K] · B[N,K]ᵀ, fp32 in / fp32 out, tcgen05.mma kind::tf32 with
+ * fp32 accumulation in TMEM.  mode 1 = single TF32 (~1e-3 relative error, fast mode), mode 2 = 3xTF32 error-compensated
+ * (~1e-6, fp32-grade).  K % 4 == 0, 16-byte aligned operands.  err_flag (optional device int): bit 1 is set if the
+ * tensor-core pipeline timed out (never expected; results are then undefined).  Serves the IVF coarse quantizer
+ * (faiss_index.py:113 → IndexFlatIP.search) and exhaustive-search score chunks.
+ * ------------------------------------------------------------------------------------------ */
+int rb200_gemm_nt(const float* A, int M, const float* B, int N, int K, int mode, float* C, int64_t ldc,
+                  int* err_flag, void* stream);
+
+/* ------------------------------------------------------------------------------------------ *
  * IVFFlat inner-product index — src/models/faiss_index.py
  * ------------------------------------------------------------------------------------------ */
 /* x / max(||x||, eps) per row (faiss_index.py:64-65,109-110,141-142; eps = 1e-8). out may alias x */

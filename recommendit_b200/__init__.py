@@ -3,7 +3,7 @@
 Python mirrors of the reference's model classes on top of ``librb200.so`` (C ABI in ``include/rb200.h``).
 """
 from .two_tower import N_GENRES, ItemTower, TwoTowerModel, UserTower          # noqa: F401
-from .faiss_index import FAISSIndex, flat_search, topk_merge                   # noqa: F401
+from .faiss_index import FAISSIndex, flat_search, scores_nt, topk_merge        # noqa: F401
 from .trainer import FusedBPRTrainer                                          # noqa: F401
 from ._lib import RB200Error                                                  # noqa: F401
 

@@ -392,19 +392,27 @@ template <> __device__ long long resolve_id<ResolveFlat>(const ResolveFlat& r, i
     return r.row_base + (c - r.kprev);
 }
 
+constexpr int SORT_CAP = 2048;   // winners + boundary bucket must fit the in-CTA sort (falls back to radix select otherwise)
+
+// Per-query top-k (one CTA per query).
+//   fast path : value-range bucket select — min/max of the scores, 256 linear buckets over [min, max] (well spread even
+//               though cosine scores share their leading float bits), locate the bucket b* that holds the k-th score,
+//               compact every candidate in buckets ≥ b* (winners + boundary bucket), bitonic-sort that small set by
+//               (score desc, candidate position asc) and emit the first k.
+//   fallback  : exact MSB-first radix select (many equal scores / boundary bucket too large).
 template <typename R>
 __global__ void __launch_bounds__(NT) select_topk_kernel(const float* __restrict__ cand, const long long* __restrict__ cand_off,
                                                          long long fixed_stride, const long long* __restrict__ counts,
-                                                         int fixed_count, int k, int sort_n, int cache_cap, R res,
+                                                         int fixed_count, int k, int cache_cap, R res,
                                                          float* __restrict__ out_scores, int64_t* __restrict__ out_ids) {
     extern __shared__ __align__(16) unsigned char sm_raw[];
-    uint32_t* skey = reinterpret_cast<uint32_t*>(sm_raw);           // [sort_n]
-    int* sidx = reinterpret_cast<int*>(skey + sort_n);              // [sort_n]
-    float* cache = reinterpret_cast<float*>(sidx + sort_n);         // [cache_cap]
+    uint32_t* skey = reinterpret_cast<uint32_t*>(sm_raw);           // [SORT_CAP]
+    int* sidx = reinterpret_cast<int*>(skey + SORT_CAP);            // [SORT_CAP]
+    float* cache = reinterpret_cast<float*>(sidx + SORT_CAP);       // [cache_cap]
     __shared__ int hist[256];
     __shared__ int wsum[2][NT / 32];
     __shared__ uint32_t s_prefix;
-    __shared__ int s_krem;
+    __shared__ int s_a, s_b, s_count;
     const int q = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const float* src = cand + (cand_off ? cand_off[q] : (long long)q * fixed_stride);
     const int n = counts ? (int)counts[q] : fixed_count;
@@ -414,86 +422,119 @@ __global__ void __launch_bounds__(NT) select_topk_kernel(const float* __restrict
         __syncthreads();
         src = cache;
     }
-    for (int i = tid; i < sort_n; i += NT) { skey[i] = 0u; sidx[i] = 0x7fffffff; }
-
-    uint32_t T = 0u;
-    int n_gt = 0, k_eq = 0;
-    if (n <= k) {
-        T = 0u; n_gt = 0; k_eq = n;     // take everything (all keys >= 0)
-        __syncthreads();
+    int m = 0;                       // number of entries placed in skey/sidx
+    bool done = false;
+    if (n <= SORT_CAP && n <= 2 * k) {
+        // small input: sort everything
+        for (int i = tid; i < n; i += NT) { skey[i] = f2key(src[i]); sidx[i] = i; }
+        m = n; done = true;
     } else {
+        // ---- fast path ------------------------------------------------------------------------------------ //
+        float lo = FLT_MAX, hi = -FLT_MAX;
+        for (int i = tid; i < n; i += NT) { const float v = src[i]; lo = fminf(lo, v); hi = fmaxf(hi, v); }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            lo = fminf(lo, __shfl_xor_sync(RB_FULL_MASK, lo, o));
+            hi = fmaxf(hi, __shfl_xor_sync(RB_FULL_MASK, hi, o));
+        }
+        if (lane == 0) { wsum[0][warp] = __float_as_int(lo); wsum[1][warp] = __float_as_int(hi); }
+        hist[tid] = 0;
+        if (tid == 0) s_count = 0;
+        __syncthreads();
+        for (int w = 0; w < NT / 32; ++w) { lo = fminf(lo, __int_as_float(wsum[0][w])); hi = fmaxf(hi, __int_as_float(wsum[1][w])); }
+        const float scale = (hi > lo) ? 256.f / (hi - lo) : 0.f;
+        for (int i = tid; i < n; i += NT) {
+            const int b = min(255, (int)((src[i] - lo) * scale));
+            atomicAdd(&hist[b], 1);
+        }
+        __syncthreads();
+        if (tid == 0) {
+            int cum = 0, b = 255;
+            for (; b > 0; --b) { if (cum + hist[b] >= k) break; cum += hist[b]; }
+            s_a = b; s_b = cum + hist[b];            // boundary bucket, #candidates in buckets >= b*
+        }
+        __syncthreads();
+        const int bstar = s_a, m_fast = s_b;
+        if (m_fast <= SORT_CAP && scale > 0.f) {
+            for (int base = 0; base < n; base += NT) {
+                const int i = base + tid;
+                bool take = false; float v = 0.f;
+                if (i < n) { v = src[i]; take = min(255, (int)((v - lo) * scale)) >= bstar; }
+                const uint32_t bal = __ballot_sync(RB_FULL_MASK, take);
+                int wbase = 0;
+                if (lane == 0 && bal) wbase = atomicAdd(&s_count, __popc(bal));
+                wbase = __shfl_sync(RB_FULL_MASK, wbase, 0);
+                if (take) { const int p = wbase + __popc(bal & ((1u << lane) - 1u)); skey[p] = f2key(v); sidx[p] = i; }
+            }
+            m = m_fast; done = true;
+        }
+    }
+    if (!done) {
+        // ---- fallback: exact radix select (4 × 8 bit, MSB first) + position-ordered compaction ------------------ //
+        __syncthreads();
         uint32_t prefix = 0u, mask = 0u;
         int krem = k;
         for (int shift = 24; shift >= 0; shift -= 8) {
             hist[tid] = 0;
             __syncthreads();
-            // warp-aggregated: the leading digits of cosine scores are heavily skewed (a few exponent values), so
-            // lanes holding the same digit elect one leader that adds their count — no same-bin atomic storms
-            for (int base = 0; base < n; base += NT) {
-                const int i = base + tid;
-                uint32_t digit = 0xFFFFFFFFu;
-                if (i < n) {
-                    const uint32_t key = f2key(src[i]);
-                    if ((key & mask) == prefix) digit = (key >> shift) & 255u;
-                }
-                const uint32_t peers = __match_any_sync(RB_FULL_MASK, digit);
-                if (digit != 0xFFFFFFFFu && lane == __ffs(peers) - 1) atomicAdd(&hist[digit], __popc(peers));
+            for (int i = tid; i < n; i += NT) {
+                const uint32_t key = f2key(src[i]);
+                if ((key & mask) == prefix) atomicAdd(&hist[(key >> shift) & 255u], 1);
             }
             __syncthreads();
             if (tid == 0) {
                 int cum = 0, d = 255;
                 for (; d > 0; --d) { if (cum + hist[d] >= krem) break; cum += hist[d]; }
                 s_prefix = prefix | ((uint32_t)d << shift);
-                s_krem = krem - cum;
+                s_a = krem - cum;
             }
             __syncthreads();
-            prefix = s_prefix; krem = s_krem; mask |= 255u << shift;
+            prefix = s_prefix; krem = s_a; mask |= 255u << shift;
             __syncthreads();
         }
-        T = prefix; k_eq = krem; n_gt = k - krem;
-    }
-
-    // ordered compaction: keys > T go to [0, n_gt) (any order is fine, they are sorted below — but we
-    // keep position order anyway), keys == T take the first k_eq positions → [n_gt, n_gt + k_eq)
-    int run_gt = 0, run_eq = 0;
-    for (int base = 0; base < n; base += NT) {
-        const int i = base + tid;
-        uint32_t key = 0u; bool gt = false, eq = false;
-        if (i < n) {
-            key = f2key(src[i]);
-            if (n <= k) eq = true; else { gt = key > T; eq = key == T; }
+        const uint32_t T = prefix;
+        const int k_eq = krem, n_gt = k - krem;
+        int run_gt = 0, run_eq = 0;
+        for (int base = 0; base < n; base += NT) {
+            const int i = base + tid;
+            uint32_t key = 0u; bool gt = false, eq = false;
+            if (i < n) { key = f2key(src[i]); gt = key > T; eq = key == T; }
+            const uint32_t bg = __ballot_sync(RB_FULL_MASK, gt), be = __ballot_sync(RB_FULL_MASK, eq);
+            if (lane == 0) { wsum[0][warp] = __popc(bg); wsum[1][warp] = __popc(be); }
+            __syncthreads();
+            int og = run_gt, oe = run_eq, tg = 0, te = 0;
+            for (int w = 0; w < NT / 32; ++w) {
+                if (w < warp) { og += wsum[0][w]; oe += wsum[1][w]; }
+                tg += wsum[0][w]; te += wsum[1][w];
+            }
+            const uint32_t lt = (1u << lane) - 1u;
+            if (gt) { const int p = og + __popc(bg & lt); skey[p] = key; sidx[p] = i; }
+            if (eq) { const int e = oe + __popc(be & lt); if (e < k_eq) { skey[n_gt + e] = key; sidx[n_gt + e] = i; } }
+            run_gt += tg; run_eq += te;
+            __syncthreads();
         }
-        const uint32_t bg = __ballot_sync(RB_FULL_MASK, gt), be = __ballot_sync(RB_FULL_MASK, eq);
-        if (lane == 0) { wsum[0][warp] = __popc(bg); wsum[1][warp] = __popc(be); }
-        __syncthreads();
-        int og = run_gt, oe = run_eq, tg = 0, te = 0;
-        for (int w = 0; w < NT / 32; ++w) {
-            if (w < warp) { og += wsum[0][w]; oe += wsum[1][w]; }
-            tg += wsum[0][w]; te += wsum[1][w];
-        }
-        const uint32_t lt = (1u << lane) - 1u;
-        if (gt) { const int p = og + __popc(bg & lt); skey[p] = key; sidx[p] = i; }
-        if (eq) { const int e = oe + __popc(be & lt); if (e < k_eq) { skey[n_gt + e] = key; sidx[n_gt + e] = i; } }
-        run_gt += tg; run_eq += te;
-        __syncthreads();
+        m = k;
     }
-
-    // bitonic sort, descending by (key, then ascending idx)
+    // ---- bitonic sort of the m collected entries, descending by (key, then ascending position) ---------------- //
+    int sort_n = 2;
+    while (sort_n < m) sort_n <<= 1;
+    __syncthreads();
+    for (int i = m + tid; i < sort_n; i += NT) { skey[i] = 0u; sidx[i] = 0x7fffffff; }
     for (int size = 2; size <= sort_n; size <<= 1) {
         for (int stride = size >> 1; stride > 0; stride >>= 1) {
             __syncthreads();
             for (int t = tid; t < sort_n / 2; t += NT) {
-                const int lo = (t / stride) * (stride << 1) + (t % stride), hi = lo + stride;
-                const bool desc = ((lo & size) == 0);
-                const uint32_t ka = skey[lo], kb = skey[hi];
-                const int ia = sidx[lo], ib = sidx[hi];
+                const int lo_i = (t / stride) * (stride << 1) + (t % stride), hi_i = lo_i + stride;
+                const bool desc = ((lo_i & size) == 0);
+                const uint32_t ka = skey[lo_i], kb = skey[hi_i];
+                const int ia = sidx[lo_i], ib = sidx[hi_i];
                 const bool a_first = ka > kb || (ka == kb && ia < ib);    // a ranks before b
-                if (a_first != desc) { skey[lo] = kb; skey[hi] = ka; sidx[lo] = ib; sidx[hi] = ia; }
+                if (a_first != desc) { skey[lo_i] = kb; skey[hi_i] = ka; sidx[lo_i] = ib; sidx[hi_i] = ia; }
             }
         }
     }
     __syncthreads();
-    const int n_out = n < k ? n : k;
+    const int n_out = m < k ? m : k;
     for (int j = tid; j < k; j += NT) {
         if (j < n_out) {
             out_scores[(long long)q * k + j] = key2f(skey[j]);
@@ -511,17 +552,16 @@ template <typename R>
 int launch_select(const float* cand, const long long* cand_off, long long fixed_stride, const long long* counts,
                   int fixed_count, long long max_count, int nq, int k, const R& res, float* out_scores, int64_t* out_ids,
                   cudaStream_t st) {
-    const int sort_n = next_pow2(k);
     int cache_cap = (int)(max_count < 24576 ? max_count : 24576);
     if (cache_cap < 0) cache_cap = 0;
-    const size_t smem = (size_t)sort_n * 8 + (size_t)cache_cap * 4 + 16;
+    const size_t smem = (size_t)SORT_CAP * 8 + (size_t)cache_cap * 4 + 16;
     static size_t attr_smem = 0;
     if (smem > attr_smem) {
         RB_CUDA(cudaFuncSetAttribute(select_topk_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem > 48 * 1024 ? smem : 48 * 1024)));
         attr_smem = smem;
     }
-    select_topk_kernel<R><<<nq, NT, smem, st>>>(cand, cand_off, fixed_stride, counts, fixed_count, k, sort_n, cache_cap, res,
-                                                out_scores, out_ids);
+    select_topk_kernel<R><<<nq, NT, smem, st>>>(cand, cand_off, fixed_stride, counts, fixed_count, k, cache_cap, res, out_scores,
+                                                out_ids);
     RB_LAUNCH_CHECK("select_topk_kernel");
     return RB200_OK;
 }

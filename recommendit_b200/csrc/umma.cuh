@@ -1,0 +1,120 @@
+// tcgen05 (5th-gen tensor core) building blocks for sm_100a, inline PTX.
+//
+//   - TMEM allocation, tcgen05.mma.kind::tf32 with both operands in shared memory ("SS"), tcgen05.commit → mbarrier,
+//     tcgen05.ld of the fp32 accumulator (32x32b: one TMEM lane = one accumulator row per thread).
+//   - Shared-memory operand layout: the canonical *no-swizzle, K-major* UMMA layout.  In 16-byte units
+//     ((8,n),2):((1,SBO),LBO) — a "core matrix" is 8 rows × 16 B stored contiguously (128 B); SBO is the byte distance
+//     between consecutive 8-row groups, LBO between the two 16-byte K chunks one K=8 (tf32) instruction consumes.
+//     We store an [R rows × KC floats] operand chunk core-matrix-major:  offset(r, k) =
+//         ((k/4)·(R/8) + r/8)·128 + (r%8)·16 + (k%4)·4      ⇒  SBO = 128 B, LBO = (R/8)·128 B,
+//     so any thread can drop a float4 (4 consecutive k of one row) with one 16-byte store.
+//   - "3xTF32": fp32 operands are split hi = tf32(x), lo = x − hi; a·b ≈ a_hi·b_hi + a_hi·b_lo + a_lo·b_hi with fp32
+//     accumulation in TMEM gives ~2^-21 relative error per product (fp32-grade), at 3 MMAs per logical MMA.
+//
+// Every mbarrier wait is BOUNDED: a wrong descriptor must never hang the GPU; on timeout the kernel sets an error flag
+// and carries on (results are garbage, the host reports the flag).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace umma {
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// ---- TMEM ------------------------------------------------------------------------------------------------ //
+// one full warp; writes the TMEM base address to *slot (shared memory)
+__device__ __forceinline__ void tmem_alloc(uint32_t* slot, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot)), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_free(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void fence_before_sync() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void fence_after_sync() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+// generic-proxy shared-memory writes → visible to the async proxy (tensor core reads operands through it)
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// ---- mbarrier ---------------------------------------------------------------------------------------------- //
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+// returns false on timeout
+__device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity, uint32_t max_polls = 4000000u) {
+    const uint32_t addr = smem_u32(bar);
+    for (uint32_t i = 0; i < max_polls; ++i) {
+        uint32_t done;
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(addr), "r"(parity)
+            : "memory");
+        if (done) return true;
+    }
+    return false;
+}
+// all previously issued tcgen05.mma of this thread → arrive(1) on bar when they complete
+__device__ __forceinline__ void commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// ---- descriptors ------------------------------------------------------------------------------------------- //
+// instruction descriptor, kind::tf32, fp32 accumulate, both operands K-major (cute::UMMA::InstrDescriptor bit layout)
+__host__ __device__ constexpr uint32_t idesc_tf32(int M, int N) {
+    return (1u << 4) /*c = F32*/ | (2u << 7) /*a = TF32*/ | (2u << 10) /*b = TF32*/ | ((uint32_t)(N >> 3) << 17) |
+           ((uint32_t)(M >> 4) << 24);
+}
+// shared-memory matrix descriptor, no swizzle (cute::UMMA::SmemDescriptor bit layout, version 1 = Blackwell)
+__device__ __forceinline__ uint64_t smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16) |
+           ((uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32) | (1ull << 46);
+}
+// byte offset of element (r, k) in an [R × KC] operand chunk stored core-matrix-major (see header)
+__device__ __forceinline__ uint32_t kmajor_offset(int R, int r, int k) {
+    return (uint32_t)((((k >> 2) * (R >> 3) + (r >> 3)) << 7) + ((r & 7) << 4) + ((k & 3) << 2));
+}
+
+// D[tmem] (+)= A[smem] · B[smem]ᵀ, M×N×8 (tf32).  Issued by ONE thread.
+__device__ __forceinline__ void mma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, bool accumulate) {
+    const uint32_t acc = accumulate ? 1u : 0u, z = 0u;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, {%5, %6, %7, %8}, p;\n\t}"
+        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(acc), "r"(z), "r"(z), "r"(z), "r"(z)
+        : "memory");
+}
+
+// ---- TMEM → registers --------------------------------------------------------------------------------------- //
+// 32 consecutive fp32 columns of this thread's lane (warp w may only touch lanes 32·(w%4) … +31)
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
+    uint32_t r[32];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, "
+        "%19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+          "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+          "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+          "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// ---- 3xTF32 split ------------------------------------------------------------------------------------------- //
+__device__ __forceinline__ float tf32_hi(float x) {     // round-to-nearest tf32, low 13 mantissa bits zero
+    uint32_t u;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
+    return __uint_as_float(u);
+}
+__device__ __forceinline__ void split4(const float4& x, float4& hi, float4& lo) {
+    hi.x = tf32_hi(x.x); hi.y = tf32_hi(x.y); hi.z = tf32_hi(x.z); hi.w = tf32_hi(x.w);
+    lo.x = x.x - hi.x; lo.y = x.y - hi.y; lo.z = x.z - hi.z; lo.w = x.w - hi.w;   // exact in fp32; the MMA truncates it to tf32
+}
+
+}  // namespace umma

@@ -328,3 +328,19 @@ def topk_merge(scores: torch.Tensor, ids: torch.Tensor) -> Tuple[torch.Tensor, t
         check(lib.rb200_topk_merge(ptr(scores), ptr(ids), parts, nq, k, ptr(out_s), ptr(out_i), ptr(ws), wb, stream_ptr()),
               "rb200_topk_merge")
     return out_s, out_i
+
+
+def scores_nt(a: torch.Tensor, b: torch.Tensor, mode: int = 2) -> torch.Tensor:
+    """``a @ b.T`` on the tcgen05 tensor cores (``rb200_gemm_nt``): mode 1 = TF32, mode 2 = 3xTF32 (fp32-grade)."""
+    lib = _lib.load()
+    _lib.require_cuda(a, b)
+    a, b = a.contiguous(), b.contiguous()
+    M, K = a.shape
+    N = b.shape[0]
+    out = torch.empty(M, N, dtype=torch.float32, device=a.device)
+    err = torch.zeros(1, dtype=torch.int32, device=a.device)
+    with torch.cuda.device(a.device):
+        check(lib.rb200_gemm_nt(ptr(a), M, ptr(b), N, K, mode, ptr(out), N, ptr(err), stream_ptr()), "rb200_gemm_nt")
+    if int(err.item()) != 0:
+        raise RB200Error("rb200_gemm_nt: tensor-core pipeline timed out (error flag %d)" % int(err.item()))
+    return out
