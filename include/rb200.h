@@ -76,8 +76,13 @@ typedef struct rb200_tower_job {
  * (optional device int64, e.g. &opt_state.step) lets a replayed CUDA graph draw a fresh mask.
  * err_flag: optional device int, bit 0 is set when an id is out of range. */
 int rb200_tower_fwd(const rb200_tower_job* jobs_host, int n_jobs, int D, int H, float dropout_p,
-                    uint64_t seed, uint64_t offset, const int64_t* offset_dev, int* err_flag,
+                    uint64_t seed, uint64_t offset, const int64_t* offset_dev, int mode, int* err_flag,
                     void* stream);
+/* mode (both tower entry points): 0 = fp32 FFMA kernels (parity mode, any supported width);
+ *   1 = tcgen05 tensor cores, single TF32 (fast mode, ~1e-3 relative error on activations/gradients);
+ *   2 = tcgen05 tensor cores, 3xTF32 error-compensated (fp32-grade, meets the 1e-5 parity bound).
+ * Tensor-core modes currently cover D = 64, H = 128, extra_dim <= 24 (the reference's production widths).
+ * All modes draw the same dropout mask for the same (seed, offset). */
 
 /* Backward of one tower evaluation (autograd of the above; src/training/train_embeddings.py:190).
  * Step 1 (data): from dY [B,D] (gradient w.r.t. the normalised output) and the saved y/denom/hid
@@ -102,7 +107,7 @@ typedef struct rb200_tower_bwd_job {
 
 size_t rb200_tower_bwd_workspace_bytes(int D, int H, int extra_dim);
 int rb200_tower_bwd(const rb200_tower_bwd_job* jobs_host, int n_jobs, int D, int H, float dropout_p,
-                    float* grads_out, int accumulate, void* workspace, size_t workspace_bytes,
+                    int mode, float* grads_out, int accumulate, void* workspace, size_t workspace_bytes,
                     void* stream);
 
 /* ------------------------------------------------------------------------------------------ *
@@ -217,6 +222,7 @@ typedef struct rb200_step_params {
     int loss_kind;      /* 0: bpr_loss with sampled negatives (what train_embeddings.py runs)
                            1: in_batch_bpr_loss (neg_* unused)                                   */
     int inbatch_mode;   /* precision mode of rb200_bpr_inbatch                                   */
+    int tower_mode;     /* precision mode of rb200_tower_fwd / rb200_tower_bwd (0 FFMA fp32, 1 TF32, 2 3xTF32) */
     int adam_mode;      /* 0: dense — every table row is updated, as torch.optim.Adam(weight_decay) on the
                               reference's dense nn.Embedding gradients (parity mode)
                            1: touched rows only (throughput mode, documented divergence)         */

@@ -57,7 +57,8 @@ class StepParams(C.Structure):
                 ("item_mlp", c_f), ("item_mlp_m", c_f), ("item_mlp_v", c_f),
                 ("user_row_slot", c_f), ("item_row_slot", c_f), ("opt", c_f),
                 ("user_ids", c_f), ("pos_ids", c_f), ("neg_ids", c_f), ("pos_extra", c_f), ("neg_extra", c_f),
-                ("extra_by_id", C.c_int), ("loss_kind", C.c_int), ("inbatch_mode", C.c_int), ("adam_mode", C.c_int),
+                ("extra_by_id", C.c_int), ("loss_kind", C.c_int), ("inbatch_mode", C.c_int), ("tower_mode", C.c_int),
+                ("adam_mode", C.c_int),
                 ("dropout_p", C.c_float), ("seed", C.c_uint64),
                 ("keep_mask_user", c_f), ("keep_mask_pos", c_f), ("keep_mask_neg", c_f),
                 ("padding_idx", C.c_int64), ("loss", c_f), ("err_flag", c_f),
@@ -79,9 +80,9 @@ SIGNATURES = {
     "rb200_sm_count": (I, []),
     "rb200_sizeof": (SZ, [I]),
     "rb200_launch_count": (U64, []),
-    "rb200_tower_fwd": (I, [C.POINTER(TowerJob), I, I, I, F, U64, U64, P, P, P]),
+    "rb200_tower_fwd": (I, [C.POINTER(TowerJob), I, I, I, F, U64, U64, P, I, P, P]),
     "rb200_tower_bwd_workspace_bytes": (SZ, [I, I, I]),
-    "rb200_tower_bwd": (I, [C.POINTER(TowerBwdJob), I, I, I, F, P, I, P, SZ, P]),
+    "rb200_tower_bwd": (I, [C.POINTER(TowerBwdJob), I, I, I, F, I, P, I, P, SZ, P]),
     "rb200_bpr_pair": (I, [P, P, P, I, I, P, P, P, P, F, P, SZ, P]),
     "rb200_bpr_pair_workspace_bytes": (SZ, [I]),
     "rb200_bpr_inbatch_workspace_bytes": (SZ, [I, I]),

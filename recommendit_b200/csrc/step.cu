@@ -184,7 +184,7 @@ extern "C" int rb200_bpr_step(const rb200_step_params* s, void* stream) {
         j.keep_mask = t == 0 ? s->keep_mask_pos : s->keep_mask_neg;
         j.n_rows = s->n_item_rows; j.B = B;
     }
-    if ((rc = rb200_tower_fwd(fj, 1 + items, D, H, s->dropout_p, s->seed, 0, &s->opt->step, s->err_flag, st))) return rc;
+    if ((rc = rb200_tower_fwd(fj, 1 + items, D, H, s->dropout_p, s->seed, 0, &s->opt->step, s->tower_mode, s->err_flag, st))) return rc;
 
     RB_STAGE_EVENT();
     // ---- loss + gradient w.r.t. the tower outputs ------------------------------------------- //
@@ -200,7 +200,7 @@ extern "C" int rb200_bpr_step(const rb200_step_params* s, void* stream) {
     bj[0].table = s->user_table; bj[0].ids = s->user_ids; bj[0].extra = nullptr; bj[0].n_rows = s->n_user_rows; bj[0].B = B;
     bj[0].extra_dim = 0; bj[0].W1 = fj[0].W1; bj[0].W2 = fj[0].W2; bj[0].dY = w.du; bj[0].y = w.u; bj[0].denom = w.den_u;
     bj[0].hid = w.hid_u; bj[0].dpre = w.dpre_u; bj[0].dact = w.dact_u; bj[0].dRows = w.drows_u;
-    if ((rc = rb200_tower_bwd(bj, 1, D, H, s->dropout_p, w.g_user_mlp, 0, w.ws_bwd, w.b_bwd, st))) return rc;
+    if ((rc = rb200_tower_bwd(bj, 1, D, H, s->dropout_p, s->tower_mode, w.g_user_mlp, 0, w.ws_bwd, w.b_bwd, st))) return rc;
     for (int t = 0; t < items; ++t) {
         rb200_tower_bwd_job& j = bj[t];
         j = rb200_tower_bwd_job{};
@@ -210,7 +210,7 @@ extern "C" int rb200_bpr_step(const rb200_step_params* s, void* stream) {
         j.hid = w.hid_pn + (size_t)t * B * H; j.dpre = w.dpre_pn + (size_t)t * B * D; j.dact = w.dact_pn + (size_t)t * B * H;
         j.dRows = w.drows_pn + (size_t)t * B * D;
     }
-    if ((rc = rb200_tower_bwd(bj, items, D, H, s->dropout_p, w.g_item_mlp, 0, w.ws_bwd, w.b_bwd, st))) return rc;
+    if ((rc = rb200_tower_bwd(bj, items, D, H, s->dropout_p, s->tower_mode, w.g_item_mlp, 0, w.ws_bwd, w.b_bwd, st))) return rc;
 
     RB_STAGE_EVENT();
     // ---- sparse embedding gradients: deterministic sorted-segment sums ---------------------- //

@@ -12,24 +12,12 @@
 // memory between the two GEMMs and never touch HBM in inference.  Register-tiled 128-bit
 // shared-memory operand loads; leading dimensions are chosen so that the loads are conflict-free.
 #include "common.cuh"
+#include "tower_common.cuh"
 
 namespace {
 
 constexpr int TM = 64;    // samples per tile
 constexpr int NT = 256;   // threads per CTA
-constexpr int MAX_JOBS = 3;
-constexpr float NORM_EPS = 1e-12f;
-
-struct FwdJob {
-    const float* table; const int64_t* ids; const float* extra;
-    const float* W1; const float* b1; const float* W2; const float* b2;
-    float* out; float* hid; float* denom; const uint8_t* keep_mask;
-    long long n_rows; int B; int E; int extra_by_id; int cta_begin; int cta_count;
-};
-struct FwdParams {
-    FwdJob job[MAX_JOBS];
-    int n_jobs; float drop_p; unsigned long long seed, offset; const long long* offset_dev; int* err_flag;
-};
 
 // C[r][c] (r < RPT rows starting at row0; 4 columns col0 + c*cstride) = Σ_k A[row][k] · W[col][k]
 // A: [rows][lda] row-major, W: [cols][ldw] row-major (torch Linear layout) — "NT" product.
@@ -157,6 +145,8 @@ __global__ void __launch_bounds__(NT, 1) tower_fwd_kernel(const FwdParams p) {
     const int n_tiles = (B + TM - 1) / TM;
     const bool do_drop = p.drop_p > 0.f;
     const float keep_scale = do_drop ? 1.f / (1.f - p.drop_p) : 1.f;
+    const unsigned long long drop_off = p.offset + (unsigned long long)j +
+                                        (p.offset_dev ? (unsigned long long)__ldg(p.offset_dev) * MAX_JOBS : 0ull);
 
     for (int tile = (int)blockIdx.x - J.cta_begin; tile < n_tiles; tile += J.cta_count) {
         const int row0 = tile * TM;
@@ -169,14 +159,6 @@ __global__ void __launch_bounds__(NT, 1) tower_fwd_kernel(const FwdParams p) {
 #pragma unroll
             for (int r = 0; r < RPT1; ++r) {
                 const int lr = ty * RPT1 + r, row = row0 + lr;
-                uint32_t rnd[4] = {0u, 0u, 0u, 0u};
-                if (do_drop && J.keep_mask == nullptr) {
-                    const unsigned long long off = p.offset + (unsigned long long)j +
-                        (p.offset_dev ? (unsigned long long)__ldg(p.offset_dev) * MAX_JOBS : 0ull);
-                    const uint4 o = rb_philox4x32(make_uint4((uint32_t)row, (uint32_t)tx, (uint32_t)off, (uint32_t)(off >> 32)),
-                                                  make_uint2((uint32_t)p.seed, (uint32_t)(p.seed >> 32)));
-                    rnd[0] = o.x; rnd[1] = o.y; rnd[2] = o.z; rnd[3] = o.w;
-                }
 #pragma unroll
                 for (int c = 0; c < 4; ++c) {
                     const int col = tx + c * NTX1;
@@ -184,7 +166,7 @@ __global__ void __launch_bounds__(NT, 1) tower_fwd_kernel(const FwdParams p) {
                     if (do_drop) {
                         bool keep;
                         if (J.keep_mask) keep = (row < B) ? (J.keep_mask[(long long)row * H + col] != 0) : true;
-                        else keep = rb_u01(rnd[c]) >= p.drop_p;
+                        else keep = rb_dropout_keep(p.seed, drop_off, row, col, p.drop_p);
                         v = keep ? v * keep_scale : 0.f;
                     }
                     Hs[lr * ldh + col] = v;
@@ -243,19 +225,6 @@ int launch_fwd(const FwdParams& p, int grid, size_t smem, cudaStream_t st) {
 // ------------------------------------------------------------------------------------------ //
 // backward, data part
 // ------------------------------------------------------------------------------------------ //
-struct BwdJob {
-    const float* table; const int64_t* ids; const float* extra; long long n_rows; int B; int E;
-    const float* W1; const float* W2;
-    const float* dY; const float* y; const float* denom; const float* hid;
-    float* dpre; float* dact; float* dRows;
-    int extra_by_id; int cta_begin; int cta_count;
-};
-struct BwdParams {
-    BwdJob job[MAX_JOBS];
-    int n_jobs; float keep_scale;
-    float* part; int nsplit; int P;
-};
-
 template <int RPT1, int RPT2>
 __global__ void __launch_bounds__(NT, 1) tower_bwd_data_kernel(const BwdParams p) {
     constexpr int H = RPT1 * 16, D = RPT2 * 16;
@@ -555,9 +524,14 @@ int partition_ctas(JobT* jobs, int n_jobs, int D, int H) {
 
 }  // namespace
 
+int rb_tower_fwd_tc(FwdParams& p, int D, int H, int mode, cudaStream_t st);
+int rb_tower_bwd_tc(BwdParams& p, int D, int H, int mode, float* grads_out, int accumulate, cudaStream_t st);
+bool rb_tower_tc_supported(int D, int H, int E);
+
 extern "C" int rb200_tower_fwd(const rb200_tower_job* jobs, int n_jobs, int D, int H, float dropout_p,
-                               uint64_t seed, uint64_t offset, const int64_t* offset_dev, int* err_flag, void* stream) {
+                               uint64_t seed, uint64_t offset, const int64_t* offset_dev, int mode, int* err_flag, void* stream) {
     RB_REQUIRE(jobs && n_jobs >= 1 && n_jobs <= MAX_JOBS, "tower_fwd: n_jobs must be 1..3");
+    RB_REQUIRE(mode >= 0 && mode <= 2, "tower_fwd: mode must be 0 (fp32 FFMA), 1 (tcgen05 TF32) or 2 (tcgen05 3xTF32)");
     RB_REQUIRE(dims_supported(D, H), "tower_fwd: unsupported widths D=%d H=%d (D in {32,64,128}, H in {64,128,256})", D, H);
     RB_REQUIRE(dropout_p >= 0.f && dropout_p < 1.f, "tower_fwd: dropout_p must be in [0,1)");
     FwdParams p{};
@@ -577,6 +551,11 @@ extern "C" int rb200_tower_fwd(const rb200_tower_job* jobs, int n_jobs, int D, i
         if (b > smem) smem = b;
     }
     if (p.n_jobs == 0) return RB200_OK;
+    if (mode != 0) {
+        for (int j = 0; j < p.n_jobs; ++j)
+            RB_REQUIRE(rb_tower_tc_supported(D, H, p.job[j].E), "tower_fwd: tcgen05 mode supports D=64, H=128, extra_dim<=24 (got D=%d H=%d E=%d)", D, H, p.job[j].E);
+        return rb_tower_fwd_tc(p, D, H, mode, (cudaStream_t)stream);
+    }
     RB_REQUIRE((int)smem <= rb_max_smem_optin(), "tower_fwd: D=%d H=%d needs %zu B of shared memory (> %d)", D, H, smem,
                rb_max_smem_optin());
     const int grid = partition_ctas(p.job, p.n_jobs, D, H);
@@ -587,13 +566,14 @@ extern "C" int rb200_tower_fwd(const rb200_tower_job* jobs, int n_jobs, int D, i
 
 extern "C" size_t rb200_tower_bwd_workspace_bytes(int D, int H, int extra_dim) {
     const size_t P = (size_t)H * (D + extra_dim) + H + (size_t)D * H + D;
-    return 256 + sizeof(float) * P * (size_t)(rb_sm_count() / 2 > 0 ? rb_sm_count() / 2 : 1);
+    return 256 + sizeof(float) * P * (size_t)rb_sm_count();      // tcgen05 path: one partial per SM; FFMA path: half
 }
 
-extern "C" int rb200_tower_bwd(const rb200_tower_bwd_job* jobs, int n_jobs, int D, int H, float dropout_p,
+extern "C" int rb200_tower_bwd(const rb200_tower_bwd_job* jobs, int n_jobs, int D, int H, float dropout_p, int mode,
                                float* grads_out, int accumulate, void* workspace, size_t workspace_bytes,
                                void* stream) {
     RB_REQUIRE(jobs && n_jobs >= 1 && n_jobs <= MAX_JOBS, "tower_bwd: n_jobs must be 1..3");
+    RB_REQUIRE(mode >= 0 && mode <= 2, "tower_bwd: mode must be 0, 1 or 2");
     RB_REQUIRE(dims_supported(D, H), "tower_bwd: unsupported widths D=%d H=%d", D, H);
     RB_REQUIRE(grads_out != nullptr, "tower_bwd: grads_out is NULL");
     BwdParams p{};
@@ -621,6 +601,15 @@ extern "C" int rb200_tower_bwd(const rb200_tower_bwd_job* jobs, int n_jobs, int 
     if (p.n_jobs == 0) {
         if (!accumulate) RB_CUDA(cudaMemsetAsync(grads_out, 0, sizeof(float) * P, st));
         return RB200_OK;
+    }
+    if (mode != 0) {
+        RB_REQUIRE(rb_tower_tc_supported(D, H, E), "tower_bwd: tcgen05 mode supports D=64, H=128, extra_dim<=24");
+        RbArena tar(workspace, workspace_bytes);
+        p.nsplit = rb_sm_count();
+        p.P = P;
+        p.part = tar.take<float>((size_t)p.nsplit * P);
+        if (!workspace || !tar.ok()) return rb_set_error(RB200_ERR_WORKSPACE, "tower_bwd: workspace too small (%zu given)", workspace_bytes);
+        return rb_tower_bwd_tc(p, D, H, mode, grads_out, accumulate, st);
     }
     int nsplit = rb_sm_count() / 2;
     const long long stages = (total_rows + RT - 1) / RT;

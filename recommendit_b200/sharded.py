@@ -88,6 +88,11 @@ class CudaOps:
     def __init__(self):
         self.lib = _lib.load()
 
+    def mode(self, D, H, jobs) -> int:
+        from .two_tower import tower_mode_for
+        E = max(0 if j.get("extra") is None else j["extra"].shape[1] for j in jobs)
+        return tower_mode_for(D, H, E)
+
     def gather_rows(self, table: torch.Tensor, rows: torch.Tensor) -> torch.Tensor:
         out = torch.empty(rows.numel(), table.shape[1], dtype=torch.float32, device=table.device)
         if rows.numel():
@@ -101,7 +106,8 @@ class CudaOps:
             arr[i] = TowerJob(ptr(j["table"]), ptr(j["ids"]), ptr(j.get("extra")), ptr(j["W1"]), ptr(j["b1"]), ptr(j["W2"]),
                               ptr(j["b2"]), ptr(j["out"]), ptr(j["hid"]), ptr(j["denom"]), None, j["table"].shape[0],
                               j["ids"].numel(), 0 if j.get("extra") is None else j["extra"].shape[1], 0)
-        check(self.lib.rb200_tower_fwd(arr, len(jobs), D, H, drop_p, seed, offset, None, None, stream_ptr()), "rb200_tower_fwd")
+        check(self.lib.rb200_tower_fwd(arr, len(jobs), D, H, drop_p, seed, offset, None, self.mode(D, H, jobs), None, stream_ptr()),
+              "rb200_tower_fwd")
 
     def bpr_pair(self, u, p, n, grad_scale: float):
         B, D = u.shape
@@ -122,7 +128,8 @@ class CudaOps:
                                  ptr(j["dpre"]), ptr(j["dact"]), ptr(j["dRows"]))
         wsb = self.lib.rb200_tower_bwd_workspace_bytes(D, H, E)
         ws = workspace(wsb, grads_out.device)
-        check(self.lib.rb200_tower_bwd(arr, len(jobs), D, H, drop_p, ptr(grads_out), 0, ptr(ws), wsb, stream_ptr()), "rb200_tower_bwd")
+        check(self.lib.rb200_tower_bwd(arr, len(jobs), D, H, drop_p, self.mode(D, H, jobs), ptr(grads_out), 0, ptr(ws), wsb, stream_ptr()),
+              "rb200_tower_bwd")
 
     def scatter_rows(self, ids: torch.Tensor, rows: torch.Tensor, n_rows: int, padding_row: int):
         """→ (uniq_ids [cap], uniq_grads [cap, D], n_uniq [1] int32), deterministic; ``padding_row`` < 0 ⇒ none"""

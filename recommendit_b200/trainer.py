@@ -34,7 +34,7 @@ class FusedBPRTrainer:
     def __init__(self, model: TwoTowerModel, lr: float = 1e-3, betas=(0.9, 0.999), eps: float = 1e-8,
                  weight_decay: float = 1e-5, max_norm: float = 1.0, adam_mode: str = "dense", loss: str = "bpr",
                  inbatch_mode: Optional[int] = None, item_extra_table: Optional[torch.Tensor] = None,
-                 use_cuda_graph: bool = True, seed: Optional[int] = None):
+                 use_cuda_graph: bool = True, seed: Optional[int] = None, tower_mode=None):
         self.lib = _lib.load()
         self.model = model
         self.dev = require_cuda(*list(model.parameters()))
@@ -45,6 +45,8 @@ class FusedBPRTrainer:
         self.adam_mode, self.loss_kind = adam_mode, (0 if loss == "bpr" else 1)
         self.inbatch_mode = INBATCH_MODE if inbatch_mode is None else int(inbatch_mode)
         self.use_graph = use_cuda_graph
+        from .two_tower import tower_mode_for
+        self.tower_mode = tower_mode_for(model.embed_dim, model.user_tower.mlp[0].out_features, model.item_tower.extra_dim, tower_mode)
         self.seed = (torch.initial_seed() if seed is None else seed) & 0x7FFFFFFFFFFFFFFF
         self.D, self.H = model.embed_dim, model.user_tower.mlp[0].out_features
         self.E = model.item_tower.extra_dim
@@ -171,6 +173,7 @@ class FusedBPRTrainer:
         p.pos_extra, p.neg_extra = ptr(self.pos_extra), ptr(self.neg_extra)
         p.extra_by_id = 1 if self.item_extra_table is not None else 0
         p.loss_kind, p.inbatch_mode = self.loss_kind, self.inbatch_mode
+        p.tower_mode = self.tower_mode
         p.adam_mode = 0 if self.adam_mode == "dense" else 1
         p.dropout_p = m.user_tower.dropout_p if m.training else 0.0
         p.seed = self.seed

@@ -36,6 +36,18 @@ logger = logging.getLogger(__name__)
 
 N_GENRES = 18  # MovieLens-1M genre multi-hot width (reference two_tower.py:16)
 
+#: precision mode of the tower MLP kernels: 0 = fp32 FFMA, 1 = tcgen05 TF32, 2 = tcgen05 3xTF32 (fp32-grade).
+#: "auto" (default) = 2 where the tensor-core kernels cover the widths (D=64, H=128), else 0.
+TOWER_MODE = os.environ.get("RB200_TOWER_MODE", "auto")
+
+
+def tower_mode_for(D: int, H: int, E: int, mode=None) -> int:
+    mode = TOWER_MODE if mode is None else mode
+    if str(mode) == "auto":
+        return 2 if (D == 64 and H == 128 and E <= 24) else 0
+    return int(mode)
+
+
 #: precision mode of the in-batch score GEMM: 0 = fp32 FFMA (parity), 1 = tcgen05 TF32, 2 = tcgen05 3xTF32
 INBATCH_MODE = int(os.environ.get("RB200_INBATCH_MODE", "0"))
 
@@ -50,7 +62,7 @@ class _TowerFn(torch.autograd.Function):
     """gather → Linear → ReLU → dropout → Linear → L2-normalise, fused (two_tower.py:39-42 / 68-72)."""
 
     @staticmethod
-    def forward(ctx, ids, extra, table, W1, b1, W2, b2, drop_p, seed, offset, keep_mask):
+    def forward(ctx, ids, extra, table, W1, b1, W2, b2, drop_p, seed, offset, keep_mask, mode=None):
         lib = _lib.load()
         dev = require_cuda(ids, extra, table, W1, b1, W2, b2, keep_mask)
         if ids.dtype != torch.int64:
@@ -70,15 +82,17 @@ class _TowerFn(torch.autograd.Function):
         denom = torch.empty(B, dtype=torch.float32, device=dev) if need_grad else None
         if keep_mask is not None:
             keep_mask = keep_mask.reshape(B, H).to(torch.uint8).contiguous()
+        mode = tower_mode_for(D, H, E, mode)
         if B > 0:
             job = TowerJob(ptr(table), ptr(ids), ptr(extra), ptr(W1), ptr(b1), ptr(W2), ptr(b2), ptr(out), ptr(hid),
                            ptr(denom), ptr(keep_mask), n_rows, B, E, 0)
             with torch.cuda.device(dev):
-                check(lib.rb200_tower_fwd(job, 1, D, H, float(drop_p), int(seed), int(offset), None, None, stream_ptr()),
+                check(lib.rb200_tower_fwd(job, 1, D, H, float(drop_p), int(seed), int(offset), None, mode, None, stream_ptr()),
                       "rb200_tower_fwd")
         if need_grad:
             ctx.save_for_backward(ids, extra, table, W1, W2, out, hid, denom)
             ctx.drop_p = float(drop_p)
+            ctx.mode = mode
             ctx.dims = (B, D, H, E, n_rows)
         return out.view(*shape, D)
 
@@ -102,7 +116,7 @@ class _TowerFn(torch.autograd.Function):
             job = TowerBwdJob(ptr(table), ptr(ids), ptr(extra), n_rows, B, E, 0, ptr(W1), ptr(W2), ptr(dY), ptr(out),
                               ptr(denom), ptr(hid), ptr(dpre), ptr(dact), ptr(drows))
             with torch.cuda.device(dev):
-                check(lib.rb200_tower_bwd(job, 1, D, H, ctx.drop_p, ptr(grads), 0, ptr(ws), wsb, stream_ptr()),
+                check(lib.rb200_tower_bwd(job, 1, D, H, ctx.drop_p, ctx.mode, ptr(grads), 0, ptr(ws), wsb, stream_ptr()),
                       "rb200_tower_bwd")
                 if g_table is not None:
                     # dense nn.Embedding gradient (padding_idx = 0 receives nothing), deterministic
@@ -117,7 +131,7 @@ class _TowerFn(torch.autograd.Function):
         gb1 = grads[o:o + H]; o += H
         gW2 = grads[o:o + D * H].view(D, H); o += D * H
         gb2 = grads[o:o + D]
-        return None, None, g_table, gW1, gb1, gW2, gb2, None, None, None, None
+        return None, None, g_table, gW1, gb1, gW2, gb2, None, None, None, None, None
 
 
 class _BprPairFn(torch.autograd.Function):
@@ -189,6 +203,7 @@ class _Tower(nn.Module):
             nn.Linear(hidden_dim, embed_dim),
         )
         self.extra_dim = extra_dim
+        self.mode = None          # None → module default (RB200_TOWER_MODE / auto); 0, 1 or 2 to force
         self._calls = 0
         self._init_weights()
 
@@ -206,7 +221,7 @@ class _Tower(nn.Module):
         seed = torch.initial_seed() & 0x7FFFFFFFFFFFFFFF
         l1, l2 = self.mlp[0], self.mlp[3]
         return _TowerFn.apply(ids, extra, self.embedding.weight, l1.weight, l1.bias, l2.weight, l2.bias, p, seed,
-                              (id(self) & 0xFFFF) * 1000003 + self._calls, keep_mask)
+                              (id(self) & 0xFFFF) * 1000003 + self._calls, keep_mask, self.mode)
 
 
 class UserTower(_Tower):

@@ -132,5 +132,7 @@ if __name__ == "__main__":
     run_steps("tt_dropout", 120, 90, 32, 64, 64, steps=2, seed=13, dropout=0.1)
     # D=128 (config C4 width), lr larger so the trajectory moves
     run_steps("tt_d128", 64, 80, 128, 128, 32, steps=2, seed=14, lr=1e-2)
+    # production widths with dropout (exercises the tensor-core tower kernels with injected masks), ragged batch
+    run_steps("tt_drop64", 700, 450, 64, 128, 200, steps=2, seed=15, dropout=0.1, with_pad=True)
     run_losses()
     run_inference()

@@ -8,7 +8,7 @@ from tests.parity import (batch_from_golden, dev, flat_mlp, grad_tol, masks_from
                           params_from_golden, rel_l2)
 
 pytestmark = pytest.mark.gpu
-CASES = ["tt_small", "tt_dup", "tt_dropout", "tt_d128"]
+CASES = ["tt_small", "tt_dup", "tt_dropout", "tt_d128", "tt_drop64"]
 
 
 def _trainer(model, g, **kw):

@@ -1,0 +1,113 @@
+"""Precision modes of the tower kernels at the reference's production widths (D = 64, H = 128):
+0 = fp32 FFMA, 1 = tcgen05 TF32 (stated looser bound), 2 = tcgen05 3xTF32 (fp32-grade, must meet the 1e-5 bar)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import two_tower_oracle as O
+from tests.parity import (batch_from_golden, dev, flat_mlp, grad_tol, masks_from_golden, model_from_golden, params_from_golden,
+                          rel_l2)
+
+pytestmark = pytest.mark.gpu
+
+#: stated bound of the single-TF32 fast mode (10-bit mantissa operands): forward 2e-3 abs on unit vectors,
+#: gradients 1e-2 relative to the tensor norm
+TF32_FWD, TF32_GRAD = 2e-3, 1e-2
+
+
+def _set_mode(model, mode):
+    model.user_tower.mode = mode
+    model.item_tower.mode = mode
+
+
+@pytest.mark.parametrize("case", ["tt_dup", "tt_drop64"])
+@pytest.mark.parametrize("mode", [0, 1, 2])
+def test_modes_against_fp64_oracle(golden, case, mode):
+    g = golden(case)
+    model = model_from_golden(g).train()
+    _set_mode(model, mode)
+    u, p, pg, n, ng = batch_from_golden(g, 0)
+    masks = masks_from_golden(g, 0)
+    mk = [None] * 3 if masks is None else [dev(m) for m in masks]
+    ue = model.user_tower(dev(u), keep_mask=mk[0])
+    pe = model.item_tower(dev(p), dev(pg), keep_mask=mk[1])
+    ne = model.item_tower(dev(n), dev(ng), keep_mask=mk[2])
+    loss = model.bpr_loss(ue, pe, ne)
+    loss.backward()
+    fwd_tol = TF32_FWD if mode == 1 else 2e-6
+    for got, key in ((ue, "user_emb"), (pe, "pos_emb"), (ne, "neg_emb")):
+        np.testing.assert_allclose(got.detach().cpu().numpy(), g["step0/" + key], atol=fwd_tol, rtol=0)
+    assert abs(loss.item() - float(g["step0/loss"])) <= (1e-4 if mode == 1 else 1e-6)
+    P = params_from_golden(g)
+    _, G64, _ = O.loss_and_grads(P, u, p, pg, n, ng, masks=masks, drop_p=float(g["dropout"]))
+    for k, prm in model.named_parameters():
+        tol = TF32_GRAD if mode == 1 else grad_tol(k)
+        assert rel_l2(prm.grad.detach().cpu().numpy(), G64[k]) <= tol, (case, mode, k, rel_l2(prm.grad.detach().cpu().numpy(), G64[k]))
+
+
+def test_modes_draw_identical_dropout_masks():
+    import recommendit_b200 as R
+    from recommendit_b200.two_tower import _TowerFn
+    torch.manual_seed(3)
+    model = R.TwoTowerModel(500, 300, 64, 128, dropout=0.3).cuda().train()
+    ids = torch.randint(1, 301, (333,), device="cuda")
+    genres = (torch.rand(333, 18, device="cuda") < 0.2).float()
+    t = model.item_tower
+    hids = []
+    for mode in (0, 2, 1):
+        w = t.embedding.weight.detach().clone().requires_grad_(True)
+        out = _TowerFn.apply(ids, genres, w, t.mlp[0].weight, t.mlp[0].bias, t.mlp[3].weight, t.mlp[3].bias, 0.3, 11, 5, None, mode)
+        hids.append(out.grad_fn.saved_tensors[6])
+    ref = hids[0]
+    strong = ref.abs() > 1e-3                       # units clearly active in the fp32 run
+    for h in hids[1:]:
+        assert ((h > 0) == (ref > 0))[strong | (ref == 0)].float().mean() > 0.999
+    assert torch.allclose(hids[1], ref, atol=2e-6)  # 3xTF32 hidden = fp32 hidden
+    kept = (ref > 0).float().mean().item()
+    assert 0.2 < kept < 0.5                          # ~ half active after ReLU × 0.7 kept
+
+
+@pytest.mark.parametrize("mode", [1, 2])
+def test_fused_step_modes_track_fp32_mode(golden, mode):
+    import recommendit_b200 as R
+    g = golden("tt_drop64")
+    res = {}
+    for m in (0, mode):
+        model = model_from_golden(g).train()
+        tr = R.FusedBPRTrainer(model, lr=float(g["lr"]), use_cuda_graph=False, tower_mode=m)
+        losses = []
+        for s in range(2):
+            tr.load_packed(tr.pack_host(*batch_from_golden(g, s)))
+            losses.append(tr.step(masks=[torch.from_numpy(x) for x in masks_from_golden(g, s)]).item())
+        res[m] = (losses, tr.views())
+    tol_l, tol_g = (1e-4, TF32_GRAD) if mode == 1 else (2e-6, 1e-5)
+    assert np.allclose(res[mode][0], res[0][0], atol=tol_l)
+    assert np.allclose(res[mode][0], [float(g["step0/loss"]), float(g["step1/loss"])], atol=max(tol_l, 5e-5))
+    for key in ("user_mlp_grad", "user_uniq_grads", "item_uniq_grads"):
+        assert rel_l2(res[mode][1][key].cpu().numpy(), res[0][1][key].cpu().numpy()) <= tol_g, key
+    assert torch.equal(res[mode][1]["item_uniq_ids"], res[0][1]["item_uniq_ids"])
+
+
+def test_full_batch_mode2_equals_mode0():
+    """C2 sizes (B = 8192): the tensor-core path and the FFMA path agree to fp32 rounding on a whole step."""
+    import recommendit_b200 as R
+    torch.manual_seed(0)
+    nu, ni, B = 6040, 3952, 8192
+    rng = np.random.default_rng(2)
+    u, p, n = rng.integers(0, nu + 1, B), rng.integers(0, ni + 1, B), rng.integers(0, ni + 1, B)
+    table = (rng.random((ni + 1, 18)) < 0.1).astype(np.float32)
+    base = R.TwoTowerModel(nu, ni, 64, 128, dropout=0.1).cuda().train()
+    sd = {k: v.clone() for k, v in base.state_dict().items()}
+    out = {}
+    for m in (0, 2):
+        model = R.TwoTowerModel(nu, ni, 64, 128, dropout=0.1).cuda().train()
+        model.load_state_dict(sd)
+        tr = R.FusedBPRTrainer(model, use_cuda_graph=False, tower_mode=m, seed=5)
+        loss = tr.step_host(u, p, table[p], n, table[n])
+        out[m] = (loss, tr.views(), tr.opt_state.total_norm)
+    assert abs(out[0][0] - out[2][0]) <= 1e-6
+    assert abs(out[0][2] - out[2][2]) <= 1e-5 * out[0][2]
+    for key in ("user_mlp_grad", "item_mlp_grad", "user_uniq_grads", "item_uniq_grads", "user_emb", "pos_emb"):
+        a, b = out[2][1][key].cpu().numpy(), out[0][1][key].cpu().numpy()
+        tol = 3e-5 if key == "item_mlp_grad" else 1e-5          # contains the cancellation-heavy second-bias gradient
+        assert rel_l2(a, b) <= tol, (key, rel_l2(a, b))

@@ -9,7 +9,7 @@ from tests.parity import (batch_from_golden, dev, grad_tol, masks_from_golden, m
                           rel_l2)
 
 pytestmark = pytest.mark.gpu
-CASES = ["tt_small", "tt_dup", "tt_dropout", "tt_d128"]
+CASES = ["tt_small", "tt_dup", "tt_dropout", "tt_d128", "tt_drop64"]
 
 
 def _run_reference_step_body(model, g, s):

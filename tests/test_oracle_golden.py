@@ -5,7 +5,7 @@ import pytest
 
 from oracle import two_tower_oracle as O
 
-CASES = ["tt_small", "tt_dup", "tt_dropout", "tt_d128"]
+CASES = ["tt_small", "tt_dup", "tt_dropout", "tt_d128", "tt_drop64"]
 
 
 def _params(g, prefix, dtype=np.float32):
