@@ -63,9 +63,16 @@ __device__ __forceinline__ void commit(uint64_t* bar) {
 
 // ---- descriptors ------------------------------------------------------------------------------------------- //
 // instruction descriptor, kind::tf32, fp32 accumulate, both operands K-major (cute::UMMA::InstrDescriptor bit layout)
-__host__ __device__ constexpr uint32_t idesc_tf32(int M, int N) {
-    return (1u << 4) /*c = F32*/ | (2u << 7) /*a = TF32*/ | (2u << 10) /*b = TF32*/ | ((uint32_t)(N >> 3) << 17) |
-           ((uint32_t)(M >> 4) << 24);
+__host__ __device__ constexpr uint32_t idesc_tf32(int M, int N, bool a_mn_major = false, bool b_mn_major = false) {
+    return (1u << 4) /*c = F32*/ | (2u << 7) /*a = TF32*/ | (2u << 10) /*b = TF32*/ | ((a_mn_major ? 1u : 0u) << 15) |
+           ((b_mn_major ? 1u : 0u) << 16) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+// MN-major no-swizzle operand ([MN × K] logical, stored so that 4 consecutive MN elements share a 16-byte unit): a core
+// matrix is 8 K-rows × 16 B.  offset(mn, k) = (mn/4)·128 + (k/8)·(MN/4)·128 + (k%8)·16 + (mn%4)·4
+//   ⇒ SBO (MN-block stride) = 128 B, LBO (K-block stride) = (MN/4)·128 B.  A row-major [K][MN] global array (e.g. the
+// batch-major activations of a weight-gradient product) is staged with plain 16-byte copies, no transposition.
+__device__ __forceinline__ uint32_t mnmajor_offset(int MN, int mn, int k) {
+    return (uint32_t)(((mn >> 2) << 7) + (k >> 3) * ((MN >> 2) << 7) + ((k & 7) << 4) + ((mn & 3) << 2));
 }
 // shared-memory matrix descriptor, no swizzle (cute::UMMA::SmemDescriptor bit layout, version 1 = Blackwell)
 __device__ __forceinline__ uint64_t smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
