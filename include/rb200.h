@@ -67,6 +67,8 @@ typedef struct rb200_tower_job {
     int extra_dim;
     int extra_by_id;           /* 0: extra is [B, extra_dim] per sample (the reference's batch
                                   format); 1: extra is [n_rows, extra_dim], looked up by id      */
+    const void* img;           /* tensor-core modes: optional weight image from rb200_tower_prep
+                                  (NULL ⇒ staged internally from the workspace)                  */
 } rb200_tower_job;
 
 /* Runs up to 3 tower evaluations (user / positive items / negative items) in ONE launch; the
@@ -77,7 +79,15 @@ typedef struct rb200_tower_job {
  * err_flag: optional device int, bit 0 is set when an id is out of range. */
 int rb200_tower_fwd(const rb200_tower_job* jobs_host, int n_jobs, int D, int H, float dropout_p,
                     uint64_t seed, uint64_t offset, const int64_t* offset_dev, int mode, int* err_flag,
-                    void* stream);
+                    void* workspace, size_t workspace_bytes, void* stream);
+/* workspace of rb200_tower_fwd: 0 bytes in mode 0; room for the weight images of the jobs whose `img` is NULL otherwise */
+size_t rb200_tower_fwd_workspace_bytes(int n_jobs, int D, int H, int extra_dim, int mode);
+/* Tensor-core modes consume the MLP weights as ready-made UMMA operand images (hi/lo-split, canonical K-major layout,
+ * also the transposed ones the backward needs), which a CTA pulls into shared memory with ONE bulk asynchronous copy
+ * (TMA engine).  rb200_tower_prep builds the image of one weight set (W1 [H, D+extra_dim], W2 [D, H]) into `img`
+ * (rb200_tower_img_bytes bytes, 16-byte aligned); it must be re-run whenever the weights change. */
+size_t rb200_tower_img_bytes(int D, int H, int extra_dim);
+int rb200_tower_prep(const float* W1, const float* W2, int D, int H, int extra_dim, void* img, void* stream);
 /* mode (both tower entry points): 0 = fp32 FFMA kernels (parity mode, any supported width);
  *   1 = tcgen05 tensor cores, single TF32 (fast mode, ~1e-3 relative error on activations/gradients);
  *   2 = tcgen05 tensor cores, 3xTF32 error-compensated (fp32-grade, meets the 1e-5 parity bound).
@@ -103,6 +113,7 @@ typedef struct rb200_tower_bwd_job {
     float* dpre;          /* [B,D] scratch/out */
     float* dact;          /* [B,H] scratch/out */
     float* dRows;         /* [B,D] out */
+    const void* img;      /* tensor-core modes: optional weight image from rb200_tower_prep, or NULL */
 } rb200_tower_bwd_job;
 
 size_t rb200_tower_bwd_workspace_bytes(int D, int H, int extra_dim);

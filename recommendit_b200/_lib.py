@@ -24,13 +24,13 @@ class RB200Error(RuntimeError):
 class TowerJob(C.Structure):
     _fields_ = [("table", c_f), ("ids", c_f), ("extra", c_f), ("W1", c_f), ("b1", c_f), ("W2", c_f), ("b2", c_f),
                 ("out", c_f), ("hid", c_f), ("denom", c_f), ("keep_mask", c_f), ("n_rows", C.c_int64),
-                ("B", C.c_int), ("extra_dim", C.c_int), ("extra_by_id", C.c_int)]
+                ("B", C.c_int), ("extra_dim", C.c_int), ("extra_by_id", C.c_int), ("img", c_f)]
 
 
 class TowerBwdJob(C.Structure):
     _fields_ = [("table", c_f), ("ids", c_f), ("extra", c_f), ("n_rows", C.c_int64), ("B", C.c_int),
                 ("extra_dim", C.c_int), ("extra_by_id", C.c_int), ("W1", c_f), ("W2", c_f), ("dY", c_f), ("y", c_f),
-                ("denom", c_f), ("hid", c_f), ("dpre", c_f), ("dact", c_f), ("dRows", c_f)]
+                ("denom", c_f), ("hid", c_f), ("dpre", c_f), ("dact", c_f), ("dRows", c_f), ("img", c_f)]
 
 
 class SumsqSeg(C.Structure):
@@ -80,7 +80,10 @@ SIGNATURES = {
     "rb200_sm_count": (I, []),
     "rb200_sizeof": (SZ, [I]),
     "rb200_launch_count": (U64, []),
-    "rb200_tower_fwd": (I, [C.POINTER(TowerJob), I, I, I, F, U64, U64, P, I, P, P]),
+    "rb200_tower_fwd": (I, [C.POINTER(TowerJob), I, I, I, F, U64, U64, P, I, P, P, SZ, P]),
+    "rb200_tower_fwd_workspace_bytes": (SZ, [I, I, I, I, I]),
+    "rb200_tower_img_bytes": (SZ, [I, I, I]),
+    "rb200_tower_prep": (I, [P, P, I, I, I, P, P]),
     "rb200_tower_bwd_workspace_bytes": (SZ, [I, I, I]),
     "rb200_tower_bwd": (I, [C.POINTER(TowerBwdJob), I, I, I, F, I, P, I, P, SZ, P]),
     "rb200_bpr_pair": (I, [P, P, P, I, I, P, P, P, P, F, P, SZ, P]),

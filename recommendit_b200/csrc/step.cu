@@ -9,6 +9,10 @@ int rb_scatter_tables(int phase, int n_tables, const int64_t* const ids_a[2], co
                       int* const row_slot[2], void* workspace, size_t workspace_bytes, cudaStream_t st);
 int rb_sumsq_accumulate(rb200_opt_state* st, const rb200_sumsq_seg* segs, int n_segs, int do_clip, void* workspace,
                         size_t workspace_bytes, cudaStream_t s);
+int rb_tower_prep_tc(int n_sets, const float* const W1[], const float* const W2[], const int E[], int D, int H,
+                     unsigned char* const img[], cudaStream_t st);
+size_t rb_tower_img_bytes(int D, int H, int E);
+bool rb_tower_tc_supported(int D, int H, int E);
 
 namespace {
 
@@ -21,6 +25,7 @@ struct StepWs {
     int64_t* ids_pn;               // [2B]
     float *g_user_mlp, *g_item_mlp;   // contiguous
     int64_t *uniq_u, *uniq_i; float *ug_u, *ug_i; int *n_uniq;   // n_uniq[0]=user, [1]=item
+    unsigned char *img_user, *img_item;   // tensor-core weight images
     void *ws_bwd, *ws_loss, *ws_scatter, *ws_sumsq;
     size_t b_bwd, b_loss, b_scatter, b_sumsq;
     int P_user, P_item;
@@ -45,6 +50,9 @@ bool carve(RbArena& ar, const rb200_step_params& s, StepWs& w) {
     w.uniq_u = ar.take<int64_t>(B); w.uniq_i = ar.take<int64_t>(items * B);
     w.ug_u = ar.take<float>(B * D); w.ug_i = ar.take<float>(items * B * D);
     w.n_uniq = ar.take<int>(2);
+    const bool tc = rb_tower_tc_supported(s.D, s.H, s.extra_dim);
+    w.img_user = ar.take<unsigned char>(tc ? rb_tower_img_bytes(s.D, s.H, 0) : 16);
+    w.img_item = ar.take<unsigned char>(tc ? rb_tower_img_bytes(s.D, s.H, s.extra_dim) : 16);
     w.b_bwd = rb200_tower_bwd_workspace_bytes(s.D, s.H, s.extra_dim);
     w.ws_bwd = ar.take<char>(w.b_bwd);
     const size_t l0 = rb200_bpr_pair_workspace_bytes(s.B), l1 = s.loss_kind == 1 ? rb200_bpr_inbatch_workspace_bytes(s.B, s.D) : 0;
@@ -169,8 +177,20 @@ extern "C" int rb200_bpr_step(const rb200_step_params* s, void* stream) {
         RB_CUDA(cudaEventRecord(side->join, side->s));
     }
 
+    // ---- tensor-core modes: stage both towers' weight images once for forward and backward ----------- //
+    const bool tc = s->tower_mode != 0;
+    if (tc) {
+        RB_REQUIRE(rb_tower_tc_supported(D, H, E), "bpr_step: tower_mode %d needs D=64, H=128, extra_dim<=24", s->tower_mode);
+        const float* pw1[2] = {s->user_mlp, s->item_mlp};
+        const float* pw2[2] = {s->user_mlp + H * D + H, s->item_mlp + H * Din_i + H};
+        const int pe[2] = {0, E};
+        unsigned char* pim[2] = {w.img_user, w.img_item};
+        if ((rc = rb_tower_prep_tc(2, pw1, pw2, pe, D, H, pim, st))) return rc;
+    }
+
     // ---- forward: user / positive / negative towers in one launch -------------------------- //
     rb200_tower_job fj[3] = {};
+    fj[0].img = tc ? w.img_user : nullptr;
     fj[0].table = s->user_table; fj[0].ids = s->user_ids; fj[0].extra = nullptr; fj[0].extra_dim = 0;
     fj[0].W1 = s->user_mlp; fj[0].b1 = s->user_mlp + H * D; fj[0].W2 = s->user_mlp + H * D + H; fj[0].b2 = s->user_mlp + H * D + H + D * H;
     fj[0].out = w.u; fj[0].hid = w.hid_u; fj[0].denom = w.den_u; fj[0].keep_mask = s->keep_mask_user;
@@ -183,8 +203,10 @@ extern "C" int rb200_bpr_step(const rb200_step_params* s, void* stream) {
         j.out = w.p + (size_t)t * B * D; j.hid = w.hid_pn + (size_t)t * B * H; j.denom = w.den_pn + (size_t)t * B;
         j.keep_mask = t == 0 ? s->keep_mask_pos : s->keep_mask_neg;
         j.n_rows = s->n_item_rows; j.B = B;
+        j.img = tc ? w.img_item : nullptr;
     }
-    if ((rc = rb200_tower_fwd(fj, 1 + items, D, H, s->dropout_p, s->seed, 0, &s->opt->step, s->tower_mode, s->err_flag, st))) return rc;
+    if ((rc = rb200_tower_fwd(fj, 1 + items, D, H, s->dropout_p, s->seed, 0, &s->opt->step, s->tower_mode, s->err_flag, nullptr, 0,
+                              st))) return rc;
 
     RB_STAGE_EVENT();
     // ---- loss + gradient w.r.t. the tower outputs ------------------------------------------- //
@@ -200,6 +222,7 @@ extern "C" int rb200_bpr_step(const rb200_step_params* s, void* stream) {
     bj[0].table = s->user_table; bj[0].ids = s->user_ids; bj[0].extra = nullptr; bj[0].n_rows = s->n_user_rows; bj[0].B = B;
     bj[0].extra_dim = 0; bj[0].W1 = fj[0].W1; bj[0].W2 = fj[0].W2; bj[0].dY = w.du; bj[0].y = w.u; bj[0].denom = w.den_u;
     bj[0].hid = w.hid_u; bj[0].dpre = w.dpre_u; bj[0].dact = w.dact_u; bj[0].dRows = w.drows_u;
+    bj[0].img = tc ? w.img_user : nullptr;
     if ((rc = rb200_tower_bwd(bj, 1, D, H, s->dropout_p, s->tower_mode, w.g_user_mlp, 0, w.ws_bwd, w.b_bwd, st))) return rc;
     for (int t = 0; t < items; ++t) {
         rb200_tower_bwd_job& j = bj[t];
@@ -209,6 +232,7 @@ extern "C" int rb200_bpr_step(const rb200_step_params* s, void* stream) {
         j.dY = w.dpn + (size_t)t * B * D; j.y = w.p + (size_t)t * B * D; j.denom = w.den_pn + (size_t)t * B;
         j.hid = w.hid_pn + (size_t)t * B * H; j.dpre = w.dpre_pn + (size_t)t * B * D; j.dact = w.dact_pn + (size_t)t * B * H;
         j.dRows = w.drows_pn + (size_t)t * B * D;
+        j.img = tc ? w.img_item : nullptr;
     }
     if ((rc = rb200_tower_bwd(bj, items, D, H, s->dropout_p, s->tower_mode, w.g_item_mlp, 0, w.ws_bwd, w.b_bwd, st))) return rc;
 

@@ -524,12 +524,19 @@ int partition_ctas(JobT* jobs, int n_jobs, int D, int H) {
 
 }  // namespace
 
-int rb_tower_fwd_tc(FwdParams& p, int D, int H, int mode, cudaStream_t st);
-int rb_tower_bwd_tc(BwdParams& p, int D, int H, int mode, float* grads_out, int accumulate, cudaStream_t st);
+int rb_tower_fwd_tc(FwdParams& p, int D, int H, int mode, void* workspace, size_t workspace_bytes, cudaStream_t st);
+int rb_tower_bwd_tc(BwdParams& p, int D, int H, int mode, float* grads_out, int accumulate, unsigned char* img_ws, cudaStream_t st);
 bool rb_tower_tc_supported(int D, int H, int E);
+size_t rb_tower_img_bytes(int D, int H, int E);
+
+extern "C" size_t rb200_tower_fwd_workspace_bytes(int n_jobs, int D, int H, int extra_dim, int mode) {
+    if (mode == 0 || !rb_tower_tc_supported(D, H, extra_dim)) return 0;
+    return 256 + (size_t)(n_jobs < 2 ? n_jobs : 2) * (rb_tower_img_bytes(D, H, extra_dim) + 256);
+}
 
 extern "C" int rb200_tower_fwd(const rb200_tower_job* jobs, int n_jobs, int D, int H, float dropout_p,
-                               uint64_t seed, uint64_t offset, const int64_t* offset_dev, int mode, int* err_flag, void* stream) {
+                               uint64_t seed, uint64_t offset, const int64_t* offset_dev, int mode, int* err_flag, void* workspace,
+                               size_t workspace_bytes, void* stream) {
     RB_REQUIRE(jobs && n_jobs >= 1 && n_jobs <= MAX_JOBS, "tower_fwd: n_jobs must be 1..3");
     RB_REQUIRE(mode >= 0 && mode <= 2, "tower_fwd: mode must be 0 (fp32 FFMA), 1 (tcgen05 TF32) or 2 (tcgen05 3xTF32)");
     RB_REQUIRE(dims_supported(D, H), "tower_fwd: unsupported widths D=%d H=%d (D in {32,64,128}, H in {64,128,256})", D, H);
@@ -545,7 +552,7 @@ extern "C" int rb200_tower_fwd(const rb200_tower_job* jobs, int n_jobs, int D, i
         RB_REQUIRE(s.table && s.ids && s.W1 && s.b1 && s.W2 && s.b2 && s.out, "tower_fwd: NULL pointer in job %d", j);
         FwdJob& d = p.job[p.n_jobs++];
         d.table = s.table; d.ids = s.ids; d.extra = s.extra; d.W1 = s.W1; d.b1 = s.b1; d.W2 = s.W2; d.b2 = s.b2;
-        d.out = s.out; d.hid = s.hid; d.denom = s.denom; d.keep_mask = s.keep_mask;
+        d.out = s.out; d.hid = s.hid; d.denom = s.denom; d.keep_mask = s.keep_mask; d.img = (const unsigned char*)s.img;
         d.n_rows = s.n_rows; d.B = s.B; d.E = s.extra_dim; d.extra_by_id = s.extra_by_id;
         const size_t b = fwd_smem_bytes(D, H, s.extra_dim);
         if (b > smem) smem = b;
@@ -554,7 +561,7 @@ extern "C" int rb200_tower_fwd(const rb200_tower_job* jobs, int n_jobs, int D, i
     if (mode != 0) {
         for (int j = 0; j < p.n_jobs; ++j)
             RB_REQUIRE(rb_tower_tc_supported(D, H, p.job[j].E), "tower_fwd: tcgen05 mode supports D=64, H=128, extra_dim<=24 (got D=%d H=%d E=%d)", D, H, p.job[j].E);
-        return rb_tower_fwd_tc(p, D, H, mode, (cudaStream_t)stream);
+        return rb_tower_fwd_tc(p, D, H, mode, workspace, workspace_bytes, (cudaStream_t)stream);
     }
     RB_REQUIRE((int)smem <= rb_max_smem_optin(), "tower_fwd: D=%d H=%d needs %zu B of shared memory (> %d)", D, H, smem,
                rb_max_smem_optin());
@@ -566,7 +573,8 @@ extern "C" int rb200_tower_fwd(const rb200_tower_job* jobs, int n_jobs, int D, i
 
 extern "C" size_t rb200_tower_bwd_workspace_bytes(int D, int H, int extra_dim) {
     const size_t P = (size_t)H * (D + extra_dim) + H + (size_t)D * H + D;
-    return 256 + sizeof(float) * P * (size_t)rb_sm_count();      // tcgen05 path: one partial per SM; FFMA path: half
+    // split-K partials (at most one per SM) + room for one weight image of the tcgen05 path
+    return 512 + sizeof(float) * P * (size_t)rb_sm_count() + (rb_tower_tc_supported(D, H, extra_dim) ? rb_tower_img_bytes(D, H, extra_dim) + 256 : 0);
 }
 
 extern "C" int rb200_tower_bwd(const rb200_tower_bwd_job* jobs, int n_jobs, int D, int H, float dropout_p, int mode,
@@ -592,7 +600,7 @@ extern "C" int rb200_tower_bwd(const rb200_tower_bwd_job* jobs, int n_jobs, int 
         BwdJob& d = p.job[p.n_jobs++];
         d.table = s.table; d.ids = s.ids; d.extra = s.extra; d.n_rows = s.n_rows; d.B = s.B; d.E = E; d.extra_by_id = s.extra_by_id;
         d.W1 = s.W1; d.W2 = s.W2; d.dY = s.dY; d.y = s.y; d.denom = s.denom; d.hid = s.hid;
-        d.dpre = s.dpre; d.dact = s.dact; d.dRows = s.dRows;
+        d.dpre = s.dpre; d.dact = s.dact; d.dRows = s.dRows; d.img = (const unsigned char*)s.img;
         total_rows += s.B;
     }
     const int Din = D + E, Kp = (Din + 3) & ~3;
@@ -605,11 +613,15 @@ extern "C" int rb200_tower_bwd(const rb200_tower_bwd_job* jobs, int n_jobs, int 
     if (mode != 0) {
         RB_REQUIRE(rb_tower_tc_supported(D, H, E), "tower_bwd: tcgen05 mode supports D=64, H=128, extra_dim<=24");
         RbArena tar(workspace, workspace_bytes);
-        p.nsplit = rb_sm_count();
+        int ns = (int)((total_rows + 255) / 256);                 // >= 256 batch rows per CTA
+        if (ns > rb_sm_count()) ns = rb_sm_count();
+        if (ns < 1) ns = 1;
+        p.nsplit = ns;
         p.P = P;
         p.part = tar.take<float>((size_t)p.nsplit * P);
+        unsigned char* img_ws = tar.take<unsigned char>(rb_tower_img_bytes(D, H, E));
         if (!workspace || !tar.ok()) return rb_set_error(RB200_ERR_WORKSPACE, "tower_bwd: workspace too small (%zu given)", workspace_bytes);
-        return rb_tower_bwd_tc(p, D, H, mode, grads_out, accumulate, st);
+        return rb_tower_bwd_tc(p, D, H, mode, grads_out, accumulate, img_ws, st);
     }
     int nsplit = rb_sm_count() / 2;
     const long long stages = (total_rows + RT - 1) / RT;

@@ -8,7 +8,7 @@ constexpr float NORM_EPS = 1e-12f;
 struct FwdJob {
     const float* table; const int64_t* ids; const float* extra;
     const float* W1; const float* b1; const float* W2; const float* b2;
-    float* out; float* hid; float* denom; const uint8_t* keep_mask;
+    float* out; float* hid; float* denom; const uint8_t* keep_mask; const unsigned char* img;
     long long n_rows; int B; int E; int extra_by_id; int cta_begin; int cta_count;
 };
 struct FwdParams {
@@ -21,7 +21,7 @@ struct BwdJob {
     const float* table; const int64_t* ids; const float* extra; long long n_rows; int B; int E;
     const float* W1; const float* W2;
     const float* dY; const float* y; const float* denom; const float* hid;
-    float* dpre; float* dact; float* dRows;
+    float* dpre; float* dact; float* dRows; const unsigned char* img;
     int extra_by_id; int cta_begin; int cta_count;
 };
 struct BwdParams {

@@ -17,13 +17,68 @@
 
 namespace {
 
-constexpr int NT = 128;        // threads per CTA = rows per tile = TMEM lanes
+constexpr int NT = 256;        // 8 warps: warps w and w+4 share TMEM lane quadrant w%4 and split the columns
+constexpr int ROWS = 128;      // samples per tile = TMEM lanes
 constexpr int TMEM_COLS = 256;
 
-struct Smem {
-    unsigned char* base;
-    __device__ unsigned char* at(size_t off) const { return base + off; }
+// ---- weight images --------------------------------------------------------------------------------------------- //
+// [W1 hi|lo : H × Kp] [W2 hi|lo : D × H] [W2ᵀ hi|lo : H × D] [W1[:, :D]ᵀ hi|lo : D × H], each in the K-major UMMA layout
+struct ImgLayout {
+    size_t w1, w2, w2t, w1t, total;
+    int Kp;
 };
+__host__ __device__ inline ImgLayout img_layout(int D, int H, int E) {
+    ImgLayout L;
+    L.Kp = (D + E + 7) & ~7;
+    L.w1 = 0;
+    L.w2 = L.w1 + (size_t)2 * H * L.Kp * 4;
+    L.w2t = L.w2 + (size_t)2 * D * H * 4;
+    L.w1t = L.w2t + (size_t)2 * H * D * 4;
+    L.total = L.w1t + (size_t)2 * D * H * 4;
+    return L;
+}
+
+struct PrepSet { const float* W1; const float* W2; unsigned char* img; int E; };
+struct PrepParams { PrepSet set[2]; int n_sets, D, H; };
+
+__device__ __forceinline__ void put4_both(unsigned char* hi_base, size_t lo_delta, int R, int r, int k, const float4& v) {
+    const uint32_t off = umma::kmajor_offset(R, r, k);
+    float4 hi, lo;
+    umma::split4(v, hi, lo);
+    *reinterpret_cast<float4*>(hi_base + off) = hi;
+    *reinterpret_cast<float4*>(hi_base + lo_delta + off) = lo;
+}
+
+__global__ void __launch_bounds__(256) tower_prep_kernel(const PrepParams p) {
+    const PrepSet S = p.set[blockIdx.y];
+    const int D = p.D, H = p.H, Din = D + S.E;
+    const ImgLayout L = img_layout(D, H, S.E);
+    const int Kp = L.Kp;
+    const int n1 = H * (Kp / 4), n2 = D * (H / 4), n3 = H * (D / 4), n4 = D * (H / 4);
+    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < n1 + n2 + n3 + n4; idx += gridDim.x * blockDim.x) {
+        if (idx < n1) {                       // W1 [H × Kp]: consecutive threads → consecutive rows (conflict-free image writes)
+            const int c4 = idx / H, h = idx - c4 * H, k = c4 * 4;
+            float4 v;
+            v.x = k + 0 < Din ? __ldg(S.W1 + (long long)h * Din + k + 0) : 0.f;
+            v.y = k + 1 < Din ? __ldg(S.W1 + (long long)h * Din + k + 1) : 0.f;
+            v.z = k + 2 < Din ? __ldg(S.W1 + (long long)h * Din + k + 2) : 0.f;
+            v.w = k + 3 < Din ? __ldg(S.W1 + (long long)h * Din + k + 3) : 0.f;
+            put4_both(S.img + L.w1, (size_t)H * Kp * 4, H, h, k, v);
+        } else if (idx < n1 + n2) {           // W2 [D × H]
+            const int i = idx - n1, c4 = i / D, d = i - c4 * D;
+            put4_both(S.img + L.w2, (size_t)D * H * 4, D, d, c4 * 4, __ldg(reinterpret_cast<const float4*>(S.W2 + (long long)d * H) + c4));
+        } else if (idx < n1 + n2 + n3) {      // W2ᵀ [H × D]: (h, d) = W2[d][h]
+            const int i = idx - n1 - n2, c4 = i / H, h = i - c4 * H;
+            const float* wp = S.W2 + (long long)(c4 * 4) * H + h;
+            put4_both(S.img + L.w2t, (size_t)H * D * 4, H, h, c4 * 4, make_float4(__ldg(wp), __ldg(wp + H), __ldg(wp + 2 * H), __ldg(wp + 3 * H)));
+        } else {                              // W1[:, :D]ᵀ [D × H]: (d, h) = W1[h][d]
+            const int i = idx - n1 - n2 - n3, c4 = i / D, d = i - c4 * D;
+            const float* wp = S.W1 + (long long)(c4 * 4) * Din + d;
+            put4_both(S.img + L.w1t, (size_t)D * H * 4, D, d, c4 * 4,
+                      make_float4(__ldg(wp), __ldg(wp + Din), __ldg(wp + 2 * Din), __ldg(wp + 3 * Din)));
+        }
+    }
+}
 
 // store 4 consecutive-k values of row r (hi and optionally lo) into an [R × K] K-major operand
 template <int MODE>
@@ -55,8 +110,7 @@ __device__ __forceinline__ void issue_gemm(uint32_t tmem_d, unsigned char* a_hi,
     }
 }
 
-struct Pipe {          // TMEM + one mbarrier, with bounded waits
-    uint32_t tmem;
+struct Bar {           // mbarrier with bounded waits and a sticky failure flag
     uint64_t* bar;
     uint32_t phase;
     int* dead;
@@ -64,27 +118,28 @@ struct Pipe {          // TMEM + one mbarrier, with bounded waits
     __device__ void wait() {
         if (!*dead && !umma::mbar_wait(bar, phase)) { *dead = 1; if (err_flag) atomicOr(err_flag, 2); }
         phase ^= 1;
-        umma::fence_after_sync();
     }
 };
 
-#define RB_TC_PROLOGUE(err_ptr)                                                        \
-    __shared__ __align__(8) uint64_t mbar;                                             \
-    __shared__ uint32_t tmem_slot;                                                     \
-    __shared__ int dead;                                                               \
-    const int tid = threadIdx.x, warp = tid >> 5;                                      \
-    if (warp == 0) umma::tmem_alloc(&tmem_slot, TMEM_COLS);                            \
-    if (tid == 0) { umma::mbar_init(&mbar, 1); umma::fence_mbar_init(); dead = 0; }    \
-    umma::fence_before_sync();                                                         \
-    __syncthreads();                                                                   \
-    umma::fence_after_sync();                                                          \
-    Pipe pipe{tmem_slot, &mbar, 0u, &dead, err_ptr};                                   \
-    const uint32_t lane_off = (uint32_t)(warp * 32) << 16;
+#define RB_TC_PROLOGUE(err_ptr)                                                                                   \
+    __shared__ __align__(8) uint64_t mma_bar_s, w_bar_s;                                                          \
+    __shared__ uint32_t tmem_slot;                                                                                \
+    __shared__ int dead;                                                                                          \
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;                                                \
+    if (warp == 0) umma::tmem_alloc(&tmem_slot, TMEM_COLS);                                                       \
+    if (tid == 0) { umma::mbar_init(&mma_bar_s, 1); umma::mbar_init(&w_bar_s, 1); umma::fence_mbar_init(); dead = 0; } \
+    umma::fence_before_sync();                                                                                    \
+    __syncthreads();                                                                                              \
+    umma::fence_after_sync();                                                                                     \
+    const uint32_t tmem = tmem_slot;                                                                              \
+    Bar mma_bar{&mma_bar_s, 0u, &dead, err_ptr}, w_bar{&w_bar_s, 0u, &dead, err_ptr};                              \
+    const int r_own = ((warp & 3) << 5) + lane, half = warp >> 2;     /* TMEM lane (= tile row) and column half */ \
+    const uint32_t lane_off = (uint32_t)((warp & 3) * 32) << 16;
 
 #define RB_TC_EPILOGUE()                                                               \
     umma::fence_before_sync();                                                         \
     __syncthreads();                                                                   \
-    if (warp == 0) umma::tmem_free(pipe.tmem, TMEM_COLS);
+    if (warp == 0) umma::tmem_free(tmem, TMEM_COLS);
 
 __device__ __forceinline__ int find_job(const int* begin, int n_jobs) {
     int j = 0;
@@ -100,76 +155,90 @@ __device__ __forceinline__ int find_job(const int* begin, int n_jobs) {
 template <int D, int H, int MODE>
 __global__ void __launch_bounds__(NT, 1) tower_fwd_tc_kernel(const FwdParams p) {
     extern __shared__ __align__(1024) unsigned char smem[];
+    __shared__ float ss_part[2][ROWS];
     RB_TC_PROLOGUE(p.err_flag)
     int begins[MAX_JOBS];
 #pragma unroll
     for (int t = 0; t < MAX_JOBS; ++t) begins[t] = p.job[t].cta_begin;
     const int j = find_job(begins, p.n_jobs);
     const FwdJob J = p.job[j];
-    const int E = J.E, Din = D + E, Kp = (Din + 7) & ~7;
-    const int row = ((int)blockIdx.x - J.cta_begin) * NT + tid;
-    const bool valid = row < J.B;
+    const int E = J.E, Din = D + E;
+    const ImgLayout L = img_layout(D, H, E);
+    const int Kp = L.Kp;
+    const int row0 = ((int)blockIdx.x - J.cta_begin) * ROWS;
 
-    // ---- stage 1: X [128 × Kp], W1 [H × Kp] ------------------------------------------------------------------ //
+    // ---- stage 1: X [128 × Kp] gathered by the threads, W1 image pulled in by one bulk asynchronous copy --------- //
     unsigned char* x_hi = smem;
-    unsigned char* x_lo = x_hi + (size_t)NT * Kp * 4;
-    unsigned char* w1_hi = x_lo + (size_t)NT * Kp * 4;
+    unsigned char* x_lo = x_hi + (size_t)ROWS * Kp * 4;
+    unsigned char* w1_hi = x_lo + (size_t)ROWS * Kp * 4;
     unsigned char* w1_lo = w1_hi + (size_t)H * Kp * 4;
+    if (tid == 0) {
+        const uint32_t bytes = (uint32_t)((MODE == 2 ? 2 : 1) * H * Kp * 4);
+        umma::mbar_expect_tx(&w_bar_s, bytes);
+        umma::bulk_g2s(w1_hi, J.img + L.w1, bytes, &w_bar_s);
+    }
     {
-        long long id = valid ? J.ids[row] : 0;
-        if ((unsigned long long)id >= (unsigned long long)J.n_rows) { if (p.err_flag) atomicOr(p.err_flag, 1); id = 0; }
-        const float4* src = reinterpret_cast<const float4*>(J.table + id * D);
-#pragma unroll 4
-        for (int c4 = 0; c4 < D / 4; ++c4)
-            put4<MODE>(x_hi, x_lo, NT, tid, c4 * 4, valid ? __ldg(src + c4) : make_float4(0.f, 0.f, 0.f, 0.f));
-        const float* ex = J.extra ? J.extra + (J.extra_by_id ? id : (long long)row) * E : nullptr;
-        for (int k = D; k < Kp; k += 4) {
-            float4 v;
-            v.x = (valid && k + 0 < Din) ? __ldg(ex + k + 0 - D) : 0.f;
-            v.y = (valid && k + 1 < Din) ? __ldg(ex + k + 1 - D) : 0.f;
-            v.z = (valid && k + 2 < Din) ? __ldg(ex + k + 2 - D) : 0.f;
-            v.w = (valid && k + 3 < Din) ? __ldg(ex + k + 3 - D) : 0.f;
-            put4<MODE>(x_hi, x_lo, NT, tid, k, v);
-        }
-        if (tid < H) {
-            const float* wr = J.W1 + (long long)tid * Din;
-            for (int k = 0; k < Kp; k += 4) {
-                float4 v;
-                v.x = k + 0 < Din ? __ldg(wr + k + 0) : 0.f;
-                v.y = k + 1 < Din ? __ldg(wr + k + 1) : 0.f;
-                v.z = k + 2 < Din ? __ldg(wr + k + 2) : 0.f;
-                v.w = k + 3 < Din ? __ldg(wr + k + 3) : 0.f;
-                put4<MODE>(w1_hi, w1_lo, H, tid, k, v);
+        // lane → (row%8 = lane&7, 16-byte chunk = 4·cq + lane>>3): 64-byte global segments, conflict-free 16-byte stores
+        const int K4 = Kp / 4, CQ = (K4 + 3) / 4;
+        for (int u = warp; u < (ROWS / 8) * CQ; u += NT / 32) {
+            const int rg = u / CQ, cq = u - rg * CQ;
+            const int r = rg * 8 + (lane & 7), c4 = cq * 4 + (lane >> 3);
+            if (c4 >= K4) continue;
+            const int row = row0 + r, k = c4 * 4;
+            const bool valid = row < J.B;
+            long long id = valid ? J.ids[row] : 0;
+            if ((unsigned long long)id >= (unsigned long long)J.n_rows) { if (p.err_flag) atomicOr(p.err_flag, 1); id = 0; }
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (valid) {
+                if (k < D) {
+                    v = __ldg(reinterpret_cast<const float4*>(J.table + id * D + k));
+                } else {
+                    const float* ex = J.extra + (J.extra_by_id ? id : (long long)row) * E + (k - D);
+                    v.x = k + 0 < Din ? __ldg(ex + 0) : 0.f;
+                    v.y = k + 1 < Din ? __ldg(ex + 1) : 0.f;
+                    v.z = k + 2 < Din ? __ldg(ex + 2) : 0.f;
+                    v.w = k + 3 < Din ? __ldg(ex + 3) : 0.f;
+                }
             }
+            put4<MODE>(x_hi, x_lo, ROWS, r, k, v);
         }
     }
     umma::fence_proxy_async();
+    w_bar.wait();
     __syncthreads();
     if (tid == 0 && !dead) {
         umma::fence_after_sync();
-        issue_gemm<MODE>(pipe.tmem, x_hi, x_lo, NT, w1_hi, w1_lo, H, H, Kp, false);
-        umma::commit(&mbar);
+        issue_gemm<MODE>(tmem, x_hi, x_lo, ROWS, w1_hi, w1_lo, H, H, Kp, false);
+        umma::commit(&mma_bar_s);
     }
-    pipe.wait();
-    __syncthreads();          // everyone is past GEMM1: stage-1 buffers are free
+    mma_bar.wait();
+    umma::fence_after_sync();
 
-    // ---- epilogue 1 + stage 2: hidden [128 × H], W2 [D × H] ---------------------------------------------------- //
+    // ---- epilogue 1 + stage 2: hidden [128 × H] staged by the threads, W2 image by bulk copy --------------------- //
     unsigned char* h_hi = smem;
-    unsigned char* h_lo = h_hi + (size_t)NT * H * 4;
-    unsigned char* w2_hi = h_lo + (size_t)NT * H * 4;
+    unsigned char* h_lo = h_hi + (size_t)ROWS * H * 4;
+    unsigned char* w2_hi = h_lo + (size_t)ROWS * H * 4;
     unsigned char* w2_lo = w2_hi + (size_t)D * H * 4;
+    if (tid == 0) {      // GEMM1 has completed (observed above): the stage-1 buffers this copy overwrites are free
+        const uint32_t bytes = (uint32_t)((MODE == 2 ? 2 : 1) * D * H * 4);
+        umma::mbar_expect_tx(&w_bar_s, bytes);
+        umma::bulk_g2s(w2_hi, J.img + L.w2, bytes, &w_bar_s);
+    }
+    const int row = row0 + r_own;
+    const bool valid = row < J.B;
     {
         const bool do_drop = p.drop_p > 0.f;
         const float keep_scale = do_drop ? 1.f / (1.f - p.drop_p) : 1.f;
         const unsigned long long drop_off = p.offset + (unsigned long long)j +
                                             (p.offset_dev ? (unsigned long long)__ldg(p.offset_dev) * MAX_JOBS : 0ull);
 #pragma unroll 1
-        for (int cb = 0; cb < H / 32; ++cb) {
+        for (int cb = 0; cb < H / 64; ++cb) {
+            const int col0 = half * (H / 2) + cb * 32;
             float v[32];
-            umma::tmem_ld32(pipe.tmem + lane_off + cb * 32, v);
+            umma::tmem_ld32(tmem + lane_off + col0, v);
 #pragma unroll
             for (int i4 = 0; i4 < 8; ++i4) {
-                const int col = cb * 32 + i4 * 4;
+                const int col = col0 + i4 * 4;
                 float4 o;
                 float* op = &o.x;
                 uint4 rnd = make_uint4(0u, 0u, 0u, 0u);
@@ -177,9 +246,11 @@ __global__ void __launch_bounds__(NT, 1) tower_fwd_tc_kernel(const FwdParams p) 
                     rnd = rb_philox4x32(make_uint4((uint32_t)row, (uint32_t)(col >> 2), (uint32_t)drop_off, (uint32_t)(drop_off >> 32)),
                                         make_uint2((uint32_t)p.seed, (uint32_t)(p.seed >> 32)));
                 const uint32_t rw[4] = {rnd.x, rnd.y, rnd.z, rnd.w};
+                const float4 bias = __ldg(reinterpret_cast<const float4*>(J.b1 + col));
+                const float bv[4] = {bias.x, bias.y, bias.z, bias.w};
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
-                    float x = fmaxf(v[i4 * 4 + e] + __ldg(J.b1 + col + e), 0.f);
+                    float x = fmaxf(v[i4 * 4 + e] + bv[e], 0.f);
                     if (do_drop) {
                         bool keep;
                         if (J.keep_mask) keep = valid ? (J.keep_mask[(long long)row * H + col + e] != 0) : true;
@@ -189,47 +260,47 @@ __global__ void __launch_bounds__(NT, 1) tower_fwd_tc_kernel(const FwdParams p) 
                     op[e] = x;
                 }
                 if (J.hid && valid) *reinterpret_cast<float4*>(J.hid + (long long)row * H + col) = o;
-                put4<MODE>(h_hi, h_lo, NT, tid, col, o);
+                put4<MODE>(h_hi, h_lo, ROWS, r_own, col, o);
             }
-        }
-        if (tid < D) {
-            const float4* wr = reinterpret_cast<const float4*>(J.W2 + (long long)tid * H);
-#pragma unroll 4
-            for (int c4 = 0; c4 < H / 4; ++c4) put4<MODE>(w2_hi, w2_lo, D, tid, c4 * 4, __ldg(wr + c4));
         }
     }
     umma::fence_before_sync();
     umma::fence_proxy_async();
+    w_bar.wait();
     __syncthreads();
     if (tid == 0 && !dead) {
         umma::fence_after_sync();
-        issue_gemm<MODE>(pipe.tmem + H, h_hi, h_lo, NT, w2_hi, w2_lo, D, D, H, false);
-        umma::commit(&mbar);
+        issue_gemm<MODE>(tmem + H, h_hi, h_lo, ROWS, w2_hi, w2_lo, D, D, H, false);
+        umma::commit(&mma_bar_s);
     }
-    pipe.wait();
+    mma_bar.wait();
+    umma::fence_after_sync();
 
-    // ---- epilogue 2: bias, L2 normalise -------------------------------------------------------------------------- //
+    // ---- epilogue 2: bias, L2 normalise (two threads per row: partial sums combined in fixed order) ------------------ //
     {
-        float y[D];
+        constexpr int HC = D / 2;       // columns per thread
+        float y[HC];
         float ss = 0.f;
 #pragma unroll
-        for (int cb = 0; cb < D / 32; ++cb) {
+        for (int cb = 0; cb < HC / 32; ++cb) {
             float v[32];
-            umma::tmem_ld32(pipe.tmem + lane_off + H + cb * 32, v);
+            umma::tmem_ld32(tmem + lane_off + H + half * HC + cb * 32, v);
 #pragma unroll
             for (int i = 0; i < 32; ++i) {
-                const float t = v[i] + __ldg(J.b2 + cb * 32 + i);
+                const float t = v[i] + __ldg(J.b2 + half * HC + cb * 32 + i);
                 y[cb * 32 + i] = t;
                 ss = fmaf(t, t, ss);
             }
         }
-        const float den = fmaxf(sqrtf(ss), NORM_EPS);
+        ss_part[half][r_own] = ss;
+        __syncthreads();
+        const float den = fmaxf(sqrtf(ss_part[0][r_own] + ss_part[1][r_own]), NORM_EPS);
         if (valid) {
 #pragma unroll
-            for (int c4 = 0; c4 < D / 4; ++c4)
-                *reinterpret_cast<float4*>(J.out + (long long)row * D + c4 * 4) =
+            for (int c4 = 0; c4 < HC / 4; ++c4)
+                *reinterpret_cast<float4*>(J.out + (long long)row * D + half * HC + c4 * 4) =
                     make_float4(y[c4 * 4] / den, y[c4 * 4 + 1] / den, y[c4 * 4 + 2] / den, y[c4 * 4 + 3] / den);
-            if (J.denom) J.denom[row] = den;
+            if (J.denom && half == 0) J.denom[row] = den;
         }
     }
     RB_TC_EPILOGUE()
@@ -241,117 +312,123 @@ __global__ void __launch_bounds__(NT, 1) tower_fwd_tc_kernel(const FwdParams p) 
 template <int D, int H, int MODE>
 __global__ void __launch_bounds__(NT, 1) tower_bwd_data_tc_kernel(const BwdParams p, int* err_flag) {
     extern __shared__ __align__(1024) unsigned char smem[];
+    __shared__ float dot_part[2][ROWS];
     RB_TC_PROLOGUE(err_flag)
     int begins[MAX_JOBS];
 #pragma unroll
     for (int t = 0; t < MAX_JOBS; ++t) begins[t] = p.job[t].cta_begin;
     const int j = find_job(begins, p.n_jobs);
     const BwdJob J = p.job[j];
-    const int Din = D + J.E;
-    const int row = ((int)blockIdx.x - J.cta_begin) * NT + tid;
+    const ImgLayout L = img_layout(D, H, J.E);
+    const int row = ((int)blockIdx.x - J.cta_begin) * ROWS + r_own;
     const bool valid = row < J.B;
 
-    // ---- stage 1: dpre [128 × D] (A), W2ᵀ [H × D] (B) ------------------------------------------------------------ //
+    // ---- stage 1: dpre [128 × D] (A), W2ᵀ image [H × D] (B) -------------------------------------------------------- //
     unsigned char* g_hi = smem;
-    unsigned char* g_lo = g_hi + (size_t)NT * D * 4;
-    unsigned char* w2t_hi = g_lo + (size_t)NT * D * 4;
+    unsigned char* g_lo = g_hi + (size_t)ROWS * D * 4;
+    unsigned char* w2t_hi = g_lo + (size_t)ROWS * D * 4;
     unsigned char* w2t_lo = w2t_hi + (size_t)H * D * 4;
+    if (tid == 0) {
+        const uint32_t bytes = (uint32_t)((MODE == 2 ? 2 : 1) * H * D * 4);
+        umma::mbar_expect_tx(&w_bar_s, bytes);
+        umma::bulk_g2s(w2t_hi, J.img + L.w2t, bytes, &w_bar_s);
+    }
     {
-        float g[D];
+        constexpr int HC = D / 2;
+        float g[HC], yv[HC];
         float dot = 0.f;
-        const float den = valid ? __ldg(J.denom + row) : 1.f;
 #pragma unroll
-        for (int c4 = 0; c4 < D / 4; ++c4) {
-            float4 gv = make_float4(0.f, 0.f, 0.f, 0.f), yv = gv;
+        for (int c4 = 0; c4 < HC / 4; ++c4) {
+            float4 gv = make_float4(0.f, 0.f, 0.f, 0.f), y4 = gv;
             if (valid) {
-                gv = __ldg(reinterpret_cast<const float4*>(J.dY + (long long)row * D) + c4);
-                yv = __ldg(reinterpret_cast<const float4*>(J.y + (long long)row * D) + c4);
+                gv = __ldg(reinterpret_cast<const float4*>(J.dY + (long long)row * D + half * HC) + c4);
+                y4 = __ldg(reinterpret_cast<const float4*>(J.y + (long long)row * D + half * HC) + c4);
             }
             g[c4 * 4] = gv.x; g[c4 * 4 + 1] = gv.y; g[c4 * 4 + 2] = gv.z; g[c4 * 4 + 3] = gv.w;
-            dot = fmaf(gv.x, yv.x, dot); dot = fmaf(gv.y, yv.y, dot); dot = fmaf(gv.z, yv.z, dot); dot = fmaf(gv.w, yv.w, dot);
+            yv[c4 * 4] = y4.x; yv[c4 * 4 + 1] = y4.y; yv[c4 * 4 + 2] = y4.z; yv[c4 * 4 + 3] = y4.w;
+            dot = fmaf(gv.x, y4.x, dot); dot = fmaf(gv.y, y4.y, dot); dot = fmaf(gv.z, y4.z, dot); dot = fmaf(gv.w, y4.w, dot);
         }
+        dot_part[half][r_own] = dot;
+        __syncthreads();
+        dot = dot_part[0][r_own] + dot_part[1][r_own];
+        const float den = valid ? __ldg(J.denom + row) : 1.f;
         const bool clamped = den <= NORM_EPS;
 #pragma unroll
-        for (int c4 = 0; c4 < D / 4; ++c4) {
-            float4 yv = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (valid) yv = __ldg(reinterpret_cast<const float4*>(J.y + (long long)row * D) + c4);
+        for (int c4 = 0; c4 < HC / 4; ++c4) {
             float4 o;
-            o.x = clamped ? g[c4 * 4] / den : (g[c4 * 4] - yv.x * dot) / den;
-            o.y = clamped ? g[c4 * 4 + 1] / den : (g[c4 * 4 + 1] - yv.y * dot) / den;
-            o.z = clamped ? g[c4 * 4 + 2] / den : (g[c4 * 4 + 2] - yv.z * dot) / den;
-            o.w = clamped ? g[c4 * 4 + 3] / den : (g[c4 * 4 + 3] - yv.w * dot) / den;
-            if (valid) *reinterpret_cast<float4*>(J.dpre + (long long)row * D + c4 * 4) = o;
-            put4<MODE>(g_hi, g_lo, NT, tid, c4 * 4, o);
-        }
-        if (tid < H) {       // B row n = h, K = d : W2ᵀ[h][d] = W2[d][h]
-#pragma unroll 4
-            for (int c4 = 0; c4 < D / 4; ++c4) {
-                const float* wp = J.W2 + (long long)(c4 * 4) * H + tid;
-                put4<MODE>(w2t_hi, w2t_lo, H, tid, c4 * 4, make_float4(__ldg(wp), __ldg(wp + H), __ldg(wp + 2 * H), __ldg(wp + 3 * H)));
+            float* op = &o.x;
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const float gg = g[c4 * 4 + e];
+                op[e] = clamped ? gg / den : (gg - yv[c4 * 4 + e] * dot) / den;
             }
+            if (valid) *reinterpret_cast<float4*>(J.dpre + (long long)row * D + half * HC + c4 * 4) = o;
+            put4<MODE>(g_hi, g_lo, ROWS, r_own, half * HC + c4 * 4, o);
         }
     }
     umma::fence_proxy_async();
+    w_bar.wait();
     __syncthreads();
     if (tid == 0 && !dead) {
         umma::fence_after_sync();
-        issue_gemm<MODE>(pipe.tmem, g_hi, g_lo, NT, w2t_hi, w2t_lo, H, H, D, false);
-        umma::commit(&mbar);
+        issue_gemm<MODE>(tmem, g_hi, g_lo, ROWS, w2t_hi, w2t_lo, H, H, D, false);
+        umma::commit(&mma_bar_s);
     }
-    pipe.wait();
-    __syncthreads();
+    mma_bar.wait();
+    umma::fence_after_sync();
 
-    // ---- epilogue 1 + stage 2: dact [128 × H] (A), W1[:, :D]ᵀ [D × H] (B) ---------------------------------------- //
+    // ---- epilogue 1 + stage 2: dact [128 × H] (A), W1[:, :D]ᵀ image [D × H] (B) -------------------------------------- //
     unsigned char* a_hi = smem;
-    unsigned char* a_lo = a_hi + (size_t)NT * H * 4;
-    unsigned char* w1t_hi = a_lo + (size_t)NT * H * 4;
+    unsigned char* a_lo = a_hi + (size_t)ROWS * H * 4;
+    unsigned char* w1t_hi = a_lo + (size_t)ROWS * H * 4;
     unsigned char* w1t_lo = w1t_hi + (size_t)D * H * 4;
-    {
+    if (tid == 0) {
+        const uint32_t bytes = (uint32_t)((MODE == 2 ? 2 : 1) * D * H * 4);
+        umma::mbar_expect_tx(&w_bar_s, bytes);
+        umma::bulk_g2s(w1t_hi, J.img + L.w1t, bytes, &w_bar_s);
+    }
 #pragma unroll 1
-        for (int cb = 0; cb < H / 32; ++cb) {
-            float v[32];
-            umma::tmem_ld32(pipe.tmem + lane_off + cb * 32, v);
+    for (int cb = 0; cb < H / 64; ++cb) {
+        const int col0 = half * (H / 2) + cb * 32;
+        float v[32];
+        umma::tmem_ld32(tmem + lane_off + col0, v);
 #pragma unroll
-            for (int i4 = 0; i4 < 8; ++i4) {
-                const int col = cb * 32 + i4 * 4;
-                float4 hv = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (valid) hv = __ldg(reinterpret_cast<const float4*>(J.hid + (long long)row * H + col));
-                float4 o;
-                o.x = hv.x > 0.f ? v[i4 * 4] * p.keep_scale : 0.f;
-                o.y = hv.y > 0.f ? v[i4 * 4 + 1] * p.keep_scale : 0.f;
-                o.z = hv.z > 0.f ? v[i4 * 4 + 2] * p.keep_scale : 0.f;
-                o.w = hv.w > 0.f ? v[i4 * 4 + 3] * p.keep_scale : 0.f;
-                if (valid) *reinterpret_cast<float4*>(J.dact + (long long)row * H + col) = o;
-                put4<MODE>(a_hi, a_lo, NT, tid, col, o);
-            }
-        }
-        if (tid < D) {       // B row n = d, K = h : W1ᵀ[d][h] = W1[h][d]
-#pragma unroll 4
-            for (int c4 = 0; c4 < H / 4; ++c4) {
-                const float* wp = J.W1 + (long long)(c4 * 4) * Din + tid;
-                put4<MODE>(w1t_hi, w1t_lo, D, tid, c4 * 4,
-                           make_float4(__ldg(wp), __ldg(wp + Din), __ldg(wp + 2 * Din), __ldg(wp + 3 * Din)));
-            }
+        for (int i4 = 0; i4 < 8; ++i4) {
+            const int col = col0 + i4 * 4;
+            float4 hv = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (valid) hv = __ldg(reinterpret_cast<const float4*>(J.hid + (long long)row * H + col));
+            float4 o;
+            o.x = hv.x > 0.f ? v[i4 * 4] * p.keep_scale : 0.f;
+            o.y = hv.y > 0.f ? v[i4 * 4 + 1] * p.keep_scale : 0.f;
+            o.z = hv.z > 0.f ? v[i4 * 4 + 2] * p.keep_scale : 0.f;
+            o.w = hv.w > 0.f ? v[i4 * 4 + 3] * p.keep_scale : 0.f;
+            if (valid) *reinterpret_cast<float4*>(J.dact + (long long)row * H + col) = o;
+            put4<MODE>(a_hi, a_lo, ROWS, r_own, col, o);
         }
     }
     umma::fence_before_sync();
     umma::fence_proxy_async();
+    w_bar.wait();
     __syncthreads();
     if (tid == 0 && !dead) {
         umma::fence_after_sync();
-        issue_gemm<MODE>(pipe.tmem + H, a_hi, a_lo, NT, w1t_hi, w1t_lo, D, D, H, false);
-        umma::commit(&mbar);
+        issue_gemm<MODE>(tmem + H, a_hi, a_lo, ROWS, w1t_hi, w1t_lo, D, D, H, false);
+        umma::commit(&mma_bar_s);
     }
-    pipe.wait();
+    mma_bar.wait();
+    umma::fence_after_sync();
+    {
+        constexpr int HC = D / 2;
 #pragma unroll
-    for (int cb = 0; cb < D / 32; ++cb) {
-        float v[32];
-        umma::tmem_ld32(pipe.tmem + lane_off + H + cb * 32, v);
-        if (valid) {
+        for (int cb = 0; cb < HC / 32; ++cb) {
+            float v[32];
+            umma::tmem_ld32(tmem + lane_off + H + half * HC + cb * 32, v);
+            if (valid) {
 #pragma unroll
-            for (int i4 = 0; i4 < 8; ++i4)
-                *reinterpret_cast<float4*>(J.dRows + (long long)row * D + cb * 32 + i4 * 4) =
-                    make_float4(v[i4 * 4], v[i4 * 4 + 1], v[i4 * 4 + 2], v[i4 * 4 + 3]);
+                for (int i4 = 0; i4 < 8; ++i4)
+                    *reinterpret_cast<float4*>(J.dRows + (long long)row * D + half * HC + cb * 32 + i4 * 4) =
+                        make_float4(v[i4 * 4], v[i4 * 4 + 1], v[i4 * 4 + 2], v[i4 * 4 + 3]);
+            }
         }
     }
     RB_TC_EPILOGUE()
@@ -362,10 +439,13 @@ __global__ void __launch_bounds__(NT, 1) tower_bwd_data_tc_kernel(const BwdParam
 // ------------------------------------------------------------------------------------------------------------ //
 constexpr int KC = 32;    // samples per staged chunk
 
-template <int D, int H, int NK, int MODE>      // NK = padded Din (multiple of 16) = N of the dW1 product
+template <int D, int H, int NK, int MODE>      // NK = padded Din (multiple of 32) = N of the dW1 product
 __global__ void __launch_bounds__(NT, 1) tower_bwd_weights_tc_kernel(const BwdParams p, int* err_flag) {
     extern __shared__ __align__(1024) unsigned char smem[];
+    __shared__ long long ids_s[KC];
+    __shared__ float bias_part[2][2][ROWS];
     RB_TC_PROLOGUE(err_flag)
+    (void)w_bar;
     const int s = blockIdx.x;
     const int E = p.job[0].E, Din = D + E;
     // chunk buffers: A1 = hidᵀ [H × KC], B1 = dpreᵀ [D × KC], A2 = dactᵀ [H × KC], B2 = Xᵀ [NK × KC]
@@ -377,7 +457,7 @@ __global__ void __launch_bounds__(NT, 1) tower_bwd_weights_tc_kernel(const BwdPa
     unsigned char* a2_lo = a2_hi + H * KC * 4;
     unsigned char* b2_hi = a2_lo + H * KC * 4;
     unsigned char* b2_lo = b2_hi + NK * KC * 4;
-    __shared__ long long ids_s[KC];
+    const int m = tid & (ROWS - 1), sh = tid >> 7;      // operand row handled by this thread, half of the chunk's samples
     float db1 = 0.f, db2 = 0.f;
     bool first = true;
     for (int j = 0; j < p.n_jobs; ++j) {
@@ -392,70 +472,77 @@ __global__ void __launch_bounds__(NT, 1) tower_bwd_weights_tc_kernel(const BwdPa
                 ids_s[tid] = id;
             }
             __syncthreads();
-            // thread t: operand row t, K = sample (4 samples per 16-byte chunk)
-#pragma unroll 2
-            for (int c4 = 0; c4 < KC / 4; ++c4) {
+            // thread = (operand row m, sample half sh); K = sample, 4 samples per 16-byte chunk; loads are coalesced across m
+#pragma unroll
+            for (int c4 = sh * (KC / 8); c4 < (sh + 1) * (KC / 8); ++c4) {
                 float hv[4], av[4], gv[4], xv[4];
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
                     const int r = c4 * 4 + e;
                     const bool ok = r < nr;
                     const long long gr = r0 + r;
-                    hv[e] = (ok && tid < H) ? __ldg(J.hid + gr * H + tid) : 0.f;
-                    av[e] = (ok && tid < H) ? __ldg(J.dact + gr * H + tid) : 0.f;
-                    gv[e] = (ok && tid < D) ? __ldg(J.dpre + gr * D + tid) : 0.f;
+                    hv[e] = (ok && m < H) ? __ldg(J.hid + gr * H + m) : 0.f;
+                    av[e] = (ok && m < H) ? __ldg(J.dact + gr * H + m) : 0.f;
+                    gv[e] = (ok && m < D) ? __ldg(J.dpre + gr * D + m) : 0.f;
                     float x = 0.f;
-                    if (ok && tid < Din) {
-                        if (tid < D) x = __ldg(J.table + ids_s[r] * D + tid);
-                        else x = __ldg(J.extra + (J.extra_by_id ? ids_s[r] : gr) * E + (tid - D));
+                    if (ok && m < Din) {
+                        if (m < D) x = __ldg(J.table + ids_s[r] * D + m);
+                        else x = __ldg(J.extra + (J.extra_by_id ? ids_s[r] : gr) * E + (m - D));
                     }
                     xv[e] = x;
                     db1 += av[e];
                     db2 += gv[e];
                 }
-                if (tid < H) {
-                    put4<MODE>(a1_hi, a1_lo, H, tid, c4 * 4, make_float4(hv[0], hv[1], hv[2], hv[3]));
-                    put4<MODE>(a2_hi, a2_lo, H, tid, c4 * 4, make_float4(av[0], av[1], av[2], av[3]));
+                if (m < H) {
+                    put4<MODE>(a1_hi, a1_lo, H, m, c4 * 4, make_float4(hv[0], hv[1], hv[2], hv[3]));
+                    put4<MODE>(a2_hi, a2_lo, H, m, c4 * 4, make_float4(av[0], av[1], av[2], av[3]));
                 }
-                if (tid < D) put4<MODE>(b1_hi, b1_lo, D, tid, c4 * 4, make_float4(gv[0], gv[1], gv[2], gv[3]));
-                if (tid < NK) put4<MODE>(b2_hi, b2_lo, NK, tid, c4 * 4, make_float4(xv[0], xv[1], xv[2], xv[3]));
+                if (m < D) put4<MODE>(b1_hi, b1_lo, D, m, c4 * 4, make_float4(gv[0], gv[1], gv[2], gv[3]));
+                if (m < NK) put4<MODE>(b2_hi, b2_lo, NK, m, c4 * 4, make_float4(xv[0], xv[1], xv[2], xv[3]));
             }
             umma::fence_proxy_async();
             __syncthreads();
             if (tid == 0 && !dead) {
                 umma::fence_after_sync();
-                issue_gemm<MODE>(pipe.tmem, a1_hi, a1_lo, H, b1_hi, b1_lo, D, D, KC, !first);        // dW2ᵀ [H × D]
-                issue_gemm<MODE>(pipe.tmem + D, a2_hi, a2_lo, H, b2_hi, b2_lo, NK, NK, KC, !first);  // dW1  [H × NK]
-                umma::commit(&mbar);
+                issue_gemm<MODE>(tmem, a1_hi, a1_lo, H, b1_hi, b1_lo, D, D, KC, !first);        // dW2ᵀ [H × D]
+                issue_gemm<MODE>(tmem + D, a2_hi, a2_lo, H, b2_hi, b2_lo, NK, NK, KC, !first);  // dW1  [H × NK]
+                umma::commit(&mma_bar_s);
             }
             first = false;
-            pipe.wait();          // chunk buffers are reused
+            mma_bar.wait();          // chunk buffers are reused
+            umma::fence_after_sync();
             __syncthreads();
         }
     }
     // partial block layout: [W1 (H*Din) | b1 (H) | W2 (D*H) | b2 (D)]
     float* part = p.part + (long long)s * p.P;
     float* w1o = part, *b1o = part + H * Din, *w2o = part + H * Din + H, *b2o = part + H * Din + H + D * H;
+    bias_part[0][sh][m] = db1;
+    bias_part[1][sh][m] = db2;
+    __syncthreads();
     if (first) {          // this CTA had no rows: its partial is all zeros
         for (int i = tid; i < p.P; i += NT) part[i] = 0.f;
-    } else if (tid < H) {
+    } else {
+        const int h = r_own;          // accumulator row
+        {   // dW2[d][h] = acc[h][d]; half selects the d range
+            constexpr int HC = D / 2;
 #pragma unroll
-        for (int cb = 0; cb < D / 32; ++cb) {
-            float v[32];
-            umma::tmem_ld32(pipe.tmem + lane_off + cb * 32, v);
+            for (int cb = 0; cb < HC / 32; ++cb) {
+                float v[32];
+                umma::tmem_ld32(tmem + lane_off + half * HC + cb * 32, v);
 #pragma unroll
-            for (int i = 0; i < 32; ++i) w2o[(long long)(cb * 32 + i) * H + tid] = v[i];       // dW2[d][h] = acc[h][d]
+                for (int i = 0; i < 32; ++i) w2o[(long long)(half * HC + cb * 32 + i) * H + h] = v[i];
+            }
         }
-#pragma unroll
-        for (int cb = 0; cb < NK / 32; ++cb) {
+        for (int cb = half; cb < NK / 32; cb += 2) {      // dW1[h][k]
             float v[32];
-            umma::tmem_ld32(pipe.tmem + lane_off + D + cb * 32, v);
+            umma::tmem_ld32(tmem + lane_off + D + cb * 32, v);
 #pragma unroll
             for (int i = 0; i < 32; ++i)
-                if (cb * 32 + i < Din) w1o[(long long)tid * Din + cb * 32 + i] = v[i];
+                if (cb * 32 + i < Din) w1o[(long long)h * Din + cb * 32 + i] = v[i];
         }
-        b1o[tid] = db1;
-        if (tid < D) b2o[tid] = db2;
+        if (tid < H) b1o[tid] = bias_part[0][0][tid] + bias_part[0][1][tid];
+        if (tid < D) b2o[tid] = bias_part[1][0][tid] + bias_part[1][1][tid];
     }
     RB_TC_EPILOGUE()
 }
@@ -473,7 +560,7 @@ template <typename JobT>
 int assign_tiles(JobT* jobs, int n_jobs) {
     int begin = 0;
     for (int j = 0; j < n_jobs; ++j) {
-        const int tiles = (jobs[j].B + NT - 1) / NT;
+        const int tiles = (jobs[j].B + ROWS - 1) / ROWS;
         jobs[j].cta_begin = begin;
         jobs[j].cta_count = tiles;
         begin += tiles;
@@ -491,8 +578,55 @@ int set_smem(K kernel, size_t bytes) {
 
 bool rb_tower_tc_supported(int D, int H, int E) { return D == 64 && H == 128 && E >= 0 && E <= 24; }
 
-int rb_tower_fwd_tc(FwdParams& p, int D, int H, int mode, cudaStream_t st) {
-    (void)D; (void)H;
+size_t rb_tower_img_bytes(int D, int H, int E) { return rb_align_up(img_layout(D, H, E).total, 256); }
+
+// builds the weight images of up to 2 weight sets in one launch
+int rb_tower_prep_tc(int n_sets, const float* const W1[], const float* const W2[], const int E[], int D, int H,
+                     unsigned char* const img[], cudaStream_t st) {
+    RB_REQUIRE(n_sets >= 1 && n_sets <= 2, "tower_prep: 1 or 2 weight sets");
+    PrepParams p{};
+    p.n_sets = n_sets; p.D = D; p.H = H;
+    for (int i = 0; i < n_sets; ++i) {
+        RB_REQUIRE(W1[i] && W2[i] && img[i], "tower_prep: NULL pointer");
+        RB_REQUIRE((reinterpret_cast<uintptr_t>(img[i]) & 15) == 0, "tower_prep: image must be 16-byte aligned");
+        p.set[i].W1 = W1[i]; p.set[i].W2 = W2[i]; p.set[i].img = img[i]; p.set[i].E = E[i];
+    }
+    tower_prep_kernel<<<dim3(24, n_sets), 256, 0, st>>>(p);
+    RB_LAUNCH_CHECK("tower_prep_kernel");
+    return RB200_OK;
+}
+
+extern "C" size_t rb200_tower_img_bytes(int D, int H, int extra_dim) { return rb_tower_img_bytes(D, H, extra_dim); }
+
+extern "C" int rb200_tower_prep(const float* W1, const float* W2, int D, int H, int extra_dim, void* img, void* stream) {
+    RB_REQUIRE(rb_tower_tc_supported(D, H, extra_dim), "tower_prep: tensor-core modes cover D=64, H=128, extra_dim<=24");
+    const float* w1[1] = {W1}; const float* w2[1] = {W2}; const int e[1] = {extra_dim};
+    unsigned char* im[1] = {(unsigned char*)img};
+    return rb_tower_prep_tc(1, w1, w2, e, D, H, im, (cudaStream_t)stream);
+}
+
+// jobs whose img is NULL get their image built into the workspace (jobs sharing W1 share the image)
+int rb_tower_fwd_tc(FwdParams& p, int D, int H, int mode, void* workspace, size_t workspace_bytes, cudaStream_t st) {
+    RbArena ar(workspace, workspace_bytes);
+    const float* w1[2]; const float* w2[2]; int es[2]; unsigned char* im[2];
+    int n_sets = 0;
+    for (int j = 0; j < p.n_jobs; ++j) {
+        if (p.job[j].img) continue;
+        int found = -1;
+        for (int k = 0; k < n_sets; ++k) if (w1[k] == p.job[j].W1 && es[k] == p.job[j].E) found = k;
+        if (found < 0) {
+            RB_REQUIRE(n_sets < 2, "tower_fwd (tcgen05): at most two distinct weight sets per call");
+            w1[n_sets] = p.job[j].W1; w2[n_sets] = p.job[j].W2; es[n_sets] = p.job[j].E;
+            im[n_sets] = ar.take<unsigned char>(rb_tower_img_bytes(D, H, p.job[j].E));
+            found = n_sets++;
+        }
+        p.job[j].img = im[found];
+    }
+    if (n_sets) {
+        if (!workspace || !ar.ok()) return rb_set_error(RB200_ERR_WORKSPACE, "tower_fwd (tcgen05): workspace too small for the weight images");
+        int rc = rb_tower_prep_tc(n_sets, w1, w2, es, D, H, im, st);
+        if (rc) return rc;
+    }
     const int grid = assign_tiles(p.job, p.n_jobs);
     int kp = 0;
     for (int j = 0; j < p.n_jobs; ++j) { const int k = (64 + p.job[j].E + 7) & ~7; if (k > kp) kp = k; }
@@ -512,10 +646,18 @@ int rb_tower_fwd_tc(FwdParams& p, int D, int H, int mode, cudaStream_t st) {
     return RB200_OK;
 }
 
-int rb_tower_bwd_tc(BwdParams& p, int D, int H, int mode, float* grads_out, int accumulate, cudaStream_t st) {
-    (void)D; (void)H;
-    const int grid = assign_tiles(p.job, p.n_jobs);
+// p.part holds the split-K partials; `img_ws` (rb_tower_img_bytes) is used when the jobs carry no image
+int rb_tower_bwd_tc(BwdParams& p, int D, int H, int mode, float* grads_out, int accumulate, unsigned char* img_ws, cudaStream_t st) {
     const int E = p.job[0].E;
+    if (!p.job[0].img) {
+        RB_REQUIRE(img_ws, "tower_bwd (tcgen05): no weight image and no workspace for one");
+        const float* w1[1] = {p.job[0].W1}; const float* w2[1] = {p.job[0].W2}; const int e[1] = {E};
+        unsigned char* im[1] = {img_ws};
+        int rc = rb_tower_prep_tc(1, w1, w2, e, D, H, im, st);
+        if (rc) return rc;
+        for (int j = 0; j < p.n_jobs; ++j) p.job[j].img = img_ws;
+    }
+    const int grid = assign_tiles(p.job, p.n_jobs);
     const size_t smem_d = (size_t)2 * 128 * 128 * 4 + (size_t)2 * 64 * 128 * 4;
     const int NK = 96;
     const size_t smem_w = (size_t)4 * (128 + 128 + 64 + NK) * KC * 2;

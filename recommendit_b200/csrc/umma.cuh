@@ -56,6 +56,18 @@ __device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity, uint32
     }
     return false;
 }
+// ---- bulk async copy (TMA engine, 1-D: no tensor map) ------------------------------------------------------- //
+// arrive(1) + expect `bytes` of asynchronous copy traffic on bar
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+// global → shared, `bytes` multiple of 16, both addresses 16-byte aligned; completion is signalled on bar (complete_tx)
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
 // all previously issued tcgen05.mma of this thread → arrive(1) on bar when they complete
 __device__ __forceinline__ void commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");

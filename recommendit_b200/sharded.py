@@ -105,8 +105,12 @@ class CudaOps:
         for i, j in enumerate(jobs):
             arr[i] = TowerJob(ptr(j["table"]), ptr(j["ids"]), ptr(j.get("extra")), ptr(j["W1"]), ptr(j["b1"]), ptr(j["W2"]),
                               ptr(j["b2"]), ptr(j["out"]), ptr(j["hid"]), ptr(j["denom"]), None, j["table"].shape[0],
-                              j["ids"].numel(), 0 if j.get("extra") is None else j["extra"].shape[1], 0)
-        check(self.lib.rb200_tower_fwd(arr, len(jobs), D, H, drop_p, seed, offset, None, self.mode(D, H, jobs), None, stream_ptr()),
+                              j["ids"].numel(), 0 if j.get("extra") is None else j["extra"].shape[1], 0, None)
+        mode = self.mode(D, H, jobs)
+        E = max(0 if j.get("extra") is None else j["extra"].shape[1] for j in jobs)
+        wsb = self.lib.rb200_tower_fwd_workspace_bytes(len(jobs), D, H, E, mode)
+        ws = workspace(wsb, jobs[0]["out"].device) if wsb else None
+        check(self.lib.rb200_tower_fwd(arr, len(jobs), D, H, drop_p, seed, offset, None, mode, None, ptr(ws), wsb, stream_ptr()),
               "rb200_tower_fwd")
 
     def bpr_pair(self, u, p, n, grad_scale: float):
@@ -125,7 +129,7 @@ class CudaOps:
         for i, j in enumerate(jobs):
             arr[i] = TowerBwdJob(ptr(j["table"]), ptr(j["ids"]), ptr(j.get("extra")), j["table"].shape[0], j["ids"].numel(), E, 0,
                                  ptr(j["W1"]), ptr(j["W2"]), ptr(j["dY"]), ptr(j["out"]), ptr(j["denom"]), ptr(j["hid"]),
-                                 ptr(j["dpre"]), ptr(j["dact"]), ptr(j["dRows"]))
+                                 ptr(j["dpre"]), ptr(j["dact"]), ptr(j["dRows"]), None)
         wsb = self.lib.rb200_tower_bwd_workspace_bytes(D, H, E)
         ws = workspace(wsb, grads_out.device)
         check(self.lib.rb200_tower_bwd(arr, len(jobs), D, H, drop_p, self.mode(D, H, jobs), ptr(grads_out), 0, ptr(ws), wsb, stream_ptr()),

@@ -85,10 +85,12 @@ class _TowerFn(torch.autograd.Function):
         mode = tower_mode_for(D, H, E, mode)
         if B > 0:
             job = TowerJob(ptr(table), ptr(ids), ptr(extra), ptr(W1), ptr(b1), ptr(W2), ptr(b2), ptr(out), ptr(hid),
-                           ptr(denom), ptr(keep_mask), n_rows, B, E, 0)
+                           ptr(denom), ptr(keep_mask), n_rows, B, E, 0, None)
+            wsb = lib.rb200_tower_fwd_workspace_bytes(1, D, H, E, mode)
+            ws = workspace(wsb, dev) if wsb else None
             with torch.cuda.device(dev):
-                check(lib.rb200_tower_fwd(job, 1, D, H, float(drop_p), int(seed), int(offset), None, mode, None, stream_ptr()),
-                      "rb200_tower_fwd")
+                check(lib.rb200_tower_fwd(job, 1, D, H, float(drop_p), int(seed), int(offset), None, mode, None, ptr(ws), wsb,
+                                          stream_ptr()), "rb200_tower_fwd")
         if need_grad:
             ctx.save_for_backward(ids, extra, table, W1, W2, out, hid, denom)
             ctx.drop_p = float(drop_p)
@@ -114,7 +116,7 @@ class _TowerFn(torch.autograd.Function):
             wsb = lib.rb200_tower_bwd_workspace_bytes(D, H, E)
             ws = workspace(wsb, dev)
             job = TowerBwdJob(ptr(table), ptr(ids), ptr(extra), n_rows, B, E, 0, ptr(W1), ptr(W2), ptr(dY), ptr(out),
-                              ptr(denom), ptr(hid), ptr(dpre), ptr(dact), ptr(drows))
+                              ptr(denom), ptr(hid), ptr(dpre), ptr(dact), ptr(drows), None)
             with torch.cuda.device(dev):
                 check(lib.rb200_tower_bwd(job, 1, D, H, ctx.drop_p, ctx.mode, ptr(grads), 0, ptr(ws), wsb, stream_ptr()),
                       "rb200_tower_bwd")
