@@ -271,10 +271,6 @@ int rb200_bpr_step_views(const rb200_step_params* params_host, rb200_step_views*
  * ------------------------------------------------------------------------------------------ */
 int rb200_gemm_nt(const float* A, int M, const float* B, int N, int K, int mode, float* C, int64_t ldc,
                   int* err_flag, void* stream);
-/* C[M,N] = Aᵀ·B with A stored [K, M] and B stored [K, N] (reduction over the leading, batch-like dimension — the
- * shape of the tower weight gradients).  Operands are consumed as MN-major UMMA matrices: no transposition pass. */
-int rb200_gemm_tn(const float* A, int M, const float* B, int N, int K, int mode, float* C, int64_t ldc,
-                  int* err_flag, void* stream);
 
 /* ------------------------------------------------------------------------------------------ *
  * IVFFlat inner-product index — src/models/faiss_index.py

@@ -106,7 +106,6 @@ SIGNATURES = {
     "rb200_bpr_step": (I, [C.POINTER(StepParams), P]),
     "rb200_bpr_step_views": (I, [C.POINTER(StepParams), C.POINTER(StepViews)]),
     "rb200_gemm_nt": (I, [P, I, P, I, I, I, P, I64, P, P]),
-    "rb200_gemm_tn": (I, [P, I, P, I, I, I, P, I64, P, P]),
     "rb200_normalize_rows": (I, [P, I64, I, F, P, P]),
     "rb200_ivf_assign": (I, [P, I64, I, P, I, P, P, P]),
     "rb200_kmeans_update_workspace_bytes": (SZ, [I64, I]),

@@ -109,121 +109,7 @@ __global__ void __launch_bounds__(128, 1) gemm_nt_tc_kernel(const float* __restr
     if (warp == 0) umma::tmem_free(tmem, TN);
 }
 
-// C[M,N] = Aᵀ·B with A stored [K][M] and B stored [K][N] (both MN-major operands) — the shape of a weight-gradient
-// product (reduction over the batch).  Same skeleton as above; exists to validate the MN-major descriptors.
-template <int MODE>
-__global__ void __launch_bounds__(128, 1) gemm_tn_tc_kernel(const float* __restrict__ A, const float* __restrict__ B,
-                                                            float* __restrict__ C, int M, int N, int K, long long ldc,
-                                                            int* __restrict__ err_flag, int dbg) {
-    extern __shared__ __align__(1024) unsigned char smem[];
-    unsigned char* sA_hi = smem;
-    unsigned char* sA_lo = smem + CHUNK_BYTES;
-    unsigned char* sB_hi = smem + 2 * CHUNK_BYTES;
-    unsigned char* sB_lo = smem + 3 * CHUNK_BYTES;
-    __shared__ __align__(8) uint64_t mbar;
-    __shared__ uint32_t tmem_slot;
-    __shared__ int dead;
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    if (warp == 0) umma::tmem_alloc(&tmem_slot, TN);
-    if (tid == 0) { umma::mbar_init(&mbar, 1); umma::fence_mbar_init(); dead = 0; }
-    umma::fence_before_sync();
-    __syncthreads();
-    umma::fence_after_sync();
-    const uint32_t tmem = tmem_slot;
-    const long long m0 = (long long)blockIdx.y * TM, n0 = (long long)blockIdx.x * TN;
-    const uint32_t idesc = umma::idesc_tf32(TM, TN, !(dbg & 1), !(dbg & 2));
-    constexpr uint32_t LBO_MN = (TM / 4) * 128;     // K-block stride
-    uint32_t phase = 0;
-    const int n_chunks = (K + KC - 1) / KC;
-    for (int c = 0; c < n_chunks; ++c) {
-        const int k0 = c * KC;
-        // 32 k-rows × 32 sixteen-byte units per operand; lane → (k%8 = lane&7, unit = 4·it + lane>>3): conflict-free stores,
-        // 64-byte global segments
-        for (int it = warp; it < (KC / 8) * (TM / 16); it += 4) {
-            const int kb = it / (TM / 16), ub = it - kb * (TM / 16);
-            const int k = kb * 8 + (lane & 7), u = ub * 4 + (lane >> 3);
-            const long long gk = k0 + k;
-            float4 va = make_float4(0.f, 0.f, 0.f, 0.f), vb = va;
-            if (gk < K) {
-                if (m0 + u * 4 < M) va = __ldg(reinterpret_cast<const float4*>(A + gk * M + m0 + u * 4));
-                if (n0 + u * 4 < N) vb = __ldg(reinterpret_cast<const float4*>(B + gk * N + n0 + u * 4));
-            }
-            const uint32_t off = umma::mnmajor_offset(TM, u * 4, k);
-            float4 hi, lo;
-            umma::split4(va, hi, lo);
-            *reinterpret_cast<float4*>(sA_hi + off) = hi;
-            if (MODE == 2) *reinterpret_cast<float4*>(sA_lo + off) = lo;
-            umma::split4(vb, hi, lo);
-            *reinterpret_cast<float4*>(sB_hi + off) = hi;
-            if (MODE == 2) *reinterpret_cast<float4*>(sB_lo + off) = lo;
-        }
-        umma::fence_proxy_async();
-        __syncthreads();
-        if (tid == 0 && !dead) {
-            umma::fence_after_sync();
-            const uint32_t a_hi = umma::smem_u32(sA_hi), a_lo = umma::smem_u32(sA_lo);
-            const uint32_t b_hi = umma::smem_u32(sB_hi), b_lo = umma::smem_u32(sB_lo);
-#pragma unroll
-            for (int j = 0; j < KC / 8; ++j) {
-                const uint32_t ko = j * LBO_MN;
-                const bool first = (c == 0 && j == 0);
-                if (MODE == 2) {
-                    umma::mma_tf32(tmem, umma::smem_desc(a_lo + ko, LBO_MN, 128), umma::smem_desc(b_hi + ko, LBO_MN, 128), idesc, !first);
-                    umma::mma_tf32(tmem, umma::smem_desc(a_hi + ko, LBO_MN, 128), umma::smem_desc(b_lo + ko, LBO_MN, 128), idesc, true);
-                    umma::mma_tf32(tmem, umma::smem_desc(a_hi + ko, LBO_MN, 128), umma::smem_desc(b_hi + ko, LBO_MN, 128), idesc, true);
-                } else {
-                    umma::mma_tf32(tmem, umma::smem_desc(a_hi + ko, LBO_MN, 128), umma::smem_desc(b_hi + ko, LBO_MN, 128), idesc, !first);
-                }
-            }
-            umma::commit(&mbar);
-        }
-        if (!dead) {
-            if (!umma::mbar_wait(&mbar, phase)) { dead = 1; if (err_flag) atomicOr(err_flag, 2); }
-        }
-        phase ^= 1;
-        umma::fence_after_sync();
-        __syncthreads();
-    }
-    const long long row = m0 + tid;
-#pragma unroll 1
-    for (int cb = 0; cb < TN / 32; ++cb) {
-        float v[32];
-        umma::tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + cb * 32, v);
-        if (row < M) {
-#pragma unroll
-            for (int i = 0; i < 32; ++i) {
-                const long long col = n0 + cb * 32 + i;
-                if (col < N) C[row * ldc + col] = v[i];
-            }
-        }
-    }
-    umma::fence_before_sync();
-    __syncthreads();
-    if (warp == 0) umma::tmem_free(tmem, TN);
-}
-
 }  // namespace
-
-extern "C" int rb200_gemm_tn(const float* A, int M, const float* B, int N, int K, int mode, float* C, int64_t ldc, int* err_flag,
-                             void* stream) {
-    RB_REQUIRE(A && B && C && M >= 4 && N >= 4 && K >= 1 && M % 4 == 0 && N % 4 == 0, "gemm_tn: bad arguments (M, N multiples of 4)");
-    const int dbg = mode >> 2;
-    mode &= 3;
-    RB_REQUIRE(mode == 1 || mode == 2, "gemm_tn: modes are 1 (TF32) and 2 (3xTF32)");
-    const dim3 grid((N + TN - 1) / TN, (M + TM - 1) / TM);
-    const size_t smem = 4 * CHUNK_BYTES;
-    static bool attr_set = false;
-    if (!attr_set) {
-        RB_CUDA(cudaFuncSetAttribute(gemm_tn_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        RB_CUDA(cudaFuncSetAttribute(gemm_tn_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_set = true;
-    }
-    cudaStream_t st = (cudaStream_t)stream;
-    if (mode == 1) gemm_tn_tc_kernel<1><<<grid, 128, smem, st>>>(A, B, C, M, N, K, ldc, err_flag, dbg);
-    else gemm_tn_tc_kernel<2><<<grid, 128, smem, st>>>(A, B, C, M, N, K, ldc, err_flag, dbg);
-    RB_LAUNCH_CHECK("gemm_tn_tc_kernel");
-    return RB200_OK;
-}
 
 int rb_gemm_nt_tc(const float* A, int M, const float* B, int N, int K, int mode, float* C, long long ldc, int* err_flag,
                   cudaStream_t st) {

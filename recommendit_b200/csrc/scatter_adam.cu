@@ -90,6 +90,14 @@ __global__ void reset_slots_kernel(const int64_t* __restrict__ uniq_ids, const i
     const int n = n_uniq[0];
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) row_slot[uniq_ids[i]] = -1;
 }
+__global__ void reset_slots2_kernel(const int64_t* __restrict__ ids0, const int* __restrict__ n0, int* __restrict__ slot0,
+                                    const int64_t* __restrict__ ids1, const int* __restrict__ n1, int* __restrict__ slot1) {
+    const int a = n0[0], b = n1[0];
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < a + b; i += gridDim.x * blockDim.x) {
+        if (i < a) slot0[ids0[i]] = -1;
+        else slot1[ids1[i - a]] = -1;
+    }
+}
 
 
 // ---------------------------------------------------------------------------------------- //
@@ -347,6 +355,52 @@ __global__ void __launch_bounds__(NT) adam_dense_kernel(float* __restrict__ w, c
         float wv = w[i], mv = m[i], vv = v[i];
         adam1(wv, g ? __ldg(g + i) : 0.f, mv, vv, k);
         w[i] = wv; m[i] = mv; v[i] = vv;
+    }
+}
+
+// up to two tensors per launch (the two MLP blocks, or the two embedding tables)
+struct AdamDenseJob { float* w; const float* g; float* m; float* v; long long n; };
+struct AdamDenseParams { AdamDenseJob job[2]; int n_jobs; };
+__global__ void __launch_bounds__(NT) adam_dense2_kernel(const AdamDenseParams p, const rb200_opt_state* __restrict__ st) {
+    const AdamK k = load_adam(st);
+    const long long stride = (long long)gridDim.x * NT;
+    for (int j = 0; j < p.n_jobs; ++j) {
+        const AdamDenseJob& J = p.job[j];
+        const long long n4 = J.n >> 2;         // callers guarantee 16-byte alignment and n % 4 == 0 handled by the tail loop
+        for (long long i = (long long)blockIdx.x * NT + threadIdx.x; i < n4; i += stride) {
+            float4 wv = reinterpret_cast<float4*>(J.w)[i], mv = reinterpret_cast<float4*>(J.m)[i], vv = reinterpret_cast<float4*>(J.v)[i];
+            const float4 gv = __ldg(reinterpret_cast<const float4*>(J.g) + i);
+            adam4(wv, gv, mv, vv, k);
+            reinterpret_cast<float4*>(J.w)[i] = wv; reinterpret_cast<float4*>(J.m)[i] = mv; reinterpret_cast<float4*>(J.v)[i] = vv;
+        }
+        for (long long i = n4 * 4 + (long long)blockIdx.x * NT + threadIdx.x; i < J.n; i += stride) {
+            float wv = J.w[i], mv = J.m[i], vv = J.v[i];
+            adam1(wv, __ldg(J.g + i), mv, vv, k);
+            J.w[i] = wv; J.m[i] = mv; J.v[i] = vv;
+        }
+    }
+}
+
+struct AdamTableJob { float* w; float* m; float* v; long long n_rows; int* row_slot; const float* uniq_grads; };
+struct AdamTableParams { AdamTableJob job[2]; int n_jobs; int D4; };
+// dense (reference-exact) table update for up to two tables in one launch
+__global__ void __launch_bounds__(NT) adam_table_dense2_kernel(const AdamTableParams p, const rb200_opt_state* __restrict__ st) {
+    const AdamK k = load_adam(st);
+    const long long stride = (long long)gridDim.x * NT;
+    const int D4 = p.D4;
+    for (int j = 0; j < p.n_jobs; ++j) {
+        const AdamTableJob& J = p.job[j];
+        const long long n4 = J.n_rows * D4;
+        for (long long i = (long long)blockIdx.x * NT + threadIdx.x; i < n4; i += stride) {
+            const long long row = i / D4;
+            const int c = (int)(i - row * D4);
+            const int slot = J.row_slot[row];
+            float4 gv = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (slot >= 0) gv = __ldg(reinterpret_cast<const float4*>(J.uniq_grads) + (long long)slot * D4 + c);
+            float4 wv = reinterpret_cast<float4*>(J.w)[i], mv = reinterpret_cast<float4*>(J.m)[i], vv = reinterpret_cast<float4*>(J.v)[i];
+            adam4(wv, gv, mv, vv, k);
+            reinterpret_cast<float4*>(J.w)[i] = wv; reinterpret_cast<float4*>(J.m)[i] = mv; reinterpret_cast<float4*>(J.v)[i] = vv;
+        }
     }
 }
 
@@ -611,5 +665,36 @@ extern "C" int rb200_adam_rows(float* w, float* m, float* v, int D, const int64_
     adam_rows_kernel<<<stream_grid((long long)max_uniq * (D / 4)), NT, 0, (cudaStream_t)stream>>>(w, m, v, D / 4, uniq_ids,
                                                                                                   uniq_grads, n_uniq, st);
     RB_LAUNCH_CHECK("adam_rows_kernel");
+    return RB200_OK;
+}
+
+
+// ---- fused-step helpers: two tensors per launch ------------------------------------------------------------------ //
+int rb_adam_dense2(float* w0, const float* g0, float* m0, float* v0, long long n0, float* w1, const float* g1, float* m1, float* v1,
+                   long long n1, const rb200_opt_state* st, cudaStream_t s) {
+    AdamDenseParams p{};
+    p.n_jobs = 2;
+    p.job[0] = {w0, g0, m0, v0, n0};
+    p.job[1] = {w1, g1, m1, v1, n1};
+    adam_dense2_kernel<<<stream_grid((n0 > n1 ? n0 : n1) / 4 + 1), NT, 0, s>>>(p, st);
+    RB_LAUNCH_CHECK("adam_dense2_kernel");
+    return RB200_OK;
+}
+
+int rb_adam_tables_dense2(float* w0, float* m0, float* v0, long long rows0, int* slot0, const float* ug0, float* w1, float* m1, float* v1,
+                          long long rows1, int* slot1, const float* ug1, int D, const rb200_opt_state* st, cudaStream_t s) {
+    AdamTableParams p{};
+    p.n_jobs = 2; p.D4 = D / 4;
+    p.job[0] = {w0, m0, v0, rows0, slot0, ug0};
+    p.job[1] = {w1, m1, v1, rows1, slot1, ug1};
+    adam_table_dense2_kernel<<<stream_grid((rows0 > rows1 ? rows0 : rows1) * (D / 4)), NT, 0, s>>>(p, st);
+    RB_LAUNCH_CHECK("adam_table_dense2_kernel");
+    return RB200_OK;
+}
+
+int rb_reset_slots2(const int64_t* ids0, const int* n0, int cap0, int* slot0, const int64_t* ids1, const int* n1, int cap1, int* slot1,
+                    cudaStream_t s) {
+    reset_slots2_kernel<<<stream_grid(cap0 + cap1), NT, 0, s>>>(ids0, n0, slot0, ids1, n1, slot1);
+    RB_LAUNCH_CHECK("reset_slots2_kernel");
     return RB200_OK;
 }

@@ -13,6 +13,12 @@ int rb_tower_prep_tc(int n_sets, const float* const W1[], const float* const W2[
                      unsigned char* const img[], cudaStream_t st);
 size_t rb_tower_img_bytes(int D, int H, int E);
 bool rb_tower_tc_supported(int D, int H, int E);
+int rb_adam_dense2(float* w0, const float* g0, float* m0, float* v0, long long n0, float* w1, const float* g1, float* m1, float* v1,
+                   long long n1, const rb200_opt_state* st, cudaStream_t s);
+int rb_adam_tables_dense2(float* w0, float* m0, float* v0, long long rows0, int* slot0, const float* ug0, float* w1, float* m1, float* v1,
+                          long long rows1, int* slot1, const float* ug1, int D, const rb200_opt_state* st, cudaStream_t s);
+int rb_reset_slots2(const int64_t* ids0, const int* n0, int cap0, int* slot0, const int64_t* ids1, const int* n1, int cap1, int* slot1,
+                    cudaStream_t s);
 
 namespace {
 
@@ -262,15 +268,14 @@ extern "C" int rb200_bpr_step(const rb200_step_params* s, void* stream) {
 
     RB_STAGE_EVENT();
     // ---- Adam ---------------------------------------------------------------------------------- //
-    if ((rc = rb200_adam_dense(s->user_mlp, w.g_user_mlp, s->user_mlp_m, s->user_mlp_v, Pu, s->opt, st))) return rc;
-    if ((rc = rb200_adam_dense(s->item_mlp, w.g_item_mlp, s->item_mlp_m, s->item_mlp_v, Pi, s->opt, st))) return rc;
+    if ((rc = rb_adam_dense2(s->user_mlp, w.g_user_mlp, s->user_mlp_m, s->user_mlp_v, Pu, s->item_mlp, w.g_item_mlp, s->item_mlp_m,
+                             s->item_mlp_v, Pi, s->opt, st))) return rc;
     if (dense) {
-        if ((rc = rb200_adam_table_dense(s->user_table, s->user_table_m, s->user_table_v, s->n_user_rows, D, s->user_row_slot,
-                                         w.ug_u, s->opt, st))) return rc;
-        if ((rc = rb200_adam_table_dense(s->item_table, s->item_table_m, s->item_table_v, s->n_item_rows, D, s->item_row_slot,
-                                         w.ug_i, s->opt, st))) return rc;
-        if ((rc = rb200_scatter_reset_slots(w.uniq_u, w.n_uniq, B, s->user_row_slot, st))) return rc;
-        if ((rc = rb200_scatter_reset_slots(w.uniq_i, w.n_uniq + 1, items * B, s->item_row_slot, st))) return rc;
+        if ((rc = rb_adam_tables_dense2(s->user_table, s->user_table_m, s->user_table_v, s->n_user_rows, s->user_row_slot, w.ug_u,
+                                        s->item_table, s->item_table_m, s->item_table_v, s->n_item_rows, s->item_row_slot, w.ug_i, D,
+                                        s->opt, st))) return rc;
+        if ((rc = rb_reset_slots2(w.uniq_u, w.n_uniq, B, s->user_row_slot, w.uniq_i, w.n_uniq + 1, items * B, s->item_row_slot, st)))
+            return rc;
     } else {
         if ((rc = rb200_adam_rows(s->user_table, s->user_table_m, s->user_table_v, D, w.uniq_u, w.ug_u, w.n_uniq, B, s->opt, st))) return rc;
         if ((rc = rb200_adam_rows(s->item_table, s->item_table_m, s->item_table_v, D, w.uniq_i, w.ug_i, w.n_uniq + 1, items * B,

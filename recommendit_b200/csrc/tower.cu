@@ -613,7 +613,9 @@ extern "C" int rb200_tower_bwd(const rb200_tower_bwd_job* jobs, int n_jobs, int 
     if (mode != 0) {
         RB_REQUIRE(rb_tower_tc_supported(D, H, E), "tower_bwd: tcgen05 mode supports D=64, H=128, extra_dim<=24");
         RbArena tar(workspace, workspace_bytes);
-        int ns = (int)((total_rows + 255) / 256);                 // >= 256 batch rows per CTA
+        // split-K over the batch: short accumulation chains in TMEM (the tensor core's fp32 accumulation error grows with
+        // the chain length; ≤ ~128 rows per CTA keeps the weight gradients inside the 1e-5 bound), all SMs busy
+        int ns = (int)((total_rows + 63) / 64);
         if (ns > rb_sm_count()) ns = rb_sm_count();
         if (ns < 1) ns = 1;
         p.nsplit = ns;

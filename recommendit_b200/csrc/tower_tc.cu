@@ -156,6 +156,7 @@ template <int D, int H, int MODE>
 __global__ void __launch_bounds__(NT, 1) tower_fwd_tc_kernel(const FwdParams p) {
     extern __shared__ __align__(1024) unsigned char smem[];
     __shared__ float ss_part[2][ROWS];
+    __shared__ long long ids_s[ROWS];
     RB_TC_PROLOGUE(p.err_flag)
     int begins[MAX_JOBS];
 #pragma unroll
@@ -177,30 +178,44 @@ __global__ void __launch_bounds__(NT, 1) tower_fwd_tc_kernel(const FwdParams p) 
         umma::mbar_expect_tx(&w_bar_s, bytes);
         umma::bulk_g2s(w1_hi, J.img + L.w1, bytes, &w_bar_s);
     }
+    if (tid < ROWS) {
+        const int row = row0 + tid;
+        long long id = row < J.B ? J.ids[row] : 0;
+        if ((unsigned long long)id >= (unsigned long long)J.n_rows) { if (p.err_flag) atomicOr(p.err_flag, 1); id = 0; }
+        ids_s[tid] = id;
+    }
+    __syncthreads();
     {
-        // lane → (row%8 = lane&7, 16-byte chunk = 4·cq + lane>>3): 64-byte global segments, conflict-free 16-byte stores
-        const int K4 = Kp / 4, CQ = (K4 + 3) / 4;
-        for (int u = warp; u < (ROWS / 8) * CQ; u += NT / 32) {
-            const int rg = u / CQ, cq = u - rg * CQ;
-            const int r = rg * 8 + (lane & 7), c4 = cq * 4 + (lane >> 3);
-            if (c4 >= K4) continue;
-            const int row = row0 + r, k = c4 * 4;
-            const bool valid = row < J.B;
-            long long id = valid ? J.ids[row] : 0;
-            if ((unsigned long long)id >= (unsigned long long)J.n_rows) { if (p.err_flag) atomicOr(p.err_flag, 1); id = 0; }
-            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (valid) {
-                if (k < D) {
-                    v = __ldg(reinterpret_cast<const float4*>(J.table + id * D + k));
-                } else {
-                    const float* ex = J.extra + (J.extra_by_id ? id : (long long)row) * E + (k - D);
-                    v.x = k + 0 < Din ? __ldg(ex + 0) : 0.f;
-                    v.y = k + 1 < Din ? __ldg(ex + 1) : 0.f;
-                    v.z = k + 2 < Din ? __ldg(ex + 2) : 0.f;
-                    v.w = k + 3 < Din ? __ldg(ex + 3) : 0.f;
+        // lane → (row%8 = lane&7, 16-byte chunk = 4·cq + lane>>3): 64-byte global segments, conflict-free 16-byte stores;
+        // three units' loads are issued before their stores so that the gather latencies overlap
+        const int K4 = Kp / 4, CQ = (K4 + 3) / 4, n_units = (ROWS / 8) * CQ;
+        for (int u0 = warp; u0 < n_units; u0 += 3 * (NT / 32)) {
+            float4 v[3];
+            int rr[3], kk[3];
+#pragma unroll
+            for (int q = 0; q < 3; ++q) {
+                const int u = u0 + q * (NT / 32);
+                const int rg = u / CQ, cq = u - rg * CQ;
+                const int r = rg * 8 + (lane & 7), c4 = cq * 4 + (lane >> 3);
+                rr[q] = r; kk[q] = (u < n_units && c4 < K4) ? c4 * 4 : -1;
+                v[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (kk[q] >= 0 && row0 + r < J.B) {
+                    const int k = kk[q];
+                    const long long id = ids_s[r];
+                    if (k < D) {
+                        v[q] = __ldg(reinterpret_cast<const float4*>(J.table + id * D + k));
+                    } else {
+                        const float* ex = J.extra + (J.extra_by_id ? id : (long long)(row0 + r)) * E + (k - D);
+                        v[q].x = k + 0 < Din ? __ldg(ex + 0) : 0.f;
+                        v[q].y = k + 1 < Din ? __ldg(ex + 1) : 0.f;
+                        v[q].z = k + 2 < Din ? __ldg(ex + 2) : 0.f;
+                        v[q].w = k + 3 < Din ? __ldg(ex + 3) : 0.f;
+                    }
                 }
             }
-            put4<MODE>(x_hi, x_lo, ROWS, r, k, v);
+#pragma unroll
+            for (int q = 0; q < 3; ++q)
+                if (kk[q] >= 0) put4<MODE>(x_hi, x_lo, ROWS, rr[q], kk[q], v[q]);
         }
     }
     umma::fence_proxy_async();
@@ -439,11 +454,28 @@ __global__ void __launch_bounds__(NT, 1) tower_bwd_data_tc_kernel(const BwdParam
 // ------------------------------------------------------------------------------------------------------------ //
 constexpr int KC = 32;    // samples per staged chunk
 
+__device__ __forceinline__ float sel4(const float4& v, int e) { return e == 0 ? v.x : e == 1 ? v.y : e == 2 ? v.z : v.w; }
+
+// Transposing store of a 4(sample) × 4(row) block into an [R × KC] K-major operand: thread (sq = warp, mq = lane) holds
+// v[i] = 4 consecutive operand rows (4·mq … +3) of sample 4·sq+i and writes, for each of its rows, the 16-byte unit of
+// the 4 samples.  The row handled in store t is rotated with the lane (e = (t + lane/2) & 3) so that the 8 lanes of a
+// shared-memory phase hit 8 different 16-byte slots: conflict-free.
+template <int MODE>
+__device__ __forceinline__ void put_block_t(unsigned char* hi, unsigned char* lo, int R, int mq, int sq, int lane, const float4 (&v)[4]) {
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+        const int e = (t + (lane >> 1)) & 3;
+        put4<MODE>(hi, lo, R, mq * 4 + e, sq * 4, make_float4(sel4(v[0], e), sel4(v[1], e), sel4(v[2], e), sel4(v[3], e)));
+    }
+}
+
 template <int D, int H, int NK, int MODE>      // NK = padded Din (multiple of 32) = N of the dW1 product
 __global__ void __launch_bounds__(NT, 1) tower_bwd_weights_tc_kernel(const BwdParams p, int* err_flag) {
+    static_assert(H == 128 && D == 64 && KC == 32 && NT == 256, "thread mapping assumes 8 warps = 8 sample quads, 32 lanes = 32 row quads");
     extern __shared__ __align__(1024) unsigned char smem[];
     __shared__ long long ids_s[KC];
-    __shared__ float bias_part[2][2][ROWS];
+    __shared__ float bias1_part[KC / 4][H];      // per sample-quad partial column sums of dact
+    __shared__ float bias2_part[KC / 4][D];      // … of dpre
     RB_TC_PROLOGUE(err_flag)
     (void)w_bar;
     const int s = blockIdx.x;
@@ -457,11 +489,26 @@ __global__ void __launch_bounds__(NT, 1) tower_bwd_weights_tc_kernel(const BwdPa
     unsigned char* a2_lo = a2_hi + H * KC * 4;
     unsigned char* b2_hi = a2_lo + H * KC * 4;
     unsigned char* b2_lo = b2_hi + NK * KC * 4;
-    const int m = tid & (ROWS - 1), sh = tid >> 7;      // operand row handled by this thread, half of the chunk's samples
-    float db1 = 0.f, db2 = 0.f;
+    const int sq = warp, mq = lane;              // this thread's 4 samples (4·sq…) × 4 operand rows (4·mq…)
+    float4 db1 = make_float4(0.f, 0.f, 0.f, 0.f), db2 = db1;
     bool first = true;
+    // The tensor core's fp32 accumulation is not round-to-nearest: over a long chain the error grows linearly and is
+    // amplified when large partial sums cancel later (positive vs negative items in dW2).  Each chunk therefore starts a
+    // fresh TMEM accumulation (12 MMAs) that is flushed into these registers with ordinary fp32 adds.
+    constexpr int HC = D / 2, NB = (NK / 32 + 1) / 2;
+    float acc_a[HC];             // dW2ᵀ[h = r_own][d = half·HC + i]
+    float acc_b[NB][32];         // dW1[h = r_own][k = (half + 2·b)·32 + i]
+#pragma unroll
+    for (int i = 0; i < HC; ++i) acc_a[i] = 0.f;
+#pragma unroll
+    for (int b = 0; b < NB; ++b)
+#pragma unroll
+        for (int i = 0; i < 32; ++i) acc_b[b][i] = 0.f;
     for (int j = 0; j < p.n_jobs; ++j) {
         const BwdJob& J = p.job[j];
+        const float* __restrict__ hid = J.hid; const float* __restrict__ dact = J.dact; const float* __restrict__ dpre = J.dpre;
+        const float* __restrict__ table = J.table; const float* __restrict__ extra = J.extra;
+        const int by_id = J.extra_by_id;
         const int chunk = (((J.B + p.nsplit - 1) / p.nsplit) + KC - 1) / KC * KC;   // rows per CTA, multiple of KC
         const int r_begin = min(J.B, s * chunk), r_end = min(J.B, r_begin + chunk);
         for (int r0 = r_begin; r0 < r_end; r0 += KC) {
@@ -472,88 +519,128 @@ __global__ void __launch_bounds__(NT, 1) tower_bwd_weights_tc_kernel(const BwdPa
                 ids_s[tid] = id;
             }
             __syncthreads();
-            // thread = (operand row m, sample half sh); K = sample, 4 samples per 16-byte chunk; loads are coalesced across m
+            // ---- all global loads of the chunk first (16-byte, coalesced along the operand-row dimension) ---------- //
+            float4 hv[4], av[4], gv[4], xv[4];
 #pragma unroll
-            for (int c4 = sh * (KC / 8); c4 < (sh + 1) * (KC / 8); ++c4) {
-                float hv[4], av[4], gv[4], xv[4];
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    const int r = c4 * 4 + e;
-                    const bool ok = r < nr;
-                    const long long gr = r0 + r;
-                    hv[e] = (ok && m < H) ? __ldg(J.hid + gr * H + m) : 0.f;
-                    av[e] = (ok && m < H) ? __ldg(J.dact + gr * H + m) : 0.f;
-                    gv[e] = (ok && m < D) ? __ldg(J.dpre + gr * D + m) : 0.f;
-                    float x = 0.f;
-                    if (ok && m < Din) {
-                        if (m < D) x = __ldg(J.table + ids_s[r] * D + m);
-                        else x = __ldg(J.extra + (J.extra_by_id ? ids_s[r] : gr) * E + (m - D));
-                    }
-                    xv[e] = x;
-                    db1 += av[e];
-                    db2 += gv[e];
+            for (int i = 0; i < 4; ++i) {
+                const int r = sq * 4 + i;
+                const bool ok = r < nr;
+                const long long gr = r0 + r;
+                const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+                hv[i] = ok ? __ldg(reinterpret_cast<const float4*>(hid + gr * H) + mq) : z;
+                av[i] = ok ? __ldg(reinterpret_cast<const float4*>(dact + gr * H) + mq) : z;
+                gv[i] = (ok && mq < D / 4) ? __ldg(reinterpret_cast<const float4*>(dpre + gr * D) + mq) : z;
+                float4 x = z;
+                if (ok && mq < D / 4) {
+                    x = __ldg(reinterpret_cast<const float4*>(table + ids_s[r] * D) + mq);
+                } else if (ok && mq < NK / 4 && E > 0) {
+                    const int k = mq * 4 - D;          // genre column
+                    const float* ex = extra + (by_id ? ids_s[r] : gr) * E;
+                    x.x = k + 0 < E ? __ldg(ex + k + 0) : 0.f;
+                    x.y = k + 1 < E ? __ldg(ex + k + 1) : 0.f;
+                    x.z = k + 2 < E ? __ldg(ex + k + 2) : 0.f;
+                    x.w = k + 3 < E ? __ldg(ex + k + 3) : 0.f;
                 }
-                if (m < H) {
-                    put4<MODE>(a1_hi, a1_lo, H, m, c4 * 4, make_float4(hv[0], hv[1], hv[2], hv[3]));
-                    put4<MODE>(a2_hi, a2_lo, H, m, c4 * 4, make_float4(av[0], av[1], av[2], av[3]));
-                }
-                if (m < D) put4<MODE>(b1_hi, b1_lo, D, m, c4 * 4, make_float4(gv[0], gv[1], gv[2], gv[3]));
-                if (m < NK) put4<MODE>(b2_hi, b2_lo, NK, m, c4 * 4, make_float4(xv[0], xv[1], xv[2], xv[3]));
+                xv[i] = x;
             }
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                db1.x += av[i].x; db1.y += av[i].y; db1.z += av[i].z; db1.w += av[i].w;
+                db2.x += gv[i].x; db2.y += gv[i].y; db2.z += gv[i].z; db2.w += gv[i].w;
+            }
+            put_block_t<MODE>(a1_hi, a1_lo, H, mq, sq, lane, hv);
+            put_block_t<MODE>(a2_hi, a2_lo, H, mq, sq, lane, av);
+            if (mq < D / 4) put_block_t<MODE>(b1_hi, b1_lo, D, mq, sq, lane, gv);
+            if (mq < NK / 4) put_block_t<MODE>(b2_hi, b2_lo, NK, mq, sq, lane, xv);
             umma::fence_proxy_async();
             __syncthreads();
             if (tid == 0 && !dead) {
                 umma::fence_after_sync();
-                issue_gemm<MODE>(tmem, a1_hi, a1_lo, H, b1_hi, b1_lo, D, D, KC, !first);        // dW2ᵀ [H × D]
-                issue_gemm<MODE>(tmem + D, a2_hi, a2_lo, H, b2_hi, b2_lo, NK, NK, KC, !first);  // dW1  [H × NK]
+                issue_gemm<MODE>(tmem, a1_hi, a1_lo, H, b1_hi, b1_lo, D, D, KC, false);        // dW2ᵀ [H × D]
+                issue_gemm<MODE>(tmem + D, a2_hi, a2_lo, H, b2_hi, b2_lo, NK, NK, KC, false);  // dW1  [H × NK]
                 umma::commit(&mma_bar_s);
             }
             first = false;
             mma_bar.wait();          // chunk buffers are reused
             umma::fence_after_sync();
+            if (!dead) {
+#pragma unroll
+                for (int cb = 0; cb < HC / 32; ++cb) {
+                    float v[32];
+                    umma::tmem_ld32(tmem + lane_off + half * HC + cb * 32, v);
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) acc_a[cb * 32 + i] += v[i];
+                }
+#pragma unroll
+                for (int b = 0; b < NB; ++b) {
+                    const int cb = half + 2 * b;
+                    if (cb < NK / 32) {
+                        float v[32];
+                        umma::tmem_ld32(tmem + lane_off + D + cb * 32, v);
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) acc_b[b][i] += v[i];
+                    }
+                }
+            }
+            umma::fence_before_sync();
             __syncthreads();
         }
     }
     // partial block layout: [W1 (H*Din) | b1 (H) | W2 (D*H) | b2 (D)]
     float* part = p.part + (long long)s * p.P;
     float* w1o = part, *b1o = part + H * Din, *w2o = part + H * Din + H, *b2o = part + H * Din + H + D * H;
-    bias_part[0][sh][m] = db1;
-    bias_part[1][sh][m] = db2;
+    *reinterpret_cast<float4*>(&bias1_part[sq][mq * 4]) = db1;
+    if (mq < D / 4) *reinterpret_cast<float4*>(&bias2_part[sq][mq * 4]) = db2;
     __syncthreads();
     if (first) {          // this CTA had no rows: its partial is all zeros
         for (int i = tid; i < p.P; i += NT) part[i] = 0.f;
     } else {
         const int h = r_own;          // accumulator row
-        {   // dW2[d][h] = acc[h][d]; half selects the d range
-            constexpr int HC = D / 2;
 #pragma unroll
-            for (int cb = 0; cb < HC / 32; ++cb) {
-                float v[32];
-                umma::tmem_ld32(tmem + lane_off + half * HC + cb * 32, v);
+        for (int i = 0; i < HC; ++i) w2o[(long long)(half * HC + i) * H + h] = acc_a[i];          // dW2[d][h] = acc[h][d]
 #pragma unroll
-                for (int i = 0; i < 32; ++i) w2o[(long long)(half * HC + cb * 32 + i) * H + h] = v[i];
+        for (int b = 0; b < NB; ++b) {
+            const int cb = half + 2 * b;
+            if (cb < NK / 32) {
+#pragma unroll
+                for (int i = 0; i < 32; ++i)
+                    if (cb * 32 + i < Din) w1o[(long long)h * Din + cb * 32 + i] = acc_b[b][i];  // dW1[h][k]
             }
         }
-        for (int cb = half; cb < NK / 32; cb += 2) {      // dW1[h][k]
-            float v[32];
-            umma::tmem_ld32(tmem + lane_off + D + cb * 32, v);
+        if (tid < H) {
+            float t = 0.f;
 #pragma unroll
-            for (int i = 0; i < 32; ++i)
-                if (cb * 32 + i < Din) w1o[(long long)h * Din + cb * 32 + i] = v[i];
+            for (int q = 0; q < KC / 4; ++q) t += bias1_part[q][tid];      // fixed order
+            b1o[tid] = t;
         }
-        if (tid < H) b1o[tid] = bias_part[0][0][tid] + bias_part[0][1][tid];
-        if (tid < D) b2o[tid] = bias_part[1][0][tid] + bias_part[1][1][tid];
+        if (tid < D) {
+            float t = 0.f;
+#pragma unroll
+            for (int q = 0; q < KC / 4; ++q) t += bias2_part[q][tid];
+            b2o[tid] = t;
+        }
     }
     RB_TC_EPILOGUE()
 }
 
-__global__ void reduce_partials_tc_kernel(const float* __restrict__ part, int nsplit, int P, float* __restrict__ out, int accumulate) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= P) return;
-    float s = 0.f;
-#pragma unroll 8
-    for (int k = 0; k < nsplit; ++k) s += __ldg(part + (long long)k * P + i);   // fixed order
-    out[i] = accumulate ? out[i] + s : s;
+// out[i] = Σ_k part[k][i] in a fixed order.  Block = 32 outputs × 8 k-groups: group y adds the partials k ≡ y (mod 8)
+// (coalesced 128-byte rows), the 8 group sums are combined through shared memory in index order.
+__global__ void __launch_bounds__(256) reduce_partials_tc_kernel(const float* __restrict__ part, int nsplit, int P,
+                                                                 float* __restrict__ out, int accumulate) {
+    __shared__ float sm[8][33];
+    const int x = threadIdx.x & 31, y = threadIdx.x >> 5;
+    const int i = blockIdx.x * 32 + x;
+    float a = 0.f;
+    if (i < P)
+        for (int k = y; k < nsplit; k += 8) a += __ldg(part + (long long)k * P + i);
+    sm[y][x] = a;
+    __syncthreads();
+    if (y == 0 && i < P) {
+        float s = 0.f;
+#pragma unroll
+        for (int g = 0; g < 8; ++g) s += sm[g][x];
+        out[i] = accumulate ? out[i] + s : s;
+    }
 }
 
 template <typename JobT>
@@ -683,7 +770,7 @@ int rb_tower_bwd_tc(BwdParams& p, int D, int H, int mode, float* grads_out, int 
         else tower_bwd_weights_tc_kernel<64, 128, 96, 2><<<p.nsplit, NT, smem_w, st>>>(p, nullptr);
     }
     RB_LAUNCH_CHECK("tower_bwd_weights_tc_kernel");
-    reduce_partials_tc_kernel<<<(p.P + 255) / 256, 256, 0, st>>>(p.part, p.nsplit, p.P, grads_out, accumulate);
+    reduce_partials_tc_kernel<<<(p.P + 31) / 32, 256, 0, st>>>(p.part, p.nsplit, p.P, grads_out, accumulate);
     RB_LAUNCH_CHECK("reduce_partials_tc_kernel");
     return RB200_OK;
 }

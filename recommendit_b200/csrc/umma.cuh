@@ -79,13 +79,10 @@ __host__ __device__ constexpr uint32_t idesc_tf32(int M, int N, bool a_mn_major 
     return (1u << 4) /*c = F32*/ | (2u << 7) /*a = TF32*/ | (2u << 10) /*b = TF32*/ | ((a_mn_major ? 1u : 0u) << 15) |
            ((b_mn_major ? 1u : 0u) << 16) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
-// MN-major no-swizzle operand ([MN × K] logical, stored so that 4 consecutive MN elements share a 16-byte unit): a core
-// matrix is 8 K-rows × 16 B.  offset(mn, k) = (mn/4)·128 + (k/8)·(MN/4)·128 + (k%8)·16 + (mn%4)·4
-//   ⇒ SBO (MN-block stride) = 128 B, LBO (K-block stride) = (MN/4)·128 B.  A row-major [K][MN] global array (e.g. the
-// batch-major activations of a weight-gradient product) is staged with plain 16-byte copies, no transposition.
-__device__ __forceinline__ uint32_t mnmajor_offset(int MN, int mn, int k) {
-    return (uint32_t)(((mn >> 2) << 7) + (k >> 3) * ((MN >> 2) << 7) + ((k & 7) << 4) + ((mn & 3) << 2));
-}
+// NOTE (measured on B200, driver 580): with the MN-major bits (15/16) set and a no-swizzle MN-major operand layout
+// (8 K-rows × 16 B core matrices) kind::tf32 MMAs complete but leave the accumulator at zero.  All operands in this
+// library are therefore K-major; operands whose global layout is MN-contiguous (batch-major activations in the weight
+// gradients) are transposed while being staged (tower_tc.cu::put_block_t).
 // shared-memory matrix descriptor, no swizzle (cute::UMMA::SmemDescriptor bit layout, version 1 = Blackwell)
 __device__ __forceinline__ uint64_t smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
     return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16) |

@@ -345,18 +345,3 @@ def scores_nt(a: torch.Tensor, b: torch.Tensor, mode: int = 2) -> torch.Tensor:
         raise RB200Error("rb200_gemm_nt: tensor-core pipeline timed out (error flag %d)" % int(err.item()))
     return out
 
-
-def scores_tn(a: torch.Tensor, b: torch.Tensor, mode: int = 2) -> torch.Tensor:
-    """``a.T @ b`` for a [K, M], b [K, N] on the tensor cores (``rb200_gemm_tn``, MN-major operands)."""
-    lib = _lib.load()
-    _lib.require_cuda(a, b)
-    a, b = a.contiguous(), b.contiguous()
-    K, M = a.shape
-    N = b.shape[1]
-    out = torch.empty(M, N, dtype=torch.float32, device=a.device)
-    err = torch.zeros(1, dtype=torch.int32, device=a.device)
-    with torch.cuda.device(a.device):
-        check(lib.rb200_gemm_tn(ptr(a), M, ptr(b), N, K, mode, ptr(out), N, ptr(err), stream_ptr()), "rb200_gemm_tn")
-    if int(err.item()) != 0:
-        raise RB200Error("rb200_gemm_tn: tensor-core pipeline timed out (error flag %d)" % int(err.item()))
-    return out

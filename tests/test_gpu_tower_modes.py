@@ -88,29 +88,38 @@ def test_fused_step_modes_track_fp32_mode(golden, mode):
     assert torch.equal(res[mode][1]["item_uniq_ids"], res[0][1]["item_uniq_ids"])
 
 
-def test_full_batch_mode2_equals_mode0():
-    """C2 sizes (B = 8192): the tensor-core path and the FFMA path agree to fp32 rounding on a whole step."""
+def test_full_batch_modes_against_fp64_oracle():
+    """C2 sizes (B = 8192): FFMA path and 3xTF32 tensor-core path against the fp64 oracle on a whole step.  The batch sums
+    of the weight gradients run over 8192 / 16384 rows here; both fp32 engines must stay inside the 1e-5 bound
+    (second-Linear bias: 1e-4, see tests/parity.py)."""
     import recommendit_b200 as R
     torch.manual_seed(0)
     nu, ni, B = 6040, 3952, 8192
     rng = np.random.default_rng(2)
     u, p, n = rng.integers(0, nu + 1, B), rng.integers(0, ni + 1, B), rng.integers(0, ni + 1, B)
     table = (rng.random((ni + 1, 18)) < 0.1).astype(np.float32)
-    base = R.TwoTowerModel(nu, ni, 64, 128, dropout=0.1).cuda().train()
+    base = R.TwoTowerModel(nu, ni, 64, 128, dropout=0.0).cuda().train()
     sd = {k: v.clone() for k, v in base.state_dict().items()}
-    out = {}
+    P = {k: v.detach().cpu().numpy().astype(np.float64) for k, v in sd.items()}
+    l64, G64, (u64, p64, _) = O.loss_and_grads(P, u, p, table[p].astype(np.float64), n, table[n].astype(np.float64))
+    ref = {"user_mlp_grad": flat_mlp(G64, "user"), "item_mlp_grad": flat_mlp(G64, "item"), "user_emb": u64, "pos_emb": p64}
+    errs = {}
     for m in (0, 2):
-        model = R.TwoTowerModel(nu, ni, 64, 128, dropout=0.1).cuda().train()
+        model = R.TwoTowerModel(nu, ni, 64, 128, dropout=0.0).cuda().train()
         model.load_state_dict(sd)
         tr = R.FusedBPRTrainer(model, use_cuda_graph=False, tower_mode=m, seed=5)
         loss = tr.step_host(u, p, table[p], n, table[n])
-        out[m] = (loss, tr.views(), tr.opt_state.total_norm)
-    assert abs(out[0][0] - out[2][0]) <= 1e-6
-    assert abs(out[0][2] - out[2][2]) <= 1e-5 * out[0][2]
-    for key in ("user_mlp_grad", "item_mlp_grad", "user_uniq_grads", "item_uniq_grads", "user_emb", "pos_emb"):
-        a, b = out[2][1][key].cpu().numpy(), out[0][1][key].cpu().numpy()
-        if key.endswith("mlp_grad"):       # the last 64 entries are the cancellation-heavy second-bias gradient (1e-4 class)
-            assert rel_l2(a[:-64], b[:-64]) <= 1e-5, (key, rel_l2(a[:-64], b[:-64]))
-            assert rel_l2(a[-64:], b[-64:]) <= 1e-4, (key, rel_l2(a[-64:], b[-64:]))
-        else:
-            assert rel_l2(a, b) <= 1e-5, (key, rel_l2(a, b))
+        v = tr.views()
+        assert abs(loss - float(l64)) <= 1e-6, (m, loss, float(l64))
+        for key in ("user_mlp_grad", "item_mlp_grad"):
+            a, b = v[key].cpu().numpy(), ref[key]
+            errs[(m, key)] = (rel_l2(a[:-64], b[:-64]), rel_l2(a[-64:], b[-64:]))
+        for tower in ("user", "item"):
+            dense = G64[f"{tower}_tower.embedding.weight"]
+            ids = v[f"{tower}_uniq_ids"].cpu().numpy()
+            errs[(m, tower + "_rows")] = (rel_l2(v[f"{tower}_uniq_grads"].cpu().numpy(), dense[ids]), 0.0)
+        np.testing.assert_allclose(v["user_emb"].cpu().numpy(), ref["user_emb"], atol=2e-6, rtol=0)
+        np.testing.assert_allclose(v["pos_emb"].cpu().numpy(), ref["pos_emb"], atol=2e-6, rtol=0)
+    print("full-batch gradient errors vs fp64 (weights, bias2):", errs)
+    for key, (ew, eb) in errs.items():
+        assert ew <= 1e-5 and eb <= 1e-4, (key, ew, eb, errs)
