@@ -17,7 +17,8 @@
 
 namespace {
 
-constexpr int NT = 256;        // 8 warps: warps w and w+4 share TMEM lane quadrant w%4 and split the columns
+constexpr int NT = 256;        // weight-gradient kernel: 8 warps; warps w and w+4 share TMEM lane quadrant w%4 and split the columns
+constexpr int NTD = 512;       // forward / backward-data kernels: 16 warps, four column quarters per TMEM lane quadrant
 constexpr int ROWS = 128;      // samples per tile = TMEM lanes
 constexpr int TMEM_COLS = 256;
 
@@ -133,7 +134,7 @@ struct Bar {           // mbarrier with bounded waits and a sticky failure flag
     umma::fence_after_sync();                                                                                     \
     const uint32_t tmem = tmem_slot;                                                                              \
     Bar mma_bar{&mma_bar_s, 0u, &dead, err_ptr}, w_bar{&w_bar_s, 0u, &dead, err_ptr};                              \
-    const int r_own = ((warp & 3) << 5) + lane, half = warp >> 2;     /* TMEM lane (= tile row) and column half */ \
+    const int r_own = ((warp & 3) << 5) + lane, half = warp >> 2;     /* TMEM lane (= tile row) and column part  */ \
     const uint32_t lane_off = (uint32_t)((warp & 3) * 32) << 16;
 
 #define RB_TC_EPILOGUE()                                                               \
@@ -153,9 +154,9 @@ __device__ __forceinline__ int find_job(const int* begin, int n_jobs) {
 // forward
 // ------------------------------------------------------------------------------------------------------------ //
 template <int D, int H, int MODE>
-__global__ void __launch_bounds__(NT, 1) tower_fwd_tc_kernel(const FwdParams p) {
+__global__ void __launch_bounds__(NTD, 1) tower_fwd_tc_kernel(const FwdParams p) {
     extern __shared__ __align__(1024) unsigned char smem[];
-    __shared__ float ss_part[2][ROWS];
+    __shared__ float ss_part[4][ROWS];
     __shared__ long long ids_s[ROWS];
     RB_TC_PROLOGUE(p.err_flag)
     int begins[MAX_JOBS];
@@ -189,12 +190,12 @@ __global__ void __launch_bounds__(NT, 1) tower_fwd_tc_kernel(const FwdParams p) 
         // lane → (row%8 = lane&7, 16-byte chunk = 4·cq + lane>>3): 64-byte global segments, conflict-free 16-byte stores;
         // three units' loads are issued before their stores so that the gather latencies overlap
         const int K4 = Kp / 4, CQ = (K4 + 3) / 4, n_units = (ROWS / 8) * CQ;
-        for (int u0 = warp; u0 < n_units; u0 += 3 * (NT / 32)) {
+        for (int u0 = warp; u0 < n_units; u0 += 3 * (NTD / 32)) {
             float4 v[3];
             int rr[3], kk[3];
 #pragma unroll
             for (int q = 0; q < 3; ++q) {
-                const int u = u0 + q * (NT / 32);
+                const int u = u0 + q * (NTD / 32);
                 const int rg = u / CQ, cq = u - rg * CQ;
                 const int r = rg * 8 + (lane & 7), c4 = cq * 4 + (lane >> 3);
                 rr[q] = r; kk[q] = (u < n_units && c4 < K4) ? c4 * 4 : -1;
@@ -246,9 +247,9 @@ __global__ void __launch_bounds__(NT, 1) tower_fwd_tc_kernel(const FwdParams p) 
         const float keep_scale = do_drop ? 1.f / (1.f - p.drop_p) : 1.f;
         const unsigned long long drop_off = p.offset + (unsigned long long)j +
                                             (p.offset_dev ? (unsigned long long)__ldg(p.offset_dev) * MAX_JOBS : 0ull);
-#pragma unroll 1
-        for (int cb = 0; cb < H / 64; ++cb) {
-            const int col0 = half * (H / 2) + cb * 32;
+        static_assert(H == 128, "one 32-column TMEM load per thread");
+        {
+            const int col0 = half * 32;          // `half` is the column quarter here (16 warps)
             float v[32];
             umma::tmem_ld32(tmem + lane_off + col0, v);
 #pragma unroll
@@ -291,29 +292,25 @@ __global__ void __launch_bounds__(NT, 1) tower_fwd_tc_kernel(const FwdParams p) 
     mma_bar.wait();
     umma::fence_after_sync();
 
-    // ---- epilogue 2: bias, L2 normalise (two threads per row: partial sums combined in fixed order) ------------------ //
+    // ---- epilogue 2: bias, L2 normalise (four threads per row: partial sums combined in fixed order) ----------------- //
     {
-        constexpr int HC = D / 2;       // columns per thread
-        float y[HC];
+        static_assert(D == 64, "16 output columns per thread");
+        constexpr int QC = D / 4;
+        float y[QC];
         float ss = 0.f;
+        umma::tmem_ld16(tmem + lane_off + H + half * QC, y);
 #pragma unroll
-        for (int cb = 0; cb < HC / 32; ++cb) {
-            float v[32];
-            umma::tmem_ld32(tmem + lane_off + H + half * HC + cb * 32, v);
-#pragma unroll
-            for (int i = 0; i < 32; ++i) {
-                const float t = v[i] + __ldg(J.b2 + half * HC + cb * 32 + i);
-                y[cb * 32 + i] = t;
-                ss = fmaf(t, t, ss);
-            }
+        for (int i = 0; i < QC; ++i) {
+            y[i] += __ldg(J.b2 + half * QC + i);
+            ss = fmaf(y[i], y[i], ss);
         }
         ss_part[half][r_own] = ss;
         __syncthreads();
-        const float den = fmaxf(sqrtf(ss_part[0][r_own] + ss_part[1][r_own]), NORM_EPS);
+        const float den = fmaxf(sqrtf((ss_part[0][r_own] + ss_part[1][r_own]) + (ss_part[2][r_own] + ss_part[3][r_own])), NORM_EPS);
         if (valid) {
 #pragma unroll
-            for (int c4 = 0; c4 < HC / 4; ++c4)
-                *reinterpret_cast<float4*>(J.out + (long long)row * D + half * HC + c4 * 4) =
+            for (int c4 = 0; c4 < QC / 4; ++c4)
+                *reinterpret_cast<float4*>(J.out + (long long)row * D + half * QC + c4 * 4) =
                     make_float4(y[c4 * 4] / den, y[c4 * 4 + 1] / den, y[c4 * 4 + 2] / den, y[c4 * 4 + 3] / den);
             if (J.denom && half == 0) J.denom[row] = den;
         }
@@ -325,9 +322,9 @@ __global__ void __launch_bounds__(NT, 1) tower_fwd_tc_kernel(const FwdParams p) 
 // backward, data part
 // ------------------------------------------------------------------------------------------------------------ //
 template <int D, int H, int MODE>
-__global__ void __launch_bounds__(NT, 1) tower_bwd_data_tc_kernel(const BwdParams p, int* err_flag) {
+__global__ void __launch_bounds__(NTD, 1) tower_bwd_data_tc_kernel(const BwdParams p, int* err_flag) {
     extern __shared__ __align__(1024) unsigned char smem[];
-    __shared__ float dot_part[2][ROWS];
+    __shared__ float dot_part[4][ROWS];
     RB_TC_PROLOGUE(err_flag)
     int begins[MAX_JOBS];
 #pragma unroll
@@ -349,7 +346,7 @@ __global__ void __launch_bounds__(NT, 1) tower_bwd_data_tc_kernel(const BwdParam
         umma::bulk_g2s(w2t_hi, J.img + L.w2t, bytes, &w_bar_s);
     }
     {
-        constexpr int HC = D / 2;
+        constexpr int HC = D / 4;            // columns per thread (`half` is the column quarter: 16 warps)
         float g[HC], yv[HC];
         float dot = 0.f;
 #pragma unroll
@@ -365,7 +362,7 @@ __global__ void __launch_bounds__(NT, 1) tower_bwd_data_tc_kernel(const BwdParam
         }
         dot_part[half][r_own] = dot;
         __syncthreads();
-        dot = dot_part[0][r_own] + dot_part[1][r_own];
+        dot = (dot_part[0][r_own] + dot_part[1][r_own]) + (dot_part[2][r_own] + dot_part[3][r_own]);
         const float den = valid ? __ldg(J.denom + row) : 1.f;
         const bool clamped = den <= NORM_EPS;
 #pragma unroll
@@ -402,9 +399,9 @@ __global__ void __launch_bounds__(NT, 1) tower_bwd_data_tc_kernel(const BwdParam
         umma::mbar_expect_tx(&w_bar_s, bytes);
         umma::bulk_g2s(w1t_hi, J.img + L.w1t, bytes, &w_bar_s);
     }
-#pragma unroll 1
-    for (int cb = 0; cb < H / 64; ++cb) {
-        const int col0 = half * (H / 2) + cb * 32;
+    static_assert(H == 128, "one 32-column TMEM load per thread");
+    {
+        const int col0 = half * 32;
         float v[32];
         umma::tmem_ld32(tmem + lane_off + col0, v);
 #pragma unroll
@@ -433,17 +430,14 @@ __global__ void __launch_bounds__(NT, 1) tower_bwd_data_tc_kernel(const BwdParam
     mma_bar.wait();
     umma::fence_after_sync();
     {
-        constexpr int HC = D / 2;
+        constexpr int QC = D / 4;
+        float v[QC];
+        umma::tmem_ld16(tmem + lane_off + H + half * QC, v);
+        if (valid) {
 #pragma unroll
-        for (int cb = 0; cb < HC / 32; ++cb) {
-            float v[32];
-            umma::tmem_ld32(tmem + lane_off + H + half * HC + cb * 32, v);
-            if (valid) {
-#pragma unroll
-                for (int i4 = 0; i4 < 8; ++i4)
-                    *reinterpret_cast<float4*>(J.dRows + (long long)row * D + half * HC + cb * 32 + i4 * 4) =
-                        make_float4(v[i4 * 4], v[i4 * 4 + 1], v[i4 * 4 + 2], v[i4 * 4 + 3]);
-            }
+            for (int i4 = 0; i4 < QC / 4; ++i4)
+                *reinterpret_cast<float4*>(J.dRows + (long long)row * D + half * QC + i4 * 4) =
+                    make_float4(v[i4 * 4], v[i4 * 4 + 1], v[i4 * 4 + 2], v[i4 * 4 + 3]);
         }
     }
     RB_TC_EPILOGUE()
@@ -727,8 +721,8 @@ int rb_tower_fwd_tc(FwdParams& p, int D, int H, int mode, void* workspace, size_
         attr = true;
     }
     RB_REQUIRE(smem <= 200 * 1024, "tower_fwd (tcgen05): shared memory budget exceeded");
-    if (mode == 1) tower_fwd_tc_kernel<64, 128, 1><<<grid, NT, smem, st>>>(p);
-    else tower_fwd_tc_kernel<64, 128, 2><<<grid, NT, smem, st>>>(p);
+    if (mode == 1) tower_fwd_tc_kernel<64, 128, 1><<<grid, NTD, smem, st>>>(p);
+    else tower_fwd_tc_kernel<64, 128, 2><<<grid, NTD, smem, st>>>(p);
     RB_LAUNCH_CHECK("tower_fwd_tc_kernel");
     return RB200_OK;
 }
@@ -759,8 +753,8 @@ int rb_tower_bwd_tc(BwdParams& p, int D, int H, int mode, float* grads_out, int 
         if ((rc = set_smem(tower_bwd_weights_tc_kernel<64, 128, 96, 2>, 128 * 1024))) return rc;
         attr = true;
     }
-    if (mode == 1) tower_bwd_data_tc_kernel<64, 128, 1><<<grid, NT, smem_d, st>>>(p, nullptr);
-    else tower_bwd_data_tc_kernel<64, 128, 2><<<grid, NT, smem_d, st>>>(p, nullptr);
+    if (mode == 1) tower_bwd_data_tc_kernel<64, 128, 1><<<grid, NTD, smem_d, st>>>(p, nullptr);
+    else tower_bwd_data_tc_kernel<64, 128, 2><<<grid, NTD, smem_d, st>>>(p, nullptr);
     RB_LAUNCH_CHECK("tower_bwd_data_tc_kernel");
     if (E == 0) {
         if (mode == 1) tower_bwd_weights_tc_kernel<64, 128, 64, 1><<<p.nsplit, NT, smem_w, st>>>(p, nullptr);
