@@ -18,6 +18,10 @@
 
 #include "common.cuh"
 
+// tcgen05 score product (gemm_tc.cu): C[M,N] = A[M,K]·B[N,K]ᵀ, mode 2 = 3xTF32 (fp32-grade)
+int rb_gemm_nt_tc(const float* A, int M, const float* B, int N, int K, int mode, float* C, long long ldc, int* err_flag,
+                  cudaStream_t st);
+
 namespace {
 
 constexpr int NT = 256;
@@ -99,36 +103,6 @@ int allow_smem(K kernel, size_t bytes, bool& done) {
         if (rc__) return rc__;                                                      \
         KERNEL<DD><<<GRID, NT, tile_pair_bytes<DD>(), ST>>>(__VA_ARGS__);           \
     } while (0)
-
-// ------------------------------------------------------------------------------------------ //
-// dense scores: out[a][col0 + b] = A[a]·Bm[b]   (coarse quantizer, flat-search chunks)
-// ------------------------------------------------------------------------------------------ //
-template <int D>
-__global__ void __launch_bounds__(NT) dense_scores_kernel(const float* __restrict__ A, long long na, const float* __restrict__ Bm,
-                                                          long long nb, float* __restrict__ out, long long ld_out,
-                                                          long long col0) {
-    constexpr int LD = Ld<D>::v;
-    extern __shared__ __align__(16) float tile_smem[];
-    float* As = tile_smem;
-    float* Bs = tile_smem + TT * LD;
-    const long long a0 = (long long)blockIdx.y * TT, b0 = (long long)blockIdx.x * TT;
-    load_tile<D, int>(As, LD, A, a0, na, nullptr, 1);
-    load_tile<D, int>(Bs, LD, Bm, b0, nb, nullptr, 1);
-    __syncthreads();
-    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
-    float acc[4][4];
-    score_tile<D, LD>(As, Bs, tx, ty, acc);
-#pragma unroll
-    for (int r = 0; r < 4; ++r) {
-        const long long a = a0 + ty * 4 + r;
-        if (a >= na) continue;
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-            const long long b = b0 + tx + 16 * c;
-            if (b < nb) out[a * ld_out + col0 + b] = acc[r][c];
-        }
-    }
-}
 
 // ------------------------------------------------------------------------------------------ //
 // assignment: argmax_c x·centroid_c  (lowest index on ties)
@@ -693,9 +667,10 @@ extern "C" int rb200_ivf_search_plan(const float* q, int nq, int D, const float*
     RbArena ar(plan_ws, plan_ws_bytes);
     PlanLayout L;
     if (!plan_ws || !carve_plan(ar, nq, nlist, nprobe, L)) return rb_set_error(RB200_ERR_WORKSPACE, "ivf_search_plan: workspace too small");
-    const dim3 g((nlist + TT - 1) / TT, (nq + TT - 1) / TT);
-    RB_DISPATCH_D(D, RB_TILE_LAUNCH(dense_scores_kernel, DD, g, st, q, nq, centroids, nlist, L.coarse, nlist, 0));
-    RB_LAUNCH_CHECK("dense_scores_kernel");
+    {   // coarse quantizer q·Cᵀ on the tensor cores (3xTF32, fp32 accumulate in TMEM)
+        int rc = rb_gemm_nt_tc(q, nq, centroids, nlist, D, 2, L.coarse, nlist, nullptr, st);
+        if (rc) return rc;
+    }
     RB_CUDA(cudaMemsetAsync(L.list_qcount, 0, sizeof(int) * ((size_t)nlist + 2), st));
     {
         ResolveIdentity res{0};
@@ -803,9 +778,10 @@ extern "C" int rb200_flat_search(const float* q, int nq, const float* x, int64_t
             copy_prev_kernel<<<(unsigned)(((long long)nq * k + NT - 1) / NT), NT, 0, st>>>(prev_s, nq, k, cand, stride);
             RB_LAUNCH_CHECK("copy_prev_kernel");
         }
-        const dim3 g((unsigned)((rows + TT - 1) / TT), (nq + TT - 1) / TT);
-        RB_DISPATCH_D(D, RB_TILE_LAUNCH(dense_scores_kernel, DD, g, st, q, nq, x + r0 * D, rows, cand, stride, kprev));
-        RB_LAUNCH_CHECK("dense_scores_kernel");
+        {   // chunk scores on the tensor cores (3xTF32)
+            int rc = rb_gemm_nt_tc(q, nq, x + r0 * D, (int)rows, D, 2, cand + kprev, stride, nullptr, st);
+            if (rc) return rc;
+        }
         ResolveFlat res{prev_i, kprev, id_base + r0};
         // previous winners may contain -FLT_MAX padding (when fewer than k rows so far): they carry id -1
         int rc = launch_select<ResolveFlat>(cand, nullptr, stride, nullptr, (int)(rows + kprev), rows + kprev, nq, k, res, cur_s, cur_i, st);
