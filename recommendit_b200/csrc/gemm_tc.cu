@@ -90,18 +90,22 @@ __global__ void __launch_bounds__(128, 1) gemm_nt_tc_kernel(const float* __restr
         umma::fence_after_sync();
         __syncthreads();
     }
-    // epilogue: TMEM lane = output row
-    const long long row = m0 + tid;
+    // epilogue: TMEM lane = output row.  The tile goes through shared memory (the operand buffers are free now) so that
+    // global stores are 128-byte row segments instead of one element per row per instruction.
+    float* tile = reinterpret_cast<float*>(smem);          // [128][33]
+    const int lane = tid & 31;
 #pragma unroll 1
     for (int cb = 0; cb < TN / 32; ++cb) {
         float v[32];
         umma::tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + cb * 32, v);
-        if (row < M) {
+        __syncthreads();                                    // previous block's readers are done
 #pragma unroll
-            for (int i = 0; i < 32; ++i) {
-                const long long col = n0 + cb * 32 + i;
-                if (col < N) C[row * ldc + col] = v[i];
-            }
+        for (int i = 0; i < 32; ++i) tile[tid * 33 + i] = v[i];
+        __syncthreads();
+        const long long col = n0 + cb * 32 + lane;
+        for (int r = warp; r < TM; r += 4) {
+            const long long row = m0 + r;
+            if (row < M && col < N) C[row * ldc + col] = tile[r * 33 + lane];
         }
     }
     umma::fence_before_sync();

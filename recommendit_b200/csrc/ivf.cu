@@ -237,24 +237,35 @@ int sort_rows_by_list(const int* assign, long long n, int nlist, SortWs& w, cuda
 // search, step 2: top-nprobe lists per query (one CTA per query) + candidate bookkeeping
 // ------------------------------------------------------------------------------------------ //
 // After the generic top-k kernel picked the nprobe best lists per query (score desc, list id asc): candidate
-// bookkeeping, one thread per query.
+// bookkeeping, one warp per query (lane = probe rank, exclusive scan of the list lengths by shuffles).
 __global__ void __launch_bounds__(NT) probe_finish_kernel(const int64_t* __restrict__ probe_ids, int nq, int nprobe,
                                                           const int64_t* __restrict__ offsets, int* __restrict__ probes,
                                                           int* __restrict__ cand_base, long long* __restrict__ totals,
                                                           int* __restrict__ list_qcount) {
-    const int q = blockIdx.x * NT + threadIdx.x;
+    const int q = (blockIdx.x * NT + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (q >= nq) return;
-    long long total = 0;
-    for (int p = 0; p < nprobe; ++p) {
-        const long long l = probe_ids[(long long)q * nprobe + p];
-        probes[(long long)q * nprobe + p] = (int)l;
-        cand_base[(long long)q * nprobe + p] = (int)total;
-        if (l >= 0) {
-            total += offsets[l + 1] - offsets[l];
-            atomicAdd(list_qcount + l, 1);
+    int running = 0;
+    for (int p0 = 0; p0 < nprobe; p0 += 32) {
+        const int p = p0 + lane;
+        long long l = -1;
+        int len = 0;
+        if (p < nprobe) {
+            l = probe_ids[(long long)q * nprobe + p];
+            if (l >= 0) { len = (int)(offsets[l + 1] - offsets[l]); atomicAdd(list_qcount + l, 1); }
         }
+        int incl = len;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(RB_FULL_MASK, incl, o);
+            if (lane >= o) incl += t;
+        }
+        if (p < nprobe) {
+            probes[(long long)q * nprobe + p] = (int)l;
+            cand_base[(long long)q * nprobe + p] = running + incl - len;
+        }
+        running += __shfl_sync(RB_FULL_MASK, incl, 31);
     }
-    totals[q] = total;
+    if (lane == 0) totals[q] = running;
 }
 
 __global__ void pair_keys_kernel(const int* __restrict__ probes, long long n_pairs, int nlist, int* __restrict__ keys,
@@ -266,11 +277,24 @@ __global__ void pair_keys_kernel(const int* __restrict__ probes, long long n_pai
     vals[i] = (int)i;
 }
 
-__global__ void reduce_totals_kernel(const long long* __restrict__ totals, int nq, long long* __restrict__ out2) {
-    if (threadIdx.x || blockIdx.x) return;
+// Σ and max of the per-query candidate counts (one block; integer arithmetic, order-independent)
+__global__ void __launch_bounds__(NT) reduce_totals_kernel(const long long* __restrict__ totals, int nq, long long* __restrict__ out2) {
+    __shared__ long long ssum[NT / 32], smax[NT / 32];
     long long s = 0, m = 0;
-    for (int i = 0; i < nq; ++i) { s += totals[i]; if (totals[i] > m) m = totals[i]; }
-    out2[0] = s; out2[1] = m;
+    for (int i = threadIdx.x; i < nq; i += NT) { const long long t = totals[i]; s += t; m = t > m ? t : m; }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        s += __shfl_xor_sync(RB_FULL_MASK, s, o);
+        const long long om = __shfl_xor_sync(RB_FULL_MASK, m, o);
+        m = om > m ? om : m;
+    }
+    if ((threadIdx.x & 31) == 0) { ssum[threadIdx.x >> 5] = s; smax[threadIdx.x >> 5] = m; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        s = 0; m = 0;
+        for (int w = 0; w < NT / 32; ++w) { s += ssum[w]; m = smax[w] > m ? smax[w] : m; }
+        out2[0] = s; out2[1] = m;
+    }
 }
 
 // ------------------------------------------------------------------------------------------ //
@@ -281,15 +305,18 @@ __global__ void __launch_bounds__(NT) list_scan_kernel(const float* __restrict__
                                                        const int64_t* __restrict__ offsets, const int* __restrict__ pair_qp,
                                                        const int* __restrict__ list_qstart, int nprobe,
                                                        const int* __restrict__ cand_base, const long long* __restrict__ cand_off,
-                                                       float* __restrict__ cand) {
+                                                       float* __restrict__ cand, const int* __restrict__ tile_list,
+                                                       const int* __restrict__ tile_idx) {
     constexpr int LD = Ld<D>::v;
     extern __shared__ __align__(16) float tile_smem[];
     float* Vs = tile_smem;
     float* Qs = tile_smem + TT * LD;
     __shared__ long long dst[TT];
-    const int l = blockIdx.y;
+    // work item = (list, 64-vector tile): from the index's precomputed tile table when given (no empty CTAs), else 2-D grid
+    const int l = tile_list ? tile_list[blockIdx.x] : (int)blockIdx.y;
+    const int ti = tile_list ? tile_idx[blockIdx.x] : (int)blockIdx.x;
     const long long lbeg = offsets[l], lend = offsets[l + 1];
-    const long long v0 = lbeg + (long long)blockIdx.x * TT;
+    const long long v0 = lbeg + (long long)ti * TT;
     if (v0 >= lend) return;
     const int qs = list_qstart[l], qe = list_qstart[l + 1];
     if (qs == qe) return;
@@ -339,25 +366,37 @@ __device__ __forceinline__ float key2f(uint32_t k) {
 // id resolution modes for the winners
 struct ResolveIvf {      // candidate position → (probe, offset in list) → list_ids
     const int* probes; const int* cand_base; const int64_t* offsets; const int64_t* list_ids; int nprobe;
+    const int* s_base; const int* s_probe;      // shared-memory copies for the current query (set by stage)
+    __host__ __device__ int aux_ints() const { return 2 * nprobe; }
+    __device__ void stage(int q, int* aux, int tid, int nt) {
+        for (int i = tid; i < nprobe; i += nt) { aux[i] = cand_base[(long long)q * nprobe + i]; aux[nprobe + i] = probes[(long long)q * nprobe + i]; }
+        s_base = aux; s_probe = aux + nprobe;
+    }
 };
-struct ResolveIdentity { int unused; };   // candidate position is the id (coarse quantizer: list number)
+struct ResolveIdentity {   // candidate position is the id (coarse quantizer: list number)
+    int unused;
+    __host__ __device__ int aux_ints() const { return 0; }
+    __device__ void stage(int, int*, int, int) {}
+};
 struct ResolveFlat {     // [running top-k (kprev entries) | chunk rows]
     const int64_t* prev_ids; int kprev; long long row_base;
+    __host__ __device__ int aux_ints() const { return 0; }
+    __device__ void stage(int, int*, int, int) {}
 };
 
 template <typename R> __device__ long long resolve_id(const R& r, int q, int c);
 template <> __device__ long long resolve_id<ResolveIvf>(const ResolveIvf& r, int q, int c) {
-    const int* base = r.cand_base + (long long)q * r.nprobe;
+    (void)q;
+    const int* base = r.s_base;
     int lo = 0, hi = r.nprobe - 1;           // last probe p with base[p] <= c  (empty lists share a base: take the last)
     while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (base[mid] <= c) lo = mid; else hi = mid - 1; }
-    // step back over probes whose list is too short to contain c (only possible for empty/invalid ones after lo)
-    int p = lo;
+    int p = lo;                              // step back over empty / invalid probes that share the base
     while (p > 0) {
-        const int l = r.probes[(long long)q * r.nprobe + p];
+        const int l = r.s_probe[p];
         if (l >= 0 && c - base[p] < r.offsets[l + 1] - r.offsets[l]) break;
         --p;
     }
-    const int l = r.probes[(long long)q * r.nprobe + p];
+    const int l = r.s_probe[p];
     return r.list_ids[r.offsets[l] + (c - base[p])];
 }
 template <> __device__ long long resolve_id<ResolveIdentity>(const ResolveIdentity&, int, int c) { return c; }
@@ -367,6 +406,7 @@ template <> __device__ long long resolve_id<ResolveFlat>(const ResolveFlat& r, i
 }
 
 constexpr int SORT_CAP = 2048;   // winners + boundary bucket must fit the in-CTA sort (falls back to radix select otherwise)
+constexpr int NBK = 1024;        // value-range buckets of the fast path (fine enough that top-500 + boundary bucket ≤ 512 usually)
 
 // Per-query top-k (one CTA per query).
 //   fast path : value-range bucket select — min/max of the scores, 256 linear buckets over [min, max] (well spread even
@@ -383,7 +423,9 @@ __global__ void __launch_bounds__(NT) select_topk_kernel(const float* __restrict
     uint32_t* skey = reinterpret_cast<uint32_t*>(sm_raw);           // [SORT_CAP]
     int* sidx = reinterpret_cast<int*>(skey + SORT_CAP);            // [SORT_CAP]
     float* cache = reinterpret_cast<float*>(sidx + SORT_CAP);       // [cache_cap]
+    int* aux = reinterpret_cast<int*>(cache + cache_cap);           // [res.aux_ints()] per-query lookup tables of the resolver
     __shared__ int hist[256];
+    __shared__ int hist_f[NBK];           // fast path: NBK linear buckets over [min, max]
     __shared__ int wsum[2][NT / 32];
     __shared__ uint32_t s_prefix;
     __shared__ int s_a, s_b, s_count;
@@ -392,7 +434,14 @@ __global__ void __launch_bounds__(NT) select_topk_kernel(const float* __restrict
     const int n = counts ? (int)counts[q] : fixed_count;
 
     if (n <= cache_cap) {
-        for (int i = tid; i < n; i += NT) cache[i] = src[i];
+        // 8 independent loads in flight per thread (a plain copy loop serialises on every load's latency)
+        for (int i0 = tid; i0 < n; i0 += 8 * NT) {
+            float v[8];
+#pragma unroll
+            for (int b = 0; b < 8; ++b) { const int i = i0 + b * NT; v[b] = i < n ? __ldg(src + i) : 0.f; }
+#pragma unroll
+            for (int b = 0; b < 8; ++b) { const int i = i0 + b * NT; if (i < n) cache[i] = v[b]; }
+        }
         __syncthreads();
         src = cache;
     }
@@ -412,20 +461,37 @@ __global__ void __launch_bounds__(NT) select_topk_kernel(const float* __restrict
             hi = fmaxf(hi, __shfl_xor_sync(RB_FULL_MASK, hi, o));
         }
         if (lane == 0) { wsum[0][warp] = __float_as_int(lo); wsum[1][warp] = __float_as_int(hi); }
-        hist[tid] = 0;
+#pragma unroll
+        for (int c = 0; c < NBK / NT; ++c) hist_f[tid * (NBK / NT) + c] = 0;
         if (tid == 0) s_count = 0;
         __syncthreads();
         for (int w = 0; w < NT / 32; ++w) { lo = fminf(lo, __int_as_float(wsum[0][w])); hi = fmaxf(hi, __int_as_float(wsum[1][w])); }
-        const float scale = (hi > lo) ? 256.f / (hi - lo) : 0.f;
+        const float scale = (hi > lo) ? (float)NBK / (hi - lo) : 0.f;
         for (int i = tid; i < n; i += NT) {
-            const int b = min(255, (int)((src[i] - lo) * scale));
-            atomicAdd(&hist[b], 1);
+            const int b = min(NBK - 1, (int)((src[i] - lo) * scale));
+            atomicAdd(&hist_f[b], 1);
         }
         __syncthreads();
-        if (tid == 0) {
-            int cum = 0, b = 255;
-            for (; b > 0; --b) { if (cum + hist[b] >= k) break; cum += hist[b]; }
-            s_a = b; s_b = cum + hist[b];            // boundary bucket, #candidates in buckets >= b*
+        {
+            // boundary bucket b* = largest b with count(bucket ≥ b) ≥ k, found with a block-wide suffix sum
+            constexpr int PB = NBK / NT;
+            int part = 0;
+#pragma unroll
+            for (int c = 0; c < PB; ++c) part += hist_f[tid * PB + c];
+            int suf = part;                              // Σ over lanes ≥ lane (within the warp)
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int t = __shfl_down_sync(RB_FULL_MASK, suf, o);
+                if (lane + o < 32) suf += t;
+            }
+            if (lane == 0) wsum[0][warp] = suf;
+            __syncthreads();
+            for (int w = warp + 1; w < NT / 32; ++w) suf += wsum[0][w];
+            if (suf >= k && suf - part < k) {            // the boundary lies inside this thread's PB buckets
+                int cum = suf - part, b = tid * PB + PB - 1;
+                for (; b > tid * PB; --b) { if (cum + hist_f[b] >= k) break; cum += hist_f[b]; }
+                s_a = b; s_b = cum + hist_f[b];
+            }
         }
         __syncthreads();
         const int bstar = s_a, m_fast = s_b;
@@ -433,7 +499,7 @@ __global__ void __launch_bounds__(NT) select_topk_kernel(const float* __restrict
             for (int base = 0; base < n; base += NT) {
                 const int i = base + tid;
                 bool take = false; float v = 0.f;
-                if (i < n) { v = src[i]; take = min(255, (int)((v - lo) * scale)) >= bstar; }
+                if (i < n) { v = src[i]; take = min(NBK - 1, (int)((v - lo) * scale)) >= bstar; }
                 const uint32_t bal = __ballot_sync(RB_FULL_MASK, take);
                 int wbase = 0;
                 if (lane == 0 && bal) wbase = atomicAdd(&s_count, __popc(bal));
@@ -508,6 +574,8 @@ __global__ void __launch_bounds__(NT) select_topk_kernel(const float* __restrict
         }
     }
     __syncthreads();
+    res.stage(q, aux, tid, NT);          // resolver copies its per-query tables into shared memory (no dependent global chains)
+    __syncthreads();
     const int n_out = m < k ? m : k;
     for (int j = tid; j < k; j += NT) {
         if (j < n_out) {
@@ -526,9 +594,11 @@ template <typename R>
 int launch_select(const float* cand, const long long* cand_off, long long fixed_stride, const long long* counts,
                   int fixed_count, long long max_count, int nq, int k, const R& res, float* out_scores, int64_t* out_ids,
                   cudaStream_t st) {
-    int cache_cap = (int)(max_count < 24576 ? max_count : 24576);
+    // candidates of a query are cached in shared memory when they fit 12288 floats (48 KB keeps 3 CTAs per SM); the few
+    // larger queries stream their candidates from L2 in every pass
+    int cache_cap = (int)(max_count < 12288 ? max_count : 12288);
     if (cache_cap < 0) cache_cap = 0;
-    const size_t smem = (size_t)SORT_CAP * 8 + (size_t)cache_cap * 4 + 16;
+    const size_t smem = (size_t)SORT_CAP * 8 + (size_t)cache_cap * 4 + (size_t)res.aux_ints() * 4 + 16;
     static size_t attr_smem = 0;
     if (smem > attr_smem) {
         RB_CUDA(cudaFuncSetAttribute(select_topk_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem > 48 * 1024 ? smem : 48 * 1024)));
@@ -541,7 +611,11 @@ int launch_select(const float* cand, const long long* cand_off, long long fixed_
 }
 
 // k-way merge of `parts` sorted lists per query: treat the concatenation as candidates
-struct ResolveMerge { const int64_t* ids; int parts; int nq; int k; };
+struct ResolveMerge {
+    const int64_t* ids; int parts; int nq; int k;
+    __host__ __device__ int aux_ints() const { return 0; }
+    __device__ void stage(int, int*, int, int) {}
+};
 template <> __device__ long long resolve_id<ResolveMerge>(const ResolveMerge& r, int q, int c) {
     const int part = c / r.k, j = c - part * r.k;
     return r.ids[((long long)part * r.nq + q) * r.k + j];
@@ -678,7 +752,7 @@ extern "C" int rb200_ivf_search_plan(const float* q, int nq, int D, const float*
                                                 L.probe_ids, st);
         if (rc) return rc;
     }
-    probe_finish_kernel<<<(nq + NT - 1) / NT, NT, 0, st>>>(L.probe_ids, nq, nprobe, offsets, L.probes, L.cand_base, L.totals,
+    probe_finish_kernel<<<(unsigned)(((long long)nq * 32 + NT - 1) / NT), NT, 0, st>>>(L.probe_ids, nq, nprobe, offsets, L.probes, L.cand_base, L.totals,
                                                          L.list_qcount);
     RB_LAUNCH_CHECK("probe_finish_kernel");
     const long long np = (long long)nq * nprobe;
@@ -692,7 +766,7 @@ extern "C" int rb200_ivf_search_plan(const float* q, int nq, int D, const float*
     RB_CUDA(cudaMemsetAsync(L.totals + nq, 0, sizeof(long long), st));
     tb = L.temp_bytes;
     RB_CUDA(cub::DeviceScan::ExclusiveSum(L.temp, tb, (const long long*)L.totals, L.cand_off, nq + 1, st));
-    reduce_totals_kernel<<<1, 32, 0, st>>>(L.totals, nq, L.tot2);
+    reduce_totals_kernel<<<1, NT, 0, st>>>(L.totals, nq, L.tot2);
     RB_LAUNCH_CHECK("reduce_totals_kernel");
     long long h[2] = {0, 0};
     RB_CUDA(cudaMemcpyAsync(h, L.tot2, sizeof(h), cudaMemcpyDeviceToHost, st));
@@ -707,7 +781,8 @@ extern "C" size_t rb200_ivf_search_workspace_bytes(int64_t total_candidates) {
 }
 
 extern "C" int rb200_ivf_search_run(const float* q, int nq, int D, int nlist, int nprobe, const int64_t* offsets,
-                                    const int64_t* list_ids, const float* list_vecs, int64_t max_list_len, int k,
+                                    const int64_t* list_ids, const float* list_vecs, int64_t max_list_len,
+                                    const int32_t* tile_list, const int32_t* tile_idx, int n_tiles, int k,
                                     void* plan_ws, size_t plan_ws_bytes, int64_t total_candidates, int64_t max_candidates,
                                     float* out_scores, int64_t* out_ids, void* workspace, size_t workspace_bytes,
                                     void* stream) {
@@ -721,13 +796,14 @@ extern "C" int rb200_ivf_search_run(const float* q, int nq, int D, int nlist, in
     float* cand = ar.take<float>((size_t)(total_candidates > 0 ? total_candidates : 1));
     if (!workspace || !ar.ok()) return rb_set_error(RB200_ERR_WORKSPACE, "ivf_search_run: workspace too small");
     if (total_candidates > 0 && max_list_len > 0) {
-        const dim3 g((unsigned)((max_list_len + TT - 1) / TT), nlist);
-        RB_REQUIRE(nlist <= 65535, "ivf_search_run: nlist must be <= 65535");
+        dim3 g((unsigned)((max_list_len + TT - 1) / TT), nlist);
+        if (tile_list && tile_idx && n_tiles > 0) g = dim3((unsigned)n_tiles, 1);
+        else { tile_list = nullptr; tile_idx = nullptr; RB_REQUIRE(nlist <= 65535, "ivf_search_run: nlist must be <= 65535 without a tile table"); }
         RB_DISPATCH_D(D, RB_TILE_LAUNCH(list_scan_kernel, DD, g, st, q, list_vecs, offsets, L.pair_qp, L.list_qstart, nprobe,
-                                        L.cand_base, L.cand_off, cand));
+                                        L.cand_base, L.cand_off, cand, tile_list, tile_idx));
         RB_LAUNCH_CHECK("list_scan_kernel");
     }
-    ResolveIvf res{L.probes, L.cand_base, offsets, list_ids, nprobe};
+    ResolveIvf res{L.probes, L.cand_base, offsets, list_ids, nprobe, nullptr, nullptr};
     return launch_select<ResolveIvf>(cand, L.cand_off, 0, L.totals, 0, max_candidates, nq, k, res, out_scores, out_ids, st);
 }
 

@@ -122,7 +122,19 @@ class _IVFState:
         check(lib.rb200_ivf_build(ptr(x), n, self.d, ptr(a), self.nlist, ptr(self.offsets), ptr(self.list_ids),
                                   ptr(self.list_vecs), ptr(ws), wsb, stream_ptr()), "rb200_ivf_build")
         self.ntotal = n
-        self.max_list_len = int((self.offsets[1:] - self.offsets[:-1]).max().item())
+        self.finalize()
+
+    def finalize(self) -> None:
+        """Derived search-side tables (depend only on ``offsets``): longest list and the (list, 64-vector tile) work items
+        of the list scan."""
+        lens = self.offsets[1:] - self.offsets[:-1]
+        self.max_list_len = int(lens.max().item()) if lens.numel() else 0
+        n_tile = (lens + 63) // 64
+        first = torch.cumsum(n_tile, 0) - n_tile
+        lists = torch.arange(self.nlist, device=lens.device)
+        self.tile_list = torch.repeat_interleave(lists, n_tile).to(torch.int32).contiguous()
+        self.tile_idx = (torch.arange(int(n_tile.sum().item()), device=lens.device) -
+                         torch.repeat_interleave(first, n_tile)).to(torch.int32).contiguous()
 
     def search_device(self, q: torch.Tensor, k: int, id_table: Optional[torch.Tensor] = None
                       ) -> Tuple[torch.Tensor, torch.Tensor]:
@@ -143,7 +155,8 @@ class _IVFState:
         scores = torch.empty(nq, k, dtype=torch.float32, device=q.device)
         rows = torch.empty(nq, k, dtype=torch.int64, device=q.device)
         check(lib.rb200_ivf_search_run(ptr(q), nq, self.d, self.nlist, nprobe, ptr(self.offsets), ptr(ids_src),
-                                       ptr(self.list_vecs), self.max_list_len, k, ptr(plan), pb, total.value, mx.value,
+                                       ptr(self.list_vecs), self.max_list_len, ptr(self.tile_list), ptr(self.tile_idx),
+                                       self.tile_list.numel(), k, ptr(plan), pb, total.value, mx.value,
                                        ptr(scores), ptr(rows), ptr(ws), wb, stream_ptr()), "rb200_ivf_search_run")
         return scores, rows
 
@@ -274,7 +287,8 @@ class FAISSIndex:
             st.offsets = torch.as_tensor(z["offsets"], device=dev)
             st.list_ids = torch.as_tensor(z["list_ids"], device=dev)
             st.list_vecs = torch.as_tensor(z["list_vecs"], device=dev)
-            st.ntotal, st.max_list_len, st.is_trained = ntotal, mx, True
+            st.ntotal, st.is_trained = ntotal, True
+            st.finalize()
         obj.index = st
         obj.item_ids = meta["item_ids"]
         obj._item_id_to_faiss_idx = meta["item_id_to_faiss_idx"]
