@@ -564,7 +564,7 @@ __global__ void __launch_bounds__(NT) select_topk_kernel(const float* __restrict
         for (int stride = size >> 1; stride > 0; stride >>= 1) {
             __syncthreads();
             for (int t = tid; t < sort_n / 2; t += NT) {
-                const int lo_i = (t / stride) * (stride << 1) + (t % stride), hi_i = lo_i + stride;
+                const int lo_i = ((t & ~(stride - 1)) << 1) | (t & (stride - 1)), hi_i = lo_i + stride;   // stride is a power of two
                 const bool desc = ((lo_i & size) == 0);
                 const uint32_t ka = skey[lo_i], kb = skey[hi_i];
                 const int ia = sidx[lo_i], ib = sidx[hi_i];
