@@ -11,8 +11,9 @@ Prints ONE JSON line (rank 0).  Workloads (BASELINE.json ``configs``; SURVEY.md 
   ``value`` = samples/s with the batch already in HBM; ``e2e`` = the same step fed from pinned host memory with
   the loss read back every step.
 * secondary (``ivf`` object) — C3: IVFFlat nlist 4096 / nprobe 32 / top-500 over 1 M × 64, batches of 4096 queries.
-* N > 1 — C4: the same step on row-sharded tables (10 M users × 1 M items, D = 128), 8192 samples per rank
-  (weak scaling), NCCL all-to-all for ids / rows / row gradients.
+* N > 1 — the same C2 step weak-scaled: 8192 samples per rank, replicated tables, one NCCL all-reduce of the dense
+  gradients per step (``DataParallelBPRTrainer``); plus a ``c4`` object: row-sharded tables (10 M users × 1 M items,
+  D = 128) with NCCL all-to-all for ids / rows / row gradients (``bench_sharded.py``).
 
 ``--impl reference`` times the CPU arm (oracle/torch_step.py: the reference's own PyTorch calls) on the host cores.
 """
@@ -394,8 +395,9 @@ def main():
     if dom in flops:
         roof["achieved"] = flops[dom] / (stages[dom] * 1e-3) / 1e12
         roof["frac"] = roof["achieved"] / pk["bf16_tflops"]
-        roof["note"] = ("fp32 FFMA parity kernels (1e-5 parity mode) measured against the bf16 tensor peak; algorithmic flops = "
-                        "107 520 (fwd) / 215 040 (bwd) per sample x 8192")
+        roof["note"] = ("tcgen05 kind::tf32 kernels in 3xTF32 mode (fp32-grade, 3 MMAs issued per logical MMA) measured against the bf16 "
+                        "tensor peak; algorithmic flops = 107 520 (fwd) / 215 040 (bwd) per sample x 8192; the stage is bound by "
+                        "operand-staging latency at this batch size, not by the tensor pipe (DESIGN.md §7)")
     else:
         by = {"scatter": (3 * B * (4 * D + 8)) * 2.0, "adam": 24.0 * (N_USERS + N_ITEMS + 2) * D + 24.0 * 35456,
               "loss": 6.0 * B * D * 4, "clip": 4.0 * (3 * B * D + 35456)}[dom]
@@ -408,7 +410,8 @@ def main():
         "config": {"workload": "C2: two-tower BPR training step, batch 8192, ML-1M-shape tables 6041x64 / 3953x64, H=128, "
                                "sampled negatives + bpr_loss, dropout 0.1, clip_grad_norm_ 1.0, Adam wd 1e-5 (dense: every row "
                                "updated, reference-exact)",
-                   "l2": "flushed between timed steps (256 MiB write); per-step CUDA events", "api": "FusedBPRTrainer (CUDA graph)"},
+                   "l2": "flushed between timed steps (256 MiB write); per-step CUDA events", "api": "FusedBPRTrainer (CUDA graph)",
+                   "tower_mode": "tcgen05 3xTF32 (fp32-grade)"},
         "e2e": {"value": e2e, "unit": "samples/s", "h2d_bytes_per_step": r["h2d"], "d2h_bytes_per_step": 4,
                 "ms_per_step": r["e2e_s"] / K * 1e3,
                 "api": "FusedBPRTrainer.load_packed(pinned batch) + step() + loss.item(), wall clock"},

@@ -245,11 +245,20 @@ typedef struct rb200_step_params {
     void* workspace; size_t workspace_bytes;
     void* const* stage_events_host;   /* optional: 7 cudaEvent_t recorded at the stage boundaries
                                          start | towers fwd | loss | towers bwd | scatter | clip | adam */
+    float grad_scale;   /* scale of the loss gradient (0 ⇒ 1).  Data-parallel replicas pass 1/world.         */
+    float* dp_grads;    /* data-parallel mode (replicated tables): when set, rb200_bpr_step stops after the
+                           gradients and leaves them DENSE in this flat buffer
+                           [user MLP | item MLP | user table (n_user_rows·D) | item table (n_item_rows·D)]
+                           for the caller to all-reduce; rb200_bpr_apply then clips and runs Adam from it.  */
 } rb200_step_params;
 
 size_t rb200_bpr_step_workspace_bytes(int B, int D, int H, int extra_dim, int64_t n_user_rows,
                                       int64_t n_item_rows, int loss_kind);
 int rb200_bpr_step(const rb200_step_params* params_host, void* stream);
+/* second half of a data-parallel step: Σg² over dp_grads → clip coefficient → Adam on MLPs and tables (every row) */
+int rb200_bpr_apply(const rb200_step_params* params_host, void* stream);
+/* number of floats in dp_grads */
+size_t rb200_bpr_dp_grad_floats(int D, int H, int extra_dim, int64_t n_user_rows, int64_t n_item_rows);
 /* Debug/test access to the step's intermediate gradients inside the workspace (device pointers,
  * valid after rb200_bpr_step on the same workspace): flat MLP grads of both towers and the
  * compact unique-row gradients. */

@@ -62,7 +62,8 @@ class StepParams(C.Structure):
                 ("dropout_p", C.c_float), ("seed", C.c_uint64),
                 ("keep_mask_user", c_f), ("keep_mask_pos", c_f), ("keep_mask_neg", c_f),
                 ("padding_idx", C.c_int64), ("loss", c_f), ("err_flag", c_f),
-                ("workspace", c_f), ("workspace_bytes", C.c_size_t), ("stage_events_host", c_f)]
+                ("workspace", c_f), ("workspace_bytes", C.c_size_t), ("stage_events_host", c_f),
+                ("grad_scale", C.c_float), ("dp_grads", c_f)]
 
 
 class StepViews(C.Structure):
@@ -104,6 +105,8 @@ SIGNATURES = {
     "rb200_adam_rows": (I, [P, P, P, I, P, P, P, I, P, P]),
     "rb200_bpr_step_workspace_bytes": (SZ, [I, I, I, I, I64, I64, I]),
     "rb200_bpr_step": (I, [C.POINTER(StepParams), P]),
+    "rb200_bpr_apply": (I, [C.POINTER(StepParams), P]),
+    "rb200_bpr_dp_grad_floats": (SZ, [I, I, I, I64, I64]),
     "rb200_bpr_step_views": (I, [C.POINTER(StepParams), C.POINTER(StepViews)]),
     "rb200_gemm_nt": (I, [P, I, P, I, I, I, P, I64, P, P]),
     "rb200_normalize_rows": (I, [P, I64, I, F, P, P]),

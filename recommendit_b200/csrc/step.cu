@@ -150,6 +150,8 @@ extern "C" int rb200_bpr_step(const rb200_step_params* s, void* stream) {
     const int items = pair ? 2 : 1;
     const int Pu = w.P_user, Pi = w.P_item;
     const int Din_i = D + E;
+    if (s->dp_grads) { w.g_user_mlp = s->dp_grads; w.g_item_mlp = s->dp_grads + Pu; }
+    const float gscale = s->grad_scale > 0.f ? s->grad_scale : 1.f;
 
     int ev_i = 0;
 #define RB_STAGE_EVENT()                                                                   \
@@ -167,11 +169,15 @@ extern "C" int rb200_bpr_step(const rb200_step_params* s, void* stream) {
     const int sc_na[2] = {B, B}, sc_nb[2] = {0, pair ? B : 0};
     const float* sc_rw[2] = {w.drows_u, w.drows_pn};
     const long long sc_nr[2] = {s->n_user_rows, s->n_item_rows};
-    float* sc_dn[2] = {nullptr, nullptr};
+    const bool dp = s->dp_grads != nullptr;
+    float* dp_user_tab = dp ? s->dp_grads + (size_t)w.P_user + w.P_item : nullptr;
+    float* dp_item_tab = dp ? dp_user_tab + (size_t)s->n_user_rows * D : nullptr;
+    float* sc_dn[2] = {dp_user_tab, dp_item_tab};
     int64_t* sc_ui[2] = {w.uniq_u, w.uniq_i};
     float* sc_ug[2] = {w.ug_u, w.ug_i};
     int* sc_nu[2] = {w.n_uniq, w.n_uniq + 1};
-    int* sc_rs[2] = {dense ? s->user_row_slot : nullptr, dense ? s->item_row_slot : nullptr};
+    int* sc_rs[2] = {(dense && !dp) ? s->user_row_slot : nullptr, (dense && !dp) ? s->item_row_slot : nullptr};
+    if (dp) RB_CUDA(cudaMemsetAsync(dp_user_tab, 0, sizeof(float) * (size_t)(s->n_user_rows + s->n_item_rows) * D, st));
     const bool fast_scatter = items * B <= 16384 && s->n_user_rows < (1ll << 31) && s->n_item_rows < (1ll << 31);
     SideStream* side = nullptr;
     if (fast_scatter) {
@@ -216,8 +222,8 @@ extern "C" int rb200_bpr_step(const rb200_step_params* s, void* stream) {
 
     RB_STAGE_EVENT();
     // ---- loss + gradient w.r.t. the tower outputs ------------------------------------------- //
-    if (pair) rc = rb200_bpr_pair(w.u, w.p, w.n, B, D, s->loss, w.du, w.dpn, w.dpn + (size_t)B * D, 1.f, w.ws_loss, w.b_loss, st);
-    else rc = rb200_bpr_inbatch(w.u, w.p, B, D, s->inbatch_mode, s->loss, w.du, w.dpn, 1.f, w.ws_loss, w.b_loss, st);
+    if (pair) rc = rb200_bpr_pair(w.u, w.p, w.n, B, D, s->loss, w.du, w.dpn, w.dpn + (size_t)B * D, gscale, w.ws_loss, w.b_loss, st);
+    else rc = rb200_bpr_inbatch(w.u, w.p, B, D, s->inbatch_mode, s->loss, w.du, w.dpn, gscale, w.ws_loss, w.b_loss, st);
     if (rc) return rc;
     copy_loss_kernel<<<1, 32, 0, st>>>(s->loss, s->opt);
     RB_LAUNCH_CHECK("copy_loss_kernel");
@@ -257,6 +263,8 @@ extern "C" int rb200_bpr_step(const rb200_step_params* s, void* stream) {
                                      w.ug_i, w.n_uniq + 1, sc_rs[1], w.ws_scatter, w.b_scatter, st))) return rc;
     }
 
+    if (dp) return RB200_OK;      // gradients are complete and dense in dp_grads: the caller all-reduces, then rb200_bpr_apply
+
     RB_STAGE_EVENT();
     // ---- clip_grad_norm_(all parameters, 1.0) ---------------------------------------------------- //
     rb200_sumsq_seg segs[3] = {
@@ -283,5 +291,32 @@ extern "C" int rb200_bpr_step(const rb200_step_params* s, void* stream) {
     }
     RB_STAGE_EVENT();
 #undef RB_STAGE_EVENT
+    return RB200_OK;
+}
+
+
+extern "C" size_t rb200_bpr_dp_grad_floats(int D, int H, int extra_dim, int64_t n_user_rows, int64_t n_item_rows) {
+    const size_t Pu = (size_t)H * D + H + (size_t)D * H + D, Pi = (size_t)H * (D + extra_dim) + H + (size_t)D * H + D;
+    return Pu + Pi + (size_t)(n_user_rows + n_item_rows) * D;
+}
+
+extern "C" int rb200_bpr_apply(const rb200_step_params* s, void* stream) {
+    int rc = check(s);
+    if (rc) return rc;
+    RB_REQUIRE(s->dp_grads, "bpr_apply: dp_grads is NULL");
+    cudaStream_t st = (cudaStream_t)stream;
+    RbArena ar(s->workspace, s->workspace_bytes);
+    StepWs w;
+    if (!carve(ar, *s, w)) return rb_set_error(RB200_ERR_WORKSPACE, "bpr_apply: workspace too small");
+    const int D = s->D;
+    const size_t Pu = w.P_user, Pi = w.P_item;
+    const size_t nu = (size_t)s->n_user_rows * D, ni = (size_t)s->n_item_rows * D;
+    float* g = s->dp_grads;
+    rb200_sumsq_seg seg[1] = {{g, (int64_t)(Pu + Pi + nu + ni), nullptr, 0}};
+    if ((rc = rb_sumsq_accumulate(s->opt, seg, 1, 1, w.ws_sumsq, w.b_sumsq, st))) return rc;
+    if ((rc = rb_adam_dense2(s->user_mlp, g, s->user_mlp_m, s->user_mlp_v, (long long)Pu, s->item_mlp, g + Pu, s->item_mlp_m,
+                             s->item_mlp_v, (long long)Pi, s->opt, st))) return rc;
+    if ((rc = rb_adam_dense2(s->user_table, g + Pu + Pi, s->user_table_m, s->user_table_v, (long long)nu, s->item_table,
+                             g + Pu + Pi + nu, s->item_table_m, s->item_table_v, (long long)ni, s->opt, st))) return rc;
     return RB200_OK;
 }

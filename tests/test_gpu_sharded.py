@@ -58,6 +58,25 @@ x = torch.nn.functional.normalize(torch.randn(20000, 64, generator=g), dim=-1)
 q = torch.nn.functional.normalize(torch.randn(9, 64, generator=g), dim=-1)
 n_loc = 20000 // world
 s, i = sharded_flat_search(q.to(dev), x[rank * n_loc:(rank + 1) * n_loc].contiguous().to(dev), 100, rank * n_loc)
+# data-parallel replicas (small tables): must equal the single-process step on the concatenated batch
+import recommendit_b200 as R
+P2 = O.init_params(400, 300, 64, 128, seed=9)
+m = R.TwoTowerModel(400, 300, 64, 128, dropout=0.0)
+m.load_state_dict({k: torch.from_numpy(v) for k, v in P2.items()}); m.to(dev).train()
+dp = R.DataParallelBPRTrainer(m, lr=1e-2, use_cuda_graph=True)
+def batch2(r, s):
+    rng = np.random.default_rng(77 * s + r)
+    return (rng.integers(0, 401, 256), rng.integers(0, 301, 256), (rng.random((256, 18)) < .2).astype(np.float32),
+            rng.integers(0, 301, 256), (rng.random((256, 18)) < .2).astype(np.float32))
+dp_losses = [float(dp.step_host(*batch2(rank, s))) for s in range(3)]
+dp_state = {k: v.detach().cpu().numpy() for k, v in m.state_dict().items()}
+if rank == 0:
+    S2 = O.AdamState(); dp_ref = []
+    for st in range(3):
+        parts = [batch2(r, st) for r in range(world)]
+        gb = tuple(np.concatenate([p[k] for p in parts]) for k in range(5))
+        dp_ref.append(float(O.train_step(P2, S2, gb, lr=1e-2)[0]))
+    dp_err = max(float(np.abs(dp_state[k] - P2[k]).max()) for k in O.PARAM_KEYS)
 if rank == 0:
     S = O.AdamState(); ref = []
     for st in range(2):
@@ -68,7 +87,8 @@ if rank == 0:
     from oracle import ivf_oracle as V
     s_ref, i_ref = V.flat_search(q.numpy(), x.numpy(), 100)
     V.assert_topk_equivalent(s.cpu().numpy(), i.cpu().numpy(), s_ref, i_ref)
-    print("RESULT " + json.dumps({"losses": losses, "ref": ref, "max_param_err": err}))
+    print("RESULT " + json.dumps({"losses": losses, "ref": ref, "max_param_err": err, "dp_losses": dp_losses, "dp_ref": dp_ref,
+                                  "dp_err": dp_err}))
 dist.barrier(); dist.destroy_process_group()
 '''
 
@@ -87,3 +107,5 @@ def test_sharded_world2_nccl_matches_single_process_oracle(tmp_path):
     r = json.loads(line[7:])
     assert np.allclose(r["losses"], r["ref"], atol=2e-5), r
     assert r["max_param_err"] <= 0.5 * 1e-2, r
+    assert np.allclose(r["dp_losses"], r["dp_ref"], atol=2e-5), r
+    assert r["dp_err"] <= 0.5 * 1e-2, r

@@ -201,3 +201,18 @@ def test_full_size_step_properties():
     st = tr.opt_state
     assert st.step == 4 and 0 < st.clip_coef <= 1.0
     tr.check_ids()
+
+
+def test_data_parallel_world1_equals_fused_step(golden):
+    """DataParallelBPRTrainer with a single replica is the fused step computed through dense gradients: bit-identical."""
+    import recommendit_b200 as R
+    g = golden("tt_dup")
+    out = []
+    for cls in (R.FusedBPRTrainer, R.DataParallelBPRTrainer):
+        model = model_from_golden(g).train()
+        tr = cls(model, lr=float(g["lr"]), use_cuda_graph=True, seed=3)
+        losses = [tr.step_host(*batch_from_golden(g, s % 2)) for s in range(5)]
+        out.append((losses, {k: v.detach().clone() for k, v in model.state_dict().items()}))
+    assert out[0][0] == out[1][0]
+    for k in out[0][1]:
+        assert torch.equal(out[0][1][k], out[1][1][k]), k
