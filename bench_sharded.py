@@ -31,6 +31,25 @@ def _timed(step_fn, K, dev):
 
 
 def main_sharded(args):
+    # NCCL may print its version banner on stdout; the contract is ONE JSON line there, so everything before the final
+    # print goes to stderr (file-descriptor level, native libraries included).
+    import sys
+    sys.stdout.flush()
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
+    try:
+        line = _run(args)
+    finally:
+        sys.stdout.flush()
+        os.dup2(saved_stdout, 1)
+        os.close(saved_stdout)
+    if line is not None:
+        print(json.dumps(line), flush=True)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def _run(args):
     rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", str(rank)))
     torch.cuda.set_device(local)
@@ -122,6 +141,5 @@ def main_sharded(args):
                                              "host-orchestrated (Python between C-ABI calls)"}},
             "clocks": clocks, "final_loss": float(loss),
         }
-        print(json.dumps(line), flush=True)
-    dist.barrier()
-    dist.destroy_process_group()
+        return line
+    return None
