@@ -339,6 +339,71 @@ def bench_ivf(args, dev):
     return out
 
 
+def bench_hbm_kernels(dev):
+    """The HBM-bound kernels of the path at a size where HBM (not L2) is the limit — BASELINE config C4 widths (D = 128):
+    row gather, sorted-segment scatter-add, Adam on touched rows, dense Adam.  Algorithmic bytes per SURVEY.md §8(d)."""
+    from recommendit_b200 import _lib
+    lib = _lib.load()
+    pk = peaks()
+    D4, rows, n_req = 128, 4_000_000, 2_000_000
+    f32 = dict(dtype=torch.float32, device=dev)
+    table = torch.randn(rows, D4, **f32)
+    m, v = torch.zeros_like(table), torch.zeros_like(table)
+    g = torch.Generator(device=dev).manual_seed(3)
+    ids = torch.randint(0, rows, (n_req,), device=dev, generator=g)
+    out = torch.empty(n_req, D4, **f32)
+    opt = torch.zeros(128, dtype=torch.uint8, device=dev)
+    st = _lib.OptState()
+    st.lr, st.beta1, st.beta2, st.eps, st.weight_decay, st.max_norm = 1e-3, 0.9, 0.999, 1e-8, 1e-5, 1.0
+    st.one_minus_beta1, st.one_minus_beta2, st.beta2_f, st.clip_coef = 0.1, 0.001, 0.999, 1.0
+    opt.copy_(torch.frombuffer(bytearray(bytes(st)), dtype=torch.uint8))
+    _lib.check(lib.rb200_opt_begin_step(opt.data_ptr(), _lib.stream_ptr()))
+    uniq = torch.unique(ids)
+    nu = torch.tensor([uniq.numel()], dtype=torch.int32, device=dev)
+    ug = torch.randn(uniq.numel(), D4, **f32) * 1e-3
+    slot = torch.full((rows,), -1, dtype=torch.int32, device=dev)
+    sp = _lib.stream_ptr
+
+    def timeit(fn, reps=5):
+        fn(); torch.cuda.synchronize(dev)
+        ts = []
+        for _ in range(reps):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(); fn(); b.record(); torch.cuda.synchronize(dev)
+            ts.append(a.elapsed_time(b))
+        return float(np.median(ts))
+
+    res = {}
+
+    def add(name, ms, nbytes, note):
+        gbs = nbytes / (ms * 1e-3) / 1e9
+        res[name] = {"ms": ms, "algorithmic_bytes": int(nbytes), "achieved": gbs, "unit": "GB/s", "peak": pk["hbm_gbs"],
+                     "frac": gbs / pk["hbm_gbs"], "note": note}
+
+    ms = timeit(lambda: _lib.check(lib.rb200_gather_rows(table.data_ptr(), ids.data_ptr(), n_req, D4, rows, out.data_ptr(), sp())))
+    add("gather_rows", ms, n_req * (2 * 4 * D4 + 8), f"{n_req} random rows of a {rows}x{D4} fp32 table (2 GB): 4·D read + 4·D written + 8 B id per row")
+    ms = timeit(lambda: _lib.check(lib.rb200_adam_rows(table.data_ptr(), m.data_ptr(), v.data_ptr(), D4, uniq.data_ptr(), ug.data_ptr(),
+                                                       nu.data_ptr(), uniq.numel(), opt.data_ptr(), sp())))
+    add("adam_rows", ms, uniq.numel() * (28 * D4 + 8), f"Adam on {uniq.numel()} touched rows: w,m,v read+written (24·D) + gradient row (4·D) + id")
+    ms = timeit(lambda: _lib.check(lib.rb200_adam_table_dense(table.data_ptr(), m.data_ptr(), v.data_ptr(), rows, D4, slot.data_ptr(), ug.data_ptr(),
+                                                              opt.data_ptr(), sp())))
+    add("adam_table_dense", ms, rows * (24 * D4 + 4), f"dense (reference-exact) Adam over the whole {rows}x{D4} table: 24 B per element + 4 B slot per row")
+    big_b = 1 << 20
+    ids2 = torch.randint(0, rows, (big_b,), device=dev, generator=g)
+    grads = torch.randn(big_b, D4, **f32)
+    wsb = lib.rb200_scatter_workspace_bytes(big_b, rows)
+    ws = _lib.workspace(wsb, dev)
+    uq = torch.empty(big_b, dtype=torch.int64, device=dev)
+    ugr = torch.empty(big_b, D4, **f32)
+    nuq = torch.zeros(1, dtype=torch.int32, device=dev)
+    ms = timeit(lambda: _lib.check(lib.rb200_scatter_rows(ids2.data_ptr(), grads.data_ptr(), big_b, D4, rows, 0, None, uq.data_ptr(), ugr.data_ptr(),
+                                                          nuq.data_ptr(), None, ws.data_ptr(), wsb, sp())))
+    n_u = int(nuq.item())
+    add("scatter_rows", ms, big_b * (4 * D4 + 8) + n_u * (4 * D4 + 8),
+        f"deterministic sorted-segment sum of {big_b} gradient rows into {n_u} unique rows (radix sort of (id, sample) pairs included)")
+    return res
+
+
 def bench_ivf_cpu(nq_sample: int = 256):
     """CPU arm of C3 on a bounded sample of queries: oracle/ivf_oracle.c (heap-based, OpenMP over queries)."""
     from oracle import ivf_oracle as V
@@ -367,6 +432,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--skip-ivf", action="store_true")
     ap.add_argument("--skip-cpu", action="store_true")
+    ap.add_argument("--skip-hbm", action="store_true")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
@@ -423,6 +489,8 @@ def main():
     }
     if not args.skip_ivf:
         line["ivf"] = bench_ivf(args, dev)
+    if not args.skip_hbm:
+        line["hbm_kernels"] = bench_hbm_kernels(dev)
     if not args.skip_cpu:
         cores = os.cpu_count() or 1
         v, ms = cpu_step_throughput(20, 3, cores)

@@ -178,31 +178,59 @@ __global__ void __launch_bounds__(BS_THREADS, 1) block_sort_segments_kernel(cons
 struct SegJob {
     const int* pos; const int* seg_start; const int64_t* uniq_ids; const int* n_uniq;
     const float* rows; float* uniq_grads; float* dense; int cap;   // cap = upper bound of n_uniq (launch sizing)
+    const int* first_pos;                                          // optional: pos[seg_start[s]] per segment (shorter load chain)
 };
 struct SegParams { SegJob job[2]; int n_jobs; int D4; };
 
-// one warp per unique id: rows added in ascending sample order (deterministic)
+// one warp per SEG_PER_WARP consecutive unique ids; the first row of each segment is fetched for all of them at once
+// (most segments of a large batch have length 1, so this keeps SEG_PER_WARP independent 16·D4-byte row reads in
+// flight per warp instead of one at the end of a seg_start → pos → row dependency chain).  Rows are added in ascending
+// sample order (deterministic).
+constexpr int SEG_PER_WARP = 8;
+__host__ __device__ inline int seg_warps(int cap) { return (cap + SEG_PER_WARP - 1) / SEG_PER_WARP; }
+
 __global__ void __launch_bounds__(NT) segment_sum2_kernel(const SegParams p) {
     int w = (blockIdx.x * NT + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     int j = 0;
-    if (p.n_jobs > 1 && w >= p.job[0].cap) { w -= p.job[0].cap; j = 1; }
+    if (p.n_jobs > 1 && w >= seg_warps(p.job[0].cap)) { w -= seg_warps(p.job[0].cap); j = 1; }
     const SegJob& J = p.job[j];
-    if (w >= J.n_uniq[0]) return;
-    const int beg = J.seg_start[w], end = J.seg_start[w + 1];
+    const int n = J.n_uniq[0];
+    const int w0 = w * SEG_PER_WARP;
+    if (w0 >= n) return;
+    const int mine = (lane <= SEG_PER_WARP && w0 + lane <= n) ? J.seg_start[w0 + lane] : 0;
+    const int first = (lane < SEG_PER_WARP && w0 + lane < n) ? (J.first_pos ? J.first_pos[w0 + lane] : J.pos[mine]) : 0;
+    long long dst = (J.dense && lane < SEG_PER_WARP && w0 + lane < n) ? (long long)J.uniq_ids[w0 + lane] : 0;
+    int beg[SEG_PER_WARP], end[SEG_PER_WARP], p0[SEG_PER_WARP];
+    long long drow[SEG_PER_WARP];
+#pragma unroll
+    for (int i = 0; i < SEG_PER_WARP; ++i) {
+        beg[i] = __shfl_sync(0xffffffffu, mine, i);
+        end[i] = __shfl_sync(0xffffffffu, mine, i + 1);
+        p0[i] = __shfl_sync(0xffffffffu, first, i);
+        drow[i] = __shfl_sync(0xffffffffu, dst, i);
+    }
     const int D4 = p.D4;
+    const float4* __restrict__ rows = reinterpret_cast<const float4*>(J.rows);
     for (int c = lane; c < D4; c += 32) {
-        float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
-        for (int k = beg; k < end; ++k) {
-            const float4 v = __ldg(reinterpret_cast<const float4*>(J.rows) + (long long)J.pos[k] * D4 + c);
-            s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
-        }
-        if (J.uniq_grads) reinterpret_cast<float4*>(J.uniq_grads)[(long long)w * D4 + c] = s;
-        if (J.dense) {
-            float4* dp = reinterpret_cast<float4*>(J.dense) + J.uniq_ids[w] * D4 + c;
-            float4 o = *dp;
-            o.x += s.x; o.y += s.y; o.z += s.z; o.w += s.w;
-            *dp = o;
+        float4 s[SEG_PER_WARP];
+#pragma unroll
+        for (int i = 0; i < SEG_PER_WARP; ++i)
+            s[i] = (w0 + i < n) ? __ldg(rows + (long long)p0[i] * D4 + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int i = 0; i < SEG_PER_WARP; ++i) {
+            if (w0 + i >= n) break;
+            for (int k = beg[i] + 1; k < end[i]; ++k) {
+                const float4 v = __ldg(rows + (long long)J.pos[k] * D4 + c);
+                s[i].x += v.x; s[i].y += v.y; s[i].z += v.z; s[i].w += v.w;
+            }
+            if (J.uniq_grads) __stcs(reinterpret_cast<float4*>(J.uniq_grads) + (long long)(w0 + i) * D4 + c, s[i]);
+            if (J.dense) {
+                float4* dp = reinterpret_cast<float4*>(J.dense) + drow[i] * D4 + c;
+                float4 o = *dp;
+                o.x += s[i].x; o.y += s[i].y; o.z += s[i].z; o.w += s[i].w;
+                *dp = o;
+            }
         }
     }
 }
@@ -226,6 +254,50 @@ int launch_block_sort(const SortParams& sp, int n_jobs, cudaStream_t st) {
     block_sort_segments_kernel<ITEMS><<<n_jobs, BS_THREADS, smem, st>>>(sp);
     RB_LAUNCH_CHECK("block_sort_segments_kernel");
     return RB200_OK;
+}
+
+// ---- large batches (> 16384 sample-rows): device-wide radix sort on 32-bit keys, then the same segment-sum kernel ---- //
+__global__ void prep_keys32_kernel(const int64_t* __restrict__ ids, int n, long long n_rows, long long padding_idx,
+                                   unsigned* __restrict__ keys, int* __restrict__ pos) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const long long id = ids[i];
+    keys[i] = (id != padding_idx && (unsigned long long)id < (unsigned long long)n_rows) ? (unsigned)id : KEY_SENTINEL;
+    pos[i] = i;
+}
+// head flag of sorted position i (1 where a new id starts; sentinels and i == n are 0), computed on the fly for the scan
+struct HeadFlag32 {
+    const unsigned* keys; int n;
+    __host__ __device__ int operator()(int i) const {
+        if (i >= n) return 0;
+        const unsigned k = keys[i];
+        return (k != KEY_SENTINEL && (i == 0 || keys[i - 1] != k)) ? 1 : 0;
+    }
+};
+using HeadFlagIter = cub::TransformInputIterator<int, HeadFlag32, cub::CountingInputIterator<int>>;
+// slots = exclusive scan of the head flags (n + 1 entries): position i is a head iff slots[i + 1] != slots[i]
+__global__ void emit_heads32_kernel(const unsigned* __restrict__ keys, const int* __restrict__ pos, const int* __restrict__ slots, int n,
+                                    int* __restrict__ seg_start, int* __restrict__ first_pos, int64_t* __restrict__ uniq_ids, int* __restrict__ n_uniq,
+                                    int* __restrict__ row_slot) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const unsigned k = keys[i];
+    const int slot = slots[i];
+    if (i == 0) n_uniq[0] = slots[n];
+    if (k == KEY_SENTINEL) { if (i == 0) seg_start[0] = 0; return; }                // nothing valid at all
+    if (i == n - 1 || keys[i + 1] == KEY_SENTINEL) seg_start[slots[i + 1]] = i + 1;   // end of the last segment (sentinels sort last)
+    if (slots[i + 1] == slot) return;
+    seg_start[slot] = i;
+    first_pos[slot] = pos[i];
+    uniq_ids[slot] = (int64_t)k;
+    if (row_slot) row_slot[k] = slot;
+}
+size_t sort32_temp_bytes(int B, int bits) {
+    size_t t = 0, t2 = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, t, (const unsigned*)nullptr, (unsigned*)nullptr, (const int*)nullptr, (int*)nullptr, B, 0, bits);
+    HeadFlagIter it(cub::CountingInputIterator<int>(0), HeadFlag32{nullptr, B});
+    cub::DeviceScan::ExclusiveSum(nullptr, t2, it, (int*)nullptr, B + 1);
+    return t > t2 ? t : t2;
 }
 
 int key_bits(long long n_rows) {
@@ -476,7 +548,7 @@ static int scatter_plan(ScatterPlan& pl, int n_tables, const int64_t* const ids_
         J.uniq_ids = uniq_ids[t]; J.n_uniq = n_uniq[t]; J.row_slot = row_slot[t];
         SegJob& G = pl.gp.job[t];
         G.pos = J.pos; G.seg_start = J.seg_start; G.uniq_ids = J.uniq_ids; G.n_uniq = J.n_uniq;
-        G.rows = rows[t]; G.uniq_grads = uniq_grads[t]; G.dense = dense[t]; G.cap = n;
+        G.rows = rows[t]; G.uniq_grads = uniq_grads[t]; G.dense = dense[t]; G.cap = n; G.first_pos = nullptr;
     }
     if (!workspace || !ar.ok()) return rb_set_error(RB200_ERR_WORKSPACE, "scatter: workspace too small (%zu given)", workspace_bytes);
     return RB200_OK;
@@ -491,7 +563,7 @@ static int scatter_sort(const ScatterPlan& pl, cudaStream_t st) {
 
 static int scatter_sum(const ScatterPlan& pl, cudaStream_t st) {
     long long warps = 0;
-    for (int t = 0; t < pl.gp.n_jobs; ++t) warps += pl.gp.job[t].cap;
+    for (int t = 0; t < pl.gp.n_jobs; ++t) warps += seg_warps(pl.gp.job[t].cap);
     segment_sum2_kernel<<<(unsigned)((warps * 32 + NT - 1) / NT), NT, 0, st>>>(pl.gp);
     RB_LAUNCH_CHECK("segment_sum2_kernel");
     return RB200_OK;
@@ -516,8 +588,8 @@ extern "C" size_t rb200_scatter_workspace_bytes(int B, int64_t n_rows) {
     if (B < 1) B = 1;
     // (fast path additionally needs an int64 scratch for unique ids and an int for the count when the caller
     //  asks only for the dense output)
-    return 256 * 8 + sizeof(int64_t) * (size_t)2 * B + sizeof(int) * ((size_t)3 * B + 2 * ((size_t)B + 1) + 2) +
-           fast_scratch_bytes(B) + sort_temp_bytes(B, key_bits(n_rows));
+    return 256 * 16 + sizeof(int64_t) * (size_t)2 * B + sizeof(int) * ((size_t)8 * B + 3 * ((size_t)B + 1) + 4) +
+           fast_scratch_bytes(B) + sort_temp_bytes(B, key_bits(n_rows)) + sort32_temp_bytes(B, 32);
 }
 
 extern "C" int rb200_scatter_rows(const int64_t* ids, const float* rows, int B, int D, int64_t n_rows, int64_t padding_idx,
@@ -544,6 +616,35 @@ extern "C" int rb200_scatter_rows(const int64_t* ids, const float* rows, int B, 
         float* dn[2] = {dense_grad, nullptr}; int64_t* ui[2] = {u_ids, nullptr}; float* ug[2] = {uniq_grads, nullptr};
         int* nu[2] = {n_u, nullptr}; int* rs[2] = {row_slot, nullptr};
         return rb_scatter_tables(0, 1, ia, ib, na, nb, rw, D, nr, padding_idx, dn, ui, ug, nu, rs, rest, fast_scratch_bytes(B), st);
+    }
+    if (n_rows < (1ll << 31)) {
+        const int bits32 = key_bits_strict(n_rows);
+        RbArena a2(workspace, workspace_bytes);
+        int64_t* u_ids = uniq_ids ? uniq_ids : a2.take<int64_t>(B);
+        int* n_u = n_uniq ? n_uniq : a2.take<int>(1);
+        unsigned* k_in = a2.take<unsigned>(B); unsigned* k_out = a2.take<unsigned>(B);
+        int* p_in = a2.take<int>(B); int* p_out = a2.take<int>(B);
+        int* slots = a2.take<int>((size_t)B + 1);
+        int* seg_start = a2.take<int>((size_t)B + 1);
+        int* first_pos = a2.take<int>(B);
+        const size_t tbytes = sort32_temp_bytes(B, bits32);
+        char* temp = a2.take<char>(tbytes);
+        if (!workspace || !a2.ok()) return rb_set_error(RB200_ERR_WORKSPACE, "scatter_rows: workspace too small (%zu given)", workspace_bytes);
+        prep_keys32_kernel<<<(B + NT - 1) / NT, NT, 0, st>>>(ids, B, n_rows, padding_idx, k_in, p_in);
+        RB_LAUNCH_CHECK("prep_keys32_kernel");
+        size_t tb = tbytes;
+        RB_CUDA(cub::DeviceRadixSort::SortPairs(temp, tb, (const unsigned*)k_in, k_out, (const int*)p_in, p_out, B, 0, bits32, st));
+        tb = tbytes;
+        HeadFlagIter heads(cub::CountingInputIterator<int>(0), HeadFlag32{k_out, B});
+        RB_CUDA(cub::DeviceScan::ExclusiveSum(temp, tb, heads, slots, B + 1, st));
+        emit_heads32_kernel<<<(B + NT - 1) / NT, NT, 0, st>>>(k_out, p_out, slots, B, seg_start, first_pos, u_ids, n_u, row_slot);
+        RB_LAUNCH_CHECK("emit_heads32_kernel");
+        SegParams gp{};
+        gp.n_jobs = 1; gp.D4 = D / 4;
+        gp.job[0] = SegJob{p_out, seg_start, u_ids, n_u, rows, uniq_grads, dense_grad, B, first_pos};
+        segment_sum2_kernel<<<(unsigned)(((long long)seg_warps(B) * 32 + NT - 1) / NT), NT, 0, st>>>(gp);
+        RB_LAUNCH_CHECK("segment_sum2_kernel");
+        return RB200_OK;
     }
     const int bits = key_bits(n_rows);
     RbArena ar(workspace, workspace_bytes);

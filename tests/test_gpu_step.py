@@ -216,3 +216,41 @@ def test_data_parallel_world1_equals_fused_step(golden):
     assert out[0][0] == out[1][0]
     for k in out[0][1]:
         assert torch.equal(out[0][1][k], out[1][1][k]), k
+
+
+@pytest.mark.parametrize("B,n_rows,D", [(16385, 5000, 64), (100000, 300, 32), (70000, 2_000_000, 128)])
+def test_scatter_rows_large_batches_vs_oracle(B, n_rows, D):
+    """Device-wide sort path (> 16384 sample-rows): compact and dense outputs against the oracle, padding id skipped."""
+    import ctypes as C
+    from recommendit_b200 import _lib
+    lib = _lib.load()
+    rng = np.random.default_rng(B)
+    ids = rng.integers(0, n_rows, B)
+    ids[::97] = 0                                                          # padding rows
+    rows = rng.standard_normal((B, D)).astype(np.float32)
+    d_ids, d_rows = dev(ids), dev(rows)
+    uq = torch.empty(B, dtype=torch.int64, device="cuda"); ug = torch.empty(B, D, device="cuda")
+    nu = torch.zeros(1, dtype=torch.int32, device="cuda")
+    dense = torch.zeros(n_rows, D, device="cuda") if n_rows <= 5000 else None
+    slot = torch.full((n_rows,), -1, dtype=torch.int32, device="cuda")
+    wsb = lib.rb200_scatter_workspace_bytes(B, n_rows)
+    ws = _lib.workspace(wsb, "cuda")
+    for _ in range(2):                                                     # twice: deterministic
+        if dense is not None:
+            dense.zero_()
+        _lib.check(lib.rb200_scatter_rows(d_ids.data_ptr(), d_rows.data_ptr(), B, D, n_rows, 0, _lib.ptr(dense), uq.data_ptr(), ug.data_ptr(),
+                                          nu.data_ptr(), slot.data_ptr(), ws.data_ptr(), wsb, _lib.stream_ptr()))
+        n = int(nu.item())
+        got_ids, got = uq[:n].cpu().numpy(), ug[:n].cpu().numpy()
+        if _ == 0:
+            first = got.copy()
+        else:
+            assert np.array_equal(first, got)
+    exp_ids = np.unique(ids[ids != 0])
+    assert np.array_equal(got_ids, exp_ids)
+    ref = np.zeros((n_rows, D), np.float64)
+    np.add.at(ref, ids[ids != 0], rows[ids != 0].astype(np.float64))
+    assert rel_l2(got, ref[exp_ids]) <= 1e-6
+    assert np.array_equal(slot.cpu().numpy()[exp_ids], np.arange(n))
+    if dense is not None:
+        assert rel_l2(dense.cpu().numpy(), ref) <= 1e-6 and torch.count_nonzero(dense[0]) == 0
