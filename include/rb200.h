@@ -182,7 +182,8 @@ typedef struct rb200_opt_state {   /* device-resident, 128 bytes; host fills the
     float clip_coef;                /* min(1, max_norm/(norm+1e-6))   (rb200_grad_norm_clip)        */
     float total_norm;
     float loss;                     /* last loss, convenience                                       */
-    float pad[11];
+    unsigned ticket;        /* internal: last-block election of the grad-norm reduction (always 0 between launches) */
+    float pad[10];
 } rb200_opt_state;
 
 /* step += 1, recompute bias corrections, sumsq = 0 */

@@ -42,7 +42,7 @@ class OptState(C.Structure):   # host mirror of rb200_opt_state (128 bytes)
                 ("step", C.c_int64), ("eps", C.c_float), ("weight_decay", C.c_float), ("max_norm", C.c_float),
                 ("one_minus_beta1", C.c_float), ("one_minus_beta2", C.c_float), ("beta2_f", C.c_float),
                 ("step_size", C.c_float), ("bias_corr2_sqrt", C.c_float), ("clip_coef", C.c_float),
-                ("total_norm", C.c_float), ("loss", C.c_float), ("pad", C.c_float * 11)]
+                ("total_norm", C.c_float), ("loss", C.c_float), ("ticket", C.c_uint32), ("pad", C.c_float * 10)]
 
 
 assert C.sizeof(OptState) == 128

@@ -30,11 +30,15 @@ __device__ __forceinline__ double block_sum(double v, double* scratch /*[NT/32]*
 }
 
 // one warp: lane-strided sums + fixed shuffle tree (deterministic)
-__global__ void finalize_sum_kernel(const double* __restrict__ partials, int n, double scale, float* __restrict__ out) {
+__global__ void finalize_sum_kernel(const double* __restrict__ partials, int n, double scale, float* __restrict__ out,
+                                    rb200_opt_state* __restrict__ opt) {
     double t = 0.0;
     for (int i = threadIdx.x; i < n; i += 32) t += partials[i];
     t = rb_warp_sum_d(t);
-    if (threadIdx.x == 0) out[0] = (float)(t * scale);
+    if (threadIdx.x == 0) {
+        out[0] = (float)(t * scale);
+        if (opt) opt->loss = out[0];
+    }
 }
 
 // ---------------------------------------------------------------------------------------- //
@@ -301,12 +305,25 @@ extern "C" size_t rb200_bpr_pair_workspace_bytes(int B) {
     return 256 + sizeof(double) * (size_t)(rb_sm_count() * 2);
 }
 
+// The gradient kernel runs on `st`; the loss reduction (block partials → loss, optionally also opt->loss) runs on
+// `st_fin` after `fork` (both may be NULL/equal to st: plain sequential).  csrc/step.cu passes its side stream so the
+// reduction leaves the critical path of the training step.
+int rb_bpr_pair(const float* u, const float* p, const float* n, int B, int D, float* loss, float* du, float* dp, float* dn,
+                float grad_scale, void* workspace, size_t workspace_bytes, rb200_opt_state* opt, cudaStream_t st,
+                cudaStream_t st_fin, cudaEvent_t fork);
+
 extern "C" int rb200_bpr_pair(const float* u, const float* p, const float* n, int B, int D, float* loss, float* du,
                               float* dp, float* dn, float grad_scale, void* workspace, size_t workspace_bytes,
                               void* stream) {
+    return rb_bpr_pair(u, p, n, B, D, loss, du, dp, dn, grad_scale, workspace, workspace_bytes, nullptr, (cudaStream_t)stream,
+                       (cudaStream_t)stream, nullptr);
+}
+
+int rb_bpr_pair(const float* u, const float* p, const float* n, int B, int D, float* loss, float* du, float* dp, float* dn,
+                float grad_scale, void* workspace, size_t workspace_bytes, rb200_opt_state* opt, cudaStream_t st,
+                cudaStream_t st_fin, cudaEvent_t fork) {
     RB_REQUIRE(u && p && n && loss && B >= 1 && D >= 1, "bpr_pair: bad arguments");
     RB_REQUIRE((du == nullptr) == (dp == nullptr) && (du == nullptr) == (dn == nullptr), "bpr_pair: du/dp/dn must be all set or all NULL");
-    cudaStream_t st = (cudaStream_t)stream;
     int grid = (B + NT / 32 - 1) / (NT / 32);
     const int cap = rb_sm_count() * 2;
     if (grid > cap) grid = cap;
@@ -315,7 +332,11 @@ extern "C" int rb200_bpr_pair(const float* u, const float* p, const float* n, in
     if (!workspace || !ar.ok()) return rb_set_error(RB200_ERR_WORKSPACE, "bpr_pair: workspace too small");
     bpr_pair_kernel<<<grid, NT, 0, st>>>(u, p, n, B, D, grad_scale / (float)B, du, dp, dn, partials);
     RB_LAUNCH_CHECK("bpr_pair_kernel");
-    finalize_sum_kernel<<<1, 32, 0, st>>>(partials, grid, 1.0 / (double)B, loss);
+    if (fork && st_fin != st) {
+        RB_CUDA(cudaEventRecord(fork, st));
+        RB_CUDA(cudaStreamWaitEvent(st_fin, fork, 0));
+    }
+    finalize_sum_kernel<<<1, 32, 0, st_fin>>>(partials, grid, 1.0 / (double)B, loss, opt);
     RB_LAUNCH_CHECK("finalize_sum_kernel");
     return RB200_OK;
 }
@@ -351,7 +372,7 @@ extern "C" int rb200_bpr_inbatch(const float* U, const float* I, int B, int D, i
         default: rc = launch_inbatch<8>(U, I, B, diag, inv, rowsum, dU, dI, partials, st); break;
     }
     if (rc) return rc;
-    finalize_sum_kernel<<<1, 32, 0, st>>>(partials, tiles, 1.0 / denom, loss);
+    finalize_sum_kernel<<<1, 32, 0, st>>>(partials, tiles, 1.0 / denom, loss, nullptr);
     RB_LAUNCH_CHECK("finalize_sum_kernel");
     return RB200_OK;
 }

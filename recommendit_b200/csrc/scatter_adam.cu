@@ -327,12 +327,17 @@ __global__ void opt_begin_step_kernel(rb200_opt_state* st) {
     st->step_size = (float)(st->lr / bc1);
     st->bias_corr2_sqrt = (float)sqrt(bc2);
     st->sumsq = 0.0;
+    st->ticket = 0u;
 }
 
 struct SumsqSegs { rb200_sumsq_seg s[4]; int n; };
 
-__global__ void __launch_bounds__(NT) sumsq_kernel(const SumsqSegs segs, double* __restrict__ partials) {
+// Block partials in fp64; the LAST block to finish (ticket in the optimizer state, self-resetting) adds them up in a
+// fixed lane-strided order — deterministic whichever block that is — and, with do_clip, derives the clip coefficient.
+__global__ void __launch_bounds__(NT) sumsq_kernel(const SumsqSegs segs, double* __restrict__ partials, rb200_opt_state* st,
+                                                   int do_clip) {
     __shared__ double scratch[NT / 32];
+    __shared__ bool is_last;
     double acc = 0.0;
     const long long stride = (long long)gridDim.x * NT;
     for (int seg = 0; seg < segs.n; ++seg) {
@@ -358,16 +363,17 @@ __global__ void __launch_bounds__(NT) sumsq_kernel(const SumsqSegs segs, double*
         double t = 0.0;
         for (int w = 0; w < NT / 32; ++w) t += scratch[w];
         partials[blockIdx.x] = t;
+        __threadfence();
+        is_last = atomicAdd(&st->ticket, 1u) == gridDim.x - 1;
     }
-}
-
-// one warp: lane-strided partial sums, then a fixed shuffle tree (deterministic); optionally also the clip coefficient
-__global__ void sumsq_finalize_kernel(const double* __restrict__ partials, int n, rb200_opt_state* st, int do_clip) {
-    const int lane = threadIdx.x;
+    __syncthreads();
+    if (!is_last || threadIdx.x >= 32) return;
+    __threadfence();
     double t = 0.0;
-    for (int i = lane; i < n; i += 32) t += partials[i];
+    for (int i = lane; i < (int)gridDim.x; i += 32) t += __ldcg(partials + i);
     t = rb_warp_sum_d(t);
     if (lane == 0) {
+        st->ticket = 0u;
         t += st->sumsq;
         st->sumsq = t;
         if (do_clip) {
@@ -455,6 +461,53 @@ __global__ void __launch_bounds__(NT) adam_dense2_kernel(const AdamDenseParams p
 
 struct AdamTableJob { float* w; float* m; float* v; long long n_rows; int* row_slot; const float* uniq_grads; };
 struct AdamTableParams { AdamTableJob job[2]; int n_jobs; int D4; };
+
+// The optimizer step of the fused training step in ONE launch: both embedding tables (dense, reference-exact: every
+// row moves) and both MLP parameter blocks.  Requires D4 a power of two <= 32, so that the D4 lanes of a table row sit
+// in one warp: the first of them reads the row's gradient slot, resets it to -1 for the next step and broadcasts it.
+__global__ void __launch_bounds__(NT) adam_step_all_kernel(const AdamTableParams tp, const AdamDenseParams dp,
+                                                           const rb200_opt_state* __restrict__ st) {
+    const AdamK k = load_adam(st);
+    const long long stride = (long long)gridDim.x * NT;
+    const int D4 = tp.D4, lane = threadIdx.x & 31;
+    for (int j = 0; j < tp.n_jobs; ++j) {
+        const AdamTableJob& J = tp.job[j];
+        const long long n4 = J.n_rows * D4;
+        for (long long base = (long long)blockIdx.x * NT + (threadIdx.x & ~31); base < n4; base += stride) {   // warp-uniform
+            const long long i = base + lane;
+            const bool live = i < n4;
+            const long long row = i / D4;
+            const int c = (int)(i - row * D4);
+            int slot = -1;
+            if (live && c == 0) {
+                slot = J.row_slot[row];
+                if (slot >= 0) J.row_slot[row] = -1;
+            }
+            slot = __shfl_sync(0xffffffffu, slot, lane & ~(D4 - 1));
+            if (!live) continue;
+            float4 gv = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (slot >= 0) gv = __ldg(reinterpret_cast<const float4*>(J.uniq_grads) + (long long)slot * D4 + c);
+            float4 wv = reinterpret_cast<float4*>(J.w)[i], mv = reinterpret_cast<float4*>(J.m)[i], vv = reinterpret_cast<float4*>(J.v)[i];
+            adam4(wv, gv, mv, vv, k);
+            reinterpret_cast<float4*>(J.w)[i] = wv; reinterpret_cast<float4*>(J.m)[i] = mv; reinterpret_cast<float4*>(J.v)[i] = vv;
+        }
+    }
+    for (int j = 0; j < dp.n_jobs; ++j) {
+        const AdamDenseJob& J = dp.job[j];
+        const long long n4 = J.n >> 2;
+        for (long long i = (long long)blockIdx.x * NT + threadIdx.x; i < n4; i += stride) {
+            float4 wv = reinterpret_cast<float4*>(J.w)[i], mv = reinterpret_cast<float4*>(J.m)[i], vv = reinterpret_cast<float4*>(J.v)[i];
+            const float4 gv = __ldg(reinterpret_cast<const float4*>(J.g) + i);
+            adam4(wv, gv, mv, vv, k);
+            reinterpret_cast<float4*>(J.w)[i] = wv; reinterpret_cast<float4*>(J.m)[i] = mv; reinterpret_cast<float4*>(J.v)[i] = vv;
+        }
+        for (long long i = n4 * 4 + (long long)blockIdx.x * NT + threadIdx.x; i < J.n; i += stride) {
+            float wv = J.w[i], mv = J.m[i], vv = J.v[i];
+            adam1(wv, __ldg(J.g + i), mv, vv, k);
+            J.w[i] = wv; J.m[i] = mv; J.v[i] = vv;
+        }
+    }
+}
 // dense (reference-exact) table update for up to two tables in one launch
 __global__ void __launch_bounds__(NT) adam_table_dense2_kernel(const AdamTableParams p, const rb200_opt_state* __restrict__ st) {
     const AdamK k = load_adam(st);
@@ -727,10 +780,8 @@ int rb_sumsq_accumulate(rb200_opt_state* st, const rb200_sumsq_seg* segs, int n_
     int grid = (int)((n / 4 + NT - 1) / NT);
     if (grid > cap) grid = cap;
     if (grid < 1) grid = 1;
-    sumsq_kernel<<<grid, NT, 0, s>>>(k, partials);
+    sumsq_kernel<<<grid, NT, 0, s>>>(k, partials, st, do_clip);
     RB_LAUNCH_CHECK("sumsq_kernel");
-    sumsq_finalize_kernel<<<1, 32, 0, s>>>(partials, grid, st, do_clip);
-    RB_LAUNCH_CHECK("sumsq_finalize_kernel");
     return RB200_OK;
 }
 
@@ -790,6 +841,26 @@ int rb_adam_tables_dense2(float* w0, float* m0, float* v0, long long rows0, int*
     p.job[1] = {w1, m1, v1, rows1, slot1, ug1};
     adam_table_dense2_kernel<<<stream_grid((rows0 > rows1 ? rows0 : rows1) * (D / 4)), NT, 0, s>>>(p, st);
     RB_LAUNCH_CHECK("adam_table_dense2_kernel");
+    return RB200_OK;
+}
+
+// returns 1 when D does not allow the fused launch (caller then uses the separate kernels)
+int rb_adam_step_all(float* const mlp_w[2], const float* const mlp_g[2], float* const mlp_m[2], float* const mlp_v[2],
+                     const long long mlp_n[2], float* const tab_w[2], float* const tab_m[2], float* const tab_v[2],
+                     const long long tab_rows[2], int* const slot[2], const float* const ug[2], int D, const rb200_opt_state* st,
+                     cudaStream_t s) {
+    const int D4 = D / 4;
+    if (D % 4 != 0 || D4 > 32 || (D4 & (D4 - 1)) != 0) return 1;
+    AdamTableParams tp{};
+    AdamDenseParams dp{};
+    tp.n_jobs = 2; tp.D4 = D4; dp.n_jobs = 2;
+    for (int t = 0; t < 2; ++t) {
+        tp.job[t] = {tab_w[t], tab_m[t], tab_v[t], tab_rows[t], slot[t], ug[t]};
+        dp.job[t] = {mlp_w[t], mlp_g[t], mlp_m[t], mlp_v[t], mlp_n[t]};
+    }
+    const long long big = (tab_rows[0] > tab_rows[1] ? tab_rows[0] : tab_rows[1]) * D4;
+    adam_step_all_kernel<<<stream_grid(big), NT, 0, s>>>(tp, dp, st);
+    RB_LAUNCH_CHECK("adam_step_all_kernel");
     return RB200_OK;
 }
 

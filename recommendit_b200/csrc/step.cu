@@ -17,6 +17,13 @@ int rb_adam_dense2(float* w0, const float* g0, float* m0, float* v0, long long n
                    long long n1, const rb200_opt_state* st, cudaStream_t s);
 int rb_adam_tables_dense2(float* w0, float* m0, float* v0, long long rows0, int* slot0, const float* ug0, float* w1, float* m1, float* v1,
                           long long rows1, int* slot1, const float* ug1, int D, const rb200_opt_state* st, cudaStream_t s);
+int rb_adam_step_all(float* const mlp_w[2], const float* const mlp_g[2], float* const mlp_m[2], float* const mlp_v[2],
+                     const long long mlp_n[2], float* const tab_w[2], float* const tab_m[2], float* const tab_v[2],
+                     const long long tab_rows[2], int* const slot[2], const float* const ug[2], int D, const rb200_opt_state* st,
+                     cudaStream_t s);
+int rb_bpr_pair(const float* u, const float* p, const float* n, int B, int D, float* loss, float* du, float* dp, float* dn,
+                float grad_scale, void* workspace, size_t workspace_bytes, rb200_opt_state* opt, cudaStream_t st,
+                cudaStream_t st_fin, cudaEvent_t fork);
 int rb_reset_slots2(const int64_t* ids0, const int* n0, int cap0, int* slot0, const int64_t* ids1, const int* n1, int cap1, int* slot1,
                     cudaStream_t s);
 
@@ -32,7 +39,7 @@ struct StepWs {
     float *g_user_mlp, *g_item_mlp;   // contiguous
     int64_t *uniq_u, *uniq_i; float *ug_u, *ug_i; int *n_uniq;   // n_uniq[0]=user, [1]=item
     unsigned char *img_user, *img_item;   // tensor-core weight images
-    void *ws_bwd, *ws_loss, *ws_scatter, *ws_sumsq;
+    void *ws_bwd, *ws_bwd_u, *ws_loss, *ws_scatter, *ws_sumsq;
     size_t b_bwd, b_loss, b_scatter, b_sumsq;
     int P_user, P_item;
 };
@@ -61,6 +68,7 @@ bool carve(RbArena& ar, const rb200_step_params& s, StepWs& w) {
     w.img_item = ar.take<unsigned char>(tc ? rb_tower_img_bytes(s.D, s.H, s.extra_dim) : 16);
     w.b_bwd = rb200_tower_bwd_workspace_bytes(s.D, s.H, s.extra_dim);
     w.ws_bwd = ar.take<char>(w.b_bwd);
+    w.ws_bwd_u = ar.take<char>(w.b_bwd);      // the user tower's backward runs concurrently with the item towers'
     const size_t l0 = rb200_bpr_pair_workspace_bytes(s.B), l1 = s.loss_kind == 1 ? rb200_bpr_inbatch_workspace_bytes(s.B, s.D) : 0;
     w.b_loss = l0 > l1 ? l0 : l1;
     w.ws_loss = ar.take<char>(w.b_loss);
@@ -74,7 +82,7 @@ bool carve(RbArena& ar, const rb200_step_params& s, StepWs& w) {
 
 // Library-owned side stream + events for the fork/join inside the step (capturable: the side stream joins the capture
 // through the event dependencies).
-struct SideStream { cudaStream_t s = nullptr; cudaEvent_t fork = nullptr, join = nullptr; };
+struct SideStream { cudaStream_t s = nullptr; cudaEvent_t fork = nullptr, fork2 = nullptr, join = nullptr; };
 int side_stream(SideStream** out) {
     static thread_local SideStream per_dev[64];
     int dev = 0;
@@ -84,6 +92,7 @@ int side_stream(SideStream** out) {
     if (!ss.s) {
         RB_CUDA(cudaStreamCreateWithFlags(&ss.s, cudaStreamNonBlocking));
         RB_CUDA(cudaEventCreateWithFlags(&ss.fork, cudaEventDisableTiming));
+        RB_CUDA(cudaEventCreateWithFlags(&ss.fork2, cudaEventDisableTiming));
         RB_CUDA(cudaEventCreateWithFlags(&ss.join, cudaEventDisableTiming));
     }
     *out = &ss;
@@ -180,13 +189,12 @@ extern "C" int rb200_bpr_step(const rb200_step_params* s, void* stream) {
     if (dp) RB_CUDA(cudaMemsetAsync(dp_user_tab, 0, sizeof(float) * (size_t)(s->n_user_rows + s->n_item_rows) * D, st));
     const bool fast_scatter = items * B <= 16384 && s->n_user_rows < (1ll << 31) && s->n_item_rows < (1ll << 31);
     SideStream* side = nullptr;
+    if ((rc = side_stream(&side))) return rc;
     if (fast_scatter) {
-        if ((rc = side_stream(&side))) return rc;
         RB_CUDA(cudaEventRecord(side->fork, st));
         RB_CUDA(cudaStreamWaitEvent(side->s, side->fork, 0));
         if ((rc = rb_scatter_tables(1, 2, sc_ia, sc_ib, sc_na, sc_nb, sc_rw, D, sc_nr, s->padding_idx, sc_dn, sc_ui, sc_ug, sc_nu,
                                     sc_rs, w.ws_scatter, w.b_scatter, side->s))) return rc;
-        RB_CUDA(cudaEventRecord(side->join, side->s));
     }
 
     // ---- tensor-core modes: stage both towers' weight images once for forward and backward ----------- //
@@ -222,11 +230,18 @@ extern "C" int rb200_bpr_step(const rb200_step_params* s, void* stream) {
 
     RB_STAGE_EVENT();
     // ---- loss + gradient w.r.t. the tower outputs ------------------------------------------- //
-    if (pair) rc = rb200_bpr_pair(w.u, w.p, w.n, B, D, s->loss, w.du, w.dpn, w.dpn + (size_t)B * D, gscale, w.ws_loss, w.b_loss, st);
-    else rc = rb200_bpr_inbatch(w.u, w.p, B, D, s->inbatch_mode, s->loss, w.du, w.dpn, gscale, w.ws_loss, w.b_loss, st);
-    if (rc) return rc;
-    copy_loss_kernel<<<1, 32, 0, st>>>(s->loss, s->opt);
-    RB_LAUNCH_CHECK("copy_loss_kernel");
+    // (pairwise: the scalar reduction of the loss goes to the side stream — nothing downstream needs it before the join)
+    if (pair) {
+        rc = rb_bpr_pair(w.u, w.p, w.n, B, D, s->loss, w.du, w.dpn, w.dpn + (size_t)B * D, gscale, w.ws_loss, w.b_loss, s->opt, st,
+                         side->s, side->fork2);
+        if (rc) return rc;
+    } else {
+        if ((rc = rb200_bpr_inbatch(w.u, w.p, B, D, s->inbatch_mode, s->loss, w.du, w.dpn, gscale, w.ws_loss, w.b_loss, st))) return rc;
+        copy_loss_kernel<<<1, 32, 0, st>>>(s->loss, s->opt);
+        RB_LAUNCH_CHECK("copy_loss_kernel");
+        RB_CUDA(cudaEventRecord(side->fork2, st));
+        RB_CUDA(cudaStreamWaitEvent(side->s, side->fork2, 0));
+    }
 
     RB_STAGE_EVENT();
     // ---- backward through the towers ----------------------------------------------------------- //
@@ -235,7 +250,10 @@ extern "C" int rb200_bpr_step(const rb200_step_params* s, void* stream) {
     bj[0].extra_dim = 0; bj[0].W1 = fj[0].W1; bj[0].W2 = fj[0].W2; bj[0].dY = w.du; bj[0].y = w.u; bj[0].denom = w.den_u;
     bj[0].hid = w.hid_u; bj[0].dpre = w.dpre_u; bj[0].dact = w.dact_u; bj[0].dRows = w.drows_u;
     bj[0].img = tc ? w.img_user : nullptr;
-    if ((rc = rb200_tower_bwd(bj, 1, D, H, s->dropout_p, s->tower_mode, w.g_user_mlp, 0, w.ws_bwd, w.b_bwd, st))) return rc;
+    // (second fork, recorded with the loss above): the user tower's backward goes to the side stream (behind the id sort, long finished by now) and
+    // overlaps the item towers' backward — neither fills the GPU on its own (64 / 128 tiles of 128 samples at B = 8192)
+    if ((rc = rb200_tower_bwd(bj, 1, D, H, s->dropout_p, s->tower_mode, w.g_user_mlp, 0, w.ws_bwd_u, w.b_bwd, side->s))) return rc;
+    RB_CUDA(cudaEventRecord(side->join, side->s));
     for (int t = 0; t < items; ++t) {
         rb200_tower_bwd_job& j = bj[t];
         j = rb200_tower_bwd_job{};
@@ -250,8 +268,8 @@ extern "C" int rb200_bpr_step(const rb200_step_params* s, void* stream) {
 
     RB_STAGE_EVENT();
     // ---- sparse embedding gradients: deterministic sorted-segment sums ---------------------- //
+    RB_CUDA(cudaStreamWaitEvent(st, side->join, 0));          // join: user-tower gradients and sorted positions / segment starts
     if (fast_scatter) {
-        RB_CUDA(cudaStreamWaitEvent(st, side->join, 0));      // join: sorted positions / segment starts are ready
         if ((rc = rb_scatter_tables(2, 2, sc_ia, sc_ib, sc_na, sc_nb, sc_rw, D, sc_nr, s->padding_idx, sc_dn, sc_ui, sc_ug, sc_nu,
                                     sc_rs, w.ws_scatter, w.b_scatter, st))) return rc;
     } else {
@@ -276,15 +294,26 @@ extern "C" int rb200_bpr_step(const rb200_step_params* s, void* stream) {
 
     RB_STAGE_EVENT();
     // ---- Adam ---------------------------------------------------------------------------------- //
-    if ((rc = rb_adam_dense2(s->user_mlp, w.g_user_mlp, s->user_mlp_m, s->user_mlp_v, Pu, s->item_mlp, w.g_item_mlp, s->item_mlp_m,
-                             s->item_mlp_v, Pi, s->opt, st))) return rc;
+    int fused = 1;
     if (dense) {
+        float* mw[2] = {s->user_mlp, s->item_mlp}; const float* mg[2] = {w.g_user_mlp, w.g_item_mlp};
+        float* mm[2] = {s->user_mlp_m, s->item_mlp_m}; float* mv[2] = {s->user_mlp_v, s->item_mlp_v};
+        const long long mn[2] = {Pu, Pi};
+        float* tw[2] = {s->user_table, s->item_table}; float* tm[2] = {s->user_table_m, s->item_table_m};
+        float* tv[2] = {s->user_table_v, s->item_table_v}; const long long tr[2] = {s->n_user_rows, s->n_item_rows};
+        int* ts[2] = {s->user_row_slot, s->item_row_slot}; const float* tg[2] = {w.ug_u, w.ug_i};
+        fused = rb_adam_step_all(mw, mg, mm, mv, mn, tw, tm, tv, tr, ts, tg, D, s->opt, st);
+        if (fused < 0) return fused;
+    }
+    if (fused == 1 && (rc = rb_adam_dense2(s->user_mlp, w.g_user_mlp, s->user_mlp_m, s->user_mlp_v, Pu, s->item_mlp, w.g_item_mlp,
+                                           s->item_mlp_m, s->item_mlp_v, Pi, s->opt, st))) return rc;
+    if (dense && fused == 1) {
         if ((rc = rb_adam_tables_dense2(s->user_table, s->user_table_m, s->user_table_v, s->n_user_rows, s->user_row_slot, w.ug_u,
                                         s->item_table, s->item_table_m, s->item_table_v, s->n_item_rows, s->item_row_slot, w.ug_i, D,
                                         s->opt, st))) return rc;
         if ((rc = rb_reset_slots2(w.uniq_u, w.n_uniq, B, s->user_row_slot, w.uniq_i, w.n_uniq + 1, items * B, s->item_row_slot, st)))
             return rc;
-    } else {
+    } else if (!dense) {
         if ((rc = rb200_adam_rows(s->user_table, s->user_table_m, s->user_table_v, D, w.uniq_u, w.ug_u, w.n_uniq, B, s->opt, st))) return rc;
         if ((rc = rb200_adam_rows(s->item_table, s->item_table_m, s->item_table_v, D, w.uniq_i, w.ug_i, w.n_uniq + 1, items * B,
                                   s->opt, st))) return rc;
