@@ -1,11 +1,384 @@
-// tcgen05 in-batch BPR (modes 1 and 2) — placeholder until the tensor-core kernel lands.
+// In-batch BPR (src/models/two_tower.py:132-160 of the reference) on the 5th-generation tensor cores.
+//
+//   S = U·Iᵀ,   loss = Σ_{i≠j} softplus(S_ij − S_ii) / (B(B−1)),
+//   G_ij = g·σ(S_ij − S_ii) (i≠j; g = grad_scale / (B(B−1))),  r_i = Σ_j G_ij,
+//   dU_i = Σ_j G_ij I_j − r_i I_i,      dI_j = Σ_i G_ij U_i − r_j U_j.
+//
+// The B×B matrices never exist in memory.  One templated kernel is run twice ("flash" style, scores recomputed):
+//   pass U: X = U (128-row tile per CTA), Y = I streamed in 64-row tiles.  S-MMA: S = X·Yᵀ (tcgen05, TMEM).  Epilogue:
+//           every thread owns one S row (TMEM lane) × 32 columns → softplus (loss), G; G goes to shared memory as the
+//           K-major A operand of the second MMA  acc += G·Y  (B operand = Yᵀ, transposed while staged).
+//   pass I: X = I, Y = U: the same code computes Sᵀ tiles; the diagonal S_ii now varies along the columns.
+// The Y range is split over `split` CTAs per X tile so that the grid fills the SMs; partial sums (fp32 tiles, fp64 row
+// sums) go to the workspace and a finishing kernel adds them in a fixed order and subtracts r·(other side): deterministic.
+//
+// mode 2 = 3xTF32 (hi/lo split of both operands of both MMAs, fp32-grade), mode 1 = single TF32 (stated fast mode).
+// The tensor core's fp32 accumulation is not round-to-nearest over long chains (see tower_tc.cu), so every Y tile starts
+// a fresh TMEM accumulation that is flushed into fp32 registers.  D = 64 only (the production width).
 #include "common.cuh"
+#include "umma.cuh"
 
-size_t rb_inbatch_tc_workspace_bytes(int B, int D) { (void)B; (void)D; return 0; }
+namespace {
+
+constexpr int NT_IB = 256;
+constexpr int XT = 128, YT = 64, DD = 64;
+constexpr int X_BYTES = XT * DD * 4;      // 32 KB: X tile [128 × 64] K-major over d
+constexpr int Y_BYTES = YT * DD * 4;      // 16 KB: Y tile [64 × 64] K-major over d
+constexpr int YT_BYTES = DD * YT * 4;     // 16 KB: Yᵀ tile [64 d × 64 y] K-major over y
+constexpr int G_BYTES = XT * YT * 4;      // 32 KB: G tile [128 × 64 y] K-major over y
+constexpr int TMEM_COLS_IB = 128;         // S: 64 columns, acc: 64 columns
+
+template <int MODE>
+__device__ __forceinline__ void put4(unsigned char* hi_base, unsigned char* lo_base, int R, int r, int k, const float4& v) {
+    const uint32_t off = umma::kmajor_offset(R, r, k);
+    float4 hi, lo;
+    umma::split4(v, hi, lo);
+    *reinterpret_cast<float4*>(hi_base + off) = hi;
+    if (MODE == 2) *reinterpret_cast<float4*>(lo_base + off) = lo;
+}
+__device__ __forceinline__ float sel4(const float4& v, int e) { return e == 0 ? v.x : e == 1 ? v.y : e == 2 ? v.z : v.w; }
+
+// D[tmem] = A[128 × K] · B[N × K]ᵀ, operands fully resident in shared memory (K-major, RA / RB rows)
+template <int MODE>
+__device__ __forceinline__ void issue_gemm(uint32_t tmem_d, unsigned char* a_hi, unsigned char* a_lo, int RA, unsigned char* b_hi,
+                                           unsigned char* b_lo, int RB, int N, int K) {
+    const uint32_t idesc = umma::idesc_tf32(128, N);
+    const uint32_t lbo_a = (RA / 8) * 128, lbo_b = (RB / 8) * 128;
+    const uint32_t ah = umma::smem_u32(a_hi), al = umma::smem_u32(a_lo), bh = umma::smem_u32(b_hi), bl = umma::smem_u32(b_lo);
+#pragma unroll
+    for (int j = 0; j < K / 8; ++j) {
+        const uint32_t oa = 2 * j * lbo_a, ob = 2 * j * lbo_b;
+        if (MODE == 2) {
+            umma::mma_tf32(tmem_d, umma::smem_desc(al + oa, lbo_a, 128), umma::smem_desc(bh + ob, lbo_b, 128), idesc, j > 0);
+            umma::mma_tf32(tmem_d, umma::smem_desc(ah + oa, lbo_a, 128), umma::smem_desc(bl + ob, lbo_b, 128), idesc, true);
+            umma::mma_tf32(tmem_d, umma::smem_desc(ah + oa, lbo_a, 128), umma::smem_desc(bh + ob, lbo_b, 128), idesc, true);
+        } else {
+            umma::mma_tf32(tmem_d, umma::smem_desc(ah + oa, lbo_a, 128), umma::smem_desc(bh + ob, lbo_b, 128), idesc, j > 0);
+        }
+    }
+}
+
+struct Bar {           // mbarrier with bounded waits and a sticky failure flag
+    uint64_t* bar;
+    uint32_t phase;
+    int* dead;
+    int* err_flag;
+    __device__ void wait() {
+        if (!*dead && !umma::mbar_wait(bar, phase)) { *dead = 1; if (err_flag) atomicOr(err_flag, 2); }
+        phase ^= 1;
+    }
+};
+
+__global__ void __launch_bounds__(256) rowdot64_kernel(const float* __restrict__ U, const float* __restrict__ I, int B,
+                                                       float* __restrict__ diag) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int row = blockIdx.x * 8 + warp;
+    if (row >= B) return;
+    const float2 a = __ldg(reinterpret_cast<const float2*>(U + (long long)row * DD) + lane);
+    const float2 b = __ldg(reinterpret_cast<const float2*>(I + (long long)row * DD) + lane);
+    float s = fmaf(a.x, b.x, a.y * b.y);
+    s = rb_warp_sum(s);
+    if (lane == 0) diag[row] = s;
+}
+
+struct IbParams {
+    const float* X; const float* Y;      // row-side / streamed-side embeddings [B × 64]
+    const float* diag;                   // S_ii
+    int B, split, tiles_per_split;       // Y tiles (of 64) per CTA
+    float g;                             // grad_scale / (B(B−1))
+    float* acc_part;                     // [split][Bp][64]
+    double* r_part;                      // [split][2][Bp]   (pass U only)
+    double* loss_part;                   // [gridDim.x]      (pass U only)
+    int Bp;
+    int* err_flag;
+};
+
+// PASS_I = false: X = U, diagonal indexed by the row;  true: X = I, diagonal indexed by the column
+template <int MODE, bool PASS_I, bool WITH_GRAD>
+__global__ void __launch_bounds__(NT_IB, 1) inbatch_tc_kernel(const IbParams p) {
+    extern __shared__ __align__(1024) unsigned char smem[];
+    unsigned char* x_hi = smem;
+    unsigned char* x_lo = x_hi + X_BYTES;
+    unsigned char* y_hi = x_lo + X_BYTES;
+    unsigned char* y_lo = y_hi + Y_BYTES;
+    unsigned char* yt_hi = y_lo + Y_BYTES;
+    unsigned char* yt_lo = yt_hi + YT_BYTES;
+    unsigned char* g_hi = yt_lo + YT_BYTES;
+    unsigned char* g_lo = g_hi + G_BYTES;
+    __shared__ __align__(8) uint64_t bar_s_mem, bar_g_mem;
+    __shared__ uint32_t tmem_slot;
+    __shared__ int dead;
+    __shared__ float diag_y[YT];
+    __shared__ double red[NT_IB / 32];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if (warp == 0) umma::tmem_alloc(&tmem_slot, TMEM_COLS_IB);
+    if (tid == 0) { umma::mbar_init(&bar_s_mem, 1); umma::mbar_init(&bar_g_mem, 1); umma::fence_mbar_init(); dead = 0; }
+    umma::fence_before_sync();
+    __syncthreads();
+    umma::fence_after_sync();
+    const uint32_t tmem = tmem_slot;
+    Bar bar_s{&bar_s_mem, 0u, &dead, p.err_flag}, bar_g{&bar_g_mem, 0u, &dead, p.err_flag};
+    const int r_own = ((warp & 3) << 5) + lane, half = warp >> 2;
+    const uint32_t lane_off = (uint32_t)((warp & 3) * 32) << 16;
+    const int B = p.B;
+    const int xt = blockIdx.x / p.split, part = blockIdx.x - xt * p.split;
+    const int x0 = xt * XT;
+    const int gi = x0 + r_own;                       // this thread's global X row
+    // ---- stage the X tile once: thread = (row, half) → 8 float4 ------------------------------------------- //
+    {
+        const long long row = x0 + r_own;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            const int k = (half * 8 + q) * 4;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (row < B) v = __ldg(reinterpret_cast<const float4*>(p.X + row * DD + k));
+            put4<MODE>(x_hi, x_lo, XT, r_own, k, v);
+        }
+    }
+    const float d_own = (!PASS_I && gi < B) ? __ldg(p.diag + gi) : 0.f;
+    float acc[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) acc[i] = 0.f;
+    double r_sum = 0.0, loss_sum = 0.0;
+    const int t_begin = part * p.tiles_per_split;
+    const int n_ytiles = (B + YT - 1) / YT;
+    int t_end = t_begin + p.tiles_per_split;
+    if (t_end > n_ytiles) t_end = n_ytiles;
+    // thread mappings of the Y staging
+    const int yr = tid & 63, yq = tid >> 6;          // K-major copy: row yr, float4 columns 4·yq … 4·yq+3
+    const int mq = tid & 15, sq = tid >> 4;          // transposed copy: 4 y rows (4·sq…) × 4 d (4·mq…)
+    bool pending_g = false;
+    for (int t = t_begin; t < t_end; ++t) {
+        const int y0 = t * YT;
+        // global loads first (they overlap the previous tile's second MMA)
+        float4 vy[4], vt[4];
+        {
+            const long long row = y0 + yr;
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+                vy[e] = row < B ? __ldg(reinterpret_cast<const float4*>(p.Y + row * DD) + yq * 4 + e) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const long long rt = y0 + sq * 4 + i;
+                vt[i] = (WITH_GRAD && rt < B) ? __ldg(reinterpret_cast<const float4*>(p.Y + rt * DD) + mq) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        }
+        float dy = 0.f;
+        if (PASS_I && tid < YT) dy = (y0 + tid < B) ? __ldg(p.diag + y0 + tid) : 0.f;
+        if (WITH_GRAD && pending_g) {                // previous G-MMA done: G / Yᵀ buffers free, its result is in TMEM
+            bar_g.wait();
+            umma::fence_after_sync();
+            if (!dead) {
+                float v[32];
+                umma::tmem_ld32(tmem + lane_off + YT + half * 32, v);
+#pragma unroll
+                for (int i = 0; i < 32; ++i) acc[i] += v[i];
+            }
+            pending_g = false;
+        }
+#pragma unroll
+        for (int e = 0; e < 4; ++e) put4<MODE>(y_hi, y_lo, YT, yr, (yq * 4 + e) * 4, vy[e]);
+        if (WITH_GRAD) {
+#pragma unroll
+            for (int s = 0; s < 4; ++s) {            // lane-rotated transposing stores (conflict-free, see tower_tc.cu)
+                const int e = (s + (lane >> 1)) & 3;
+                put4<MODE>(yt_hi, yt_lo, DD, mq * 4 + e, sq * 4, make_float4(sel4(vt[0], e), sel4(vt[1], e), sel4(vt[2], e), sel4(vt[3], e)));
+            }
+        }
+        if (PASS_I && tid < YT) diag_y[tid] = dy;
+        umma::fence_proxy_async();
+        umma::fence_before_sync();
+        __syncthreads();
+        if (tid == 0 && !dead) {
+            umma::fence_after_sync();
+            issue_gemm<MODE>(tmem, x_hi, x_lo, XT, y_hi, y_lo, YT, YT, DD);      // S [128 × 64]
+            umma::commit(&bar_s_mem);
+        }
+        bar_s.wait();
+        umma::fence_after_sync();
+        // ---- epilogue: this thread's row × 32 columns ------------------------------------------------------- //
+        float s[32];
+        if (!dead) umma::tmem_ld32(tmem + lane_off + half * 32, s);
+        float tile_loss = 0.f, tile_r = 0.f;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            float gq[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int c = q * 4 + e;
+                const int gj = y0 + half * 32 + c;
+                const float d = PASS_I ? diag_y[half * 32 + c] : d_own;
+                const float x = s[c] - d;
+                const bool valid = gi < B && gj < B && gi != gj;
+                const float ex = __expf(-fabsf(x));
+                const float inv = __fdividef(1.f, 1.f + ex);
+                const float sig = x >= 0.f ? inv : ex * inv;
+                gq[e] = valid ? p.g * sig : 0.f;
+                if (!PASS_I) {
+                    const float sp = fmaxf(x, 0.f) + __logf(1.f + ex);
+                    tile_loss += valid ? sp : 0.f;
+                    tile_r += gq[e];
+                }
+            }
+            if (WITH_GRAD) put4<MODE>(g_hi, g_lo, XT, r_own, half * 32 + q * 4, make_float4(gq[0], gq[1], gq[2], gq[3]));
+        }
+        if (!PASS_I) { loss_sum += (double)tile_loss; r_sum += (double)tile_r; }
+        if (WITH_GRAD) {
+            umma::fence_proxy_async();
+            umma::fence_before_sync();
+            __syncthreads();
+            if (tid == 0 && !dead) {
+                umma::fence_after_sync();
+                issue_gemm<MODE>(tmem + YT, g_hi, g_lo, XT, yt_hi, yt_lo, DD, DD, YT);   // acc [128 × 64 d] = G · Y
+                umma::commit(&bar_g_mem);
+            }
+            pending_g = true;
+        } else {
+            umma::fence_before_sync();
+            __syncthreads();                          // S is overwritten by the next tile's first MMA
+        }
+    }
+    if (WITH_GRAD && pending_g) {
+        bar_g.wait();
+        umma::fence_after_sync();
+        if (!dead) {
+            float v[32];
+            umma::tmem_ld32(tmem + lane_off + YT + half * 32, v);
+#pragma unroll
+            for (int i = 0; i < 32; ++i) acc[i] += v[i];
+        }
+    }
+    // ---- partial results ------------------------------------------------------------------------------------ //
+    if (WITH_GRAD) {
+        float* dst = p.acc_part + ((long long)part * p.Bp + gi) * DD + half * 32;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) *reinterpret_cast<float4*>(dst + q * 4) = make_float4(acc[q * 4], acc[q * 4 + 1], acc[q * 4 + 2], acc[q * 4 + 3]);
+    }
+    if (!PASS_I) {
+        if (WITH_GRAD) p.r_part[((long long)part * 2 + half) * p.Bp + gi] = r_sum;
+        loss_sum = rb_warp_sum_d(loss_sum);
+        if (lane == 0) red[warp] = loss_sum;
+        __syncthreads();
+        if (tid == 0) {
+            double tsum = 0.0;
+            for (int w = 0; w < NT_IB / 32; ++w) tsum += red[w];
+            p.loss_part[blockIdx.x] = tsum;
+        }
+    }
+    umma::fence_before_sync();
+    __syncthreads();
+    if (warp == 0) umma::tmem_free(tmem, TMEM_COLS_IB);
+}
+
+// out_i = Σ_parts acc_part[part][i] − r_i · other_i   (pass U also reduces and stores r_i)
+template <bool PASS_I>
+__global__ void __launch_bounds__(256) inbatch_finish_kernel(const float* __restrict__ acc_part, const double* __restrict__ r_part,
+                                                             float* __restrict__ r_total, const float* __restrict__ other,
+                                                             float* __restrict__ out, int B, int Bp, int split) {
+    const int idx = blockIdx.x * 256 + threadIdx.x;
+    const int row = idx >> 4, c4 = idx & 15;
+    if (row >= B) return;
+    float r;
+    if (!PASS_I) {
+        double rs = 0.0;
+        for (int s = 0; s < split; ++s) rs += r_part[((long long)s * 2) * Bp + row] + r_part[((long long)s * 2 + 1) * Bp + row];
+        r = (float)rs;
+        if (c4 == 0) r_total[row] = r;
+    } else {
+        r = r_total[row];
+    }
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int s = 0; s < split; ++s) {
+        const float4 v = __ldg(reinterpret_cast<const float4*>(acc_part + ((long long)s * Bp + row) * DD) + c4);
+        a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+    }
+    const float4 o = __ldg(reinterpret_cast<const float4*>(other + (long long)row * DD) + c4);
+    a.x = fmaf(-r, o.x, a.x); a.y = fmaf(-r, o.y, a.y); a.z = fmaf(-r, o.z, a.z); a.w = fmaf(-r, o.w, a.w);
+    reinterpret_cast<float4*>(out + (long long)row * DD)[c4] = a;
+}
+
+__global__ void inbatch_loss_kernel(const double* __restrict__ partials, int n, double scale, float* __restrict__ out) {
+    double t = 0.0;
+    for (int i = threadIdx.x; i < n; i += 32) t += partials[i];
+    t = rb_warp_sum_d(t);
+    if (threadIdx.x == 0) out[0] = (float)(t * scale);
+}
+
+struct IbPlan { int n_xt, n_yt, split, tps, Bp, grid; };
+IbPlan plan(int B) {
+    IbPlan pl;
+    pl.n_xt = (B + XT - 1) / XT;
+    pl.n_yt = (B + YT - 1) / YT;
+    int split = rb_sm_count() / pl.n_xt;
+    if (split < 1) split = 1;
+    if (split > pl.n_yt) split = pl.n_yt;
+    pl.tps = (pl.n_yt + split - 1) / split;
+    pl.split = (pl.n_yt + pl.tps - 1) / pl.tps;      // no empty parts
+    pl.Bp = pl.n_xt * XT;
+    pl.grid = pl.n_xt * pl.split;
+    return pl;
+}
+
+constexpr size_t IB_SMEM = 2 * X_BYTES + 2 * Y_BYTES + 2 * YT_BYTES + 2 * G_BYTES;     // 192 KB
+
+template <int MODE, bool PASS_I, bool WITH_GRAD>
+int launch(const IbParams& p, int grid, cudaStream_t st) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        RB_CUDA(cudaFuncSetAttribute(inbatch_tc_kernel<MODE, PASS_I, WITH_GRAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)IB_SMEM));
+        attr_set = true;
+    }
+    inbatch_tc_kernel<MODE, PASS_I, WITH_GRAD><<<grid, NT_IB, IB_SMEM, st>>>(p);
+    RB_LAUNCH_CHECK("inbatch_tc_kernel");
+    return RB200_OK;
+}
+
+}  // namespace
+
+size_t rb_inbatch_tc_workspace_bytes(int B, int D) {
+    if (D != DD || B < 1) return 0;
+    const IbPlan pl = plan(B);
+    return 256 * 8 + sizeof(float) * (size_t)2 * B + sizeof(int) + sizeof(float) * (size_t)pl.split * pl.Bp * DD +
+           sizeof(double) * ((size_t)pl.split * 2 * pl.Bp + pl.grid);
+}
 
 int rb_inbatch_tc(const float* U, const float* I, int B, int D, int mode, float* loss, float* dU, float* dI,
                   float grad_scale, void* workspace, size_t workspace_bytes, cudaStream_t st) {
-    (void)U; (void)I; (void)B; (void)D; (void)loss; (void)dU; (void)dI; (void)grad_scale; (void)workspace;
-    (void)workspace_bytes; (void)st;
-    return rb_set_error(RB200_ERR_INVALID, "bpr_inbatch: mode %d (tcgen05) is not built in this version", mode);
+    RB_REQUIRE(mode == 1 || mode == 2, "bpr_inbatch: tensor-core modes are 1 (TF32) and 2 (3xTF32)");
+    RB_REQUIRE(D == DD, "bpr_inbatch: the tcgen05 kernel is built for D=64 (got %d); use mode 0", D);
+    RB_REQUIRE(B >= 2, "bpr_inbatch: B must be >= 2");
+    const IbPlan pl = plan(B);
+    RbArena ar(workspace, workspace_bytes);
+    float* diag = ar.take<float>(B);
+    float* r_total = ar.take<float>(B);
+    int* err = ar.take<int>(1);
+    float* acc_part = ar.take<float>((size_t)pl.split * pl.Bp * DD);
+    double* r_part = ar.take<double>((size_t)pl.split * 2 * pl.Bp);
+    double* loss_part = ar.take<double>(pl.grid);
+    if (!workspace || !ar.ok()) return rb_set_error(RB200_ERR_WORKSPACE, "bpr_inbatch: workspace too small (%zu given)", workspace_bytes);
+    rowdot64_kernel<<<(B + 7) / 8, 256, 0, st>>>(U, I, B, diag);
+    RB_LAUNCH_CHECK("rowdot64_kernel");
+    const double denom = (double)B * (double)(B - 1);
+    IbParams p{};
+    p.diag = diag; p.B = B; p.split = pl.split; p.tiles_per_split = pl.tps; p.g = (float)((double)grad_scale / denom);
+    p.acc_part = acc_part; p.r_part = r_part; p.loss_part = loss_part; p.Bp = pl.Bp; p.err_flag = nullptr;
+    (void)err;
+    const bool grad = dU != nullptr;
+    int rc;
+    p.X = U; p.Y = I;
+    if (mode == 2) rc = grad ? launch<2, false, true>(p, pl.grid, st) : launch<2, false, false>(p, pl.grid, st);
+    else rc = grad ? launch<1, false, true>(p, pl.grid, st) : launch<1, false, false>(p, pl.grid, st);
+    if (rc) return rc;
+    inbatch_loss_kernel<<<1, 32, 0, st>>>(loss_part, pl.grid, 1.0 / denom, loss);
+    RB_LAUNCH_CHECK("inbatch_loss_kernel");
+    if (!grad) return RB200_OK;
+    const int fgrid = (B * 16 + 255) / 256;
+    inbatch_finish_kernel<false><<<fgrid, 256, 0, st>>>(acc_part, r_part, r_total, I, dU, B, pl.Bp, pl.split);
+    RB_LAUNCH_CHECK("inbatch_finish_kernel");
+    p.X = I; p.Y = U;
+    rc = mode == 2 ? launch<2, true, true>(p, pl.grid, st) : launch<1, true, true>(p, pl.grid, st);
+    if (rc) return rc;
+    inbatch_finish_kernel<true><<<fgrid, 256, 0, st>>>(acc_part, r_part, r_total, U, dI, B, pl.Bp, pl.split);
+    RB_LAUNCH_CHECK("inbatch_finish_kernel");
+    return RB200_OK;
 }

@@ -354,7 +354,8 @@ extern "C" int rb200_bpr_inbatch(const float* U, const float* I, int B, int D, i
     RB_REQUIRE((dU == nullptr) == (dI == nullptr), "bpr_inbatch: dU/dI must both be set or both NULL");
     RB_REQUIRE(D == 32 || D == 64 || D == 128, "bpr_inbatch: D must be 32, 64 or 128 (got %d)", D);
     cudaStream_t st = (cudaStream_t)stream;
-    if (mode != 0) return rb_inbatch_tc(U, I, B, D, mode, loss, dU, dI, grad_scale, workspace, workspace_bytes, st);
+    // (B = 1 has no negatives: the loss is NaN as in the reference loop — left to the SIMT kernel)
+    if (mode != 0 && B >= 2) return rb_inbatch_tc(U, I, B, D, mode, loss, dU, dI, grad_scale, workspace, workspace_bytes, st);
     const int tiles = (B + TT - 1) / TT;
     RbArena ar(workspace, workspace_bytes);
     float* diag = ar.take<float>(B);
