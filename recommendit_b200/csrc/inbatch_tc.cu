@@ -6,7 +6,7 @@
 //
 // The B×B matrices never exist in memory.  One templated kernel is run twice ("flash" style, scores recomputed):
 //   pass U: X = U (128-row tile per CTA), Y = I streamed in 64-row tiles.  S-MMA: S = X·Yᵀ (tcgen05, TMEM).  Epilogue:
-//           every thread owns one S row (TMEM lane) × 32 columns → softplus (loss), G; G goes to shared memory as the
+//           every thread owns one S row (TMEM lane) × 16 columns → softplus (loss), G; G goes to shared memory as the
 //           K-major A operand of the second MMA  acc += G·Y  (B operand = Yᵀ, transposed while staged).
 //   pass I: X = I, Y = U: the same code computes Sᵀ tiles; the diagonal S_ii now varies along the columns.
 // The Y range is split over `split` CTAs per X tile so that the grid fills the SMs; partial sums (fp32 tiles, fp64 row
@@ -20,13 +20,14 @@
 
 namespace {
 
-constexpr int NT_IB = 256;
+constexpr int NT_IB = 512;            // worker threads
+constexpr int NT_ALL = NT_IB + 32;     // + the MMA-issuing warp
 constexpr int XT = 128, YT = 64, DD = 64;
 constexpr int X_BYTES = XT * DD * 4;      // 32 KB: X tile [128 × 64] K-major over d
 constexpr int Y_BYTES = YT * DD * 4;      // 16 KB: Y tile [64 × 64] K-major over d
 constexpr int YT_BYTES = DD * YT * 4;     // 16 KB: Yᵀ tile [64 d × 64 y] K-major over y
 constexpr int G_BYTES = XT * YT * 4;      // 32 KB: G tile [128 × 64 y] K-major over y
-constexpr int TMEM_COLS_IB = 128;         // S: 64 columns, acc: 64 columns
+constexpr int TMEM_COLS_IB = 256;         // S: 2 × 64 columns (double-buffered), acc: 64 columns
 
 template <int MODE>
 __device__ __forceinline__ void put4(unsigned char* hi_base, unsigned char* lo_base, int R, int r, int k, const float4& v) {
@@ -38,24 +39,17 @@ __device__ __forceinline__ void put4(unsigned char* hi_base, unsigned char* lo_b
 }
 __device__ __forceinline__ float sel4(const float4& v, int e) { return e == 0 ? v.x : e == 1 ? v.y : e == 2 ? v.z : v.w; }
 
-// D[tmem] = A[128 × K] · B[N × K]ᵀ, operands fully resident in shared memory (K-major, RA / RB rows)
-template <int MODE>
-__device__ __forceinline__ void issue_gemm(uint32_t tmem_d, unsigned char* a_hi, unsigned char* a_lo, int RA, unsigned char* b_hi,
-                                           unsigned char* b_lo, int RB, int N, int K) {
-    const uint32_t idesc = umma::idesc_tf32(128, N);
-    const uint32_t lbo_a = (RA / 8) * 128, lbo_b = (RB / 8) * 128;
-    const uint32_t ah = umma::smem_u32(a_hi), al = umma::smem_u32(a_lo), bh = umma::smem_u32(b_hi), bl = umma::smem_u32(b_lo);
-#pragma unroll
-    for (int j = 0; j < K / 8; ++j) {
-        const uint32_t oa = 2 * j * lbo_a, ob = 2 * j * lbo_b;
-        if (MODE == 2) {
-            umma::mma_tf32(tmem_d, umma::smem_desc(al + oa, lbo_a, 128), umma::smem_desc(bh + ob, lbo_b, 128), idesc, j > 0);
-            umma::mma_tf32(tmem_d, umma::smem_desc(ah + oa, lbo_a, 128), umma::smem_desc(bl + ob, lbo_b, 128), idesc, true);
-            umma::mma_tf32(tmem_d, umma::smem_desc(ah + oa, lbo_a, 128), umma::smem_desc(bh + ob, lbo_b, 128), idesc, true);
-        } else {
-            umma::mma_tf32(tmem_d, umma::smem_desc(ah + oa, lbo_a, 128), umma::smem_desc(bh + ob, lbo_b, 128), idesc, j > 0);
-        }
-    }
+__device__ __forceinline__ float rcp_approx(float x) {
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+// (hi, lo) += x, error-free (Knuth two-sum): fp32 pair instead of an fp64 accumulator (fp64 adds are slow on this part)
+__device__ __forceinline__ void two_sum(float& hi, float& lo, float x) {
+    const float t = hi + x;
+    const float z = t - hi;
+    lo += (hi - (t - z)) + (x - z);
+    hi = t;
 }
 
 struct Bar {           // mbarrier with bounded waits and a sticky failure flag
@@ -69,11 +63,12 @@ struct Bar {           // mbarrier with bounded waits and a sticky failure flag
     }
 };
 
-__global__ void __launch_bounds__(256) rowdot64_kernel(const float* __restrict__ U, const float* __restrict__ I, int B,
+__global__ void __launch_bounds__(256) rowdot64_kernel(const float* __restrict__ U, const float* __restrict__ I, int B, int Bd,
                                                        float* __restrict__ diag) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int row = blockIdx.x * 8 + warp;
-    if (row >= B) return;
+    if (row >= Bd) return;
+    if (row >= B) { if (lane == 0) diag[row] = 0.f; return; }
     const float2 a = __ldg(reinterpret_cast<const float2*>(U + (long long)row * DD) + lane);
     const float2 b = __ldg(reinterpret_cast<const float2*>(I + (long long)row * DD) + lane);
     float s = fmaf(a.x, b.x, a.y * b.y);
@@ -87,15 +82,53 @@ struct IbParams {
     int B, split, tiles_per_split;       // Y tiles (of 64) per CTA
     float g;                             // grad_scale / (B(B−1))
     float* acc_part;                     // [split][Bp][64]
-    double* r_part;                      // [split][2][Bp]   (pass U only)
+    double* r_part;                      // [split][NQ][Bp]  (pass U only)
     double* loss_part;                   // [gridDim.x]      (pass U only)
     int Bp;
     int* err_flag;
 };
 
-// PASS_I = false: X = U, diagonal indexed by the row;  true: X = I, diagonal indexed by the column
+constexpr int NQ = NT_IB / 128;          // column quarters of a tile: 16 warps = 4 TMEM lane groups × 4 quarters
+constexpr int QC = YT / NQ;              // 16 columns per thread
+
+// descriptors of one resident GEMM (computed once; the k-step only moves the 14-bit start address field)
+struct GemmDesc { uint64_t a_hi, a_lo, b_hi, b_lo; uint32_t step_a, step_b, idesc; };
+__device__ __forceinline__ GemmDesc make_gemm(unsigned char* a_hi, unsigned char* a_lo, int RA, unsigned char* b_hi, unsigned char* b_lo,
+                                              int RB, int N) {
+    GemmDesc g;
+    const uint32_t lbo_a = (RA / 8) * 128, lbo_b = (RB / 8) * 128;
+    g.a_hi = umma::smem_desc(umma::smem_u32(a_hi), lbo_a, 128); g.a_lo = umma::smem_desc(umma::smem_u32(a_lo), lbo_a, 128);
+    g.b_hi = umma::smem_desc(umma::smem_u32(b_hi), lbo_b, 128); g.b_lo = umma::smem_desc(umma::smem_u32(b_lo), lbo_b, 128);
+    g.step_a = (2 * lbo_a) >> 4; g.step_b = (2 * lbo_b) >> 4;
+    g.idesc = umma::idesc_tf32(128, N);
+    return g;
+}
+template <int MODE, int KSTEPS>
+__device__ __forceinline__ void issue(const GemmDesc& g, uint32_t tmem_d) {
+#pragma unroll
+    for (int j = 0; j < KSTEPS; ++j) {
+        const uint64_t oa = (uint64_t)(j * g.step_a), ob = (uint64_t)(j * g.step_b);
+        if (MODE == 2) {
+            umma::mma_tf32(tmem_d, g.a_lo + oa, g.b_hi + ob, g.idesc, j > 0);
+            umma::mma_tf32(tmem_d, g.a_hi + oa, g.b_lo + ob, g.idesc, true);
+            umma::mma_tf32(tmem_d, g.a_hi + oa, g.b_hi + ob, g.idesc, true);
+        } else {
+            umma::mma_tf32(tmem_d, g.a_hi + oa, g.b_hi + ob, g.idesc, j > 0);
+        }
+    }
+}
+
+__device__ __forceinline__ void bar_arrive(int id, int count) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory"); }
+__device__ __forceinline__ void bar_sync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
+
+// PASS_I = false: X = U, diagonal indexed by the row;  true: X = I, diagonal indexed by the column.
+//
+// 16 worker warps + 1 MMA-issuing warp.  Software pipeline over the Y tiles (S double-buffered in TMEM): while the
+// workers run the epilogue of tile t the tensor core computes S(t+1), and the loads of tile t+2 (K-major copy) /
+// t+1 (transposed copy) are in flight.  Hand-offs: workers → issuer through named barriers 1 ("Y(t+1) staged", S(t)
+// drained) and 2 ("G(t), Yᵀ(t) staged"); issuer → workers through tcgen05.commit on two mbarriers.
 template <int MODE, bool PASS_I, bool WITH_GRAD>
-__global__ void __launch_bounds__(NT_IB, 1) inbatch_tc_kernel(const IbParams p) {
+__global__ void __launch_bounds__(NT_ALL, 1) inbatch_tc_kernel(const IbParams p) {
     extern __shared__ __align__(1024) unsigned char smem[];
     unsigned char* x_hi = smem;
     unsigned char* x_lo = x_hi + X_BYTES;
@@ -108,7 +141,6 @@ __global__ void __launch_bounds__(NT_IB, 1) inbatch_tc_kernel(const IbParams p) 
     __shared__ __align__(8) uint64_t bar_s_mem, bar_g_mem;
     __shared__ uint32_t tmem_slot;
     __shared__ int dead;
-    __shared__ float diag_y[YT];
     __shared__ double red[NT_IB / 32];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     if (warp == 0) umma::tmem_alloc(&tmem_slot, TMEM_COLS_IB);
@@ -116,157 +148,195 @@ __global__ void __launch_bounds__(NT_IB, 1) inbatch_tc_kernel(const IbParams p) 
     umma::fence_before_sync();
     __syncthreads();
     umma::fence_after_sync();
-    const uint32_t tmem = tmem_slot;
-    Bar bar_s{&bar_s_mem, 0u, &dead, p.err_flag}, bar_g{&bar_g_mem, 0u, &dead, p.err_flag};
-    const int r_own = ((warp & 3) << 5) + lane, half = warp >> 2;
-    const uint32_t lane_off = (uint32_t)((warp & 3) * 32) << 16;
+    const uint32_t tmem = tmem_slot;                 // columns: S buffer 0 | S buffer 1 | acc
+    const uint32_t tmem_acc = tmem + 2 * YT;
     const int B = p.B;
     const int xt = blockIdx.x / p.split, part = blockIdx.x - xt * p.split;
     const int x0 = xt * XT;
-    const int gi = x0 + r_own;                       // this thread's global X row
-    // ---- stage the X tile once: thread = (row, half) → 8 float4 ------------------------------------------- //
-    {
-        const long long row = x0 + r_own;
-#pragma unroll
-        for (int q = 0; q < 8; ++q) {
-            const int k = (half * 8 + q) * 4;
-            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (row < B) v = __ldg(reinterpret_cast<const float4*>(p.X + row * DD + k));
-            put4<MODE>(x_hi, x_lo, XT, r_own, k, v);
-        }
-    }
-    const float d_own = (!PASS_I && gi < B) ? __ldg(p.diag + gi) : 0.f;
-    float acc[32];
-#pragma unroll
-    for (int i = 0; i < 32; ++i) acc[i] = 0.f;
-    double r_sum = 0.0, loss_sum = 0.0;
     const int t_begin = part * p.tiles_per_split;
     const int n_ytiles = (B + YT - 1) / YT;
     int t_end = t_begin + p.tiles_per_split;
     if (t_end > n_ytiles) t_end = n_ytiles;
-    // thread mappings of the Y staging
-    const int yr = tid & 63, yq = tid >> 6;          // K-major copy: row yr, float4 columns 4·yq … 4·yq+3
-    const int mq = tid & 15, sq = tid >> 4;          // transposed copy: 4 y rows (4·sq…) × 4 d (4·mq…)
-    bool pending_g = false;
-    for (int t = t_begin; t < t_end; ++t) {
-        const int y0 = t * YT;
-        // global loads first (they overlap the previous tile's second MMA)
-        float4 vy[4], vt[4];
-        {
-            const long long row = y0 + yr;
-#pragma unroll
-            for (int e = 0; e < 4; ++e)
-                vy[e] = row < B ? __ldg(reinterpret_cast<const float4*>(p.Y + row * DD) + yq * 4 + e) : make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const long long rt = y0 + sq * 4 + i;
-                vt[i] = (WITH_GRAD && rt < B) ? __ldg(reinterpret_cast<const float4*>(p.Y + rt * DD) + mq) : make_float4(0.f, 0.f, 0.f, 0.f);
+
+    if (warp == NT_IB / 32) {
+        // ================================ MMA-issuing warp ================================================== //
+        GemmDesc gs = make_gemm(x_hi, x_lo, XT, y_hi, y_lo, YT, YT);        // S   [128 × 64 y] = X · Yᵀ
+        GemmDesc gg = make_gemm(g_hi, g_lo, XT, yt_hi, yt_lo, DD, DD);      // acc [128 × 64 d] = G · Y
+        bar_sync(1, NT_ALL);                                                // X and Y(t_begin) staged
+        if (lane == 0) {
+            umma::fence_after_sync();
+            issue<MODE, DD / 8>(gs, tmem);
+            umma::commit(&bar_s_mem);
+        }
+        for (int t = t_begin; t < t_end; ++t) {
+            bar_sync(1, NT_ALL);                                            // Y(t+1) staged, S(t−1) drained
+            if (lane == 0 && t + 1 < t_end) {
+                umma::fence_after_sync();
+                issue<MODE, DD / 8>(gs, tmem + (uint32_t)((((t - t_begin) & 1) ^ 1) * YT));
+                umma::commit(&bar_s_mem);
+            }
+            if (WITH_GRAD) {
+                bar_sync(2, NT_ALL);                                        // G(t), Yᵀ(t) staged, acc(t−1) drained
+                if (lane == 0) {
+                    umma::fence_after_sync();
+                    issue<MODE, YT / 8>(gg, tmem_acc);
+                    umma::commit(&bar_g_mem);
+                }
             }
         }
-        float dy = 0.f;
-        if (PASS_I && tid < YT) dy = (y0 + tid < B) ? __ldg(p.diag + y0 + tid) : 0.f;
-        if (WITH_GRAD && pending_g) {                // previous G-MMA done: G / Yᵀ buffers free, its result is in TMEM
+    } else {
+        // ================================ worker warps ====================================================== //
+        Bar bar_s{&bar_s_mem, 0u, &dead, p.err_flag}, bar_g{&bar_g_mem, 0u, &dead, p.err_flag};
+        const int r_own = ((warp & 3) << 5) + lane, quarter = warp >> 2;
+        const uint32_t lane_off = (uint32_t)((warp & 3) * 32) << 16;
+        const int gi = x0 + r_own;                   // this thread's global X row
+        {   // stage the X tile once: thread = (row, quarter) → 4 float4
+            const long long row = x0 + r_own;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int k = (quarter * 4 + q) * 4;
+                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (row < B) v = __ldg(reinterpret_cast<const float4*>(p.X + row * DD + k));
+                put4<MODE>(x_hi, x_lo, XT, r_own, k, v);
+            }
+        }
+        const float d_own = (!PASS_I && gi < B) ? __ldg(p.diag + gi) : 0.f;
+        float acc[QC];
+#pragma unroll
+        for (int i = 0; i < QC; ++i) acc[i] = 0.f;
+        float r_hi = 0.f, r_lo = 0.f, loss_hi = 0.f, loss_lo = 0.f;
+        // Staging roles: threads 256…511 copy the Y tile K-major (row yr, float4 columns 4·yq…), threads 0…255 copy it
+        // transposed in 4(y) × 4(d) blocks (sq, mq); every thread carries 4 float4 of the tile it stages next.
+        const bool role_t = tid < 256;
+        const int yr = tid & 63, yq = (tid >> 6) & 3;
+        const int mq = tid & 15, sq = (tid >> 4) & 15;
+        float4 v[4];
+        auto load_tile = [&](int t) {                // role_t: transposed copy of tile t; else: K-major copy of tile t
+            const int y0 = t * YT;
+            if (role_t) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const long long rt = y0 + sq * 4 + i;
+                    v[i] = (WITH_GRAD && t < t_end && rt < B) ? __ldg(reinterpret_cast<const float4*>(p.Y + rt * DD) + mq) : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+            } else {
+                const long long row = y0 + yr;
+#pragma unroll
+                for (int e = 0; e < 4; ++e)
+                    v[e] = (t < t_end && row < B) ? __ldg(reinterpret_cast<const float4*>(p.Y + row * DD) + yq * 4 + e) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        };
+        auto store_y = [&]() {                       // K-major copy (threads 256…511)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) put4<MODE>(y_hi, y_lo, YT, yr, (yq * 4 + e) * 4, v[e]);
+        };
+        auto store_yt = [&]() {                      // transposed copy (threads 0…255), lane-rotated: conflict-free
+#pragma unroll
+            for (int s = 0; s < 4; ++s) {
+                const int e = (s + (lane >> 1)) & 3;
+                put4<MODE>(yt_hi, yt_lo, DD, mq * 4 + e, sq * 4, make_float4(sel4(v[0], e), sel4(v[1], e), sel4(v[2], e), sel4(v[3], e)));
+            }
+        };
+        // ---- prologue: Y(t_begin) staged → S(t_begin) in flight; registers hold Yᵀ(t_begin) / Y(t_begin+1) ---- //
+        if (!role_t) { load_tile(t_begin); store_y(); }
+        umma::fence_proxy_async();
+        bar_arrive(1, NT_ALL);
+        load_tile(role_t ? t_begin : t_begin + 1);
+        bool pending_g = false;
+        for (int t = t_begin; t < t_end; ++t) {
+            const int y0 = t * YT;
+            const uint32_t s_cur = tmem + (uint32_t)(((t - t_begin) & 1) * YT);
+            float4 dq[QC / 4];                       // S_ii of this thread's columns (pass I; diag is padded with zeros)
+            if (PASS_I) {
+#pragma unroll
+                for (int q = 0; q < QC / 4; ++q) dq[q] = __ldg(reinterpret_cast<const float4*>(p.diag + y0 + quarter * QC) + q);
+            }
+            bar_s.wait();                            // S(t) ready (issued one tile ago); the Y buffer is free
+            umma::fence_after_sync();
+            if (!role_t) store_y();                  // Y(t+1) (zeros past the end)
+            umma::fence_proxy_async();
+            umma::fence_before_sync();               // (this thread's tcgen05.ld of S(t−1) completed in the last iteration)
+            bar_arrive(1, NT_ALL);
+            if (!role_t) load_tile(t + 2);           // in flight during the epilogue
+            // ---- epilogue of tile t: this thread's row × 16 columns, kept in registers ---------------------- //
+            float s[QC], gq[QC];
+            if (!dead) umma::tmem_ld16(s_cur + lane_off + quarter * QC, s);
+            float tile_loss = 0.f, tile_r = 0.f;
+            // tiles that touch neither the diagonal nor the ragged end need no masking (uniform per CTA)
+            const bool clean = y0 + YT <= B && x0 + XT <= B && (y0 + YT <= x0 || y0 >= x0 + XT);
+            if (clean) {
+#pragma unroll
+                for (int c = 0; c < QC; ++c) {
+                    const float x = s[c] - (PASS_I ? sel4(dq[c >> 2], c & 3) : d_own);
+                    const float ex = __expf(-fabsf(x));
+                    const float inv = rcp_approx(1.f + ex);
+                    gq[c] = p.g * (x >= 0.f ? inv : ex * inv);
+                    if (!PASS_I) { tile_loss += fmaxf(x, 0.f) + __logf(1.f + ex); tile_r += gq[c]; }
+                }
+            } else {
+#pragma unroll
+                for (int c = 0; c < QC; ++c) {
+                    const int gj = y0 + quarter * QC + c;
+                    const float x = s[c] - (PASS_I ? sel4(dq[c >> 2], c & 3) : d_own);
+                    const bool valid = gi < B && gj < B && gi != gj;
+                    const float ex = __expf(-fabsf(x));
+                    const float inv = rcp_approx(1.f + ex);
+                    gq[c] = valid ? p.g * (x >= 0.f ? inv : ex * inv) : 0.f;
+                    if (!PASS_I) { tile_loss += valid ? fmaxf(x, 0.f) + __logf(1.f + ex) : 0.f; tile_r += gq[c]; }
+                }
+            }
+            if (!PASS_I) { two_sum(loss_hi, loss_lo, tile_loss); two_sum(r_hi, r_lo, tile_r); }
+            if (WITH_GRAD) {
+                if (pending_g) {                     // G-MMA(t−1) finished under the epilogue: G / Yᵀ buffers free, result in TMEM
+                    bar_g.wait();
+                    umma::fence_after_sync();
+                    if (!dead) {
+                        float f[QC];
+                        umma::tmem_ld16(tmem_acc + lane_off + quarter * QC, f);
+#pragma unroll
+                        for (int i = 0; i < QC; ++i) acc[i] += f[i];
+                    }
+                }
+                if (role_t) store_yt();              // Yᵀ(t)
+#pragma unroll
+                for (int q = 0; q < QC / 4; ++q)
+                    put4<MODE>(g_hi, g_lo, XT, r_own, quarter * QC + q * 4, make_float4(gq[q * 4], gq[q * 4 + 1], gq[q * 4 + 2], gq[q * 4 + 3]));
+                umma::fence_proxy_async();
+                umma::fence_before_sync();
+                bar_arrive(2, NT_ALL);
+                pending_g = true;
+                if (role_t) load_tile(t + 1);        // Yᵀ(t+1): consumed after the next epilogue
+            }
+        }
+        if (WITH_GRAD && pending_g) {
             bar_g.wait();
             umma::fence_after_sync();
             if (!dead) {
-                float v[32];
-                umma::tmem_ld32(tmem + lane_off + YT + half * 32, v);
+                float f[QC];
+                umma::tmem_ld16(tmem_acc + lane_off + quarter * QC, f);
 #pragma unroll
-                for (int i = 0; i < 32; ++i) acc[i] += v[i];
+                for (int i = 0; i < QC; ++i) acc[i] += f[i];
             }
-            pending_g = false;
         }
-#pragma unroll
-        for (int e = 0; e < 4; ++e) put4<MODE>(y_hi, y_lo, YT, yr, (yq * 4 + e) * 4, vy[e]);
+        // ---- partial results -------------------------------------------------------------------------------- //
         if (WITH_GRAD) {
+            float* dst = p.acc_part + ((long long)part * p.Bp + gi) * DD + quarter * QC;
 #pragma unroll
-            for (int s = 0; s < 4; ++s) {            // lane-rotated transposing stores (conflict-free, see tower_tc.cu)
-                const int e = (s + (lane >> 1)) & 3;
-                put4<MODE>(yt_hi, yt_lo, DD, mq * 4 + e, sq * 4, make_float4(sel4(vt[0], e), sel4(vt[1], e), sel4(vt[2], e), sel4(vt[3], e)));
-            }
+            for (int q = 0; q < QC / 4; ++q) *reinterpret_cast<float4*>(dst + q * 4) = make_float4(acc[q * 4], acc[q * 4 + 1], acc[q * 4 + 2], acc[q * 4 + 3]);
         }
-        if (PASS_I && tid < YT) diag_y[tid] = dy;
-        umma::fence_proxy_async();
-        umma::fence_before_sync();
-        __syncthreads();
-        if (tid == 0 && !dead) {
-            umma::fence_after_sync();
-            issue_gemm<MODE>(tmem, x_hi, x_lo, XT, y_hi, y_lo, YT, YT, DD);      // S [128 × 64]
-            umma::commit(&bar_s_mem);
-        }
-        bar_s.wait();
-        umma::fence_after_sync();
-        // ---- epilogue: this thread's row × 32 columns ------------------------------------------------------- //
-        float s[32];
-        if (!dead) umma::tmem_ld32(tmem + lane_off + half * 32, s);
-        float tile_loss = 0.f, tile_r = 0.f;
-#pragma unroll
-        for (int q = 0; q < 8; ++q) {
-            float gq[4];
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                const int c = q * 4 + e;
-                const int gj = y0 + half * 32 + c;
-                const float d = PASS_I ? diag_y[half * 32 + c] : d_own;
-                const float x = s[c] - d;
-                const bool valid = gi < B && gj < B && gi != gj;
-                const float ex = __expf(-fabsf(x));
-                const float inv = __fdividef(1.f, 1.f + ex);
-                const float sig = x >= 0.f ? inv : ex * inv;
-                gq[e] = valid ? p.g * sig : 0.f;
-                if (!PASS_I) {
-                    const float sp = fmaxf(x, 0.f) + __logf(1.f + ex);
-                    tile_loss += valid ? sp : 0.f;
-                    tile_r += gq[e];
-                }
-            }
-            if (WITH_GRAD) put4<MODE>(g_hi, g_lo, XT, r_own, half * 32 + q * 4, make_float4(gq[0], gq[1], gq[2], gq[3]));
-        }
-        if (!PASS_I) { loss_sum += (double)tile_loss; r_sum += (double)tile_r; }
-        if (WITH_GRAD) {
-            umma::fence_proxy_async();
-            umma::fence_before_sync();
-            __syncthreads();
-            if (tid == 0 && !dead) {
-                umma::fence_after_sync();
-                issue_gemm<MODE>(tmem + YT, g_hi, g_lo, XT, yt_hi, yt_lo, DD, DD, YT);   // acc [128 × 64 d] = G · Y
-                umma::commit(&bar_g_mem);
-            }
-            pending_g = true;
-        } else {
-            umma::fence_before_sync();
-            __syncthreads();                          // S is overwritten by the next tile's first MMA
-        }
-    }
-    if (WITH_GRAD && pending_g) {
-        bar_g.wait();
-        umma::fence_after_sync();
-        if (!dead) {
-            float v[32];
-            umma::tmem_ld32(tmem + lane_off + YT + half * 32, v);
-#pragma unroll
-            for (int i = 0; i < 32; ++i) acc[i] += v[i];
-        }
-    }
-    // ---- partial results ------------------------------------------------------------------------------------ //
-    if (WITH_GRAD) {
-        float* dst = p.acc_part + ((long long)part * p.Bp + gi) * DD + half * 32;
-#pragma unroll
-        for (int q = 0; q < 8; ++q) *reinterpret_cast<float4*>(dst + q * 4) = make_float4(acc[q * 4], acc[q * 4 + 1], acc[q * 4 + 2], acc[q * 4 + 3]);
-    }
-    if (!PASS_I) {
-        if (WITH_GRAD) p.r_part[((long long)part * 2 + half) * p.Bp + gi] = r_sum;
-        loss_sum = rb_warp_sum_d(loss_sum);
-        if (lane == 0) red[warp] = loss_sum;
-        __syncthreads();
-        if (tid == 0) {
-            double tsum = 0.0;
-            for (int w = 0; w < NT_IB / 32; ++w) tsum += red[w];
-            p.loss_part[blockIdx.x] = tsum;
+        if (!PASS_I) {
+            if (WITH_GRAD) p.r_part[((long long)part * NQ + quarter) * p.Bp + gi] = (double)r_hi + (double)r_lo;
+            const double loss_sum = rb_warp_sum_d((double)loss_hi + (double)loss_lo);
+            if (lane == 0) red[warp] = loss_sum;
         }
     }
     umma::fence_before_sync();
     __syncthreads();
+    if (!PASS_I && tid == 0) {
+        double tsum = 0.0;
+        for (int w = 0; w < NT_IB / 32; ++w) tsum += red[w];
+        p.loss_part[blockIdx.x] = tsum;
+    }
     if (warp == 0) umma::tmem_free(tmem, TMEM_COLS_IB);
 }
 
@@ -281,7 +351,7 @@ __global__ void __launch_bounds__(256) inbatch_finish_kernel(const float* __rest
     float r;
     if (!PASS_I) {
         double rs = 0.0;
-        for (int s = 0; s < split; ++s) rs += r_part[((long long)s * 2) * Bp + row] + r_part[((long long)s * 2 + 1) * Bp + row];
+        for (int s = 0; s < split * NQ; ++s) rs += r_part[(long long)s * Bp + row];
         r = (float)rs;
         if (c4 == 0) r_total[row] = r;
     } else {
@@ -328,7 +398,7 @@ int launch(const IbParams& p, int grid, cudaStream_t st) {
         RB_CUDA(cudaFuncSetAttribute(inbatch_tc_kernel<MODE, PASS_I, WITH_GRAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)IB_SMEM));
         attr_set = true;
     }
-    inbatch_tc_kernel<MODE, PASS_I, WITH_GRAD><<<grid, NT_IB, IB_SMEM, st>>>(p);
+    inbatch_tc_kernel<MODE, PASS_I, WITH_GRAD><<<grid, NT_ALL, IB_SMEM, st>>>(p);
     RB_LAUNCH_CHECK("inbatch_tc_kernel");
     return RB200_OK;
 }
@@ -338,8 +408,8 @@ int launch(const IbParams& p, int grid, cudaStream_t st) {
 size_t rb_inbatch_tc_workspace_bytes(int B, int D) {
     if (D != DD || B < 1) return 0;
     const IbPlan pl = plan(B);
-    return 256 * 8 + sizeof(float) * (size_t)2 * B + sizeof(int) + sizeof(float) * (size_t)pl.split * pl.Bp * DD +
-           sizeof(double) * ((size_t)pl.split * 2 * pl.Bp + pl.grid);
+    return 256 * 8 + sizeof(float) * ((size_t)2 * B + YT) + sizeof(int) + sizeof(float) * (size_t)pl.split * pl.Bp * DD +
+           sizeof(double) * ((size_t)pl.split * NQ * pl.Bp + pl.grid);
 }
 
 int rb_inbatch_tc(const float* U, const float* I, int B, int D, int mode, float* loss, float* dU, float* dI,
@@ -349,14 +419,15 @@ int rb_inbatch_tc(const float* U, const float* I, int B, int D, int mode, float*
     RB_REQUIRE(B >= 2, "bpr_inbatch: B must be >= 2");
     const IbPlan pl = plan(B);
     RbArena ar(workspace, workspace_bytes);
-    float* diag = ar.take<float>(B);
+    const int Bd = pl.n_yt * YT;                     // diag padded to whole Y tiles (zeros past B)
+    float* diag = ar.take<float>(Bd);
     float* r_total = ar.take<float>(B);
     int* err = ar.take<int>(1);
     float* acc_part = ar.take<float>((size_t)pl.split * pl.Bp * DD);
-    double* r_part = ar.take<double>((size_t)pl.split * 2 * pl.Bp);
+    double* r_part = ar.take<double>((size_t)pl.split * NQ * pl.Bp);
     double* loss_part = ar.take<double>(pl.grid);
     if (!workspace || !ar.ok()) return rb_set_error(RB200_ERR_WORKSPACE, "bpr_inbatch: workspace too small (%zu given)", workspace_bytes);
-    rowdot64_kernel<<<(B + 7) / 8, 256, 0, st>>>(U, I, B, diag);
+    rowdot64_kernel<<<(Bd + 7) / 8, 256, 0, st>>>(U, I, B, Bd, diag);
     RB_LAUNCH_CHECK("rowdot64_kernel");
     const double denom = (double)B * (double)(B - 1);
     IbParams p{};
