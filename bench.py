@@ -339,6 +339,67 @@ def bench_ivf(args, dev):
     return out
 
 
+def bench_inbatch(args, dev):
+    """C2 in-batch variant: in_batch_bpr_loss (two_tower.py:132-160) — kernel alone (SIMT vs tcgen05) and the
+    whole training step (2 towers + B×B loss).  The score/gradient products are the one GEMM-shaped stage of the path:
+    reported against the tensor roofline with 6·B²·D logical flops (S, dU, dI; scores are recomputed in the second pass,
+    so 8·B²·D are executed, x3 in 3xTF32 mode)."""
+    import recommendit_b200 as R
+    from recommendit_b200 import _lib
+    lib = _lib.load()
+    pk = peaks()
+    g = torch.Generator(device=dev).manual_seed(3)
+    U = torch.nn.functional.normalize(torch.randn(B, D, device=dev, generator=g), dim=-1)
+    I = torch.nn.functional.normalize(torch.randn(B, D, device=dev, generator=g), dim=-1)
+    loss = torch.empty(1, device=dev); dU = torch.empty_like(U); dI = torch.empty_like(I)
+    wsb = lib.rb200_bpr_inbatch_workspace_bytes(B, D)
+    ws = _lib.workspace(wsb, dev)
+    flush = torch.zeros(256 << 20, dtype=torch.uint8, device=dev)
+    out = {"B": B, "D": D, "logical_flops": 6.0 * B * B * D}
+    for mode, name in ((0, "simt_fp32"), (2, "tcgen05_3xtf32"), (1, "tcgen05_tf32")):
+        def run():
+            _lib.check(lib.rb200_bpr_inbatch(U.data_ptr(), I.data_ptr(), B, D, mode, loss.data_ptr(), dU.data_ptr(), dI.data_ptr(), 1.0,
+                                             ws.data_ptr(), wsb, _lib.stream_ptr()))
+        for _ in range(3):
+            run()
+        ts = []
+        for _ in range(10):
+            flush_l2(flush)
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(); run(); b.record()
+            torch.cuda.synchronize(dev)
+            ts.append(a.elapsed_time(b))
+        ms = float(np.median(ts))
+        out[name] = {"ms": ms, "logical_tflops": 6.0 * B * B * D / (ms * 1e-3) / 1e12}
+    t = out["tcgen05_3xtf32"]
+    out["roofline"] = {"kernel": "inbatch_tc_kernel<2> x2 (rb200_bpr_inbatch mode 2)", "bound": "tensor", "unit": "TFLOP/s",
+                       "achieved": t["logical_tflops"], "issued_tflops": t["logical_tflops"] * 4.0, "peak": pk["bf16_tflops"],
+                       "frac": t["logical_tflops"] / pk["bf16_tflops"], "traffic": None,
+                       "note": "logical 6·B²·D fp32-grade flops vs the measured bf16 peak (kind::tf32 peaks at half of it); issued = "
+                               "8·B²·D (scores recomputed) x 3 (3xTF32).  The kernel is bound by the B² sigmoid/softplus epilogue and "
+                               "operand staging (SFU + issue slots), not by the tensor pipe (profiles/r01_inbatch_tc.md)"}
+    # whole step with the in-batch loss (2 towers + B×B), CUDA graph, device-resident batch
+    torch.manual_seed(0)
+    model = R.TwoTowerModel(N_USERS, N_ITEMS, D, H, dropout=DROPOUT).to(dev).train()
+    tr = R.FusedBPRTrainer(model, lr=1e-3, weight_decay=1e-5, max_norm=1.0, adam_mode="dense", loss="in_batch", use_cuda_graph=True)
+    batches, _ = synth_batches(4)
+    resident = [tr.pack_host(*b).to(dev) for b in batches]
+    for i in range(5):
+        tr.load_packed(resident[i % 4]); tr.step()
+    torch.cuda.synchronize(dev)
+    ts = []
+    for i in range(max(10, args.steps)):
+        flush_l2(flush)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(); tr.load_packed(resident[i % 4]); tr.step(); b.record()
+        torch.cuda.synchronize(dev)
+        ts.append(a.elapsed_time(b))
+    ms = float(np.mean(ts))
+    out["step"] = {"ms_per_step": ms, "samples_per_s": B / (ms * 1e-3), "final_loss": float(tr.loss_dev.item()),
+                   "api": "FusedBPRTrainer(loss='in_batch') (CUDA graph), in-batch kernel mode auto = tcgen05 3xTF32"}
+    return out
+
+
 def bench_hbm_kernels(dev):
     """The HBM-bound kernels of the path at a size where HBM (not L2) is the limit — BASELINE config C4 widths (D = 128):
     row gather, sorted-segment scatter-add, Adam on touched rows, dense Adam.  Algorithmic bytes per SURVEY.md §8(d)."""
@@ -433,6 +494,7 @@ def main():
     ap.add_argument("--skip-ivf", action="store_true")
     ap.add_argument("--skip-cpu", action="store_true")
     ap.add_argument("--skip-hbm", action="store_true")
+    ap.add_argument("--skip-inbatch", action="store_true")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
@@ -489,6 +551,8 @@ def main():
     }
     if not args.skip_ivf:
         line["ivf"] = bench_ivf(args, dev)
+    if not args.skip_inbatch:
+        line["inbatch"] = bench_inbatch(args, dev)
     if not args.skip_hbm:
         line["hbm_kernels"] = bench_hbm_kernels(dev)
     if not args.skip_cpu:

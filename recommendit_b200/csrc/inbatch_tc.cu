@@ -12,6 +12,11 @@
 // The Y range is split over `split` CTAs per X tile so that the grid fills the SMs; partial sums (fp32 tiles, fp64 row
 // sums) go to the workspace and a finishing kernel adds them in a fixed order and subtracts r·(other side): deterministic.
 //
+// The second product is centred: Σ_j G_ij (Y_j − c) − r_i (other_i − c) [+ (q_j − r_j) c in pass I, q = column sums of G]
+// with c = column mean of Y.  The identity holds
+// for any c; with c = mean the terms are small when the embeddings are alike (untrained towers), so the fp32-grade
+// product error is not amplified by the cancellation between Σ_j G_ij Y_j and r_i·other_i.
+//
 // mode 2 = 3xTF32 (hi/lo split of both operands of both MMAs, fp32-grade), mode 1 = single TF32 (stated fast mode).
 // The tensor core's fp32 accumulation is not round-to-nearest over long chains (see tower_tc.cu), so every Y tile starts
 // a fresh TMEM accumulation that is flushed into fp32 registers.  D = 64 only (the production width).
@@ -79,6 +84,7 @@ __global__ void __launch_bounds__(256) rowdot64_kernel(const float* __restrict__
 struct IbParams {
     const float* X; const float* Y;      // row-side / streamed-side embeddings [B × 64]
     const float* diag;                   // S_ii
+    const float* ycen;                   // [64] column means of Y (centring of the second product, see header)
     int B, split, tiles_per_split;       // Y tiles (of 64) per CTA
     float g;                             // grad_scale / (B(B−1))
     float* acc_part;                     // [split][Bp][64]
@@ -210,6 +216,7 @@ __global__ void __launch_bounds__(NT_ALL, 1) inbatch_tc_kernel(const IbParams p)
         const bool role_t = tid < 256;
         const int yr = tid & 63, yq = (tid >> 6) & 3;
         const int mq = tid & 15, sq = (tid >> 4) & 15;
+        const float4 cen = (WITH_GRAD && role_t) ? __ldg(reinterpret_cast<const float4*>(p.ycen) + mq) : make_float4(0.f, 0.f, 0.f, 0.f);
         float4 v[4];
         auto load_tile = [&](int t) {                // role_t: transposed copy of tile t; else: K-major copy of tile t
             const int y0 = t * YT;
@@ -217,7 +224,8 @@ __global__ void __launch_bounds__(NT_ALL, 1) inbatch_tc_kernel(const IbParams p)
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
                     const long long rt = y0 + sq * 4 + i;
-                    v[i] = (WITH_GRAD && t < t_end && rt < B) ? __ldg(reinterpret_cast<const float4*>(p.Y + rt * DD) + mq) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    v[i] = (WITH_GRAD && t < t_end && rt < B) ? __ldg(reinterpret_cast<const float4*>(p.Y + rt * DD) + mq) : cen;
+                    v[i].x -= cen.x; v[i].y -= cen.y; v[i].z -= cen.z; v[i].w -= cen.w;
                 }
             } else {
                 const long long row = y0 + yr;
@@ -271,7 +279,8 @@ __global__ void __launch_bounds__(NT_ALL, 1) inbatch_tc_kernel(const IbParams p)
                     const float ex = __expf(-fabsf(x));
                     const float inv = rcp_approx(1.f + ex);
                     gq[c] = p.g * (x >= 0.f ? inv : ex * inv);
-                    if (!PASS_I) { tile_loss += fmaxf(x, 0.f) + __logf(1.f + ex); tile_r += gq[c]; }
+                    tile_r += gq[c];
+                    if (!PASS_I) tile_loss += fmaxf(x, 0.f) + __logf(1.f + ex);
                 }
             } else {
 #pragma unroll
@@ -282,10 +291,12 @@ __global__ void __launch_bounds__(NT_ALL, 1) inbatch_tc_kernel(const IbParams p)
                     const float ex = __expf(-fabsf(x));
                     const float inv = rcp_approx(1.f + ex);
                     gq[c] = valid ? p.g * (x >= 0.f ? inv : ex * inv) : 0.f;
-                    if (!PASS_I) { tile_loss += valid ? fmaxf(x, 0.f) + __logf(1.f + ex) : 0.f; tile_r += gq[c]; }
+                    tile_r += gq[c];
+                    if (!PASS_I) tile_loss += valid ? fmaxf(x, 0.f) + __logf(1.f + ex) : 0.f;
                 }
             }
-            if (!PASS_I) { two_sum(loss_hi, loss_lo, tile_loss); two_sum(r_hi, r_lo, tile_r); }
+            two_sum(r_hi, r_lo, tile_r);             // row sums of this pass's G tile: r_i (pass U) / column sums q_j (pass I)
+            if (!PASS_I) two_sum(loss_hi, loss_lo, tile_loss);
             if (WITH_GRAD) {
                 if (pending_g) {                     // G-MMA(t−1) finished under the epilogue: G / Yᵀ buffers free, result in TMEM
                     bar_g.wait();
@@ -324,8 +335,8 @@ __global__ void __launch_bounds__(NT_ALL, 1) inbatch_tc_kernel(const IbParams p)
 #pragma unroll
             for (int q = 0; q < QC / 4; ++q) *reinterpret_cast<float4*>(dst + q * 4) = make_float4(acc[q * 4], acc[q * 4 + 1], acc[q * 4 + 2], acc[q * 4 + 3]);
         }
+        if (WITH_GRAD) p.r_part[((long long)part * NQ + quarter) * p.Bp + gi] = (double)r_hi + (double)r_lo;
         if (!PASS_I) {
-            if (WITH_GRAD) p.r_part[((long long)part * NQ + quarter) * p.Bp + gi] = (double)r_hi + (double)r_lo;
             const double loss_sum = rb_warp_sum_d((double)loss_hi + (double)loss_lo);
             if (lane == 0) red[warp] = loss_sum;
         }
@@ -340,30 +351,35 @@ __global__ void __launch_bounds__(NT_ALL, 1) inbatch_tc_kernel(const IbParams p)
     if (warp == 0) umma::tmem_free(tmem, TMEM_COLS_IB);
 }
 
-// out_i = Σ_parts acc_part[part][i] − r_i · other_i   (pass U also reduces and stores r_i)
+// out_i = Σ_parts acc_part[part][i] − r_i · (other_i − c) + (q_i − r_i) · c   (q = r in pass U, which also stores r_i)
 template <bool PASS_I>
 __global__ void __launch_bounds__(256) inbatch_finish_kernel(const float* __restrict__ acc_part, const double* __restrict__ r_part,
                                                              float* __restrict__ r_total, const float* __restrict__ other,
-                                                             float* __restrict__ out, int B, int Bp, int split) {
+                                                             const float* __restrict__ cen, float* __restrict__ out, int B, int Bp,
+                                                             int split) {
     const int idx = blockIdx.x * 256 + threadIdx.x;
     const int row = idx >> 4, c4 = idx & 15;
     if (row >= B) return;
-    float r;
-    if (!PASS_I) {
-        double rs = 0.0;
-        for (int s = 0; s < split * NQ; ++s) rs += r_part[(long long)s * Bp + row];
-        r = (float)rs;
-        if (c4 == 0) r_total[row] = r;
-    } else {
-        r = r_total[row];
-    }
+    // rs = row sum of this pass's G: r_i in pass U; the column sum q_j = Σ_i G_ij in pass I (whose diagonal term uses r_j)
+    double rs = 0.0;
+    for (int s = 0; s < split * NQ; ++s) rs += r_part[(long long)s * Bp + row];
+    const float q = (float)rs;
+    float r = q;
+    if (!PASS_I) { if (c4 == 0) r_total[row] = r; }
+    else r = r_total[row];
     float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
     for (int s = 0; s < split; ++s) {
         const float4 v = __ldg(reinterpret_cast<const float4*>(acc_part + ((long long)s * Bp + row) * DD) + c4);
         a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
     }
-    const float4 o = __ldg(reinterpret_cast<const float4*>(other + (long long)row * DD) + c4);
+    float4 o = __ldg(reinterpret_cast<const float4*>(other + (long long)row * DD) + c4);
+    const float4 cc = __ldg(reinterpret_cast<const float4*>(cen) + c4);
+    o.x -= cc.x; o.y -= cc.y; o.z -= cc.z; o.w -= cc.w;
     a.x = fmaf(-r, o.x, a.x); a.y = fmaf(-r, o.y, a.y); a.z = fmaf(-r, o.z, a.z); a.w = fmaf(-r, o.w, a.w);
+    if (PASS_I) {                  // Σ_i G_ij c = q_j c, while the diagonal term took r_j c
+        const float dq = q - r;
+        a.x = fmaf(dq, cc.x, a.x); a.y = fmaf(dq, cc.y, a.y); a.z = fmaf(dq, cc.z, a.z); a.w = fmaf(dq, cc.w, a.w);
+    }
     reinterpret_cast<float4*>(out + (long long)row * DD)[c4] = a;
 }
 
@@ -372,6 +388,34 @@ __global__ void inbatch_loss_kernel(const double* __restrict__ partials, int n, 
     for (int i = threadIdx.x; i < n; i += 32) t += partials[i];
     t = rb_warp_sum_d(t);
     if (threadIdx.x == 0) out[0] = (float)(t * scale);
+}
+
+// column means of U (blockIdx.y = 0) and I (1): fixed-order partial sums over CM_BLOCKS row ranges, then one small block
+constexpr int CM_BLOCKS = 64;
+__global__ void __launch_bounds__(256) colsum_partial_kernel(const float* __restrict__ U, const float* __restrict__ I, int B,
+                                                             float* __restrict__ part) {
+    __shared__ float4 red[16][16];
+    const float* X = blockIdx.y ? I : U;
+    const int c4 = threadIdx.x & 15, rg = threadIdx.x >> 4;
+    const int per = (B + CM_BLOCKS - 1) / CM_BLOCKS;
+    const int r0 = blockIdx.x * per, r1 = min(B, r0 + per);
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int r = r0 + rg; r < r1; r += 16) {
+        const float4 v = __ldg(reinterpret_cast<const float4*>(X + (long long)r * DD) + c4);
+        a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+    }
+    red[rg][c4] = a;
+    __syncthreads();
+    if (rg == 0) {
+        for (int k = 1; k < 16; ++k) { const float4 v = red[k][c4]; a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w; }
+        reinterpret_cast<float4*>(part + ((long long)blockIdx.y * CM_BLOCKS + blockIdx.x) * DD)[c4] = a;
+    }
+}
+__global__ void colsum_final_kernel(const float* __restrict__ part, int B, float* __restrict__ cen) {   // <<<1, 128>>>
+    const int which = threadIdx.x >> 6, d = threadIdx.x & 63;
+    float a = 0.f;
+    for (int k = 0; k < CM_BLOCKS; ++k) a += part[((long long)which * CM_BLOCKS + k) * DD + d];
+    cen[which * DD + d] = a / (float)B;
 }
 
 struct IbPlan { int n_xt, n_yt, split, tps, Bp, grid; };
@@ -408,7 +452,7 @@ int launch(const IbParams& p, int grid, cudaStream_t st) {
 size_t rb_inbatch_tc_workspace_bytes(int B, int D) {
     if (D != DD || B < 1) return 0;
     const IbPlan pl = plan(B);
-    return 256 * 8 + sizeof(float) * ((size_t)2 * B + YT) + sizeof(int) + sizeof(float) * (size_t)pl.split * pl.Bp * DD +
+    return 256 * 10 + sizeof(float) * ((size_t)2 * B + YT + 2 * DD + 2 * CM_BLOCKS * DD) + sizeof(int) + sizeof(float) * (size_t)pl.split * pl.Bp * DD +
            sizeof(double) * ((size_t)pl.split * NQ * pl.Bp + pl.grid);
 }
 
@@ -423,6 +467,8 @@ int rb_inbatch_tc(const float* U, const float* I, int B, int D, int mode, float*
     float* diag = ar.take<float>(Bd);
     float* r_total = ar.take<float>(B);
     int* err = ar.take<int>(1);
+    float* cen = ar.take<float>(2 * DD);              // column means: [0] of U, [1] of I
+    float* cen_part = ar.take<float>((size_t)2 * CM_BLOCKS * DD);
     float* acc_part = ar.take<float>((size_t)pl.split * pl.Bp * DD);
     double* r_part = ar.take<double>((size_t)pl.split * NQ * pl.Bp);
     double* loss_part = ar.take<double>(pl.grid);
@@ -436,7 +482,13 @@ int rb_inbatch_tc(const float* U, const float* I, int B, int D, int mode, float*
     (void)err;
     const bool grad = dU != nullptr;
     int rc;
-    p.X = U; p.Y = I;
+    if (grad) {
+        colsum_partial_kernel<<<dim3(CM_BLOCKS, 2), 256, 0, st>>>(U, I, B, cen_part);
+        RB_LAUNCH_CHECK("colsum_partial_kernel");
+        colsum_final_kernel<<<1, 128, 0, st>>>(cen_part, B, cen);
+        RB_LAUNCH_CHECK("colsum_final_kernel");
+    }
+    p.X = U; p.Y = I; p.ycen = cen + DD;
     if (mode == 2) rc = grad ? launch<2, false, true>(p, pl.grid, st) : launch<2, false, false>(p, pl.grid, st);
     else rc = grad ? launch<1, false, true>(p, pl.grid, st) : launch<1, false, false>(p, pl.grid, st);
     if (rc) return rc;
@@ -444,12 +496,12 @@ int rb_inbatch_tc(const float* U, const float* I, int B, int D, int mode, float*
     RB_LAUNCH_CHECK("inbatch_loss_kernel");
     if (!grad) return RB200_OK;
     const int fgrid = (B * 16 + 255) / 256;
-    inbatch_finish_kernel<false><<<fgrid, 256, 0, st>>>(acc_part, r_part, r_total, I, dU, B, pl.Bp, pl.split);
+    inbatch_finish_kernel<false><<<fgrid, 256, 0, st>>>(acc_part, r_part, r_total, I, cen + DD, dU, B, pl.Bp, pl.split);
     RB_LAUNCH_CHECK("inbatch_finish_kernel");
-    p.X = I; p.Y = U;
+    p.X = I; p.Y = U; p.ycen = cen;
     rc = mode == 2 ? launch<2, true, true>(p, pl.grid, st) : launch<1, true, true>(p, pl.grid, st);
     if (rc) return rc;
-    inbatch_finish_kernel<true><<<fgrid, 256, 0, st>>>(acc_part, r_part, r_total, U, dI, B, pl.Bp, pl.split);
+    inbatch_finish_kernel<true><<<fgrid, 256, 0, st>>>(acc_part, r_part, r_total, U, cen, dI, B, pl.Bp, pl.split);
     RB_LAUNCH_CHECK("inbatch_finish_kernel");
     return RB200_OK;
 }

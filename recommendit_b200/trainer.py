@@ -23,7 +23,7 @@ import torch
 
 from . import _lib
 from ._lib import OptState, RB200Error, StepParams, StepViews, check, ptr, require_cuda, stream_ptr
-from .two_tower import INBATCH_MODE, TwoTowerModel
+from .two_tower import TwoTowerModel, inbatch_mode_for
 
 
 def _flat_len(tower) -> int:
@@ -43,7 +43,7 @@ class FusedBPRTrainer:
         if loss not in ("bpr", "in_batch"):
             raise ValueError("loss must be 'bpr' or 'in_batch'")
         self.adam_mode, self.loss_kind = adam_mode, (0 if loss == "bpr" else 1)
-        self.inbatch_mode = INBATCH_MODE if inbatch_mode is None else int(inbatch_mode)
+        self.inbatch_mode = inbatch_mode          # None → auto (tcgen05 3xTF32 where built), resolved per batch size
         self.use_graph = use_cuda_graph
         from .two_tower import tower_mode_for
         self.tower_mode = tower_mode_for(model.embed_dim, model.user_tower.mlp[0].out_features, model.item_tower.extra_dim, tower_mode)
@@ -172,7 +172,7 @@ class FusedBPRTrainer:
         p.user_ids, p.pos_ids, p.neg_ids = ptr(self.user_ids), ptr(self.pos_ids), ptr(self.neg_ids)
         p.pos_extra, p.neg_extra = ptr(self.pos_extra), ptr(self.neg_extra)
         p.extra_by_id = 1 if self.item_extra_table is not None else 0
-        p.loss_kind, p.inbatch_mode = self.loss_kind, self.inbatch_mode
+        p.loss_kind, p.inbatch_mode = self.loss_kind, inbatch_mode_for(self._B, self.D, self.inbatch_mode)
         p.tower_mode = self.tower_mode
         p.adam_mode = 0 if self.adam_mode == "dense" else 1
         p.dropout_p = m.user_tower.dropout_p if m.training else 0.0

@@ -48,8 +48,16 @@ def tower_mode_for(D: int, H: int, E: int, mode=None) -> int:
     return int(mode)
 
 
-#: precision mode of the in-batch score GEMM: 0 = fp32 FFMA (parity), 1 = tcgen05 TF32, 2 = tcgen05 3xTF32
-INBATCH_MODE = int(os.environ.get("RB200_INBATCH_MODE", "0"))
+#: in-batch BPR kernel: 0 = fp32 FFMA (SIMT), 1 = tcgen05 TF32 (stated fast mode), 2 = tcgen05 3xTF32 (fp32-grade);
+#: "auto" = 2 where the tensor-core kernel is built (D = 64, B >= 2), else 0
+INBATCH_MODE = os.environ.get("RB200_INBATCH_MODE", "auto")
+
+
+def inbatch_mode_for(B: int, D: int, mode=None) -> int:
+    mode = INBATCH_MODE if mode is None else mode
+    if str(mode) == "auto":
+        return 2 if (D == 64 and B >= 2) else 0
+    return int(mode)
 
 
 def _f32c(t: torch.Tensor) -> torch.Tensor:
@@ -272,7 +280,7 @@ class TwoTowerModel(nn.Module):
         return _BprPairFn.apply(user_emb, pos_item_emb, neg_item_emb)
 
     def in_batch_bpr_loss(self, user_emb, item_emb, mode: Optional[int] = None) -> torch.Tensor:
-        return _BprInBatchFn.apply(user_emb, item_emb, INBATCH_MODE if mode is None else mode)
+        return _BprInBatchFn.apply(user_emb, item_emb, inbatch_mode_for(user_emb.shape[0], user_emb.shape[1], mode))
 
     # -- inference helpers (two_tower.py:166-210) ------------------------------------------ #
     def _device(self) -> torch.device:

@@ -61,6 +61,20 @@ def test_inbatch_correlated_embeddings():
     assert rel_l2(dU, rU) <= 1e-5 and rel_l2(dI, rI) <= 1e-5
 
 
+def test_inbatch_untrained_regime_all_embeddings_alike():
+    """Untrained towers: every embedding is close to one common direction, so dU = Σ_j G_ij I_j − r_i I_i is a small
+    difference of large terms — the kernel centres the second product to keep fp32-grade accuracy."""
+    rng = np.random.default_rng(21)
+    B = 600
+    base = rng.standard_normal(64)
+    U = base + 0.05 * rng.standard_normal((B, 64)); U /= np.linalg.norm(U, axis=1, keepdims=True)
+    I = base + 0.05 * rng.standard_normal((B, 64)); I /= np.linalg.norm(I, axis=1, keepdims=True)
+    loss, dU, dI = _run(U, I, 2)
+    l64, rU, rI = O.in_batch_bpr_loss(U, I)
+    assert abs(loss - float(l64)) <= 1e-6
+    assert rel_l2(dU, rU) <= 1e-5 and rel_l2(dI, rI) <= 1e-5
+
+
 def test_inbatch_tf32_fast_mode_stated_bound():
     """mode 1 = one TF32 pass per product: operands rounded to 10 mantissa bits (stated fast mode, not the parity mode)."""
     rng = np.random.default_rng(11)

@@ -142,10 +142,12 @@ def test_cuda_graph_replay_equals_eager_and_is_deterministic(golden):
             assert torch.equal(sd[k], runs[0][1][k]), k
 
 
-def test_in_batch_step_matches_oracle(golden):
+@pytest.mark.parametrize("inbatch_mode,graph", [(0, False), (2, False), (None, True)])
+def test_in_batch_step_matches_oracle(golden, inbatch_mode, graph):
+    """in_batch_bpr_loss step: SIMT kernel, tcgen05 3xTF32 kernel, and the default (auto → tcgen05) under a CUDA graph."""
     g = golden("tt_dup")
     model = model_from_golden(g).train()
-    tr = _trainer(model, g, loss="in_batch", inbatch_mode=0, use_cuda_graph=False)
+    tr = _trainer(model, g, loss="in_batch", inbatch_mode=inbatch_mode, use_cuda_graph=graph)
     b = batch_from_golden(g, 0)
     tr.load_packed(tr.pack_host(*b))
     loss = tr.step().item()
