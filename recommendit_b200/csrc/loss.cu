@@ -309,18 +309,18 @@ extern "C" size_t rb200_bpr_pair_workspace_bytes(int B) {
 // `st_fin` after `fork` (both may be NULL/equal to st: plain sequential).  csrc/step.cu passes its side stream so the
 // reduction leaves the critical path of the training step.
 int rb_bpr_pair(const float* u, const float* p, const float* n, int B, int D, float* loss, float* du, float* dp, float* dn,
-                float grad_scale, void* workspace, size_t workspace_bytes, rb200_opt_state* opt, cudaStream_t st,
+                float grad_scale, float loss_scale, void* workspace, size_t workspace_bytes, rb200_opt_state* opt, cudaStream_t st,
                 cudaStream_t st_fin, cudaEvent_t fork);
 
 extern "C" int rb200_bpr_pair(const float* u, const float* p, const float* n, int B, int D, float* loss, float* du,
                               float* dp, float* dn, float grad_scale, void* workspace, size_t workspace_bytes,
                               void* stream) {
-    return rb_bpr_pair(u, p, n, B, D, loss, du, dp, dn, grad_scale, workspace, workspace_bytes, nullptr, (cudaStream_t)stream,
+    return rb_bpr_pair(u, p, n, B, D, loss, du, dp, dn, grad_scale, 1.f, workspace, workspace_bytes, nullptr, (cudaStream_t)stream,
                        (cudaStream_t)stream, nullptr);
 }
 
 int rb_bpr_pair(const float* u, const float* p, const float* n, int B, int D, float* loss, float* du, float* dp, float* dn,
-                float grad_scale, void* workspace, size_t workspace_bytes, rb200_opt_state* opt, cudaStream_t st,
+                float grad_scale, float loss_scale, void* workspace, size_t workspace_bytes, rb200_opt_state* opt, cudaStream_t st,
                 cudaStream_t st_fin, cudaEvent_t fork) {
     RB_REQUIRE(u && p && n && loss && B >= 1 && D >= 1, "bpr_pair: bad arguments");
     RB_REQUIRE((du == nullptr) == (dp == nullptr) && (du == nullptr) == (dn == nullptr), "bpr_pair: du/dp/dn must be all set or all NULL");
@@ -336,7 +336,7 @@ int rb_bpr_pair(const float* u, const float* p, const float* n, int B, int D, fl
         RB_CUDA(cudaEventRecord(fork, st));
         RB_CUDA(cudaStreamWaitEvent(st_fin, fork, 0));
     }
-    finalize_sum_kernel<<<1, 32, 0, st_fin>>>(partials, grid, 1.0 / (double)B, loss, opt);
+    finalize_sum_kernel<<<1, 32, 0, st_fin>>>(partials, grid, (double)loss_scale / (double)B, loss, opt);
     RB_LAUNCH_CHECK("finalize_sum_kernel");
     return RB200_OK;
 }

@@ -22,7 +22,7 @@ int rb_adam_step_all(float* const mlp_w[2], const float* const mlp_g[2], float* 
                      const long long tab_rows[2], int* const slot[2], const float* const ug[2], int D, const rb200_opt_state* st,
                      cudaStream_t s);
 int rb_bpr_pair(const float* u, const float* p, const float* n, int B, int D, float* loss, float* du, float* dp, float* dn,
-                float grad_scale, void* workspace, size_t workspace_bytes, rb200_opt_state* opt, cudaStream_t st,
+                float grad_scale, float loss_scale, void* workspace, size_t workspace_bytes, rb200_opt_state* opt, cudaStream_t st,
                 cudaStream_t st_fin, cudaEvent_t fork);
 int rb_reset_slots2(const int64_t* ids0, const int* n0, int cap0, int* slot0, const int64_t* ids1, const int* n1, int cap1, int* slot1,
                     cudaStream_t s);
@@ -99,8 +99,9 @@ int side_stream(SideStream** out) {
     return RB200_OK;
 }
 
-__global__ void copy_loss_kernel(const float* loss, rb200_opt_state* st) {
-    if (threadIdx.x == 0 && blockIdx.x == 0) st->loss = loss[0];
+// (data-parallel mode: the loss is pre-scaled by 1/world like the gradients, so that one SUM all-reduce yields the mean)
+__global__ void copy_loss_kernel(float* loss, rb200_opt_state* st, float scale) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) { loss[0] *= scale; st->loss = loss[0]; }
 }
 
 int check(const rb200_step_params* s) {
@@ -232,12 +233,12 @@ extern "C" int rb200_bpr_step(const rb200_step_params* s, void* stream) {
     // ---- loss + gradient w.r.t. the tower outputs ------------------------------------------- //
     // (pairwise: the scalar reduction of the loss goes to the side stream — nothing downstream needs it before the join)
     if (pair) {
-        rc = rb_bpr_pair(w.u, w.p, w.n, B, D, s->loss, w.du, w.dpn, w.dpn + (size_t)B * D, gscale, w.ws_loss, w.b_loss, s->opt, st,
-                         side->s, side->fork2);
+        rc = rb_bpr_pair(w.u, w.p, w.n, B, D, s->loss, w.du, w.dpn, w.dpn + (size_t)B * D, gscale, dp ? gscale : 1.f, w.ws_loss, w.b_loss,
+                         s->opt, st, side->s, side->fork2);
         if (rc) return rc;
     } else {
         if ((rc = rb200_bpr_inbatch(w.u, w.p, B, D, s->inbatch_mode, s->loss, w.du, w.dpn, gscale, w.ws_loss, w.b_loss, st))) return rc;
-        copy_loss_kernel<<<1, 32, 0, st>>>(s->loss, s->opt);
+        copy_loss_kernel<<<1, 32, 0, st>>>(s->loss, s->opt, dp ? gscale : 1.f);
         RB_LAUNCH_CHECK("copy_loss_kernel");
         RB_CUDA(cudaEventRecord(side->fork2, st));
         RB_CUDA(cudaStreamWaitEvent(side->s, side->fork2, 0));

@@ -15,6 +15,7 @@ the autograd path in ``two_tower.py``.  This class is the alternative trainer fo
 from __future__ import annotations
 
 import ctypes as C
+import os
 import math
 from typing import Dict, Optional
 
@@ -322,14 +323,17 @@ class DataParallelBPRTrainer(FusedBPRTrainer):
                 dist.broadcast(p.data, src=0, group=group)
             self._flatten()
         n = self.lib.rb200_bpr_dp_grad_floats(self.D, self.H, self.E, model.n_users + 1, model.n_items + 1)
-        self.dp_grads = torch.zeros(n, dtype=torch.float32, device=self.dev)
-        self.loss_sum = torch.zeros(1, dtype=torch.float32, device=self.dev)
+        # dense gradients + one trailing float for the loss (pre-scaled by 1/world on the device): ONE all-reduce per step
+        self._dp_buf = torch.zeros(n + 4, dtype=torch.float32, device=self.dev)
+        self.dp_grads = self._dp_buf[:n]
+        self.loss_sum = self._dp_buf[n:n + 1]
         self._graph_b = None
 
     def _make_params(self) -> StepParams:
         p = super()._make_params()
         p.grad_scale = 1.0 / self.world
         p.dp_grads = ptr(self.dp_grads)
+        p.loss = ptr(self.loss_sum)
         return p
 
     def _phase(self, which: int) -> None:
@@ -340,6 +344,12 @@ class DataParallelBPRTrainer(FusedBPRTrainer):
         self._params = p
         fn = self.lib.rb200_bpr_step if which == 0 else self.lib.rb200_bpr_apply
         check(fn(C.byref(p), stream_ptr()), "rb200_bpr_step" if which == 0 else "rb200_bpr_apply")
+
+    def _whole(self) -> None:
+        self._phase(0)
+        if self.world > 1:
+            self.dist.all_reduce(self._dp_buf, group=self.group)
+        self._phase(1)
 
     def step(self, masks=None) -> torch.Tensor:
         """Returns the device scalar holding the GLOBAL mean loss."""
@@ -359,18 +369,11 @@ class DataParallelBPRTrainer(FusedBPRTrainer):
                 self._graph_b = g2
             if use_graph:
                 self._graph.replay()
-            else:
-                self._phase(0)
-            if self.world > 1:
-                self.dist.all_reduce(self.dp_grads, group=self.group)
-                self.loss_sum.copy_(self.loss_dev).div_(self.world)
-                self.dist.all_reduce(self.loss_sum, group=self.group)
-            else:
-                self.loss_sum.copy_(self.loss_dev)
-            if use_graph:
+                if self.world > 1:
+                    self.dist.all_reduce(self._dp_buf, group=self.group)
                 self._graph_b.replay()
             else:
-                self._phase(1)
+                self._whole()
             self._warm_key = key
         self._steps_done += 1
         return self.loss_sum
