@@ -247,6 +247,56 @@ class FusedBPRTrainer:
         self.load_packed(self.pack_host(user_ids, pos_ids, pos_genres, neg_ids, neg_genres))
         return float(self.step().item())
 
+    def train_epoch(self, packed_batches) -> float:
+        """The reference's ``train_epoch`` loop (train_embeddings.py:170-199) over an iterable of PINNED packed host batches
+        (``pack_host(...).pin_memory()``), pipelined: the host→device copy of batch i+1 runs on a copy stream while batch i
+        computes, and each step's loss is copied back asynchronously into a pinned array (one 4-byte D2H per step) that
+        is summed once at the end — the same per-batch traffic as ``step_host`` without a host synchronisation per step.
+        Returns the mean loss over the batches, like the reference."""
+        with torch.cuda.device(self.dev):
+            main = torch.cuda.current_stream(self.dev)
+            if getattr(self, "_copy_stream", None) is None:
+                self._copy_stream = torch.cuda.Stream(self.dev)
+                self._stage = [None, None]
+                self._stage_ready = [torch.cuda.Event(), torch.cuda.Event()]
+                self._stage_free = [torch.cuda.Event(), torch.cuda.Event()]
+            it = iter(packed_batches)
+            losses_host = None
+            n = 0
+
+            def prefetch(k, batch):
+                if self._stage[k] is None or self._stage[k].shape != batch.shape:
+                    self._stage[k] = torch.empty(batch.shape, dtype=batch.dtype, device=self.dev)
+                with torch.cuda.stream(self._copy_stream):
+                    self._copy_stream.wait_event(self._stage_free[k])
+                    self._stage[k].copy_(batch, non_blocking=True)
+                    self._stage_ready[k].record(self._copy_stream)
+
+            for k in (0, 1):
+                self._stage_free[k].record(main)
+            nxt = next(it, None)
+            if nxt is not None:
+                prefetch(0, nxt)
+            while nxt is not None:
+                k = n & 1
+                cur, nxt = nxt, next(it, None)
+                if nxt is not None:
+                    prefetch(k ^ 1, nxt)
+                main.wait_event(self._stage_ready[k])
+                self.batch_dev.copy_(self._stage[k], non_blocking=True)       # device→device into the graph's static buffer
+                self._stage_free[k].record(main)
+                loss = self.step()
+                if losses_host is None or n >= losses_host.numel():
+                    grown = torch.zeros(max(1024, 2 * n), dtype=torch.float32).pin_memory()
+                    if losses_host is not None:
+                        main.synchronize()
+                        grown[:n] = losses_host[:n]
+                    losses_host = grown
+                losses_host[n:n + 1].copy_(loss, non_blocking=True)
+                n += 1
+            main.synchronize()
+        return float(losses_host[:n].double().mean()) if n else float("nan")
+
     def check_ids(self) -> None:
         if int(self.err_flag.item()) != 0:
             raise IndexError("an id in a previous batch was outside its embedding table (torch would raise "

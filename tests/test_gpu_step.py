@@ -256,3 +256,25 @@ def test_scatter_rows_large_batches_vs_oracle(B, n_rows, D):
     assert np.array_equal(slot.cpu().numpy()[exp_ids], np.arange(n))
     if dense is not None:
         assert rel_l2(dense.cpu().numpy(), ref) <= 1e-6 and torch.count_nonzero(dense[0]) == 0
+
+
+def test_train_epoch_pipelined_equals_step_host_loop(golden):
+    """train_epoch (H2D prefetch on a copy stream, async loss read-back) must produce exactly the parameters and the mean
+    loss of the synchronous per-step loop (train_embeddings.py:170-199) on the same batches."""
+    g = golden("tt_dup")
+    rng = np.random.default_rng(0)
+    nu, ni, B = int(g["meta"][0]), int(g["meta"][1]), 256
+
+    def batch():
+        return (rng.integers(0, nu + 1, B), rng.integers(0, ni + 1, B), (rng.random((B, 18)) < 0.2).astype(np.float32),
+                rng.integers(0, ni + 1, B), (rng.random((B, 18)) < 0.2).astype(np.float32))
+    batches = [batch() for _ in range(7)]
+    m1, m2 = model_from_golden(g).train(), model_from_golden(g).train()
+    t1, t2 = _trainer(m1, g, seed=5), _trainer(m2, g, seed=5)
+    losses = [t1.step_host(*b) for b in batches]
+    packed = [t2.pack_host(*b).clone().pin_memory() for b in batches]
+    mean = t2.train_epoch(packed)
+    assert abs(mean - float(np.mean(losses))) <= 1e-7
+    for (k, a), (_, b) in zip(m1.state_dict().items(), m2.state_dict().items()):
+        assert torch.equal(a, b), k
+    assert np.isnan(t2.train_epoch([]))
