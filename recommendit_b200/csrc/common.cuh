@@ -94,3 +94,15 @@ __device__ __forceinline__ uint4 rb_philox4x32(uint4 ctr, uint2 key) {
 __device__ __forceinline__ float rb_u01(uint32_t x) { return (x >> 8) * (1.0f / 16777216.0f); }
 
 #endif  // __CUDACC__
+
+// per-step constants of Adam (bias corrections, step size) and reset of the grad-norm accumulator; one thread
+__device__ __forceinline__ void rb_opt_begin_step_dev(rb200_opt_state* st) {
+    const long long step = st->step + 1;
+    st->step = step;
+    const double bc1 = 1.0 - pow(st->beta1, (double)step);
+    const double bc2 = 1.0 - pow(st->beta2, (double)step);
+    st->step_size = (float)(st->lr / bc1);
+    st->bias_corr2_sqrt = (float)sqrt(bc2);
+    st->sumsq = 0.0;
+    st->ticket = 0u;
+}

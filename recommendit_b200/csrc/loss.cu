@@ -302,7 +302,7 @@ int launch_inbatch(const float* U, const float* I, int B, const float* diag, flo
 
 extern "C" size_t rb200_bpr_pair_workspace_bytes(int B) {
     (void)B;
-    return 256 + sizeof(double) * (size_t)(rb_sm_count() * 2);
+    return 256 + sizeof(double) * (size_t)(rb_sm_count() * 8);
 }
 
 // The gradient kernel runs on `st`; the loss reduction (block partials → loss, optionally also opt->loss) runs on
@@ -325,7 +325,7 @@ int rb_bpr_pair(const float* u, const float* p, const float* n, int B, int D, fl
     RB_REQUIRE(u && p && n && loss && B >= 1 && D >= 1, "bpr_pair: bad arguments");
     RB_REQUIRE((du == nullptr) == (dp == nullptr) && (du == nullptr) == (dn == nullptr), "bpr_pair: du/dp/dn must be all set or all NULL");
     int grid = (B + NT / 32 - 1) / (NT / 32);
-    const int cap = rb_sm_count() * 2;
+    const int cap = rb_sm_count() * 8;          // 8192 samples → one sample per warp, every warp resident at once
     if (grid > cap) grid = cap;
     RbArena ar(workspace, workspace_bytes);
     double* partials = ar.take<double>(cap);

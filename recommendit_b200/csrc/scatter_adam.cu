@@ -186,14 +186,15 @@ struct SegParams { SegJob job[2]; int n_jobs; int D4; };
 // (most segments of a large batch have length 1, so this keeps SEG_PER_WARP independent 16·D4-byte row reads in
 // flight per warp instead of one at the end of a seg_start → pos → row dependency chain).  Rows are added in ascending
 // sample order (deterministic).
-constexpr int SEG_PER_WARP = 8;
+template <int SEG_PER_WARP>
 __host__ __device__ inline int seg_warps(int cap) { return (cap + SEG_PER_WARP - 1) / SEG_PER_WARP; }
 
+template <int SEG_PER_WARP>
 __global__ void __launch_bounds__(NT) segment_sum2_kernel(const SegParams p) {
     int w = (blockIdx.x * NT + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     int j = 0;
-    if (p.n_jobs > 1 && w >= seg_warps(p.job[0].cap)) { w -= seg_warps(p.job[0].cap); j = 1; }
+    if (p.n_jobs > 1 && w >= seg_warps<SEG_PER_WARP>(p.job[0].cap)) { w -= seg_warps<SEG_PER_WARP>(p.job[0].cap); j = 1; }
     const SegJob& J = p.job[j];
     const int n = J.n_uniq[0];
     const int w0 = w * SEG_PER_WARP;
@@ -320,14 +321,7 @@ size_t sort_temp_bytes(int B, int bits) {
 // ---------------------------------------------------------------------------------------- //
 __global__ void opt_begin_step_kernel(rb200_opt_state* st) {
     if (threadIdx.x || blockIdx.x) return;
-    const long long step = st->step + 1;
-    st->step = step;
-    const double bc1 = 1.0 - pow(st->beta1, (double)step);
-    const double bc2 = 1.0 - pow(st->beta2, (double)step);
-    st->step_size = (float)(st->lr / bc1);
-    st->bias_corr2_sqrt = (float)sqrt(bc2);
-    st->sumsq = 0.0;
-    st->ticket = 0u;
+    rb_opt_begin_step_dev(st);
 }
 
 struct SumsqSegs { rb200_sumsq_seg s[4]; int n; };
@@ -615,9 +609,10 @@ static int scatter_sort(const ScatterPlan& pl, cudaStream_t st) {
 }
 
 static int scatter_sum(const ScatterPlan& pl, cudaStream_t st) {
+    // small batches (the fused step): one segment per warp keeps every SM busy; see the large-batch path for 8 per warp
     long long warps = 0;
-    for (int t = 0; t < pl.gp.n_jobs; ++t) warps += seg_warps(pl.gp.job[t].cap);
-    segment_sum2_kernel<<<(unsigned)((warps * 32 + NT - 1) / NT), NT, 0, st>>>(pl.gp);
+    for (int t = 0; t < pl.gp.n_jobs; ++t) warps += seg_warps<1>(pl.gp.job[t].cap);
+    segment_sum2_kernel<1><<<(unsigned)((warps * 32 + NT - 1) / NT), NT, 0, st>>>(pl.gp);
     RB_LAUNCH_CHECK("segment_sum2_kernel");
     return RB200_OK;
 }
@@ -695,7 +690,7 @@ extern "C" int rb200_scatter_rows(const int64_t* ids, const float* rows, int B, 
         SegParams gp{};
         gp.n_jobs = 1; gp.D4 = D / 4;
         gp.job[0] = SegJob{p_out, seg_start, u_ids, n_u, rows, uniq_grads, dense_grad, B, first_pos};
-        segment_sum2_kernel<<<(unsigned)(((long long)seg_warps(B) * 32 + NT - 1) / NT), NT, 0, st>>>(gp);
+        segment_sum2_kernel<8><<<(unsigned)(((long long)seg_warps<8>(B) * 32 + NT - 1) / NT), NT, 0, st>>>(gp);
         RB_LAUNCH_CHECK("segment_sum2_kernel");
         return RB200_OK;
     }

@@ -10,7 +10,7 @@ int rb_scatter_tables(int phase, int n_tables, const int64_t* const ids_a[2], co
 int rb_sumsq_accumulate(rb200_opt_state* st, const rb200_sumsq_seg* segs, int n_segs, int do_clip, void* workspace,
                         size_t workspace_bytes, cudaStream_t s);
 int rb_tower_prep_tc(int n_sets, const float* const W1[], const float* const W2[], const int E[], int D, int H,
-                     unsigned char* const img[], cudaStream_t st);
+                     unsigned char* const img[], rb200_opt_state* opt, cudaStream_t st);
 size_t rb_tower_img_bytes(int D, int H, int E);
 bool rb_tower_tc_supported(int D, int H, int E);
 int rb_adam_dense2(float* w0, const float* g0, float* m0, float* v0, long long n0, float* w1, const float* g1, float* m1, float* v1,
@@ -170,7 +170,8 @@ extern "C" int rb200_bpr_step(const rb200_step_params* s, void* stream) {
         ++ev_i;                                                                            \
     } while (0)
     RB_STAGE_EVENT();
-    if ((rc = rb200_opt_begin_step(s->opt, st))) return rc;
+    const bool tc = s->tower_mode != 0;
+    if (!tc && (rc = rb200_opt_begin_step(s->opt, st))) return rc;      // (tensor-core modes: done by the weight-image kernel)
 
     // ---- fork: the (id, sample) sort needs only the ids, so it runs on a side stream under the towers ------- //
     const bool dense = s->adam_mode == 0;
@@ -199,14 +200,13 @@ extern "C" int rb200_bpr_step(const rb200_step_params* s, void* stream) {
     }
 
     // ---- tensor-core modes: stage both towers' weight images once for forward and backward ----------- //
-    const bool tc = s->tower_mode != 0;
     if (tc) {
         RB_REQUIRE(rb_tower_tc_supported(D, H, E), "bpr_step: tower_mode %d needs D=64, H=128, extra_dim<=24", s->tower_mode);
         const float* pw1[2] = {s->user_mlp, s->item_mlp};
         const float* pw2[2] = {s->user_mlp + H * D + H, s->item_mlp + H * Din_i + H};
         const int pe[2] = {0, E};
         unsigned char* pim[2] = {w.img_user, w.img_item};
-        if ((rc = rb_tower_prep_tc(2, pw1, pw2, pe, D, H, pim, st))) return rc;
+        if ((rc = rb_tower_prep_tc(2, pw1, pw2, pe, D, H, pim, s->opt, st))) return rc;
     }
 
     // ---- forward: user / positive / negative towers in one launch -------------------------- //

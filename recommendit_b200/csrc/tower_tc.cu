@@ -40,7 +40,7 @@ __host__ __device__ inline ImgLayout img_layout(int D, int H, int E) {
 }
 
 struct PrepSet { const float* W1; const float* W2; unsigned char* img; int E; };
-struct PrepParams { PrepSet set[2]; int n_sets, D, H; };
+struct PrepParams { PrepSet set[2]; int n_sets, D, H; rb200_opt_state* opt; };   // opt != NULL: also begin the optimizer step
 
 __device__ __forceinline__ void put4_both(unsigned char* hi_base, size_t lo_delta, int R, int r, int k, const float4& v) {
     const uint32_t off = umma::kmajor_offset(R, r, k);
@@ -51,6 +51,7 @@ __device__ __forceinline__ void put4_both(unsigned char* hi_base, size_t lo_delt
 }
 
 __global__ void __launch_bounds__(256) tower_prep_kernel(const PrepParams p) {
+    if (p.opt && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) rb_opt_begin_step_dev(p.opt);
     const PrepSet S = p.set[blockIdx.y];
     const int D = p.D, H = p.H, Din = D + S.E;
     const ImgLayout L = img_layout(D, H, S.E);
@@ -663,10 +664,10 @@ size_t rb_tower_img_bytes(int D, int H, int E) { return rb_align_up(img_layout(D
 
 // builds the weight images of up to 2 weight sets in one launch
 int rb_tower_prep_tc(int n_sets, const float* const W1[], const float* const W2[], const int E[], int D, int H,
-                     unsigned char* const img[], cudaStream_t st) {
+                     unsigned char* const img[], rb200_opt_state* opt, cudaStream_t st) {
     RB_REQUIRE(n_sets >= 1 && n_sets <= 2, "tower_prep: 1 or 2 weight sets");
     PrepParams p{};
-    p.n_sets = n_sets; p.D = D; p.H = H;
+    p.n_sets = n_sets; p.D = D; p.H = H; p.opt = opt;
     for (int i = 0; i < n_sets; ++i) {
         RB_REQUIRE(W1[i] && W2[i] && img[i], "tower_prep: NULL pointer");
         RB_REQUIRE((reinterpret_cast<uintptr_t>(img[i]) & 15) == 0, "tower_prep: image must be 16-byte aligned");
@@ -683,7 +684,7 @@ extern "C" int rb200_tower_prep(const float* W1, const float* W2, int D, int H, 
     RB_REQUIRE(rb_tower_tc_supported(D, H, extra_dim), "tower_prep: tensor-core modes cover D=64, H=128, extra_dim<=24");
     const float* w1[1] = {W1}; const float* w2[1] = {W2}; const int e[1] = {extra_dim};
     unsigned char* im[1] = {(unsigned char*)img};
-    return rb_tower_prep_tc(1, w1, w2, e, D, H, im, (cudaStream_t)stream);
+    return rb_tower_prep_tc(1, w1, w2, e, D, H, im, nullptr, (cudaStream_t)stream);
 }
 
 // jobs whose img is NULL get their image built into the workspace (jobs sharing W1 share the image)
@@ -705,7 +706,7 @@ int rb_tower_fwd_tc(FwdParams& p, int D, int H, int mode, void* workspace, size_
     }
     if (n_sets) {
         if (!workspace || !ar.ok()) return rb_set_error(RB200_ERR_WORKSPACE, "tower_fwd (tcgen05): workspace too small for the weight images");
-        int rc = rb_tower_prep_tc(n_sets, w1, w2, es, D, H, im, st);
+        int rc = rb_tower_prep_tc(n_sets, w1, w2, es, D, H, im, nullptr, st);
         if (rc) return rc;
     }
     const int grid = assign_tiles(p.job, p.n_jobs);
@@ -734,7 +735,7 @@ int rb_tower_bwd_tc(BwdParams& p, int D, int H, int mode, float* grads_out, int 
         RB_REQUIRE(img_ws, "tower_bwd (tcgen05): no weight image and no workspace for one");
         const float* w1[1] = {p.job[0].W1}; const float* w2[1] = {p.job[0].W2}; const int e[1] = {E};
         unsigned char* im[1] = {img_ws};
-        int rc = rb_tower_prep_tc(1, w1, w2, e, D, H, im, st);
+        int rc = rb_tower_prep_tc(1, w1, w2, e, D, H, im, nullptr, st);
         if (rc) return rc;
         for (int j = 0; j < p.n_jobs; ++j) p.job[j].img = img_ws;
     }
