@@ -79,6 +79,11 @@ def all_to_all_var(send: torch.Tensor, send_counts: List[int], recv_counts: List
     return out
 
 
+# positions of rb200_opt_state fields (include/rb200.h) in float64 / float32 views of the 128-byte state
+_OPT_SUMSQ_F64 = OptState.sumsq.offset // 8
+_OPT_LOSS_F32 = OptState.loss.offset // 4
+
+
 # --------------------------------------------------------------------------------------------------------- #
 # arithmetic back end over the C ABI
 # --------------------------------------------------------------------------------------------------------- #
@@ -163,6 +168,10 @@ class CudaOps:
     def begin_step(self, opt: torch.Tensor) -> None:
         check(self.lib.rb200_opt_begin_step(ptr(opt), stream_ptr()), "rb200_opt_begin_step")
 
+    def grad_norm_clip(self, opt: torch.Tensor) -> None:
+        """total_norm = sqrt(opt.sumsq); clip_coef = min(1, max_norm / (total_norm + 1e-6)) — on the device"""
+        check(self.lib.rb200_grad_norm_clip(ptr(opt), stream_ptr()), "rb200_grad_norm_clip")
+
     def adam_dense(self, w, g, m, v, opt) -> None:
         check(self.lib.rb200_adam_dense(ptr(w), ptr(g), ptr(m), ptr(v), w.numel(), ptr(opt), stream_ptr()), "rb200_adam_dense")
 
@@ -205,10 +214,15 @@ class ShardedBPRTrainer:
         f32 = dict(dtype=torch.float32, device=self.dev)
         W, r = self.world, self.rank
         nu, ni = shard_rows(self.n_user_rows, W, r), shard_rows(self.n_item_rows, W, r)
+        # Both shards live in ONE tensor (user rows first, then item rows): a request is a row of the combined shard, so
+        # one exchange / gather / scatter / Adam launch serves both tables.  user_table / item_table are views.
+        self.table = torch.empty(nu + ni, embed_dim, **f32)
+        self.user_table, self.item_table = self.table[:nu], self.table[nu:]
+        self._nu_by_rank = torch.tensor([shard_rows(self.n_user_rows, W, k) for k in range(W)], dtype=torch.int64, device=self.dev)
         if init is not None:
             # parity runs: slice a full (single-process) state dict
-            self.user_table = init["user_tower.embedding.weight"][r::W].to(**f32).contiguous()
-            self.item_table = init["item_tower.embedding.weight"][r::W].to(**f32).contiguous()
+            self.user_table.copy_(init["user_tower.embedding.weight"][r::W])
+            self.item_table.copy_(init["item_tower.embedding.weight"][r::W])
             flat = lambda t: torch.cat([init[f"{t}_tower.mlp.0.weight"].reshape(-1), init[f"{t}_tower.mlp.0.bias"].reshape(-1),
                                         init[f"{t}_tower.mlp.3.weight"].reshape(-1), init[f"{t}_tower.mlp.3.bias"].reshape(-1)])
             self.user_mlp, self.item_mlp = flat("user").to(**f32).contiguous(), flat("item").to(**f32).contiguous()
@@ -217,8 +231,8 @@ class ShardedBPRTrainer:
             # U(±1/√fan_in) Linear layers); MLPs use one seed on every rank (replicated), tables a per-rank seed
             g = torch.Generator(device=self.dev).manual_seed(seed * 1000 + 17 + r)
             a_u, a_i = math.sqrt(6.0 / (self.n_user_rows + embed_dim)), math.sqrt(6.0 / (self.n_item_rows + embed_dim))
-            self.user_table = (torch.rand(nu, embed_dim, generator=g, **f32) * 2 - 1) * a_u
-            self.item_table = (torch.rand(ni, embed_dim, generator=g, **f32) * 2 - 1) * a_i
+            self.user_table.copy_((torch.rand(nu, embed_dim, generator=g, **f32) * 2 - 1) * a_u)
+            self.item_table.copy_((torch.rand(ni, embed_dim, generator=g, **f32) * 2 - 1) * a_i)
             g2 = torch.Generator(device=self.dev).manual_seed(seed * 1000 + 3)
 
             def mlp(din):
@@ -228,10 +242,11 @@ class ShardedBPRTrainer:
                          (torch.rand(embed_dim, generator=g2, **f32) * 2 - 1) / math.sqrt(hidden_dim)]
                 return torch.cat(parts).contiguous()
             self.user_mlp, self.item_mlp = mlp(embed_dim), mlp(embed_dim + n_genres)
-        self.state = {k: torch.zeros_like(getattr(self, k)) for k in ("user_table", "item_table", "user_mlp", "item_mlp")}
-        self.state_v = {k: torch.zeros_like(getattr(self, k)) for k in ("user_table", "item_table", "user_mlp", "item_mlp")}
-        self.user_slot = torch.full((max(nu, 1),), -1, dtype=torch.int32, device=self.dev) if adam_mode == "dense" else None
-        self.item_slot = torch.full((max(ni, 1),), -1, dtype=torch.int32, device=self.dev) if adam_mode == "dense" else None
+        self.state = {k: torch.zeros_like(getattr(self, k)) for k in ("table", "user_mlp", "item_mlp")}
+        self.state_v = {k: torch.zeros_like(getattr(self, k)) for k in ("table", "user_mlp", "item_mlp")}
+        for d in (self.state, self.state_v):
+            d["user_table"], d["item_table"] = d["table"][:nu], d["table"][nu:]
+        self.slot = torch.full((max(nu + ni, 1),), -1, dtype=torch.int32, device=self.dev) if adam_mode == "dense" else None
         st = OptState()
         st.lr, st.beta1, st.beta2, st.eps, st.weight_decay, st.max_norm = lr, betas[0], betas[1], eps, weight_decay, max_norm
         st.one_minus_beta1, st.one_minus_beta2, st.beta2_f, st.clip_coef = 1 - betas[0], 1 - betas[1], betas[1], 1.0
@@ -251,33 +266,42 @@ class ShardedBPRTrainer:
         b2 = flat[o:o + D]
         return W1, b1, W2, b2
 
-    def _fetch(self, table: torch.Tensor, ids: torch.Tensor):
-        """steps 1-2: route ids to owners, gather there, bring the rows back (bucket order)"""
-        rt = make_route(ids, self.world)
-        if self.world == 1:
-            rt.recv_counts, rt.recv_rows = rt.send_counts, rt.local_rows
-            return rt, self.ops.gather_rows(table, rt.local_rows)
-        rt.recv_counts = all_to_all_counts(rt.send_counts, self.group, ids.device)
+    def _route(self, user_ids: torch.Tensor, item_ids: torch.Tensor) -> Route:
+        """Requests of BOTH tables in one plan: sample order = [user ids | item ids], bucket order = stable by owner."""
+        W = self.world
+        ids = torch.cat([user_ids, item_ids])
+        owner = ids % W
+        local = torch.div(ids, W, rounding_mode="floor")
+        local[user_ids.numel():] += self._nu_by_rank[owner[user_ids.numel():]]      # item rows sit behind the owner's user rows
+        perm = torch.argsort(owner, stable=True)
+        inv = torch.empty_like(perm)
+        inv[perm] = torch.arange(ids.numel(), device=ids.device, dtype=perm.dtype)
+        send = torch.bincount(owner, minlength=W)
+        rt = Route(perm=perm, inv=inv, local_rows=local[perm].contiguous(), send_counts=None)
+        if W == 1:
+            rt.send_counts = rt.recv_counts = [ids.numel()]
+            rt.recv_rows = rt.local_rows
+            return rt
+        recv = torch.empty_like(send)
+        dist.all_to_all_single(recv, send, group=self.group)
+        both = torch.stack([send, recv]).tolist()                                   # the ONE host synchronisation of the step
+        rt.send_counts, rt.recv_counts = [int(c) for c in both[0]], [int(c) for c in both[1]]
         rt.recv_rows = all_to_all_var(rt.local_rows, rt.send_counts, rt.recv_counts, self.group)
-        served = self.ops.gather_rows(table, rt.recv_rows)
-        return rt, all_to_all_var(served, rt.recv_counts, rt.send_counts, self.group)
-
-    def _return_grads(self, rt: Route, drows: torch.Tensor) -> torch.Tensor:
-        """step 4: row gradients (sample order) → bucket order → owners"""
-        sorted_rows = self.ops.gather_rows(drows, rt.perm)
-        if self.world == 1:
-            return sorted_rows
-        return all_to_all_var(sorted_rows, rt.send_counts, rt.recv_counts, self.group)
+        return rt
 
     def step(self, user_ids, pos_ids, pos_genres, neg_ids, neg_genres) -> torch.Tensor:
-        """One optimiser step on this rank's local batch (device tensors).  Returns the global mean loss (device scalar)."""
+        """One optimiser step on this rank's local batch (device tensors).  Returns the global mean loss (device scalar).
+
+        Exchanges per step: request counts, requested rows, served rows, row gradients (all-to-all), MLP gradients and the
+        {Σg², loss} pair (all-reduce).  One host synchronisation (the split sizes of the all-to-alls)."""
         ops, D, H, E, W = self.ops, self.D, self.H, self.E, self.world
         B = user_ids.numel()
         dev = user_ids.device
         f32 = dict(dtype=torch.float32, device=dev)
-        item_ids = torch.cat([pos_ids, neg_ids])
-        rt_u, rows_u = self._fetch(self.user_table, user_ids)
-        rt_i, rows_i = self._fetch(self.item_table, item_ids)
+        # steps 1-3: route the ids to their owners, gather there, bring the rows back (bucket order)
+        rt = self._route(user_ids, torch.cat([pos_ids, neg_ids]))
+        served = ops.gather_rows(self.table, rt.recv_rows)
+        rows = served if W == 1 else all_to_all_var(served, rt.recv_counts, rt.send_counts, self.group)
         ops.begin_step(self.opt)
 
         uW1, ub1, uW2, ub2 = self._mlp_views(self.user_mlp, D)
@@ -285,11 +309,11 @@ class ShardedBPRTrainer:
         out = torch.empty(3 * B, D, **f32)
         hid = torch.empty(3 * B, H, **f32)
         den = torch.empty(3 * B, **f32)
-        inv_p, inv_n = rt_i.inv[:B].contiguous(), rt_i.inv[B:].contiguous()
+        inv_u, inv_p, inv_n = rt.inv[:B].contiguous(), rt.inv[B:2 * B].contiguous(), rt.inv[2 * B:].contiguous()
         jobs = [
-            dict(table=rows_u, ids=rt_u.inv, extra=None, W1=uW1, b1=ub1, W2=uW2, b2=ub2, out=out[:B], hid=hid[:B], denom=den[:B]),
-            dict(table=rows_i, ids=inv_p, extra=pos_genres, W1=iW1, b1=ib1, W2=iW2, b2=ib2, out=out[B:2 * B], hid=hid[B:2 * B], denom=den[B:2 * B]),
-            dict(table=rows_i, ids=inv_n, extra=neg_genres, W1=iW1, b1=ib1, W2=iW2, b2=ib2, out=out[2 * B:], hid=hid[2 * B:], denom=den[2 * B:]),
+            dict(table=rows, ids=inv_u, extra=None, W1=uW1, b1=ub1, W2=uW2, b2=ub2, out=out[:B], hid=hid[:B], denom=den[:B]),
+            dict(table=rows, ids=inv_p, extra=pos_genres, W1=iW1, b1=ib1, W2=iW2, b2=ib2, out=out[B:2 * B], hid=hid[B:2 * B], denom=den[B:2 * B]),
+            dict(table=rows, ids=inv_n, extra=neg_genres, W1=iW1, b1=ib1, W2=iW2, b2=ib2, out=out[2 * B:], hid=hid[2 * B:], denom=den[2 * B:]),
         ]
         ops.towers_fwd(jobs, D, H, 0.0, 0, self.steps)
         loss, du, dp, dn = ops.bpr_pair(out[:B], out[B:2 * B], out[2 * B:], 1.0 / W)
@@ -302,40 +326,39 @@ class ShardedBPRTrainer:
         ops.towers_bwd(jobs[:1], D, H, 0.0, g_mlp[:Pu])
         ops.towers_bwd(jobs[1:], D, H, 0.0, g_mlp[Pu:])
 
-        # step 4-5: gradients back to the owning shards, deterministic segment sums there
-        gu = self._return_grads(rt_u, drows[:B])
-        gi = self._return_grads(rt_i, drows[B:])
-        pad_u = 0 if self.rank == 0 else -1          # global padding id 0 lives on rank 0 as local row 0
-        uq_u, ug_u, nu_u = ops.scatter_rows(rt_u.recv_rows, gu, max(self.user_table.shape[0], 1), pad_u)
-        uq_i, ug_i, nu_i = ops.scatter_rows(rt_i.recv_rows, gi, max(self.item_table.shape[0], 1), pad_u)
+        # steps 4-5: row gradients (sample order → bucket order) back to the owning shards, deterministic segment sums there
+        g_rows = ops.gather_rows(drows, rt.perm)
+        if W > 1:
+            g_rows = all_to_all_var(g_rows, rt.send_counts, rt.recv_counts, self.group)
+        rows_sc = rt.recv_rows
+        if self.rank == 0:       # the global padding ids 0 live on rank 0 (local rows 0 and n_user_local): no gradient
+            nu0 = self.user_table.shape[0]
+            rows_sc = torch.where((rows_sc == 0) | (rows_sc == nu0), torch.full_like(rows_sc, -1), rows_sc)
+        uq, ug, n_uq = ops.scatter_rows(rows_sc, g_rows, max(self.table.shape[0], 1), -1)
         if W > 1:
             dist.all_reduce(g_mlp, group=self.group)                       # Σ over ranks of (1/W)-scaled local gradients
-        # step 6: global gradient norm.  Table shards are disjoint → their Σg² add up; the MLP gradient is replicated →
-        # counted once (on rank 0).
-        segs = [(ug_u, nu_u, D), (ug_i, nu_i, D)]
+        # step 6: global gradient norm and mean loss, on the device.  Table shards are disjoint → their Σg² add up; the MLP
+        # gradient is replicated → counted once (on rank 0).
+        segs = [(ug, n_uq, D)]
         if self.rank == 0:
             segs.append((g_mlp, None, 0))
         ops.sumsq(self.opt, segs)
-        st = ops.read_opt(self.opt)                                            # (host sync; scalars only)
-        red = torch.tensor([st.sumsq, float(loss.item()) / W], dtype=torch.float64, device=dev)
+        opt64, opt32 = self.opt.view(torch.float64), self.opt.view(torch.float32)
+        red = torch.cat([opt64[_OPT_SUMSQ_F64:_OPT_SUMSQ_F64 + 1], loss.to(torch.float64) / W])
         if W > 1:
             dist.all_reduce(red, group=self.group)
-        total = math.sqrt(float(red[0].item()))
-        st.sumsq, st.total_norm = float(red[0].item()), total
-        st.clip_coef = min(1.0, self.max_norm / (total + 1e-6))
-        st.loss = float(red[1].item())
-        ops.write_opt(self.opt, st)
+        opt64[_OPT_SUMSQ_F64:_OPT_SUMSQ_F64 + 1].copy_(red[0:1])
+        opt32[_OPT_LOSS_F32:_OPT_LOSS_F32 + 1].copy_(red[1:2].to(torch.float32))
+        ops.grad_norm_clip(self.opt)
 
         ops.adam_dense(self.user_mlp, g_mlp[:Pu], self.state["user_mlp"], self.state_v["user_mlp"], self.opt)
         ops.adam_dense(self.item_mlp, g_mlp[Pu:], self.state["item_mlp"], self.state_v["item_mlp"], self.opt)
         if self.adam_mode == "dense":
-            ops.adam_table_dense(self.user_table, self.state["user_table"], self.state_v["user_table"], uq_u, ug_u, nu_u, self.user_slot, self.opt)
-            ops.adam_table_dense(self.item_table, self.state["item_table"], self.state_v["item_table"], uq_i, ug_i, nu_i, self.item_slot, self.opt)
+            ops.adam_table_dense(self.table, self.state["table"], self.state_v["table"], uq, ug, n_uq, self.slot, self.opt)
         else:
-            ops.adam_rows(self.user_table, self.state["user_table"], self.state_v["user_table"], uq_u, ug_u, nu_u, self.opt)
-            ops.adam_rows(self.item_table, self.state["item_table"], self.state_v["item_table"], uq_i, ug_i, nu_i, self.opt)
+            ops.adam_rows(self.table, self.state["table"], self.state_v["table"], uq, ug, n_uq, self.opt)
         self.steps += 1
-        return torch.tensor(st.loss, **f32)
+        return opt32[_OPT_LOSS_F32:_OPT_LOSS_F32 + 1].clone()
 
     def full_state(self) -> Dict[str, torch.Tensor]:
         """Gather the shards into a single-process ``state_dict`` layout on every rank (tests / checkpoints)."""

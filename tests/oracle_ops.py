@@ -72,6 +72,12 @@ class OracleOps:
         st.sumsq = 0.0
         self.write_opt(opt, st)
 
+    def grad_norm_clip(self, opt):
+        st = self.read_opt(opt)
+        st.total_norm = math.sqrt(st.sumsq)
+        st.clip_coef = min(1.0, st.max_norm / (st.total_norm + 1e-6))
+        self.write_opt(opt, st)
+
     def sumsq(self, opt, segs):
         st = self.read_opt(opt)
         for t, cnt, rl in segs:
