@@ -19,6 +19,9 @@
 #include "common.cuh"
 
 // tcgen05 score product (gemm_tc.cu): C[M,N] = A[M,K]·B[N,K]ᵀ, mode 2 = 3xTF32 (fp32-grade)
+int rb_list_scan_tc(const float* q, int D, const float* list_vecs, const int64_t* offsets, const int* pair_qp, const int* list_qstart,
+                    int nprobe, const int* cand_base, const long long* cand_off, float* cand, const int* tile_list,
+                    const int* tile_idx, long long n_tiles, cudaStream_t st);
 int rb_gemm_nt_tc(const float* A, int M, const float* B, int N, int K, int mode, float* C, long long ldc, int* err_flag,
                   cudaStream_t st);
 
@@ -796,12 +799,18 @@ extern "C" int rb200_ivf_search_run(const float* q, int nq, int D, int nlist, in
     float* cand = ar.take<float>((size_t)(total_candidates > 0 ? total_candidates : 1));
     if (!workspace || !ar.ok()) return rb_set_error(RB200_ERR_WORKSPACE, "ivf_search_run: workspace too small");
     if (total_candidates > 0 && max_list_len > 0) {
-        dim3 g((unsigned)((max_list_len + TT - 1) / TT), nlist);
-        if (tile_list && tile_idx && n_tiles > 0) g = dim3((unsigned)n_tiles, 1);
-        else { tile_list = nullptr; tile_idx = nullptr; RB_REQUIRE(nlist <= 65535, "ivf_search_run: nlist must be <= 65535 without a tile table"); }
-        RB_DISPATCH_D(D, RB_TILE_LAUNCH(list_scan_kernel, DD, g, st, q, list_vecs, offsets, L.pair_qp, L.list_qstart, nprobe,
-                                        L.cand_base, L.cand_off, cand, tile_list, tile_idx));
-        RB_LAUNCH_CHECK("list_scan_kernel");
+        // D = 64 with a tile table: tcgen05 kernel (ivf_scan_tc.cu); otherwise the FFMA tile kernel
+        const int tc = rb_list_scan_tc(q, D, list_vecs, offsets, L.pair_qp, L.list_qstart, nprobe, L.cand_base, L.cand_off, cand,
+                                       tile_list, tile_idx, n_tiles, st);
+        if (tc < 0) return tc;
+        if (tc != 0) {
+            dim3 g((unsigned)((max_list_len + TT - 1) / TT), nlist);
+            if (tile_list && tile_idx && n_tiles > 0) g = dim3((unsigned)n_tiles, 1);
+            else { tile_list = nullptr; tile_idx = nullptr; RB_REQUIRE(nlist <= 65535, "ivf_search_run: nlist must be <= 65535 without a tile table"); }
+            RB_DISPATCH_D(D, RB_TILE_LAUNCH(list_scan_kernel, DD, g, st, q, list_vecs, offsets, L.pair_qp, L.list_qstart, nprobe,
+                                            L.cand_base, L.cand_off, cand, tile_list, tile_idx));
+            RB_LAUNCH_CHECK("list_scan_kernel");
+        }
     }
     ResolveIvf res{L.probes, L.cand_base, offsets, list_ids, nprobe, nullptr, nullptr};
     return launch_select<ResolveIvf>(cand, L.cand_off, 0, L.totals, 0, max_candidates, nq, k, res, out_scores, out_ids, st);
