@@ -49,48 +49,75 @@ __global__ void __launch_bounds__(NT_SC, 2) list_scan_tc_kernel(const float* __r
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     if (warp == 0) umma::tmem_alloc(&tmem_slot, QT);
     if (tid == 0) { umma::mbar_init(&bar_mem, 1); umma::fence_mbar_init(); dead = 0; }
-    // ---- stage the vector tile: a warp covers 8 rows × 4 16-byte chunks per step (64-byte global segments, conflict-free
-    //      128-byte shared-memory phases) ---------------------------------------------------------------------------- //
+    // Every global load of the first chunk is issued before any of them is used: the (list, query) pairs first, then the
+    // vector tile, then the query rows the pairs point to (measured: the serial version spent 1.9 us staging the tile and
+    // another 2.7 us gathering the queries per work item).  A warp covers 8 rows × 4 16-byte chunks per step (64-byte
+    // global segments, conflict-free 128-byte shared-memory phases).
     const int r8 = lane & 7, c4l = lane >> 3;
+    const int nv = (int)min((long long)VT, lend - v0);
+    int qrow[4];
+    auto load_pairs = [&](int p0, long long& d) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int pi = p0 + ((warp * 4 + i) >> 2) * 8 + r8;
+            qrow[i] = pi < qe ? __ldg(pair_qp + pi) / nprobe : -1;
+        }
+        d = -1;
+        if (tid < QT && p0 + tid < qe) {
+            const int qp = __ldg(pair_qp + p0 + tid);
+            d = cand_off[qp / nprobe] + cand_base[qp] + (v0 - lbeg);
+        }
+    };
+    auto load_queries = [&](float4 (&qv)[4]) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int c4 = ((warp * 4 + i) & 3) * 4 + c4l;
+            qv[i] = qrow[i] >= 0 ? __ldg(reinterpret_cast<const float4*>(q + (long long)qrow[i] * DD) + c4) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+    };
+    auto store_queries = [&](const float4 (&qv)[4], long long d) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int u = warp * 4 + i;
+            put4s(q_hi, q_lo, QT, (u >> 2) * 8 + r8, ((u & 3) * 4 + c4l) * 4, qv[i]);
+        }
+        if (tid < QT) dst[tid] = d;
+    };
+    long long d_first;
+    float4 qv[4], vv[8];
+    load_pairs(qs, d_first);
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
         const int u = warp * 8 + i, row = (u >> 2) * 8 + r8, c4 = (u & 3) * 4 + c4l;
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (v0 + row < lend) v = __ldg(reinterpret_cast<const float4*>(list_vecs + (v0 + row) * DD) + c4);
-        put4s(v_hi, v_lo, VT, row, c4 * 4, v);
+        vv[i] = (v0 + row < lend) ? __ldg(reinterpret_cast<const float4*>(list_vecs + (v0 + row) * DD) + c4) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
+    load_queries(qv);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int u = warp * 8 + i;
+        put4s(v_hi, v_lo, VT, (u >> 2) * 8 + r8, ((u & 3) * 4 + c4l) * 4, vv[i]);
+    }
+    store_queries(qv, d_first);
+    umma::fence_proxy_async();
     umma::fence_before_sync();
     __syncthreads();
     umma::fence_after_sync();
     const uint32_t tmem = tmem_slot;
     const int r_own = ((warp & 3) << 5) + lane, half = warp >> 2;
     const uint32_t lane_off = (uint32_t)((warp & 3) * 32) << 16;
-    const int nv = (int)min((long long)VT, lend - v0);
     const uint32_t idesc = umma::idesc_tf32(VT, QT);
     const uint32_t lbo_a = (VT / 8) * 128, lbo_b = (QT / 8) * 128;
     uint32_t phase = 0;
     for (int p0 = qs; p0 < qe; p0 += QT) {
-        // ---- gather this chunk's queries (B operand) and their candidate rows ------------------------------------ //
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const int u = warp * 4 + i, row = (u >> 2) * 8 + r8, c4 = (u & 3) * 4 + c4l;
-            const int pi = p0 + row;
-            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (pi < qe) v = __ldg(reinterpret_cast<const float4*>(q + (long long)(pair_qp[pi] / nprobe) * DD) + c4);
-            put4s(q_hi, q_lo, QT, row, c4 * 4, v);
+        if (p0 != qs) {                        // further chunks of a popular list (rare): gather + stage, then the same MMA path
+            long long d;
+            load_pairs(p0, d);
+            load_queries(qv);
+            store_queries(qv, d);
+            umma::fence_proxy_async();
+            umma::fence_before_sync();
+            __syncthreads();
         }
-        if (tid < QT) {
-            const int pi = p0 + tid;
-            long long d = -1;
-            if (pi < qe) {
-                const int qp = pair_qp[pi];
-                d = cand_off[qp / nprobe] + cand_base[qp] + (v0 - lbeg);
-            }
-            dst[tid] = d;
-        }
-        umma::fence_proxy_async();
-        umma::fence_before_sync();
-        __syncthreads();
         if (tid == 0 && !dead) {
             umma::fence_after_sync();
             const uint32_t ah = umma::smem_u32(v_hi), al = umma::smem_u32(v_lo), bh = umma::smem_u32(q_hi), bl = umma::smem_u32(q_lo);
