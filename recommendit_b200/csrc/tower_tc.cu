@@ -98,16 +98,19 @@ __device__ __forceinline__ void issue_gemm(uint32_t tmem_d, unsigned char* a_hi,
                                            unsigned char* b_lo, int RB, int N, int K, bool accumulate_first) {
     const uint32_t idesc = umma::idesc_tf32(128, N);
     const uint32_t lbo_a = (RA / 8) * 128, lbo_b = (RB / 8) * 128;
-    const uint32_t ah = umma::smem_u32(a_hi), al = umma::smem_u32(a_lo), bh = umma::smem_u32(b_hi), bl = umma::smem_u32(b_lo);
-    for (int j = 0; j < K / 8; ++j) {
-        const uint32_t oa = 2 * j * lbo_a, ob = 2 * j * lbo_b;
+    // descriptors are built once; a k-step (8 floats = two 16-byte K chunks) only advances the 14-bit start-address field
+    const uint64_t dah = umma::smem_desc(umma::smem_u32(a_hi), lbo_a, 128), dal = umma::smem_desc(umma::smem_u32(a_lo), lbo_a, 128);
+    const uint64_t dbh = umma::smem_desc(umma::smem_u32(b_hi), lbo_b, 128), dbl = umma::smem_desc(umma::smem_u32(b_lo), lbo_b, 128);
+    const uint64_t sa = (uint64_t)((2 * lbo_a) >> 4), sb = (uint64_t)((2 * lbo_b) >> 4);
+    uint64_t oa = 0, ob = 0;
+    for (int j = 0; j < K / 8; ++j, oa += sa, ob += sb) {
         const bool acc = accumulate_first || j > 0;
         if (MODE == 2) {
-            umma::mma_tf32(tmem_d, umma::smem_desc(al + oa, lbo_a, 128), umma::smem_desc(bh + ob, lbo_b, 128), idesc, acc);
-            umma::mma_tf32(tmem_d, umma::smem_desc(ah + oa, lbo_a, 128), umma::smem_desc(bl + ob, lbo_b, 128), idesc, true);
-            umma::mma_tf32(tmem_d, umma::smem_desc(ah + oa, lbo_a, 128), umma::smem_desc(bh + ob, lbo_b, 128), idesc, true);
+            umma::mma_tf32(tmem_d, dal + oa, dbh + ob, idesc, acc);
+            umma::mma_tf32(tmem_d, dah + oa, dbl + ob, idesc, true);
+            umma::mma_tf32(tmem_d, dah + oa, dbh + ob, idesc, true);
         } else {
-            umma::mma_tf32(tmem_d, umma::smem_desc(ah + oa, lbo_a, 128), umma::smem_desc(bh + ob, lbo_b, 128), idesc, acc);
+            umma::mma_tf32(tmem_d, dah + oa, dbh + ob, idesc, acc);
         }
     }
 }
@@ -159,7 +162,6 @@ __global__ void __launch_bounds__(NTD, 1) tower_fwd_tc_kernel(const FwdParams p)
     extern __shared__ __align__(1024) unsigned char smem[];
     __shared__ float ss_part[4][ROWS];
     __shared__ long long ids_s[ROWS];
-    RB_TC_PROLOGUE(p.err_flag)
     int begins[MAX_JOBS];
 #pragma unroll
     for (int t = 0; t < MAX_JOBS; ++t) begins[t] = p.job[t].cta_begin;
@@ -169,6 +171,15 @@ __global__ void __launch_bounds__(NTD, 1) tower_fwd_tc_kernel(const FwdParams p)
     const ImgLayout L = img_layout(D, H, E);
     const int Kp = L.Kp;
     const int row0 = ((int)blockIdx.x - J.cta_begin) * ROWS;
+    // the ids are fetched first: their latency hides under the TMEM allocation / barrier setup of the prologue, whose
+    // __syncthreads also publishes ids_s
+    if (threadIdx.x < ROWS) {
+        const int row = row0 + (int)threadIdx.x;
+        long long id = row < J.B ? J.ids[row] : 0;
+        if ((unsigned long long)id >= (unsigned long long)J.n_rows) { if (p.err_flag) atomicOr(p.err_flag, 1); id = 0; }
+        ids_s[threadIdx.x] = id;
+    }
+    RB_TC_PROLOGUE(p.err_flag)
 
     // ---- stage 1: X [128 × Kp] gathered by the threads, W1 image pulled in by one bulk asynchronous copy --------- //
     unsigned char* x_hi = smem;
@@ -180,13 +191,6 @@ __global__ void __launch_bounds__(NTD, 1) tower_fwd_tc_kernel(const FwdParams p)
         umma::mbar_expect_tx(&w_bar_s, bytes);
         umma::bulk_g2s(w1_hi, J.img + L.w1, bytes, &w_bar_s);
     }
-    if (tid < ROWS) {
-        const int row = row0 + tid;
-        long long id = row < J.B ? J.ids[row] : 0;
-        if ((unsigned long long)id >= (unsigned long long)J.n_rows) { if (p.err_flag) atomicOr(p.err_flag, 1); id = 0; }
-        ids_s[tid] = id;
-    }
-    __syncthreads();
     {
         // lane → (row%8 = lane&7, 16-byte chunk = 4·cq + lane>>3): 64-byte global segments, conflict-free 16-byte stores;
         // three units' loads are issued before their stores so that the gather latencies overlap
@@ -276,7 +280,9 @@ __global__ void __launch_bounds__(NTD, 1) tower_fwd_tc_kernel(const FwdParams p)
                     }
                     op[e] = x;
                 }
-                if (J.hid && valid) *reinterpret_cast<float4*>(J.hid + (long long)row * H + col) = o;
+                // (3xTF32: the saved hidden tile leaves through shared memory below, with 64-byte row segments — one 16-byte
+                //  store per thread-row here costs 32 LSU wavefronts per instruction and dominated this epilogue)
+                if (MODE != 2 && J.hid && valid) *reinterpret_cast<float4*>(J.hid + (long long)row * H + col) = o;
                 put4<MODE>(h_hi, h_lo, ROWS, r_own, col, o);
             }
         }
@@ -290,6 +296,20 @@ __global__ void __launch_bounds__(NTD, 1) tower_fwd_tc_kernel(const FwdParams p)
         issue_gemm<MODE>(tmem + H, h_hi, h_lo, ROWS, w2_hi, w2_lo, D, D, H, false);
         umma::commit(&mma_bar_s);
     }
+    if (MODE == 2 && J.hid) {
+        // hidden activations for the backward pass, copied out of the operand tile (hi + lo = the fp32 value, exactly) while
+        // GEMM2 runs: lane → (row%8, 16-byte chunk): conflict-free shared-memory phases, 64-byte global segments
+        constexpr int CQ = H / 16, UNITS = (ROWS / 8) * CQ;
+        for (int u = warp; u < UNITS; u += NTD / 32) {
+            const int rg = u / CQ, cq = u - rg * CQ;
+            const int r = rg * 8 + (lane & 7), c4 = cq * 4 + (lane >> 3);
+            if (row0 + r < J.B) {
+                const uint32_t off = umma::kmajor_offset(ROWS, r, c4 * 4);
+                const float4 a = *reinterpret_cast<const float4*>(h_hi + off), b = *reinterpret_cast<const float4*>(h_lo + off);
+                *reinterpret_cast<float4*>(J.hid + (long long)(row0 + r) * H + c4 * 4) = make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w);
+            }
+        }
+    }
     mma_bar.wait();
     umma::fence_after_sync();
 
@@ -301,18 +321,21 @@ __global__ void __launch_bounds__(NTD, 1) tower_fwd_tc_kernel(const FwdParams p)
         float ss = 0.f;
         umma::tmem_ld16(tmem + lane_off + H + half * QC, y);
 #pragma unroll
-        for (int i = 0; i < QC; ++i) {
-            y[i] += __ldg(J.b2 + half * QC + i);
-            ss = fmaf(y[i], y[i], ss);
+        for (int i4 = 0; i4 < QC / 4; ++i4) {
+            const float4 b = __ldg(reinterpret_cast<const float4*>(J.b2 + half * QC) + i4);
+            y[i4 * 4] += b.x; y[i4 * 4 + 1] += b.y; y[i4 * 4 + 2] += b.z; y[i4 * 4 + 3] += b.w;
         }
+#pragma unroll
+        for (int i = 0; i < QC; ++i) ss = fmaf(y[i], y[i], ss);
         ss_part[half][r_own] = ss;
         __syncthreads();
         const float den = fmaxf(sqrtf((ss_part[0][r_own] + ss_part[1][r_own]) + (ss_part[2][r_own] + ss_part[3][r_own])), NORM_EPS);
+        const float inv_den = 1.f / den;         // (x · (1/den) is within 1 ulp of x / den; the forward bound is 2e-6)
         if (valid) {
 #pragma unroll
             for (int c4 = 0; c4 < QC / 4; ++c4)
                 *reinterpret_cast<float4*>(J.out + (long long)row * D + half * QC + c4 * 4) =
-                    make_float4(y[c4 * 4] / den, y[c4 * 4 + 1] / den, y[c4 * 4 + 2] / den, y[c4 * 4 + 3] / den);
+                    make_float4(y[c4 * 4] * inv_den, y[c4 * 4 + 1] * inv_den, y[c4 * 4 + 2] * inv_den, y[c4 * 4 + 3] * inv_den);
             if (J.denom && half == 0) J.denom[row] = den;
         }
     }
@@ -366,6 +389,7 @@ __global__ void __launch_bounds__(NTD, 1) tower_bwd_data_tc_kernel(const BwdPara
         dot = (dot_part[0][r_own] + dot_part[1][r_own]) + (dot_part[2][r_own] + dot_part[3][r_own]);
         const float den = valid ? __ldg(J.denom + row) : 1.f;
         const bool clamped = den <= NORM_EPS;
+        const float inv_den = 1.f / den;         // one IEEE reciprocal per row-quarter instead of 16 divisions (≤ 1 ulp apart)
 #pragma unroll
         for (int c4 = 0; c4 < HC / 4; ++c4) {
             float4 o;
@@ -373,7 +397,7 @@ __global__ void __launch_bounds__(NTD, 1) tower_bwd_data_tc_kernel(const BwdPara
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
                 const float gg = g[c4 * 4 + e];
-                op[e] = clamped ? gg / den : (gg - yv[c4 * 4 + e] * dot) / den;
+                op[e] = clamped ? gg * inv_den : (gg - yv[c4 * 4 + e] * dot) * inv_den;
             }
             if (valid) *reinterpret_cast<float4*>(J.dpre + (long long)row * D + half * HC + c4 * 4) = o;
             put4<MODE>(g_hi, g_lo, ROWS, r_own, half * HC + c4 * 4, o);
@@ -581,7 +605,7 @@ __global__ void __launch_bounds__(NT, 1) tower_bwd_weights_tc_kernel(const BwdPa
             __syncthreads();
         }
     }
-    // partial block layout: [W1 (H*Din) | b1 (H) | W2 (D*H) | b2 (D)]
+    // partial block layout: [W1ᵀ (Din*H, transposed) | b1 (H) | W2 (D*H) | b2 (D)]; reduce_partials_tc_kernel undoes the transpose
     float* part = p.part + (long long)s * p.P;
     float* w1o = part, *b1o = part + H * Din, *w2o = part + H * Din + H, *b2o = part + H * Din + H + D * H;
     *reinterpret_cast<float4*>(&bias1_part[sq][mq * 4]) = db1;
@@ -598,8 +622,8 @@ __global__ void __launch_bounds__(NT, 1) tower_bwd_weights_tc_kernel(const BwdPa
             const int cb = half + 2 * b;
             if (cb < NK / 32) {
 #pragma unroll
-                for (int i = 0; i < 32; ++i)
-                    if (cb * 32 + i < Din) w1o[(long long)h * Din + cb * 32 + i] = acc_b[b][i];  // dW1[h][k]
+                for (int i = 0; i < 32; ++i)          // the W1 block of a partial is stored TRANSPOSED ([k][h]): 128-byte warp stores
+                    if (cb * 32 + i < Din) w1o[(long long)(cb * 32 + i) * H + h] = acc_b[b][i];  // dW1[h][k]
             }
         }
         if (tid < H) {
@@ -618,9 +642,10 @@ __global__ void __launch_bounds__(NT, 1) tower_bwd_weights_tc_kernel(const BwdPa
     RB_TC_EPILOGUE()
 }
 
-// out[i] = Σ_k part[k][i] in a fixed order.  Block = 32 outputs × 8 k-groups: group y adds the partials k ≡ y (mod 8)
-// (coalesced 128-byte rows), the 8 group sums are combined through shared memory in index order.
-__global__ void __launch_bounds__(256) reduce_partials_tc_kernel(const float* __restrict__ part, int nsplit, int P,
+// out[i] = Σ_k part[k][i] in a fixed order.  Block = 32 partial elements × 8 k-groups: group y adds the partials k ≡ y (mod 8)
+// (coalesced 128-byte rows), the 8 group sums are combined through shared memory in index order.  The first H·Din elements
+// of a partial hold W1 transposed ([k][h]); they are written back to out as [h][k].
+__global__ void __launch_bounds__(256) reduce_partials_tc_kernel(const float* __restrict__ part, int nsplit, int P, int H, int Din,
                                                                  float* __restrict__ out, int accumulate) {
     __shared__ float sm[8][33];
     const int x = threadIdx.x & 31, y = threadIdx.x >> 5;
@@ -634,7 +659,9 @@ __global__ void __launch_bounds__(256) reduce_partials_tc_kernel(const float* __
         float s = 0.f;
 #pragma unroll
         for (int g = 0; g < 8; ++g) s += sm[g][x];
-        out[i] = accumulate ? out[i] + s : s;
+        int o = i;
+        if (i < H * Din) { const int k = i / H, h = i - k * H; o = h * Din + k; }
+        out[o] = accumulate ? out[o] + s : s;
     }
 }
 
@@ -765,7 +792,7 @@ int rb_tower_bwd_tc(BwdParams& p, int D, int H, int mode, float* grads_out, int 
         else tower_bwd_weights_tc_kernel<64, 128, 96, 2><<<p.nsplit, NT, smem_w, st>>>(p, nullptr);
     }
     RB_LAUNCH_CHECK("tower_bwd_weights_tc_kernel");
-    reduce_partials_tc_kernel<<<(p.P + 31) / 32, 256, 0, st>>>(p.part, p.nsplit, p.P, grads_out, accumulate);
+    reduce_partials_tc_kernel<<<(p.P + 31) / 32, 256, 0, st>>>(p.part, p.nsplit, p.P, H, 64 + E, grads_out, accumulate);
     RB_LAUNCH_CHECK("reduce_partials_tc_kernel");
     return RB200_OK;
 }
