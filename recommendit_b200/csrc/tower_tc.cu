@@ -411,6 +411,16 @@ __global__ void __launch_bounds__(NTD, 1) tower_bwd_data_tc_kernel(const BwdPara
         issue_gemm<MODE>(tmem, g_hi, g_lo, ROWS, w2t_hi, w2t_lo, H, H, D, false);
         umma::commit(&mma_bar_s);
     }
+    // while GEMM1 runs: this thread's 32 saved hidden activations → one 32-bit "unit was active and kept" mask
+    uint32_t act_mask = 0u;
+    if (valid) {
+        float4 hv[8];
+#pragma unroll
+        for (int i4 = 0; i4 < 8; ++i4) hv[i4] = __ldg(reinterpret_cast<const float4*>(J.hid + (long long)row * H + half * 32) + i4);
+#pragma unroll
+        for (int i4 = 0; i4 < 8; ++i4)
+            act_mask |= ((hv[i4].x > 0.f ? 1u : 0u) | (hv[i4].y > 0.f ? 2u : 0u) | (hv[i4].z > 0.f ? 4u : 0u) | (hv[i4].w > 0.f ? 8u : 0u)) << (4 * i4);
+    }
     mma_bar.wait();
     umma::fence_after_sync();
 
@@ -432,13 +442,12 @@ __global__ void __launch_bounds__(NTD, 1) tower_bwd_data_tc_kernel(const BwdPara
 #pragma unroll
         for (int i4 = 0; i4 < 8; ++i4) {
             const int col = col0 + i4 * 4;
-            float4 hv = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (valid) hv = __ldg(reinterpret_cast<const float4*>(J.hid + (long long)row * H + col));
+            const uint32_t m4 = act_mask >> (4 * i4);
             float4 o;
-            o.x = hv.x > 0.f ? v[i4 * 4] * p.keep_scale : 0.f;
-            o.y = hv.y > 0.f ? v[i4 * 4 + 1] * p.keep_scale : 0.f;
-            o.z = hv.z > 0.f ? v[i4 * 4 + 2] * p.keep_scale : 0.f;
-            o.w = hv.w > 0.f ? v[i4 * 4 + 3] * p.keep_scale : 0.f;
+            o.x = (m4 & 1u) ? v[i4 * 4] * p.keep_scale : 0.f;
+            o.y = (m4 & 2u) ? v[i4 * 4 + 1] * p.keep_scale : 0.f;
+            o.z = (m4 & 4u) ? v[i4 * 4 + 2] * p.keep_scale : 0.f;
+            o.w = (m4 & 8u) ? v[i4 * 4 + 3] * p.keep_scale : 0.f;
             if (valid) *reinterpret_cast<float4*>(J.dact + (long long)row * H + col) = o;
             put4<MODE>(a_hi, a_lo, ROWS, r_own, col, o);
         }
@@ -492,7 +501,7 @@ template <int D, int H, int NK, int MODE>      // NK = padded Din (multiple of 3
 __global__ void __launch_bounds__(NT, 1) tower_bwd_weights_tc_kernel(const BwdParams p, int* err_flag) {
     static_assert(H == 128 && D == 64 && KC == 32 && NT == 256, "thread mapping assumes 8 warps = 8 sample quads, 32 lanes = 32 row quads");
     extern __shared__ __align__(1024) unsigned char smem[];
-    __shared__ long long ids_s[KC];
+    __shared__ long long ids_s[2][KC];
     __shared__ float bias1_part[KC / 4][H];      // per sample-quad partial column sums of dact
     __shared__ float bias2_part[KC / 4][D];      // … of dpre
     RB_TC_PROLOGUE(err_flag)
@@ -523,87 +532,110 @@ __global__ void __launch_bounds__(NT, 1) tower_bwd_weights_tc_kernel(const BwdPa
     for (int b = 0; b < NB; ++b)
 #pragma unroll
         for (int i = 0; i < 32; ++i) acc_b[b][i] = 0.f;
-    for (int j = 0; j < p.n_jobs; ++j) {
-        const BwdJob& J = p.job[j];
-        const float* __restrict__ hid = J.hid; const float* __restrict__ dact = J.dact; const float* __restrict__ dpre = J.dpre;
-        const float* __restrict__ table = J.table; const float* __restrict__ extra = J.extra;
-        const int by_id = J.extra_by_id;
-        const int chunk = (((J.B + p.nsplit - 1) / p.nsplit) + KC - 1) / KC * KC;   // rows per CTA, multiple of KC
-        const int r_begin = min(J.B, s * chunk), r_end = min(J.B, r_begin + chunk);
-        for (int r0 = r_begin; r0 < r_end; r0 += KC) {
-            const int nr = min(KC, r_end - r0);
-            if (tid < KC) {
-                long long id = tid < nr ? J.ids[r0 + tid] : 0;
-                if ((unsigned long long)id >= (unsigned long long)J.n_rows) id = 0;
-                ids_s[tid] = id;
-            }
-            __syncthreads();
-            // ---- all global loads of the chunk first (16-byte, coalesced along the operand-row dimension) ---------- //
-            float4 hv[4], av[4], gv[4], xv[4];
+    // ---- this CTA's chunks: up to two jobs (positive / negative items share the weights), rows [r_begin, r_end) of each -- //
+    int jb[2] = {0, 0}, je[2] = {0, 0}, nc[2] = {0, 0};
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const int r = sq * 4 + i;
-                const bool ok = r < nr;
-                const long long gr = r0 + r;
-                const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-                hv[i] = ok ? __ldg(reinterpret_cast<const float4*>(hid + gr * H) + mq) : z;
-                av[i] = ok ? __ldg(reinterpret_cast<const float4*>(dact + gr * H) + mq) : z;
-                gv[i] = (ok && mq < D / 4) ? __ldg(reinterpret_cast<const float4*>(dpre + gr * D) + mq) : z;
-                float4 x = z;
-                if (ok && mq < D / 4) {
-                    x = __ldg(reinterpret_cast<const float4*>(table + ids_s[r] * D) + mq);
-                } else if (ok && mq < NK / 4 && E > 0) {
-                    const int k = mq * 4 - D;          // genre column
-                    const float* ex = extra + (by_id ? ids_s[r] : gr) * E;
-                    x.x = k + 0 < E ? __ldg(ex + k + 0) : 0.f;
-                    x.y = k + 1 < E ? __ldg(ex + k + 1) : 0.f;
-                    x.z = k + 2 < E ? __ldg(ex + k + 2) : 0.f;
-                    x.w = k + 3 < E ? __ldg(ex + k + 3) : 0.f;
-                }
-                xv[i] = x;
-            }
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                db1.x += av[i].x; db1.y += av[i].y; db1.z += av[i].z; db1.w += av[i].w;
-                db2.x += gv[i].x; db2.y += gv[i].y; db2.z += gv[i].z; db2.w += gv[i].w;
-            }
-            put_block_t<MODE>(a1_hi, a1_lo, H, mq, sq, lane, hv);
-            put_block_t<MODE>(a2_hi, a2_lo, H, mq, sq, lane, av);
-            if (mq < D / 4) put_block_t<MODE>(b1_hi, b1_lo, D, mq, sq, lane, gv);
-            if (mq < NK / 4) put_block_t<MODE>(b2_hi, b2_lo, NK, mq, sq, lane, xv);
-            umma::fence_proxy_async();
-            __syncthreads();
-            if (tid == 0 && !dead) {
-                umma::fence_after_sync();
-                issue_gemm<MODE>(tmem, a1_hi, a1_lo, H, b1_hi, b1_lo, D, D, KC, false);        // dW2ᵀ [H × D]
-                issue_gemm<MODE>(tmem + D, a2_hi, a2_lo, H, b2_hi, b2_lo, NK, NK, KC, false);  // dW1  [H × NK]
-                umma::commit(&mma_bar_s);
-            }
-            first = false;
-            mma_bar.wait();          // chunk buffers are reused
-            umma::fence_after_sync();
-            if (!dead) {
-#pragma unroll
-                for (int cb = 0; cb < HC / 32; ++cb) {
-                    float v[32];
-                    umma::tmem_ld32(tmem + lane_off + half * HC + cb * 32, v);
-#pragma unroll
-                    for (int i = 0; i < 32; ++i) acc_a[cb * 32 + i] += v[i];
-                }
-#pragma unroll
-                for (int b = 0; b < NB; ++b) {
-                    const int cb = half + 2 * b;
-                    if (cb < NK / 32) {
-                        float v[32];
-                        umma::tmem_ld32(tmem + lane_off + D + cb * 32, v);
-#pragma unroll
-                        for (int i = 0; i < 32; ++i) acc_b[b][i] += v[i];
-                    }
-                }
-            }
-            umma::fence_before_sync();
-            __syncthreads();
+    for (int j = 0; j < 2; ++j) {
+        if (j < p.n_jobs) {
+            const int B = p.job[j].B;
+            const int chunk = (((B + p.nsplit - 1) / p.nsplit) + KC - 1) / KC * KC;   // rows per CTA, multiple of KC
+            jb[j] = min(B, s * chunk); je[j] = min(B, jb[j] + chunk);
+            nc[j] = (je[j] - jb[j] + KC - 1) / KC;
         }
+    }
+    const int n_chunks = nc[0] + nc[1];
+    auto chunk_at = [&](int t, int& j, int& r0, int& nr) {
+        j = t < nc[0] ? 0 : 1;
+        r0 = jb[j] + (t - (j ? nc[0] : 0)) * KC;
+        nr = min(KC, je[j] - r0);
+    };
+    auto load_ids = [&](int t) {                 // ids of chunk t → ids_s[t & 1] (visible after the next __syncthreads)
+        if (tid < KC && t < n_chunks) {
+            int j, r0, nr;
+            chunk_at(t, j, r0, nr);
+            long long id = tid < nr ? p.job[j].ids[r0 + tid] : 0;
+            if ((unsigned long long)id >= (unsigned long long)p.job[j].n_rows) id = 0;
+            ids_s[t & 1][tid] = id;
+        }
+    };
+    // all global loads of a chunk (16-byte, coalesced along the operand-row dimension); issued one chunk ahead so that their
+    // latency overlaps the previous chunk's MMAs and accumulator flush
+    float4 hv[4], av[4], gv[4], xv[4];
+    auto load_chunk = [&](int t) {
+        int j, r0, nr;
+        chunk_at(t, j, r0, nr);
+        const BwdJob& J = p.job[j];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int r = sq * 4 + i;
+            const bool ok = r < nr;
+            const long long gr = r0 + r;
+            const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+            hv[i] = ok ? __ldg(reinterpret_cast<const float4*>(J.hid + gr * H) + mq) : z;
+            av[i] = ok ? __ldg(reinterpret_cast<const float4*>(J.dact + gr * H) + mq) : z;
+            gv[i] = (ok && mq < D / 4) ? __ldg(reinterpret_cast<const float4*>(J.dpre + gr * D) + mq) : z;
+            float4 x = z;
+            if (ok && mq < D / 4) {
+                x = __ldg(reinterpret_cast<const float4*>(J.table + ids_s[t & 1][r] * D) + mq);
+            } else if (ok && mq < NK / 4 && E > 0) {
+                const int k = mq * 4 - D;          // genre column
+                const float* ex = J.extra + (J.extra_by_id ? ids_s[t & 1][r] : gr) * E;
+                x.x = k + 0 < E ? __ldg(ex + k + 0) : 0.f;
+                x.y = k + 1 < E ? __ldg(ex + k + 1) : 0.f;
+                x.z = k + 2 < E ? __ldg(ex + k + 2) : 0.f;
+                x.w = k + 3 < E ? __ldg(ex + k + 3) : 0.f;
+            }
+            xv[i] = x;
+        }
+    };
+    load_ids(0);
+    load_ids(1);
+    __syncthreads();
+    if (n_chunks > 0) load_chunk(0);
+    for (int t = 0; t < n_chunks; ++t) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            db1.x += av[i].x; db1.y += av[i].y; db1.z += av[i].z; db1.w += av[i].w;
+            db2.x += gv[i].x; db2.y += gv[i].y; db2.z += gv[i].z; db2.w += gv[i].w;
+        }
+        put_block_t<MODE>(a1_hi, a1_lo, H, mq, sq, lane, hv);
+        put_block_t<MODE>(a2_hi, a2_lo, H, mq, sq, lane, av);
+        if (mq < D / 4) put_block_t<MODE>(b1_hi, b1_lo, D, mq, sq, lane, gv);
+        if (mq < NK / 4) put_block_t<MODE>(b2_hi, b2_lo, NK, mq, sq, lane, xv);
+        umma::fence_proxy_async();
+        __syncthreads();                         // operands staged; ids of chunk t+1 (stored one iteration ago) visible
+        if (tid == 0 && !dead) {
+            umma::fence_after_sync();
+            issue_gemm<MODE>(tmem, a1_hi, a1_lo, H, b1_hi, b1_lo, D, D, KC, false);        // dW2ᵀ [H × D]
+            issue_gemm<MODE>(tmem + D, a2_hi, a2_lo, H, b2_hi, b2_lo, NK, NK, KC, false);  // dW1  [H × NK]
+            umma::commit(&mma_bar_s);
+        }
+        first = false;
+        if (t + 1 < n_chunks) load_chunk(t + 1);  // in flight while the tensor core works on chunk t
+        mma_bar.wait();                          // chunk buffers are reused
+        umma::fence_after_sync();
+        if (!dead) {
+#pragma unroll
+            for (int cb = 0; cb < HC / 32; ++cb) {
+                float v[32];
+                umma::tmem_ld32(tmem + lane_off + half * HC + cb * 32, v);
+#pragma unroll
+                for (int i = 0; i < 32; ++i) acc_a[cb * 32 + i] += v[i];
+            }
+#pragma unroll
+            for (int b = 0; b < NB; ++b) {
+                const int cb = half + 2 * b;
+                if (cb < NK / 32) {
+                    float v[32];
+                    umma::tmem_ld32(tmem + lane_off + D + cb * 32, v);
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) acc_b[b][i] += v[i];
+                }
+            }
+        }
+        load_ids(t + 2);                         // ids_s[t & 1] was last read by load_chunk(t), long done
+        umma::fence_before_sync();
+        __syncthreads();
     }
     // partial block layout: [W1ᵀ (Din*H, transposed) | b1 (H) | W2 (D*H) | b2 (D)]; reduce_partials_tc_kernel undoes the transpose
     float* part = p.part + (long long)s * p.P;
