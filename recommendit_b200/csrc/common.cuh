@@ -106,3 +106,7 @@ __device__ __forceinline__ void rb_opt_begin_step_dev(rb200_opt_state* st) {
     st->sumsq = 0.0;
     st->ticket = 0u;
 }
+
+// split-K partials of a tower's weight gradients left unreduced by rb_tower_bwd (tensor-core modes): nsplit blocks of P
+// floats, the first H·Din of each holding W1 transposed ([k][h]); nsplit == 0 → the gradient is all zeros
+struct RbPartials { const float* part; int nsplit; int P; int H; int Din; };

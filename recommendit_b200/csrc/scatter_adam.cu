@@ -379,6 +379,117 @@ __global__ void __launch_bounds__(NT) sumsq_kernel(const SumsqSegs segs, double*
     }
 }
 
+// ------------------------------------------------------------------------------------------------------------ //
+// Gradient finish of the fused training step, ONE launch instead of four:
+//   blocks [0, nb_seg)            deterministic segment sums of the embedding-row gradients (segment_sum2, 1 segment / warp)
+//   blocks [nb_seg, +nb_red[0])   reduction of the user tower's split-K weight-gradient partials   (reduce_partials_tc)
+//   blocks [.., +nb_red[1])       … of the item towers'
+// and, with do_sumsq, Σ g² of everything those blocks produce (fp64 block partials; the last block to finish adds them in
+// index order and derives total_norm / clip_coef): clip_grad_norm_ needs no pass of its own.
+// ------------------------------------------------------------------------------------------------------------ //
+struct RedSet { const float* part; int nsplit; int P; int H; int Din; float* out; };
+struct FinishParams { SegParams seg; RedSet red[2]; int nb_seg; int nb_red[2]; int do_sumsq; int do_clip; };
+
+__global__ void __launch_bounds__(NT) grad_finish_kernel(const FinishParams p, double* __restrict__ partials) {
+    __shared__ double scratch[NT / 32];
+    __shared__ float sm[8][33];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    double sq = 0.0;
+    if ((int)blockIdx.x < p.nb_seg) {
+        int w = blockIdx.x * (NT / 32) + warp;
+        int j = 0;
+        if (p.seg.n_jobs > 1 && w >= p.seg.job[0].cap) { w -= p.seg.job[0].cap; j = 1; }
+        const SegJob& J = p.seg.job[j];
+        if (w < J.cap && w < J.n_uniq[0]) {
+            const int beg = J.seg_start[w], end = J.seg_start[w + 1];
+            const int D4 = p.seg.D4;
+            const float4* __restrict__ rows = reinterpret_cast<const float4*>(J.rows);
+            for (int c = lane; c < D4; c += 32) {
+                float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+                for (int k = beg; k < end; ++k) {
+                    const float4 v = __ldg(rows + (long long)J.pos[k] * D4 + c);
+                    s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+                }
+                if (J.uniq_grads) reinterpret_cast<float4*>(J.uniq_grads)[(long long)w * D4 + c] = s;
+                if (J.dense) {
+                    float4* dp = reinterpret_cast<float4*>(J.dense) + J.uniq_ids[w] * D4 + c;
+                    float4 o = *dp;
+                    o.x += s.x; o.y += s.y; o.z += s.z; o.w += s.w;
+                    *dp = o;
+                }
+                sq += (double)fmaf(s.x, s.x, fmaf(s.y, s.y, fmaf(s.z, s.z, s.w * s.w)));
+            }
+        }
+    } else {
+        int b = (int)blockIdx.x - p.nb_seg, r = 0;
+        if (b >= p.nb_red[0]) { b -= p.nb_red[0]; r = 1; }
+        const RedSet& R = p.red[r];
+        const int x = lane, y = warp;
+        const int i = b * 32 + x;
+        float a = 0.f;
+        if (i < R.P) {
+            // six independent loads in flight per thread; the additions keep the order k = y, y+8, y+16, …
+            for (int k0 = y; k0 < R.nsplit; k0 += 48) {
+                float v[6];
+#pragma unroll
+                for (int u = 0; u < 6; ++u) { const int k = k0 + 8 * u; v[u] = k < R.nsplit ? __ldg(R.part + (long long)k * R.P + i) : 0.f; }
+#pragma unroll
+                for (int u = 0; u < 6; ++u) a += v[u];
+            }
+        }
+        sm[y][x] = a;
+        __syncthreads();
+        if (y == 0 && i < R.P) {
+            float t = 0.f;
+#pragma unroll
+            for (int g = 0; g < 8; ++g) t += sm[g][x];
+            int o = i;
+            if (i < R.H * R.Din) { const int k = i / R.H, h = i - k * R.H; o = h * R.Din + k; }
+            R.out[o] = t;
+            sq = (double)(t * t);
+        }
+    }
+    if (!p.do_sumsq) return;
+    sq = rb_warp_sum_d(sq);
+    if (lane == 0) scratch[warp] = sq;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int w = 0; w < NT / 32; ++w) t += scratch[w];
+        partials[blockIdx.x] = t;      // summed in index order by the consumer (the Adam launch, or norm_from_partials_kernel)
+    }
+}
+
+// Σ of n fp64 block partials in a fixed order (thread t takes t, t+NT, …; then warps, then the block); valid on thread 0.
+__device__ __forceinline__ double block_sum_partials(const double* __restrict__ partials, int n, double* scratch /*[NT/32]*/) {
+    double t = 0.0;
+    for (int i = threadIdx.x; i < n; i += NT) t += __ldcg(partials + i);
+    t = rb_warp_sum_d(t);
+    if ((threadIdx.x & 31) == 0) scratch[threadIdx.x >> 5] = t;
+    __syncthreads();
+    double tot = 0.0;
+    if (threadIdx.x == 0)
+        for (int w = 0; w < NT / 32; ++w) tot += scratch[w];
+    return tot;
+}
+__device__ __forceinline__ float clip_from_sumsq(double sumsq, float max_norm, float* total_norm) {
+    const float total = (float)sqrt(sumsq);
+    *total_norm = total;
+    const float coef = max_norm / (total + 1e-6f);
+    return coef < 1.f ? coef : 1.f;
+}
+__global__ void __launch_bounds__(NT) norm_from_partials_kernel(const double* __restrict__ partials, int n, rb200_opt_state* st) {
+    __shared__ double scratch[NT / 32];
+    const double tot = block_sum_partials(partials, n, scratch);
+    if (threadIdx.x == 0) {
+        const double t = tot + st->sumsq;
+        st->sumsq = t;
+        float tn;
+        st->clip_coef = clip_from_sumsq(t, st->max_norm, &tn);
+        st->total_norm = tn;
+    }
+}
+
 __global__ void grad_norm_clip_kernel(rb200_opt_state* st) {
     if (threadIdx.x || blockIdx.x) return;
     const float total = (float)sqrt(st->sumsq);
@@ -459,9 +570,24 @@ struct AdamTableParams { AdamTableJob job[2]; int n_jobs; int D4; };
 // The optimizer step of the fused training step in ONE launch: both embedding tables (dense, reference-exact: every
 // row moves) and both MLP parameter blocks.  Requires D4 a power of two <= 32, so that the D4 lanes of a table row sit
 // in one warp: the first of them reads the row's gradient slot, resets it to -1 for the next step and broadcasts it.
-__global__ void __launch_bounds__(NT) adam_step_all_kernel(const AdamTableParams tp, const AdamDenseParams dp,
-                                                           const rb200_opt_state* __restrict__ st) {
-    const AdamK k = load_adam(st);
+// `partials` != NULL: the gradient norm has not been finalised yet — every block adds the n_partials fp64 block partials of
+// grad_finish_kernel in the same fixed order (no atomics, no extra launch) and derives the clip coefficient itself; block 0
+// also records sumsq / total_norm / clip_coef in the optimizer state.
+__global__ void __launch_bounds__(NT) adam_step_all_kernel(const AdamTableParams tp, const AdamDenseParams dp, rb200_opt_state* st,
+                                                           const double* __restrict__ partials, int n_partials) {
+    AdamK k = load_adam(st);
+    if (partials) {
+        __shared__ double scratch[NT / 32];
+        __shared__ float s_clip;
+        const double tot = block_sum_partials(partials, n_partials, scratch);
+        if (threadIdx.x == 0) {
+            float tn;
+            s_clip = clip_from_sumsq(tot, st->max_norm, &tn);
+            if (blockIdx.x == 0) { st->sumsq = tot; st->total_norm = tn; st->clip_coef = s_clip; }
+        }
+        __syncthreads();
+        k.clip = s_clip;
+    }
     const long long stride = (long long)gridDim.x * NT;
     const int D4 = tp.D4, lane = threadIdx.x & 31;
     for (int j = 0; j < tp.n_jobs; ++j) {
@@ -629,6 +755,52 @@ int rb_scatter_tables(int phase, int n_tables, const int64_t* const ids_a[2], co
     if (rc) return rc;
     if (phase == 0 || phase == 1) { if ((rc = scatter_sort(pl, st))) return rc; }
     if (phase == 0 || phase == 2) { if ((rc = scatter_sum(pl, st))) return rc; }
+    return RB200_OK;
+}
+
+// Phase 2 of rb_scatter_tables fused with the reduction of up to two towers' weight-gradient partials and (do_sumsq) the
+// global gradient norm.  `red[t].nsplit == 0` → that gradient block is zero-filled.  `sumsq_ws` holds the fp64 block partials.
+size_t rb_grad_finish_workspace_bytes(int n_seg_rows, const RbPartials red[2]) {
+    size_t blocks = (size_t)(n_seg_rows + NT / 32 - 1) / (NT / 32);
+    for (int t = 0; t < 2; ++t) blocks += (size_t)(red[t].P + 31) / 32;
+    return 256 + sizeof(double) * blocks;
+}
+
+int rb_grad_finish(int n_tables, const int64_t* const ids_a[2], const int64_t* const ids_b[2], const int n_a[2], const int n_b[2],
+                   const float* const rows[2], int D, const long long n_rows[2], long long padding_idx, float* const dense[2],
+                   int64_t* const uniq_ids[2], float* const uniq_grads[2], int* const n_uniq[2], int* const row_slot[2],
+                   void* scatter_ws, size_t scatter_ws_bytes, const RbPartials red[2], float* const red_out[2], int do_sumsq,
+                   void* sumsq_ws, size_t sumsq_ws_bytes, const double** norm_partials, int* n_norm_partials, cudaStream_t s) {
+    ScatterPlan pl;
+    int rc = scatter_plan(pl, n_tables, ids_a, ids_b, n_a, n_b, rows, D, n_rows, padding_idx, dense, uniq_ids, uniq_grads, n_uniq,
+                          row_slot, scatter_ws, scatter_ws_bytes);
+    if (rc) return rc;
+    FinishParams fp{};
+    fp.seg = pl.gp;
+    long long warps = 0;
+    for (int t = 0; t < pl.gp.n_jobs; ++t) warps += pl.gp.job[t].cap;
+    fp.nb_seg = (int)((warps + NT / 32 - 1) / (NT / 32));
+    for (int t = 0; t < 2; ++t) {
+        if (red[t].nsplit == 0 && red_out[t]) RB_CUDA(cudaMemsetAsync(red_out[t], 0, sizeof(float) * red[t].P, s));
+        fp.red[t] = RedSet{red[t].part, red[t].nsplit, red[t].P, red[t].H, red[t].Din, red_out[t]};
+        fp.nb_red[t] = (red_out[t] && red[t].nsplit > 0) ? (red[t].P + 31) / 32 : 0;
+    }
+    fp.do_sumsq = do_sumsq; fp.do_clip = do_sumsq;
+    const int grid = fp.nb_seg + fp.nb_red[0] + fp.nb_red[1];
+    RbArena ar(sumsq_ws, sumsq_ws_bytes);
+    double* partials = ar.take<double>(grid);
+    if (do_sumsq && (!sumsq_ws || !ar.ok())) return rb_set_error(RB200_ERR_WORKSPACE, "grad_finish: workspace too small");
+    RB_REQUIRE(grid >= 1, "grad_finish: nothing to do");
+    grad_finish_kernel<<<grid, NT, 0, s>>>(fp, partials);
+    RB_LAUNCH_CHECK("grad_finish_kernel");
+    if (norm_partials) { *norm_partials = do_sumsq ? partials : nullptr; *n_norm_partials = do_sumsq ? grid : 0; }
+    return RB200_OK;
+}
+
+// Σg² block partials of rb_grad_finish → sumsq / total_norm / clip_coef (for consumers other than the fused Adam launch)
+int rb_norm_from_partials(const double* partials, int n, rb200_opt_state* st, cudaStream_t s) {
+    norm_from_partials_kernel<<<1, NT, 0, s>>>(partials, n, st);
+    RB_LAUNCH_CHECK("norm_from_partials_kernel");
     return RB200_OK;
 }
 
@@ -842,8 +1014,8 @@ int rb_adam_tables_dense2(float* w0, float* m0, float* v0, long long rows0, int*
 // returns 1 when D does not allow the fused launch (caller then uses the separate kernels)
 int rb_adam_step_all(float* const mlp_w[2], const float* const mlp_g[2], float* const mlp_m[2], float* const mlp_v[2],
                      const long long mlp_n[2], float* const tab_w[2], float* const tab_m[2], float* const tab_v[2],
-                     const long long tab_rows[2], int* const slot[2], const float* const ug[2], int D, const rb200_opt_state* st,
-                     cudaStream_t s) {
+                     const long long tab_rows[2], int* const slot[2], const float* const ug[2], int D, rb200_opt_state* st,
+                     const double* norm_partials, int n_norm_partials, cudaStream_t s) {
     const int D4 = D / 4;
     if (D % 4 != 0 || D4 > 32 || (D4 & (D4 - 1)) != 0) return 1;
     AdamTableParams tp{};
@@ -854,7 +1026,7 @@ int rb_adam_step_all(float* const mlp_w[2], const float* const mlp_g[2], float* 
         dp.job[t] = {mlp_w[t], mlp_g[t], mlp_m[t], mlp_v[t], mlp_n[t]};
     }
     const long long big = (tab_rows[0] > tab_rows[1] ? tab_rows[0] : tab_rows[1]) * D4;
-    adam_step_all_kernel<<<stream_grid(big), NT, 0, s>>>(tp, dp, st);
+    adam_step_all_kernel<<<stream_grid(big), NT, 0, s>>>(tp, dp, st, norm_partials, n_norm_partials);
     RB_LAUNCH_CHECK("adam_step_all_kernel");
     return RB200_OK;
 }

@@ -19,11 +19,19 @@ int rb_adam_tables_dense2(float* w0, float* m0, float* v0, long long rows0, int*
                           long long rows1, int* slot1, const float* ug1, int D, const rb200_opt_state* st, cudaStream_t s);
 int rb_adam_step_all(float* const mlp_w[2], const float* const mlp_g[2], float* const mlp_m[2], float* const mlp_v[2],
                      const long long mlp_n[2], float* const tab_w[2], float* const tab_m[2], float* const tab_v[2],
-                     const long long tab_rows[2], int* const slot[2], const float* const ug[2], int D, const rb200_opt_state* st,
-                     cudaStream_t s);
+                     const long long tab_rows[2], int* const slot[2], const float* const ug[2], int D, rb200_opt_state* st,
+                     const double* norm_partials, int n_norm_partials, cudaStream_t s);
+int rb_norm_from_partials(const double* partials, int n, rb200_opt_state* st, cudaStream_t s);
 int rb_bpr_pair(const float* u, const float* p, const float* n, int B, int D, float* loss, float* du, float* dp, float* dn,
                 float grad_scale, float loss_scale, void* workspace, size_t workspace_bytes, rb200_opt_state* opt, cudaStream_t st,
                 cudaStream_t st_fin, cudaEvent_t fork);
+int rb_tower_bwd(const rb200_tower_bwd_job* jobs, int n_jobs, int D, int H, float dropout_p, int mode, float* grads_out,
+                 int accumulate, void* workspace, size_t workspace_bytes, cudaStream_t stream, RbPartials* defer);
+int rb_grad_finish(int n_tables, const int64_t* const ids_a[2], const int64_t* const ids_b[2], const int n_a[2], const int n_b[2],
+                   const float* const rows[2], int D, const long long n_rows[2], long long padding_idx, float* const dense[2],
+                   int64_t* const uniq_ids[2], float* const uniq_grads[2], int* const n_uniq[2], int* const row_slot[2],
+                   void* scatter_ws, size_t scatter_ws_bytes, const RbPartials red[2], float* const red_out[2], int do_sumsq,
+                   void* sumsq_ws, size_t sumsq_ws_bytes, const double** norm_partials, int* n_norm_partials, cudaStream_t s);
 int rb_reset_slots2(const int64_t* ids0, const int* n0, int cap0, int* slot0, const int64_t* ids1, const int* n1, int cap1, int* slot1,
                     cudaStream_t s);
 
@@ -76,6 +84,10 @@ bool carve(RbArena& ar, const rb200_step_params& s, StepWs& w) {
     w.b_scatter = s0 + s1;
     w.ws_scatter = ar.take<char>(w.b_scatter);
     w.b_sumsq = rb200_sumsq_workspace_bytes();
+    {   // fp64 block partials of the fused gradient-finish kernel (segment blocks + partial-reduction blocks)
+        const size_t fin = 256 + sizeof(double) * ((size_t)(items + 1) * B / 8 + ((size_t)w.P_user + w.P_item) / 32 + 16);
+        if (fin > w.b_sumsq) w.b_sumsq = fin;
+    }
     w.ws_sumsq = ar.take<char>(w.b_sumsq);
     return ar.ok();
 }
@@ -253,7 +265,14 @@ extern "C" int rb200_bpr_step(const rb200_step_params* s, void* stream) {
     bj[0].img = tc ? w.img_user : nullptr;
     // (second fork, recorded with the loss above): the user tower's backward goes to the side stream (behind the id sort, long finished by now) and
     // overlaps the item towers' backward — neither fills the GPU on its own (64 / 128 tiles of 128 samples at B = 8192)
-    if ((rc = rb200_tower_bwd(bj, 1, D, H, s->dropout_p, s->tower_mode, w.g_user_mlp, 0, w.ws_bwd_u, w.b_bwd, side->s))) return rc;
+    // tensor-core modes + in-graph scatter: the split-K partials stay unreduced; rb_grad_finish reduces them together with the
+    // segment sums and the gradient norm in one launch
+    const bool fuse_finish = tc && fast_scatter;
+    RbPartials red[2] = {};
+    const double* norm_part = nullptr;           // Σg² block partials of the fused finish, finalised inside the Adam launch
+    int n_norm_part = 0;
+    if ((rc = rb_tower_bwd(bj, 1, D, H, s->dropout_p, s->tower_mode, w.g_user_mlp, 0, w.ws_bwd_u, w.b_bwd, side->s,
+                           fuse_finish ? &red[0] : nullptr))) return rc;
     RB_CUDA(cudaEventRecord(side->join, side->s));
     for (int t = 0; t < items; ++t) {
         rb200_tower_bwd_job& j = bj[t];
@@ -265,12 +284,18 @@ extern "C" int rb200_bpr_step(const rb200_step_params* s, void* stream) {
         j.dRows = w.drows_pn + (size_t)t * B * D;
         j.img = tc ? w.img_item : nullptr;
     }
-    if ((rc = rb200_tower_bwd(bj, items, D, H, s->dropout_p, s->tower_mode, w.g_item_mlp, 0, w.ws_bwd, w.b_bwd, st))) return rc;
+    if ((rc = rb_tower_bwd(bj, items, D, H, s->dropout_p, s->tower_mode, w.g_item_mlp, 0, w.ws_bwd, w.b_bwd, st,
+                           fuse_finish ? &red[1] : nullptr))) return rc;
 
     RB_STAGE_EVENT();
     // ---- sparse embedding gradients: deterministic sorted-segment sums ---------------------- //
     RB_CUDA(cudaStreamWaitEvent(st, side->join, 0));          // join: user-tower gradients and sorted positions / segment starts
-    if (fast_scatter) {
+    if (fuse_finish) {
+        float* red_out[2] = {w.g_user_mlp, w.g_item_mlp};
+        if ((rc = rb_grad_finish(2, sc_ia, sc_ib, sc_na, sc_nb, sc_rw, D, sc_nr, s->padding_idx, sc_dn, sc_ui, sc_ug, sc_nu, sc_rs,
+                                 w.ws_scatter, w.b_scatter, red, red_out, dp ? 0 : 1, w.ws_sumsq, w.b_sumsq, &norm_part, &n_norm_part,
+                                 st))) return rc;
+    } else if (fast_scatter) {
         if ((rc = rb_scatter_tables(2, 2, sc_ia, sc_ib, sc_na, sc_nb, sc_rw, D, sc_nr, s->padding_idx, sc_dn, sc_ui, sc_ug, sc_nu,
                                     sc_rs, w.ws_scatter, w.b_scatter, st))) return rc;
     } else {
@@ -291,7 +316,7 @@ extern "C" int rb200_bpr_step(const rb200_step_params* s, void* stream) {
         {w.ug_u, (int64_t)B * D, w.n_uniq, D},
         {w.ug_i, (int64_t)items * B * D, w.n_uniq + 1, D},
     };
-    if ((rc = rb_sumsq_accumulate(s->opt, segs, 3, 1, w.ws_sumsq, w.b_sumsq, st))) return rc;
+    if (!fuse_finish && (rc = rb_sumsq_accumulate(s->opt, segs, 3, 1, w.ws_sumsq, w.b_sumsq, st))) return rc;
 
     RB_STAGE_EVENT();
     // ---- Adam ---------------------------------------------------------------------------------- //
@@ -303,9 +328,10 @@ extern "C" int rb200_bpr_step(const rb200_step_params* s, void* stream) {
         float* tw[2] = {s->user_table, s->item_table}; float* tm[2] = {s->user_table_m, s->item_table_m};
         float* tv[2] = {s->user_table_v, s->item_table_v}; const long long tr[2] = {s->n_user_rows, s->n_item_rows};
         int* ts[2] = {s->user_row_slot, s->item_row_slot}; const float* tg[2] = {w.ug_u, w.ug_i};
-        fused = rb_adam_step_all(mw, mg, mm, mv, mn, tw, tm, tv, tr, ts, tg, D, s->opt, st);
+        fused = rb_adam_step_all(mw, mg, mm, mv, mn, tw, tm, tv, tr, ts, tg, D, s->opt, norm_part, n_norm_part, st);
         if (fused < 0) return fused;
     }
+    if (norm_part && fused != 0 && (rc = rb_norm_from_partials(norm_part, n_norm_part, s->opt, st))) return rc;
     if (fused == 1 && (rc = rb_adam_dense2(s->user_mlp, w.g_user_mlp, s->user_mlp_m, s->user_mlp_v, Pu, s->item_mlp, w.g_item_mlp,
                                            s->item_mlp_m, s->item_mlp_v, Pi, s->opt, st))) return rc;
     if (dense && fused == 1) {

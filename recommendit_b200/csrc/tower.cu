@@ -577,13 +577,25 @@ extern "C" size_t rb200_tower_bwd_workspace_bytes(int D, int H, int extra_dim) {
     return 512 + sizeof(float) * P * (size_t)rb_sm_count() + (rb_tower_tc_supported(D, H, extra_dim) ? rb_tower_img_bytes(D, H, extra_dim) + 256 : 0);
 }
 
+// `defer` != NULL (tensor-core modes only): the weight-gradient partials are NOT reduced; *defer describes them and the
+// caller reduces them (csrc/step.cu → rb_grad_finish).  Returns 1 if the mode cannot defer (caller passes grads_out then).
+int rb_tower_bwd(const rb200_tower_bwd_job* jobs, int n_jobs, int D, int H, float dropout_p, int mode, float* grads_out,
+                 int accumulate, void* workspace, size_t workspace_bytes, cudaStream_t stream, RbPartials* defer);
+
 extern "C" int rb200_tower_bwd(const rb200_tower_bwd_job* jobs, int n_jobs, int D, int H, float dropout_p, int mode,
                                float* grads_out, int accumulate, void* workspace, size_t workspace_bytes,
                                void* stream) {
+    RB_REQUIRE(grads_out != nullptr, "tower_bwd: grads_out is NULL");
+    return rb_tower_bwd(jobs, n_jobs, D, H, dropout_p, mode, grads_out, accumulate, workspace, workspace_bytes, (cudaStream_t)stream,
+                        nullptr);
+}
+
+int rb_tower_bwd(const rb200_tower_bwd_job* jobs, int n_jobs, int D, int H, float dropout_p, int mode, float* grads_out,
+                 int accumulate, void* workspace, size_t workspace_bytes, cudaStream_t stream, RbPartials* defer) {
     RB_REQUIRE(jobs && n_jobs >= 1 && n_jobs <= MAX_JOBS, "tower_bwd: n_jobs must be 1..3");
     RB_REQUIRE(mode >= 0 && mode <= 2, "tower_bwd: mode must be 0, 1 or 2");
     RB_REQUIRE(dims_supported(D, H), "tower_bwd: unsupported widths D=%d H=%d", D, H);
-    RB_REQUIRE(grads_out != nullptr, "tower_bwd: grads_out is NULL");
+    RB_REQUIRE(grads_out != nullptr || (defer != nullptr && mode != 0), "tower_bwd: grads_out is NULL");
     BwdParams p{};
     p.n_jobs = 0;
     p.keep_scale = dropout_p > 0.f ? 1.f / (1.f - dropout_p) : 1.f;
@@ -605,9 +617,10 @@ extern "C" int rb200_tower_bwd(const rb200_tower_bwd_job* jobs, int n_jobs, int 
     }
     const int Din = D + E, Kp = (Din + 3) & ~3;
     const int P = H * Din + H + D * H + D;
-    cudaStream_t st = (cudaStream_t)stream;
+    cudaStream_t st = stream;
+    if (defer) *defer = RbPartials{nullptr, 0, P, H, Din};
     if (p.n_jobs == 0) {
-        if (!accumulate) RB_CUDA(cudaMemsetAsync(grads_out, 0, sizeof(float) * P, st));
+        if (grads_out && !accumulate) RB_CUDA(cudaMemsetAsync(grads_out, 0, sizeof(float) * P, st));
         return RB200_OK;
     }
     if (mode != 0) {
@@ -623,7 +636,8 @@ extern "C" int rb200_tower_bwd(const rb200_tower_bwd_job* jobs, int n_jobs, int 
         p.part = tar.take<float>((size_t)p.nsplit * P);
         unsigned char* img_ws = tar.take<unsigned char>(rb_tower_img_bytes(D, H, E));
         if (!workspace || !tar.ok()) return rb_set_error(RB200_ERR_WORKSPACE, "tower_bwd: workspace too small (%zu given)", workspace_bytes);
-        return rb_tower_bwd_tc(p, D, H, mode, grads_out, accumulate, img_ws, st);
+        if (defer) { defer->part = p.part; defer->nsplit = p.nsplit; }
+        return rb_tower_bwd_tc(p, D, H, mode, defer ? nullptr : grads_out, accumulate, img_ws, st);
     }
     int nsplit = rb_sm_count() / 2;
     const long long stages = (total_rows + RT - 1) / RT;

@@ -683,8 +683,15 @@ __global__ void __launch_bounds__(256) reduce_partials_tc_kernel(const float* __
     const int x = threadIdx.x & 31, y = threadIdx.x >> 5;
     const int i = blockIdx.x * 32 + x;
     float a = 0.f;
-    if (i < P)
-        for (int k = y; k < nsplit; k += 8) a += __ldg(part + (long long)k * P + i);
+    if (i < P) {
+        for (int k0 = y; k0 < nsplit; k0 += 48) {          // six independent loads in flight; additions in the order k = y, y+8, …
+            float v[6];
+#pragma unroll
+            for (int u = 0; u < 6; ++u) { const int k = k0 + 8 * u; v[u] = k < nsplit ? __ldg(part + (long long)k * P + i) : 0.f; }
+#pragma unroll
+            for (int u = 0; u < 6; ++u) a += v[u];
+        }
+    }
     sm[y][x] = a;
     __syncthreads();
     if (y == 0 && i < P) {
@@ -788,6 +795,8 @@ int rb_tower_fwd_tc(FwdParams& p, int D, int H, int mode, void* workspace, size_
 }
 
 // p.part holds the split-K partials; `img_ws` (rb_tower_img_bytes) is used when the jobs carry no image
+// grads_out == NULL: the split-K partials are left unreduced for the caller (csrc/step.cu fuses the reduction into its
+// gradient-finish kernel)
 int rb_tower_bwd_tc(BwdParams& p, int D, int H, int mode, float* grads_out, int accumulate, unsigned char* img_ws, cudaStream_t st) {
     const int E = p.job[0].E;
     if (!p.job[0].img) {
@@ -824,6 +833,7 @@ int rb_tower_bwd_tc(BwdParams& p, int D, int H, int mode, float* grads_out, int 
         else tower_bwd_weights_tc_kernel<64, 128, 96, 2><<<p.nsplit, NT, smem_w, st>>>(p, nullptr);
     }
     RB_LAUNCH_CHECK("tower_bwd_weights_tc_kernel");
+    if (!grads_out) return RB200_OK;
     reduce_partials_tc_kernel<<<(p.P + 31) / 32, 256, 0, st>>>(p.part, p.nsplit, p.P, H, 64 + E, grads_out, accumulate);
     RB_LAUNCH_CHECK("reduce_partials_tc_kernel");
     return RB200_OK;
