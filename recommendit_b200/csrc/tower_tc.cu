@@ -193,13 +193,14 @@ __global__ void __launch_bounds__(NTD, 1) tower_fwd_tc_kernel(const FwdParams p)
     }
     {
         // lane → (row%8 = lane&7, 16-byte chunk = 4·cq + lane>>3): 64-byte global segments, conflict-free 16-byte stores;
-        // three units' loads are issued before their stores so that the gather latencies overlap
+        // several units' loads are issued before their stores so that the gather latencies overlap
         const int K4 = Kp / 4, CQ = (K4 + 3) / 4, n_units = (ROWS / 8) * CQ;
-        for (int u0 = warp; u0 < n_units; u0 += 3 * (NTD / 32)) {
-            float4 v[3];
-            int rr[3], kk[3];
+        constexpr int UF = 6;       // units in flight per warp: the whole tile's gather is one round of loads at D+E <= 96
+        for (int u0 = warp; u0 < n_units; u0 += UF * (NTD / 32)) {
+            float4 v[UF];
+            int rr[UF], kk[UF];
 #pragma unroll
-            for (int q = 0; q < 3; ++q) {
+            for (int q = 0; q < UF; ++q) {
                 const int u = u0 + q * (NTD / 32);
                 const int rg = u / CQ, cq = u - rg * CQ;
                 const int r = rg * 8 + (lane & 7), c4 = cq * 4 + (lane >> 3);
@@ -220,7 +221,7 @@ __global__ void __launch_bounds__(NTD, 1) tower_fwd_tc_kernel(const FwdParams p)
                 }
             }
 #pragma unroll
-            for (int q = 0; q < 3; ++q)
+            for (int q = 0; q < UF; ++q)
                 if (kk[q] >= 0) put4<MODE>(x_hi, x_lo, ROWS, rr[q], kk[q], v[q]);
         }
     }
@@ -232,6 +233,9 @@ __global__ void __launch_bounds__(NTD, 1) tower_fwd_tc_kernel(const FwdParams p)
         issue_gemm<MODE>(tmem, x_hi, x_lo, ROWS, w1_hi, w1_lo, H, H, Kp, false);
         umma::commit(&mma_bar_s);
     }
+    float4 bias1[8];                       // this thread's 32 hidden-unit biases, fetched while GEMM1 runs
+#pragma unroll
+    for (int i4 = 0; i4 < 8; ++i4) bias1[i4] = __ldg(reinterpret_cast<const float4*>(J.b1 + half * 32) + i4);
     mma_bar.wait();
     umma::fence_after_sync();
 
@@ -267,8 +271,7 @@ __global__ void __launch_bounds__(NTD, 1) tower_fwd_tc_kernel(const FwdParams p)
                     rnd = rb_philox4x32(make_uint4((uint32_t)row, (uint32_t)(col >> 2), (uint32_t)drop_off, (uint32_t)(drop_off >> 32)),
                                         make_uint2((uint32_t)p.seed, (uint32_t)(p.seed >> 32)));
                 const uint32_t rw[4] = {rnd.x, rnd.y, rnd.z, rnd.w};
-                const float4 bias = __ldg(reinterpret_cast<const float4*>(J.b1 + col));
-                const float bv[4] = {bias.x, bias.y, bias.z, bias.w};
+                const float bv[4] = {bias1[i4].x, bias1[i4].y, bias1[i4].z, bias1[i4].w};
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
                     float x = fmaxf(v[i4 * 4 + e] + bv[e], 0.f);
@@ -310,6 +313,9 @@ __global__ void __launch_bounds__(NTD, 1) tower_fwd_tc_kernel(const FwdParams p)
             }
         }
     }
+    float4 bias2[D / 16];
+#pragma unroll
+    for (int i4 = 0; i4 < D / 16; ++i4) bias2[i4] = __ldg(reinterpret_cast<const float4*>(J.b2 + half * (D / 4)) + i4);
     mma_bar.wait();
     umma::fence_after_sync();
 
@@ -322,7 +328,7 @@ __global__ void __launch_bounds__(NTD, 1) tower_fwd_tc_kernel(const FwdParams p)
         umma::tmem_ld16(tmem + lane_off + H + half * QC, y);
 #pragma unroll
         for (int i4 = 0; i4 < QC / 4; ++i4) {
-            const float4 b = __ldg(reinterpret_cast<const float4*>(J.b2 + half * QC) + i4);
+            const float4 b = bias2[i4];
             y[i4 * 4] += b.x; y[i4 * 4 + 1] += b.y; y[i4 * 4 + 2] += b.z; y[i4 * 4 + 3] += b.w;
         }
 #pragma unroll

@@ -137,10 +137,12 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
 }
 
 // ---- 3xTF32 split ------------------------------------------------------------------------------------------- //
-__device__ __forceinline__ float tf32_hi(float x) {     // round-to-nearest tf32, low 13 mantissa bits zero
-    uint32_t u;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
-    return __uint_as_float(u);
+// round-to-nearest (ties away from zero) tf32 with the low 13 mantissa bits zero — what cvt.rna.tf32.f32 returns, done on
+// the integer pipe: adding half a tf32 ulp to the sign-magnitude bit pattern and truncating IS that rounding (the carry into
+// the exponent is the correct result).  The conversion instruction issues at a fraction of the ALU rate and showed up as the
+// top stall in the staging code of every tensor-core kernel.
+__device__ __forceinline__ float tf32_hi(float x) {
+    return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u);
 }
 __device__ __forceinline__ void split4(const float4& x, float4& hi, float4& lo) {
     hi.x = tf32_hi(x.x); hi.y = tf32_hi(x.y); hi.z = tf32_hi(x.z); hi.w = tf32_hi(x.w);
