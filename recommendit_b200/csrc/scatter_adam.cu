@@ -381,9 +381,9 @@ __global__ void __launch_bounds__(NT) sumsq_kernel(const SumsqSegs segs, double*
 
 // ------------------------------------------------------------------------------------------------------------ //
 // Gradient finish of the fused training step, ONE launch instead of four:
-//   blocks [0, nb_seg)            deterministic segment sums of the embedding-row gradients (segment_sum2, 1 segment / warp)
-//   blocks [nb_seg, +nb_red[0])   reduction of the user tower's split-K weight-gradient partials   (reduce_partials_tc)
+//   blocks [0, nb_red[0])         reduction of the user tower's split-K weight-gradient partials   (reduce_partials_tc)
 //   blocks [.., +nb_red[1])       … of the item towers'
+//   blocks [.., +nb_seg)          deterministic segment sums of the embedding-row gradients (segment_sum2, 1 segment / warp)
 // and, with do_sumsq, Σ g² of everything those blocks produce (fp64 block partials; the last block to finish adds them in
 // index order and derives total_norm / clip_coef): clip_grad_norm_ needs no pass of its own.
 // ------------------------------------------------------------------------------------------------------------ //
@@ -395,8 +395,11 @@ __global__ void __launch_bounds__(NT) grad_finish_kernel(const FinishParams p, d
     __shared__ float sm[8][33];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     double sq = 0.0;
-    if ((int)blockIdx.x < p.nb_seg) {
-        int w = blockIdx.x * (NT / 32) + warp;
+    // the partial-reduction blocks come FIRST in the grid: each is one long chain of dependent-latency loads, so they should
+    // be resident from the start and overlap the many short segment blocks behind them
+    const int nb_red_all = p.nb_red[0] + p.nb_red[1];
+    if ((int)blockIdx.x >= nb_red_all) {
+        int w = ((int)blockIdx.x - nb_red_all) * (NT / 32) + warp;
         int j = 0;
         if (p.seg.n_jobs > 1 && w >= p.seg.job[0].cap) { w -= p.seg.job[0].cap; j = 1; }
         const SegJob& J = p.seg.job[j];
@@ -421,7 +424,7 @@ __global__ void __launch_bounds__(NT) grad_finish_kernel(const FinishParams p, d
             }
         }
     } else {
-        int b = (int)blockIdx.x - p.nb_seg, r = 0;
+        int b = (int)blockIdx.x, r = 0;
         if (b >= p.nb_red[0]) { b -= p.nb_red[0]; r = 1; }
         const RedSet& R = p.red[r];
         const int x = lane, y = warp;
