@@ -500,15 +500,21 @@ __global__ void __launch_bounds__(NT) select_topk_kernel(const float* __restrict
         __syncthreads();
         const int bstar = s_a, m_fast = s_b;
         if (m_fast <= SORT_CAP && scale > 0.f) {
-            for (int base = 0; base < n; base += NT) {
-                const int i = base + tid;
-                bool take = false; float v = 0.f;
-                if (i < n) { v = src[i]; take = min(NBK - 1, (int)((v - lo) * scale)) >= bstar; }
-                const uint32_t bal = __ballot_sync(RB_FULL_MASK, take);
-                int wbase = 0;
-                if (lane == 0 && bal) wbase = atomicAdd(&s_count, __popc(bal));
-                wbase = __shfl_sync(RB_FULL_MASK, wbase, 0);
-                if (take) { const int p = wbase + __popc(bal & ((1u << lane) - 1u)); skey[p] = f2key(v); sidx[p] = i; }
+            // compaction without a per-iteration atomic (measured: the ballot + atomicAdd loop was 29 % of the kernel): every
+            // thread counts its own survivors, one block-wide exclusive scan places them, a second pass writes them.  The
+            // order of the survivors is irrelevant (they are sorted by (score, position) below).
+            int cnt = 0;
+            for (int i = tid; i < n; i += NT) cnt += (min(NBK - 1, (int)((src[i] - lo) * scale)) >= bstar) ? 1 : 0;
+            int incl = cnt;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(RB_FULL_MASK, incl, o); if (lane >= o) incl += t; }
+            if (lane == 31) wsum[1][warp] = incl;
+            __syncthreads();
+            int p = incl - cnt;
+            for (int w = 0; w < warp; ++w) p += wsum[1][w];
+            for (int i = tid; i < n; i += NT) {
+                const float v = src[i];
+                if (min(NBK - 1, (int)((v - lo) * scale)) >= bstar) { skey[p] = f2key(v); sidx[p] = i; ++p; }
             }
             m = m_fast; done = true;
         }
@@ -564,6 +570,55 @@ __global__ void __launch_bounds__(NT) select_topk_kernel(const float* __restrict
     while (sort_n < m) sort_n <<= 1;
     __syncthreads();
     for (int i = m + tid; i < sort_n; i += NT) { skey[i] = 0u; sidx[i] = 0x7fffffff; }
+    if (sort_n == 1024) {
+        // the common top-500 case (512 < m <= 1024): 4 consecutive entries per thread as 64-bit composites (key, inverted
+        // position) in registers; strides 1-2 are register swaps, 4-64 warp shuffles, only strides >= 128 (6 of the 55 steps)
+        // go through shared memory — the all-shared-memory network below costs a __syncthreads per step
+        unsigned long long v[4];
+        unsigned long long* xbuf = reinterpret_cast<unsigned long long*>(skey);      // skey|sidx = 16 KB, reused for exchanges
+        __syncthreads();                                                             // padding entries written above
+#pragma unroll
+        for (int e = 0; e < 4; ++e) v[e] = ((unsigned long long)skey[4 * tid + e] << 32) | (uint32_t)(0xFFFFFFFFu - (uint32_t)sidx[4 * tid + e]);
+        __syncthreads();
+        for (int size = 2; size <= 1024; size <<= 1) {
+            for (int stride = size >> 1; stride > 0; stride >>= 1) {
+                if (stride >= 128) {
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) xbuf[4 * tid + e] = v[e];
+                    __syncthreads();
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const int i = 4 * tid + e;
+                        const unsigned long long pv = xbuf[i ^ stride];
+                        const bool keep_max = ((i & stride) == 0) == ((i & size) == 0);
+                        v[e] = keep_max ? (v[e] > pv ? v[e] : pv) : (v[e] < pv ? v[e] : pv);
+                    }
+                    __syncthreads();
+                } else if (stride >= 4) {
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const int i = 4 * tid + e;
+                        const unsigned long long pv = __shfl_xor_sync(RB_FULL_MASK, v[e], stride >> 2);
+                        const bool keep_max = ((i & stride) == 0) == ((i & size) == 0);
+                        v[e] = keep_max ? (v[e] > pv ? v[e] : pv) : (v[e] < pv ? v[e] : pv);
+                    }
+                } else {
+                    const bool desc = ((4 * tid) & size) == 0;       // size >= 4 here or the pair shares the block bit
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        if ((e & stride) == 0) {
+                            const bool d2 = size >= 4 ? desc : (((4 * tid + e) & size) == 0);
+                            const unsigned long long a = v[e], b = v[e | stride];
+                            const unsigned long long hi = a > b ? a : b, lo = a > b ? b : a;
+                            v[e] = d2 ? hi : lo; v[e | stride] = d2 ? lo : hi;
+                        }
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int e = 0; e < 4; ++e) { skey[4 * tid + e] = (uint32_t)(v[e] >> 32); sidx[4 * tid + e] = (int)(0xFFFFFFFFu - (uint32_t)v[e]); }
+    } else
     for (int size = 2; size <= sort_n; size <<= 1) {
         for (int stride = size >> 1; stride > 0; stride >>= 1) {
             __syncthreads();
