@@ -418,6 +418,58 @@ constexpr int NBK = 1024;        // value-range buckets of the fast path (fine e
 //               compact every candidate in buckets ≥ b* (winners + boundary bucket), bitonic-sort that small set by
 //               (score desc, candidate position asc) and emit the first k.
 //   fallback  : exact MSB-first radix select (many equal scores / boundary bucket too large).
+// Bitonic sort of NT·EPT entries, descending by (key, then ascending position): EPT consecutive entries per thread as 64-bit
+// composites (key, inverted position) in registers; strides < EPT are register swaps, strides < 32·EPT warp shuffles, only the
+// larger ones go through shared memory (6 of the 45 / 55 steps at 512 / 1024 entries) — the all-shared-memory network costs a
+// __syncthreads per step.  skey|sidx (16 KB) double as the exchange buffer.
+template <int EPT>
+__device__ __forceinline__ void reg_bitonic_sort(uint32_t* skey, int* sidx, int tid) {
+    constexpr int N = NT * EPT;
+    unsigned long long v[EPT];
+    unsigned long long* xbuf = reinterpret_cast<unsigned long long*>(skey);
+    __syncthreads();                                                             // entries (and padding) written by other threads
+#pragma unroll
+    for (int e = 0; e < EPT; ++e) v[e] = ((unsigned long long)skey[EPT * tid + e] << 32) | (uint32_t)(0xFFFFFFFFu - (uint32_t)sidx[EPT * tid + e]);
+    __syncthreads();
+    for (int size = 2; size <= N; size <<= 1) {
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+            if (stride >= 32 * EPT) {
+#pragma unroll
+                for (int e = 0; e < EPT; ++e) xbuf[EPT * tid + e] = v[e];
+                __syncthreads();
+#pragma unroll
+                for (int e = 0; e < EPT; ++e) {
+                    const int i = EPT * tid + e;
+                    const unsigned long long pv = xbuf[i ^ stride];
+                    const bool keep_max = ((i & stride) == 0) == ((i & size) == 0);
+                    v[e] = keep_max ? (v[e] > pv ? v[e] : pv) : (v[e] < pv ? v[e] : pv);
+                }
+                __syncthreads();
+            } else if (stride >= EPT) {
+#pragma unroll
+                for (int e = 0; e < EPT; ++e) {
+                    const int i = EPT * tid + e;
+                    const unsigned long long pv = __shfl_xor_sync(RB_FULL_MASK, v[e], stride / EPT);
+                    const bool keep_max = ((i & stride) == 0) == ((i & size) == 0);
+                    v[e] = keep_max ? (v[e] > pv ? v[e] : pv) : (v[e] < pv ? v[e] : pv);
+                }
+            } else {
+#pragma unroll
+                for (int e = 0; e < EPT; ++e) {
+                    if ((e & stride) == 0) {
+                        const bool desc = ((EPT * tid + e) & size) == 0;
+                        const unsigned long long a = v[e], b = v[e | stride];
+                        const unsigned long long hi = a > b ? a : b, lo = a > b ? b : a;
+                        v[e] = desc ? hi : lo; v[e | stride] = desc ? lo : hi;
+                    }
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int e = 0; e < EPT; ++e) { skey[EPT * tid + e] = (uint32_t)(v[e] >> 32); sidx[EPT * tid + e] = (int)(0xFFFFFFFFu - (uint32_t)v[e]); }
+}
+
 template <typename R>
 __global__ void __launch_bounds__(NT) select_topk_kernel(const float* __restrict__ cand, const long long* __restrict__ cand_off,
                                                          long long fixed_stride, const long long* __restrict__ counts,
@@ -437,6 +489,8 @@ __global__ void __launch_bounds__(NT) select_topk_kernel(const float* __restrict
     const float* src = cand + (cand_off ? cand_off[q] : (long long)q * fixed_stride);
     const int n = counts ? (int)counts[q] : fixed_count;
 
+    float lo = FLT_MAX, hi = -FLT_MAX;          // range of the scores, gathered while they are being cached
+    bool have_range = false;
     if (n <= cache_cap) {
         // 8 independent loads in flight per thread (a plain copy loop serialises on every load's latency)
         for (int i0 = tid; i0 < n; i0 += 8 * NT) {
@@ -444,10 +498,14 @@ __global__ void __launch_bounds__(NT) select_topk_kernel(const float* __restrict
 #pragma unroll
             for (int b = 0; b < 8; ++b) { const int i = i0 + b * NT; v[b] = i < n ? __ldg(src + i) : 0.f; }
 #pragma unroll
-            for (int b = 0; b < 8; ++b) { const int i = i0 + b * NT; if (i < n) cache[i] = v[b]; }
+            for (int b = 0; b < 8; ++b) {
+                const int i = i0 + b * NT;
+                if (i < n) { cache[i] = v[b]; lo = fminf(lo, v[b]); hi = fmaxf(hi, v[b]); }
+            }
         }
         __syncthreads();
         src = cache;
+        have_range = true;
     }
     int m = 0;                       // number of entries placed in skey/sidx
     bool done = false;
@@ -457,8 +515,8 @@ __global__ void __launch_bounds__(NT) select_topk_kernel(const float* __restrict
         m = n; done = true;
     } else {
         // ---- fast path ------------------------------------------------------------------------------------ //
-        float lo = FLT_MAX, hi = -FLT_MAX;
-        for (int i = tid; i < n; i += NT) { const float v = src[i]; lo = fminf(lo, v); hi = fmaxf(hi, v); }
+        if (!have_range)
+            for (int i = tid; i < n; i += NT) { const float v = src[i]; lo = fminf(lo, v); hi = fmaxf(hi, v); }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
             lo = fminf(lo, __shfl_xor_sync(RB_FULL_MASK, lo, o));
@@ -503,20 +561,49 @@ __global__ void __launch_bounds__(NT) select_topk_kernel(const float* __restrict
             // compaction without a per-iteration atomic (measured: the ballot + atomicAdd loop was 29 % of the kernel): every
             // thread counts its own survivors, one block-wide exclusive scan places them, a second pass writes them.  The
             // order of the survivors is irrelevant (they are sorted by (score, position) below).
-            int cnt = 0;
-            for (int i = tid; i < n; i += NT) cnt += (min(NBK - 1, (int)((src[i] - lo) * scale)) >= bstar) ? 1 : 0;
-            int incl = cnt;
+            // Entries above the boundary bucket are certainly among the k best; of the c_b entries IN the boundary bucket only the
+            // best r = k − (count above) are.  When that makes exactly k <= 512 entries the final sort runs on 512 instead of
+            // 1024 slots, so the boundary bucket (a handful of entries) is cut by exact rank first.
+            const int c_b = hist_f[bstar], n_above = m_fast - c_b, r_keep = k - n_above;
+            const bool cut = m_fast > 512 && k <= 512 && c_b <= 512;
+            int cnt_a = 0, cnt_b = 0;
+            for (int i = tid; i < n; i += NT) {
+                const int b = min(NBK - 1, (int)((src[i] - lo) * scale));
+                cnt_a += b > bstar ? 1 : 0; cnt_b += b == bstar ? 1 : 0;
+            }
+            int inc_a = cnt_a, inc_b = cnt_b;
 #pragma unroll
-            for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(RB_FULL_MASK, incl, o); if (lane >= o) incl += t; }
-            if (lane == 31) wsum[1][warp] = incl;
+            for (int o = 1; o < 32; o <<= 1) {
+                const int ta = __shfl_up_sync(RB_FULL_MASK, inc_a, o), tb = __shfl_up_sync(RB_FULL_MASK, inc_b, o);
+                if (lane >= o) { inc_a += ta; inc_b += tb; }
+            }
+            if (lane == 31) { wsum[0][warp] = inc_a; wsum[1][warp] = inc_b; }
             __syncthreads();
-            int p = incl - cnt;
-            for (int w = 0; w < warp; ++w) p += wsum[1][w];
+            int pa = inc_a - cnt_a, pb = inc_b - cnt_b;
+            for (int w = 0; w < warp; ++w) { pa += wsum[0][w]; pb += wsum[1][w]; }
+            // boundary entries: behind the others (plain compaction) or parked at the end of the sort buffer (exact cut)
+            const int b_base = cut ? SORT_CAP - c_b : n_above;
             for (int i = tid; i < n; i += NT) {
                 const float v = src[i];
-                if (min(NBK - 1, (int)((v - lo) * scale)) >= bstar) { skey[p] = f2key(v); sidx[p] = i; ++p; }
+                const int b = min(NBK - 1, (int)((v - lo) * scale));
+                if (b > bstar) { skey[pa] = f2key(v); sidx[pa] = i; ++pa; }
+                else if (b == bstar) { skey[b_base + pb] = f2key(v); sidx[b_base + pb] = i; ++pb; }
             }
-            m = m_fast; done = true;
+            m = m_fast;
+            if (cut) {
+                __syncthreads();
+                for (int j = tid; j < c_b; j += NT) {
+                    const uint32_t kj = skey[b_base + j]; const int ij = sidx[b_base + j];
+                    int rank = 0;
+                    for (int t = 0; t < c_b; ++t) {
+                        const uint32_t kt = skey[b_base + t]; const int it = sidx[b_base + t];
+                        rank += (kt > kj || (kt == kj && it < ij)) ? 1 : 0;
+                    }
+                    if (rank < r_keep) { skey[n_above + rank] = kj; sidx[n_above + rank] = ij; }     // ranks are distinct
+                }
+                m = k;
+            }
+            done = true;
         }
     }
     if (!done) {
@@ -570,55 +657,9 @@ __global__ void __launch_bounds__(NT) select_topk_kernel(const float* __restrict
     while (sort_n < m) sort_n <<= 1;
     __syncthreads();
     for (int i = m + tid; i < sort_n; i += NT) { skey[i] = 0u; sidx[i] = 0x7fffffff; }
-    if (sort_n == 1024) {
-        // the common top-500 case (512 < m <= 1024): 4 consecutive entries per thread as 64-bit composites (key, inverted
-        // position) in registers; strides 1-2 are register swaps, 4-64 warp shuffles, only strides >= 128 (6 of the 55 steps)
-        // go through shared memory — the all-shared-memory network below costs a __syncthreads per step
-        unsigned long long v[4];
-        unsigned long long* xbuf = reinterpret_cast<unsigned long long*>(skey);      // skey|sidx = 16 KB, reused for exchanges
-        __syncthreads();                                                             // padding entries written above
-#pragma unroll
-        for (int e = 0; e < 4; ++e) v[e] = ((unsigned long long)skey[4 * tid + e] << 32) | (uint32_t)(0xFFFFFFFFu - (uint32_t)sidx[4 * tid + e]);
-        __syncthreads();
-        for (int size = 2; size <= 1024; size <<= 1) {
-            for (int stride = size >> 1; stride > 0; stride >>= 1) {
-                if (stride >= 128) {
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) xbuf[4 * tid + e] = v[e];
-                    __syncthreads();
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                        const int i = 4 * tid + e;
-                        const unsigned long long pv = xbuf[i ^ stride];
-                        const bool keep_max = ((i & stride) == 0) == ((i & size) == 0);
-                        v[e] = keep_max ? (v[e] > pv ? v[e] : pv) : (v[e] < pv ? v[e] : pv);
-                    }
-                    __syncthreads();
-                } else if (stride >= 4) {
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                        const int i = 4 * tid + e;
-                        const unsigned long long pv = __shfl_xor_sync(RB_FULL_MASK, v[e], stride >> 2);
-                        const bool keep_max = ((i & stride) == 0) == ((i & size) == 0);
-                        v[e] = keep_max ? (v[e] > pv ? v[e] : pv) : (v[e] < pv ? v[e] : pv);
-                    }
-                } else {
-                    const bool desc = ((4 * tid) & size) == 0;       // size >= 4 here or the pair shares the block bit
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                        if ((e & stride) == 0) {
-                            const bool d2 = size >= 4 ? desc : (((4 * tid + e) & size) == 0);
-                            const unsigned long long a = v[e], b = v[e | stride];
-                            const unsigned long long hi = a > b ? a : b, lo = a > b ? b : a;
-                            v[e] = d2 ? hi : lo; v[e | stride] = d2 ? lo : hi;
-                        }
-                    }
-                }
-            }
-        }
-#pragma unroll
-        for (int e = 0; e < 4; ++e) { skey[4 * tid + e] = (uint32_t)(v[e] >> 32); sidx[4 * tid + e] = (int)(0xFFFFFFFFu - (uint32_t)v[e]); }
-    } else
+    if (sort_n == 1024) reg_bitonic_sort<4>(skey, sidx, tid);
+    else if (sort_n == 512) reg_bitonic_sort<2>(skey, sidx, tid);
+    else
     for (int size = 2; size <= sort_n; size <<= 1) {
         for (int stride = size >> 1; stride > 0; stride >>= 1) {
             __syncthreads();
