@@ -161,6 +161,15 @@ int rb200_scatter_reset_slots(const int64_t* uniq_ids, const int* n_uniq, int ma
 /* row_slot[uniq_ids[i]] = i for i < n_uniq[0] (when the compact list was produced without a slot map) */
 int rb200_scatter_set_slots(const int64_t* uniq_ids, const int* n_uniq, int max_uniq, int* row_slot,
                             void* stream);
+/* Exchange plan of the row-sharded step (tables sharded by id mod world, both shards of a rank in
+ * one tensor: user rows first, item rows behind them).  Requests = [user_ids | item_ids] (n = n_user + n_item) in sample
+ * order; bucket order = stable by owner.  perm[j] = sample of bucket position j, inv = its inverse, local_rows[j] = row in
+ * the owner's combined shard (id / world, + user_rows_by_rank[owner] for items), send_counts[w] = requests owned by w.
+ * All device pointers; deterministic. */
+size_t rb200_route_plan_workspace_bytes(int64_t n, int world);
+int rb200_route_plan(const int64_t* user_ids, int64_t n_user, const int64_t* item_ids, int64_t n_item, int world,
+                     const int64_t* user_rows_by_rank, int64_t* perm, int64_t* inv, int64_t* local_rows,
+                     int64_t* send_counts, void* workspace, size_t workspace_bytes, void* stream);
 /* out[i,:] = table[rows[i],:] — the owner-side row gather of row-sharded tables; rows outside
  * [0, n_table_rows) yield zeros */
 int rb200_gather_rows(const float* table, const int64_t* rows, int64_t n, int D, int64_t n_table_rows,

@@ -96,6 +96,8 @@ SIGNATURES = {
     "rb200_scatter_reset_slots": (I, [P, P, I, P, P]),
     "rb200_scatter_set_slots": (I, [P, P, I, P, P]),
     "rb200_gather_rows": (I, [P, P, I64, I, I64, P, P]),
+    "rb200_route_plan_workspace_bytes": (SZ, [I64, I]),
+    "rb200_route_plan": (I, [P, I64, P, I64, I, P, P, P, P, P, P, SZ, P]),
     "rb200_opt_begin_step": (I, [P, P]),
     "rb200_sumsq_accumulate": (I, [P, C.POINTER(SumsqSeg), I, P, SZ, P]),
     "rb200_sumsq_workspace_bytes": (SZ, []),

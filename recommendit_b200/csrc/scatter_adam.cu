@@ -1040,3 +1040,77 @@ int rb_reset_slots2(const int64_t* ids0, const int* n0, int cap0, int* slot0, co
     RB_LAUNCH_CHECK("reset_slots2_kernel");
     return RB200_OK;
 }
+
+// ------------------------------------------------------------------------------------------------------------ //
+// exchange plan of the row-sharded step: stable partition of the requests by owner (one 1-pass radix sort on log2(world) bits)
+// ------------------------------------------------------------------------------------------------------------ //
+namespace {
+__global__ void __launch_bounds__(NT) route_prep_kernel(const int64_t* __restrict__ user_ids, long long n_user,
+                                                        const int64_t* __restrict__ item_ids, long long n, int world,
+                                                        const int64_t* __restrict__ user_rows_by_rank, unsigned* __restrict__ keys,
+                                                        int* __restrict__ vals, int64_t* __restrict__ local, int* __restrict__ counts) {
+    const long long i = (long long)blockIdx.x * NT + threadIdx.x;
+    if (i >= n) return;
+    const bool is_item = i >= n_user;
+    const long long id = is_item ? item_ids[i - n_user] : user_ids[i];
+    const int owner = (int)(id % world);
+    keys[i] = (unsigned)owner;
+    vals[i] = (int)i;
+    local[i] = id / world + (is_item ? user_rows_by_rank[owner] : 0);
+    atomicAdd(&counts[owner], 1);                 // integer: the result does not depend on the order
+}
+__global__ void __launch_bounds__(NT) route_finish_kernel(const int* __restrict__ vals_sorted, const int64_t* __restrict__ local,
+                                                          long long n, int world, const int* __restrict__ counts,
+                                                          int64_t* __restrict__ perm, int64_t* __restrict__ inv,
+                                                          int64_t* __restrict__ local_rows, int64_t* __restrict__ send_counts) {
+    const long long j = (long long)blockIdx.x * NT + threadIdx.x;
+    if (j < world) send_counts[j] = counts[j];
+    if (j >= n) return;
+    const int smp = vals_sorted[j];
+    perm[j] = smp;
+    inv[smp] = j;
+    local_rows[j] = local[smp];
+}
+size_t route_temp_bytes(long long n, int bits) {
+    size_t t = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, t, (const unsigned*)nullptr, (unsigned*)nullptr, (const int*)nullptr, (int*)nullptr, (int)n, 0, bits);
+    return t;
+}
+}  // namespace
+
+extern "C" size_t rb200_route_plan_workspace_bytes(int64_t n, int world) {
+    if (n < 1) n = 1;
+    return 256 * 8 + sizeof(unsigned) * 2 * (size_t)n + sizeof(int) * (2 * (size_t)n + (size_t)world) + sizeof(int64_t) * (size_t)n +
+           route_temp_bytes(n, 32);
+}
+
+extern "C" int rb200_route_plan(const int64_t* user_ids, int64_t n_user, const int64_t* item_ids, int64_t n_item, int world,
+                                const int64_t* user_rows_by_rank, int64_t* perm, int64_t* inv, int64_t* local_rows,
+                                int64_t* send_counts, void* workspace, size_t workspace_bytes, void* stream) {
+    const long long n = n_user + n_item;
+    RB_REQUIRE(n_user >= 0 && n_item >= 0 && world >= 1 && n < (1ll << 31), "route_plan: bad sizes");
+    RB_REQUIRE((n_user == 0 || user_ids) && (n_item == 0 || item_ids) && user_rows_by_rank && perm && inv && local_rows && send_counts,
+               "route_plan: NULL pointer");
+    cudaStream_t st = (cudaStream_t)stream;
+    RbArena ar(workspace, workspace_bytes);
+    unsigned* keys = ar.take<unsigned>(n > 0 ? n : 1); unsigned* keys_out = ar.take<unsigned>(n > 0 ? n : 1);
+    int* vals = ar.take<int>(n > 0 ? n : 1); int* vals_out = ar.take<int>(n > 0 ? n : 1);
+    int* counts = ar.take<int>(world);
+    int64_t* local = ar.take<int64_t>(n > 0 ? n : 1);
+    int bits = 1;
+    while ((1 << bits) < world) ++bits;
+    size_t tb = route_temp_bytes(n > 0 ? n : 1, bits);
+    char* temp = ar.take<char>(tb);
+    if (!workspace || !ar.ok()) return rb_set_error(RB200_ERR_WORKSPACE, "route_plan: workspace too small (%zu given)", workspace_bytes);
+    RB_CUDA(cudaMemsetAsync(counts, 0, sizeof(int) * world, st));
+    if (n > 0) {
+        const unsigned grid = (unsigned)((n + NT - 1) / NT);
+        route_prep_kernel<<<grid, NT, 0, st>>>(user_ids, n_user, item_ids, n, world, user_rows_by_rank, keys, vals, local, counts);
+        RB_LAUNCH_CHECK("route_prep_kernel");
+        RB_CUDA(cub::DeviceRadixSort::SortPairs(temp, tb, (const unsigned*)keys, keys_out, (const int*)vals, vals_out, (int)n, 0, bits, st));
+    }
+    const long long m = n > world ? n : world;
+    route_finish_kernel<<<(unsigned)((m + NT - 1) / NT), NT, 0, st>>>(vals_out, local, n, world, counts, perm, inv, local_rows, send_counts);
+    RB_LAUNCH_CHECK("route_finish_kernel");
+    return RB200_OK;
+}

@@ -61,6 +61,19 @@ def make_route(ids: torch.Tensor, world: int) -> Route:
                  send_counts=[int(c) for c in counts.tolist()])
 
 
+def route_reference(user_ids: torch.Tensor, item_ids: torch.Tensor, world: int, nu_by_rank: torch.Tensor):
+    """What ``rb200_route_plan`` computes, restated with generic tensor ops — used by the CPU test back end
+    (tests/oracle_ops.py) and as the oracle of the kernel's GPU test; the product path calls the kernel."""
+    ids = torch.cat([user_ids, item_ids])
+    owner = ids % world
+    local = torch.div(ids, world, rounding_mode="floor")
+    local[user_ids.numel():] += nu_by_rank[owner[user_ids.numel():]]          # item rows sit behind the owner's user rows
+    perm = torch.argsort(owner, stable=True)
+    inv = torch.empty_like(perm)
+    inv[perm] = torch.arange(ids.numel(), device=ids.device, dtype=perm.dtype)
+    return perm, inv, local[perm].contiguous(), torch.bincount(owner, minlength=world)
+
+
 def shard_rows(n_rows: int, world: int, rank: int) -> int:
     """rows of a table with global ids 0..n_rows-1 owned by ``rank`` under modulo sharding"""
     return (n_rows - rank + world - 1) // world if n_rows > rank else 0
@@ -97,6 +110,19 @@ class CudaOps:
         from .two_tower import tower_mode_for
         E = max(0 if j.get("extra") is None else j["extra"].shape[1] for j in jobs)
         return tower_mode_for(D, H, E)
+
+    def route(self, user_ids: torch.Tensor, item_ids: torch.Tensor, world: int, nu_by_rank: torch.Tensor):
+        """→ (perm, inv, local_rows, send_counts) of the combined request list, one C call (``rb200_route_plan``)"""
+        n = user_ids.numel() + item_ids.numel()
+        dev = user_ids.device
+        perm = torch.empty(n, dtype=torch.int64, device=dev)
+        inv, local = torch.empty_like(perm), torch.empty_like(perm)
+        send = torch.empty(world, dtype=torch.int64, device=dev)
+        wsb = self.lib.rb200_route_plan_workspace_bytes(n, world)
+        ws = workspace(wsb, dev)
+        check(self.lib.rb200_route_plan(ptr(user_ids), user_ids.numel(), ptr(item_ids), item_ids.numel(), world, ptr(nu_by_rank),
+                                        ptr(perm), ptr(inv), ptr(local), ptr(send), ptr(ws), wsb, stream_ptr()), "rb200_route_plan")
+        return perm, inv, local, send
 
     def gather_rows(self, table: torch.Tensor, rows: torch.Tensor) -> torch.Tensor:
         out = torch.empty(rows.numel(), table.shape[1], dtype=torch.float32, device=table.device)
@@ -269,17 +295,11 @@ class ShardedBPRTrainer:
     def _route(self, user_ids: torch.Tensor, item_ids: torch.Tensor) -> Route:
         """Requests of BOTH tables in one plan: sample order = [user ids | item ids], bucket order = stable by owner."""
         W = self.world
-        ids = torch.cat([user_ids, item_ids])
-        owner = ids % W
-        local = torch.div(ids, W, rounding_mode="floor")
-        local[user_ids.numel():] += self._nu_by_rank[owner[user_ids.numel():]]      # item rows sit behind the owner's user rows
-        perm = torch.argsort(owner, stable=True)
-        inv = torch.empty_like(perm)
-        inv[perm] = torch.arange(ids.numel(), device=ids.device, dtype=perm.dtype)
-        send = torch.bincount(owner, minlength=W)
-        rt = Route(perm=perm, inv=inv, local_rows=local[perm].contiguous(), send_counts=None)
+        n = user_ids.numel() + item_ids.numel()
+        perm, inv, local_rows, send = self.ops.route(user_ids.contiguous(), item_ids.contiguous(), W, self._nu_by_rank)
+        rt = Route(perm=perm, inv=inv, local_rows=local_rows, send_counts=None)
         if W == 1:
-            rt.send_counts = rt.recv_counts = [ids.numel()]
+            rt.send_counts = rt.recv_counts = [n]
             rt.recv_rows = rt.local_rows
             return rt
         recv = torch.empty_like(send)

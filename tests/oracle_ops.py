@@ -16,6 +16,10 @@ def _np(t):
 
 
 class OracleOps:
+    def route(self, user_ids, item_ids, world, nu_by_rank):
+        from recommendit_b200.sharded import route_reference
+        return route_reference(user_ids, item_ids, world, nu_by_rank)
+
     def gather_rows(self, table, rows):
         out = torch.zeros(rows.numel(), table.shape[1], dtype=torch.float32)
         ok = (rows >= 0) & (rows < table.shape[0])

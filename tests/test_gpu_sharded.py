@@ -109,3 +109,17 @@ def test_sharded_world2_nccl_matches_single_process_oracle(tmp_path):
     assert r["max_param_err"] <= 0.5 * 1e-2, r
     assert np.allclose(r["dp_losses"], r["dp_ref"], atol=2e-5), r
     assert r["dp_err"] <= 0.5 * 1e-2, r
+
+
+@pytest.mark.parametrize("world,n_u,n_i", [(1, 100, 200), (2, 8192, 16384), (8, 5000, 10001), (3, 0, 77), (64, 300, 0)])
+def test_route_plan_kernel_matches_tensor_reference(world, n_u, n_i):
+    """rb200_route_plan (stable partition of the requests by owner) against the generic-tensor restatement."""
+    from recommendit_b200.sharded import CudaOps, route_reference, shard_rows
+    g = torch.Generator().manual_seed(world * 7 + n_u)
+    u = torch.randint(0, 1_000_003, (n_u,), generator=g).cuda()
+    i = torch.randint(0, 50_021, (n_i,), generator=g).cuda()
+    nu_by_rank = torch.tensor([shard_rows(1_000_003, world, r) for r in range(world)], dtype=torch.int64, device="cuda")
+    got = CudaOps().route(u, i, world, nu_by_rank)
+    ref = route_reference(u, i, world, nu_by_rank)
+    for a, b, name in zip(got, ref, ("perm", "inv", "local_rows", "send_counts")):
+        assert torch.equal(a, b.to(a.dtype)), name
