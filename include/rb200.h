@@ -161,6 +161,31 @@ int rb200_scatter_reset_slots(const int64_t* uniq_ids, const int* n_uniq, int ma
 /* row_slot[uniq_ids[i]] = i for i < n_uniq[0] (when the compact list was produced without a slot map) */
 int rb200_scatter_set_slots(const int64_t* uniq_ids, const int* n_uniq, int max_uniq, int* row_slot,
                             void* stream);
+/* Device-side batch producer: the sample stream of the reference's UserItemDataset + DataLoader
+ * (src/training/train_embeddings.py:23-79, 144-151: positives shuffled per epoch with drop_last, one negative per sample drawn
+ * uniformly from the catalog and rejected while the user has rated it).  pos_users/pos_items: the n_pos positive pairs;
+ * rated_offsets [max user id + 2] / rated_items: CSR of every user's rated items, ascending within a user; catalog: the
+ * n_cat candidate item ids.  Batch `step` of `epoch` (0-based, (step+1)·B <= n_pos) is a pure function of `seed`. */
+int rb200_sample_batch(const int64_t* pos_users, const int64_t* pos_items, int64_t n_pos, const int64_t* rated_offsets,
+                       const int64_t* rated_items, const int64_t* catalog, int64_t n_cat, int B, uint64_t seed,
+                       int64_t epoch, int64_t step, int64_t* out_users, int64_t* out_pos, int64_t* out_neg,
+                       void* stream);
+/* The same producer as a description the fused step can run by itself (rb200_step_params.next_batch): at the end of step t it
+ * writes the batch of step t+1 into the step's own id buffers, on a side stream under the optimizer kernels.  The global batch
+ * index g is read on the device from the optimizer's step counter (opt->step = number of steps begun so far), epoch =
+ * g / batches_per_epoch, step = g % batches_per_epoch — nothing comes from the host, so the whole epoch is graph replays.
+ * rated_bitmap (optional, [n_users + 1][bitmap_words] uint32, bit i of a user's row = "has rated item i") replaces the binary
+ * search in the CSR by one load; results are identical. */
+typedef struct rb200_sampler {
+    const int64_t *pos_users, *pos_items; int64_t n_pos;
+    const int64_t *rated_offsets, *rated_items;
+    const uint32_t* rated_bitmap; int64_t bitmap_words;
+    const int64_t* catalog; int64_t n_cat;
+    uint64_t seed; int64_t batches_per_epoch;
+} rb200_sampler;
+/* batch g = *counter_dev of the stream described by `s` (what the fused step runs); B·batches_per_epoch <= n_pos */
+int rb200_sample_batch_dev(const rb200_sampler* s, int B, const int64_t* counter_dev, int64_t* out_users, int64_t* out_pos,
+                           int64_t* out_neg, void* stream);
 /* Exchange plan of the row-sharded step (tables sharded by id mod world, both shards of a rank in
  * one tensor: user rows first, item rows behind them).  Requests = [user_ids | item_ids] (n = n_user + n_item) in sample
  * order; bucket order = stable by owner.  perm[j] = sample of bucket position j, inv = its inverse, local_rows[j] = row in
@@ -260,6 +285,8 @@ typedef struct rb200_step_params {
                            gradients and leaves them DENSE in this flat buffer
                            [user MLP | item MLP | user table (n_user_rows·D) | item table (n_item_rows·D)]
                            for the caller to all-reduce; rb200_bpr_apply then clips and runs Adam from it.  */
+    const rb200_sampler* next_batch;   /* optional (host pointer): produce the NEXT step's user/pos/neg ids on the device at the
+                           end of this step (device-side batch producer; needs extra_by_id or extra_dim == 0) */
 } rb200_step_params;
 
 size_t rb200_bpr_step_workspace_bytes(int B, int D, int H, int extra_dim, int64_t n_user_rows,

@@ -63,7 +63,13 @@ class StepParams(C.Structure):
                 ("keep_mask_user", c_f), ("keep_mask_pos", c_f), ("keep_mask_neg", c_f),
                 ("padding_idx", C.c_int64), ("loss", c_f), ("err_flag", c_f),
                 ("workspace", c_f), ("workspace_bytes", C.c_size_t), ("stage_events_host", c_f),
-                ("grad_scale", C.c_float), ("dp_grads", c_f)]
+                ("grad_scale", C.c_float), ("dp_grads", c_f), ("next_batch", c_f)]
+
+
+class Sampler(C.Structure):      # host mirror of rb200_sampler
+    _fields_ = [("pos_users", c_f), ("pos_items", c_f), ("n_pos", C.c_int64), ("rated_offsets", c_f), ("rated_items", c_f),
+                ("rated_bitmap", c_f), ("bitmap_words", C.c_int64), ("catalog", c_f), ("n_cat", C.c_int64),
+                ("seed", C.c_uint64), ("batches_per_epoch", C.c_int64)]
 
 
 class StepViews(C.Structure):
@@ -96,6 +102,8 @@ SIGNATURES = {
     "rb200_scatter_reset_slots": (I, [P, P, I, P, P]),
     "rb200_scatter_set_slots": (I, [P, P, I, P, P]),
     "rb200_gather_rows": (I, [P, P, I64, I, I64, P, P]),
+    "rb200_sample_batch": (I, [P, P, I64, P, P, P, I64, I, U64, I64, I64, P, P, P, P]),
+    "rb200_sample_batch_dev": (I, [P, I, P, P, P, P, P]),
     "rb200_route_plan_workspace_bytes": (SZ, [I64, I]),
     "rb200_route_plan": (I, [P, I64, P, I64, I, P, P, P, P, P, P, SZ, P]),
     "rb200_opt_begin_step": (I, [P, P]),
@@ -145,7 +153,7 @@ def load() -> C.CDLL:
         fn = getattr(lib, name)   # AttributeError if the symbol is missing
         fn.restype = res
         fn.argtypes = args
-    for which, cls in enumerate((TowerJob, TowerBwdJob, OptState, StepParams, StepViews, SumsqSeg)):
+    for which, cls in enumerate((TowerJob, TowerBwdJob, OptState, StepParams, StepViews, SumsqSeg, Sampler)):
         if lib.rb200_sizeof(which) != C.sizeof(cls):
             raise RB200Error(f"ABI mismatch: sizeof({cls.__name__}) is {C.sizeof(cls)} here, {lib.rb200_sizeof(which)} in {path}")
     _lib = lib

@@ -43,6 +43,7 @@ extern "C" size_t rb200_sizeof(int which) {
         case 3: return sizeof(rb200_step_params);
         case 4: return sizeof(rb200_step_views);
         case 5: return sizeof(rb200_sumsq_seg);
+        case 6: return sizeof(rb200_sampler);
         default: return 0;
     }
 }

@@ -32,6 +32,8 @@ int rb_grad_finish(int n_tables, const int64_t* const ids_a[2], const int64_t* c
                    int64_t* const uniq_ids[2], float* const uniq_grads[2], int* const n_uniq[2], int* const row_slot[2],
                    void* scatter_ws, size_t scatter_ws_bytes, const RbPartials red[2], float* const red_out[2], int do_sumsq,
                    void* sumsq_ws, size_t sumsq_ws_bytes, const double** norm_partials, int* n_norm_partials, cudaStream_t s);
+int rb_sample_batch(const rb200_sampler& S, int B, long long epoch, long long step, const int64_t* counter_dev, int64_t* out_users,
+                    int64_t* out_pos, int64_t* out_neg, cudaStream_t st);
 int rb_reset_slots2(const int64_t* ids0, const int* n0, int cap0, int* slot0, const int64_t* ids1, const int* n1, int cap1, int* slot1,
                     cudaStream_t s);
 
@@ -94,7 +96,7 @@ bool carve(RbArena& ar, const rb200_step_params& s, StepWs& w) {
 
 // Library-owned side stream + events for the fork/join inside the step (capturable: the side stream joins the capture
 // through the event dependencies).
-struct SideStream { cudaStream_t s = nullptr; cudaEvent_t fork = nullptr, fork2 = nullptr, join = nullptr; };
+struct SideStream { cudaStream_t s = nullptr; cudaEvent_t fork = nullptr, fork2 = nullptr, fork3 = nullptr, join = nullptr, join2 = nullptr; };
 int side_stream(SideStream** out) {
     static thread_local SideStream per_dev[64];
     int dev = 0;
@@ -105,6 +107,8 @@ int side_stream(SideStream** out) {
         RB_CUDA(cudaStreamCreateWithFlags(&ss.s, cudaStreamNonBlocking));
         RB_CUDA(cudaEventCreateWithFlags(&ss.fork, cudaEventDisableTiming));
         RB_CUDA(cudaEventCreateWithFlags(&ss.fork2, cudaEventDisableTiming));
+        RB_CUDA(cudaEventCreateWithFlags(&ss.fork3, cudaEventDisableTiming));
+        RB_CUDA(cudaEventCreateWithFlags(&ss.join2, cudaEventDisableTiming));
         RB_CUDA(cudaEventCreateWithFlags(&ss.join, cudaEventDisableTiming));
     }
     *out = &ss;
@@ -307,7 +311,24 @@ extern "C" int rb200_bpr_step(const rb200_step_params* s, void* stream) {
                                      w.ug_i, w.n_uniq + 1, sc_rs[1], w.ws_scatter, w.b_scatter, st))) return rc;
     }
 
-    if (dp) return RB200_OK;      // gradients are complete and dense in dp_grads: the caller all-reduces, then rb200_bpr_apply
+    // ---- device-side batch producer: the ids of this step are dead from here on (sort, gathers and the weight-gradient
+    //      kernels have run), so the NEXT batch is sampled into the same buffers on the side stream, under the optimizer -- //
+    bool next_pending = false;
+    if (s->next_batch) {
+        RB_REQUIRE(pair, "bpr_step: next_batch produces (user, positive, negative) triples: loss_kind must be 0");
+        RB_REQUIRE(E == 0 || s->extra_by_id, "bpr_step: next_batch needs the genre table mode (extra_by_id)");
+        RB_CUDA(cudaEventRecord(side->fork3, st));
+        RB_CUDA(cudaStreamWaitEvent(side->s, side->fork3, 0));
+        if ((rc = rb_sample_batch(*s->next_batch, B, 0, 0, reinterpret_cast<const int64_t*>(&s->opt->step),
+                                  const_cast<int64_t*>(s->user_ids), const_cast<int64_t*>(s->pos_ids), const_cast<int64_t*>(s->neg_ids),
+                                  side->s))) return rc;
+        RB_CUDA(cudaEventRecord(side->join2, side->s));
+        next_pending = true;
+    }
+    if (dp) {                     // gradients are complete and dense in dp_grads: the caller all-reduces, then rb200_bpr_apply
+        if (next_pending) RB_CUDA(cudaStreamWaitEvent(st, side->join2, 0));
+        return RB200_OK;
+    }
 
     RB_STAGE_EVENT();
     // ---- clip_grad_norm_(all parameters, 1.0) ---------------------------------------------------- //
@@ -345,6 +366,7 @@ extern "C" int rb200_bpr_step(const rb200_step_params* s, void* stream) {
         if ((rc = rb200_adam_rows(s->item_table, s->item_table_m, s->item_table_v, D, w.uniq_i, w.ug_i, w.n_uniq + 1, items * B,
                                   s->opt, st))) return rc;
     }
+    if (next_pending) RB_CUDA(cudaStreamWaitEvent(st, side->join2, 0));      // the side stream rejoins (graph capture needs it)
     RB_STAGE_EVENT();
 #undef RB_STAGE_EVENT
     return RB200_OK;

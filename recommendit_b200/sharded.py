@@ -63,7 +63,7 @@ def make_route(ids: torch.Tensor, world: int) -> Route:
 
 def route_reference(user_ids: torch.Tensor, item_ids: torch.Tensor, world: int, nu_by_rank: torch.Tensor):
     """What ``rb200_route_plan`` computes, restated with generic tensor ops — used by the CPU test back end
-    (tests/oracle_ops.py) and as the oracle of the kernel's GPU test; the product path calls the kernel."""
+    (tests/) and as the checker of the kernel in its GPU test; the product path calls the kernel."""
     ids = torch.cat([user_ids, item_ids])
     owner = ids % world
     local = torch.div(ids, world, rounding_mode="floor")
@@ -232,7 +232,7 @@ class ShardedBPRTrainer:
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
-        self.dev = torch.device(device if device is not None else ("cuda", torch.cuda.current_device()))
+        self.dev = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
         self.ops = ops if ops is not None else CudaOps()
         self.D, self.H, self.E = embed_dim, hidden_dim, n_genres
         self.n_user_rows, self.n_item_rows = n_users + 1, n_items + 1

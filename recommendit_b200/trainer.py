@@ -23,7 +23,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from ._lib import OptState, RB200Error, StepParams, StepViews, check, ptr, require_cuda, stream_ptr
+from ._lib import OptState, RB200Error, Sampler, StepParams, StepViews, check, ptr, require_cuda, stream_ptr
 from .two_tower import TwoTowerModel, inbatch_mode_for
 
 
@@ -80,6 +80,17 @@ class FusedBPRTrainer:
         self._B = None
         self._graph = None
         self._steps_done = 0
+        self._sampler = None          # (Sampler struct, producer) when the step produces its own next batch
+
+    def attach_producer(self, sampler: Optional[Sampler], owner=None) -> None:
+        """Let the step sample its own NEXT batch on the device (``rb200_step_params.next_batch``, csrc/sampler.cu): the
+        ids never come from the host and an epoch is nothing but graph replays.  ``None`` detaches."""
+        if sampler is not None and self.loss_kind != 0:
+            raise RB200Error("the device-side producer yields (user, positive, negative) triples: loss must be 'bpr'")
+        if sampler is not None and self.E and self.item_extra_table is None:
+            raise RB200Error("the device-side producer needs a trainer built with item_extra_table (genres by item id)")
+        self._sampler = None if sampler is None else (sampler, owner)
+        self._graph = None
 
     # ---- parameter plumbing ------------------------------------------------------------------- #
     def _flatten(self) -> None:
@@ -182,6 +193,7 @@ class FusedBPRTrainer:
         p.padding_idx = 0
         p.loss, p.err_flag = ptr(self.loss_dev), ptr(self.err_flag)
         p.workspace, p.workspace_bytes = ptr(self.ws), self.ws.numel()
+        p.next_batch = C.addressof(self._sampler[0]) if self._sampler is not None else None
         return p
 
     def _launch(self, masks=None) -> None:

@@ -1,0 +1,68 @@
+"""The batch-producer oracle against the reference's sampling semantics (train_embeddings.py:23-79, 144-151) — CPU."""
+import numpy as np
+
+from oracle import sampler_oracle as S
+
+
+def _toy(seed=0, n_users=40, n_items=60, n_ratings=900):
+    rng = np.random.default_rng(seed)
+    u = rng.integers(1, n_users + 1, n_ratings)
+    i = rng.integers(1, n_items + 1, n_ratings)
+    r = rng.integers(1, 6, n_ratings)
+    pairs = np.unique(np.stack([u, i], 1), axis=0, return_index=True)[1]
+    u, i, r = u[pairs], i[pairs], r[pairs]
+    pos = r >= 4
+    offsets, rated = S.build_rated_csr(u, i, n_users)
+    catalog = np.arange(1, n_items + 1, dtype=np.int64)
+    return u[pos].astype(np.int64), i[pos].astype(np.int64), offsets, rated, catalog, (u, i)
+
+
+def test_philox_known_answer():
+    # Random123 known-answer vectors for philox4x32-10
+    assert [int(x) for x in S.philox4x32(0, 0, 0, 0, 0, 0)] == [0x6627E8D5, 0xE169C58D, 0xBC57AC4C, 0x9B00DBD8]
+    assert [int(x) for x in S.philox4x32(0xFFFFFFFF, 0xFFFFFFFF, 0xFFFFFFFF, 0xFFFFFFFF, 0xFFFFFFFF, 0xFFFFFFFF)] == \
+        [0x408F276D, 0x41C83B0E, 0xA20BC7C6, 0x6D5451FD]
+
+
+def test_feistel_is_a_permutation_and_differs_per_epoch():
+    for n in (1, 2, 7, 64, 1000, 4097):
+        k = S.epoch_keys(5, 0)
+        p = S.feistel_perm(np.arange(n), n, *k)
+        assert np.array_equal(np.sort(p), np.arange(n))
+    a = S.feistel_perm(np.arange(1000), 1000, *S.epoch_keys(5, 0))
+    b = S.feistel_perm(np.arange(1000), 1000, *S.epoch_keys(5, 1))
+    assert (a != b).mean() > 0.95
+
+
+def test_epoch_visits_every_positive_once_and_drops_the_last_partial_batch():
+    pu, pi, off, rated, cat, _ = _toy()
+    B = 32
+    nb = len(pu) // B
+    seen = []
+    for step in range(nb):
+        u, p, n = S.sample_batch(pu, pi, off, rated, cat, B, seed=9, epoch=2, step=step)
+        seen.append(np.stack([u, p], 1))
+    seen = np.concatenate(seen)
+    assert len(np.unique(seen, axis=0)) == nb * B                       # no positive twice in an epoch
+    allpos = set(map(tuple, np.stack([pu, pi], 1)))
+    assert all(tuple(x) in allpos for x in seen)
+
+
+def test_negatives_are_never_rated_and_cover_the_unrated_catalog_uniformly():
+    pu, pi, off, rated, cat, (u_all, i_all) = _toy(seed=3, n_users=5, n_items=40, n_ratings=100)
+    rated_set = {}
+    for u, i in zip(u_all, i_all):
+        rated_set.setdefault(int(u), set()).add(int(i))
+    B = len(pu)
+    counts = {}
+    for epoch in range(300):
+        u, p, n = S.sample_batch(pu, pi, off, rated, cat, B, seed=1, epoch=epoch, step=0)
+        for uu, nn in zip(u, n):
+            assert int(nn) not in rated_set.get(int(uu), set())
+            counts.setdefault(int(uu), []).append(int(nn))
+    for uu, draws in counts.items():
+        free = sorted(set(range(1, 41)) - rated_set[uu])
+        h = np.array([draws.count(f) for f in free], dtype=np.float64)
+        exp = len(draws) / len(free)
+        chi2 = ((h - exp) ** 2 / exp).sum()
+        assert chi2 < 2.0 * len(free) + 30, (uu, chi2)                 # loose: uniform over the unrated items
