@@ -432,14 +432,17 @@ def bench_producer(args, dev):
     nb = prod.batches_per_epoch(B)
     prod.train_epoch(tr, B, 0)                                  # warm-up epoch (captures the graph)
     torch.cuda.synchronize(dev)
+    n_ep = 5
     t0 = time.perf_counter()
-    loss = prod.train_epoch(tr, B, 1)
-    dt = time.perf_counter() - t0
+    for e in range(1, 1 + n_ep):
+        loss = prod.train_epoch(tr, B, e)
+    dt = (time.perf_counter() - t0) / n_ep
     tr.check_ids()
     return {"metric": "bpr_train_samples_per_s", "value": nb * B / dt, "unit": "samples/s", "ms_per_step": dt / nb * 1e3,
-            "batches_per_epoch": nb, "positives": prod.n_pos, "epoch_mean_loss": loss, "index_build_s": build_s,
-            "api": "DeviceBatchProducer.train_epoch(FusedBPRTrainer(item_extra_table=genres), 8192, epoch): one sampling launch "
-                   "(rb200_sample_batch) + one graph replay per step, wall clock around the epoch, loss read once",
+            "batches_per_epoch": nb, "epochs_timed": n_ep, "positives": prod.n_pos, "epoch_mean_loss": loss, "index_build_s": build_s,
+            "api": "DeviceBatchProducer.train_epoch(FusedBPRTrainer(item_extra_table=genres), 8192, epoch): the step samples its own "
+                   "next batch on the device (rb200_step_params.next_batch), so an epoch is one graph replay per step; wall clock "
+                   "around the epochs, mean loss read once per epoch",
             "reference_producer": "UserItemDataset + DataLoader: ≈ 22 k samples/s (SURVEY.md §6.2)"}
 
 
@@ -508,6 +511,75 @@ def bench_hbm_kernels(dev):
     return res
 
 
+def make_flat_shard(dev, rows: int, seed: int):
+    """C5 shard: unit-norm N(0,1) rows generated on the device in slices (a 12.5 M x 64 shard is 3.2 GB)."""
+    g = torch.Generator(device=dev).manual_seed(seed)
+    x = torch.empty(rows, 64, dtype=torch.float32, device=dev)
+    for r0 in range(0, rows, 1 << 20):
+        blk = torch.randn(min(1 << 20, rows - r0), 64, device=dev, generator=g)
+        x[r0:r0 + blk.shape[0]] = torch.nn.functional.normalize(blk, dim=-1)
+    return x
+
+
+def bench_flat(args, dev, rows: int = 12_500_000, nqs=(4096, 64), reps: int = 3):
+    """BASELINE C5, the work of ONE of its 8 shards: exhaustive inner-product top-500 over 12.5 M x 64 rows (100 M / 8) —
+    rb200_flat_search = first exact chunk, then threshold-pruned tcgen05 rounds (csrc/flat_scan_tc.cu).  The N>1 line adds the
+    all-gather + merge across shards."""
+    import recommendit_b200 as R
+    pk = peaks()
+    x = make_flat_shard(dev, rows, 13)
+    g = torch.Generator(device=dev).manual_seed(14)
+    out = {"rows_per_shard": rows, "k": 500, "D": 64}
+    for nq in nqs:
+        q = torch.nn.functional.normalize(torch.randn(nq, 64, device=dev, generator=g), dim=-1)
+        R.flat_search(q, x, 500)                              # warm-up (kernel attributes, workspace)
+        torch.cuda.synchronize(dev)
+        ms = []
+        for _ in range(reps):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(); s, i = R.flat_search(q, x, 500); b.record()
+            torch.cuda.synchronize(dev)
+            ms.append(a.elapsed_time(b))
+        t = float(np.median(ms))
+        # sanity (library matmul + topk on a row prefix, not the oracle): the winners over a 1M-row prefix
+        sub = 1_000_000
+        s1, i1 = R.flat_search(q[:64], x[:sub], 500)
+        ref = torch.topk(q[:64].double() @ x[:sub].double().T, 500, dim=1)
+        agree = float((i1 == ref.indices).float().mean())
+        flops = 2.0 * nq * rows * 64
+        ent = {"ms_per_batch": t, "queries_per_s": nq / t * 1e3, "logical_tflops": flops / (t * 1e-3) / 1e12,
+               "ids_equal_to_fp64_topk_on_1M_prefix": agree}
+        if nq >= 1024:
+            ent["roofline"] = {"kernel": "flat_scan_tc_kernel (3xTF32: 3 MMAs per logical MMA)", "bound": "tensor", "unit": "TFLOP/s",
+                               "achieved": flops / (t * 1e-3) / 1e12, "issued_tflops": 3 * flops / (t * 1e-3) / 1e12,
+                               "peak": pk["bf16_tflops"], "frac": flops / (t * 1e-3) / 1e12 / pk["bf16_tflops"], "traffic": None,
+                               "note": "logical 2·nq·N·D flops vs the measured bf16 peak; kind::tf32 peaks at half of it and 3xTF32 "
+                                       "issues 3 MMAs per logical one, so 1/6 of the bf16 peak is this kernel's ceiling"}
+        else:
+            by = rows * 64 * 4.0
+            ent["roofline"] = {"kernel": "flat_scan_tc_kernel", "bound": "hbm", "unit": "GB/s", "achieved": by / (t * 1e-3) / 1e9,
+                               "peak": pk["hbm_gbs"], "frac": by / (t * 1e-3) / 1e9 / pk["hbm_gbs"], "traffic": None,
+                               "note": "the shard is read once per batch: N·D·4 bytes"}
+        out[f"nq{nq}"] = ent
+    del x
+    torch.cuda.empty_cache()
+    return out
+
+
+def bench_flat_cpu(nq: int = 16, rows: int = 1_000_000):
+    from oracle import ivf_oracle as V
+    rng = np.random.default_rng(13)
+    x = V.normalize_rows(rng.standard_normal((rows, 64)).astype(np.float32))
+    q = V.normalize_rows(rng.standard_normal((nq, 64)).astype(np.float32))
+    V.flat_search_c(q[:2], x[:10000], 500)
+    t0 = time.perf_counter()
+    V.flat_search_c(q, x, 500)
+    dt = time.perf_counter() - t0
+    return {"value": nq / dt * rows / 12_500_000, "unit": "queries/s", "cores": os.cpu_count(), "kind": "port",
+            "sample": f"{nq} queries x {rows} rows with oracle/ivf_oracle.c (heap-based IndexFlatIP restatement, OpenMP over queries), "
+                      "scaled linearly in rows to the 12.5 M-row shard"}
+
+
 def bench_ivf_cpu(nq_sample: int = 256):
     """CPU arm of C3 on a bounded sample of queries: oracle/ivf_oracle.c (heap-based, OpenMP over queries)."""
     from oracle import ivf_oracle as V
@@ -539,6 +611,7 @@ def main():
     ap.add_argument("--skip-hbm", action="store_true")
     ap.add_argument("--skip-inbatch", action="store_true")
     ap.add_argument("--skip-producer", action="store_true")
+    ap.add_argument("--skip-flat", action="store_true")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
@@ -607,6 +680,8 @@ def main():
         line["device_producer"] = bench_producer(args, dev)
     if not args.skip_hbm:
         line["hbm_kernels"] = bench_hbm_kernels(dev)
+    if not args.skip_flat:
+        line["c5_shard"] = bench_flat(args, dev)
     if not args.skip_cpu:
         cores = os.cpu_count() or 1
         v, ms = cpu_step_throughput(20, 3, cores)
@@ -618,6 +693,11 @@ def main():
                 line["ivf"]["cpu_baseline"] = bench_ivf_cpu()
             except Exception as e:   # the C oracle is optional test infrastructure
                 line["ivf"]["cpu_baseline"] = {"unavailable": str(e)[:200]}
+        if not args.skip_flat:
+            try:
+                line["c5_shard"]["cpu_baseline"] = bench_flat_cpu()
+            except Exception as e:
+                line["c5_shard"]["cpu_baseline"] = {"unavailable": str(e)[:200]}
     print(json.dumps(line), flush=True)
 
 

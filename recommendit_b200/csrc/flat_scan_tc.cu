@@ -1,0 +1,230 @@
+// Exhaustive inner-product scan with threshold pruning on the tensor cores (faiss IndexFlatIP.search at BASELINE cfg 5 sizes:
+// 12.5 M rows per GPU × thousands of queries).
+//
+// The chunked path in ivf.cu (score GEMM → [nq × chunk] scores in HBM → select) writes and re-reads every score: 205 GB of
+// traffic per 4096-query batch over a 12.5 M-row shard.  Here a score leaves the SM only if it can still enter its query's
+// top-k: the caller passes, per query, the k-th best score over the rows seen so far (`thr`), and the epilogue appends
+// (score, row) to the query's survivor list only when score > thr (strictly: rows are visited in ascending order, so an equal
+// score loses the tie to the earlier row, as in the reference's heap).  The host loop in ivf.cu grows the row range
+// geometrically (×4 per round), so a round is expected to leave 3·k survivors per query whatever the database size.
+//
+// Database-stationary: one CTA owns TILES × 128 database rows, staged once as K-major A operands (hi/lo split: 3xTF32 = fp32-grade
+// products, same arithmetic as the IVF list scan), and streams the whole query set past them in chunks of 64 queries.  The
+// query chunks come from a pre-split image (`qimg`, built once per search by flat_qimage_kernel; 2 MB at nq = 4096, L2-resident)
+// by ONE bulk asynchronous copy (TMA engine) per chunk into a ring of NSLOT shared-memory slots; S[128 rows × 64 queries] per
+// tile is accumulated in TMEM, double-buffered.  Warp-specialised: warp 8 issues the copies and the MMAs (one thread), warps 0-7
+// stage the rows once and then run the epilogues — the MMAs of chunk c+1 run under the epilogue of chunk c, and hand-offs go
+// through mbarriers only (copy → MMA: expect_tx; MMA → epilogue and MMA → slot reuse: tcgen05.commit; epilogue → MMA: arrive).
+// D = 64.  <TILES 2, NSLOT 3>: 224 KB of shared memory, 256 TMEM columns, 1 CTA per SM (many query chunks: tensor-bound);
+// <TILES 1, NSLOT 1>: 96 KB, 2 CTAs per SM (one or two query chunks: the scan is bound by reading the rows).
+#include "common.cuh"
+#include "umma.cuh"
+
+namespace {
+
+constexpr int VT = 128, QT = 64, DD = 64, NT_EPI = 256, NT_F = NT_EPI + 32;
+constexpr int V_BYTES = VT * DD * 4;             // one half (hi or lo) of one tile: 32 KB
+constexpr int Q_HALF = QT * DD * 4;              // 16 KB
+constexpr int Q_IMG = 2 * Q_HALF;                // hi image then lo image of one 64-query chunk: 32 KB
+template <int TILES, int NSLOT> constexpr size_t flat_smem() { return (size_t)TILES * 2 * V_BYTES + (size_t)NSLOT * Q_IMG; }
+
+// q [nq, 64] fp32 → per chunk of 64 queries [hi | lo], each in the K-major core-matrix layout of umma.cuh; rows past nq are zero
+__global__ void __launch_bounds__(256) flat_qimage_kernel(const float* __restrict__ q, int nq, int n_chunks, unsigned char* __restrict__ qimg) {
+    const int i = blockIdx.x * 256 + threadIdx.x;                // (row, 16-byte chunk)
+    if (i >= n_chunks * QT * (DD / 4)) return;
+    const int r = i >> 4, c4 = i & 15;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (r < nq) v = __ldg(reinterpret_cast<const float4*>(q + (long long)r * DD) + c4);
+    float4 hi, lo;
+    umma::split4(v, hi, lo);
+    unsigned char* base = qimg + (size_t)(r / QT) * Q_IMG;
+    const uint32_t off = umma::kmajor_offset(QT, r % QT, c4 * 4);
+    *reinterpret_cast<float4*>(base + off) = hi;
+    *reinterpret_cast<float4*>(base + Q_HALF + off) = lo;
+}
+
+template <int TILES, int NSLOT>
+__global__ void __launch_bounds__(NT_F, 1) flat_scan_tc_kernel(const float* __restrict__ x, long long n_rows,
+                                                               const unsigned char* __restrict__ qimg, int n_chunks,
+                                                               const float* __restrict__ thr, int* __restrict__ count,
+                                                               float* __restrict__ cand_s, long long stride, int kprev,
+                                                               int* __restrict__ cand_r, int cap, int* __restrict__ flags) {
+    extern __shared__ __align__(1024) unsigned char smem[];
+    unsigned char* v_hi = smem;                                  // [TILES][V_BYTES]
+    unsigned char* v_lo = smem + TILES * V_BYTES;
+    unsigned char* qbuf = smem + 2 * TILES * V_BYTES;            // [NSLOT][Q_IMG]
+    __shared__ __align__(8) uint64_t bar_qfull[NSLOT], bar_qfree[NSLOT], bar_m[2], bar_accfree[2];
+    __shared__ uint32_t tmem_slot;
+    __shared__ int dead;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const long long row0 = (long long)blockIdx.x * (TILES * VT);
+    constexpr uint32_t TM_COLS = 2 * TILES * QT;
+
+    if (warp == 0) umma::tmem_alloc(&tmem_slot, TM_COLS);
+    if (tid == NT_EPI) {
+        for (int i = 0; i < NSLOT; ++i) { umma::mbar_init(&bar_qfull[i], 1); umma::mbar_init(&bar_qfree[i], 1); }
+        for (int i = 0; i < 2; ++i) { umma::mbar_init(&bar_m[i], 1); umma::mbar_init(&bar_accfree[i], NT_EPI); }
+        umma::fence_mbar_init();
+        dead = 0;
+        for (int i = 0; i < NSLOT && i < n_chunks; ++i) {        // the first query chunks are on their way while the rows are staged
+            umma::mbar_expect_tx(&bar_qfull[i], Q_IMG);
+            umma::bulk_g2s(qbuf + i * Q_IMG, qimg + (size_t)i * Q_IMG, Q_IMG, &bar_qfull[i]);
+        }
+    }
+    // ---- stage the database rows (warps 0-7): all loads of a thread are issued before the first is used.  A warp covers 8 rows ×
+    //      4 16-byte chunks per step (64-byte global segments, conflict-free 128-byte shared-memory phases) ------------------- //
+    if (warp < NT_EPI / 32) {
+        const int r8 = lane & 7, c4l = lane >> 3;
+        float4 vv[8 * TILES];
+#pragma unroll
+        for (int i = 0; i < 8 * TILES; ++i) {
+            const int u = warp * 8 * TILES + i;                  // 0 .. 64·TILES
+            const int row = (u >> 2) * 8 + r8, c4 = (u & 3) * 4 + c4l;
+            vv[i] = (row0 + row < n_rows) ? __ldcs(reinterpret_cast<const float4*>(x + (row0 + row) * DD) + c4) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int i = 0; i < 8 * TILES; ++i) {
+            const int u = warp * 8 * TILES + i;
+            const int row = (u >> 2) * 8 + r8, c4 = (u & 3) * 4 + c4l;
+            const int t = row / VT;
+            const uint32_t off = (uint32_t)t * V_BYTES + umma::kmajor_offset(VT, row % VT, c4 * 4);
+            float4 hi, lo;
+            umma::split4(vv[i], hi, lo);
+            *reinterpret_cast<float4*>(v_hi + off) = hi;
+            *reinterpret_cast<float4*>(v_lo + off) = lo;
+        }
+    }
+    umma::fence_proxy_async();
+    umma::fence_before_sync();
+    __syncthreads();
+    umma::fence_after_sync();
+    const uint32_t tmem = tmem_slot;
+
+    if (warp == NT_EPI / 32) {
+        // ================================ copy + MMA issuer (one thread) ================================ //
+        if (lane == 0) {
+            const uint32_t idesc = umma::idesc_tf32(VT, QT);
+            constexpr uint32_t lbo_a = (VT / 8) * 128, lbo_b = (QT / 8) * 128;
+            // descriptors differ only in the start address field (bits 0-13, in 16-byte units): build them once, add per k-step
+            uint64_t dah[TILES], dal[TILES];
+#pragma unroll
+            for (int t = 0; t < TILES; ++t) {
+                dah[t] = umma::smem_desc(umma::smem_u32(v_hi + t * V_BYTES), lbo_a, 128);
+                dal[t] = umma::smem_desc(umma::smem_u32(v_lo + t * V_BYTES), lbo_a, 128);
+            }
+            uint32_t ph_full = 0, ph_free = 0, ph_acc = 0;      // one phase bit per barrier (bit i = barrier i)
+            bool ok = true;
+            for (int c = 0; c < n_chunks && ok; ++c) {
+                const int b = c & 1, sl = c % NSLOT;
+                ok = umma::mbar_wait(&bar_qfull[sl], (ph_full >> sl) & 1);
+                ph_full ^= 1u << sl;
+                if (ok && c >= 2) { ok = umma::mbar_wait(&bar_accfree[b], (ph_acc >> b) & 1); ph_acc ^= 1u << b; }
+                if (!ok) break;
+                umma::fence_after_sync();
+                const uint64_t dbh = umma::smem_desc(umma::smem_u32(qbuf + sl * Q_IMG), lbo_b, 128);
+                const uint64_t dbl = umma::smem_desc(umma::smem_u32(qbuf + sl * Q_IMG + Q_HALF), lbo_b, 128);
+#pragma unroll
+                for (int t = 0; t < TILES; ++t) {
+                    const uint32_t acc = tmem + (uint32_t)(b * TILES + t) * QT;
+#pragma unroll
+                    for (int j = 0; j < DD / 8; ++j) {
+                        const uint64_t oa = (uint64_t)((2 * j * lbo_a) >> 4), ob = (uint64_t)((2 * j * lbo_b) >> 4);
+                        umma::mma_tf32(acc, dal[t] + oa, dbh + ob, idesc, j > 0);
+                        umma::mma_tf32(acc, dah[t] + oa, dbl + ob, idesc, true);
+                        umma::mma_tf32(acc, dah[t] + oa, dbh + ob, idesc, true);
+                    }
+                }
+                umma::commit(&bar_m[b]);                         // → epilogue of chunk c
+                umma::commit(&bar_qfree[sl]);                    // → slot sl may be refilled
+                // refill: with a ring of NSLOT > 1 the slot of the PREVIOUS chunk is recycled (its MMAs finish while this chunk's
+                // are queued behind them); a single slot has to wait for this chunk itself
+                const int cc = NSLOT > 1 ? c - 1 : c;
+                if (cc >= 0 && cc + NSLOT < n_chunks) {
+                    const int s2 = cc % NSLOT;
+                    ok = umma::mbar_wait(&bar_qfree[s2], (ph_free >> s2) & 1);
+                    ph_free ^= 1u << s2;
+                    if (ok) {
+                        umma::mbar_expect_tx(&bar_qfull[s2], Q_IMG);
+                        umma::bulk_g2s(qbuf + s2 * Q_IMG, qimg + (size_t)(cc + NSLOT) * Q_IMG, Q_IMG, &bar_qfull[s2]);
+                    }
+                }
+            }
+            if (!ok) { dead = 1; atomicOr(flags + 1, 1); }
+        }
+    } else {
+        // ================================ epilogue warps ================================ //
+        const int r_own = ((warp & 3) << 5) + lane, half = warp >> 2;
+        const uint32_t lane_off = (uint32_t)((warp & 3) * 32) << 16;
+        uint32_t ph_m = 0;
+        for (int c = 0; c < n_chunks; ++c) {
+            const int b = c & 1;
+            float4 th4[8];                                       // thresholds of this thread's 32 queries (uniform loads)
+#pragma unroll
+            for (int i = 0; i < 8; ++i) th4[i] = __ldg(reinterpret_cast<const float4*>(thr + (long long)c * QT + half * 32) + i);
+            if (!umma::mbar_wait(&bar_m[b], (ph_m >> b) & 1)) { atomicOr(flags + 1, 2); break; }
+            ph_m ^= 1u << b;
+            umma::fence_after_sync();
+            const float* th = reinterpret_cast<const float*>(th4);
+            const int q0 = c * QT + half * 32;
+#pragma unroll
+            for (int t = 0; t < TILES; ++t) {
+                float s[32];
+                umma::tmem_ld32(tmem + lane_off + (uint32_t)(b * TILES + t) * QT + half * 32, s);
+                const long long row = row0 + t * VT + r_own;
+                if (row < n_rows) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        if (s[j] > th[j]) {
+                            const int pos = atomicAdd(count + q0 + j, 1);
+                            if (pos < cap) {
+                                cand_s[(long long)(q0 + j) * stride + kprev + pos] = s[j];
+                                cand_r[(long long)(q0 + j) * cap + pos] = (int)row;
+                            } else {
+                                flags[0] = 1;                    // survivor list full: the caller redoes the search on the chunked path
+                            }
+                        }
+                    }
+                }
+            }
+            umma::fence_before_sync();
+            umma::mbar_arrive(&bar_accfree[b]);                  // accumulator b may be overwritten by chunk c + 2
+        }
+    }
+    umma::fence_before_sync();
+    __syncthreads();
+    if (warp == 0) umma::tmem_free(tmem, TM_COLS);
+}
+
+template <int TILES, int NSLOT>
+int launch_flat_scan(const float* x, long long n_rows, const unsigned char* qimg, int n_chunks, const float* thr, int* count,
+                     float* cand_s, long long stride, int kprev, int* cand_r, int cap, int* flags, cudaStream_t st) {
+    static bool attr_set = false;
+    constexpr size_t smem = flat_smem<TILES, NSLOT>();
+    if (!attr_set) {
+        RB_CUDA(cudaFuncSetAttribute(flat_scan_tc_kernel<TILES, NSLOT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_set = true;
+    }
+    const long long n_cta = (n_rows + TILES * VT - 1) / (TILES * VT);
+    RB_REQUIRE(n_rows >= 1 && n_rows < (1ll << 31) && n_cta < (1ll << 31), "flat_scan: a round holds at most 2^31 rows");
+    flat_scan_tc_kernel<TILES, NSLOT><<<(unsigned)n_cta, NT_F, smem, st>>>(x, n_rows, qimg, n_chunks, thr, count, cand_s, stride, kprev,
+                                                                         cand_r, cap, flags);
+    RB_LAUNCH_CHECK("flat_scan_tc_kernel");
+    return RB200_OK;
+}
+
+}  // namespace
+
+// one round: rows [0, n_rows) of x (the caller offsets x) against n_chunks·64 queries (image), thresholds thr[n_chunks·64]
+int rb_flat_scan_tc(const float* x, long long n_rows, const unsigned char* qimg, int n_chunks, const float* thr, int* count,
+                    float* cand_s, long long stride, int kprev, int* cand_r, int cap, int* flags, cudaStream_t st) {
+    if (n_chunks <= 2)
+        return launch_flat_scan<1, 1>(x, n_rows, qimg, n_chunks, thr, count, cand_s, stride, kprev, cand_r, cap, flags, st);
+    return launch_flat_scan<2, 3>(x, n_rows, qimg, n_chunks, thr, count, cand_s, stride, kprev, cand_r, cap, flags, st);
+}
+
+int rb_flat_qimage(const float* q, int nq, int n_chunks, unsigned char* qimg, cudaStream_t st) {
+    const int n = n_chunks * QT * (DD / 4);
+    flat_qimage_kernel<<<(n + 255) / 256, 256, 0, st>>>(q, nq, n_chunks, qimg);
+    RB_LAUNCH_CHECK("flat_qimage_kernel");
+    return RB200_OK;
+}

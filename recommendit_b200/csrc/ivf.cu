@@ -25,6 +25,10 @@ int rb_list_scan_tc(const float* q, int D, const float* list_vecs, const int64_t
                     const int* tile_idx, long long n_tiles, cudaStream_t st);
 int rb_gemm_nt_tc(const float* A, int M, const float* B, int N, int K, int mode, float* C, long long ldc, int* err_flag,
                   cudaStream_t st);
+// threshold-pruned exhaustive scan (flat_scan_tc.cu)
+int rb_flat_scan_tc(const float* x, long long n_rows, const unsigned char* qimg, int n_chunks, const float* thr, int* count,
+                    float* cand_s, long long stride, int kprev, int* cand_r, int cap, int* flags, cudaStream_t st);
+int rb_flat_qimage(const float* q, int nq, int n_chunks, unsigned char* qimg, cudaStream_t st);
 
 namespace {
 
@@ -387,6 +391,11 @@ struct ResolveFlat {     // [running top-k (kprev entries) | chunk rows]
     __host__ __device__ int aux_ints() const { return 0; }
     __device__ void stage(int, int*, int, int) {}
 };
+struct ResolveSurv {     // [running top-k (kprev entries) | survivors of a pruned round: explicit rows relative to row_base]
+    const int64_t* prev_ids; int kprev; const int* rows; int cap; long long row_base;
+    __host__ __device__ int aux_ints() const { return 0; }
+    __device__ void stage(int, int*, int, int) {}
+};
 
 template <typename R> __device__ long long resolve_id(const R& r, int q, int c);
 template <> __device__ long long resolve_id<ResolveIvf>(const ResolveIvf& r, int q, int c) {
@@ -407,6 +416,10 @@ template <> __device__ long long resolve_id<ResolveIdentity>(const ResolveIdenti
 template <> __device__ long long resolve_id<ResolveFlat>(const ResolveFlat& r, int q, int c) {
     if (c < r.kprev) return r.prev_ids[(long long)q * r.kprev + c];
     return r.row_base + (c - r.kprev);
+}
+template <> __device__ long long resolve_id<ResolveSurv>(const ResolveSurv& r, int q, int c) {
+    if (c < r.kprev) return r.prev_ids[(long long)q * r.kprev + c];
+    return r.row_base + r.rows[(long long)q * r.cap + (c - r.kprev)];
 }
 
 constexpr int SORT_CAP = 2048;   // winners + boundary bucket must fit the in-CTA sort (falls back to radix select otherwise)
@@ -928,9 +941,24 @@ static long long flat_chunk_rows(int nq, int64_t n) {
     return c;
 }
 
+// Threshold-pruned rounds (flat_scan_tc.cu) take over after the first exact chunk when D = 64: round j scans rows
+// [seen, 4·seen) against thr[q] = the k-th best score over [0, seen), so it is expected to leave 3·k survivors per query;
+// the survivor lists hold FLAT_CAP_K·k (at least 3584) entries — if one ever fills up (a database sorted by score towards a
+// query), the search is redone on the chunked path, which has no such limit.
+constexpr int FLAT_GROWTH = 4, FLAT_CAP_K = 7, FLAT_CAP_MIN = 3584;
+static int flat_cap(int k) { const int c = FLAT_CAP_K * k; return ((c < FLAT_CAP_MIN ? FLAT_CAP_MIN : c) + 511) / 512 * 512; }
+static bool flat_use_rounds(int D, int64_t n, long long chunk) {
+    static int off = -1;
+    if (off < 0) { const char* e = getenv("RB200_FLAT_CHUNKED"); off = (e && atoi(e)) ? 1 : 0; }     // testing knob: chunked path only
+    return !off && D == 64 && n > chunk;
+}
+
 extern "C" size_t rb200_flat_search_workspace_bytes(int nq, int64_t n, int k) {
     const long long chunk = flat_chunk_rows(nq, n);
-    return 256 * 4 + sizeof(float) * (size_t)nq * (size_t)(chunk + k) + (sizeof(float) + sizeof(int64_t)) * (size_t)nq * k;
+    const long long cap = flat_cap(k), wide = chunk > cap ? chunk : cap;
+    const size_t nq_pad = ((size_t)nq + 63) / 64 * 64;
+    return 256 * 12 + sizeof(float) * (size_t)nq * (size_t)(wide + k) + (sizeof(float) + sizeof(int64_t)) * (size_t)nq * k
+           + nq_pad * 64 * 8 + nq_pad * 8 + sizeof(long long) * (size_t)nq + sizeof(int) * (size_t)nq * cap + 64;
 }
 
 __global__ void copy_prev_kernel(const float* __restrict__ prev_scores, int nq, int k, float* __restrict__ cand, long long stride) {
@@ -940,40 +968,103 @@ __global__ void copy_prev_kernel(const float* __restrict__ prev_scores, int nq, 
     cand[q * stride + j] = prev_scores[i];
 }
 
-extern "C" int rb200_flat_search(const float* q, int nq, const float* x, int64_t n, int D, int k, int64_t id_base,
-                                 float* out_scores, int64_t* out_ids, void* workspace, size_t workspace_bytes, void* stream) {
-    RB_REQUIRE(q && x && out_scores && out_ids && nq >= 1 && n >= 1 && k >= 1 && k <= 2048, "flat_search: bad arguments (k must be 1..2048)");
-    cudaStream_t st = (cudaStream_t)stream;
-    const long long chunk = flat_chunk_rows(nq, n);
-    const long long stride = chunk + k;
-    RbArena ar(workspace, workspace_bytes);
-    float* cand = ar.take<float>((size_t)nq * stride);
-    float* tmp_scores = ar.take<float>((size_t)nq * k);
-    int64_t* tmp_ids = ar.take<int64_t>((size_t)nq * k);
-    if (!workspace || !ar.ok()) return rb_set_error(RB200_ERR_WORKSPACE, "flat_search: workspace too small");
-    const long long n_chunks = (n + chunk - 1) / chunk;
-    // ping-pong between (out) and (tmp) so that the last chunk lands in out_*
-    float* cur_s = (n_chunks % 2) ? out_scores : tmp_scores;
-    int64_t* cur_i = (n_chunks % 2) ? out_ids : tmp_ids;
-    float* prev_s = nullptr; int64_t* prev_i = nullptr;
-    for (long long ci = 0; ci < n_chunks; ++ci) {
-        const long long r0 = ci * chunk, rows = (n - r0 < chunk) ? n - r0 : chunk;
-        const int kprev = ci == 0 ? 0 : k;
+// start of a pruned round: running top-k in front of the survivor list, thr = its k-th score (+inf for the padding queries of the
+// last 64-query chunk), survivor counters cleared
+__global__ void flat_round_prep_kernel(const float* __restrict__ prev_scores, int nq, int nq_pad, int k, float* __restrict__ cand,
+                                       long long stride, float* __restrict__ thr, int* __restrict__ count) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (long long)nq_pad * k) return;
+    const int q = (int)(i / k), j = (int)(i - (long long)q * k);
+    if (q < nq) cand[q * stride + j] = prev_scores[i];
+    if (j == k - 1) { thr[q] = q < nq ? prev_scores[i] : FLT_MAX; count[q] = 0; }
+}
+__global__ void flat_round_lens_kernel(const int* __restrict__ count, int nq, int k, int cap, long long* __restrict__ lens) {
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q < nq) lens[q] = k + (count[q] < cap ? count[q] : cap);
+}
+
+// chunked exact path over rows [r_begin, r_end): score GEMM → select, running top-k carried in front of the chunk's scores.
+// bufS/bufI: two (scores, ids) buffers used alternately; cur = the one holding the running top-k (-1: none yet).
+static int flat_chunked_range(const float* q, int nq, const float* x, int D, long long r_begin, long long r_end, long long chunk,
+                              long long stride, int k, int64_t id_base, float* cand, float* const bufS[2], int64_t* const bufI[2],
+                              int& cur, cudaStream_t st) {
+    for (long long r0 = r_begin; r0 < r_end; r0 += chunk) {
+        const long long rows = (r_end - r0 < chunk) ? r_end - r0 : chunk;
+        const int kprev = cur < 0 ? 0 : k, nxt = cur < 0 ? 0 : cur ^ 1;
         if (kprev) {
-            copy_prev_kernel<<<(unsigned)(((long long)nq * k + NT - 1) / NT), NT, 0, st>>>(prev_s, nq, k, cand, stride);
+            copy_prev_kernel<<<(unsigned)(((long long)nq * k + NT - 1) / NT), NT, 0, st>>>(bufS[cur], nq, k, cand, stride);
             RB_LAUNCH_CHECK("copy_prev_kernel");
         }
         {   // chunk scores on the tensor cores (3xTF32)
             int rc = rb_gemm_nt_tc(q, nq, x + r0 * D, (int)rows, D, 2, cand + kprev, stride, nullptr, st);
             if (rc) return rc;
         }
-        ResolveFlat res{prev_i, kprev, id_base + r0};
+        ResolveFlat res{kprev ? bufI[cur] : nullptr, kprev, id_base + r0};
         // previous winners may contain -FLT_MAX padding (when fewer than k rows so far): they carry id -1
-        int rc = launch_select<ResolveFlat>(cand, nullptr, stride, nullptr, (int)(rows + kprev), rows + kprev, nq, k, res, cur_s, cur_i, st);
+        int rc = launch_select<ResolveFlat>(cand, nullptr, stride, nullptr, (int)(rows + kprev), rows + kprev, nq, k, res, bufS[nxt],
+                                            bufI[nxt], st);
         if (rc) return rc;
-        prev_s = cur_s; prev_i = cur_i;
-        cur_s = (cur_s == out_scores) ? tmp_scores : out_scores;
-        cur_i = (cur_i == out_ids) ? tmp_ids : out_ids;
+        cur = nxt;
+    }
+    return RB200_OK;
+}
+
+extern "C" int rb200_flat_search(const float* q, int nq, const float* x, int64_t n, int D, int k, int64_t id_base,
+                                 float* out_scores, int64_t* out_ids, void* workspace, size_t workspace_bytes, void* stream) {
+    RB_REQUIRE(q && x && out_scores && out_ids && nq >= 1 && n >= 1 && k >= 1 && k <= 2048, "flat_search: bad arguments (k must be 1..2048)");
+    cudaStream_t st = (cudaStream_t)stream;
+    const long long chunk = flat_chunk_rows(nq, n);
+    const int cap = flat_cap(k);
+    const long long stride = (chunk > cap ? chunk : cap) + k;
+    const int n_qchunks = (nq + 63) / 64, nq_pad = n_qchunks * 64;
+    RbArena ar(workspace, workspace_bytes);
+    float* cand = ar.take<float>((size_t)nq * stride);
+    float* tmp_scores = ar.take<float>((size_t)nq * k);
+    int64_t* tmp_ids = ar.take<int64_t>((size_t)nq * k);
+    unsigned char* qimg = ar.take<unsigned char>((size_t)nq_pad * 64 * 8);
+    float* thr = ar.take<float>(nq_pad);
+    int* count = ar.take<int>(nq_pad);
+    long long* lens = ar.take<long long>(nq);
+    int* cand_r = ar.take<int>((size_t)nq * cap);
+    int* flags = ar.take<int>(4);
+    if (!workspace || !ar.ok()) return rb_set_error(RB200_ERR_WORKSPACE, "flat_search: workspace too small");
+    float* const bufS[2] = {out_scores, tmp_scores};
+    int64_t* const bufI[2] = {out_ids, tmp_ids};
+    int cur = -1, rc;
+    const bool rounds = flat_use_rounds(D, n, chunk);
+    const long long n0 = rounds ? chunk : n;
+    if ((rc = flat_chunked_range(q, nq, x, D, 0, n0, chunk, stride, k, id_base, cand, bufS, bufI, cur, st))) return rc;
+    if (rounds) {
+        RB_CUDA(cudaMemsetAsync(flags, 0, 4 * sizeof(int), st));
+        if ((rc = rb_flat_qimage(q, nq, n_qchunks, qimg, st))) return rc;
+        const long long rstride = (long long)k + cap;
+        for (long long seen = n0; seen < n;) {
+            const long long upto = (n / FLAT_GROWTH >= seen) ? seen * FLAT_GROWTH : n;
+            const long long rows = (upto < n ? upto : n) - seen;
+            flat_round_prep_kernel<<<(unsigned)(((long long)nq_pad * k + NT - 1) / NT), NT, 0, st>>>(bufS[cur], nq, nq_pad, k, cand, rstride,
+                                                                                                  thr, count);
+            RB_LAUNCH_CHECK("flat_round_prep_kernel");
+            if ((rc = rb_flat_scan_tc(x + seen * D, rows, qimg, n_qchunks, thr, count, cand, rstride, k, cand_r, cap, flags, st))) return rc;
+            flat_round_lens_kernel<<<(nq + NT - 1) / NT, NT, 0, st>>>(count, nq, k, cap, lens);
+            RB_LAUNCH_CHECK("flat_round_lens_kernel");
+            ResolveSurv res{bufI[cur], k, cand_r, cap, id_base + seen};
+            if ((rc = launch_select<ResolveSurv>(cand, nullptr, rstride, lens, 0, rstride, nq, k, res, bufS[cur ^ 1], bufI[cur ^ 1], st)))
+                return rc;
+            cur ^= 1;
+            seen += rows;
+        }
+        int h[4] = {0, 0, 0, 0};
+        RB_CUDA(cudaMemcpyAsync(h, flags, sizeof(h), cudaMemcpyDeviceToHost, st));
+        RB_CUDA(cudaStreamSynchronize(st));
+        RB_REQUIRE(h[1] == 0, "flat_search: tensor-core pipeline timed out (flag %d)", h[1]);
+        if (h[0]) {            // a survivor list overflowed: redo everything on the chunked path (exact for any row order)
+            cur = -1;
+            if ((rc = flat_chunked_range(q, nq, x, D, 0, n, chunk, stride, k, id_base, cand, bufS, bufI, cur, st))) return rc;
+        }
+    }
+    if (cur == 1) {
+        RB_CUDA(cudaMemcpyAsync(out_scores, tmp_scores, sizeof(float) * (size_t)nq * k, cudaMemcpyDeviceToDevice, st));
+        RB_CUDA(cudaMemcpyAsync(out_ids, tmp_ids, sizeof(int64_t) * (size_t)nq * k, cudaMemcpyDeviceToDevice, st));
     }
     return RB200_OK;
 }

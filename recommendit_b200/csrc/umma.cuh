@@ -56,6 +56,9 @@ __device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity, uint32
     }
     return false;
 }
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
 // ---- bulk async copy (TMA engine, 1-D: no tensor map) ------------------------------------------------------- //
 // arrive(1) + expect `bytes` of asynchronous copy traffic on bar
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {

@@ -140,6 +140,43 @@ def test_flat_search_matches_oracle(n, d, k, nq):
     V.assert_topk_equivalent(s.cpu().numpy(), ids.cpu().numpy(), s_ref, np.where(i_ref >= 0, i_ref + 1000, -1))
 
 
+@pytest.mark.parametrize("n,k,nq", [(300001, 500, 1000), (150000, 100, 4096), (1300000, 500, 24), (90000, 2048, 2048)])
+def test_flat_search_pruned_rounds_match_oracle(n, k, nq):
+    """D = 64 databases larger than the first exact chunk run the threshold-pruned tcgen05 rounds (csrc/flat_scan_tc.cu):
+    ragged query counts (not a multiple of 64), several rounds, rows not a multiple of the 256-row tile."""
+    import recommendit_b200 as R
+    x, rng = _data(n, 64, 1, seed=n % 1000)
+    q = V.normalize_rows(rng.standard_normal((nq, 64)).astype(np.float32))
+    s, ids = R.flat_search(torch.from_numpy(q).cuda(), torch.from_numpy(x).cuda(), k, id_base=7)
+    s_ref, i_ref = V.flat_search_c(q, x, k)
+    V.assert_topk_equivalent(s.cpu().numpy(), ids.cpu().numpy(), s_ref, np.where(i_ref >= 0, i_ref + 7, -1))
+
+
+def test_flat_search_pruned_rounds_survive_an_adversarial_row_order_and_duplicates():
+    """A database sorted by ascending score towards the queries makes every later row beat the running threshold: the survivor
+    lists overflow and the search must come back exact (redone on the chunked path).  Duplicated rows give exact-score ties."""
+    import recommendit_b200 as R
+    rng = np.random.default_rng(5)
+    n, nq, k = 200000, 1024, 500
+    e = V.normalize_rows(rng.standard_normal((1, 64)).astype(np.float32))
+    t = np.linspace(-1.0, 1.0, n, dtype=np.float32)[:, None]
+    x = V.normalize_rows((t * e + 0.05 * rng.standard_normal((n, 64))).astype(np.float32))
+    order = np.argsort(x @ e[0], kind="stable")
+    x = np.ascontiguousarray(x[order])
+    x[n - 50:] = x[n - 100:n - 50]                                   # exact duplicates among the winners
+    q = V.normalize_rows((e + 0.02 * rng.standard_normal((nq, 64))).astype(np.float32))
+    s, ids = R.flat_search(torch.from_numpy(q).cuda(), torch.from_numpy(x).cuda(), k)
+    s_ref, i_ref = V.flat_search_c(q, x, k)
+    V.assert_topk_equivalent(s.cpu().numpy(), ids.cpu().numpy(), s_ref, i_ref)
+    # shuffled rows: the pruned rounds themselves (no overflow) with the same duplicates
+    perm = rng.permutation(n)
+    xs = np.ascontiguousarray(x[perm])
+    s2, ids2 = R.flat_search(torch.from_numpy(q).cuda(), torch.from_numpy(xs).cuda(), k)
+    np.testing.assert_allclose(s2.cpu().numpy(), s_ref, rtol=2e-6, atol=2e-6)
+    s_ref2, i_ref2 = V.flat_search_c(q, xs, k)
+    V.assert_topk_equivalent(s2.cpu().numpy(), ids2.cpu().numpy(), s_ref2, i_ref2)
+
+
 def test_sharded_flat_search_merge_equals_unsharded():
     """BASELINE config C5 in miniature: per-shard top-k + merge == global top-k."""
     import recommendit_b200 as R
