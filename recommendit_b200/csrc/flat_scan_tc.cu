@@ -17,6 +17,8 @@
 // through mbarriers only (copy → MMA: expect_tx; MMA → epilogue and MMA → slot reuse: tcgen05.commit; epilogue → MMA: arrive).
 // D = 64.  <TILES 2, NSLOT 3>: 224 KB of shared memory, 256 TMEM columns, 1 CTA per SM (many query chunks: tensor-bound);
 // <TILES 1, NSLOT 1>: 96 KB, 2 CTAs per SM (one or two query chunks: the scan is bound by reading the rows).
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "umma.cuh"
 
@@ -26,7 +28,7 @@ constexpr int VT = 128, QT = 64, DD = 64, NT_EPI = 256, NT_F = NT_EPI + 32;
 constexpr int V_BYTES = VT * DD * 4;             // one half (hi or lo) of one tile: 32 KB
 constexpr int Q_HALF = QT * DD * 4;              // 16 KB
 constexpr int Q_IMG = 2 * Q_HALF;                // hi image then lo image of one 64-query chunk: 32 KB
-template <int TILES, int NSLOT> constexpr size_t flat_smem() { return (size_t)TILES * 2 * V_BYTES + (size_t)NSLOT * Q_IMG; }
+template <int TILES, int NSLOT, bool A_TMEM> constexpr size_t flat_smem() { return (A_TMEM ? 0 : (size_t)TILES * 2 * V_BYTES) + (size_t)NSLOT * Q_IMG; }
 
 // q [nq, 64] fp32 → per chunk of 64 queries [hi | lo], each in the K-major core-matrix layout of umma.cuh; rows past nq are zero
 __global__ void __launch_bounds__(256) flat_qimage_kernel(const float* __restrict__ q, int nq, int n_chunks, unsigned char* __restrict__ qimg) {
@@ -43,7 +45,7 @@ __global__ void __launch_bounds__(256) flat_qimage_kernel(const float* __restric
     *reinterpret_cast<float4*>(base + Q_HALF + off) = lo;
 }
 
-template <int TILES, int NSLOT>
+template <int TILES, int NSLOT, bool A_TMEM>
 __global__ void __launch_bounds__(NT_F, 1) flat_scan_tc_kernel(const float* __restrict__ x, long long n_rows,
                                                                const unsigned char* __restrict__ qimg, int n_chunks,
                                                                const float* __restrict__ thr, int* __restrict__ count,
@@ -52,13 +54,15 @@ __global__ void __launch_bounds__(NT_F, 1) flat_scan_tc_kernel(const float* __re
     extern __shared__ __align__(1024) unsigned char smem[];
     unsigned char* v_hi = smem;                                  // [TILES][V_BYTES]
     unsigned char* v_lo = smem + TILES * V_BYTES;
-    unsigned char* qbuf = smem + 2 * TILES * V_BYTES;            // [NSLOT][Q_IMG]
+    unsigned char* qbuf = smem + (A_TMEM ? 0 : 2 * TILES * V_BYTES);      // [NSLOT][Q_IMG]
     __shared__ __align__(8) uint64_t bar_qfull[NSLOT], bar_qfree[NSLOT], bar_m[2], bar_accfree[2];
     __shared__ uint32_t tmem_slot;
     __shared__ int dead;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const long long row0 = (long long)blockIdx.x * (TILES * VT);
-    constexpr uint32_t TM_COLS = 2 * TILES * QT;
+    // TMEM columns: [2 buffers][TILES] accumulators of 64, then (A_TMEM) per tile the hi and the lo image of the rows, 64 columns each
+    constexpr uint32_t ACC_COLS = 2 * TILES * QT, TM_COLS = A_TMEM ? ACC_COLS + TILES * 2 * DD : ACC_COLS;
+    static_assert(TM_COLS == 128 || TM_COLS == 256 || TM_COLS == 512, "TMEM allocations are powers of two");
 
     if (warp == 0) umma::tmem_alloc(&tmem_slot, TM_COLS);
     if (tid == NT_EPI) {
@@ -73,7 +77,39 @@ __global__ void __launch_bounds__(NT_F, 1) flat_scan_tc_kernel(const float* __re
     }
     // ---- stage the database rows (warps 0-7): all loads of a thread are issued before the first is used.  A warp covers 8 rows ×
     //      4 16-byte chunks per step (64-byte global segments, conflict-free 128-byte shared-memory phases) ------------------- //
-    if (warp < NT_EPI / 32) {
+    if (A_TMEM) {
+        // rows go to TMEM as the A operand (lane = row, column = k): the tensor core then reads only the query chunk from shared
+        // memory (with both operands there an M128×N64×K8 MMA needs 6 KB = 48 cycles of shared-memory bandwidth for 32 cycles of
+        // math).  Thread = one row: 16 independent 16-byte loads, hi/lo split, 8 tcgen05.st of 16 columns.
+        const bool stager = warp < TILES * 4;
+        const long long row = row0 + (warp >> 2) * VT + ((warp & 3) << 5) + lane;
+        float4 vv[DD / 4];
+        if (stager) {
+#pragma unroll
+            for (int i = 0; i < DD / 4; ++i)
+                vv[i] = row < n_rows ? __ldcs(reinterpret_cast<const float4*>(x + row * DD) + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        umma::fence_before_sync();
+        __syncthreads();                                         // TMEM base address published (tmem_slot)
+        umma::fence_after_sync();
+        if (stager) {
+            const uint32_t a_base = tmem_slot + ((uint32_t)((warp & 3) * 32) << 16) + ACC_COLS + (uint32_t)(warp >> 2) * 2 * DD;
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+                float hi[16], lo[16];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    float4 h, l;
+                    umma::split4(vv[g * 4 + i], h, l);
+                    hi[4 * i] = h.x; hi[4 * i + 1] = h.y; hi[4 * i + 2] = h.z; hi[4 * i + 3] = h.w;
+                    lo[4 * i] = l.x; lo[4 * i + 1] = l.y; lo[4 * i + 2] = l.z; lo[4 * i + 3] = l.w;
+                }
+                umma::tmem_st16(a_base + g * 16, hi);
+                umma::tmem_st16(a_base + DD + g * 16, lo);
+            }
+            umma::tmem_st_wait();
+        }
+    } else if (warp < NT_EPI / 32) {
         const int r8 = lane & 7, c4l = lane >> 3;
         float4 vv[8 * TILES];
 #pragma unroll
@@ -102,55 +138,62 @@ __global__ void __launch_bounds__(NT_F, 1) flat_scan_tc_kernel(const float* __re
 
     if (warp == NT_EPI / 32) {
         // ================================ copy + MMA issuer (one thread) ================================ //
-        if (lane == 0) {
-            const uint32_t idesc = umma::idesc_tf32(VT, QT);
-            constexpr uint32_t lbo_a = (VT / 8) * 128, lbo_b = (QT / 8) * 128;
-            // descriptors differ only in the start address field (bits 0-13, in 16-byte units): build them once, add per k-step
-            uint64_t dah[TILES], dal[TILES];
-#pragma unroll
-            for (int t = 0; t < TILES; ++t) {
-                dah[t] = umma::smem_desc(umma::smem_u32(v_hi + t * V_BYTES), lbo_a, 128);
-                dal[t] = umma::smem_desc(umma::smem_u32(v_lo + t * V_BYTES), lbo_a, 128);
-            }
-            uint32_t ph_full = 0, ph_free = 0, ph_acc = 0;      // one phase bit per barrier (bit i = barrier i)
-            bool ok = true;
-            for (int c = 0; c < n_chunks && ok; ++c) {
-                const int b = c & 1, sl = c % NSLOT;
-                ok = umma::mbar_wait(&bar_qfull[sl], (ph_full >> sl) & 1);
-                ph_full ^= 1u << sl;
-                if (ok && c >= 2) { ok = umma::mbar_wait(&bar_accfree[b], (ph_acc >> b) & 1); ph_acc ^= 1u << b; }
-                if (!ok) break;
-                umma::fence_after_sync();
-                const uint64_t dbh = umma::smem_desc(umma::smem_u32(qbuf + sl * Q_IMG), lbo_b, 128);
-                const uint64_t dbl = umma::smem_desc(umma::smem_u32(qbuf + sl * Q_IMG + Q_HALF), lbo_b, 128);
+        // The whole warp walks the loop (warp-uniform control flow and operands); single instructions are issued by one elected lane.
+        const uint32_t idesc = umma::idesc_tf32(VT, QT);
+        constexpr uint32_t lbo_a = (VT / 8) * 128, lbo_b = (QT / 8) * 128;
+        const uint32_t v_hi_s = umma::smem_u32(v_hi), v_lo_s = umma::smem_u32(v_lo), q_s = umma::smem_u32(qbuf);
+        uint32_t ph_full = 0, ph_free = 0, ph_acc = 0;          // one phase bit per barrier (bit i = barrier i)
+        bool ok = true;
+        for (int c = 0; c < n_chunks && ok; ++c) {
+            const int b = c & 1, sl = c % NSLOT;
+            ok = umma::mbar_wait(&bar_qfull[sl], (ph_full >> sl) & 1);
+            ph_full ^= 1u << sl;
+            if (ok && c >= 2) { ok = umma::mbar_wait(&bar_accfree[b], (ph_acc >> b) & 1); ph_acc ^= 1u << b; }
+            if (!ok) break;
+            umma::fence_after_sync();
+            // descriptors differ only in the start address field (bits 0-13, in 16-byte units)
+            const uint64_t dbh = umma::smem_desc(q_s + sl * Q_IMG, lbo_b, 128);
+            const uint64_t dbl = umma::smem_desc(q_s + sl * Q_IMG + Q_HALF, lbo_b, 128);
+            if (umma::elect_one()) {
 #pragma unroll
                 for (int t = 0; t < TILES; ++t) {
                     const uint32_t acc = tmem + (uint32_t)(b * TILES + t) * QT;
+                    const uint32_t a_hi = tmem + ACC_COLS + (uint32_t)t * 2 * DD, a_lo = a_hi + DD;
+                    const uint64_t dah = A_TMEM ? 0 : umma::smem_desc(v_hi_s + t * V_BYTES, lbo_a, 128);
+                    const uint64_t dal = A_TMEM ? 0 : umma::smem_desc(v_lo_s + t * V_BYTES, lbo_a, 128);
 #pragma unroll
                     for (int j = 0; j < DD / 8; ++j) {
                         const uint64_t oa = (uint64_t)((2 * j * lbo_a) >> 4), ob = (uint64_t)((2 * j * lbo_b) >> 4);
-                        umma::mma_tf32(acc, dal[t] + oa, dbh + ob, idesc, j > 0);
-                        umma::mma_tf32(acc, dah[t] + oa, dbl + ob, idesc, true);
-                        umma::mma_tf32(acc, dah[t] + oa, dbh + ob, idesc, true);
+                        if (A_TMEM) {
+                            umma::mma_tf32_ts(acc, a_lo + 8 * j, dbh + ob, idesc, j > 0);
+                            umma::mma_tf32_ts(acc, a_hi + 8 * j, dbl + ob, idesc, true);
+                            umma::mma_tf32_ts(acc, a_hi + 8 * j, dbh + ob, idesc, true);
+                        } else {
+                            umma::mma_tf32(acc, dal + oa, dbh + ob, idesc, j > 0);
+                            umma::mma_tf32(acc, dah + oa, dbl + ob, idesc, true);
+                            umma::mma_tf32(acc, dah + oa, dbh + ob, idesc, true);
+                        }
                     }
                 }
                 umma::commit(&bar_m[b]);                         // → epilogue of chunk c
                 umma::commit(&bar_qfree[sl]);                    // → slot sl may be refilled
-                // refill: with a ring of NSLOT > 1 the slot of the PREVIOUS chunk is recycled (its MMAs finish while this chunk's
-                // are queued behind them); a single slot has to wait for this chunk itself
-                const int cc = NSLOT > 1 ? c - 1 : c;
-                if (cc >= 0 && cc + NSLOT < n_chunks) {
-                    const int s2 = cc % NSLOT;
-                    ok = umma::mbar_wait(&bar_qfree[s2], (ph_free >> s2) & 1);
-                    ph_free ^= 1u << s2;
-                    if (ok) {
-                        umma::mbar_expect_tx(&bar_qfull[s2], Q_IMG);
-                        umma::bulk_g2s(qbuf + s2 * Q_IMG, qimg + (size_t)(cc + NSLOT) * Q_IMG, Q_IMG, &bar_qfull[s2]);
-                    }
-                }
             }
-            if (!ok) { dead = 1; atomicOr(flags + 1, 1); }
+            __syncwarp();
+            // refill: with a ring of NSLOT > 1 the slot of the PREVIOUS chunk is recycled (its MMAs finish while this chunk's
+            // are queued behind them); a single slot has to wait for this chunk itself
+            const int cc = NSLOT > 1 ? c - 1 : c;
+            if (cc >= 0 && cc + NSLOT < n_chunks) {
+                const int s2 = cc % NSLOT;
+                ok = umma::mbar_wait(&bar_qfree[s2], (ph_free >> s2) & 1);
+                ph_free ^= 1u << s2;
+                if (ok && umma::elect_one()) {
+                    umma::mbar_expect_tx(&bar_qfull[s2], Q_IMG);
+                    umma::bulk_g2s(qbuf + s2 * Q_IMG, qimg + (size_t)(cc + NSLOT) * Q_IMG, Q_IMG, &bar_qfull[s2]);
+                }
+                __syncwarp();
+            }
         }
+        if (!ok && lane == 0) { dead = 1; atomicOr(flags + 1, 1); }
     } else {
         // ================================ epilogue warps ================================ //
         const int r_own = ((warp & 3) << 5) + lane, half = warp >> 2;
@@ -168,20 +211,29 @@ __global__ void __launch_bounds__(NT_F, 1) flat_scan_tc_kernel(const float* __re
             const int q0 = c * QT + half * 32;
 #pragma unroll
             for (int t = 0; t < TILES; ++t) {
+                const uint32_t acc = tmem + lane_off + (uint32_t)(b * TILES + t) * QT + half * 32;
                 float s[32];
-                umma::tmem_ld32(tmem + lane_off + (uint32_t)(b * TILES + t) * QT + half * 32, s);
+                umma::tmem_ld32(acc, s);
                 const long long row = row0 + t * VT + r_own;
-                if (row < n_rows) {
+                // branch-free survivor mask (a branch per score made the epilogue the bottleneck: 64 reconvergence regions per
+                // chunk, instruction-fetch bound); survivors are rare, so their columns are walked in a warp-uniform loop and
+                // the score is re-read from TMEM (one column for the 32 lanes) instead of indexing registers dynamically
+                uint32_t m = 0;
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        if (s[j] > th[j]) {
-                            const int pos = atomicAdd(count + q0 + j, 1);
-                            if (pos < cap) {
-                                cand_s[(long long)(q0 + j) * stride + kprev + pos] = s[j];
-                                cand_r[(long long)(q0 + j) * cap + pos] = (int)row;
-                            } else {
-                                flags[0] = 1;                    // survivor list full: the caller redoes the search on the chunked path
-                            }
+                for (int j = 0; j < 32; ++j) m |= (s[j] > th[j] ? 1u : 0u) << j;
+                if (row >= n_rows) m = 0;
+                uint32_t u = __reduce_or_sync(0xffffffffu, m);
+                while (u) {
+                    const int j = __ffs(u) - 1;
+                    u &= u - 1;
+                    const float v = umma::tmem_ld1(acc + j);
+                    if ((m >> j) & 1u) {
+                        const int pos = atomicAdd(count + q0 + j, 1);
+                        if (pos < cap) {
+                            cand_s[(long long)(q0 + j) * stride + kprev + pos] = v;
+                            cand_r[(long long)(q0 + j) * cap + pos] = (int)row;
+                        } else {
+                            flags[0] = 1;                        // survivor list full: the caller redoes the search on the chunked path
                         }
                     }
                 }
@@ -195,19 +247,19 @@ __global__ void __launch_bounds__(NT_F, 1) flat_scan_tc_kernel(const float* __re
     if (warp == 0) umma::tmem_free(tmem, TM_COLS);
 }
 
-template <int TILES, int NSLOT>
+template <int TILES, int NSLOT, bool A_TMEM>
 int launch_flat_scan(const float* x, long long n_rows, const unsigned char* qimg, int n_chunks, const float* thr, int* count,
                      float* cand_s, long long stride, int kprev, int* cand_r, int cap, int* flags, cudaStream_t st) {
     static bool attr_set = false;
-    constexpr size_t smem = flat_smem<TILES, NSLOT>();
+    constexpr size_t smem = flat_smem<TILES, NSLOT, A_TMEM>();
     if (!attr_set) {
-        RB_CUDA(cudaFuncSetAttribute(flat_scan_tc_kernel<TILES, NSLOT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        RB_CUDA(cudaFuncSetAttribute(flat_scan_tc_kernel<TILES, NSLOT, A_TMEM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_set = true;
     }
     const long long n_cta = (n_rows + TILES * VT - 1) / (TILES * VT);
     RB_REQUIRE(n_rows >= 1 && n_rows < (1ll << 31) && n_cta < (1ll << 31), "flat_scan: a round holds at most 2^31 rows");
-    flat_scan_tc_kernel<TILES, NSLOT><<<(unsigned)n_cta, NT_F, smem, st>>>(x, n_rows, qimg, n_chunks, thr, count, cand_s, stride, kprev,
-                                                                         cand_r, cap, flags);
+    flat_scan_tc_kernel<TILES, NSLOT, A_TMEM><<<(unsigned)n_cta, NT_F, smem, st>>>(x, n_rows, qimg, n_chunks, thr, count, cand_s, stride,
+                                                                                 kprev, cand_r, cap, flags);
     RB_LAUNCH_CHECK("flat_scan_tc_kernel");
     return RB200_OK;
 }
@@ -217,9 +269,13 @@ int launch_flat_scan(const float* x, long long n_rows, const unsigned char* qimg
 // one round: rows [0, n_rows) of x (the caller offsets x) against n_chunks·64 queries (image), thresholds thr[n_chunks·64]
 int rb_flat_scan_tc(const float* x, long long n_rows, const unsigned char* qimg, int n_chunks, const float* thr, int* count,
                     float* cand_s, long long stride, int kprev, int* cand_r, int cap, int* flags, cudaStream_t st) {
+    static int variant = -1;                // RB200_FLAT_VARIANT: 0 = rows in shared memory (SS MMAs), 1 = rows in TMEM (TS MMAs)
+    if (variant < 0) { const char* e = getenv("RB200_FLAT_VARIANT"); variant = e ? atoi(e) : 1; }
     if (n_chunks <= 2)
-        return launch_flat_scan<1, 1>(x, n_rows, qimg, n_chunks, thr, count, cand_s, stride, kprev, cand_r, cap, flags, st);
-    return launch_flat_scan<2, 3>(x, n_rows, qimg, n_chunks, thr, count, cand_s, stride, kprev, cand_r, cap, flags, st);
+        return launch_flat_scan<1, 1, false>(x, n_rows, qimg, n_chunks, thr, count, cand_s, stride, kprev, cand_r, cap, flags, st);
+    if (variant == 1)
+        return launch_flat_scan<2, 4, true>(x, n_rows, qimg, n_chunks, thr, count, cand_s, stride, kprev, cand_r, cap, flags, st);
+    return launch_flat_scan<2, 3, false>(x, n_rows, qimg, n_chunks, thr, count, cand_s, stride, kprev, cand_r, cap, flags, st);
 }
 
 int rb_flat_qimage(const float* q, int nq, int n_chunks, unsigned char* qimg, cudaStream_t st) {
