@@ -55,7 +55,7 @@ __global__ void __launch_bounds__(NT_F, 1) flat_scan_tc_kernel(const float* __re
     unsigned char* v_hi = smem;                                  // [TILES][V_BYTES]
     unsigned char* v_lo = smem + TILES * V_BYTES;
     unsigned char* qbuf = smem + (A_TMEM ? 0 : 2 * TILES * V_BYTES);      // [NSLOT][Q_IMG]
-    __shared__ __align__(8) uint64_t bar_qfull[NSLOT], bar_qfree[NSLOT], bar_m[2], bar_accfree[2];
+    __shared__ __align__(8) uint64_t bar_qfull[NSLOT], bar_qfree[NSLOT], bar_m[2 * TILES], bar_accfree[2 * TILES];   // per (buffer, tile) unit
     __shared__ uint32_t tmem_slot;
     __shared__ int dead;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -67,7 +67,7 @@ __global__ void __launch_bounds__(NT_F, 1) flat_scan_tc_kernel(const float* __re
     if (warp == 0) umma::tmem_alloc(&tmem_slot, TM_COLS);
     if (tid == NT_EPI) {
         for (int i = 0; i < NSLOT; ++i) { umma::mbar_init(&bar_qfull[i], 1); umma::mbar_init(&bar_qfree[i], 1); }
-        for (int i = 0; i < 2; ++i) { umma::mbar_init(&bar_m[i], 1); umma::mbar_init(&bar_accfree[i], NT_EPI); }
+        for (int i = 0; i < 2 * TILES; ++i) { umma::mbar_init(&bar_m[i], 1); umma::mbar_init(&bar_accfree[i], NT_EPI); }
         umma::fence_mbar_init();
         dead = 0;
         for (int i = 0; i < NSLOT && i < n_chunks; ++i) {        // the first query chunks are on their way while the rows are staged
@@ -148,16 +148,20 @@ __global__ void __launch_bounds__(NT_F, 1) flat_scan_tc_kernel(const float* __re
             const int b = c & 1, sl = c % NSLOT;
             ok = umma::mbar_wait(&bar_qfull[sl], (ph_full >> sl) & 1);
             ph_full ^= 1u << sl;
-            if (ok && c >= 2) { ok = umma::mbar_wait(&bar_accfree[b], (ph_acc >> b) & 1); ph_acc ^= 1u << b; }
             if (!ok) break;
-            umma::fence_after_sync();
             // descriptors differ only in the start address field (bits 0-13, in 16-byte units)
             const uint64_t dbh = umma::smem_desc(q_s + sl * Q_IMG, lbo_b, 128);
             const uint64_t dbl = umma::smem_desc(q_s + sl * Q_IMG + Q_HALF, lbo_b, 128);
-            if (umma::elect_one()) {
+            // one unit = (chunk, tile): 24 MMAs into its own accumulator, its own completion barrier — the epilogue of tile 0
+            // starts while the MMAs of tile 1 run, and an accumulator is needed again only four units later
 #pragma unroll
-                for (int t = 0; t < TILES; ++t) {
-                    const uint32_t acc = tmem + (uint32_t)(b * TILES + t) * QT;
+            for (int t = 0; t < TILES; ++t) {
+                const int un = b * TILES + t;
+                if (c >= 2) { ok = ok && umma::mbar_wait(&bar_accfree[un], (ph_acc >> un) & 1); ph_acc ^= 1u << un; }
+                if (!ok) break;
+                umma::fence_after_sync();
+                if (umma::elect_one()) {
+                    const uint32_t acc = tmem + (uint32_t)un * QT;
                     const uint32_t a_hi = tmem + ACC_COLS + (uint32_t)t * 2 * DD, a_lo = a_hi + DD;
                     const uint64_t dah = A_TMEM ? 0 : umma::smem_desc(v_hi_s + t * V_BYTES, lbo_a, 128);
                     const uint64_t dal = A_TMEM ? 0 : umma::smem_desc(v_lo_s + t * V_BYTES, lbo_a, 128);
@@ -174,10 +178,12 @@ __global__ void __launch_bounds__(NT_F, 1) flat_scan_tc_kernel(const float* __re
                             umma::mma_tf32(acc, dah + oa, dbh + ob, idesc, true);
                         }
                     }
+                    umma::commit(&bar_m[un]);                    // → epilogue of this unit
+                    if (t == TILES - 1) umma::commit(&bar_qfree[sl]);      // → slot sl may be refilled
                 }
-                umma::commit(&bar_m[b]);                         // → epilogue of chunk c
-                umma::commit(&bar_qfree[sl]);                    // → slot sl may be refilled
+                __syncwarp();
             }
+            if (!ok) break;
             __syncwarp();
             // refill: with a ring of NSLOT > 1 the slot of the PREVIOUS chunk is recycled (its MMAs finish while this chunk's
             // are queued behind them); a single slot has to wait for this chunk itself
@@ -204,42 +210,53 @@ __global__ void __launch_bounds__(NT_F, 1) flat_scan_tc_kernel(const float* __re
             float4 th4[8];                                       // thresholds of this thread's 32 queries (uniform loads)
 #pragma unroll
             for (int i = 0; i < 8; ++i) th4[i] = __ldg(reinterpret_cast<const float4*>(thr + (long long)c * QT + half * 32) + i);
-            if (!umma::mbar_wait(&bar_m[b], (ph_m >> b) & 1)) { atomicOr(flags + 1, 2); break; }
-            ph_m ^= 1u << b;
-            umma::fence_after_sync();
             const float* th = reinterpret_cast<const float*>(th4);
             const int q0 = c * QT + half * 32;
+            bool alive = true;
 #pragma unroll
             for (int t = 0; t < TILES; ++t) {
-                const uint32_t acc = tmem + lane_off + (uint32_t)(b * TILES + t) * QT + half * 32;
+                const int un = b * TILES + t;
+                if (!umma::mbar_wait(&bar_m[un], (ph_m >> un) & 1)) { atomicOr(flags + 1, 2); alive = false; break; }
+                ph_m ^= 1u << un;
+                umma::fence_after_sync();
+                const uint32_t acc = tmem + lane_off + (uint32_t)un * QT + half * 32;
                 float s[32];
                 umma::tmem_ld32(acc, s);
                 const long long row = row0 + t * VT + r_own;
-                // branch-free survivor mask (a branch per score made the epilogue the bottleneck: 64 reconvergence regions per
-                // chunk, instruction-fetch bound); survivors are rare, so their columns are walked in a warp-uniform loop and
-                // the score is re-read from TMEM (one column for the 32 lanes) instead of indexing registers dynamically
-                uint32_t m = 0;
+                // branch-free (a branch per score made the epilogue the bottleneck: 64 reconvergence regions per chunk,
+                // instruction-fetch bound).  One predicate-accumulating compare per score decides whether the warp has any
+                // survivor at all; only then is the per-score mask built.  Survivors are rare, so their columns are walked in a
+                // warp-uniform loop and the score is re-read from TMEM (one column for the 32 lanes) instead of indexing
+                // registers dynamically.
+                bool any = false;
 #pragma unroll
-                for (int j = 0; j < 32; ++j) m |= (s[j] > th[j] ? 1u : 0u) << j;
-                if (row >= n_rows) m = 0;
-                uint32_t u = __reduce_or_sync(0xffffffffu, m);
-                while (u) {
-                    const int j = __ffs(u) - 1;
-                    u &= u - 1;
-                    const float v = umma::tmem_ld1(acc + j);
-                    if ((m >> j) & 1u) {
-                        const int pos = atomicAdd(count + q0 + j, 1);
-                        if (pos < cap) {
-                            cand_s[(long long)(q0 + j) * stride + kprev + pos] = v;
-                            cand_r[(long long)(q0 + j) * cap + pos] = (int)row;
-                        } else {
-                            flags[0] = 1;                        // survivor list full: the caller redoes the search on the chunked path
+                for (int j = 0; j < 32; ++j) any = any || (s[j] > th[j]);
+                if (row >= n_rows) any = false;
+                if (__any_sync(0xffffffffu, any)) {
+                    uint32_t m = 0;
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) m |= (s[j] > th[j] ? 1u : 0u) << j;
+                    if (row >= n_rows) m = 0;
+                    uint32_t u = __reduce_or_sync(0xffffffffu, m);
+                    while (u) {
+                        const int j = __ffs(u) - 1;
+                        u &= u - 1;
+                        const float v = umma::tmem_ld1(acc + j);
+                        if ((m >> j) & 1u) {
+                            const int pos = atomicAdd(count + q0 + j, 1);
+                            if (pos < cap) {
+                                cand_s[(long long)(q0 + j) * stride + kprev + pos] = v;
+                                cand_r[(long long)(q0 + j) * cap + pos] = (int)row;
+                            } else {
+                                flags[0] = 1;                    // survivor list full: the caller redoes the search on the chunked path
+                            }
                         }
                     }
                 }
+                umma::fence_before_sync();
+                umma::mbar_arrive(&bar_accfree[un]);             // this accumulator may be overwritten by chunk c + 2
             }
-            umma::fence_before_sync();
-            umma::mbar_arrive(&bar_accfree[b]);                  // accumulator b may be overwritten by chunk c + 2
+            if (!alive) break;
         }
     }
     umma::fence_before_sync();

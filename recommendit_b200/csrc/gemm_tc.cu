@@ -64,7 +64,7 @@ __global__ void __launch_bounds__(128, 1) gemm_nt_tc_kernel(const float* __restr
         }
         umma::fence_proxy_async();
         __syncthreads();
-        if (tid == 0 && !dead) {
+        if (!dead && umma::elect_issuer(tid)) {
             umma::fence_after_sync();
             const uint32_t a_hi = umma::smem_u32(sA_hi), a_lo = umma::smem_u32(sA_lo);
             const uint32_t b_hi = umma::smem_u32(sB_hi), b_lo = umma::smem_u32(sB_lo);

@@ -169,21 +169,21 @@ __global__ void __launch_bounds__(NT_ALL, 1) inbatch_tc_kernel(const IbParams p)
         GemmDesc gs = make_gemm(x_hi, x_lo, XT, y_hi, y_lo, YT, YT);        // S   [128 × 64 y] = X · Yᵀ
         GemmDesc gg = make_gemm(g_hi, g_lo, XT, yt_hi, yt_lo, DD, DD);      // acc [128 × 64 d] = G · Y
         bar_sync(1, NT_ALL);                                                // X and Y(t_begin) staged
-        if (lane == 0) {
+        if (umma::elect_one()) {
             umma::fence_after_sync();
             issue<MODE, DD / 8>(gs, tmem);
             umma::commit(&bar_s_mem);
         }
         for (int t = t_begin; t < t_end; ++t) {
             bar_sync(1, NT_ALL);                                            // Y(t+1) staged, S(t−1) drained
-            if (lane == 0 && t + 1 < t_end) {
+            if (t + 1 < t_end && umma::elect_one()) {
                 umma::fence_after_sync();
                 issue<MODE, DD / 8>(gs, tmem + (uint32_t)((((t - t_begin) & 1) ^ 1) * YT));
                 umma::commit(&bar_s_mem);
             }
             if (WITH_GRAD) {
                 bar_sync(2, NT_ALL);                                        // G(t), Yᵀ(t) staged, acc(t−1) drained
-                if (lane == 0) {
+                if (umma::elect_one()) {
                     umma::fence_after_sync();
                     issue<MODE, YT / 8>(gg, tmem_acc);
                     umma::commit(&bar_g_mem);

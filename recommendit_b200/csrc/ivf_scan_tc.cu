@@ -118,7 +118,7 @@ __global__ void __launch_bounds__(NT_SC, 2) list_scan_tc_kernel(const float* __r
             umma::fence_before_sync();
             __syncthreads();
         }
-        if (tid == 0 && !dead) {
+        if (!dead && umma::elect_issuer(tid)) {
             umma::fence_after_sync();
             const uint32_t ah = umma::smem_u32(v_hi), al = umma::smem_u32(v_lo), bh = umma::smem_u32(q_hi), bl = umma::smem_u32(q_lo);
 #pragma unroll

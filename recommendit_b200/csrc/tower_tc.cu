@@ -228,7 +228,7 @@ __global__ void __launch_bounds__(NTD, 1) tower_fwd_tc_kernel(const FwdParams p)
     umma::fence_proxy_async();
     w_bar.wait();
     __syncthreads();
-    if (tid == 0 && !dead) {
+    if (!dead && umma::elect_issuer(tid)) {
         umma::fence_after_sync();
         issue_gemm<MODE>(tmem, x_hi, x_lo, ROWS, w1_hi, w1_lo, H, H, Kp, false);
         umma::commit(&mma_bar_s);
@@ -294,7 +294,7 @@ __global__ void __launch_bounds__(NTD, 1) tower_fwd_tc_kernel(const FwdParams p)
     umma::fence_proxy_async();
     w_bar.wait();
     __syncthreads();
-    if (tid == 0 && !dead) {
+    if (!dead && umma::elect_issuer(tid)) {
         umma::fence_after_sync();
         issue_gemm<MODE>(tmem + H, h_hi, h_lo, ROWS, w2_hi, w2_lo, D, D, H, false);
         umma::commit(&mma_bar_s);
@@ -412,7 +412,7 @@ __global__ void __launch_bounds__(NTD, 1) tower_bwd_data_tc_kernel(const BwdPara
     umma::fence_proxy_async();
     w_bar.wait();
     __syncthreads();
-    if (tid == 0 && !dead) {
+    if (!dead && umma::elect_issuer(tid)) {
         umma::fence_after_sync();
         issue_gemm<MODE>(tmem, g_hi, g_lo, ROWS, w2t_hi, w2t_lo, H, H, D, false);
         umma::commit(&mma_bar_s);
@@ -462,7 +462,7 @@ __global__ void __launch_bounds__(NTD, 1) tower_bwd_data_tc_kernel(const BwdPara
     umma::fence_proxy_async();
     w_bar.wait();
     __syncthreads();
-    if (tid == 0 && !dead) {
+    if (!dead && umma::elect_issuer(tid)) {
         umma::fence_after_sync();
         issue_gemm<MODE>(tmem + H, a_hi, a_lo, ROWS, w1t_hi, w1t_lo, D, D, H, false);
         umma::commit(&mma_bar_s);
@@ -610,7 +610,7 @@ __global__ void __launch_bounds__(NT, 1) tower_bwd_weights_tc_kernel(const BwdPa
         if (mq < NK / 4) put_block_t<MODE>(b2_hi, b2_lo, NK, mq, sq, lane, xv);
         umma::fence_proxy_async();
         __syncthreads();                         // operands staged; ids of chunk t+1 (stored one iteration ago) visible
-        if (tid == 0 && !dead) {
+        if (!dead && umma::elect_issuer(tid)) {
             umma::fence_after_sync();
             issue_gemm<MODE>(tmem, a1_hi, a1_lo, H, b1_hi, b1_lo, D, D, KC, false);        // dW2ᵀ [H × D]
             issue_gemm<MODE>(tmem + D, a2_hi, a2_lo, H, b2_hi, b2_lo, NK, NK, KC, false);  // dW1  [H × NK]

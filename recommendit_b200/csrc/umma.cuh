@@ -29,6 +29,9 @@ __device__ __forceinline__ bool elect_one() {
     return pred != 0;
 }
 
+// the MMA-issuing lane of warp 0: every lane of warp 0 must reach this call converged (it follows a __syncthreads everywhere)
+__device__ __forceinline__ bool elect_issuer(int tid) { return (tid >> 5) == 0 && elect_one(); }
+
 // ---- TMEM ------------------------------------------------------------------------------------------------ //
 // one full warp; writes the TMEM base address to *slot (shared memory)
 __device__ __forceinline__ void tmem_alloc(uint32_t* slot, uint32_t ncols) {
