@@ -180,7 +180,45 @@ struct SegJob {
     const float* rows; float* uniq_grads; float* dense; int cap;   // cap = upper bound of n_uniq (launch sizing)
     const int* first_pos;                                          // optional: pos[seg_start[s]] per segment (shorter load chain)
 };
-struct SegParams { SegJob job[2]; int n_jobs; int D4; };
+struct SegParams { SegJob job[2]; int n_jobs; int D4; int skip_long; };   // skip_long: segments over LONG_SEG rows are left to long_segments_kernel
+constexpr int LONG_SEG = 96;
+
+// s += rows[pos[k]] (column c) for k = k0 … k1-1 in ascending k — the order (hence the rounding) of a plain loop — but with the
+// loads of 16 rows issued before the first add: a plain loop is one pos → row dependent-latency chain per row, and a popular id
+// (Zipf-skewed users: one id can own 9 % of a batch) made one warp run 700 such links while the rest of the grid had long finished
+// (333 us of the C4 step; 20x the median segment kernel).
+__device__ __forceinline__ void seg_accumulate(float4& s, const float4* __restrict__ rows, const int* __restrict__ pos, int k0, int k1,
+                                               int D4, int c) {
+    constexpr int U = 16;
+    int k = k0;
+    for (; k + U <= k1; k += U) {
+        int pk[U];
+        float4 v[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) pk[u] = __ldg(pos + k + u);
+#pragma unroll
+        for (int u = 0; u < U; ++u) v[u] = __ldg(rows + (long long)pk[u] * D4 + c);
+        asm volatile("" ::: "memory");          // keep the 16 loads ahead of the adds (ptxas otherwise interleaves them 2-4 deep)
+#pragma unroll
+        for (int u = 0; u < U; ++u) { s.x += v[u].x; s.y += v[u].y; s.z += v[u].z; s.w += v[u].w; }
+    }
+    if (k + 4 <= k1) {
+        int pk[4];
+        float4 v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) pk[u] = __ldg(pos + k + u);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) v[u] = __ldg(rows + (long long)pk[u] * D4 + c);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) { s.x += v[u].x; s.y += v[u].y; s.z += v[u].z; s.w += v[u].w; }
+        k += 4;
+        // (segments of 4-15 rows take this branch once, then the tail loop)
+    }
+    for (; k < k1; ++k) {
+        const float4 v = __ldg(rows + (long long)__ldg(pos + k) * D4 + c);
+        s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+    }
+}
 
 // one warp per SEG_PER_WARP consecutive unique ids; the first row of each segment is fetched for all of them at once
 // (most segments of a large batch have length 1, so this keeps SEG_PER_WARP independent 16·D4-byte row reads in
@@ -221,10 +259,8 @@ __global__ void __launch_bounds__(NT) segment_sum2_kernel(const SegParams p) {
 #pragma unroll
         for (int i = 0; i < SEG_PER_WARP; ++i) {
             if (w0 + i >= n) break;
-            for (int k = beg[i] + 1; k < end[i]; ++k) {
-                const float4 v = __ldg(rows + (long long)J.pos[k] * D4 + c);
-                s[i].x += v.x; s[i].y += v.y; s[i].z += v.z; s[i].w += v.w;
-            }
+            if (p.skip_long && end[i] - beg[i] > LONG_SEG) continue;
+            seg_accumulate(s[i], rows, J.pos, beg[i] + 1, end[i], D4, c);
             if (J.uniq_grads) __stcs(reinterpret_cast<float4*>(J.uniq_grads) + (long long)(w0 + i) * D4 + c, s[i]);
             if (J.dense) {
                 float4* dp = reinterpret_cast<float4*>(J.dense) + drow[i] * D4 + c;
@@ -234,6 +270,62 @@ __global__ void __launch_bounds__(NT) segment_sum2_kernel(const SegParams p) {
             }
         }
     }
+}
+
+// Segments of more than LONG_SEG rows (a popular id under Zipf-skewed traffic: hundreds of rows) — one CTA of 32 warps per segment
+// instead of one warp: warp w adds rows beg+w, beg+w+32, … (ascending), the 32 partial sums are then added in warp order.
+// Deterministic (the split depends only on the segment's length).  Block b looks at segments b, b+G, b+2G, ….
+constexpr int LS_THREADS = 1024, LS_MAX_D = 256;
+__global__ void __launch_bounds__(LS_THREADS) long_segments_kernel(const SegParams p) {
+    __shared__ float part[32][LS_MAX_D + 4];
+    __shared__ int list[LS_THREADS], wcount[32];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int D4 = p.D4, D = D4 * 4;
+    for (int j = 0; j < p.n_jobs; ++j) {
+        const SegJob& J = p.job[j];
+        const int n = J.n_uniq[0];
+        const float4* __restrict__ rows = reinterpret_cast<const float4*>(J.rows);
+        for (int base = blockIdx.x; base < n; base += gridDim.x * LS_THREADS) {
+            // this block's long segments among base, base+G, …, listed in index order (ballot + prefix over the warps)
+            const int sidx = base + tid * gridDim.x;
+            const bool is_long = sidx < n && J.seg_start[sidx + 1] - J.seg_start[sidx] > LONG_SEG;
+            const unsigned bal = __ballot_sync(0xffffffffu, is_long);
+            __syncthreads();                                   // previous round's list / partials are no longer read
+            if (lane == 0) wcount[warp] = __popc(bal);
+            __syncthreads();
+            int off = __popc(bal & ((1u << lane) - 1u)), nl = 0;
+            for (int w = 0; w < 32; ++w) { const int cw = wcount[w]; if (w < warp) off += cw; nl += cw; }
+            if (is_long) list[off] = sidx;
+            __syncthreads();
+            for (int li = 0; li < nl; ++li) {
+                const int sg = list[li];
+                const int beg = J.seg_start[sg], end = J.seg_start[sg + 1];
+                for (int c = lane; c < D4; c += 32) {
+                    float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+                    for (int k = beg + warp; k < end; k += 32) {
+                        const float4 v = __ldg(rows + (long long)__ldg(J.pos + k) * D4 + c);
+                        a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+                    }
+                    *reinterpret_cast<float4*>(&part[warp][c * 4]) = a;
+                }
+                __syncthreads();
+                for (int d = tid; d < D; d += LS_THREADS) {
+                    float t = part[0][d];
+#pragma unroll 8
+                    for (int w = 1; w < 32; ++w) t += part[w][d];
+                    if (J.uniq_grads) J.uniq_grads[(long long)sg * D + d] = t;
+                    if (J.dense) J.dense[J.uniq_ids[sg] * (long long)D + d] += t;
+                }
+                __syncthreads();
+            }
+        }
+    }
+}
+static int launch_long_segments(const SegParams& gp, cudaStream_t st) {
+    if (gp.D4 * 4 > LS_MAX_D) return RB200_OK;      // (callers clear skip_long for such widths)
+    long_segments_kernel<<<64, LS_THREADS, 0, st>>>(gp);
+    RB_LAUNCH_CHECK("long_segments_kernel");
+    return RB200_OK;
 }
 
 int key_bits_strict(long long n_rows) {     // smallest b with 2^b > n_rows
@@ -409,10 +501,7 @@ __global__ void __launch_bounds__(NT) grad_finish_kernel(const FinishParams p, d
             const float4* __restrict__ rows = reinterpret_cast<const float4*>(J.rows);
             for (int c = lane; c < D4; c += 32) {
                 float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
-                for (int k = beg; k < end; ++k) {
-                    const float4 v = __ldg(rows + (long long)J.pos[k] * D4 + c);
-                    s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
-                }
+                seg_accumulate(s, rows, J.pos, beg, end, D4, c);
                 if (J.uniq_grads) reinterpret_cast<float4*>(J.uniq_grads)[(long long)w * D4 + c] = s;
                 if (J.dense) {
                     float4* dp = reinterpret_cast<float4*>(J.dense) + J.uniq_ids[w] * D4 + c;
@@ -741,8 +830,11 @@ static int scatter_sum(const ScatterPlan& pl, cudaStream_t st) {
     // small batches (the fused step): one segment per warp keeps every SM busy; see the large-batch path for 8 per warp
     long long warps = 0;
     for (int t = 0; t < pl.gp.n_jobs; ++t) warps += seg_warps<1>(pl.gp.job[t].cap);
-    segment_sum2_kernel<1><<<(unsigned)((warps * 32 + NT - 1) / NT), NT, 0, st>>>(pl.gp);
+    SegParams gp = pl.gp;
+    gp.skip_long = gp.D4 * 4 <= LS_MAX_D;
+    segment_sum2_kernel<1><<<(unsigned)((warps * 32 + NT - 1) / NT), NT, 0, st>>>(gp);
     RB_LAUNCH_CHECK("segment_sum2_kernel");
+    if (gp.skip_long) return launch_long_segments(gp, st);
     return RB200_OK;
 }
 
@@ -865,8 +957,10 @@ extern "C" int rb200_scatter_rows(const int64_t* ids, const float* rows, int B, 
         SegParams gp{};
         gp.n_jobs = 1; gp.D4 = D / 4;
         gp.job[0] = SegJob{p_out, seg_start, u_ids, n_u, rows, uniq_grads, dense_grad, B, first_pos};
+        gp.skip_long = D <= LS_MAX_D;
         segment_sum2_kernel<8><<<(unsigned)(((long long)seg_warps<8>(B) * 32 + NT - 1) / NT), NT, 0, st>>>(gp);
         RB_LAUNCH_CHECK("segment_sum2_kernel");
+        if (gp.skip_long) return launch_long_segments(gp, st);
         return RB200_OK;
     }
     const int bits = key_bits(n_rows);

@@ -228,7 +228,15 @@ class ShardedBPRTrainer:
 
     def __init__(self, n_users: int, n_items: int, embed_dim: int = 128, hidden_dim: int = 128, n_genres: int = 18,
                  lr: float = 1e-3, betas=(0.9, 0.999), eps: float = 1e-8, weight_decay: float = 1e-5, max_norm: float = 1.0,
-                 adam_mode: str = "rows", device=None, group=None, ops=None, seed: int = 0, init: Optional[Dict] = None):
+                 adam_mode: str = "rows", device=None, group=None, ops=None, seed: int = 0, init: Optional[Dict] = None,
+                 exchange: str = "exact", capacity_factor: float = 2.0, use_cuda_graph: bool = False):
+        if exchange not in ("exact", "padded"):
+            raise ValueError("exchange must be 'exact' (variable-size all-to-alls, one host sync per step) or 'padded' "
+                             "(fixed-capacity all-to-alls: no host sync, CUDA-graph capturable)")
+        if use_cuda_graph and exchange != "padded":
+            raise ValueError("use_cuda_graph needs exchange='padded' (the exact exchange reads its split sizes on the host)")
+        self.exchange, self.capacity_factor, self.use_graph = exchange, float(capacity_factor), use_cuda_graph
+        self._graph, self._static_in, self._static_loss, self._eager_steps = None, None, None, 0
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
@@ -281,6 +289,7 @@ class ShardedBPRTrainer:
         self.ops.write_opt(self.opt, st)
         self.steps = 0
         self.max_norm = max_norm
+        self.overflow = torch.zeros(1, dtype=torch.int64, device=self.dev)     # padded exchange: requests that did not fit
 
     # views of the flat MLP blocks
     def _mlp_views(self, flat: torch.Tensor, din: int):
@@ -309,19 +318,101 @@ class ShardedBPRTrainer:
         rt.recv_rows = all_to_all_var(rt.local_rows, rt.send_counts, rt.recv_counts, self.group)
         return rt
 
+    def capacity(self, n_requests: int) -> int:
+        """rows one (source, owner) pair can exchange per step in the padded mode"""
+        return min(n_requests, int(math.ceil(n_requests / self.world * self.capacity_factor)) + 16)
+
+    def _route_padded(self, user_ids: torch.Tensor, item_ids: torch.Tensor):
+        """Fixed-capacity form of the plan: bucket w of the request list occupies slots [w·C, (w+1)·C) of a padded buffer
+        (empty slots carry row -1), so every all-to-all has equal, host-known splits — nothing is read back from the device
+        and the whole step can be captured in a CUDA graph.  Requests beyond a bucket's capacity are counted in
+        ``self.overflow`` (see ``check_exchange``).  → (slot of each sample-order request [n], rows requested FROM this
+        rank [W·C] with -1 padding, C)"""
+        W = self.world
+        n = user_ids.numel() + item_ids.numel()
+        C = self.capacity(n)
+        dev = user_ids.device
+        perm, inv, local_rows, send = self.ops.route(user_ids.contiguous(), item_ids.contiguous(), W, self._nu_by_rank)
+        ends = torch.cumsum(send, 0)
+        pos = torch.arange(n, device=dev, dtype=torch.int64)
+        owner = torch.bucketize(pos, ends, right=True).clamp_(max=W - 1)       # bucket of each position of the bucket order
+        off = pos - (ends - send)[owner]
+        fits = off < C
+        self.overflow += (~fits).sum()
+        slot = torch.where(fits, owner * C + off, torch.full_like(pos, W * C))  # what does not fit goes to a dummy slot
+        send_rows = torch.full((W * C + 1,), -1, dtype=torch.int64, device=dev)
+        send_rows.index_copy_(0, slot, local_rows)
+        if W == 1:
+            recv_rows = send_rows[:W * C]
+        else:
+            recv_rows = torch.empty(W * C, dtype=torch.int64, device=dev)
+            dist.all_to_all_single(recv_rows, send_rows[:W * C].contiguous(), group=self.group)
+        return slot[inv].clamp_(max=W * C - 1), recv_rows, C
+
+    def close(self) -> None:
+        """Release the captured step.  A CUDA graph that holds NCCL collectives must be gone BEFORE
+        ``torch.distributed.destroy_process_group()`` — destroying the communicator under a live graph hangs the process at
+        exit (measured on NCCL 2.28 / torch 2.11) — so call this (or drop the trainer) first."""
+        self._graph = None
+        self._static_loss = None
+
+    def check_exchange(self) -> None:
+        """Padded exchange only: raise if any request of a past step did not fit its bucket (synchronises)."""
+        lost = int(self.overflow.item())
+        if lost:
+            raise _lib.RB200Error(f"{lost} embedding-row requests exceeded the exchange capacity (capacity_factor="
+                                  f"{self.capacity_factor}): the affected steps are wrong — rebuild the trainer with a larger "
+                                  "capacity_factor or exchange='exact'")
+
     def step(self, user_ids, pos_ids, pos_genres, neg_ids, neg_genres) -> torch.Tensor:
         """One optimiser step on this rank's local batch (device tensors).  Returns the global mean loss (device scalar).
 
         Exchanges per step: request counts, requested rows, served rows, row gradients (all-to-all), MLP gradients and the
-        {Σg², loss} pair (all-reduce).  One host synchronisation (the split sizes of the all-to-alls)."""
+        {Σg², loss} pair (all-reduce).  ``exchange='exact'``: variable-size all-to-alls, one host synchronisation (their split
+        sizes).  ``exchange='padded'``: fixed-capacity all-to-alls, no host synchronisation; with ``use_cuda_graph`` the whole
+        step, collectives included, is one graph replay after two eager steps."""
+        if not self.use_graph:
+            return self._step(user_ids, pos_ids, pos_genres, neg_ids, neg_genres)
+        batch = (user_ids, pos_ids, pos_genres, neg_ids, neg_genres)
+        if self._static_in is None or any(a.shape != b.shape for a, b in zip(self._static_in, batch)):
+            self._static_in = [b.clone() for b in batch]
+            self._graph, self._eager_steps = None, 0
+        else:
+            for dst, src in zip(self._static_in, batch):
+                dst.copy_(src, non_blocking=True)
+        if self._graph is None and self._eager_steps < 2:          # communicators, kernel attributes and allocator warm up
+            self._eager_steps += 1
+            return self._step(*self._static_in)
+        if self._graph is None:
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self._static_loss = self._step(*self._static_in)
+            self._graph = g
+            self.steps -= 1                                        # capture enqueues nothing
+        self._graph.replay()
+        self.steps += 1
+        return self._static_loss
+
+    def _step(self, user_ids, pos_ids, pos_genres, neg_ids, neg_genres) -> torch.Tensor:
         ops, D, H, E, W = self.ops, self.D, self.H, self.E, self.world
         B = user_ids.numel()
         dev = user_ids.device
         f32 = dict(dtype=torch.float32, device=dev)
+        padded = self.exchange == "padded"
         # steps 1-3: route the ids to their owners, gather there, bring the rows back (bucket order)
-        rt = self._route(user_ids, torch.cat([pos_ids, neg_ids]))
-        served = ops.gather_rows(self.table, rt.recv_rows)
-        rows = served if W == 1 else all_to_all_var(served, rt.recv_counts, rt.send_counts, self.group)
+        if padded:
+            slot, recv_rows, C = self._route_padded(user_ids, torch.cat([pos_ids, neg_ids]))
+            served = ops.gather_rows(self.table, recv_rows.clamp(min=0))
+            if W == 1:
+                rows = served
+            else:
+                rows = torch.empty_like(served)
+                dist.all_to_all_single(rows, served, group=self.group)
+            rt = Route(perm=None, inv=slot, local_rows=None, send_counts=None, recv_rows=recv_rows)
+        else:
+            rt = self._route(user_ids, torch.cat([pos_ids, neg_ids]))
+            served = ops.gather_rows(self.table, rt.recv_rows)
+            rows = served if W == 1 else all_to_all_var(served, rt.recv_counts, rt.send_counts, self.group)
         ops.begin_step(self.opt)
 
         uW1, ub1, uW2, ub2 = self._mlp_views(self.user_mlp, D)
@@ -347,9 +438,18 @@ class ShardedBPRTrainer:
         ops.towers_bwd(jobs[1:], D, H, 0.0, g_mlp[Pu:])
 
         # steps 4-5: row gradients (sample order → bucket order) back to the owning shards, deterministic segment sums there
-        g_rows = ops.gather_rows(drows, rt.perm)
-        if W > 1:
-            g_rows = all_to_all_var(g_rows, rt.send_counts, rt.recv_counts, self.group)
+        if padded:
+            g_pad = torch.empty(W * C + 1, D, **f32)               # empty slots are skipped at the owner (their row is -1)
+            g_pad.index_copy_(0, rt.inv, drows)
+            if W == 1:
+                g_rows = g_pad[:W * C]
+            else:
+                g_rows = torch.empty(W * C, D, **f32)
+                dist.all_to_all_single(g_rows, g_pad[:W * C], group=self.group)
+        else:
+            g_rows = ops.gather_rows(drows, rt.perm)
+            if W > 1:
+                g_rows = all_to_all_var(g_rows, rt.send_counts, rt.recv_counts, self.group)
         rows_sc = rt.recv_rows
         if self.rank == 0:       # the global padding ids 0 live on rank 0 (local rows 0 and n_user_local): no gradient
             nu0 = self.user_table.shape[0]

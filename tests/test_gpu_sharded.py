@@ -52,6 +52,21 @@ def batch(r, s):
             rng.integers(0, NI + 1, B), (rng.random((B, 18)) < .2).astype(np.float32))
 losses = [float(tr.step(*[torch.from_numpy(a).to(dev) for a in batch(rank, s)])) for s in range(2)]
 full = tr.full_state()
+# the same steps through the fixed-capacity exchange, eagerly and as ONE CUDA graph per step (NCCL collectives captured):
+# 4 steps = 2 eager + capture + replay; must equal the exact exchange step for step (same kernels, same order of sums)
+tr_e = ShardedBPRTrainer(NU, NI, D, H, adam_mode="dense", device=dev, init={k: torch.from_numpy(v) for k, v in P.items()}, lr=1e-2)
+tr_g = ShardedBPRTrainer(NU, NI, D, H, adam_mode="dense", device=dev, init={k: torch.from_numpy(v) for k, v in P.items()}, lr=1e-2,
+                         exchange="padded", capacity_factor=1.5, use_cuda_graph=True)
+pad_diff = 0.0
+for s in range(4):
+    b = [torch.from_numpy(a).to(dev) for a in batch(rank, s)]
+    le, lg = float(tr_e.step(*b)), float(tr_g.step(*b))
+    pad_diff = max(pad_diff, abs(le - lg))
+tr_g.check_exchange()
+assert tr_g._graph is not None
+fe, fg = tr_e.full_state(), tr_g.full_state()
+pad_param_diff = max(float((fe[k] - fg[k]).abs().max()) for k in O.PARAM_KEYS)
+tr_g.close()          # a live graph with NCCL nodes would hang destroy_process_group()
 # sharded retrieval
 g = torch.Generator().manual_seed(0)
 x = torch.nn.functional.normalize(torch.randn(20000, 64, generator=g), dim=-1)
@@ -88,9 +103,29 @@ if rank == 0:
     s_ref, i_ref = V.flat_search(q.numpy(), x.numpy(), 100)
     V.assert_topk_equivalent(s.cpu().numpy(), i.cpu().numpy(), s_ref, i_ref)
     print("RESULT " + json.dumps({"losses": losses, "ref": ref, "max_param_err": err, "dp_losses": dp_losses, "dp_ref": dp_ref,
-                                  "dp_err": dp_err}))
+                                  "dp_err": dp_err, "pad_diff": pad_diff, "pad_param_diff": pad_param_diff}))
 dist.barrier(); dist.destroy_process_group()
 '''
+
+
+def test_sharded_world1_padded_graph_equals_exact(golden):
+    """exchange='padded' + use_cuda_graph (the whole step one graph replay) against the exact exchange, world 1."""
+    from recommendit_b200.sharded import ShardedBPRTrainer
+    g = golden("tt_d128")
+    nu, ni, D, H = (int(v) for v in g["meta"][:4])
+    init = {k: torch.from_numpy(g["init/" + k]) for k in O.PARAM_KEYS}
+    a = ShardedBPRTrainer(nu, ni, D, H, adam_mode="rows", device="cuda", init=init, lr=float(g["lr"]))
+    b = ShardedBPRTrainer(nu, ni, D, H, adam_mode="rows", device="cuda", init=init, lr=float(g["lr"]), exchange="padded",
+                          use_cuda_graph=True)
+    for s in range(5):
+        batch = [dev(x) for x in batch_from_golden(g, s % 2)]
+        la, lb = float(a.step(*batch)), float(b.step(*batch))
+        assert abs(la - lb) <= 1e-6, (s, la, lb)
+    assert b._graph is not None
+    b.check_exchange()
+    fa, fb = a.full_state(), b.full_state()
+    for k in O.PARAM_KEYS:
+        assert float((fa[k] - fb[k]).abs().max()) <= 1e-6, k
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
@@ -101,7 +136,7 @@ def test_sharded_world2_nccl_matches_single_process_oracle(tmp_path):
     with socket.socket() as s:
         s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]
     out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
-                          "--master-port", str(port), str(script)], capture_output=True, text=True, timeout=600)
+                          "--master-port", str(port), str(script)], capture_output=True, text=True, timeout=240)
     assert out.returncode == 0, out.stderr[-3000:]
     line = [l for l in out.stdout.splitlines() if l.startswith("RESULT ")][0]
     r = json.loads(line[7:])
@@ -109,6 +144,7 @@ def test_sharded_world2_nccl_matches_single_process_oracle(tmp_path):
     assert r["max_param_err"] <= 0.5 * 1e-2, r
     assert np.allclose(r["dp_losses"], r["dp_ref"], atol=2e-5), r
     assert r["dp_err"] <= 0.5 * 1e-2, r
+    assert r["pad_diff"] <= 1e-6 and r["pad_param_diff"] <= 1e-6, r
 
 
 @pytest.mark.parametrize("world,n_u,n_i", [(1, 100, 200), (2, 8192, 16384), (8, 5000, 10001), (3, 0, 77), (64, 300, 0)])

@@ -258,6 +258,43 @@ def test_scatter_rows_large_batches_vs_oracle(B, n_rows, D):
         assert rel_l2(dense.cpu().numpy(), ref) <= 1e-6 and torch.count_nonzero(dense[0]) == 0
 
 
+@pytest.mark.parametrize("B,n_rows,D,kind", [(24576, 1_250_000, 128, "zipf"), (6000, 50_000, 64, "zipf"), (9000, 77, 64, "one"),
+                                             (500_000, 4200, 32, "uniform")])
+def test_scatter_rows_long_segments(B, n_rows, D, kind):
+    """Popular ids (Zipf-skewed users: one id owns hundreds of rows of a batch) go through long_segments_kernel — one CTA per
+    segment instead of one warp; a single segment holding the whole batch; more long segments than a block's list holds."""
+    from recommendit_b200 import _lib
+    lib = _lib.load()
+    rng = np.random.default_rng(B)
+    if kind == "zipf":
+        ids = (rng.zipf(1.05, B) - 1) % n_rows
+    elif kind == "one":
+        ids = np.full(B, 5, dtype=np.int64)
+    else:
+        ids = rng.integers(0, n_rows, B)
+    rows = rng.standard_normal((B, D)).astype(np.float32)
+    d_ids, d_rows = dev(ids), dev(rows)
+    uq = torch.empty(B, dtype=torch.int64, device="cuda"); ug = torch.empty(B, D, device="cuda")
+    nu = torch.zeros(1, dtype=torch.int32, device="cuda")
+    wsb = lib.rb200_scatter_workspace_bytes(B, n_rows)
+    ws = _lib.workspace(wsb, "cuda")
+    outs = []
+    for _ in range(2):
+        ug.fill_(float("nan"))
+        _lib.check(lib.rb200_scatter_rows(d_ids.data_ptr(), d_rows.data_ptr(), B, D, n_rows, -1, None, uq.data_ptr(), ug.data_ptr(),
+                                          nu.data_ptr(), None, ws.data_ptr(), wsb, _lib.stream_ptr()))
+        n = int(nu.item())
+        outs.append((uq[:n].cpu().numpy().copy(), ug[:n].cpu().numpy().copy()))
+    assert np.array_equal(outs[0][1], outs[1][1])                          # deterministic
+    exp_ids, counts = np.unique(ids, return_counts=True)
+    assert np.array_equal(outs[0][0], exp_ids)
+    if kind != "uniform":
+        assert counts.max() > 96                                           # the case really has a long segment
+    ref = np.zeros((n_rows, D), np.float64)
+    np.add.at(ref, ids, rows.astype(np.float64))
+    assert rel_l2(outs[0][1], ref[exp_ids]) <= 1e-6
+
+
 def test_train_epoch_pipelined_equals_step_host_loop(golden):
     """train_epoch (H2D prefetch on a copy stream, async loss read-back) must produce exactly the parameters and the mean
     loss of the synchronous per-step loop (train_embeddings.py:170-199) on the same batches."""

@@ -29,7 +29,7 @@ def _batches(rank, step):
     return u, p, pg, n, ng
 
 
-def _train_worker(rank, world, port, adam_mode, q):
+def _train_worker(rank, world, port, adam_mode, exchange, q):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
@@ -37,25 +37,39 @@ def _train_worker(rank, world, port, adam_mode, q):
         from tests.oracle_ops import OracleOps
         P = O.init_params(NU, NI, D, H, seed=3)
         init = {k: torch.from_numpy(v) for k, v in P.items()}
-        tr = ShardedBPRTrainer(NU, NI, D, H, adam_mode=adam_mode, device="cpu", ops=OracleOps(), init=init, lr=1e-2)
+        tr = ShardedBPRTrainer(NU, NI, D, H, adam_mode=adam_mode, device="cpu", ops=OracleOps(), init=init, lr=1e-2, exchange=exchange,
+                               capacity_factor=1.5)
         losses = []
         for step in range(2):
             b = _batches(rank, step)
             losses.append(float(tr.step(*[torch.from_numpy(a) for a in b])))
         full = {k: v.numpy() for k, v in tr.full_state().items()}
+        if exchange == "padded":
+            tr.check_exchange()                                    # nothing was dropped at the default capacity
+            assert tr.capacity(3 * B) < 3 * B                      # … and the buffers really are smaller than the worst case
+            # a capacity that cannot hold the batch must be reported, not silently produce a wrong step
+            from recommendit_b200 import RB200Error
+            small = ShardedBPRTrainer(NU, NI, D, H, adam_mode=adam_mode, device="cpu", ops=OracleOps(), init=init, exchange="padded",
+                                      capacity_factor=0.25)
+            small.step(*[torch.from_numpy(a) for a in _batches(rank, 0)])
+            try:
+                small.check_exchange()
+                raise AssertionError("overflow not reported")
+            except RB200Error:
+                pass
         if rank == 0:
             q.put((losses, full))
     finally:
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("adam_mode", ["dense", "rows"])
-def test_sharded_step_equals_single_process(adam_mode):
+@pytest.mark.parametrize("adam_mode,exchange", [("dense", "exact"), ("rows", "exact"), ("rows", "padded"), ("dense", "padded")])
+def test_sharded_step_equals_single_process(adam_mode, exchange):
     world = 2
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_train_worker, args=(r, world, port, adam_mode, q)) for r in range(world)]
+    procs = [ctx.Process(target=_train_worker, args=(r, world, port, adam_mode, exchange, q)) for r in range(world)]
     for p in procs:
         p.start()
     losses, full = q.get(timeout=240)
