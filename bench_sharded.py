@@ -115,6 +115,26 @@ def _run(args):
     ms4 = _timed(lambda i: st4.step(*res4[i % 8]), K4, dev)
     st4.check_exchange()                                 # no request exceeded the exchange capacity
 
+    cap4 = st4.capacity(3 * B)
+    st4.close(); del st4                                 # the captured step holds NCCL nodes: release it before the process group goes
+    torch.cuda.empty_cache()
+
+    # ---- secondary: C5, exhaustive top-500 over a row-sharded database (12.5 M x 64 per rank; 100 M rows at world 8) -------- #
+    from bench import make_flat_shard
+    from recommendit_b200.sharded import sharded_flat_search
+    rows5, nq5, k5 = 12_500_000, 4096, 500
+    x5 = make_flat_shard(dev, rows5, 13 + rank)
+    g5 = torch.Generator(device=dev).manual_seed(14)                       # the same queries on every rank
+    q5 = torch.nn.functional.normalize(torch.randn(nq5, 64, device=dev, generator=g5), dim=-1)
+    s5, i5 = sharded_flat_search(q5, x5, k5, rank * rows5)                  # warm-up
+    ms5 = _timed(lambda i: sharded_flat_search(q5, x5, k5, rank * rows5), 3, dev) / 3
+    # every rank must hold the same merged result; its ids must come from all shards
+    chk5 = i5.double().sum().reshape(1)
+    lo5, hi5 = chk5.clone(), chk5.clone()
+    dist.all_reduce(lo5, op=dist.ReduceOp.MIN); dist.all_reduce(hi5, op=dist.ReduceOp.MAX)
+    shards_hit = int(torch.unique(torch.div(i5, rows5, rounding_mode="floor")).numel())
+    del x5
+
     if rank == 0:
         value = world * B * K / (total_ms * 1e-3)
         ar_bytes = tr.dp_grads.numel() * 4
@@ -140,8 +160,15 @@ def _run(args):
                    "config": {"workload": f"C4: row-sharded tables x{world} (id mod world), 10M users x 1M items, D=128, H=128, "
                                           f"{B} samples per rank per step, ids Zipf(1.05) users / uniform items, Adam on touched rows",
                               "parallelism": "NCCL all-to-all ids/rows/row-gradients + all-reduce MLP grads and scalars; fixed-capacity "
-                                             f"exchange buffers ({st4.capacity(3 * B)} rows per rank pair, 2x the mean), no host "
+                                             f"exchange buffers ({cap4} rows per rank pair, 2x the mean), no host "
                                              "synchronisation: the whole step incl. the collectives is ONE CUDA graph replay"}},
+            "c5": {"metric": "flat_top500_qps", "value": nq5 / ms5 * 1e3, "unit": "queries/s", "ms_per_batch": ms5,
+                   "logical_tflops_all_gpus": 2.0 * nq5 * rows5 * world * 64 / (ms5 * 1e-3) / 1e12,
+                   "ranks_agree": bool((lo5 == hi5).item()), "shards_in_result": shards_hit,
+                   "config": {"workload": f"C5: exhaustive inner-product top-{k5} over {rows5 * world / 1e6:.1f} M x 64 fp32 rows "
+                                          f"sharded over {world} GPUs ({rows5 / 1e6:.1f} M rows each), {nq5} queries per batch",
+                              "parallelism": "per-shard rb200_flat_search (threshold-pruned tcgen05 scan) + NCCL all-gather of the "
+                                             "(score, id)[nq, 500] lists + rb200_topk_merge on every rank"}},
             "clocks": clocks, "final_loss": float(loss),
         }
         return line
