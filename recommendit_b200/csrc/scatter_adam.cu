@@ -180,41 +180,16 @@ struct SegJob {
     const float* rows; float* uniq_grads; float* dense; int cap;   // cap = upper bound of n_uniq (launch sizing)
     const int* first_pos;                                          // optional: pos[seg_start[s]] per segment (shorter load chain)
 };
-struct SegParams { SegJob job[2]; int n_jobs; int D4; int skip_long; };   // skip_long: segments over LONG_SEG rows are left to long_segments_kernel
-constexpr int LONG_SEG = 96;
+struct SegParams { SegJob job[2]; int n_jobs; int D4; int skip_long; int* long_count; };   // skip_long: segments over LONG_SEG rows are left to long_segments_kernel
+constexpr int LONG_SEG = 48;
 
-// s += rows[pos[k]] (column c) for k = k0 … k1-1 in ascending k — the order (hence the rounding) of a plain loop — but with the
-// loads of 16 rows issued before the first add: a plain loop is one pos → row dependent-latency chain per row, and a popular id
-// (Zipf-skewed users: one id can own 9 % of a batch) made one warp run 700 such links while the rest of the grid had long finished
-// (333 us of the C4 step; 20x the median segment kernel).
+// s += rows[pos[k]] (column c) for k = k0 … k1-1 in ascending k.  One pos → row dependent-latency chain per row: fine for the short
+// segments this is used for; segments of a popular id (Zipf-skewed users: one id can own 9 % of a batch, 700 links, 333 us of the
+// C4 step while the rest of the grid had long finished) are summed by many warps instead — long_segments_kernel after
+// segment_sum2_kernel, the whole block inside grad_finish_kernel.
 __device__ __forceinline__ void seg_accumulate(float4& s, const float4* __restrict__ rows, const int* __restrict__ pos, int k0, int k1,
                                                int D4, int c) {
-    constexpr int U = 16;
-    int k = k0;
-    for (; k + U <= k1; k += U) {
-        int pk[U];
-        float4 v[U];
-#pragma unroll
-        for (int u = 0; u < U; ++u) pk[u] = __ldg(pos + k + u);
-#pragma unroll
-        for (int u = 0; u < U; ++u) v[u] = __ldg(rows + (long long)pk[u] * D4 + c);
-        asm volatile("" ::: "memory");          // keep the 16 loads ahead of the adds (ptxas otherwise interleaves them 2-4 deep)
-#pragma unroll
-        for (int u = 0; u < U; ++u) { s.x += v[u].x; s.y += v[u].y; s.z += v[u].z; s.w += v[u].w; }
-    }
-    if (k + 4 <= k1) {
-        int pk[4];
-        float4 v[4];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) pk[u] = __ldg(pos + k + u);
-#pragma unroll
-        for (int u = 0; u < 4; ++u) v[u] = __ldg(rows + (long long)pk[u] * D4 + c);
-#pragma unroll
-        for (int u = 0; u < 4; ++u) { s.x += v[u].x; s.y += v[u].y; s.z += v[u].z; s.w += v[u].w; }
-        k += 4;
-        // (segments of 4-15 rows take this branch once, then the tail loop)
-    }
-    for (; k < k1; ++k) {
+    for (int k = k0; k < k1; ++k) {
         const float4 v = __ldg(rows + (long long)__ldg(pos + k) * D4 + c);
         s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
     }
@@ -251,6 +226,14 @@ __global__ void __launch_bounds__(NT) segment_sum2_kernel(const SegParams p) {
     }
     const int D4 = p.D4;
     const float4* __restrict__ rows = reinterpret_cast<const float4*>(J.rows);
+    if (p.skip_long) {
+        // a long segment (popular id) keeps only its FIRST row here; long_segments_kernel adds the rest with 32 warps
+        bool any = false;
+#pragma unroll
+        for (int i = 0; i < SEG_PER_WARP; ++i)
+            if (w0 + i < n && end[i] - beg[i] > LONG_SEG) { end[i] = beg[i] + 1; any = true; }
+        if (any && p.long_count && lane == 0) atomicAdd(p.long_count, 1);
+    }
     for (int c = lane; c < D4; c += 32) {
         float4 s[SEG_PER_WARP];
 #pragma unroll
@@ -259,8 +242,10 @@ __global__ void __launch_bounds__(NT) segment_sum2_kernel(const SegParams p) {
 #pragma unroll
         for (int i = 0; i < SEG_PER_WARP; ++i) {
             if (w0 + i >= n) break;
-            if (p.skip_long && end[i] - beg[i] > LONG_SEG) continue;
-            seg_accumulate(s[i], rows, J.pos, beg[i] + 1, end[i], D4, c);
+            for (int k = beg[i] + 1; k < end[i]; ++k) {
+                const float4 v = __ldg(rows + (long long)J.pos[k] * D4 + c);
+                s[i].x += v.x; s[i].y += v.y; s[i].z += v.z; s[i].w += v.w;
+            }
             if (J.uniq_grads) __stcs(reinterpret_cast<float4*>(J.uniq_grads) + (long long)(w0 + i) * D4 + c, s[i]);
             if (J.dense) {
                 float4* dp = reinterpret_cast<float4*>(J.dense) + drow[i] * D4 + c;
@@ -273,7 +258,8 @@ __global__ void __launch_bounds__(NT) segment_sum2_kernel(const SegParams p) {
 }
 
 // Segments of more than LONG_SEG rows (a popular id under Zipf-skewed traffic: hundreds of rows) — one CTA of 32 warps per segment
-// instead of one warp: warp w adds rows beg+w, beg+w+32, … (ascending), the 32 partial sums are then added in warp order.
+// instead of one warp: segment_sum2_kernel has written the segment's first row; warp w adds rows beg+1+w, beg+1+w+32, … (ascending),
+// the 32 partial sums are added in warp order and the total is added to the first row.
 // Deterministic (the split depends only on the segment's length).  Block b looks at segments b, b+G, b+2G, ….
 constexpr int LS_THREADS = 1024, LS_MAX_D = 256;
 __global__ void __launch_bounds__(LS_THREADS) long_segments_kernel(const SegParams p) {
@@ -281,6 +267,7 @@ __global__ void __launch_bounds__(LS_THREADS) long_segments_kernel(const SegPara
     __shared__ int list[LS_THREADS], wcount[32];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int D4 = p.D4, D = D4 * 4;
+    if (p.long_count && *p.long_count == 0) return;            // the segment kernel met no long segment: nothing to do
     for (int j = 0; j < p.n_jobs; ++j) {
         const SegJob& J = p.job[j];
         const int n = J.n_uniq[0];
@@ -302,7 +289,7 @@ __global__ void __launch_bounds__(LS_THREADS) long_segments_kernel(const SegPara
                 const int beg = J.seg_start[sg], end = J.seg_start[sg + 1];
                 for (int c = lane; c < D4; c += 32) {
                     float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
-                    for (int k = beg + warp; k < end; k += 32) {
+                    for (int k = beg + 1 + warp; k < end; k += 32) {       // (row `beg` was taken by segment_sum2_kernel)
                         const float4 v = __ldg(rows + (long long)__ldg(J.pos + k) * D4 + c);
                         a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
                     }
@@ -313,7 +300,7 @@ __global__ void __launch_bounds__(LS_THREADS) long_segments_kernel(const SegPara
                     float t = part[0][d];
 #pragma unroll 8
                     for (int w = 1; w < 32; ++w) t += part[w][d];
-                    if (J.uniq_grads) J.uniq_grads[(long long)sg * D + d] = t;
+                    if (J.uniq_grads) J.uniq_grads[(long long)sg * D + d] += t;
                     if (J.dense) J.dense[J.uniq_ids[sg] * (long long)D + d] += t;
                 }
                 __syncthreads();
@@ -480,11 +467,14 @@ __global__ void __launch_bounds__(NT) sumsq_kernel(const SumsqSegs segs, double*
 // index order and derives total_norm / clip_coef): clip_grad_norm_ needs no pass of its own.
 // ------------------------------------------------------------------------------------------------------------ //
 struct RedSet { const float* part; int nsplit; int P; int H; int Din; float* out; };
+constexpr int FIN_LONG_SEG = 32, FIN_MAX_D = 256;      // grad_finish_kernel: segments above 32 rows are summed by the whole block
 struct FinishParams { SegParams seg; RedSet red[2]; int nb_seg; int nb_red[2]; int do_sumsq; int do_clip; };
 
 __global__ void __launch_bounds__(NT) grad_finish_kernel(const FinishParams p, double* __restrict__ partials) {
     __shared__ double scratch[NT / 32];
     __shared__ float sm[8][33];
+    __shared__ __align__(16) float lg_part[NT / 32][FIN_MAX_D];
+    __shared__ int lg_seg[NT / 32], lg_job[NT / 32];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     double sq = 0.0;
     // the partial-reduction blocks come FIRST in the grid: each is one long chain of dependent-latency loads, so they should
@@ -495,9 +485,15 @@ __global__ void __launch_bounds__(NT) grad_finish_kernel(const FinishParams p, d
         int j = 0;
         if (p.seg.n_jobs > 1 && w >= p.seg.job[0].cap) { w -= p.seg.job[0].cap; j = 1; }
         const SegJob& J = p.seg.job[j];
-        if (w < J.cap && w < J.n_uniq[0]) {
-            const int beg = J.seg_start[w], end = J.seg_start[w + 1];
-            const int D4 = p.seg.D4;
+        const int D4 = p.seg.D4;
+        const bool valid = w < J.cap && w < J.n_uniq[0];
+        const int beg = valid ? J.seg_start[w] : 0, end = valid ? J.seg_start[w + 1] : 0;
+        // A popular id (Zipf-skewed users: one id can own > 100 rows of a batch) would make this warp walk a chain of that many
+        // dependent loads while the rest of the grid has long finished.  Such segments are summed by the block's 8 warps together:
+        // warp v adds rows beg+v, beg+v+8, … (ascending), the 8 partial rows are then added in warp order — a fixed split, so the
+        // result is as deterministic as the single-warp sum.
+        const bool is_long = valid && end - beg > FIN_LONG_SEG && D4 * 4 <= FIN_MAX_D;
+        if (valid && !is_long) {
             const float4* __restrict__ rows = reinterpret_cast<const float4*>(J.rows);
             for (int c = lane; c < D4; c += 32) {
                 float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -511,6 +507,35 @@ __global__ void __launch_bounds__(NT) grad_finish_kernel(const FinishParams p, d
                 }
                 sq += (double)fmaf(s.x, s.x, fmaf(s.y, s.y, fmaf(s.z, s.z, s.w * s.w)));
             }
+        }
+        if (__syncthreads_or(is_long)) {                       // (one barrier is all a block without long segments pays)
+        if (lane == 0) { lg_seg[warp] = is_long ? w : -1; lg_job[warp] = j; }
+        __syncthreads();
+        for (int i = 0; i < NT / 32; ++i) {
+            const int sg = lg_seg[i];
+            if (sg < 0) continue;                              // block-uniform
+            const SegJob& L = p.seg.job[lg_job[i]];
+            const int lb = L.seg_start[sg], le = L.seg_start[sg + 1];
+            const float4* __restrict__ rows = reinterpret_cast<const float4*>(L.rows);
+            for (int c = lane; c < D4; c += 32) {
+                float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+                for (int k = lb + warp; k < le; k += NT / 32) {
+                    const float4 v = __ldg(rows + (long long)__ldg(L.pos + k) * D4 + c);
+                    a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+                }
+                *reinterpret_cast<float4*>(&lg_part[warp][c * 4]) = a;
+            }
+            __syncthreads();
+            for (int d = threadIdx.x; d < D4 * 4; d += NT) {
+                float t = lg_part[0][d];
+#pragma unroll
+                for (int v = 1; v < NT / 32; ++v) t += lg_part[v][d];
+                if (L.uniq_grads) L.uniq_grads[(long long)sg * (D4 * 4) + d] = t;
+                if (L.dense) L.dense[L.uniq_ids[sg] * (long long)(D4 * 4) + d] += t;
+                sq += (double)(t * t);
+            }
+            __syncthreads();
+        }
         }
     } else {
         int b = (int)blockIdx.x, r = 0;
@@ -958,6 +983,8 @@ extern "C" int rb200_scatter_rows(const int64_t* ids, const float* rows, int B, 
         gp.n_jobs = 1; gp.D4 = D / 4;
         gp.job[0] = SegJob{p_out, seg_start, u_ids, n_u, rows, uniq_grads, dense_grad, B, first_pos};
         gp.skip_long = D <= LS_MAX_D;
+        gp.long_count = reinterpret_cast<int*>(k_in);            // the unsorted keys are dead: their first word counts the long segments
+        if (gp.skip_long) RB_CUDA(cudaMemsetAsync(gp.long_count, 0, sizeof(int), st));
         segment_sum2_kernel<8><<<(unsigned)(((long long)seg_warps<8>(B) * 32 + NT - 1) / NT), NT, 0, st>>>(gp);
         RB_LAUNCH_CHECK("segment_sum2_kernel");
         if (gp.skip_long) return launch_long_segments(gp, st);

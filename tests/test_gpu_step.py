@@ -295,6 +295,47 @@ def test_scatter_rows_long_segments(B, n_rows, D, kind):
     assert rel_l2(outs[0][1], ref[exp_ids]) <= 1e-6
 
 
+@pytest.mark.parametrize("graph", [False, True])
+def test_fused_step_with_popular_ids_matches_fp64_oracle(golden, graph):
+    """A batch where one user owns 40 % of the samples and one item 25 % (Zipf-skewed traffic): the long segments are summed by
+    a whole block in grad_finish_kernel.  Row gradients, total norm and determinism against the fp64 oracle."""
+    g = golden("tt_small")
+    nu, ni = int(g["meta"][0]), int(g["meta"][1])
+    rng = np.random.default_rng(11)
+    B = 700
+    u = rng.integers(1, nu + 1, B); u[rng.random(B) < 0.4] = 3
+    p = rng.integers(1, ni + 1, B); p[rng.random(B) < 0.25] = 7
+    n = rng.integers(1, ni + 1, B); n[rng.random(B) < 0.1] = 7
+    pg, ng = (rng.random((B, 18)) < 0.2).astype(np.float32), (rng.random((B, 18)) < 0.2).astype(np.float32)
+    b = (u, p, pg, n, ng)
+    assert (u == 3).sum() > 200 and ((p == 7).sum() + (n == 7).sum()) > 150
+    outs = []
+    for rep in range(2):
+        model = model_from_golden(g).train()
+        model.user_tower.mlp[2].p = model.item_tower.mlp[2].p = 0.0
+        tr = _trainer(model, g, use_cuda_graph=graph)
+        for _ in range(3 if graph else 1):
+            model.load_state_dict({k: torch.from_numpy(np.array(g["init/" + k])) for k in O.PARAM_KEYS})
+            tr.load_packed(tr.pack_host(*b))
+            tr.step()
+        v = tr.views()
+        outs.append({k: t.cpu().numpy().copy() for k, t in v.items()})
+        if rep == 0:
+            P = params_from_golden(g)
+            _, G64, _ = O.loss_and_grads(P, *b, masks=None, drop_p=0.0)
+            for tower in ("user", "item"):
+                dense = G64[f"{tower}_tower.embedding.weight"]
+                ids = v[f"{tower}_uniq_ids"].cpu().numpy()
+                bids = b[0] if tower == "user" else np.concatenate([b[1], b[3]])
+                assert np.array_equal(ids, np.unique(bids[bids != 0]))
+                assert rel_l2(v[f"{tower}_uniq_grads"].cpu().numpy(), dense[ids]) <= 1e-5
+            if not graph:
+                tot = np.sqrt(sum(float((G64[k].astype(np.float64) ** 2).sum()) for k in O.PARAM_KEYS))
+                assert abs(tr.opt_state.total_norm - tot) <= 1e-5 * tot
+    for k in outs[0]:
+        assert np.array_equal(outs[0][k], outs[1][k]), k                  # bit-reproducible
+
+
 def test_train_epoch_pipelined_equals_step_host_loop(golden):
     """train_epoch (H2D prefetch on a copy stream, async loss read-back) must produce exactly the parameters and the mean
     loss of the synchronous per-step loop (train_embeddings.py:170-199) on the same batches."""
