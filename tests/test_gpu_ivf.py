@@ -229,3 +229,22 @@ def test_full_size_ivf_properties():
     # idempotence: same call, same answer
     s2, ids2 = idx.batch_search(qh, k)
     assert np.array_equal(ids, ids2) and np.array_equal(s, s2)
+
+
+def test_retrieval_quality_harness_ivf_vs_exact():
+    """Recall@K / NDCG@K of the IVF result against the exhaustive top-k of the same queries — probing every
+    list must reproduce it (recall 1), a few lists lose some neighbours but keep the nearest ones."""
+    import recommendit_b200 as R
+    from recommendit_b200.evaluation import retrieval_report
+    x, rng = _data(20000, 64, 40, seed=9, skew=True)
+    q = V.normalize_rows(x[rng.integers(0, 20000, 200)] + 0.1 * rng.standard_normal((200, 64)).astype(np.float32))
+    qd, xd = torch.from_numpy(q).cuda(), torch.from_numpy(x).cuda()
+    _, exact = R.flat_search(qd, xd, 100)
+    reports = {}
+    for nprobe in (64, 4):
+        idx = R.FAISSIndex(64, 64, nprobe)
+        idx.build_ivf_index(x, list(range(20000)))
+        _, ids = idx.batch_search(q, 100)
+        reports[nprobe] = retrieval_report(torch.from_numpy(ids).cuda(), exact, ks=(10, 100))
+    assert reports[64]["recall@100"] > 0.999 and reports[64]["ndcg@10"] > 0.999, reports
+    assert 0.1 < reports[4]["recall@100"] < 1.0 and reports[4]["recall@10"] >= reports[4]["recall@100"] - 0.05, reports
