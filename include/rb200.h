@@ -195,6 +195,16 @@ size_t rb200_route_plan_workspace_bytes(int64_t n, int world);
 int rb200_route_plan(const int64_t* user_ids, int64_t n_user, const int64_t* item_ids, int64_t n_item, int world,
                      const int64_t* user_rows_by_rank, int64_t* perm, int64_t* inv, int64_t* local_rows,
                      int64_t* send_counts, void* workspace, size_t workspace_bytes, void* stream);
+/* Fixed-capacity form of the same plan (the CUDA-graph-captured sharded step: every all-to-all gets equal, host-known splits, so
+ * nothing is read back from the device).  Bucket w of the request list occupies slots [w·capacity, (w+1)·capacity) of a padded
+ * buffer: slot_of_sample[i] = slot of request i (sample order), send_rows[world·capacity] = the owner-local row in each slot,
+ * -1 in empty slots.  A request that does not fit its bucket gets slot world·capacity - 1 and is counted in *overflow
+ * (device int64, accumulated — the caller reports it: recommendit_b200/sharded.py check_exchange). */
+size_t rb200_route_plan_padded_workspace_bytes(int64_t n, int world);
+int rb200_route_plan_padded(const int64_t* user_ids, int64_t n_user, const int64_t* item_ids, int64_t n_item, int world,
+                            const int64_t* user_rows_by_rank, int64_t capacity, int64_t* slot_of_sample,
+                            int64_t* send_rows, int64_t* overflow, void* workspace, size_t workspace_bytes,
+                            void* stream);
 /* out[i,:] = table[rows[i],:] — the owner-side row gather of row-sharded tables; rows outside
  * [0, n_table_rows) yield zeros */
 int rb200_gather_rows(const float* table, const int64_t* rows, int64_t n, int D, int64_t n_table_rows,

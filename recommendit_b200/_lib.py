@@ -106,6 +106,8 @@ SIGNATURES = {
     "rb200_sample_batch_dev": (I, [P, I, P, P, P, P, P]),
     "rb200_route_plan_workspace_bytes": (SZ, [I64, I]),
     "rb200_route_plan": (I, [P, I64, P, I64, I, P, P, P, P, P, P, SZ, P]),
+    "rb200_route_plan_padded_workspace_bytes": (SZ, [I64, I]),
+    "rb200_route_plan_padded": (I, [P, I64, P, I64, I, P, I64, P, P, P, P, SZ, P]),
     "rb200_opt_begin_step": (I, [P, P]),
     "rb200_sumsq_accumulate": (I, [P, C.POINTER(SumsqSeg), I, P, SZ, P]),
     "rb200_sumsq_workspace_bytes": (SZ, []),

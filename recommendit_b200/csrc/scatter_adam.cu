@@ -1170,15 +1170,60 @@ __global__ void __launch_bounds__(NT) route_prep_kernel(const int64_t* __restric
                                                         const int64_t* __restrict__ item_ids, long long n, int world,
                                                         const int64_t* __restrict__ user_rows_by_rank, unsigned* __restrict__ keys,
                                                         int* __restrict__ vals, int64_t* __restrict__ local, int* __restrict__ counts) {
+    // per-block histogram in shared memory, one global atomic per (block, owner): 24 576 threads hammering `world` global
+    // counters took 19.5 us of the C4 step (integer counts: the result does not depend on the order)
+    __shared__ int hist[64];
+    const bool small = world <= 64;
+    if (small && threadIdx.x < 64) hist[threadIdx.x] = 0;
+    if (small) __syncthreads();
     const long long i = (long long)blockIdx.x * NT + threadIdx.x;
-    if (i >= n) return;
-    const bool is_item = i >= n_user;
-    const long long id = is_item ? item_ids[i - n_user] : user_ids[i];
-    const int owner = (int)(id % world);
-    keys[i] = (unsigned)owner;
-    vals[i] = (int)i;
-    local[i] = id / world + (is_item ? user_rows_by_rank[owner] : 0);
-    atomicAdd(&counts[owner], 1);                 // integer: the result does not depend on the order
+    if (i < n) {
+        const bool is_item = i >= n_user;
+        const long long id = is_item ? item_ids[i - n_user] : user_ids[i];
+        const int owner = (int)(id % world);
+        keys[i] = (unsigned)owner;
+        vals[i] = (int)i;
+        local[i] = id / world + (is_item ? user_rows_by_rank[owner] : 0);
+        if (small) atomicAdd(&hist[owner], 1); else atomicAdd(&counts[owner], 1);
+    }
+    if (small) {
+        __syncthreads();
+        if (threadIdx.x < world && hist[threadIdx.x]) atomicAdd(&counts[threadIdx.x], hist[threadIdx.x]);
+    }
+}
+// padded form: bucket w occupies slots [w·C, (w+1)·C); grid covers max(n, world·C)
+__global__ void __launch_bounds__(NT) route_finish_padded_kernel(const unsigned* __restrict__ keys_sorted, const int* __restrict__ vals_sorted,
+                                                                 const int64_t* __restrict__ local, long long n, int world,
+                                                                 const int* __restrict__ counts, long long C,
+                                                                 int64_t* __restrict__ slot_of_sample, int64_t* __restrict__ send_rows,
+                                                                 unsigned long long* __restrict__ overflow) {
+    extern __shared__ int start_s[];                           // [world + 1] exclusive prefix of the bucket sizes
+    if (threadIdx.x == 0) {
+        int acc = 0;
+        for (int b = 0; b < world; ++b) { start_s[b] = acc; acc += counts[b]; }
+        start_s[world] = acc;
+    }
+    __syncthreads();
+    const long long j = (long long)blockIdx.x * NT + threadIdx.x;
+    if (j < n) {
+        const int smp = vals_sorted[j];
+        const int owner = (int)keys_sorted[j];
+        const long long off = j - start_s[owner];
+        if (off < C) {
+            const long long slot = (long long)owner * C + off;
+            send_rows[slot] = local[smp];
+            slot_of_sample[smp] = slot;
+        } else {
+            slot_of_sample[smp] = (long long)world * C - 1;    // does not fit: counted, the caller reports it
+            atomicAdd(overflow, 1ull);
+        }
+    }
+    if (j < (long long)world * C) {
+        const int b = (int)(j / C);
+        const long long off = j - (long long)b * C;
+        const long long cnt = start_s[b + 1] - start_s[b];
+        if (off >= (cnt < C ? cnt : C)) send_rows[j] = -1;     // empty slot
+    }
 }
 __global__ void __launch_bounds__(NT) route_finish_kernel(const int* __restrict__ vals_sorted, const int64_t* __restrict__ local,
                                                           long long n, int world, const int* __restrict__ counts,
@@ -1233,5 +1278,37 @@ extern "C" int rb200_route_plan(const int64_t* user_ids, int64_t n_user, const i
     const long long m = n > world ? n : world;
     route_finish_kernel<<<(unsigned)((m + NT - 1) / NT), NT, 0, st>>>(vals_out, local, n, world, counts, perm, inv, local_rows, send_counts);
     RB_LAUNCH_CHECK("route_finish_kernel");
+    return RB200_OK;
+}
+
+extern "C" size_t rb200_route_plan_padded_workspace_bytes(int64_t n, int world) { return rb200_route_plan_workspace_bytes(n, world); }
+
+extern "C" int rb200_route_plan_padded(const int64_t* user_ids, int64_t n_user, const int64_t* item_ids, int64_t n_item, int world,
+                                       const int64_t* user_rows_by_rank, int64_t capacity, int64_t* slot_of_sample,
+                                       int64_t* send_rows, int64_t* overflow, void* workspace, size_t workspace_bytes, void* stream) {
+    const long long n = n_user + n_item;
+    RB_REQUIRE(n_user >= 0 && n_item >= 0 && n >= 1 && world >= 1 && world <= 4096 && n < (1ll << 31) && capacity >= 1 &&
+               (long long)world * capacity < (1ll << 40), "route_plan_padded: bad sizes");
+    RB_REQUIRE((n_user == 0 || user_ids) && (n_item == 0 || item_ids) && user_rows_by_rank && slot_of_sample && send_rows && overflow,
+               "route_plan_padded: NULL pointer");
+    cudaStream_t st = (cudaStream_t)stream;
+    RbArena ar(workspace, workspace_bytes);
+    unsigned* keys = ar.take<unsigned>(n); unsigned* keys_out = ar.take<unsigned>(n);
+    int* vals = ar.take<int>(n); int* vals_out = ar.take<int>(n);
+    int* counts = ar.take<int>(world);
+    int64_t* local = ar.take<int64_t>(n);
+    int bits = 1;
+    while ((1 << bits) < world) ++bits;
+    size_t tb = route_temp_bytes(n, bits);
+    char* temp = ar.take<char>(tb);
+    if (!workspace || !ar.ok()) return rb_set_error(RB200_ERR_WORKSPACE, "route_plan_padded: workspace too small (%zu given)", workspace_bytes);
+    RB_CUDA(cudaMemsetAsync(counts, 0, sizeof(int) * world, st));
+    route_prep_kernel<<<(unsigned)((n + NT - 1) / NT), NT, 0, st>>>(user_ids, n_user, item_ids, n, world, user_rows_by_rank, keys, vals, local, counts);
+    RB_LAUNCH_CHECK("route_prep_kernel");
+    RB_CUDA(cub::DeviceRadixSort::SortPairs(temp, tb, (const unsigned*)keys, keys_out, (const int*)vals, vals_out, (int)n, 0, bits, st));
+    const long long m = n > (long long)world * capacity ? n : (long long)world * capacity;
+    route_finish_padded_kernel<<<(unsigned)((m + NT - 1) / NT), NT, sizeof(int) * (world + 1), st>>>(
+        keys_out, vals_out, local, n, world, counts, capacity, slot_of_sample, send_rows, reinterpret_cast<unsigned long long*>(overflow));
+    RB_LAUNCH_CHECK("route_finish_padded_kernel");
     return RB200_OK;
 }

@@ -74,6 +74,25 @@ def route_reference(user_ids: torch.Tensor, item_ids: torch.Tensor, world: int, 
     return perm, inv, local[perm].contiguous(), torch.bincount(owner, minlength=world)
 
 
+def route_padded_reference(user_ids: torch.Tensor, item_ids: torch.Tensor, world: int, nu_by_rank: torch.Tensor, capacity: int,
+                           overflow: torch.Tensor):
+    """What ``rb200_route_plan_padded`` computes, restated with generic tensor ops (CPU test back end and the checker of the
+    kernel in its GPU test): → (slot of each sample-order request [n], rows per slot [world·capacity], -1 = empty)."""
+    W, C = world, capacity
+    perm, inv, local_rows, send = route_reference(user_ids, item_ids, W, nu_by_rank)
+    n = perm.numel()
+    ends = torch.cumsum(send, 0)
+    pos = torch.arange(n, device=perm.device, dtype=torch.int64)
+    owner = torch.bucketize(pos, ends, right=True).clamp_(max=W - 1)           # bucket of each position of the bucket order
+    off = pos - (ends - send)[owner]
+    fits = off < C
+    overflow += (~fits).sum()
+    slot = torch.where(fits, owner * C + off, torch.full_like(pos, W * C))     # what does not fit goes to a dummy slot
+    send_rows = torch.full((W * C + 1,), -1, dtype=torch.int64, device=perm.device)
+    send_rows.index_copy_(0, slot, local_rows)
+    return slot[inv].clamp_(max=W * C - 1), send_rows[:W * C].contiguous()
+
+
 def shard_rows(n_rows: int, world: int, rank: int) -> int:
     """rows of a table with global ids 0..n_rows-1 owned by ``rank`` under modulo sharding"""
     return (n_rows - rank + world - 1) // world if n_rows > rank else 0
@@ -123,6 +142,21 @@ class CudaOps:
         check(self.lib.rb200_route_plan(ptr(user_ids), user_ids.numel(), ptr(item_ids), item_ids.numel(), world, ptr(nu_by_rank),
                                         ptr(perm), ptr(inv), ptr(local), ptr(send), ptr(ws), wsb, stream_ptr()), "rb200_route_plan")
         return perm, inv, local, send
+
+    def route_padded(self, user_ids: torch.Tensor, item_ids: torch.Tensor, world: int, nu_by_rank: torch.Tensor, capacity: int,
+                     overflow: torch.Tensor):
+        """→ (slot of each sample-order request [n], rows per slot [world·capacity], -1 = empty), one C call
+        (``rb200_route_plan_padded``); requests beyond a bucket's capacity are added to ``overflow``"""
+        n = user_ids.numel() + item_ids.numel()
+        dev = user_ids.device
+        slot = torch.empty(n, dtype=torch.int64, device=dev)
+        send_rows = torch.empty(world * capacity, dtype=torch.int64, device=dev)
+        wsb = self.lib.rb200_route_plan_padded_workspace_bytes(n, world)
+        ws = workspace(wsb, dev)
+        check(self.lib.rb200_route_plan_padded(ptr(user_ids), user_ids.numel(), ptr(item_ids), item_ids.numel(), world, ptr(nu_by_rank),
+                                               capacity, ptr(slot), ptr(send_rows), ptr(overflow), ptr(ws), wsb, stream_ptr()),
+              "rb200_route_plan_padded")
+        return slot, send_rows
 
     def gather_rows(self, table: torch.Tensor, rows: torch.Tensor) -> torch.Tensor:
         out = torch.empty(rows.numel(), table.shape[1], dtype=torch.float32, device=table.device)
@@ -332,22 +366,16 @@ class ShardedBPRTrainer:
         n = user_ids.numel() + item_ids.numel()
         C = self.capacity(n)
         dev = user_ids.device
-        perm, inv, local_rows, send = self.ops.route(user_ids.contiguous(), item_ids.contiguous(), W, self._nu_by_rank)
-        ends = torch.cumsum(send, 0)
-        pos = torch.arange(n, device=dev, dtype=torch.int64)
-        owner = torch.bucketize(pos, ends, right=True).clamp_(max=W - 1)       # bucket of each position of the bucket order
-        off = pos - (ends - send)[owner]
-        fits = off < C
-        self.overflow += (~fits).sum()
-        slot = torch.where(fits, owner * C + off, torch.full_like(pos, W * C))  # what does not fit goes to a dummy slot
-        send_rows = torch.full((W * C + 1,), -1, dtype=torch.int64, device=dev)
-        send_rows.index_copy_(0, slot, local_rows)
+        if hasattr(self.ops, "route_padded"):                  # the product: one kernel sequence (rb200_route_plan_padded)
+            slot_s, send_rows = self.ops.route_padded(user_ids.contiguous(), item_ids.contiguous(), W, self._nu_by_rank, C, self.overflow)
+        else:                                                  # the same plan with generic tensor ops (CPU test back end)
+            slot_s, send_rows = route_padded_reference(user_ids, item_ids, W, self._nu_by_rank, C, self.overflow)
         if W == 1:
             recv_rows = send_rows[:W * C]
         else:
             recv_rows = torch.empty(W * C, dtype=torch.int64, device=dev)
             dist.all_to_all_single(recv_rows, send_rows[:W * C].contiguous(), group=self.group)
-        return slot[inv].clamp_(max=W * C - 1), recv_rows, C
+        return slot_s, recv_rows, C
 
     def close(self) -> None:
         """Release the captured step.  A CUDA graph that holds NCCL collectives must be gone BEFORE

@@ -159,3 +159,23 @@ def test_route_plan_kernel_matches_tensor_reference(world, n_u, n_i):
     ref = route_reference(u, i, world, nu_by_rank)
     for a, b, name in zip(got, ref, ("perm", "inv", "local_rows", "send_counts")):
         assert torch.equal(a, b.to(a.dtype)), name
+
+
+@pytest.mark.parametrize("world,n_u,n_i,cap", [(1, 100, 200, 300), (2, 8192, 16384, 13000), (8, 8192, 16384, 6160), (8, 5000, 10001, 1000),
+                                               (3, 0, 77, 40), (64, 300, 0, 9)])
+def test_route_plan_padded_kernel_matches_tensor_reference(world, n_u, n_i, cap):
+    """rb200_route_plan_padded (fixed-capacity exchange plan) against the generic-tensor restatement, incl. buckets that overflow
+    their capacity (the overflowing requests are counted; the slots of the others must still agree)."""
+    from recommendit_b200.sharded import CudaOps, route_padded_reference, shard_rows
+    g = torch.Generator().manual_seed(world * 11 + n_u)
+    u = torch.randint(0, 1_000_003, (n_u,), generator=g).cuda()
+    i = torch.randint(0, 50_021, (n_i,), generator=g).cuda()
+    nu_by_rank = torch.tensor([shard_rows(1_000_003, world, r) for r in range(world)], dtype=torch.int64, device="cuda")
+    of_k, of_r = torch.zeros(1, dtype=torch.int64, device="cuda"), torch.zeros(1, dtype=torch.int64, device="cuda")
+    slot_k, rows_k = CudaOps().route_padded(u, i, world, nu_by_rank, cap, of_k)
+    slot_r, rows_r = route_padded_reference(u, i, world, nu_by_rank, cap, of_r)
+    assert int(of_k) == int(of_r)
+    assert torch.equal(rows_k, rows_r)
+    assert torch.equal(slot_k, slot_r)
+    if world == 8 and cap == 1000:
+        assert int(of_k) > 0                                   # this case really overflows
