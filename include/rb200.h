@@ -356,7 +356,9 @@ int rb200_ivf_build(const float* x, int64_t n, int D, const int32_t* assign, int
  * Two calls, because the candidate buffer is sized by the lists the batch actually probes:
  *   rb200_ivf_search_plan  coarse scores, top-nprobe lists per query, (list → queries) inverse map;
  *                          SYNCHRONISES the stream once to return Σ and max of per-query candidate
- *                          counts to the host.
+ *                          counts to the host — unless both host pointers are NULL: then nothing is read
+ *                          back (CUDA-graph capturable) and the caller sizes rb200_ivf_search_run by the
+ *                          upper bounds total = nq·nprobe·max_list_len, max = nprobe·max_list_len.
  *   rb200_ivf_search_run   list-major scan into the candidate buffer + per-query top-k.
  * out_scores [nq,k] (-FLT_MAX padding), out_ids [nq,k] internal row numbers (-1 padding); k <= 2048. */
 size_t rb200_ivf_plan_workspace_bytes(int nq, int nlist, int nprobe);

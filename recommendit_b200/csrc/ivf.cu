@@ -851,7 +851,7 @@ extern "C" int rb200_ivf_search_plan(const float* q, int nq, int D, const float*
                                      const int64_t* offsets, void* plan_ws, size_t plan_ws_bytes,
                                      int64_t* total_candidates_host, int64_t* max_candidates_host, void* stream) {
     RB_REQUIRE(q && centroids && offsets && nq >= 1 && nlist >= 1 && nprobe >= 1 && nprobe <= nlist, "ivf_search_plan: bad arguments");
-    RB_REQUIRE(total_candidates_host && max_candidates_host, "ivf_search_plan: NULL host outputs");
+    RB_REQUIRE((total_candidates_host == nullptr) == (max_candidates_host == nullptr), "ivf_search_plan: pass both host outputs or neither");
     RB_REQUIRE(nprobe <= 2048, "ivf_search_plan: nprobe must be <= 2048");
     cudaStream_t st = (cudaStream_t)stream;
     RbArena ar(plan_ws, plan_ws_bytes);
@@ -884,6 +884,7 @@ extern "C" int rb200_ivf_search_plan(const float* q, int nq, int D, const float*
     RB_CUDA(cub::DeviceScan::ExclusiveSum(L.temp, tb, (const long long*)L.totals, L.cand_off, nq + 1, st));
     reduce_totals_kernel<<<1, NT, 0, st>>>(L.totals, nq, L.tot2);
     RB_LAUNCH_CHECK("reduce_totals_kernel");
+    if (!total_candidates_host) return RB200_OK;      // asynchronous form (CUDA-graph capturable): the caller sizes by upper bounds
     long long h[2] = {0, 0};
     RB_CUDA(cudaMemcpyAsync(h, L.tot2, sizeof(h), cudaMemcpyDeviceToHost, st));
     RB_CUDA(cudaStreamSynchronize(st));

@@ -97,3 +97,38 @@ def test_training_loop_build_index_and_serve(tmp_path):
         d, ids = index.search(user_emb, k=50)
         s_ref, i_ref = V.flat_search(V.normalize_rows(user_emb[None]), xn, 50)
         V.assert_topk_equivalent(d[None], ids[None], s_ref, i_ref + 1)
+
+
+@pytest.mark.parametrize("d,nlist,nprobe", [(64, 16, 4), (32, 8, 8)])
+def test_graph_captured_request_equals_the_two_drop_in_calls(d, nlist, nprobe):
+    """serving micro-path: UserRecommender.recommend(u) — one CUDA-graph replay — must return exactly what
+    `index.search(model.get_user_embedding(u), k)` returns (recommender.py:148-156, 203), for k above and below the candidates."""
+    import recommendit_b200 as R
+    from recommendit_b200 import RB200Error
+    dev = torch.device("cuda")
+    rng = np.random.default_rng(3)
+    torch.manual_seed(1)
+    model = R.TwoTowerModel(n_users=300, n_items=500, embed_dim=d, hidden_dim=128, dropout=0.1).to(dev)
+    genres = (rng.random((500, 18)) < 0.15).astype(np.float32)
+    item_ids = [int(i) for i in rng.permutation(np.arange(1, 501))]
+    emb = model.get_item_embeddings(item_ids, genres, dev)
+    index = R.FAISSIndex(embed_dim=d, n_lists=nlist, n_probe=nprobe)
+    index.build_ivf_index(emb, item_ids)
+    for k in (50, 500):
+        rec = R.UserRecommender(model, index, k=k)
+        for u in (1, 17, 300, 17, 0):
+            s_ref, i_ref = index.search(model.get_user_embedding(u, dev), k)
+            s, i = rec.recommend(u)
+            assert np.array_equal(i, i_ref) and np.array_equal(s, s_ref), (k, u)
+            assert i.dtype == np.int64 and s.dtype == np.float32 and np.all(np.diff(s) <= 0)
+        assert rec._graph is not None
+    # the model's weights are read in place: an update is seen by the captured request
+    with torch.no_grad():
+        model.user_tower.embedding.weight[17].add_(0.5)
+    s_ref, i_ref = index.search(model.get_user_embedding(17, dev), 500)
+    s, i = rec.recommend(17)
+    assert np.array_equal(i, i_ref) and np.array_equal(s, s_ref)
+    index.set_n_probe(max(1, nprobe // 2))
+    if nprobe // 2 >= 1 and nprobe // 2 != nprobe:
+        with pytest.raises(RB200Error, match="n_probe changed"):
+            rec.recommend(1)
