@@ -561,7 +561,10 @@ def bench_flat(args, dev, rows: int = 12_500_000, nqs=(4096, 64), reps: int = 3)
         if nq >= 1024:
             ent["roofline"] = {"kernel": "flat_scan_tc_kernel (3xTF32: 3 MMAs per logical MMA)", "bound": "tensor", "unit": "TFLOP/s",
                                "achieved": flops / (t * 1e-3) / 1e12, "issued_tflops": 3 * flops / (t * 1e-3) / 1e12,
-                               "peak": pk["bf16_tflops"], "frac": flops / (t * 1e-3) / 1e12 / pk["bf16_tflops"], "traffic": None,
+                               "peak": pk["bf16_tflops"], "frac": flops / (t * 1e-3) / 1e12 / pk["bf16_tflops"],
+                               "traffic": None, "traffic_note": "ncu --set full of the 786 432-row round of a 2 M-row search "
+                               "(profiles/r01_flat_scan_tc.md): dram read 245.8 MB + write 12.1 MB for 201 MB of rows — the shard is "
+                               "read once; tensor pipe 56.7 % active",
                                "note": "logical 2·nq·N·D flops vs the measured bf16 peak; kind::tf32 peaks at half of it and 3xTF32 "
                                        "issues 3 MMAs per logical one, so 1/6 of the bf16 peak is this kernel's ceiling"}
         else:

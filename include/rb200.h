@@ -165,11 +165,13 @@ int rb200_scatter_set_slots(const int64_t* uniq_ids, const int* n_uniq, int max_
  * (src/training/train_embeddings.py:23-79, 144-151: positives shuffled per epoch with drop_last, one negative per sample drawn
  * uniformly from the catalog and rejected while the user has rated it).  pos_users/pos_items: the n_pos positive pairs;
  * rated_offsets [max user id + 2] / rated_items: CSR of every user's rated items, ascending within a user; catalog: the
- * n_cat candidate item ids.  Batch `step` of `epoch` (0-based, (step+1)·B <= n_pos) is a pure function of `seed`. */
+ * n_cat candidate item ids.  Batch `step` of `epoch` (0-based) is a pure function of `seed`.  Several data-parallel ranks share one
+ * epoch: rank r of `world` takes slots [(step·world + r)·B, +B) of the epoch's permutation, so the ranks' batches are disjoint and
+ * a step consumes world·B positives ((step+1)·world·B <= n_pos; world = 1, rank = 0 for a single process). */
 int rb200_sample_batch(const int64_t* pos_users, const int64_t* pos_items, int64_t n_pos, const int64_t* rated_offsets,
                        const int64_t* rated_items, const int64_t* catalog, int64_t n_cat, int B, uint64_t seed,
-                       int64_t epoch, int64_t step, int64_t* out_users, int64_t* out_pos, int64_t* out_neg,
-                       void* stream);
+                       int64_t epoch, int64_t step, int64_t rank, int64_t world, int64_t* out_users, int64_t* out_pos,
+                       int64_t* out_neg, void* stream);
 /* The same producer as a description the fused step can run by itself (rb200_step_params.next_batch): at the end of step t it
  * writes the batch of step t+1 into the step's own id buffers, on a side stream under the optimizer kernels.  The global batch
  * index g is read on the device from the optimizer's step counter (opt->step = number of steps begun so far), epoch =
@@ -182,8 +184,9 @@ typedef struct rb200_sampler {
     const uint32_t* rated_bitmap; int64_t bitmap_words;
     const int64_t* catalog; int64_t n_cat;
     uint64_t seed; int64_t batches_per_epoch;
+    int64_t rank, world;               /* data-parallel slice of every step (world <= 1: single process) */
 } rb200_sampler;
-/* batch g = *counter_dev of the stream described by `s` (what the fused step runs); B·batches_per_epoch <= n_pos */
+/* batch g = *counter_dev of the stream described by `s` (what the fused step runs); world·B·batches_per_epoch <= n_pos */
 int rb200_sample_batch_dev(const rb200_sampler* s, int B, const int64_t* counter_dev, int64_t* out_users, int64_t* out_pos,
                            int64_t* out_neg, void* stream);
 /* Exchange plan of the row-sharded step (tables sharded by id mod world, both shards of a rank in

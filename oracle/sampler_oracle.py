@@ -63,12 +63,12 @@ def epoch_keys(seed, epoch):
     return k0, k1
 
 
-def sample_batch(pos_users, pos_items, rated_offsets, rated_items, catalog, B, seed, epoch, step):
+def sample_batch(pos_users, pos_items, rated_offsets, rated_items, catalog, B, seed, epoch, step, rank=0, world=1):
     """→ (user_ids, pos_ids, neg_ids) int64[B] of batch `step` of `epoch`"""
     n_pos, n_cat = len(pos_users), len(catalog)
-    assert (step + 1) * B <= n_pos, "drop_last: only full batches"
+    assert (step + 1) * B * world <= n_pos, "drop_last: only full batches"
     k0, k1 = epoch_keys(seed, epoch)
-    slot = np.arange(step * B, (step + 1) * B, dtype=np.uint64)
+    slot = np.arange((step * world + rank) * B, (step * world + rank + 1) * B, dtype=np.uint64)   # rank's slice of the step
     p = feistel_perm(slot, n_pos, k0, k1)
     users, pos = np.asarray(pos_users)[p].astype(np.int64), np.asarray(pos_items)[p].astype(np.int64)
     neg = np.zeros(B, dtype=np.int64)

@@ -69,7 +69,7 @@ class StepParams(C.Structure):
 class Sampler(C.Structure):      # host mirror of rb200_sampler
     _fields_ = [("pos_users", c_f), ("pos_items", c_f), ("n_pos", C.c_int64), ("rated_offsets", c_f), ("rated_items", c_f),
                 ("rated_bitmap", c_f), ("bitmap_words", C.c_int64), ("catalog", c_f), ("n_cat", C.c_int64),
-                ("seed", C.c_uint64), ("batches_per_epoch", C.c_int64)]
+                ("seed", C.c_uint64), ("batches_per_epoch", C.c_int64), ("rank", C.c_int64), ("world", C.c_int64)]
 
 
 class StepViews(C.Structure):
@@ -102,7 +102,7 @@ SIGNATURES = {
     "rb200_scatter_reset_slots": (I, [P, P, I, P, P]),
     "rb200_scatter_set_slots": (I, [P, P, I, P, P]),
     "rb200_gather_rows": (I, [P, P, I64, I, I64, P, P]),
-    "rb200_sample_batch": (I, [P, P, I64, P, P, P, I64, I, U64, I64, I64, P, P, P, P]),
+    "rb200_sample_batch": (I, [P, P, I64, P, P, P, I64, I, U64, I64, I64, I64, I64, P, P, P, P]),
     "rb200_sample_batch_dev": (I, [P, I, P, P, P, P, P]),
     "rb200_route_plan_workspace_bytes": (SZ, [I64, I]),
     "rb200_route_plan": (I, [P, I64, P, I64, I, P, P, P, P, P, P, SZ, P]),

@@ -48,7 +48,8 @@ __global__ void __launch_bounds__(NT_S) sample_batch_kernel(const rb200_sampler 
     const uint64_t seed = S.seed;
     const uint32_t k0 = mix32((uint32_t)seed ^ 0xA511E9B3u) + (uint32_t)epoch * 0x632BE5ABu;
     const uint32_t k1 = mix32((uint32_t)(seed >> 32) ^ 0x94D049BBu) ^ mix32((uint32_t)epoch + 0x7F4A7C15u);
-    const unsigned long long slot = (unsigned long long)step * (unsigned long long)B + (unsigned long long)s;   // < n_pos (drop_last)
+    const unsigned long long W = S.world > 1 ? (unsigned long long)S.world : 1ull, R = S.world > 1 ? (unsigned long long)S.rank : 0ull;
+    const unsigned long long slot = ((unsigned long long)step * W + R) * (unsigned long long)B + (unsigned long long)s;   // < n_pos (drop_last)
     const uint32_t p = feistel_perm((uint32_t)slot, (uint32_t)S.n_pos, h, k0, k1);
     const long long u = S.pos_users[p];
     out_users[s] = u;
@@ -97,11 +98,13 @@ int rb_sample_batch(const rb200_sampler& S, int B, long long epoch, long long st
     RB_REQUIRE(S.pos_users && S.pos_items && S.catalog && (S.rated_bitmap || (S.rated_offsets && S.rated_items)) && out_users &&
                out_pos && out_neg, "sample_batch: NULL pointer");
     RB_REQUIRE(B >= 1 && S.n_cat >= 1 && S.n_pos >= B && S.n_pos < (1ll << 31) && S.n_cat < (1ll << 31), "sample_batch: bad sizes");
+    const long long W = S.world > 1 ? S.world : 1;
+    RB_REQUIRE(S.world <= 1 || (S.rank >= 0 && S.rank < S.world), "sample_batch: rank outside [0, world)");
     if (counter_dev) {
-        RB_REQUIRE(S.batches_per_epoch >= 1 && S.batches_per_epoch * (long long)B <= S.n_pos,
-                   "sample_batch: batches_per_epoch * B exceeds the number of positives (drop_last)");
+        RB_REQUIRE(S.batches_per_epoch >= 1 && S.batches_per_epoch * (long long)B * W <= S.n_pos,
+                   "sample_batch: batches_per_epoch * world * B exceeds the number of positives (drop_last)");
     } else {
-        RB_REQUIRE(epoch >= 0 && step >= 0 && (step + 1) * (long long)B <= S.n_pos, "sample_batch: step %lld is past the epoch (drop_last)",
+        RB_REQUIRE(epoch >= 0 && step >= 0 && (step + 1) * (long long)B * W <= S.n_pos, "sample_batch: step %lld is past the epoch (drop_last)",
                    step);
     }
     sample_batch_kernel<<<(B + NT_S - 1) / NT_S, NT_S, 0, st>>>(S, B, epoch, step, reinterpret_cast<const long long*>(counter_dev),
@@ -112,11 +115,11 @@ int rb_sample_batch(const rb200_sampler& S, int B, long long epoch, long long st
 
 extern "C" int rb200_sample_batch(const int64_t* pos_users, const int64_t* pos_items, int64_t n_pos, const int64_t* rated_offsets,
                                   const int64_t* rated_items, const int64_t* catalog, int64_t n_cat, int B, uint64_t seed,
-                                  int64_t epoch, int64_t step, int64_t* out_users, int64_t* out_pos, int64_t* out_neg,
-                                  void* stream) {
+                                  int64_t epoch, int64_t step, int64_t rank, int64_t world, int64_t* out_users, int64_t* out_pos,
+                                  int64_t* out_neg, void* stream) {
     rb200_sampler S{};
     S.pos_users = pos_users; S.pos_items = pos_items; S.n_pos = n_pos; S.rated_offsets = rated_offsets; S.rated_items = rated_items;
-    S.catalog = catalog; S.n_cat = n_cat; S.seed = seed; S.batches_per_epoch = 1;
+    S.catalog = catalog; S.n_cat = n_cat; S.seed = seed; S.batches_per_epoch = 1; S.rank = rank; S.world = world;
     return rb_sample_batch(S, B, epoch, step, nullptr, out_users, out_pos, out_neg, (cudaStream_t)stream);
 }
 

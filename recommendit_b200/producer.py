@@ -30,7 +30,7 @@ _BITMAP_MAX_BYTES = 1 << 28      # rated-items bitmap (one bit per (user, item i
 
 class DeviceBatchProducer:
     def __init__(self, user_ids, item_ids, ratings, all_item_ids, n_users: int, min_rating: float = 4.0, seed: int = 0,
-                 device=None):
+                 device=None, rank: int = 0, world: int = 1):
         self.lib = _lib.load()
         if not torch.cuda.is_available():
             raise RB200Error("DeviceBatchProducer needs a CUDA device (there is no CPU fallback)")
@@ -43,6 +43,11 @@ class DeviceBatchProducer:
         pos = r >= min_rating
         self.n_pos = int(pos.sum())
         self.seed = int(seed) & 0xFFFFFFFFFFFFFFFF
+        # data-parallel ranks share one epoch: every step consumes world·B positives, rank r takes the r-th slice of B
+        # (same seed on every rank → disjoint batches; DataParallelBPRTrainer averages their gradients)
+        if not (world >= 1 and 0 <= rank < world):
+            raise ValueError("rank must lie in [0, world)")
+        self.rank, self.world = int(rank), int(world)
         # one-time index build on the host (like the reference's groupby in UserItemDataset.__init__): CSR of rated items
         pairs = np.unique(np.stack([u, i], 1), axis=0)
         counts = np.bincount(pairs[:, 0], minlength=n_users + 1)
@@ -77,11 +82,12 @@ class DeviceBatchProducer:
             s.bitmap_words = self.bitmap_words
             s.catalog, s.n_cat = ptr(self.catalog), self.catalog.numel()
             s.seed, s.batches_per_epoch = self.seed, nb
+            s.rank, s.world = self.rank, self.world
             self._samplers[batch_size] = s
         return self._samplers[batch_size]
 
     def batches_per_epoch(self, batch_size: int) -> int:
-        return self.n_pos // batch_size                                     # drop_last=True
+        return self.n_pos // (batch_size * self.world)                      # drop_last=True; a step takes world·batch_size positives
 
     def fill(self, out_users: torch.Tensor, out_pos: torch.Tensor, out_neg: torch.Tensor, epoch: int, step: int) -> None:
         """Write batch ``step`` of ``epoch`` into three int64 device tensors of the same length (asynchronous)."""
@@ -89,7 +95,8 @@ class DeviceBatchProducer:
         with torch.cuda.device(self.dev):
             check(self.lib.rb200_sample_batch(ptr(self.pos_users), ptr(self.pos_items), self.n_pos, ptr(self.rated_offsets),
                                               ptr(self.rated_items), ptr(self.catalog), self.catalog.numel(), B, self.seed, int(epoch),
-                                              int(step), ptr(out_users), ptr(out_pos), ptr(out_neg), stream_ptr()),
+                                              int(step), self.rank, self.world, ptr(out_users), ptr(out_pos), ptr(out_neg),
+                                              stream_ptr()),
                   "rb200_sample_batch")
 
     def fill_from_counter(self, batch_size: int, counter: torch.Tensor, out_users, out_pos, out_neg) -> None:

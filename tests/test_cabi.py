@@ -78,6 +78,10 @@ def test_no_cpu_fallback():
             R.FAISSIndex(32, 4, 2).build_ivf_index(np.zeros((8, 32), np.float32), list(range(8)))
         with pytest.raises(R.RB200Error):
             R.FusedBPRTrainer(model)
+        with pytest.raises(R.RB200Error):                      # the device-side batch producer has no host form either
+            R.DeviceBatchProducer([1, 2], [3, 4], [5.0, 4.0], [3, 4, 5], 2)
+        with pytest.raises(R.RB200Error):
+            R.flat_search(torch.randn(2, 64), torch.randn(100, 64), 5)
 
 
 def test_product_does_not_import_the_oracle():

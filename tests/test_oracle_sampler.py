@@ -66,3 +66,17 @@ def test_negatives_are_never_rated_and_cover_the_unrated_catalog_uniformly():
         exp = len(draws) / len(free)
         chi2 = ((h - exp) ** 2 / exp).sum()
         assert chi2 < 2.0 * len(free) + 30, (uu, chi2)                 # loose: uniform over the unrated items
+
+
+def test_data_parallel_ranks_take_disjoint_slices_of_one_epoch():
+    """world ranks with the same seed: a step consumes world·B positives, rank r the r-th slice — together the ranks visit
+    exactly what a single process with batch world·B visits in the same steps."""
+    pu, pi, off, rated, cat, _ = _toy()
+    B, world = 8, 3
+    nb = len(pu) // (B * world)
+    assert nb >= 2
+    for step in range(nb):
+        parts = [S.sample_batch(pu, pi, off, rated, cat, B, seed=4, epoch=1, step=step, rank=r, world=world) for r in range(world)]
+        whole = S.sample_batch(pu, pi, off, rated, cat, B * world, seed=4, epoch=1, step=step)
+        for k in range(3):
+            assert np.array_equal(np.concatenate([p[k] for p in parts]), whole[k])
