@@ -181,7 +181,7 @@ struct SegJob {
     const int* first_pos;                                          // optional: pos[seg_start[s]] per segment (shorter load chain)
 };
 struct SegParams { SegJob job[2]; int n_jobs; int D4; int skip_long; int* long_count; };   // skip_long: segments over LONG_SEG rows are left to long_segments_kernel
-constexpr int LONG_SEG = 48;
+constexpr int LONG_SEG = 8;           // (a chain of 48 rows still cost 55 us of the C4 step: two dependent loads per link)
 
 // s += rows[pos[k]] (column c) for k = k0 … k1-1 in ascending k.  One pos → row dependent-latency chain per row: fine for the short
 // segments this is used for; segments of a popular id (Zipf-skewed users: one id can own 9 % of a batch, 700 links, 333 us of the
@@ -467,7 +467,7 @@ __global__ void __launch_bounds__(NT) sumsq_kernel(const SumsqSegs segs, double*
 // index order and derives total_norm / clip_coef): clip_grad_norm_ needs no pass of its own.
 // ------------------------------------------------------------------------------------------------------------ //
 struct RedSet { const float* part; int nsplit; int P; int H; int Din; float* out; };
-constexpr int FIN_LONG_SEG = 32, FIN_MAX_D = 256;      // grad_finish_kernel: segments above 32 rows are summed by the whole block
+constexpr int FIN_LONG_SEG = 16, FIN_MAX_D = 256;      // grad_finish_kernel: segments above 16 rows are summed by the whole block
 struct FinishParams { SegParams seg; RedSet red[2]; int nb_seg; int nb_red[2]; int do_sumsq; int do_clip; };
 
 __global__ void __launch_bounds__(NT) grad_finish_kernel(const FinishParams p, double* __restrict__ partials) {
