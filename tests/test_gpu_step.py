@@ -336,6 +336,35 @@ def test_fused_step_with_popular_ids_matches_fp64_oracle(golden, graph):
         assert np.array_equal(outs[0][k], outs[1][k]), k                  # bit-reproducible
 
 
+def test_scatter_rows_small_batch_dense_output_with_popular_ids():
+    """Single-CTA sort path (<= 16384 rows) writing the DENSE gradient (what the drop-in autograd path asks for) with ids that
+    own far more than 8 rows: first row by segment_sum2_kernel, the rest added by long_segments_kernel; padding id skipped."""
+    from recommendit_b200 import _lib
+    lib = _lib.load()
+    rng = np.random.default_rng(2)
+    B, n_rows, D = 3000, 400, 64
+    ids = rng.integers(0, n_rows, B)
+    ids[rng.random(B) < 0.3] = 7
+    ids[rng.random(B) < 0.1] = 0                                           # padding rows
+    rows = rng.standard_normal((B, D)).astype(np.float32)
+    d_ids, d_rows = dev(ids), dev(rows)
+    uq = torch.empty(B, dtype=torch.int64, device="cuda"); ug = torch.empty(B, D, device="cuda")
+    nu = torch.zeros(1, dtype=torch.int32, device="cuda")
+    dense = torch.zeros(n_rows, D, device="cuda")
+    wsb = lib.rb200_scatter_workspace_bytes(B, n_rows)
+    ws = _lib.workspace(wsb, "cuda")
+    _lib.check(lib.rb200_scatter_rows(d_ids.data_ptr(), d_rows.data_ptr(), B, D, n_rows, 0, dense.data_ptr(), uq.data_ptr(), ug.data_ptr(),
+                                      nu.data_ptr(), None, ws.data_ptr(), wsb, _lib.stream_ptr()))
+    n = int(nu.item())
+    ref = np.zeros((n_rows, D), np.float64)
+    np.add.at(ref, ids[ids != 0], rows[ids != 0].astype(np.float64))
+    exp_ids = np.unique(ids[ids != 0])
+    assert (ids == 7).sum() > 500
+    assert np.array_equal(uq[:n].cpu().numpy(), exp_ids)
+    assert rel_l2(ug[:n].cpu().numpy(), ref[exp_ids]) <= 1e-6
+    assert rel_l2(dense.cpu().numpy(), ref) <= 1e-6 and torch.count_nonzero(dense[0]) == 0
+
+
 def test_train_epoch_pipelined_equals_step_host_loop(golden):
     """train_epoch (H2D prefetch on a copy stream, async loss read-back) must produce exactly the parameters and the mean
     loss of the synchronous per-step loop (train_embeddings.py:170-199) on the same batches."""
