@@ -1,0 +1,53 @@
+"""CPU restatement of the threshold-pruned exhaustive search (rb200_flat_search's round loop, csrc/ivf.cu + csrc/flat_scan_tc.cu)
+— TEST INFRASTRUCTURE ONLY.  It restates the ALGORITHM, not the arithmetic: scores come from the same fp32 matmul as
+``ivf_oracle.flat_search``; what is checked (tests/test_oracle_flat_rounds.py) is that pruning by the running k-th best score with a
+strict comparison, row ranges growing by a factor of four, a bounded survivor list and the redo-on-overflow rule return exactly the
+exhaustive top-k (faiss IndexFlatIP semantics: score descending, earlier row first on equal scores) for any row order.
+"""
+import numpy as np
+
+PREFIX, GROWTH, CAP_K, CAP_MIN = 8192, 4, 7, 3584       # the constants of csrc/ivf.cu
+
+
+def _topk_rows(scores, rows, k):
+    """(score desc, row asc) top-k of one query's candidates"""
+    order = np.lexsort((rows, -scores.astype(np.float64)))[:k]
+    return scores[order], rows[order]
+
+
+def flat_search_rounds(q, x, k, prefix=PREFIX, growth=GROWTH, cap=None):
+    """→ (scores [nq, k], rows [nq, k], overflowed: bool).  -FLT_MAX / -1 padded when k > rows."""
+    q, x = np.asarray(q, np.float32), np.asarray(x, np.float32)
+    nq, n = q.shape[0], x.shape[0]
+    if cap is None:
+        cap = (max(CAP_K * k, CAP_MIN) + 511) // 512 * 512
+    out_s = np.full((nq, k), -np.finfo(np.float32).max, np.float32)
+    out_i = np.full((nq, k), -1, np.int64)
+    n0 = min(n, prefix)
+    s0 = q @ x[:n0].T
+    best = []
+    for i in range(nq):
+        best.append(_topk_rows(s0[i], np.arange(n0, dtype=np.int64), k))
+    overflow = False
+    seen = n0
+    while seen < n:
+        upto = min(n, seen * growth)
+        sc = q @ x[seen:upto].T
+        for i in range(nq):
+            bs, bi = best[i]
+            thr = bs[k - 1] if len(bs) >= k else -np.inf           # k-th best so far
+            surv = np.nonzero(sc[i] > thr)[0]                       # strict: an equal score loses to the earlier row
+            if len(surv) > cap:
+                overflow = True                                     # the kernel drops what does not fit and flags the search
+                surv = surv[:cap]
+            cs = np.concatenate([bs, sc[i][surv]])
+            ci = np.concatenate([bi, surv.astype(np.int64) + seen])
+            best[i] = _topk_rows(cs, ci, k)
+        seen = upto
+    if overflow:                                                    # redone on the chunked path: exact for any row order
+        s_all = q @ x.T
+        best = [_topk_rows(s_all[i], np.arange(n, dtype=np.int64), k) for i in range(nq)]
+    for i in range(nq):
+        m = len(best[i][0])
+        out_s[i, :m], out_i[i, :m] = best[i]
+    return out_s, out_i, overflow
