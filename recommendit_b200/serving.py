@@ -85,3 +85,74 @@ class UserRecommender:
         s, ids = self._scores_pinned.numpy()[0], self._ids_pinned.numpy()[0]
         valid = ids >= 0
         return s[valid].copy(), ids[valid].copy()
+
+
+class MicroBatcher:
+    """Request micro-batching for the retrieval call of ``recommender.py:304-313`` (second half): concurrent
+    callers hand in one query vector each; a worker thread groups whatever arrived within ``max_wait_ms`` (at most ``max_batch``)
+    into ONE ``batch_search`` and hands every caller its own row, in the form ``FAISSIndex.search`` returns (padding dropped).
+
+        batcher = MicroBatcher(faiss_index.batch_search, k=500)
+        scores, item_ids = batcher.search(user_vec)          # blocks the calling thread only; thread-safe
+        batcher.close()
+
+    Pure host logic (``search_fn(np[nq, D], k) -> (np[nq, k], np[nq, k])`` is the only thing it calls), exercised on CPU with a
+    stand-in search function in tests/test_serving_host.py.  One request alone waits at most ``max_wait_ms``.
+    """
+
+    def __init__(self, search_fn, k: int = 500, max_batch: int = 64, max_wait_ms: float = 0.2):
+        import queue
+        import threading
+        self._search, self.k, self.max_batch, self.max_wait = search_fn, int(k), int(max_batch), float(max_wait_ms) * 1e-3
+        self._q: "queue.Queue" = queue.Queue()
+        self._closed = False
+        self.batches, self.requests = 0, 0
+        self._worker = threading.Thread(target=self._run, name="rb200-microbatcher", daemon=True)
+        self._worker.start()
+
+    def search(self, query_vector: np.ndarray) -> Tuple[np.ndarray, np.ndarray]:
+        import concurrent.futures
+        if self._closed:
+            raise RuntimeError("MicroBatcher is closed")
+        fut: "concurrent.futures.Future" = concurrent.futures.Future()
+        self._q.put((np.asarray(query_vector, dtype=np.float32).reshape(-1), fut))
+        return fut.result()
+
+    def _run(self) -> None:
+        import queue
+        import time
+        while True:
+            item = self._q.get()
+            if item is None:
+                return
+            group = [item]
+            deadline = time.perf_counter() + self.max_wait
+            while len(group) < self.max_batch:
+                left = deadline - time.perf_counter()
+                if left <= 0:
+                    break
+                try:
+                    nxt = self._q.get(timeout=left)
+                except queue.Empty:
+                    break
+                if nxt is None:
+                    self._q.put(None)                      # let the outer loop see the shutdown after this group
+                    break
+                group.append(nxt)
+            try:
+                scores, ids = self._search(np.stack([g[0] for g in group]), self.k)
+                self.batches += 1
+                self.requests += len(group)
+                for row, (_, fut) in enumerate(group):
+                    valid = ids[row] >= 0
+                    fut.set_result((scores[row][valid].copy(), ids[row][valid].copy()))
+            except Exception as e:                         # a failed batch fails its callers, not the worker
+                for _, fut in group:
+                    if not fut.done():
+                        fut.set_exception(e)
+
+    def close(self) -> None:
+        if not self._closed:
+            self._closed = True
+            self._q.put(None)
+            self._worker.join(timeout=5)
