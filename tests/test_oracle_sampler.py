@@ -80,3 +80,29 @@ def test_data_parallel_ranks_take_disjoint_slices_of_one_epoch():
         whole = S.sample_batch(pu, pi, off, rated, cat, B * world, seed=4, epoch=1, step=step)
         for k in range(3):
             assert np.array_equal(np.concatenate([p[k] for p in parts]), whole[k])
+
+
+def test_index_build_equals_the_reference_dataset():
+    """Positives (order and repeats) and the rated relation against the reference's own UserItemDataset
+    (tests/golden/sampler.npz, made by tests/golden/make_sampler_golden.py from train_embeddings.py:23-63); the reference's
+    negatives for three users must lie in the support the oracle's rejection test allows."""
+    from pathlib import Path
+    g = np.load(Path(__file__).parent / "golden" / "sampler.npz")
+    u, i, r, cat = g["user_id"], g["item_id"], g["rating"], g["all_item_ids"]
+    pos = r >= 4.0
+    assert np.array_equal(u[pos], g["pos_users"]) and np.array_equal(i[pos], g["pos_items"]) and int(g["n_samples"]) == int(pos.sum())
+    off, rated = S.build_rated_csr(u, i, int(u.max()))
+    pairs = np.array([(usr, it) for usr in range(len(off) - 1) for it in rated[off[usr]:off[usr + 1]]], dtype=np.int64)
+    assert np.array_equal(pairs, g["rated_pairs"])
+    for usr, draws in zip(g["neg_user"], g["neg_draws"]):
+        allowed = np.setdiff1d(cat, rated[off[usr]:off[usr + 1]])
+        assert np.isin(draws, allowed).all()
+        # and the oracle's own negatives for that user cover the same support
+        idx = np.nonzero(u[pos] == usr)[0]
+        if len(idx):
+            seen = set()
+            for epoch in range(60):
+                _, _, n = S.sample_batch(u[pos], i[pos], off, rated, cat, int(pos.sum()), seed=2, epoch=epoch, step=0)
+                perm_users = S.sample_batch(u[pos], i[pos], off, rated, cat, int(pos.sum()), seed=2, epoch=epoch, step=0)[0]
+                seen.update(n[perm_users == usr].tolist())
+            assert seen <= set(allowed.tolist())
