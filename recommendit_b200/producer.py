@@ -28,6 +28,37 @@ from ._lib import RB200Error, Sampler, check, ptr, stream_ptr
 _BITMAP_MAX_BYTES = 1 << 28      # rated-items bitmap (one bit per (user, item id)) is built when it fits this; else the CSR is searched
 
 
+def build_host_index(user_ids, item_ids, ratings, all_item_ids, n_users: int, min_rating: float = 4.0,
+                     bitmap_max_bytes: int = 1 << 28) -> dict:
+    """One-time index build on the host — what ``UserItemDataset.__init__`` does with pandas (train_embeddings.py:39-48):
+    positives = the (user, item) rows with rating >= ``min_rating`` in input order (repeated rows stay), rated = the SET of
+    (user, item) pairs of any rating as a CSR (items ascending within a user), plus, when it fits ``bitmap_max_bytes``, the same
+    relation as one bit per (user, item id).  Pure NumPy (checked on CPU against the reference's own dataset class:
+    tests/golden/sampler.npz)."""
+    u = np.asarray(user_ids, dtype=np.int64)
+    i = np.asarray(item_ids, dtype=np.int64)
+    r = np.asarray(ratings, dtype=np.float64)
+    catalog = np.asarray(all_item_ids, dtype=np.int64)
+    if u.size == 0 or u.min() < 0 or u.max() > n_users:
+        raise ValueError("user ids must lie in [0, n_users]")
+    pos = r >= min_rating
+    if catalog.size < 1 or int(pos.sum()) < 1:
+        raise ValueError("empty catalog or no positive pairs")
+    pairs = np.unique(np.stack([u, i], 1), axis=0)
+    counts = np.bincount(pairs[:, 0], minlength=n_users + 1)
+    offsets = np.zeros(n_users + 2, dtype=np.int64)
+    offsets[1:] = np.cumsum(counts)
+    out = {"pos_users": u[pos], "pos_items": i[pos], "rated_offsets": offsets, "rated_items": pairs[:, 1].copy(), "catalog": catalog,
+           "bitmap": None, "bitmap_words": 0}
+    # optional bitmap of the same relation: one 32-bit load instead of a binary search per rejection test (same results)
+    words = (max(int(pairs[:, 1].max()), int(catalog.max())) >> 5) + 1
+    if (n_users + 1) * words * 4 <= bitmap_max_bytes:
+        bm = np.zeros((n_users + 1) * words, dtype=np.uint32)
+        np.bitwise_or.at(bm, pairs[:, 0] * words + (pairs[:, 1] >> 5), (np.uint32(1) << (pairs[:, 1] & 31).astype(np.uint32)))
+        out["bitmap"], out["bitmap_words"] = bm, words
+    return out
+
+
 class DeviceBatchProducer:
     def __init__(self, user_ids, item_ids, ratings, all_item_ids, n_users: int, min_rating: float = 4.0, seed: int = 0,
                  device=None, rank: int = 0, world: int = 1):
@@ -35,38 +66,22 @@ class DeviceBatchProducer:
         if not torch.cuda.is_available():
             raise RB200Error("DeviceBatchProducer needs a CUDA device (there is no CPU fallback)")
         self.dev = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
-        u = np.asarray(user_ids, dtype=np.int64)
-        i = np.asarray(item_ids, dtype=np.int64)
-        r = np.asarray(ratings, dtype=np.float64)
-        if u.min() < 0 or u.max() > n_users:
-            raise ValueError("user ids must lie in [0, n_users]")
-        pos = r >= min_rating
-        self.n_pos = int(pos.sum())
         self.seed = int(seed) & 0xFFFFFFFFFFFFFFFF
         # data-parallel ranks share one epoch: every step consumes world·B positives, rank r takes the r-th slice of B
         # (same seed on every rank → disjoint batches; DataParallelBPRTrainer averages their gradients)
         if not (world >= 1 and 0 <= rank < world):
             raise ValueError("rank must lie in [0, world)")
         self.rank, self.world = int(rank), int(world)
-        # one-time index build on the host (like the reference's groupby in UserItemDataset.__init__): CSR of rated items
-        pairs = np.unique(np.stack([u, i], 1), axis=0)
-        counts = np.bincount(pairs[:, 0], minlength=n_users + 1)
-        offsets = np.zeros(n_users + 2, dtype=np.int64)
-        offsets[1:] = np.cumsum(counts)
+        ix = build_host_index(user_ids, item_ids, ratings, all_item_ids, n_users, min_rating, _BITMAP_MAX_BYTES)
+        self.n_pos = len(ix["pos_users"])
         to = lambda a: torch.as_tensor(np.ascontiguousarray(a, dtype=np.int64), device=self.dev)
-        self.pos_users, self.pos_items = to(u[pos]), to(i[pos])
-        self.rated_offsets, self.rated_items = to(offsets), to(pairs[:, 1])
-        self.catalog = to(np.asarray(all_item_ids, dtype=np.int64))
-        if self.catalog.numel() < 1 or self.n_pos < 1:
-            raise ValueError("empty catalog or no positive pairs")
-        # optional bitmap of the same relation: one 32-bit load instead of a binary search per rejection test (same results)
+        self.pos_users, self.pos_items = to(ix["pos_users"]), to(ix["pos_items"])
+        self.rated_offsets, self.rated_items = to(ix["rated_offsets"]), to(ix["rated_items"])
+        self.catalog = to(ix["catalog"])
         self.rated_bitmap, self.bitmap_words = None, 0
-        words = (max(int(pairs[:, 1].max()), int(np.max(all_item_ids))) >> 5) + 1
-        if (n_users + 1) * words * 4 <= _BITMAP_MAX_BYTES:
-            bm = np.zeros((n_users + 1) * words, dtype=np.uint32)
-            np.bitwise_or.at(bm, pairs[:, 0] * words + (pairs[:, 1] >> 5), (np.uint32(1) << (pairs[:, 1] & 31).astype(np.uint32)))
-            self.rated_bitmap = torch.as_tensor(bm.view(np.int32), device=self.dev)
-            self.bitmap_words = words
+        if ix["bitmap"] is not None:
+            self.rated_bitmap = torch.as_tensor(ix["bitmap"].view(np.int32), device=self.dev)
+            self.bitmap_words = ix["bitmap_words"]
         self._samplers = {}
 
     def sampler(self, batch_size: int) -> Sampler:

@@ -106,3 +106,31 @@ def test_index_build_equals_the_reference_dataset():
                 perm_users = S.sample_batch(u[pos], i[pos], off, rated, cat, int(pos.sum()), seed=2, epoch=epoch, step=0)[0]
                 seen.update(n[perm_users == usr].tolist())
             assert seen <= set(allowed.tolist())
+
+
+def test_product_host_index_build_equals_the_reference_dataset_and_the_oracle():
+    """recommendit_b200.producer.build_host_index (the host half of DeviceBatchProducer; pure NumPy) against the golden of the
+    reference's UserItemDataset and the oracle's CSR; the bitmap must encode exactly the CSR's relation."""
+    from pathlib import Path
+    from recommendit_b200.producer import build_host_index
+    g = np.load(Path(__file__).parent / "golden" / "sampler.npz")
+    u, i, r, cat = g["user_id"], g["item_id"], g["rating"], g["all_item_ids"]
+    n_users = int(u.max()) + 3                                   # ids need not fill the table
+    ix = build_host_index(u, i, r, cat, n_users)
+    assert np.array_equal(ix["pos_users"], g["pos_users"]) and np.array_equal(ix["pos_items"], g["pos_items"])
+    off, rated = S.build_rated_csr(u, i, n_users)
+    assert np.array_equal(ix["rated_offsets"], off) and np.array_equal(ix["rated_items"], rated)
+    pairs = np.array([(usr, it) for usr in range(n_users + 1) for it in rated[off[usr]:off[usr + 1]]], dtype=np.int64)
+    assert np.array_equal(pairs, g["rated_pairs"])
+    W = ix["bitmap_words"]
+    bm = ix["bitmap"].reshape(n_users + 1, W)
+    dense = np.zeros((n_users + 1, W * 32), dtype=bool)
+    dense[pairs[:, 0], pairs[:, 1]] = True
+    bits = ((bm[:, :, None] >> np.arange(32, dtype=np.uint32)) & 1).astype(bool).reshape(n_users + 1, W * 32)
+    assert np.array_equal(bits, dense)
+    assert build_host_index(u, i, r, cat, n_users, bitmap_max_bytes=0)["bitmap"] is None
+    import pytest
+    with pytest.raises(ValueError):
+        build_host_index(u, i, r, cat, 5)                        # a user id outside the table
+    with pytest.raises(ValueError):
+        build_host_index(u, i, np.zeros_like(r), cat, n_users)   # no positive pair
