@@ -71,6 +71,9 @@ class UserRecommender:
         nprobe = max(1, min(int(st.nprobe), st.nlist))
         if nprobe != self.nprobe:
             raise RB200Error("n_probe changed after the recommender was built: build a new UserRecommender")
+        if not 0 <= int(user_id) <= self.model.n_users:          # the captured request cannot raise from the device
+            raise IndexError(f"user id {user_id} is outside the embedding table [0, {self.model.n_users}] (torch would raise "
+                             "'index out of range in self')")
         self._id_pinned[0] = int(user_id)
         with torch.cuda.device(self.dev), torch.cuda.stream(self._stream):
             if self._graph is None:
