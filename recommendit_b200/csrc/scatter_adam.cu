@@ -1214,7 +1214,8 @@ __global__ void __launch_bounds__(NT) route_finish_padded_kernel(const unsigned*
             send_rows[slot] = local[smp];
             slot_of_sample[smp] = slot;
         } else {
-            slot_of_sample[smp] = (long long)world * C - 1;    // does not fit: counted, the caller reports it
+            slot_of_sample[smp] = (long long)world * C;        // does not fit: the DUMMY slot past the buffer (a zero row on the way
+                                                               // in, a dropped gradient on the way out) — counted, the caller reports it
             atomicAdd(overflow, 1ull);
         }
     }

@@ -217,7 +217,7 @@ extern "C" int rb200_bpr_step(const rb200_step_params* s, void* stream) {
 
     // ---- tensor-core modes: stage both towers' weight images once for forward and backward ----------- //
     if (tc) {
-        RB_REQUIRE(rb_tower_tc_supported(D, H, E), "bpr_step: tower_mode %d needs D=64, H=128, extra_dim<=24", s->tower_mode);
+        RB_REQUIRE(rb_tower_tc_supported(D, H, E), "bpr_step: tower_mode %d needs D in {64,128}, H=128, extra_dim<=24", s->tower_mode);
         const float* pw1[2] = {s->user_mlp, s->item_mlp};
         const float* pw2[2] = {s->user_mlp + H * D + H, s->item_mlp + H * Din_i + H};
         const int pe[2] = {0, E};

@@ -527,6 +527,7 @@ int partition_ctas(JobT* jobs, int n_jobs, int D, int H) {
 int rb_tower_fwd_tc(FwdParams& p, int D, int H, int mode, void* workspace, size_t workspace_bytes, cudaStream_t st);
 int rb_tower_bwd_tc(BwdParams& p, int D, int H, int mode, float* grads_out, int accumulate, unsigned char* img_ws, cudaStream_t st);
 bool rb_tower_tc_supported(int D, int H, int E);
+bool rb_tower_use_ts(int D);
 size_t rb_tower_img_bytes(int D, int H, int E);
 
 extern "C" size_t rb200_tower_fwd_workspace_bytes(int n_jobs, int D, int H, int extra_dim, int mode) {
@@ -560,7 +561,7 @@ extern "C" int rb200_tower_fwd(const rb200_tower_job* jobs, int n_jobs, int D, i
     if (p.n_jobs == 0) return RB200_OK;
     if (mode != 0) {
         for (int j = 0; j < p.n_jobs; ++j)
-            RB_REQUIRE(rb_tower_tc_supported(D, H, p.job[j].E), "tower_fwd: tcgen05 mode supports D=64, H=128, extra_dim<=24 (got D=%d H=%d E=%d)", D, H, p.job[j].E);
+            RB_REQUIRE(rb_tower_tc_supported(D, H, p.job[j].E), "tower_fwd: tcgen05 mode supports D in {64,128}, H=128, extra_dim<=24 (got D=%d H=%d E=%d)", D, H, p.job[j].E);
         return rb_tower_fwd_tc(p, D, H, mode, workspace, workspace_bytes, (cudaStream_t)stream);
     }
     RB_REQUIRE((int)smem <= rb_max_smem_optin(), "tower_fwd: D=%d H=%d needs %zu B of shared memory (> %d)", D, H, smem,
@@ -624,12 +625,14 @@ int rb_tower_bwd(const rb200_tower_bwd_job* jobs, int n_jobs, int D, int H, floa
         return RB200_OK;
     }
     if (mode != 0) {
-        RB_REQUIRE(rb_tower_tc_supported(D, H, E), "tower_bwd: tcgen05 mode supports D=64, H=128, extra_dim<=24");
+        RB_REQUIRE(rb_tower_tc_supported(D, H, E), "tower_bwd: tcgen05 mode supports D in {64,128}, H=128, extra_dim<=24");
         RbArena tar(workspace, workspace_bytes);
         // split-K over the batch: short accumulation chains in TMEM (the tensor core's fp32 accumulation error grows with
         // the chain length; ≤ ~128 rows per CTA keeps the weight gradients inside the 1e-5 bound), all SMs busy
         int ns = (int)((total_rows + 63) / 64);
-        if (ns > rb_sm_count()) ns = rb_sm_count();
+        // (the TMEM-operand weight-gradient kernel runs two CTAs per split — one per product — so half the splits fill the SMs)
+        const int ns_max = rb_tower_use_ts(D) ? (rb_sm_count() + 1) / 2 : rb_sm_count();
+        if (ns > ns_max) ns = ns_max;
         if (ns < 1) ns = 1;
         p.nsplit = ns;
         p.P = P;

@@ -11,33 +11,17 @@
 //   bwd wts   split-K over the batch: per CTA, chunks of 32 samples; operands are transposed while being staged
 //             (K = sample index): dW2ᵀ[h][d] = Σ_r hid[r][h]·dpre[r][d], dW1[h][k] = Σ_r dact[r][h]·X[r][k]; accumulators
 //             stay in TMEM across chunks; per-CTA partials reduced in fixed order (deterministic).
-#include "common.cuh"
-#include "tower_common.cuh"
-#include "umma.cuh"
+#include <stdlib.h>
+
+#include "tower_tc_common.cuh"
+
+using namespace towertc;
 
 namespace {
 
 constexpr int NT = 256;        // weight-gradient kernel: 8 warps; warps w and w+4 share TMEM lane quadrant w%4 and split the columns
 constexpr int NTD = 512;       // forward / backward-data kernels: 16 warps, four column quarters per TMEM lane quadrant
-constexpr int ROWS = 128;      // samples per tile = TMEM lanes
 constexpr int TMEM_COLS = 256;
-
-// ---- weight images --------------------------------------------------------------------------------------------- //
-// [W1 hi|lo : H × Kp] [W2 hi|lo : D × H] [W2ᵀ hi|lo : H × D] [W1[:, :D]ᵀ hi|lo : D × H], each in the K-major UMMA layout
-struct ImgLayout {
-    size_t w1, w2, w2t, w1t, total;
-    int Kp;
-};
-__host__ __device__ inline ImgLayout img_layout(int D, int H, int E) {
-    ImgLayout L;
-    L.Kp = (D + E + 7) & ~7;
-    L.w1 = 0;
-    L.w2 = L.w1 + (size_t)2 * H * L.Kp * 4;
-    L.w2t = L.w2 + (size_t)2 * D * H * 4;
-    L.w1t = L.w2t + (size_t)2 * H * D * 4;
-    L.total = L.w1t + (size_t)2 * D * H * 4;
-    return L;
-}
 
 struct PrepSet { const float* W1; const float* W2; unsigned char* img; int E; };
 struct PrepParams { PrepSet set[2]; int n_sets, D, H; rb200_opt_state* opt; };   // opt != NULL: also begin the optimizer step
@@ -66,9 +50,10 @@ __global__ void __launch_bounds__(256) tower_prep_kernel(const PrepParams p) {
             v.z = k + 2 < Din ? __ldg(S.W1 + (long long)h * Din + k + 2) : 0.f;
             v.w = k + 3 < Din ? __ldg(S.W1 + (long long)h * Din + k + 3) : 0.f;
             put4_both(S.img + L.w1, (size_t)H * Kp * 4, H, h, k, v);
-        } else if (idx < n1 + n2) {           // W2 [D × H]
+        } else if (idx < n1 + n2) {           // W2 [D × H], in sub-images of 64 rows
             const int i = idx - n1, c4 = i / D, d = i - c4 * D;
-            put4_both(S.img + L.w2, (size_t)D * H * 4, D, d, c4 * 4, __ldg(reinterpret_cast<const float4*>(S.W2 + (long long)d * H) + c4));
+            put4_both(S.img + L.w2 + (size_t)(d / SUBR) * 2 * SUBR * H * 4, (size_t)SUBR * H * 4, SUBR, d % SUBR, c4 * 4,
+                      __ldg(reinterpret_cast<const float4*>(S.W2 + (long long)d * H) + c4));
         } else if (idx < n1 + n2 + n3) {      // W2ᵀ [H × D]: (h, d) = W2[d][h]
             const int i = idx - n1 - n2, c4 = i / H, h = i - c4 * H;
             const float* wp = S.W2 + (long long)(c4 * 4) * H + h;
@@ -76,20 +61,10 @@ __global__ void __launch_bounds__(256) tower_prep_kernel(const PrepParams p) {
         } else {                              // W1[:, :D]ᵀ [D × H]: (d, h) = W1[h][d]
             const int i = idx - n1 - n2 - n3, c4 = i / D, d = i - c4 * D;
             const float* wp = S.W1 + (long long)(c4 * 4) * Din + d;
-            put4_both(S.img + L.w1t, (size_t)D * H * 4, D, d, c4 * 4,
+            put4_both(S.img + L.w1t + (size_t)(d / SUBR) * 2 * SUBR * H * 4, (size_t)SUBR * H * 4, SUBR, d % SUBR, c4 * 4,
                       make_float4(__ldg(wp), __ldg(wp + Din), __ldg(wp + 2 * Din), __ldg(wp + 3 * Din)));
         }
     }
-}
-
-// store 4 consecutive-k values of row r (hi and optionally lo) into an [R × K] K-major operand
-template <int MODE>
-__device__ __forceinline__ void put4(unsigned char* hi_base, unsigned char* lo_base, int R, int r, int k, const float4& v) {
-    const uint32_t off = umma::kmajor_offset(R, r, k);
-    float4 hi, lo;
-    umma::split4(v, hi, lo);
-    *reinterpret_cast<float4*>(hi_base + off) = hi;
-    if (MODE == 2) *reinterpret_cast<float4*>(lo_base + off) = lo;
 }
 
 // issue the MMAs of one GEMM: D[tmem] = A[M=128 × K] · B[N × K]ᵀ, operands fully resident (K-major, rows RA / RB)
@@ -115,17 +90,6 @@ __device__ __forceinline__ void issue_gemm(uint32_t tmem_d, unsigned char* a_hi,
     }
 }
 
-struct Bar {           // mbarrier with bounded waits and a sticky failure flag
-    uint64_t* bar;
-    uint32_t phase;
-    int* dead;
-    int* err_flag;
-    __device__ void wait() {
-        if (!*dead && !umma::mbar_wait(bar, phase)) { *dead = 1; if (err_flag) atomicOr(err_flag, 2); }
-        phase ^= 1;
-    }
-};
-
 #define RB_TC_PROLOGUE(err_ptr)                                                                                   \
     __shared__ __align__(8) uint64_t mma_bar_s, w_bar_s;                                                          \
     __shared__ uint32_t tmem_slot;                                                                                \
@@ -145,14 +109,6 @@ struct Bar {           // mbarrier with bounded waits and a sticky failure flag
     umma::fence_before_sync();                                                         \
     __syncthreads();                                                                   \
     if (warp == 0) umma::tmem_free(tmem, TMEM_COLS);
-
-__device__ __forceinline__ int find_job(const int* begin, int n_jobs) {
-    int j = 0;
-#pragma unroll
-    for (int t = 1; t < MAX_JOBS; ++t)
-        if (t < n_jobs && (int)blockIdx.x >= begin[t]) j = t;
-    return j;
-}
 
 // ------------------------------------------------------------------------------------------------------------ //
 // forward
@@ -488,21 +444,6 @@ __global__ void __launch_bounds__(NTD, 1) tower_bwd_data_tc_kernel(const BwdPara
 // ------------------------------------------------------------------------------------------------------------ //
 constexpr int KC = 32;    // samples per staged chunk
 
-__device__ __forceinline__ float sel4(const float4& v, int e) { return e == 0 ? v.x : e == 1 ? v.y : e == 2 ? v.z : v.w; }
-
-// Transposing store of a 4(sample) × 4(row) block into an [R × KC] K-major operand: thread (sq = warp, mq = lane) holds
-// v[i] = 4 consecutive operand rows (4·mq … +3) of sample 4·sq+i and writes, for each of its rows, the 16-byte unit of
-// the 4 samples.  The row handled in store t is rotated with the lane (e = (t + lane/2) & 3) so that the 8 lanes of a
-// shared-memory phase hit 8 different 16-byte slots: conflict-free.
-template <int MODE>
-__device__ __forceinline__ void put_block_t(unsigned char* hi, unsigned char* lo, int R, int mq, int sq, int lane, const float4 (&v)[4]) {
-#pragma unroll
-    for (int t = 0; t < 4; ++t) {
-        const int e = (t + (lane >> 1)) & 3;
-        put4<MODE>(hi, lo, R, mq * 4 + e, sq * 4, make_float4(sel4(v[0], e), sel4(v[1], e), sel4(v[2], e), sel4(v[3], e)));
-    }
-}
-
 template <int D, int H, int NK, int MODE>      // NK = padded Din (multiple of 32) = N of the dW1 product
 __global__ void __launch_bounds__(NT, 1) tower_bwd_weights_tc_kernel(const BwdParams p, int* err_flag) {
     static_assert(H == 128 && D == 64 && KC == 32 && NT == 256, "thread mapping assumes 8 warps = 8 sample quads, 32 lanes = 32 row quads");
@@ -710,27 +651,21 @@ __global__ void __launch_bounds__(256) reduce_partials_tc_kernel(const float* __
     }
 }
 
-template <typename JobT>
-int assign_tiles(JobT* jobs, int n_jobs) {
-    int begin = 0;
-    for (int j = 0; j < n_jobs; ++j) {
-        const int tiles = (jobs[j].B + ROWS - 1) / ROWS;
-        jobs[j].cta_begin = begin;
-        jobs[j].cta_count = tiles;
-        begin += tiles;
-    }
-    return begin;
-}
-
-template <typename K>
-int set_smem(K kernel, size_t bytes) {
-    RB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
-    return RB200_OK;
-}
-
 }  // namespace
 
-bool rb_tower_tc_supported(int D, int H, int E) { return D == 64 && H == 128 && E >= 0 && E <= 24; }
+int rb_tower_fwd_ts(FwdParams& p, int D, int mode, cudaStream_t st);
+int rb_tower_bwd_ts(BwdParams& p, int D, int mode, cudaStream_t st);
+
+bool rb_tower_tc_supported(int D, int H, int E) { return (D == 64 || D == 128) && H == 128 && E >= 0 && E <= 24; }
+
+// which tensor-core implementation serves width D: the TMEM-operand kernels (tower_ts.cu) — always at D = 128 (the kernels of this
+// file do not fit it), and at D = 64 unless RB200_TOWER_TS=0 selects the shared-memory-operand kernels of this file (measured on
+// the C2 step: 0.128 ms with the TMEM-operand kernels, 0.137 ms with these)
+bool rb_tower_use_ts(int D) {
+    static int ts64 = -1;
+    if (ts64 < 0) { const char* e = getenv("RB200_TOWER_TS"); ts64 = (e && atoi(e) == 0) ? 0 : 1; }
+    return D == 128 || ts64 == 1;
+}
 
 size_t rb_tower_img_bytes(int D, int H, int E) { return rb_align_up(img_layout(D, H, E).total, 256); }
 
@@ -745,7 +680,8 @@ int rb_tower_prep_tc(int n_sets, const float* const W1[], const float* const W2[
         RB_REQUIRE((reinterpret_cast<uintptr_t>(img[i]) & 15) == 0, "tower_prep: image must be 16-byte aligned");
         p.set[i].W1 = W1[i]; p.set[i].W2 = W2[i]; p.set[i].img = img[i]; p.set[i].E = E[i];
     }
-    tower_prep_kernel<<<dim3(24, n_sets), 256, 0, st>>>(p);
+    const int items = H * (((D + 24 + 7) & ~7) / 4) + 3 * D * (H / 4);      // float4 units of the largest image
+    tower_prep_kernel<<<dim3((items + 255) / 256, n_sets), 256, 0, st>>>(p);
     RB_LAUNCH_CHECK("tower_prep_kernel");
     return RB200_OK;
 }
@@ -753,7 +689,7 @@ int rb_tower_prep_tc(int n_sets, const float* const W1[], const float* const W2[
 extern "C" size_t rb200_tower_img_bytes(int D, int H, int extra_dim) { return rb_tower_img_bytes(D, H, extra_dim); }
 
 extern "C" int rb200_tower_prep(const float* W1, const float* W2, int D, int H, int extra_dim, void* img, void* stream) {
-    RB_REQUIRE(rb_tower_tc_supported(D, H, extra_dim), "tower_prep: tensor-core modes cover D=64, H=128, extra_dim<=24");
+    RB_REQUIRE(rb_tower_tc_supported(D, H, extra_dim), "tower_prep: tensor-core modes cover D in {64,128}, H=128, extra_dim<=24");
     const float* w1[1] = {W1}; const float* w2[1] = {W2}; const int e[1] = {extra_dim};
     unsigned char* im[1] = {(unsigned char*)img};
     return rb_tower_prep_tc(1, w1, w2, e, D, H, im, nullptr, (cudaStream_t)stream);
@@ -781,6 +717,7 @@ int rb_tower_fwd_tc(FwdParams& p, int D, int H, int mode, void* workspace, size_
         int rc = rb_tower_prep_tc(n_sets, w1, w2, es, D, H, im, nullptr, st);
         if (rc) return rc;
     }
+    if (rb_tower_use_ts(D)) return rb_tower_fwd_ts(p, D, mode, st);
     const int grid = assign_tiles(p.job, p.n_jobs);
     int kp = 0;
     for (int j = 0; j < p.n_jobs; ++j) { const int k = (64 + p.job[j].E + 7) & ~7; if (k > kp) kp = k; }
@@ -812,6 +749,13 @@ int rb_tower_bwd_tc(BwdParams& p, int D, int H, int mode, float* grads_out, int 
         int rc = rb_tower_prep_tc(1, w1, w2, e, D, H, im, nullptr, st);
         if (rc) return rc;
         for (int j = 0; j < p.n_jobs; ++j) p.job[j].img = img_ws;
+    }
+    if (rb_tower_use_ts(D)) {
+        int rc = rb_tower_bwd_ts(p, D, mode, st);
+        if (rc || !grads_out) return rc;
+        reduce_partials_tc_kernel<<<(p.P + 31) / 32, 256, 0, st>>>(p.part, p.nsplit, p.P, H, D + E, grads_out, accumulate);
+        RB_LAUNCH_CHECK("reduce_partials_tc_kernel");
+        return RB200_OK;
     }
     const int grid = assign_tiles(p.job, p.n_jobs);
     const size_t smem_d = (size_t)2 * 128 * 128 * 4 + (size_t)2 * 64 * 128 * 4;

@@ -87,10 +87,10 @@ def route_padded_reference(user_ids: torch.Tensor, item_ids: torch.Tensor, world
     off = pos - (ends - send)[owner]
     fits = off < C
     overflow += (~fits).sum()
-    slot = torch.where(fits, owner * C + off, torch.full_like(pos, W * C))     # what does not fit goes to a dummy slot
+    slot = torch.where(fits, owner * C + off, torch.full_like(pos, W * C))     # what does not fit goes to the dummy slot W·C
     send_rows = torch.full((W * C + 1,), -1, dtype=torch.int64, device=perm.device)
     send_rows.index_copy_(0, slot, local_rows)
-    return slot[inv].clamp_(max=W * C - 1), send_rows[:W * C].contiguous()
+    return slot[inv], send_rows[:W * C].contiguous()
 
 
 def shard_rows(n_rows: int, world: int, rank: int) -> int:
@@ -165,7 +165,9 @@ class CudaOps:
                                              stream_ptr()), "rb200_gather_rows")
         return out
 
-    def towers_fwd(self, jobs: List[dict], D: int, H: int, drop_p: float, seed: int, offset: int) -> None:
+    def towers_fwd(self, jobs: List[dict], D: int, H: int, drop_p: float, seed: int, offset: int, offset_dev=None) -> None:
+        """``offset_dev``: device int64 added (× 3) to the dropout offset inside the kernel — the optimizer's step counter, so
+        that replays of a captured step draw fresh masks"""
         arr = (TowerJob * len(jobs))()
         for i, j in enumerate(jobs):
             arr[i] = TowerJob(ptr(j["table"]), ptr(j["ids"]), ptr(j.get("extra")), ptr(j["W1"]), ptr(j["b1"]), ptr(j["W2"]),
@@ -175,7 +177,7 @@ class CudaOps:
         E = max(0 if j.get("extra") is None else j["extra"].shape[1] for j in jobs)
         wsb = self.lib.rb200_tower_fwd_workspace_bytes(len(jobs), D, H, E, mode)
         ws = workspace(wsb, jobs[0]["out"].device) if wsb else None
-        check(self.lib.rb200_tower_fwd(arr, len(jobs), D, H, drop_p, seed, offset, None, mode, None, ptr(ws), wsb, stream_ptr()),
+        check(self.lib.rb200_tower_fwd(arr, len(jobs), D, H, drop_p, seed, offset, offset_dev, mode, None, ptr(ws), wsb, stream_ptr()),
               "rb200_tower_fwd")
 
     def bpr_pair(self, u, p, n, grad_scale: float):
@@ -263,13 +265,21 @@ class ShardedBPRTrainer:
     def __init__(self, n_users: int, n_items: int, embed_dim: int = 128, hidden_dim: int = 128, n_genres: int = 18,
                  lr: float = 1e-3, betas=(0.9, 0.999), eps: float = 1e-8, weight_decay: float = 1e-5, max_norm: float = 1.0,
                  adam_mode: str = "rows", device=None, group=None, ops=None, seed: int = 0, init: Optional[Dict] = None,
-                 exchange: str = "exact", capacity_factor: float = 2.0, use_cuda_graph: bool = False):
+                 exchange: str = "exact", capacity_factor: float = 2.0, use_cuda_graph: bool = False, dropout: float = 0.0,
+                 check_every: int = 256):
+        """``dropout``: the towers' dropout probability (the reference's model default is 0.1; 0.0 here keeps the parity runs
+        mask-free).  Masks are drawn in-kernel (Philox) from (seed + 7919·rank, optimizer step).  ``check_every``: padded
+        exchange — every that many steps the overflow counter is read back and an overflow raises (0 = only on
+        ``check_exchange()``)."""
         if exchange not in ("exact", "padded"):
             raise ValueError("exchange must be 'exact' (variable-size all-to-alls, one host sync per step) or 'padded' "
                              "(fixed-capacity all-to-alls: no host sync, CUDA-graph capturable)")
         if use_cuda_graph and exchange != "padded":
             raise ValueError("use_cuda_graph needs exchange='padded' (the exact exchange reads its split sizes on the host)")
+        if not 0.0 <= dropout < 1.0:
+            raise ValueError("dropout must be in [0, 1)")
         self.exchange, self.capacity_factor, self.use_graph = exchange, float(capacity_factor), use_cuda_graph
+        self.dropout, self.check_every, self.seed = float(dropout), int(check_every), int(seed)
         self._graph, self._static_in, self._static_loss, self._eager_steps = None, None, None, 0
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
@@ -399,6 +409,8 @@ class ShardedBPRTrainer:
         {Σg², loss} pair (all-reduce).  ``exchange='exact'``: variable-size all-to-alls, one host synchronisation (their split
         sizes).  ``exchange='padded'``: fixed-capacity all-to-alls, no host synchronisation; with ``use_cuda_graph`` the whole
         step, collectives included, is one graph replay after two eager steps."""
+        if self.exchange == "padded" and self.check_every > 0 and self.steps > 0 and self.steps % self.check_every == 0:
+            self.check_exchange()
         if not self.use_graph:
             return self._step(user_ids, pos_ids, pos_genres, neg_ids, neg_genres)
         batch = (user_ids, pos_ids, pos_genres, neg_ids, neg_genres)
@@ -421,6 +433,28 @@ class ShardedBPRTrainer:
         self.steps += 1
         return self._static_loss
 
+    _marks = None
+
+    def _mark(self, name: str) -> None:
+        if self._marks is not None:
+            e = torch.cuda.Event(enable_timing=True)
+            e.record()
+            self._marks.append((name, e))
+
+    def profile_stages(self, user_ids, pos_ids, pos_genres, neg_ids, neg_genres, reps: int = 5) -> Dict[str, float]:
+        """Device time of each phase of the step (ms, mean of ``reps`` eager steps with CUDA events at the phase boundaries).
+        The steps are real optimiser steps.  Eager launches: read the SHARES, the graph replay is faster than the sum."""
+        acc: Dict[str, float] = {}
+        for _ in range(reps):
+            self._marks = []
+            self._mark("begin")
+            self._step(user_ids, pos_ids, pos_genres, neg_ids, neg_genres)
+            marks, self._marks = self._marks, None
+            torch.cuda.synchronize(self.dev)
+            for (_, a), (name, b) in zip(marks[:-1], marks[1:]):
+                acc[name] = acc.get(name, 0.0) + a.elapsed_time(b) / reps
+        return acc
+
     def _step(self, user_ids, pos_ids, pos_genres, neg_ids, neg_genres) -> torch.Tensor:
         ops, D, H, E, W = self.ops, self.D, self.H, self.E, self.world
         B = user_ids.numel()
@@ -431,17 +465,21 @@ class ShardedBPRTrainer:
         if padded:
             slot, recv_rows, C = self._route_padded(user_ids, torch.cat([pos_ids, neg_ids]))
             served = ops.gather_rows(self.table, recv_rows.clamp(min=0))
+            # one row more than the exchange carries: slot W·C is the dummy slot of requests that overflowed their bucket — they
+            # read a zero row here and their gradient is dropped below, so an overflow costs samples, never another row's data
+            rows = torch.empty(W * C + 1, D, **f32)
+            rows[W * C:].zero_()
             if W == 1:
-                rows = served
+                rows[:W * C].copy_(served)
             else:
-                rows = torch.empty_like(served)
-                dist.all_to_all_single(rows, served, group=self.group)
+                dist.all_to_all_single(rows[:W * C], served, group=self.group)
             rt = Route(perm=None, inv=slot, local_rows=None, send_counts=None, recv_rows=recv_rows)
         else:
             rt = self._route(user_ids, torch.cat([pos_ids, neg_ids]))
             served = ops.gather_rows(self.table, rt.recv_rows)
             rows = served if W == 1 else all_to_all_var(served, rt.recv_counts, rt.send_counts, self.group)
         ops.begin_step(self.opt)
+        self._mark("route_gather_exchange")
 
         uW1, ub1, uW2, ub2 = self._mlp_views(self.user_mlp, D)
         iW1, ib1, iW2, ib2 = self._mlp_views(self.item_mlp, D + E)
@@ -454,21 +492,29 @@ class ShardedBPRTrainer:
             dict(table=rows, ids=inv_p, extra=pos_genres, W1=iW1, b1=ib1, W2=iW2, b2=ib2, out=out[B:2 * B], hid=hid[B:2 * B], denom=den[B:2 * B]),
             dict(table=rows, ids=inv_n, extra=neg_genres, W1=iW1, b1=ib1, W2=iW2, b2=ib2, out=out[2 * B:], hid=hid[2 * B:], denom=den[2 * B:]),
         ]
-        ops.towers_fwd(jobs, D, H, 0.0, 0, self.steps)
+        drop_p = self.dropout
+        if drop_p > 0.0:
+            # masks keyed by (seed of this rank; optimizer step read on the device, so a graph replay draws new ones)
+            ops.towers_fwd(jobs, D, H, drop_p, self.seed + 7919 * self.rank, 0, self.opt.data_ptr() + OptState.step.offset)
+        else:
+            ops.towers_fwd(jobs, D, H, 0.0, 0, 0)
+        self._mark("towers_fwd")
         loss, du, dp, dn = ops.bpr_pair(out[:B], out[B:2 * B], out[2 * B:], 1.0 / W)
+        self._mark("loss")
 
         dpre, dact, drows = torch.empty(3 * B, D, **f32), torch.empty(3 * B, H, **f32), torch.empty(3 * B, D, **f32)
         Pu, Pi = self.user_mlp.numel(), self.item_mlp.numel()
         g_mlp = torch.empty(Pu + Pi, **f32)
         for j, dY, sl in ((jobs[0], du, slice(0, B)), (jobs[1], dp, slice(B, 2 * B)), (jobs[2], dn, slice(2 * B, 3 * B))):
             j.update(dY=dY, dpre=dpre[sl], dact=dact[sl], dRows=drows[sl])
-        ops.towers_bwd(jobs[:1], D, H, 0.0, g_mlp[:Pu])
-        ops.towers_bwd(jobs[1:], D, H, 0.0, g_mlp[Pu:])
+        ops.towers_bwd(jobs[:1], D, H, drop_p, g_mlp[:Pu])
+        ops.towers_bwd(jobs[1:], D, H, drop_p, g_mlp[Pu:])
+        self._mark("towers_bwd")
 
         # steps 4-5: row gradients (sample order → bucket order) back to the owning shards, deterministic segment sums there
         if padded:
-            g_pad = torch.empty(W * C + 1, D, **f32)               # empty slots are skipped at the owner (their row is -1)
-            g_pad.index_copy_(0, rt.inv, drows)
+            g_pad = torch.empty(W * C + 1, D, **f32)               # empty slots are skipped at the owner (their row is -1);
+            g_pad.index_copy_(0, rt.inv, drows)                    # row W·C collects the overflowed requests and is not sent
             if W == 1:
                 g_rows = g_pad[:W * C]
             else:
@@ -482,7 +528,9 @@ class ShardedBPRTrainer:
         if self.rank == 0:       # the global padding ids 0 live on rank 0 (local rows 0 and n_user_local): no gradient
             nu0 = self.user_table.shape[0]
             rows_sc = torch.where((rows_sc == 0) | (rows_sc == nu0), torch.full_like(rows_sc, -1), rows_sc)
+        self._mark("grad_exchange")
         uq, ug, n_uq = ops.scatter_rows(rows_sc, g_rows, max(self.table.shape[0], 1), -1)
+        self._mark("scatter")
         if W > 1:
             dist.all_reduce(g_mlp, group=self.group)                       # Σ over ranks of (1/W)-scaled local gradients
         # step 6: global gradient norm and mean loss, on the device.  Table shards are disjoint → their Σg² add up; the MLP
@@ -498,6 +546,7 @@ class ShardedBPRTrainer:
         opt64[_OPT_SUMSQ_F64:_OPT_SUMSQ_F64 + 1].copy_(red[0:1])
         opt32[_OPT_LOSS_F32:_OPT_LOSS_F32 + 1].copy_(red[1:2].to(torch.float32))
         ops.grad_norm_clip(self.opt)
+        self._mark("allreduce_norm_clip")
 
         ops.adam_dense(self.user_mlp, g_mlp[:Pu], self.state["user_mlp"], self.state_v["user_mlp"], self.opt)
         ops.adam_dense(self.item_mlp, g_mlp[Pu:], self.state["item_mlp"], self.state_v["item_mlp"], self.opt)
@@ -505,6 +554,7 @@ class ShardedBPRTrainer:
             ops.adam_table_dense(self.table, self.state["table"], self.state_v["table"], uq, ug, n_uq, self.slot, self.opt)
         else:
             ops.adam_rows(self.table, self.state["table"], self.state_v["table"], uq, ug, n_uq, self.opt)
+        self._mark("adam")
         self.steps += 1
         return opt32[_OPT_LOSS_F32:_OPT_LOSS_F32 + 1].clone()
 

@@ -37,14 +37,14 @@ logger = logging.getLogger(__name__)
 N_GENRES = 18  # MovieLens-1M genre multi-hot width (reference two_tower.py:16)
 
 #: precision mode of the tower MLP kernels: 0 = fp32 FFMA, 1 = tcgen05 TF32, 2 = tcgen05 3xTF32 (fp32-grade).
-#: "auto" (default) = 2 where the tensor-core kernels cover the widths (D=64, H=128), else 0.
+#: "auto" (default) = 2 where the tensor-core kernels cover the widths (D in {64, 128}, H=128, <= 24 extra columns), else 0.
 TOWER_MODE = os.environ.get("RB200_TOWER_MODE", "auto")
 
 
 def tower_mode_for(D: int, H: int, E: int, mode=None) -> int:
     mode = TOWER_MODE if mode is None else mode
     if str(mode) == "auto":
-        return 2 if (D == 64 and H == 128 and E <= 24) else 0
+        return 2 if (D in (64, 128) and H == 128 and E <= 24) else 0
     return int(mode)
 
 
@@ -64,6 +64,14 @@ def _f32c(t: torch.Tensor) -> torch.Tensor:
     if t.dtype != torch.float32:
         t = t.float()
     return t.contiguous()
+
+
+def _raise_on_bad_ids(err: torch.Tensor, n_rows: int) -> None:
+    flag = int(err.item())
+    if flag & 1:
+        raise IndexError(f"index out of range in self (an id was outside the embedding table [0, {n_rows - 1}])")
+    if flag & 2:
+        raise RB200Error("tower kernel: a tensor-core pipeline wait timed out (results of this call are invalid)")
 
 
 class _TowerFn(torch.autograd.Function):
@@ -91,27 +99,36 @@ class _TowerFn(torch.autograd.Function):
         if keep_mask is not None:
             keep_mask = keep_mask.reshape(B, H).to(torch.uint8).contiguous()
         mode = tower_mode_for(D, H, E, mode)
+        # an id outside the table is clamped to row 0 by the kernels and reported through this flag; nn.Embedding raises
+        # IndexError there, and serving/recommender.py:200-207 relies on the exception for its cold-start fallback
+        err = torch.zeros(1, dtype=torch.int32, device=dev)
         if B > 0:
             job = TowerJob(ptr(table), ptr(ids), ptr(extra), ptr(W1), ptr(b1), ptr(W2), ptr(b2), ptr(out), ptr(hid),
                            ptr(denom), ptr(keep_mask), n_rows, B, E, 0, None)
             wsb = lib.rb200_tower_fwd_workspace_bytes(1, D, H, E, mode)
             ws = workspace(wsb, dev) if wsb else None
             with torch.cuda.device(dev):
-                check(lib.rb200_tower_fwd(job, 1, D, H, float(drop_p), int(seed), int(offset), None, mode, None, ptr(ws), wsb,
+                check(lib.rb200_tower_fwd(job, 1, D, H, float(drop_p), int(seed), int(offset), None, mode, ptr(err), ptr(ws), wsb,
                                           stream_ptr()), "rb200_tower_fwd")
         if need_grad:
-            ctx.save_for_backward(ids, extra, table, W1, W2, out, hid, denom)
+            # training: the flag is read in backward (the caller's loss.item() synchronises every step anyway), so the forward
+            # of the three towers stays asynchronous
+            ctx.save_for_backward(ids, extra, table, W1, W2, out, hid, denom, err)
             ctx.drop_p = float(drop_p)
             ctx.mode = mode
             ctx.dims = (B, D, H, E, n_rows)
+        elif B > 0 and not torch.cuda.is_current_stream_capturing():
+            _raise_on_bad_ids(err, n_rows)        # inference: synchronous, like the .cpu() that follows in every caller
         return out.view(*shape, D)
 
     @staticmethod
     def backward(ctx, dY):
         lib = _lib.load()
-        ids, extra, table, W1, W2, out, hid, denom = ctx.saved_tensors
+        ids, extra, table, W1, W2, out, hid, denom, err = ctx.saved_tensors
         B, D, H, E, n_rows = ctx.dims
         dev = table.device
+        if not torch.cuda.is_current_stream_capturing():
+            _raise_on_bad_ids(err, n_rows)
         Din = D + E
         P = H * Din + H + D * H + D
         grads = torch.empty(P, dtype=torch.float32, device=dev)
@@ -215,6 +232,9 @@ class _Tower(nn.Module):
         self.extra_dim = extra_dim
         self.mode = None          # None → module default (RB200_TOWER_MODE / auto); 0, 1 or 2 to force
         self._calls = 0
+        # dropout stream of this tower: Philox offset = stream id · 2^40 + call counter, seed = torch.initial_seed() — a fixed
+        # torch.manual_seed gives the same masks in every process (user tower 0, item tower 1; the reference is reproducible too)
+        self._stream_id = 1 if extra_dim else 0
         self._init_weights()
 
     def _init_weights(self):
@@ -231,7 +251,7 @@ class _Tower(nn.Module):
         seed = torch.initial_seed() & 0x7FFFFFFFFFFFFFFF
         l1, l2 = self.mlp[0], self.mlp[3]
         return _TowerFn.apply(ids, extra, self.embedding.weight, l1.weight, l1.bias, l2.weight, l2.bias, p, seed,
-                              (id(self) & 0xFFFF) * 1000003 + self._calls, keep_mask, self.mode)
+                              (self._stream_id << 40) + self._calls, keep_mask, self.mode)
 
 
 class UserTower(_Tower):
@@ -284,11 +304,20 @@ class TwoTowerModel(nn.Module):
 
     # -- inference helpers (two_tower.py:166-210) ------------------------------------------ #
     def _device(self) -> torch.device:
-        return self.user_tower.embedding.weight.device
+        """The COMPUTE device.  The helpers below take and return host NumPy data, so the `device` argument the reference's
+        callers pass (run_pipeline.py:145-177 hardcodes torch.device('cpu')) only says where the caller's tensors live; the
+        arithmetic has no CPU path.  Weights still on the CPU are moved to the current CUDA device on first use."""
+        dev = self.user_tower.embedding.weight.device
+        if dev.type != "cuda" and torch.cuda.is_available():
+            dev = torch.device("cuda", torch.cuda.current_device())
+            self.to(dev)
+        return dev
 
     @torch.no_grad()
     def get_user_embedding(self, user_id: int, device: torch.device = None) -> np.ndarray:
         self.eval()   # the reference leaves the model in eval mode too (SURVEY.md Appendix A)
+        if not 0 <= int(user_id) <= self.n_users:     # nn.Embedding raises here; recommender.py:200-207 turns it into the fallback
+            raise IndexError(f"index out of range in self (user id {user_id}, table [0, {self.n_users}])")
         ids = torch.tensor([int(user_id)], dtype=torch.long, device=self._device())
         return self.user_tower(ids).cpu().numpy()[0]
 
@@ -308,8 +337,8 @@ class TwoTowerModel(nn.Module):
     def precompute_item_embeddings(self, item_ids: List[int], genre_vectors: np.ndarray, device: torch.device = None) -> None:
         embs = self.get_item_embeddings(item_ids, genre_vectors, device)
         self._item_embeddings = torch.tensor(embs, dtype=torch.float32)
-        self._item_id_to_idx = {iid: idx for idx, iid in enumerate(item_ids)}
-        self._idx_to_item_id = {idx: iid for idx, iid in enumerate(item_ids)}
+        self._item_id_to_idx = {int(iid): idx for idx, iid in enumerate(item_ids)}     # plain ints: loadable with weights_only
+        self._idx_to_item_id = {idx: int(iid) for idx, iid in enumerate(item_ids)}
         logger.info("Precomputed %d item embeddings (dim=%d)", len(item_ids), embs.shape[1])
 
     # -- persistence (two_tower.py:216-251) -------------------------------------------------- #
@@ -331,13 +360,18 @@ class TwoTowerModel(nn.Module):
 
     @classmethod
     def load(cls, path: str, device: torch.device = torch.device("cpu")) -> "TwoTowerModel":
-        ck = torch.load(path, map_location="cpu", weights_only=False)
+        ck = torch.load(path, map_location="cpu", weights_only=True)      # tensors + int dicts: no arbitrary pickles
         sd = ck["state_dict"]
         hidden = ck.get("hidden_dim", sd["user_tower.mlp.0.weight"].shape[0])
         model = cls(n_users=ck["n_users"], n_items=ck["n_items"], embed_dim=ck["embed_dim"], hidden_dim=hidden)
         model.load_state_dict(sd)
         model._item_id_to_idx = ck.get("item_id_to_idx")
         model._idx_to_item_id = ck.get("idx_to_item_id")
+        # `device` is the caller's host-facing device (the reference's default and run_pipeline.py:146 pass cpu); the weights go
+        # to the compute device: the requested CUDA device, else the current one when a GPU is present
+        device = torch.device(device)
+        if device.type != "cuda" and torch.cuda.is_available():
+            device = torch.device("cuda", torch.cuda.current_device())
         model.to(device)
         model.eval()
         logger.info("Loaded two-tower model from %s (users=%d, items=%d, dim=%d)", path, model.n_users, model.n_items,

@@ -179,3 +179,56 @@ def test_route_plan_padded_kernel_matches_tensor_reference(world, n_u, n_i, cap)
     assert torch.equal(slot_k, slot_r)
     if world == 8 and cap == 1000:
         assert int(of_k) > 0                                   # this case really overflows
+
+
+def test_padded_exchange_overflow_goes_to_the_dummy_slot():
+    """A request that does not fit its bucket must cost that sample only (zero row in, gradient dropped), never touch another
+    row, and must be reported — by check_exchange() and by the automatic check every `check_every` steps."""
+    import recommendit_b200 as R
+    from recommendit_b200.sharded import ShardedBPRTrainer
+    NU, NI, D, H, B = 3000, 2000, 64, 128, 256
+    P = O.init_params(NU, NI, D, H, seed=3)
+    init = {k: torch.from_numpy(v) for k, v in P.items()}
+    tr = ShardedBPRTrainer(NU, NI, D, H, adam_mode="rows", device="cuda", init=init, lr=1e-2, exchange="padded", capacity_factor=0.5,
+                           check_every=2)
+    C = tr.capacity(3 * B)
+    assert C < 3 * B
+    # distinct ids everywhere: requests in sample order [users | positives | negatives]; those at positions >= C overflow
+    u = np.arange(1, B + 1); p = np.arange(1, B + 1); n = np.arange(B + 1, 2 * B + 1)
+    z = np.zeros((B, 18), np.float32)
+    before = tr.full_state()
+    loss = float(tr.step(*[dev(a) for a in (u, p, z, n, z)]))
+    assert np.isfinite(loss)
+    after = tr.full_state()
+    req_items = np.concatenate([p, n])
+    fits = np.arange(B, 3 * B) < C                     # item requests that fit
+    moved = (after["item_tower.embedding.weight"] - before["item_tower.embedding.weight"]).abs().sum(1).cpu().numpy() > 0
+    assert moved[req_items[fits]].all()                # served requests update their rows
+    assert not moved[req_items[~fits]].any()           # overflowed requests update nothing …
+    untouched = np.setdiff1d(np.arange(NI + 1), req_items)
+    assert not moved[untouched].any()                  # … and nobody else's row either
+    with pytest.raises(R.RB200Error, match="exceeded the exchange capacity"):
+        tr.check_exchange()
+    tr.step(*[dev(a) for a in (u, p, z, n, z)])
+    with pytest.raises(R.RB200Error, match="exceeded the exchange capacity"):
+        tr.step(*[dev(a) for a in (u, p, z, n, z)])    # steps == 2: the automatic check fires
+
+
+def test_sharded_dropout_is_seeded_and_graph_replays_draw_fresh_masks():
+    from recommendit_b200.sharded import ShardedBPRTrainer
+    NU, NI, D, H, B = 3000, 2000, 128, 128, 512
+    P = O.init_params(NU, NI, D, H, seed=4)
+    init = {k: torch.from_numpy(v) for k, v in P.items()}
+    rng = np.random.default_rng(0)
+    batch = [dev(a) for a in (rng.integers(1, NU + 1, B), rng.integers(1, NI + 1, B), (rng.random((B, 18)) < .2).astype(np.float32),
+                              rng.integers(1, NI + 1, B), (rng.random((B, 18)) < .2).astype(np.float32))]
+
+    def run(seed, graph, drop, lr=0.0):
+        tr = ShardedBPRTrainer(NU, NI, D, H, adam_mode="rows", device="cuda", init=init, lr=lr, weight_decay=0.0, exchange="padded",
+                               use_cuda_graph=graph, dropout=drop, seed=seed)
+        return [float(tr.step(*batch)) for _ in range(5)]
+
+    a, b, c, d = run(1, False, 0.3), run(1, True, 0.3), run(2, False, 0.3), run(1, False, 0.0)
+    assert a == b                                        # replays read the step counter on the device: same masks as eager
+    assert len(set(a)) == 5                              # lr = 0: only the masks change from step to step
+    assert a != c and len(set(d)) == 1

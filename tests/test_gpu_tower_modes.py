@@ -1,5 +1,10 @@
-"""Precision modes of the tower kernels at the reference's production widths (D = 64, H = 128):
-0 = fp32 FFMA, 1 = tcgen05 TF32 (stated looser bound), 2 = tcgen05 3xTF32 (fp32-grade, must meet the 1e-5 bar)."""
+"""Precision modes of the tower kernels at the reference's production widths (D = 64, H = 128) and at BASELINE C4's (D = 128):
+0 = fp32 FFMA, 1 = tcgen05 TF32 (stated looser bound), 2 = tcgen05 3xTF32 (fp32-grade, must meet the 1e-5 bar).
+Both widths run the TMEM-operand kernels (csrc/tower_ts.cu); at D = 64 RB200_TOWER_TS=0 selects the shared-memory-operand
+kernels (csrc/tower_tc.cu), covered by the subprocess test at the end."""
+import os
+import subprocess
+import sys
 import numpy as np
 import pytest
 import torch
@@ -20,7 +25,7 @@ def _set_mode(model, mode):
     model.item_tower.mode = mode
 
 
-@pytest.mark.parametrize("case", ["tt_dup", "tt_drop64"])
+@pytest.mark.parametrize("case", ["tt_dup", "tt_drop64", "tt_d128"])
 @pytest.mark.parametrize("mode", [0, 1, 2])
 def test_modes_against_fp64_oracle(golden, case, mode):
     g = golden(case)
@@ -45,11 +50,12 @@ def test_modes_against_fp64_oracle(golden, case, mode):
         assert rel_l2(prm.grad.detach().cpu().numpy(), G64[k]) <= tol, (case, mode, k, rel_l2(prm.grad.detach().cpu().numpy(), G64[k]))
 
 
-def test_modes_draw_identical_dropout_masks():
+@pytest.mark.parametrize("D", [64, 128])
+def test_modes_draw_identical_dropout_masks(D):
     import recommendit_b200 as R
     from recommendit_b200.two_tower import _TowerFn
     torch.manual_seed(3)
-    model = R.TwoTowerModel(500, 300, 64, 128, dropout=0.3).cuda().train()
+    model = R.TwoTowerModel(500, 300, D, 128, dropout=0.3).cuda().train()
     ids = torch.randint(1, 301, (333,), device="cuda")
     genres = (torch.rand(333, 18, device="cuda") < 0.2).float()
     t = model.item_tower
@@ -88,24 +94,25 @@ def test_fused_step_modes_track_fp32_mode(golden, mode):
     assert torch.equal(res[mode][1]["item_uniq_ids"], res[0][1]["item_uniq_ids"])
 
 
-def test_full_batch_modes_against_fp64_oracle():
-    """C2 sizes (B = 8192): FFMA path and 3xTF32 tensor-core path against the fp64 oracle on a whole step.  The batch sums
-    of the weight gradients run over 8192 / 16384 rows here; both fp32 engines must stay inside the 1e-5 bound
-    (second-Linear bias: 1e-4, see tests/parity.py)."""
+@pytest.mark.parametrize("D", [64, 128])
+def test_full_batch_modes_against_fp64_oracle(D):
+    """C2 sizes (B = 8192; D = 128: the per-rank batch of C4): FFMA path and 3xTF32 tensor-core path against the fp64 oracle on a
+    whole step.  The batch sums of the weight gradients run over 8192 / 16384 rows here; both fp32 engines must stay inside the
+    1e-5 bound (second-Linear bias: 1e-4, see tests/parity.py)."""
     import recommendit_b200 as R
     torch.manual_seed(0)
     nu, ni, B = 6040, 3952, 8192
     rng = np.random.default_rng(2)
     u, p, n = rng.integers(0, nu + 1, B), rng.integers(0, ni + 1, B), rng.integers(0, ni + 1, B)
     table = (rng.random((ni + 1, 18)) < 0.1).astype(np.float32)
-    base = R.TwoTowerModel(nu, ni, 64, 128, dropout=0.0).cuda().train()
+    base = R.TwoTowerModel(nu, ni, D, 128, dropout=0.0).cuda().train()
     sd = {k: v.clone() for k, v in base.state_dict().items()}
     P = {k: v.detach().cpu().numpy().astype(np.float64) for k, v in sd.items()}
     l64, G64, (u64, p64, _) = O.loss_and_grads(P, u, p, table[p].astype(np.float64), n, table[n].astype(np.float64))
     ref = {"user_mlp_grad": flat_mlp(G64, "user"), "item_mlp_grad": flat_mlp(G64, "item"), "user_emb": u64, "pos_emb": p64}
     errs = {}
     for m in (0, 2):
-        model = R.TwoTowerModel(nu, ni, 64, 128, dropout=0.0).cuda().train()
+        model = R.TwoTowerModel(nu, ni, D, 128, dropout=0.0).cuda().train()
         model.load_state_dict(sd)
         tr = R.FusedBPRTrainer(model, use_cuda_graph=False, tower_mode=m, seed=5)
         loss = tr.step_host(u, p, table[p], n, table[n])
@@ -113,7 +120,7 @@ def test_full_batch_modes_against_fp64_oracle():
         assert abs(loss - float(l64)) <= 1e-6, (m, loss, float(l64))
         for key in ("user_mlp_grad", "item_mlp_grad"):
             a, b = v[key].cpu().numpy(), ref[key]
-            errs[(m, key)] = (rel_l2(a[:-64], b[:-64]), rel_l2(a[-64:], b[-64:]))
+            errs[(m, key)] = (rel_l2(a[:-D], b[:-D]), rel_l2(a[-D:], b[-D:]))
         for tower in ("user", "item"):
             dense = G64[f"{tower}_tower.embedding.weight"]
             ids = v[f"{tower}_uniq_ids"].cpu().numpy()
@@ -123,3 +130,16 @@ def test_full_batch_modes_against_fp64_oracle():
     print("full-batch gradient errors vs fp64 (weights, bias2):", errs)
     for key, (ew, eb) in errs.items():
         assert ew <= 1e-5 and eb <= 1e-4, (key, ew, eb, errs)
+
+
+def test_shared_memory_operand_kernels_at_d64():
+    """The shared-memory-operand tower kernels (csrc/tower_tc.cu, the D = 64 default of round 1) stay selectable with
+    RB200_TOWER_TS=0: the parity cases of this file again on them (the selector is read once per process, hence the subprocess)."""
+    if os.environ.get("RB200_TOWER_TS") == "0":
+        pytest.skip("already inside the RB200_TOWER_TS=0 run")
+    env = dict(os.environ, RB200_TOWER_TS="0")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "pytest", "-x", "-q", "-m", "gpu", "tests/test_gpu_tower_modes.py", "-k",
+                        "(fp64_oracle or dropout_masks or track_fp32) and not d128 and not 128"], cwd=root, env=env,
+                       capture_output=True, text=True, timeout=1200)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
