@@ -360,10 +360,19 @@ class TwoTowerModel(nn.Module):
 
     @classmethod
     def load(cls, path: str, device: torch.device = torch.device("cpu")) -> "TwoTowerModel":
-        ck = torch.load(path, map_location="cpu", weights_only=True)      # tensors + int dicts: no arbitrary pickles
+        # tensors + int dicts; no arbitrary pickles.  Checkpoints written by the reference hold NumPy integer scalars
+        # (`n_users = ratings_df["user_id"].max()`, train_embeddings.py:135-136), which the safe unpickler admits by name.
+        import numpy
+        scalars = [numpy.dtype, numpy.dtypes.Int64DType, numpy.dtypes.Int32DType, numpy.dtypes.Float64DType, numpy.dtypes.Float32DType]
+        try:
+            scalars.append(numpy._core.multiarray.scalar)
+        except AttributeError:                                       # numpy < 2
+            scalars.append(numpy.core.multiarray.scalar)
+        with torch.serialization.safe_globals(scalars):
+            ck = torch.load(path, map_location="cpu", weights_only=True)
         sd = ck["state_dict"]
         hidden = ck.get("hidden_dim", sd["user_tower.mlp.0.weight"].shape[0])
-        model = cls(n_users=ck["n_users"], n_items=ck["n_items"], embed_dim=ck["embed_dim"], hidden_dim=hidden)
+        model = cls(n_users=int(ck["n_users"]), n_items=int(ck["n_items"]), embed_dim=int(ck["embed_dim"]), hidden_dim=int(hidden))
         model.load_state_dict(sd)
         model._item_id_to_idx = ck.get("item_id_to_idx")
         model._idx_to_item_id = ck.get("idx_to_item_id")
