@@ -48,6 +48,16 @@ def peaks():
     return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
 
 
+def ncu_traffic(kernel: str):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel`, from the committed `ncu --set full` captures
+    (profiles/r02_traffic.json: kernel -> {"read": B, "write": B, "source": file}); None when no capture holds the kernel."""
+    p = ROOT / "profiles" / "r02_traffic.json"
+    if not p.exists():
+        return None
+    ent = json.loads(p.read_text()).get(kernel)
+    return None if ent is None else int(ent["read"] + ent["write"])
+
+
 def synth_batches(n_batches: int, seed: int = 1):
     """C2 batches: ids uniform over the tables, genres = per-item multi-hot (Bernoulli 0.092, ≥ 1 bit)."""
     rng = np.random.default_rng(SEED)
@@ -72,7 +82,7 @@ class ClockSampler:
     def __init__(self, gpu_index: int):
         self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
         try:
-            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "500",
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
                                        "-i", str(gpu_index)], stdout=self.f, stderr=subprocess.DEVNULL)
         except Exception:
             self.p = None
@@ -80,6 +90,9 @@ class ClockSampler:
     def stop(self):
         if self.p is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        t_end = time.time() + 3.0                  # a short timed region can end before nvidia-smi printed its first sample
+        while time.time() < t_end and Path(self.f.name).stat().st_size < 40:
+            time.sleep(0.05)
         time.sleep(0.15)
         self.p.terminate()
         try:
@@ -101,42 +114,96 @@ class ClockSampler:
         return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(rows[0][2]), "reasons": sorted(reasons), "samples": len(rows)}
 
 
+#: the workload both arms of the N = 1 line run (identical dict in both JSON lines: the driver compares them)
+C2_CONFIG = {"workload": "C2: two-tower BPR training step, batch 8192, ML-1M-shape tables 6041x64 / 3953x64, H=128, 18 genres, "
+                         "sampled negatives + bpr_loss, dropout 0.1, clip_grad_norm_ 1.0, Adam wd 1e-5 (dense: every row updated, "
+                         "as torch.optim.Adam on the reference's dense embedding gradients does)"}
+
+
 # --------------------------------------------------------------------------------------------------------- #
 # CPU arm
 # --------------------------------------------------------------------------------------------------------- #
-def cpu_step_throughput(steps: int, warmup: int, threads: int):
+def reference_stepper(n_users: int, n_items: int, d: int, h: int, dropout: float, threads: int):
+    """→ (step(batch of CPU tensors) -> loss float, kind).  kind "reference": the UNMODIFIED reference module (oracle/_ref, a byte
+    copy of /root/reference/src made by oracle/make_ref.py and shipped with the snapshot) driven through the reference's own step
+    body, train_embeddings.py:183-194.  kind "port": the same ATen calls restated (oracle/torch_step.py) when the copy is absent."""
+    torch.set_num_threads(threads)
+    from oracle import make_ref
+    if make_ref.available():
+        if make_ref.path() not in sys.path:
+            sys.path.insert(1, make_ref.path())
+        import logging
+        logging.disable(logging.WARNING)                 # the reference logs "faiss not available" at import
+        from src.models.two_tower import TwoTowerModel    # the stock class: nothing of this repository on this path
+        logging.disable(logging.NOTSET)
+        assert "oracle/_ref" in sys.modules["src.models.two_tower"].__file__
+        torch.manual_seed(0)
+        model = TwoTowerModel(n_users=n_users, n_items=n_items, embed_dim=d, hidden_dim=h, dropout=dropout).train()
+        optimizer = torch.optim.Adam(model.parameters(), lr=1e-3, weight_decay=1e-5)
+
+        def step(batch):
+            user_ids, pos_ids, pos_genres, neg_ids, neg_genres = batch
+            user_emb = model.user_tower(user_ids)
+            pos_item_emb = model.item_tower(pos_ids, pos_genres)
+            neg_item_emb = model.item_tower(neg_ids, neg_genres)
+            loss = model.bpr_loss(user_emb, pos_item_emb, neg_item_emb)
+            optimizer.zero_grad()
+            loss.backward()
+            torch.nn.utils.clip_grad_norm_(model.parameters(), max_norm=1.0)
+            optimizer.step()
+            return loss.item()
+        return step, "reference"
     from oracle import torch_step as TS
     from oracle import two_tower_oracle as O
-    torch.set_num_threads(threads)
-    P = O.init_params(N_USERS, N_ITEMS, D, H, seed=0)
-    T = TS.make_params(P)
+    T = TS.make_params(O.init_params(n_users, n_items, d, h, seed=0))
     opt = TS.make_optimizer(T)
+    return (lambda batch: TS.step(T, opt, batch, dropout=dropout)), "port"
+
+
+def cpu_step_throughput(steps: int, warmup: int, threads: int):
+    step, kind = reference_stepper(N_USERS, N_ITEMS, D, H, DROPOUT, threads)
     batches, _ = synth_batches(min(steps + warmup, 8))
     tb = [tuple(torch.from_numpy(np.ascontiguousarray(a)) for a in b) for b in batches]
     for i in range(warmup):
-        TS.step(T, opt, tb[i % len(tb)], dropout=DROPOUT)
+        step(tb[i % len(tb)])
     t0 = time.perf_counter()
     for i in range(steps):
-        TS.step(T, opt, tb[(warmup + i) % len(tb)], dropout=DROPOUT)
+        step(tb[(warmup + i) % len(tb)])
     dt = time.perf_counter() - t0
-    return B * steps / dt, dt / steps * 1e3
+    return B * steps / dt, dt / steps * 1e3, kind
+
+
+def _ref_how(kind: str) -> str:
+    return ("the UNMODIFIED reference module (oracle/_ref/src/models/two_tower.py, byte copy of the reference) through the "
+            "reference's own step body, train_embeddings.py:183-194" if kind == "reference"
+            else "oracle/torch_step.py: the reference's own PyTorch calls restated (oracle/_ref not shipped)")
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
     if rank != 0:
         return
     cores = os.cpu_count() or 1
-    val, ms = cpu_step_throughput(args.steps, max(args.warmup, 1), cores)
+    if world > 1 or args.gpus > 1:
+        # the N > 1 arm measures C4 (bench_sharded.py): the reference's step at C4 widths on a bounded sample, same config dict
+        import bench_sharded as BS
+        n = max(world, args.gpus)
+        cb = BS.cpu_baseline_c4(steps=max(2, min(args.steps, 4)))
+        line = {"impl": "reference", "metric": "bpr_train_samples_per_s", "value": cb["value"], "unit": "samples/s", "n_gpus": n,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": cb["ms_per_step"], "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": BS.c4_config(n), "cpu_baseline": cb,
+                "e2e": {"value": cb["value"], "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+        print(json.dumps(line), flush=True)
+        return
+    val, ms, kind = cpu_step_throughput(args.steps, max(args.warmup, 1), cores)
     line = {
         "impl": "reference", "metric": "bpr_train_samples_per_s", "value": val, "unit": "samples/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "C2: two-tower BPR training step, batch 8192, ML-1M-shape tables 6041x64 / 3953x64, H=128, "
-                               "sampled negatives + bpr_loss, dropout 0.1, clip_grad_norm_ 1.0, Adam wd 1e-5 (dense)"},
-        "cpu_baseline": {"value": val, "unit": "samples/s", "cores": cores, "kind": "port",
-                         "sample": f"{args.steps} full steps of batch {B} (oracle/torch_step.py: the reference's own PyTorch "
-                                   f"calls on CPU, torch {torch.__version__}, {cores} threads)"},
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": dict(C2_CONFIG),
+        "cpu_baseline": {"value": val, "unit": "samples/s", "cores": cores, "kind": kind,
+                         "sample": f"{args.steps} full steps of batch {B} ({_ref_how(kind)}; torch {torch.__version__} CPU, "
+                                   f"{cores} threads, dropout on)"},
         "e2e": {"value": val, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -268,6 +335,24 @@ def bench_train_single(args, dev):
             "clocks": clocks, "stages": stages, "loss": loss, "dropin_ms": dropin_ms}
 
 
+def ivf_roofline(scan_bytes, run_ms, n, d, nq, k, n_cand, pk):
+    """The list scan + select pair (rb200_ivf_search_run) against the HBM roofline, stated BOTH ways (SURVEY.md §8d note):
+    `frac` uses the bytes a list-major kernel must move — the database once (vectors + ids), the candidate scores written once
+    and read once by the select, the results — because the query-major figure (every probing query re-reads its lists: 8.45 GB
+    per C3 batch against a 264 MB database) exceeds what any kernel that shares a list between its queries needs to read, and a
+    fraction of peak computed from it (2.7 in round 1) is not a roofline statement; it is kept as `query_major`."""
+    phys = n * (4 * d + 8) + 2 * n_cand * 4 + nq * k * 12
+    traffic = ncu_traffic("list_scan_tc_kernel+select_topk_kernel")
+    return {"kernel": "list_scan_tc_kernel + select_topk_kernel<ResolveIvf> (rb200_ivf_search_run)", "bound": "hbm", "unit": "GB/s",
+            "achieved": phys / (run_ms * 1e-3) / 1e9, "peak": pk["hbm_gbs"], "frac": phys / (run_ms * 1e-3) / 1e9 / pk["hbm_gbs"],
+            "peak_source": pk["source"], "algorithmic_bytes": phys, "ms": run_ms, "traffic": traffic,
+            "definition": "list-major: database read once (N·(4·D+8)) + candidate scores written and read once (2·4·candidates) + results",
+            "query_major": {"algorithmic_bytes": scan_bytes, "GBps_equivalent": scan_bytes / (run_ms * 1e-3) / 1e9,
+                            "note": "SURVEY.md §8d's per-query figure nq·Σ_probed len·(4·D+8): what a query-major scan would read; "
+                                    "reported for comparison with CPU FAISS-style scans, not as a fraction of peak"},
+            "note": "the pair is latency / SM-bound, not HBM-bound (profiles/r01_ncu_full_v2.md: DRAM traffic is 1.4x the database)"}
+
+
 def bench_ivf(args, dev):
     """C3: nlist 4096, nprobe 32, top-500, 4096 queries over 1 M × 64."""
     import recommendit_b200 as R
@@ -341,12 +426,7 @@ def bench_ivf(args, dev):
                    "l2": "flushed between timed batches (256 MiB write)"},
         "e2e": {"value": nq / e2e_ms * 1e3, "unit": "queries/s", "h2d_bytes_per_step": nq * d * 4, "d2h_bytes_per_step": nq * k * 12,
                 "ms_per_batch": e2e_ms},
-        "roofline": {"kernel": "list_scan_kernel<64> + select_topk_kernel (rb200_ivf_search_run)", "bound": "hbm",
-                     "achieved": scan_bytes / (run * 1e-3) / 1e9, "peak": pk["hbm_gbs"], "unit": "GB/s",
-                     "frac": scan_bytes / (run * 1e-3) / 1e9 / pk["hbm_gbs"], "traffic": None, "peak_source": pk["source"],
-                     "algorithmic_bytes": scan_bytes, "ms": run,
-                     "note": "query-major algorithmic bytes; the list-major kernel reads each list once per batch, so DRAM "
-                             "traffic is far below this figure (see profiles/)"},
+        "roofline": ivf_roofline(scan_bytes, run, n, d, nq, k, int(tot.value), pk),
         "quality_vs_exact": quality,
         "quality_note": "Recall@K / NDCG@K of the IVF ids against the exhaustive top-K of the same queries.  The C3 generator adds "
                         "noise of norm 0.35*sqrt(64) = 2.8 to unit cluster centres, so list membership says little about neighbourhood "
@@ -392,7 +472,7 @@ def bench_inbatch(args, dev):
     t = out["tcgen05_3xtf32"]
     out["roofline"] = {"kernel": "inbatch_tc_kernel<2> x2 (rb200_bpr_inbatch mode 2)", "bound": "tensor", "unit": "TFLOP/s",
                        "achieved": t["logical_tflops"], "issued_tflops": t["logical_tflops"] * 4.0, "peak": pk["bf16_tflops"],
-                       "frac": t["logical_tflops"] / pk["bf16_tflops"], "traffic": None,
+                       "frac": t["logical_tflops"] / pk["bf16_tflops"], "traffic": ncu_traffic("inbatch_tc_kernel"),
                        "note": "logical 6·B²·D fp32-grade flops vs the measured bf16 peak (kind::tf32 peaks at half of it); issued = "
                                "8·B²·D (scores recomputed) x 3 (3xTF32).  The kernel is bound by the B² sigmoid/softplus epilogue and "
                                "operand staging (SFU + issue slots), not by the tensor pipe (profiles/r01_inbatch_tc.md)"}
@@ -497,7 +577,12 @@ def bench_hbm_kernels(dev):
                      "frac": gbs / pk["hbm_gbs"], "note": note}
 
     ms = timeit(lambda: _lib.check(lib.rb200_gather_rows(table.data_ptr(), ids.data_ptr(), n_req, D4, rows, out.data_ptr(), sp())))
-    add("gather_rows", ms, n_req * (2 * 4 * D4 + 8), f"{n_req} random rows of a {rows}x{D4} fp32 table (2 GB): 4·D read + 4·D written + 8 B id per row")
+    add("gather_rows", ms, n_req * (2 * 4 * D4 + 8), f"{n_req} random rows of a {rows}x{D4} fp32 table (2 GB): 4·D read + 4·D written + 8 B id per row (physical bytes of a stand-alone gather)")
+    res["gather_rows"]["survey_8d_definition"] = {"algorithmic_bytes": n_req * (4 * D4 + 8), "achieved": n_req * (4 * D4 + 8) / (ms * 1e-3) / 1e9,
+                                                   "frac": n_req * (4 * D4 + 8) / (ms * 1e-3) / 1e9 / pk["hbm_gbs"],
+                                                   "note": "SURVEY.md §8d counts only the gathered row + its id (4·D + 8 B): the figure for a gather "
+                                                           "FUSED into its consumer (the tower kernels read the rows straight into TMEM and never "
+                                                           "write them back); this stand-alone kernel also writes every row"}
     ms = timeit(lambda: _lib.check(lib.rb200_adam_rows(table.data_ptr(), m.data_ptr(), v.data_ptr(), D4, uniq.data_ptr(), ug.data_ptr(),
                                                        nu.data_ptr(), uniq.numel(), opt.data_ptr(), sp())))
     add("adam_rows", ms, uniq.numel() * (28 * D4 + 8), f"Adam on {uniq.numel()} touched rows: w,m,v read+written (24·D) + gradient row (4·D) + id")
@@ -550,19 +635,28 @@ def bench_flat(args, dev, rows: int = 12_500_000, nqs=(4096, 64), reps: int = 3)
             torch.cuda.synchronize(dev)
             ms.append(a.elapsed_time(b))
         t = float(np.median(ms))
-        # sanity (library matmul + topk on a row prefix, not the oracle): the winners over a 1M-row prefix
+        # sanity on a 1M-row prefix against a library matmul + top-k, judged by the parity rule of the tests
+        # (oracle/ivf_oracle.assert_topk_equivalent): ids identical except where scores tie within the fp32 rounding of a
+        # 64-term dot product (two engines sum in different orders) — an id may differ only if its score equals the
+        # reference's score at that rank, or it sits at the k-th-score boundary
         sub = 1_000_000
         s1, i1 = R.flat_search(q[:64], x[:sub], 500)
         ref = torch.topk(q[:64].double() @ x[:sub].double().T, 500, dim=1)
-        agree = float((i1 == ref.indices).float().mean())
+        same = i1 == ref.indices
+        near = (s1.double() - ref.values).abs() <= 4e-7
+        kth = ref.values[:, -1:]
+        in_ref = (s1.double() >= kth - 4e-7)
+        parity_ok = bool(((same | near) & in_ref).all().item())
         flops = 2.0 * nq * rows * 64
         ent = {"ms_per_batch": t, "queries_per_s": nq / t * 1e3, "logical_tflops": flops / (t * 1e-3) / 1e12,
-               "ids_equal_to_fp64_topk_on_1M_prefix": agree}
+               "prefix_1M_parity": {"ok": parity_ok, "ids_identical_frac": float(same.float().mean()),
+                                    "ids_differing_are_score_ties_within": 4e-7, "max_score_diff": float((s1.double() - ref.values).abs().max()),
+                                    "rule": "ids identical except exact/rounding-level score ties (north_star); scores within 2e-6"}}
         if nq >= 1024:
             ent["roofline"] = {"kernel": "flat_scan_tc_kernel (3xTF32: 3 MMAs per logical MMA)", "bound": "tensor", "unit": "TFLOP/s",
                                "achieved": flops / (t * 1e-3) / 1e12, "issued_tflops": 3 * flops / (t * 1e-3) / 1e12,
                                "peak": pk["bf16_tflops"], "frac": flops / (t * 1e-3) / 1e12 / pk["bf16_tflops"],
-                               "traffic": None, "traffic_note": "ncu --set full of the 786 432-row round of a 2 M-row search "
+                               "traffic": ncu_traffic("flat_scan_tc_kernel"), "traffic_note": "per launch; ncu --set full of the 786 432-row round of a 2 M-row search "
                                "(profiles/r01_flat_scan_tc.md): dram read 245.8 MB + write 12.1 MB for 201 MB of rows — the shard is "
                                "read once; tensor pipe 56.7 % active",
                                "note": "logical 2·nq·N·D flops vs the measured bf16 peak; kind::tf32 peaks at half of it and 3xTF32 "
@@ -570,7 +664,7 @@ def bench_flat(args, dev, rows: int = 12_500_000, nqs=(4096, 64), reps: int = 3)
         else:
             by = rows * 64 * 4.0
             ent["roofline"] = {"kernel": "flat_scan_tc_kernel", "bound": "hbm", "unit": "GB/s", "achieved": by / (t * 1e-3) / 1e9,
-                               "peak": pk["hbm_gbs"], "frac": by / (t * 1e-3) / 1e9 / pk["hbm_gbs"], "traffic": None,
+                               "peak": pk["hbm_gbs"], "frac": by / (t * 1e-3) / 1e9 / pk["hbm_gbs"], "traffic": ncu_traffic("flat_scan_tc_kernel_small_nq"),
                                "note": "the shard is read once per batch: N·D·4 bytes"}
         out[f"nq{nq}"] = ent
     del x
@@ -680,6 +774,7 @@ def main():
     ap.add_argument("--skip-inbatch", action="store_true")
     ap.add_argument("--skip-producer", action="store_true")
     ap.add_argument("--skip-flat", action="store_true")
+    ap.add_argument("--skip-c4", action="store_true")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
@@ -704,7 +799,7 @@ def main():
     dom = max(stages, key=stages.get)
     flops = {"towers_fwd": 107520.0 * B, "towers_bwd": 215040.0 * B}
     roof = {"kernel": dom, "bound": "tensor", "unit": "TFLOP/s", "peak": pk["bf16_tflops"], "peak_source": pk["source"],
-            "traffic": None, "ms": stages[dom], "share_of_step": stages[dom] / sum(stages.values())}
+            "traffic": ncu_traffic(dom), "ms": stages[dom], "share_of_step": stages[dom] / sum(stages.values())}
     if dom in flops:
         roof["achieved"] = flops[dom] / (stages[dom] * 1e-3) / 1e12
         roof["frac"] = roof["achieved"] / pk["bf16_tflops"]
@@ -720,11 +815,9 @@ def main():
         "metric": "bpr_train_samples_per_s", "value": value, "unit": "samples/s", "n_gpus": 1, "steps": K, "warmup": args.warmup,
         "ms_per_step": r["total_ms"] / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic",
-        "config": {"workload": "C2: two-tower BPR training step, batch 8192, ML-1M-shape tables 6041x64 / 3953x64, H=128, "
-                               "sampled negatives + bpr_loss, dropout 0.1, clip_grad_norm_ 1.0, Adam wd 1e-5 (dense: every row "
-                               "updated, reference-exact)",
-                   "l2": "flushed between timed steps (256 MiB write); per-step CUDA events", "api": "FusedBPRTrainer (CUDA graph)",
-                   "tower_mode": "tcgen05 3xTF32 (fp32-grade)"},
+        "config": dict(C2_CONFIG),
+        "config_detail": {"l2": "flushed between timed steps (256 MiB write); per-step CUDA events", "api": "FusedBPRTrainer (CUDA graph)",
+                          "tower_mode": "tcgen05 3xTF32 (fp32-grade), activations as the TMEM A operand (csrc/tower_ts.cu)"},
         "e2e": {"value": e2e, "unit": "samples/s", "h2d_bytes_per_step": r["h2d"], "d2h_bytes_per_step": 4,
                 "ms_per_step": r["pipe_s"] / K * 1e3, "mean_loss": r["epoch_loss"],
                 "api": "FusedBPRTrainer.train_epoch(pinned host batches): the reference's train_epoch loop "
@@ -750,14 +843,19 @@ def main():
         line["hbm_kernels"] = bench_hbm_kernels(dev)
     if not args.skip_flat:
         line["c5_shard"] = bench_flat(args, dev)
+    if not args.skip_c4:
+        # BASELINE C4 at world 1 with the per-rank batch of the N > 1 lines (their headline): the N = 1 point of the C4 scaling curve
+        import bench_sharded as BS
+        torch.cuda.empty_cache()
+        line["c4"] = BS.bench_c4(min(K, 50), args.warmup, dev, 0, 1)
     if not args.skip_ivf:
         line["serving_c1"] = bench_serving(dev)
     if not args.skip_cpu:
         cores = os.cpu_count() or 1
-        v, ms = cpu_step_throughput(20, 3, cores)
-        line["cpu_baseline"] = {"value": v, "unit": "samples/s", "cores": cores, "kind": "port", "ms_per_step": ms,
-                                "sample": f"20 full steps of batch {B} after 3 warm-up (oracle/torch_step.py: the reference's own "
-                                          f"PyTorch calls, torch {torch.__version__} CPU, {cores} threads, dropout on)"}
+        v, ms, kind = cpu_step_throughput(20, 3, cores)
+        line["cpu_baseline"] = {"value": v, "unit": "samples/s", "cores": cores, "kind": kind, "ms_per_step": ms,
+                                "sample": f"20 full steps of batch {B} after 3 warm-up ({_ref_how(kind)}; torch {torch.__version__} "
+                                          f"CPU, {cores} threads, dropout on)"}
         if not args.skip_ivf:
             try:
                 line["ivf"]["cpu_baseline"] = bench_ivf_cpu()

@@ -250,19 +250,30 @@ class FAISSIndex:
         return self._search_normalised(query_vectors, k)                # padding slots already carry id -1
 
     # ---- persistence (faiss_index.py:159-205) ---------------------------------------------- #
-    def save(self, path: str) -> None:
-        """``path`` holds the index (own binary format: magic + npz of centroids / offsets / list ids /
-        list vectors); ``path.with_suffix('.meta.pkl')`` is the same pickle sidecar the reference writes."""
+    def save(self, path: str, file_format: str = "faiss") -> None:
+        """``path`` holds the index in FAISS's own on-disk format — what ``faiss.write_index(IndexIVFFlat)`` writes at
+        faiss_index.py:164 ("IwFl": flat IP quantizer + array inverted lists, ``faiss_io.py``) — so index files move between the
+        reference and this package in both directions; ``path.with_suffix('.meta.pkl')`` is the same pickle sidecar the
+        reference writes.  ``file_format='rb200'`` writes round 1's private container (still readable by ``load``)."""
         if self.index is None:
             raise RuntimeError("Index not built.")
+        if file_format not in ("faiss", "rb200"):
+            raise ValueError("file_format must be 'faiss' or 'rb200'")
         save_path = Path(path)
         save_path.parent.mkdir(parents=True, exist_ok=True)
         st = self.index
         with open(save_path, "wb") as f:
-            f.write(_MAGIC)
-            np.savez(f, centroids=st.centroids.cpu().numpy(), offsets=st.offsets.cpu().numpy(),
-                     list_ids=st.list_ids.cpu().numpy(), list_vecs=st.list_vecs.cpu().numpy(),
-                     dims=np.array([st.d, st.nlist, st.ntotal, st.max_list_len], dtype=np.int64))
+            if file_format == "faiss":
+                from . import faiss_io
+                faiss_io.write_ivfflat(f, faiss_io.IVFFlatData(
+                    d=st.d, nlist=st.nlist, nprobe=max(1, int(st.nprobe)), metric_type=faiss_io.METRIC_INNER_PRODUCT,
+                    centroids=st.centroids.cpu().numpy(), offsets=st.offsets.cpu().numpy(), list_ids=st.list_ids.cpu().numpy(),
+                    list_vecs=st.list_vecs.cpu().numpy(), is_trained=True))
+            else:
+                f.write(_MAGIC)
+                np.savez(f, centroids=st.centroids.cpu().numpy(), offsets=st.offsets.cpu().numpy(),
+                         list_ids=st.list_ids.cpu().numpy(), list_vecs=st.list_vecs.cpu().numpy(),
+                         dims=np.array([st.d, st.nlist, st.ntotal, st.max_list_len], dtype=np.int64))
         with open(save_path.with_suffix(".meta.pkl"), "wb") as f:
             pickle.dump({"item_ids": self.item_ids, "item_id_to_faiss_idx": self._item_id_to_faiss_idx,
                          "embed_dim": self.embed_dim, "n_lists": self.n_lists, "n_probe": self.n_probe}, f)
@@ -270,6 +281,8 @@ class FAISSIndex:
 
     @classmethod
     def load(cls, path: str) -> "FAISSIndex":
+        """Reads an index file written by this class OR by the reference (``faiss.write_index`` of its IndexIVFFlat) plus the
+        ``.meta.pkl`` sidecar both write (faiss_index.py:184-197)."""
         load_path = Path(path)
         if not load_path.exists():
             raise FileNotFoundError(f"FAISS index not found at {load_path}")
@@ -277,18 +290,30 @@ class FAISSIndex:
             meta = pickle.load(f)
         obj = cls(embed_dim=meta["embed_dim"], n_lists=meta["n_lists"], n_probe=meta["n_probe"])
         dev = _device()
+        from . import faiss_io
         with open(load_path, "rb") as f:
-            if f.read(len(_MAGIC)) != _MAGIC:
-                raise RB200Error(f"{load_path} is not a recommendit_b200 IVF index file")
-            z = np.load(f)
-            d, nlist, ntotal, mx = (int(v) for v in z["dims"])
-            st = _IVFState(d, nlist, meta["n_probe"])
-            st.centroids = torch.as_tensor(z["centroids"], device=dev)
-            st.offsets = torch.as_tensor(z["offsets"], device=dev)
-            st.list_ids = torch.as_tensor(z["list_ids"], device=dev)
-            st.list_vecs = torch.as_tensor(z["list_vecs"], device=dev)
-            st.ntotal, st.is_trained = ntotal, True
-            st.finalize()
+            head = f.read(len(_MAGIC))
+            f.seek(0)
+            if head == _MAGIC:
+                f.read(len(_MAGIC))
+                z = np.load(f)
+                d, nlist, ntotal, mx = (int(v) for v in z["dims"])
+                cen, off, lid, lvec = z["centroids"], z["offsets"], z["list_ids"], z["list_vecs"]
+            elif head[:4] == b"IwFl":
+                x = faiss_io.read_ivfflat(f)
+                if x.metric_type != faiss_io.METRIC_INNER_PRODUCT:
+                    raise RB200Error(f"{load_path}: the index uses metric {x.metric_type}; this class serves inner-product indexes")
+                d, nlist, ntotal = x.d, x.nlist, x.ntotal
+                cen, off, lid, lvec = x.centroids, x.offsets, x.list_ids, x.list_vecs
+            else:
+                raise RB200Error(f"{load_path} is neither a FAISS IndexIVFFlat file ('IwFl') nor a recommendit_b200 IVF index file")
+        st = _IVFState(d, nlist, meta["n_probe"])                          # nprobe from the sidecar, as faiss_index.py:197
+        st.centroids = torch.as_tensor(np.ascontiguousarray(cen, dtype=np.float32), device=dev)
+        st.offsets = torch.as_tensor(np.ascontiguousarray(off, dtype=np.int64), device=dev)
+        st.list_ids = torch.as_tensor(np.ascontiguousarray(lid, dtype=np.int64), device=dev)
+        st.list_vecs = torch.as_tensor(np.ascontiguousarray(lvec, dtype=np.float32), device=dev)
+        st.ntotal, st.is_trained = ntotal, True
+        st.finalize()
         obj.index = st
         obj.item_ids = meta["item_ids"]
         obj._item_id_to_faiss_idx = meta["item_id_to_faiss_idx"]

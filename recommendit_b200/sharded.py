@@ -442,18 +442,21 @@ class ShardedBPRTrainer:
             self._marks.append((name, e))
 
     def profile_stages(self, user_ids, pos_ids, pos_genres, neg_ids, neg_genres, reps: int = 5) -> Dict[str, float]:
-        """Device time of each phase of the step (ms, mean of ``reps`` eager steps with CUDA events at the phase boundaries).
-        The steps are real optimiser steps.  Eager launches: read the SHARES, the graph replay is faster than the sum."""
-        acc: Dict[str, float] = {}
-        for _ in range(reps):
+        """Time between CUDA events at the phase boundaries of EAGER steps (ms, median of ``reps`` after one untimed step that
+        lets the eager allocator pool grow).  The steps are real optimiser steps.  Eager launches include the host's enqueue
+        time wherever the device runs ahead of it: read the SHARES; the graph replay is faster than the sum."""
+        acc: Dict[str, list] = {}
+        for rep in range(reps + 1):
             self._marks = []
             self._mark("begin")
             self._step(user_ids, pos_ids, pos_genres, neg_ids, neg_genres)
             marks, self._marks = self._marks, None
             torch.cuda.synchronize(self.dev)
+            if rep == 0:
+                continue
             for (_, a), (name, b) in zip(marks[:-1], marks[1:]):
-                acc[name] = acc.get(name, 0.0) + a.elapsed_time(b) / reps
-        return acc
+                acc.setdefault(name, []).append(a.elapsed_time(b))
+        return {k: float(sorted(v)[len(v) // 2]) for k, v in acc.items()}
 
     def _step(self, user_ids, pos_ids, pos_genres, neg_ids, neg_genres) -> torch.Tensor:
         ops, D, H, E, W = self.ops, self.D, self.H, self.E, self.world
@@ -604,3 +607,92 @@ def sharded_flat_search(queries: torch.Tensor, local_db: torch.Tensor, k: int, i
     dist.all_gather(ss, s.contiguous(), group=group)
     dist.all_gather(ii, i.contiguous(), group=group)
     return merge(torch.stack(ss), torch.stack(ii))
+
+
+# --------------------------------------------------------------------------------------------------------- #
+# sharded IVFFlat retrieval (SURVEY.md §8e "IVF (C3 scaled)")
+# --------------------------------------------------------------------------------------------------------- #
+class ShardedIVFIndex:
+    """IVFFlat over a database whose ROWS are sharded across the ranks: every rank holds all centroids and its slice of every
+    inverted list (a complete ``FAISSIndex`` over its own rows, built on the shared coarse quantizer).  A query batch is
+    replicated; every rank scans its slices of the probed lists, takes its local top-k, the ``(score, item id)[nq, k]`` lists
+    are all-gathered over NCCL and merged (``rb200_topk_merge``), so every rank ends with the same global result.
+
+    With the same centroids the union of the shards' candidates of a query is exactly the candidate set of the unsharded
+    index (the probed lists depend only on the query and the centroids), hence the result equals the unsharded search except for
+    the order of exact-score ties.  Shards must be ordered by rank (rank r's rows before rank r+1's) so that ties resolve to
+    the earlier row, as in the unsharded scan.
+
+    ``index_factory`` / ``merge`` are parameters only so that the host logic can run on CPU/gloo in the tests with stand-ins
+    built on the oracle; the product uses ``FAISSIndex`` and ``topk_merge`` (C ABI)."""
+
+    def __init__(self, embed_dim: int = 64, n_lists: int = 100, n_probe: int = 10, group=None, index_factory=None, merge=None):
+        from .faiss_index import FAISSIndex, topk_merge
+        self.embed_dim, self.n_lists, self.n_probe = embed_dim, n_lists, n_probe
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self._factory = index_factory or (lambda: FAISSIndex(embed_dim, n_lists, n_probe))
+        self._merge = merge or topk_merge
+        self.local = None
+        self.ntotal = 0
+
+    def build(self, local_embeddings, local_item_ids, centroids=None) -> None:
+        """``local_embeddings`` f32 [n_local, D] (host) = this rank's rows; ``centroids`` [n_lists, D] shared by all ranks —
+        when omitted, rank 0 trains the coarse quantizer on its own rows (spherical k-means on the device) and broadcasts it."""
+        import numpy as np
+        x = np.ascontiguousarray(local_embeddings, dtype=np.float32)
+        if centroids is None:
+            dev = torch.device("cuda", torch.cuda.current_device())
+            if self.rank == 0:
+                trainer = self._factory()
+                trainer.build_ivf_index(x, list(local_item_ids))
+                cen = trainer.index.centroids.clone()
+                del trainer
+            else:
+                cen = torch.empty(self.n_lists, self.embed_dim, dtype=torch.float32, device=dev)
+            if self.world > 1:
+                dist.broadcast(cen, src=0, group=self.group)
+            centroids = cen.cpu().numpy()
+        self.local = self._factory()
+        self.local.build_ivf_index(x, list(local_item_ids), centroids=np.ascontiguousarray(centroids, dtype=np.float32))
+        n = torch.tensor([len(local_item_ids)], dtype=torch.int64, device=self._dev())
+        if self.world > 1:
+            dist.all_reduce(n, group=self.group)
+        self.ntotal = int(n.item())
+
+    def _dev(self):
+        st = getattr(self.local, "index", None)
+        cen = getattr(st, "centroids", None)
+        return cen.device if isinstance(cen, torch.Tensor) else torch.device("cpu")
+
+    def set_n_probe(self, n_probe: int) -> None:
+        self.n_probe = n_probe
+        self.local.set_n_probe(n_probe)
+
+    def search_device(self, queries: torch.Tensor, k: int = 500) -> Tuple[torch.Tensor, torch.Tensor]:
+        """queries: L2-normalised f32 [nq, D] on this rank's device, the same on every rank → (scores [nq, k], item ids [nq, k]),
+        -FLT_MAX / -1 padded, identical on every rank."""
+        st = self.local.index
+        kk = min(k, max(st.ntotal, 1))
+        s, i = st.search_device(queries, kk, id_table=self.local._list_item_ids)
+        if kk < k:                                               # a shard with fewer than k rows: pad to the common width
+            pad_s = torch.full((s.shape[0], k - kk), -3.4028234663852886e38, dtype=s.dtype, device=s.device)
+            pad_i = torch.full((s.shape[0], k - kk), -1, dtype=i.dtype, device=i.device)
+            s, i = torch.cat([s, pad_s], 1), torch.cat([i, pad_i], 1)
+        if self.world == 1:
+            return s, i
+        ss = [torch.empty_like(s) for _ in range(self.world)]
+        ii = [torch.empty_like(i) for _ in range(self.world)]
+        dist.all_gather(ss, s.contiguous(), group=self.group)
+        dist.all_gather(ii, i.contiguous(), group=self.group)
+        return self._merge(torch.stack(ss), torch.stack(ii))
+
+    def batch_search(self, query_vectors, k: int = 500):
+        """host queries (any norm) → host (scores, item ids): ``FAISSIndex.batch_search`` semantics over the whole database"""
+        import numpy as np
+        from .faiss_index import _normalize_device
+        dev = self._dev()
+        q = _normalize_device(torch.as_tensor(np.ascontiguousarray(query_vectors, dtype=np.float32), device=dev))
+        s, i = self.search_device(q, min(k, self.ntotal))
+        return s.cpu().numpy(), i.cpu().numpy()

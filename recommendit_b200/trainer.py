@@ -365,6 +365,8 @@ class DataParallelBPRTrainer(FusedBPRTrainer):
         torch.distributed.all_reduce(dp_grads)                                   # NCCL over NVLink
         rb200_bpr_apply (Σg² → clip → Adam on every parameter, as torch.optim.Adam on dense grads does)
 
+    — all three captured in ONE CUDA graph after two eager steps (call ``close()`` before ``destroy_process_group()``).
+
     The result equals the single-process step on the concatenated global batch (mean loss over world·B samples).
     Parameters are broadcast from rank 0 at construction.  Huge tables use ``sharded.ShardedBPRTrainer`` instead."""
 
@@ -389,7 +391,11 @@ class DataParallelBPRTrainer(FusedBPRTrainer):
         self._dp_buf = torch.zeros(n + 4, dtype=torch.float32, device=self.dev)
         self.dp_grads = self._dp_buf[:n]
         self.loss_sum = self._dp_buf[n:n + 1]
-        self._graph_b = None
+        self._eager_dp = 0
+
+    def close(self) -> None:
+        """Release the captured step: a CUDA graph that holds NCCL nodes must be gone before ``destroy_process_group()``."""
+        self._graph = None
 
     def _make_params(self) -> StepParams:
         p = super()._make_params()
@@ -401,7 +407,7 @@ class DataParallelBPRTrainer(FusedBPRTrainer):
     def _phase(self, which: int) -> None:
         if not self._is_flat():
             self._flatten()
-            self._graph = self._graph_b = None
+            self._graph = None
         p = self._make_params()
         self._params = p
         fn = self.lib.rb200_bpr_step if which == 0 else self.lib.rb200_bpr_apply
@@ -419,23 +425,19 @@ class DataParallelBPRTrainer(FusedBPRTrainer):
             raise RB200Error("no batch staged: call load_batch()/step_host() first")
         with torch.cuda.device(self.dev):
             key = (self._B, self.model.user_tower.dropout_p if self.model.training else 0.0)
-            use_graph = self.use_graph and self._warm_key == key
+            use_graph = self.use_graph and self._warm_key == key and self._eager_dp >= 2
             if use_graph and self._graph is None:
+                # the whole step — both halves AND the NCCL all-reduce between them — is ONE graph (round 1 replayed two graphs
+                # with an eagerly issued all-reduce in between: three host launches and a serial collective per step)
                 g = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(g):
-                    self._phase(0)
+                    self._whole()
                 self._graph = g
-                g2 = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(g2):
-                    self._phase(1)
-                self._graph_b = g2
             if use_graph:
                 self._graph.replay()
-                if self.world > 1:
-                    self.dist.all_reduce(self._dp_buf, group=self.group)
-                self._graph_b.replay()
             else:
-                self._whole()
+                self._whole()             # two eager steps first: communicator, kernel attributes and allocator warm up
+                self._eager_dp = self._eager_dp + 1 if self._warm_key == key else 1
             self._warm_key = key
         self._steps_done += 1
         return self.loss_sum

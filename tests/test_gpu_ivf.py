@@ -248,3 +248,79 @@ def test_retrieval_quality_harness_ivf_vs_exact():
         reports[nprobe] = retrieval_report(torch.from_numpy(ids).cuda(), exact, ks=(10, 100))
     assert reports[64]["recall@100"] > 0.999 and reports[64]["ndcg@10"] > 0.999, reports
     assert 0.1 < reports[4]["recall@100"] < 1.0 and reports[4]["recall@10"] >= reports[4]["recall@100"] - 0.05, reports
+
+
+def test_index_files_are_faiss_files_and_both_formats_load(tmp_path):
+    """save() writes FAISS's own IndexIVFFlat format (faiss_index.py:164 → faiss_io.py); load() reads it and round 1's private
+    container; a FAISS file assembled by hand (the layout restated independently in tests/test_faiss_io.py) loads and searches."""
+    import recommendit_b200 as R
+    from recommendit_b200 import faiss_io
+    rng = np.random.default_rng(123)
+    x = V.normalize_rows(rng.standard_normal((500, 32)).astype(np.float32))
+    ids = list(range(100, 600))
+    idx = R.FAISSIndex(32, 10, 5)
+    idx.build_ivf_index(x, ids)
+    q = V.normalize_rows(rng.standard_normal((20, 32)).astype(np.float32))
+    s0, i0 = idx.batch_search(q, 50)
+    for fmt in ("faiss", "rb200"):
+        p = tmp_path / f"{fmt}.index"
+        idx.save(str(p), file_format=fmt)
+        assert (faiss_io.sniff(p) == b"IwFl") == (fmt == "faiss")
+        assert p.with_suffix(".meta.pkl").exists()
+        back = R.FAISSIndex.load(str(p))
+        s1, i1 = back.batch_search(q, 50)
+        assert np.array_equal(i0, i1) and np.array_equal(s0, s1)
+        assert back.stats() == idx.stats()
+    # the parsed file holds exactly the CSR lists of the index, with FAISS's internal ids (sequential add order)
+    with open(tmp_path / "faiss.index", "rb") as f:
+        d = faiss_io.read_ivfflat(f)
+    st = idx.index
+    assert np.array_equal(d.offsets, st.offsets.cpu().numpy()) and np.array_equal(d.list_ids, st.list_ids.cpu().numpy())
+    assert np.array_equal(d.list_vecs, st.list_vecs.cpu().numpy()) and np.array_equal(d.centroids, st.centroids.cpu().numpy())
+    assert sorted(d.list_ids.tolist()) == list(range(500)) and d.nprobe == 5 and d.metric_type == 0
+    for l in range(10):                               # insertion order inside a list = ascending internal id
+        seg = d.list_ids[d.offsets[l]:d.offsets[l + 1]]
+        assert np.all(np.diff(seg) > 0)
+
+
+def test_real_faiss_cross_check(tmp_path):
+    """Runs only where the real library exists (`faiss-cpu>=1.7.4`, requirements.txt:2; absent from this image): pins the IVF
+    oracle and the file format to FAISS itself — centroids harvested from a trained IndexIVFFlat, ids compared directly, files
+    exchanged in both directions."""
+    faiss = pytest.importorskip("faiss")
+    import recommendit_b200 as R
+    rng = np.random.default_rng(123)                  # the reference's own fixture: tests/test_models.py:155-166
+    x = V.normalize_rows(rng.standard_normal((500, 32)).astype(np.float32))
+    ids = list(range(500))
+    quant = faiss.IndexFlatIP(32)
+    fi = faiss.IndexIVFFlat(quant, 32, 10, faiss.METRIC_INNER_PRODUCT)
+    fi.nprobe = 5
+    fi.train(x); fi.add(x)
+    cen = quant.reconstruct_n(0, 10)
+    q = V.normalize_rows(rng.standard_normal((50, 32)).astype(np.float32))
+    fs, fids = fi.search(q, 50)
+    # (1) same centroids → same neighbours (ids identical except exact-score ties)
+    idx = R.FAISSIndex(32, 10, 5)
+    idx.build_ivf_index(x, ids, centroids=cen)
+    s, i = idx.batch_search(q, 50)
+    V.assert_topk_equivalent(s, i, fs, fids)
+    # … and the CPU oracle agrees with FAISS too: the restatement is pinned
+    off, order = V.build_lists(V.assign(x, cen), 10)
+    so, io_ = V.ivf_search(q, cen, off, order, x, 5, 50)
+    V.assert_topk_equivalent(so, io_, fs, fids)
+    # (2) a file written by FAISS loads here
+    import pickle
+    p = tmp_path / "from_faiss.index"
+    faiss.write_index(fi, str(p))
+    with open(p.with_suffix(".meta.pkl"), "wb") as f:
+        pickle.dump({"item_ids": np.array(ids), "item_id_to_faiss_idx": {i: i for i in ids}, "embed_dim": 32, "n_lists": 10, "n_probe": 5}, f)
+    back = R.FAISSIndex.load(str(p))
+    s2, i2 = back.batch_search(q, 50)
+    V.assert_topk_equivalent(s2, i2, fs, fids)
+    # (3) a file written here loads in FAISS
+    p2 = tmp_path / "to_faiss.index"
+    idx.save(str(p2))
+    fi2 = faiss.read_index(str(p2))
+    fi2.nprobe = 5
+    fs2, fids2 = fi2.search(q, 50)
+    V.assert_topk_equivalent(fs2, fids2, fs, fids)

@@ -144,3 +144,73 @@ def test_sharded_flat_search_equals_unsharded():
     s_ref, i_ref = V.flat_search(qv, x, 50)
     np.testing.assert_array_equal(i, i_ref)            # incl. the cross-shard tie: lower id first
     np.testing.assert_allclose(s, s_ref, rtol=0, atol=1e-6)
+
+
+class _OracleIVF:
+    """CPU stand-in for FAISSIndex (the surface ShardedIVFIndex uses), arithmetic from oracle/ivf_oracle.py."""
+
+    class _State:
+        pass
+
+    def __init__(self, d, nlist, nprobe):
+        self.d, self.nlist, self.nprobe = d, nlist, nprobe
+        self.index = None
+
+    def build_ivf_index(self, x, ids, centroids=None):
+        xn = V.normalize_rows(np.asarray(x, np.float32))
+        cen = V.spherical_kmeans(xn, self.nlist) if centroids is None else np.asarray(centroids, np.float32)
+        off, order = V.build_lists(V.assign(xn, cen), self.nlist)
+        st = self._State()
+        st.centroids, st.ntotal = torch.from_numpy(cen), len(ids)
+        ids = np.asarray(ids, np.int64)
+
+        def search_device(q, k, id_table=None):
+            s, r = V.ivf_search(q.numpy(), cen, off, order, xn, self.nprobe, k)
+            return torch.from_numpy(s), torch.from_numpy(np.where(r >= 0, ids[np.maximum(r, 0)], -1))
+        st.search_device = search_device
+        self.index, self._list_item_ids = st, None
+
+    def set_n_probe(self, n):
+        self.nprobe = n
+
+
+def _ivf_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from recommendit_b200.sharded import ShardedIVFIndex
+        from tests.oracle_ops import topk_merge_cpu
+        rng = np.random.default_rng(5)
+        x = V.normalize_rows(rng.standard_normal((2400, 32)).astype(np.float32))
+        x[1900] = x[17]                                                    # an exact tie across the two shards
+        ids = np.arange(1000, 3400)
+        cen = V.spherical_kmeans(x, 12)
+        qv = V.normalize_rows(rng.standard_normal((7, 32)).astype(np.float32)); qv[0] = x[17]
+        lo, hi = (0, 1200) if rank == 0 else (1200, 2400)
+        sh = ShardedIVFIndex(32, 12, 4, index_factory=lambda: _OracleIVF(32, 12, 4), merge=topk_merge_cpu)
+        sh.build(x[lo:hi], ids[lo:hi], centroids=cen)
+        assert sh.ntotal == 2400
+        s, i = sh.search_device(torch.from_numpy(qv), 60)
+        if rank == 1:
+            q.put((s.numpy(), i.numpy(), x, ids, cen, qv))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_sharded_ivf_search_equals_unsharded():
+    """Row-sharded IVFFlat (every rank: all centroids + its slice of every list; per-shard top-k → all-gather → merge) equals the
+    unsharded IVF search on the same centroids, cross-shard tie included."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_ivf_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    s, i, x, ids, cen, qv = q.get(timeout=240)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    off, order = V.build_lists(V.assign(x, cen), 12)
+    s_ref, r_ref = V.ivf_search(qv, cen, off, order, x, 4, 60)
+    np.testing.assert_array_equal(i, np.where(r_ref >= 0, ids[np.maximum(r_ref, 0)], -1))
+    np.testing.assert_allclose(s, s_ref, rtol=0, atol=1e-6)
