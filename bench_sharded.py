@@ -25,6 +25,7 @@ import torch.distributed as dist
 NU4, NI4, D4, H4, E4 = 10_000_000, 1_000_000, 128, 128, 18
 DROPOUT4 = 0.1
 CAPACITY_FACTOR = 1.5
+EXCHANGE = os.environ.get("RB200_C4_EXCHANGE", "p2p")      # "p2p" (peer memory over NVLink) or "padded" (NCCL all-to-alls)
 
 
 def _dist_on() -> bool:
@@ -68,10 +69,22 @@ def c4_config(world: int, B: int = 8192):
                         f"{world * B}), ids Zipf(1.05) users / uniform items, sampled negatives + bpr_loss, dropout {DROPOUT4}, "
                         "clip_grad_norm_ 1.0, Adam wd 1e-5 on the touched rows (rows mode: the dense reference-exact update "
                         "would move all 11M rows, 33.8 GB per step — DESIGN.md §5)",
-            "parallelism": (f"row-sharded x{world}: NCCL all-to-all of ids / rows / row gradients + all-reduce of the MLP gradients "
-                            f"and of {{sum g^2, loss}}; fixed-capacity exchange buckets ({cap} rows per rank pair = "
-                            f"{CAPACITY_FACTOR}x the mean), no host synchronisation: the whole step incl. the collectives is ONE "
-                            "CUDA-graph replay") if world > 1 else "world 1: same code path, no collectives"}
+            "parallelism": _parallelism(world, cap)}
+
+
+def _parallelism(world: int, cap: int) -> str:
+    if world == 1:
+        return "world 1: same code path, no collectives"
+    if EXCHANGE == "p2p":
+        return (f"row-sharded x{world}, peer-memory exchange over NVLink/NVSwitch (torch symmetric memory): every rank READS the rows it "
+                f"needs straight from the owners' shards and WRITES its row gradients into the owners' receive buckets ({cap} rows per "
+                f"rank pair = {CAPACITY_FACTOR}x the mean) — one kernel each, two cross-GPU barriers per step, no collective on the row "
+                "path; NCCL all-reduce only for the MLP gradients (273 KB) and {sum g^2, loss}; no host synchronisation: the whole step "
+                "is ONE CUDA-graph replay")
+    return (f"row-sharded x{world}: NCCL all-to-all of ids / rows / row gradients + all-reduce of the MLP gradients "
+            f"and of {{sum g^2, loss}}; fixed-capacity exchange buckets ({cap} rows per rank pair = "
+            f"{CAPACITY_FACTOR}x the mean), no host synchronisation: the whole step incl. the collectives is ONE "
+            "CUDA-graph replay")
 
 
 def c4_batches(rank: int, B: int, n: int):
@@ -94,7 +107,7 @@ def bench_c4(K: int, W: int, dev, rank: int, world: int, B: int = 8192, strong_g
     from recommendit_b200.sharded import ShardedBPRTrainer
     lib = _lib.load()
     pk = peaks()
-    tr = ShardedBPRTrainer(NU4, NI4, D4, H4, E4, adam_mode="rows", device=dev, seed=11, exchange="padded", capacity_factor=CAPACITY_FACTOR,
+    tr = ShardedBPRTrainer(NU4, NI4, D4, H4, E4, adam_mode="rows", device=dev, seed=11, exchange=EXCHANGE, capacity_factor=CAPACITY_FACTOR,
                            use_cuda_graph=True, dropout=DROPOUT4, check_every=0)
     host = c4_batches(rank, B, 8)
     pinned = [tuple(torch.from_numpy(a).pin_memory() for a in b) for b in host]
@@ -181,7 +194,7 @@ def bench_c4(K: int, W: int, dev, rank: int, world: int, B: int = 8192, strong_g
         "metric": "bpr_train_samples_per_s", "value": value, "unit": "samples/s", "ms_per_step": step_ms, "steps": K, "n_gpus": world,
         "config": c4_config(world, B),
         "config_detail": {"l2": "not flushed: every step gathers 24 576 random rows of a table shard far larger than L2",
-                          "api": "ShardedBPRTrainer(exchange='padded', use_cuda_graph=True).step(device batch)",
+                          "api": f"ShardedBPRTrainer(exchange='{EXCHANGE}', use_cuda_graph=True).step(device batch)",
                           "tower_mode": "tcgen05 3xTF32 (fp32-grade), activations as the TMEM A operand (csrc/tower_ts.cu)",
                           "exchange_capacity_rows": cap, "table_bytes_per_rank": table_bytes},
         "e2e": {"value": world * B * Ke / e2e_s, "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
@@ -204,7 +217,7 @@ def parity_c4(dev, rank: int, world: int):
     NU, NI, B, lr, steps = 10_000, 1_000, 512, 1e-2, 4
     P = O.init_params(NU, NI, D4, H4, seed=5)
     init = {k: torch.from_numpy(v) for k, v in P.items()}
-    tr = ShardedBPRTrainer(NU, NI, D4, H4, E4, adam_mode="dense", device=dev, init=init, lr=lr, exchange="padded", capacity_factor=2.0,
+    tr = ShardedBPRTrainer(NU, NI, D4, H4, E4, adam_mode="dense", device=dev, init=init, lr=lr, exchange=EXCHANGE, capacity_factor=2.0,
                            use_cuda_graph=True, dropout=0.0)
 
     def batch(r, s):

@@ -201,7 +201,8 @@ int rb200_route_plan(const int64_t* user_ids, int64_t n_user, const int64_t* ite
 /* Fixed-capacity form of the same plan (the CUDA-graph-captured sharded step: every all-to-all gets equal, host-known splits, so
  * nothing is read back from the device).  Bucket w of the request list occupies slots [w·capacity, (w+1)·capacity) of a padded
  * buffer: slot_of_sample[i] = slot of request i (sample order), send_rows[world·capacity] = the owner-local row in each slot,
- * -1 in empty slots.  A request that does not fit its bucket gets slot world·capacity - 1 and is counted in *overflow
+ * -1 in empty slots.  A request that does not fit its bucket gets the DUMMY slot world·capacity (one past the buffer: the caller
+ * keeps a zero row there on the way in and drops that gradient row on the way out) and is counted in *overflow
  * (device int64, accumulated — the caller reports it: recommendit_b200/sharded.py check_exchange). */
 size_t rb200_route_plan_padded_workspace_bytes(int64_t n, int world);
 int rb200_route_plan_padded(const int64_t* user_ids, int64_t n_user, const int64_t* item_ids, int64_t n_item, int world,
@@ -212,6 +213,34 @@ int rb200_route_plan_padded(const int64_t* user_ids, int64_t n_user, const int64
  * [0, n_table_rows) yield zeros */
 int rb200_gather_rows(const float* table, const int64_t* rows, int64_t n, int D, int64_t n_table_rows,
                       float* out, void* stream);
+
+/* Peer-memory form of SURVEY.md §8e steps 1-3 and 5 on one NVLink / NVSwitch box: every rank's combined shard (user rows, then
+ * item rows; owner(id) = id % world, local row = id / world) and its gradient receive buckets are mapped into every process
+ * (torch symmetric memory; the caller passes HOST arrays of the `world` device pointers, and user_rows_by_rank — the number of
+ * user rows in each rank's shard — as a HOST array too).  The kernels are collective-free: the
+ * caller brackets them with cross-GPU barriers (recommendit_b200/sharded.py, exchange="p2p").
+ *   gather: out[r,:] = shard[owner(id_r)][local(id_r),:] for the requests in sample order [user ids | item ids] — replaces the id
+ *           all-to-all, the owner-side gather and the row all-to-all.  Ids outside their table read row 0 and set bit 0 of
+ *           *err_flag (may be NULL).
+ *   push:   gradient row r → owner's grad bucket, slot rank·capacity + off, where slot_of_sample[r] = owner·capacity + off comes
+ *           from rb200_route_plan_padded (slot world·capacity = overflowed: dropped); send_rows (the plan's owner-local row per
+ *           slot, -1 = empty) is written to the owners' row buckets alongside — replaces the gradient all-to-all.  Ends with a
+ *           system-scope fence. */
+#define RB200_MAX_PEERS 16
+int rb200_gather_rows_sharded(const void* const* shard_ptrs, const int64_t* user_rows_by_rank, int world,
+                              const int64_t* user_ids, int64_t n_user, const int64_t* item_ids, int64_t n_item,
+                              int64_t n_user_rows, int64_t n_item_rows, int D, float* out, int* err_flag, void* stream);
+int rb200_push_rows_sharded(void* const* grad_bucket_ptrs, void* const* row_bucket_ptrs, int world, int rank, int64_t capacity,
+                            const float* drows, const int64_t* slot_of_sample, int64_t n, int D, const int64_t* send_rows,
+                            void* stream);
+/* Reductions of the same step over peer memory ("ncclAllReduce of MLP grads and of {norm², loss}"),
+ * deterministic and identical on every rank: each rank reads all ranks' buffers and adds them in rank order.
+ *   allreduce_oneshot: out[i] = Σ_k src_ptrs[k][i] (n floats, n % 4 == 0; HOST array of `world` device pointers).
+ *   scalars_publish:   slot[0..3] = {hi(st->sumsq), lo(st->sumsq), loss[0]·scale, 0} (this rank's partial, peer-readable).
+ *   scalars_reduce:    st->sumsq = Σ_k (slot_k[0] + slot_k[1]) in fp64, st->loss = Σ_k slot_k[2].
+ * The caller orders them with cross-GPU barriers (publish → barrier → reduce). */
+int rb200_allreduce_oneshot(const void* const* src_ptrs, int world, int64_t n, float* out, void* stream);
+/* (rb200_sharded_scalars_publish / _reduce are declared below, after rb200_opt_state) */
 
 /* ------------------------------------------------------------------------------------------ *
  * clip_grad_norm_ + Adam — src/training/train_embeddings.py:160,191-192
@@ -235,6 +264,9 @@ typedef struct rb200_opt_state {   /* device-resident, 128 bytes; host fills the
 
 /* step += 1, recompute bias corrections, sumsq = 0 */
 int rb200_opt_begin_step(rb200_opt_state* st, void* stream);
+/* peer-memory reduction of the step's scalars, see rb200_allreduce_oneshot above */
+int rb200_sharded_scalars_publish(const rb200_opt_state* st, const float* loss, float scale, float* slot, void* stream);
+int rb200_sharded_scalars_reduce(const void* const* slot_ptrs, int world, rb200_opt_state* st, void* stream);
 /* sumsq += Σ x² over up to 4 segments.  A segment is n floats at x; when `count` (device int) is
  * set the length is count[0]*row_len instead (compact unique-row gradients) and n is only the
  * capacity used to size the grid.  Deterministic (fixed partition, fixed-order fp64 finalisation). */

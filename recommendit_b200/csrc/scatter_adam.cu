@@ -1039,6 +1039,161 @@ extern "C" int rb200_gather_rows(const float* table, const int64_t* rows, int64_
     return RB200_OK;
 }
 
+// ---------------------------------------------------------------------------------------- //
+// Peer-memory exchange of the row-sharded step (one NVLink / NVSwitch box, tables mapped into every process with
+// torch symmetric memory): the requester READS the rows it needs straight out of the owners' shards and WRITES its row
+// gradients straight into the owners' receive buckets — the gather and its all-to-all, and the all-to-all of the gradients,
+// are one kernel each; no NCCL on the row path.
+// ---------------------------------------------------------------------------------------- //
+struct PeerTables { const float* table[RB200_MAX_PEERS]; long long user_rows[RB200_MAX_PEERS]; };
+struct PeerBuckets { float* grads[RB200_MAX_PEERS]; int64_t* rows[RB200_MAX_PEERS]; };
+
+// out[r] = shard[owner(id_r)][local_row(id_r)], requests in sample order [user ids | item ids]; one warp per 32 float4 of a row
+__global__ void __launch_bounds__(NT) gather_rows_sharded_kernel(const PeerTables P, int world, const int64_t* __restrict__ user_ids,
+                                                                 long long n_u, const int64_t* __restrict__ item_ids, long long n_i,
+                                                                 long long n_user_rows, long long n_item_rows, int D4,
+                                                                 float* __restrict__ out, int* __restrict__ err_flag) {
+    const long long total = (n_u + n_i) * D4, stride = (long long)gridDim.x * NT;
+    for (long long i = (long long)blockIdx.x * NT + threadIdx.x; i < total; i += stride) {
+        const long long r = i / D4;
+        const int c = (int)(i - r * D4);
+        const bool is_user = r < n_u;
+        long long id = is_user ? user_ids[r] : item_ids[r - n_u];
+        if ((unsigned long long)id >= (unsigned long long)(is_user ? n_user_rows : n_item_rows)) {
+            if (err_flag && c == 0) atomicOr(err_flag, 1);
+            id = 0;
+        }
+        const int owner = (int)(id % world);
+        const long long local = id / world + (is_user ? 0 : P.user_rows[owner]);
+        // (plain loads, not the read-only path: the source may be peer memory that other GPUs rewrite between steps)
+        reinterpret_cast<float4*>(out)[i] = *(reinterpret_cast<const float4*>(P.table[owner]) + local * D4 + c);
+    }
+}
+
+// gradient rows (sample order) → bucket (this rank) of their owner's receive buffer, at the slot the exchange plan assigned;
+// the plan's row list (owner-local row per slot, -1 = empty) goes with them.  Requests that overflowed their bucket (slot ==
+// world·C) are dropped (counted by the plan).
+__global__ void __launch_bounds__(NT) push_rows_sharded_kernel(const PeerBuckets P, int world, int rank, long long C,
+                                                               const float* __restrict__ drows, const int64_t* __restrict__ slot_of_sample,
+                                                               long long n, int D4, const int64_t* __restrict__ send_rows) {
+    const long long total = n * D4, stride = (long long)gridDim.x * NT;
+    for (long long i = (long long)blockIdx.x * NT + threadIdx.x; i < total; i += stride) {
+        const long long r = i / D4;
+        const int c = (int)(i - r * D4);
+        const long long slot = slot_of_sample[r];
+        if (slot >= (long long)world * C) continue;
+        const int owner = (int)(slot / C);
+        const long long off = slot - (long long)owner * C;
+        reinterpret_cast<float4*>(P.grads[owner])[((long long)rank * C + off) * D4 + c] = __ldg(reinterpret_cast<const float4*>(drows) + i);
+    }
+    for (long long j = (long long)blockIdx.x * NT + threadIdx.x; j < (long long)world * C; j += stride) {
+        const int owner = (int)(j / C);
+        const long long off = j - (long long)owner * C;
+        P.rows[owner][(long long)rank * C + off] = send_rows[j];
+    }
+    __threadfence_system();          // peer writes ordered before the cross-GPU barrier that follows on the stream
+}
+
+// out[i] = Σ_k src[k][i], k ascending — every rank reads every rank's buffer (peer memory) and adds in the SAME order, so all
+// ranks hold bit-identical sums without a broadcast ("one-shot" all-reduce; the MLP gradients are 273 KB at C4 widths)
+struct PeerSrc { const float* p[RB200_MAX_PEERS]; };
+__global__ void __launch_bounds__(NT) allreduce_oneshot_kernel(const PeerSrc P, int world, long long n4, float* __restrict__ out) {
+    const long long stride = (long long)gridDim.x * NT;
+    for (long long i = (long long)blockIdx.x * NT + threadIdx.x; i < n4; i += stride) {
+        float4 a = *(reinterpret_cast<const float4*>(P.p[0]) + i);
+        for (int k = 1; k < world; ++k) {
+            const float4 v = *(reinterpret_cast<const float4*>(P.p[k]) + i);
+            a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+        }
+        reinterpret_cast<float4*>(out)[i] = a;
+    }
+}
+// this rank's {Σg² of its table-shard gradients (fp64 as a hi/lo float pair), loss·scale} → its 4-float slot (peer-readable)
+__global__ void scalars_publish_kernel(const rb200_opt_state* st, const float* loss, float scale, float* slot) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        const double s = st->sumsq;
+        const float hi = (float)s;
+        slot[0] = hi; slot[1] = (float)(s - (double)hi); slot[2] = loss[0] * scale; slot[3] = 0.f;
+        __threadfence_system();
+    }
+}
+__global__ void scalars_reduce_kernel(const PeerSrc P, int world, rb200_opt_state* st) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        double s = 0.0;
+        float l = 0.f;
+        for (int k = 0; k < world; ++k) {
+            const volatile float* q = P.p[k];
+            s += (double)q[0] + (double)q[1];
+            l += q[2];
+        }
+        st->sumsq = s;
+        st->loss = l;
+    }
+}
+
+extern "C" int rb200_allreduce_oneshot(const void* const* src_ptrs, int world, int64_t n, float* out, void* stream) {
+    RB_REQUIRE(src_ptrs && out && world >= 1 && world <= RB200_MAX_PEERS && n >= 4 && n % 4 == 0, "allreduce_oneshot: n must be a multiple of 4, 1..%d ranks", RB200_MAX_PEERS);
+    PeerSrc P{};
+    for (int k = 0; k < world; ++k) { RB_REQUIRE(src_ptrs[k], "allreduce_oneshot: NULL pointer of rank %d", k); P.p[k] = (const float*)src_ptrs[k]; }
+    allreduce_oneshot_kernel<<<stream_grid(n / 4), NT, 0, (cudaStream_t)stream>>>(P, world, n / 4, out);
+    RB_LAUNCH_CHECK("allreduce_oneshot_kernel");
+    return RB200_OK;
+}
+
+extern "C" int rb200_sharded_scalars_publish(const rb200_opt_state* st, const float* loss, float scale, float* slot, void* stream) {
+    RB_REQUIRE(st && loss && slot, "sharded_scalars_publish: NULL pointer");
+    scalars_publish_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(st, loss, scale, slot);
+    RB_LAUNCH_CHECK("scalars_publish_kernel");
+    return RB200_OK;
+}
+
+extern "C" int rb200_sharded_scalars_reduce(const void* const* slot_ptrs, int world, rb200_opt_state* st, void* stream) {
+    RB_REQUIRE(slot_ptrs && st && world >= 1 && world <= RB200_MAX_PEERS, "sharded_scalars_reduce: 1..%d ranks", RB200_MAX_PEERS);
+    PeerSrc P{};
+    for (int k = 0; k < world; ++k) { RB_REQUIRE(slot_ptrs[k], "sharded_scalars_reduce: NULL pointer of rank %d", k); P.p[k] = (const float*)slot_ptrs[k]; }
+    scalars_reduce_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(P, world, st);
+    RB_LAUNCH_CHECK("scalars_reduce_kernel");
+    return RB200_OK;
+}
+
+extern "C" int rb200_gather_rows_sharded(const void* const* shard_ptrs, const int64_t* user_rows_by_rank, int world,
+                                         const int64_t* user_ids, int64_t n_user, const int64_t* item_ids, int64_t n_item,
+                                         int64_t n_user_rows, int64_t n_item_rows, int D, float* out, int* err_flag, void* stream) {
+    RB_REQUIRE(shard_ptrs && user_rows_by_rank && out && world >= 1 && world <= RB200_MAX_PEERS, "gather_rows_sharded: 1..%d ranks", RB200_MAX_PEERS);
+    RB_REQUIRE(n_user >= 0 && n_item >= 0 && (n_user == 0 || user_ids) && (n_item == 0 || item_ids) && D >= 4 && D % 4 == 0,
+               "gather_rows_sharded: bad arguments");
+    if (n_user + n_item == 0) return RB200_OK;
+    PeerTables P{};
+    for (int k = 0; k < world; ++k) {
+        RB_REQUIRE(shard_ptrs[k], "gather_rows_sharded: NULL shard pointer of rank %d", k);
+        P.table[k] = (const float*)shard_ptrs[k];
+        P.user_rows[k] = user_rows_by_rank[k];
+    }
+    gather_rows_sharded_kernel<<<stream_grid((n_user + n_item) * (D / 4)), NT, 0, (cudaStream_t)stream>>>(
+        P, world, user_ids, n_user, item_ids, n_item, n_user_rows, n_item_rows, D / 4, out, err_flag);
+    RB_LAUNCH_CHECK("gather_rows_sharded_kernel");
+    return RB200_OK;
+}
+
+extern "C" int rb200_push_rows_sharded(void* const* grad_bucket_ptrs, void* const* row_bucket_ptrs, int world, int rank, int64_t capacity,
+                                       const float* drows, const int64_t* slot_of_sample, int64_t n, int D, const int64_t* send_rows,
+                                       void* stream) {
+    RB_REQUIRE(grad_bucket_ptrs && row_bucket_ptrs && world >= 1 && world <= RB200_MAX_PEERS && rank >= 0 && rank < world,
+               "push_rows_sharded: 1..%d ranks", RB200_MAX_PEERS);
+    RB_REQUIRE(drows && slot_of_sample && send_rows && n >= 1 && capacity >= 1 && D >= 4 && D % 4 == 0, "push_rows_sharded: bad arguments");
+    PeerBuckets P{};
+    for (int k = 0; k < world; ++k) {
+        RB_REQUIRE(grad_bucket_ptrs[k] && row_bucket_ptrs[k], "push_rows_sharded: NULL bucket pointer of rank %d", k);
+        P.grads[k] = (float*)grad_bucket_ptrs[k];
+        P.rows[k] = (int64_t*)row_bucket_ptrs[k];
+    }
+    const long long work = n * (D / 4) > (long long)world * capacity ? n * (D / 4) : (long long)world * capacity;
+    push_rows_sharded_kernel<<<stream_grid(work), NT, 0, (cudaStream_t)stream>>>(P, world, rank, capacity, drows, slot_of_sample, n, D / 4,
+                                                                                send_rows);
+    RB_LAUNCH_CHECK("push_rows_sharded_kernel");
+    return RB200_OK;
+}
+
 extern "C" int rb200_opt_begin_step(rb200_opt_state* st, void* stream) {
     RB_REQUIRE(st, "opt_begin_step: NULL state");
     opt_begin_step_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(st);

@@ -165,6 +165,37 @@ class CudaOps:
                                              stream_ptr()), "rb200_gather_rows")
         return out
 
+    def gather_rows_sharded(self, shard_ptrs: List[int], user_rows_by_rank: List[int], user_ids: torch.Tensor, item_ids: torch.Tensor,
+                            n_user_rows: int, n_item_rows: int, D: int, err_flag: Optional[torch.Tensor]) -> torch.Tensor:
+        """out[r] = the row of request r (sample order [users | items]) read straight from its owner's shard through the peer
+        pointers (``rb200_gather_rows_sharded``): no id exchange, no owner-side gather, no row exchange"""
+        W = len(shard_ptrs)
+        n = user_ids.numel() + item_ids.numel()
+        out = torch.empty(n, D, dtype=torch.float32, device=user_ids.device)
+        check(self.lib.rb200_gather_rows_sharded((C.c_void_p * W)(*shard_ptrs), (C.c_int64 * W)(*user_rows_by_rank), W, ptr(user_ids),
+                                                 user_ids.numel(), ptr(item_ids), item_ids.numel(), n_user_rows, n_item_rows, D, ptr(out),
+                                                 ptr(err_flag), stream_ptr()), "rb200_gather_rows_sharded")
+        return out
+
+    def push_rows_sharded(self, grad_ptrs: List[int], row_ptrs: List[int], rank: int, capacity: int, drows: torch.Tensor,
+                          slot: torch.Tensor, send_rows: torch.Tensor) -> None:
+        """gradient rows + the plan's row list → the owners' receive buckets through the peer pointers (``rb200_push_rows_sharded``)"""
+        W = len(grad_ptrs)
+        check(self.lib.rb200_push_rows_sharded((C.c_void_p * W)(*grad_ptrs), (C.c_void_p * W)(*row_ptrs), W, rank, capacity, ptr(drows),
+                                               ptr(slot), drows.shape[0], drows.shape[1], ptr(send_rows), stream_ptr()),
+              "rb200_push_rows_sharded")
+
+    def allreduce_oneshot(self, src_ptrs: List[int], n: int, out: torch.Tensor) -> None:
+        W = len(src_ptrs)
+        check(self.lib.rb200_allreduce_oneshot((C.c_void_p * W)(*src_ptrs), W, n, ptr(out), stream_ptr()), "rb200_allreduce_oneshot")
+
+    def scalars_publish(self, opt: torch.Tensor, loss: torch.Tensor, scale: float, slot: torch.Tensor) -> None:
+        check(self.lib.rb200_sharded_scalars_publish(ptr(opt), ptr(loss), scale, ptr(slot), stream_ptr()), "rb200_sharded_scalars_publish")
+
+    def scalars_reduce(self, slot_ptrs: List[int], opt: torch.Tensor) -> None:
+        W = len(slot_ptrs)
+        check(self.lib.rb200_sharded_scalars_reduce((C.c_void_p * W)(*slot_ptrs), W, ptr(opt), stream_ptr()), "rb200_sharded_scalars_reduce")
+
     def towers_fwd(self, jobs: List[dict], D: int, H: int, drop_p: float, seed: int, offset: int, offset_dev=None) -> None:
         """``offset_dev``: device int64 added (× 3) to the dropout offset inside the kernel — the optimizer's step counter, so
         that replays of a captured step draw fresh masks"""
@@ -271,11 +302,12 @@ class ShardedBPRTrainer:
         mask-free).  Masks are drawn in-kernel (Philox) from (seed + 7919·rank, optimizer step).  ``check_every``: padded
         exchange — every that many steps the overflow counter is read back and an overflow raises (0 = only on
         ``check_exchange()``)."""
-        if exchange not in ("exact", "padded"):
-            raise ValueError("exchange must be 'exact' (variable-size all-to-alls, one host sync per step) or 'padded' "
-                             "(fixed-capacity all-to-alls: no host sync, CUDA-graph capturable)")
-        if use_cuda_graph and exchange != "padded":
-            raise ValueError("use_cuda_graph needs exchange='padded' (the exact exchange reads its split sizes on the host)")
+        if exchange not in ("exact", "padded", "p2p"):
+            raise ValueError("exchange must be 'exact' (variable-size all-to-alls, one host sync per step), 'padded' "
+                             "(fixed-capacity all-to-alls: no host sync, CUDA-graph capturable) or 'p2p' (rows read from / gradients "
+                             "written to the owners' memory over NVLink: no collective on the row path, CUDA-graph capturable)")
+        if use_cuda_graph and exchange == "exact":
+            raise ValueError("use_cuda_graph needs exchange='padded' or 'p2p' (the exact exchange reads its split sizes on the host)")
         if not 0.0 <= dropout < 1.0:
             raise ValueError("dropout must be in [0, 1)")
         self.exchange, self.capacity_factor, self.use_graph = exchange, float(capacity_factor), use_cuda_graph
@@ -294,8 +326,23 @@ class ShardedBPRTrainer:
         nu, ni = shard_rows(self.n_user_rows, W, r), shard_rows(self.n_item_rows, W, r)
         # Both shards live in ONE tensor (user rows first, then item rows): a request is a row of the combined shard, so
         # one exchange / gather / scatter / Adam launch serves both tables.  user_table / item_table are views.
-        self.table = torch.empty(nu + ni, embed_dim, **f32)
+        self._symm, self._tab_hdl, self._buckets = None, None, {}
+        self._nu_host = [shard_rows(self.n_user_rows, W, k) for k in range(W)]
+        if exchange == "p2p" and W > 1:
+            # the shard lives in symmetric memory: every rank maps every other rank's shard (NVLink peer access through NVSwitch)
+            import torch.distributed._symmetric_memory as symm_mem
+            self._symm = symm_mem
+            rows_alloc = shard_rows(self.n_user_rows, W, 0) + shard_rows(self.n_item_rows, W, 0)        # the largest shard
+            flat = symm_mem.empty(rows_alloc * embed_dim, dtype=torch.float32, device=self.dev)
+            self._tab_hdl = symm_mem.rendezvous(flat, group if group is not None else dist.group.WORLD)
+            self._tab_flat = flat
+            self.table = flat[: (nu + ni) * embed_dim].view(nu + ni, embed_dim)
+            self._shard_ptrs = [int(p) for p in self._tab_hdl.buffer_ptrs]
+        else:
+            self.table = torch.empty(nu + ni, embed_dim, **f32)
+            self._shard_ptrs = [self.table.data_ptr()] if W == 1 else None
         self.user_table, self.item_table = self.table[:nu], self.table[nu:]
+        self.err_flag = torch.zeros(1, dtype=torch.int32, device=self.dev)
         self._nu_by_rank = torch.tensor([shard_rows(self.n_user_rows, W, k) for k in range(W)], dtype=torch.int64, device=self.dev)
         if init is not None:
             # parity runs: slice a full (single-process) state dict
@@ -334,6 +381,16 @@ class ShardedBPRTrainer:
         self.steps = 0
         self.max_norm = max_norm
         self.overflow = torch.zeros(1, dtype=torch.int64, device=self.dev)     # padded exchange: requests that did not fit
+        self._mlp_sym = None
+        if self._symm is not None:
+            # p2p exchange: the MLP gradients and the step's scalars are reduced over peer memory too (no NCCL inside the step)
+            grp = group if group is not None else dist.group.WORLD
+            n_mlp = (self.user_mlp.numel() + self.item_mlp.numel() + 3) // 4 * 4
+            gm = self._symm.empty(n_mlp, dtype=torch.float32, device=self.dev)
+            sc = self._symm.empty(4, dtype=torch.float32, device=self.dev)
+            gm.zero_(); sc.zero_()
+            hm, hs = self._symm.rendezvous(gm, grp), self._symm.rendezvous(sc, grp)
+            self._mlp_sym = (gm, sc, [int(p) for p in hm.buffer_ptrs], [int(p) for p in hs.buffer_ptrs], (hm, hs))
 
     # views of the flat MLP blocks
     def _mlp_views(self, flat: torch.Tensor, din: int):
@@ -387,6 +444,34 @@ class ShardedBPRTrainer:
             dist.all_to_all_single(recv_rows, send_rows[:W * C].contiguous(), group=self.group)
         return slot_s, recv_rows, C
 
+    def _barrier(self, channel: int) -> None:
+        """cross-GPU barrier on the stream (symmetric-memory signal pads; capturable; traps after 60 s instead of hanging)"""
+        if self._tab_hdl is not None:
+            self._tab_hdl.barrier(channel=channel, timeout_ms=60000)
+
+    def _p2p_buckets(self, n_requests: int):
+        """receive buckets of this rank for batches of ``n_requests`` requests: gradient rows [W·C, D] and owner-local rows [W·C],
+        bucket k written by rank k — symmetric memory when W > 1 (allocated and exchanged once per batch size, collectively)"""
+        Cc = self.capacity(n_requests)
+        if Cc not in self._buckets:
+            W, D = self.world, self.D
+            if self._symm is not None:
+                grp = self.group if self.group is not None else dist.group.WORLD
+                g = self._symm.empty(W * Cc * D, dtype=torch.float32, device=self.dev)
+                r = self._symm.empty(W * Cc, dtype=torch.int64, device=self.dev)
+                hg, hr = self._symm.rendezvous(g, grp), self._symm.rendezvous(r, grp)
+                self._buckets[Cc] = (g.view(W * Cc, D), r, [int(p) for p in hg.buffer_ptrs], [int(p) for p in hr.buffer_ptrs], (hg, hr))
+            else:
+                g = torch.empty(W * Cc, D, dtype=torch.float32, device=self.dev)
+                r = torch.empty(W * Cc, dtype=torch.int64, device=self.dev)
+                self._buckets[Cc] = (g, r, [g.data_ptr()], [r.data_ptr()], None)
+        return self._buckets[Cc]
+
+    def check_ids(self) -> None:
+        """p2p exchange: raise if an id of a past step was outside its table (synchronises)"""
+        if int(self.err_flag.item()) & 1:
+            raise IndexError("an id in a previous batch was outside its embedding table")
+
     def close(self) -> None:
         """Release the captured step.  A CUDA graph that holds NCCL collectives must be gone BEFORE
         ``torch.distributed.destroy_process_group()`` — destroying the communicator under a live graph hangs the process at
@@ -409,7 +494,7 @@ class ShardedBPRTrainer:
         {Σg², loss} pair (all-reduce).  ``exchange='exact'``: variable-size all-to-alls, one host synchronisation (their split
         sizes).  ``exchange='padded'``: fixed-capacity all-to-alls, no host synchronisation; with ``use_cuda_graph`` the whole
         step, collectives included, is one graph replay after two eager steps."""
-        if self.exchange == "padded" and self.check_every > 0 and self.steps > 0 and self.steps % self.check_every == 0:
+        if self.exchange in ("padded", "p2p") and self.check_every > 0 and self.steps > 0 and self.steps % self.check_every == 0:
             self.check_exchange()
         if not self.use_graph:
             return self._step(user_ids, pos_ids, pos_genres, neg_ids, neg_genres)
@@ -464,8 +549,19 @@ class ShardedBPRTrainer:
         dev = user_ids.device
         f32 = dict(dtype=torch.float32, device=dev)
         padded = self.exchange == "padded"
+        p2p = self.exchange == "p2p"
         # steps 1-3: route the ids to their owners, gather there, bring the rows back (bucket order)
-        if padded:
+        if p2p:
+            # peer-memory form: the rows are READ from the owners' shards over NVLink, in sample order — one kernel, no collective.
+            # The barrier orders this read after every rank's Adam of the previous step.
+            item_ids = torch.cat([pos_ids, neg_ids])
+            self._barrier(0)
+            rows = ops.gather_rows_sharded(self._shard_ptrs, self._nu_host, user_ids.contiguous(), item_ids, self.n_user_rows,
+                                           self.n_item_rows, D, self.err_flag)
+            if getattr(self, "_ident", None) is None or self._ident.numel() != 3 * B:
+                self._ident = torch.arange(3 * B, dtype=torch.int64, device=dev)
+            rt = Route(perm=None, inv=self._ident, local_rows=None, send_counts=None, recv_rows=None)
+        elif padded:
             slot, recv_rows, C = self._route_padded(user_ids, torch.cat([pos_ids, neg_ids]))
             served = ops.gather_rows(self.table, recv_rows.clamp(min=0))
             # one row more than the exchange carries: slot W·C is the dummy slot of requests that overflowed their bucket — they
@@ -507,7 +603,8 @@ class ShardedBPRTrainer:
 
         dpre, dact, drows = torch.empty(3 * B, D, **f32), torch.empty(3 * B, H, **f32), torch.empty(3 * B, D, **f32)
         Pu, Pi = self.user_mlp.numel(), self.item_mlp.numel()
-        g_mlp = torch.empty(Pu + Pi, **f32)
+        sym_red = p2p and self._mlp_sym is not None
+        g_mlp = self._mlp_sym[0][:Pu + Pi] if sym_red else torch.empty(Pu + Pi, **f32)     # (peer-readable in the p2p exchange)
         for j, dY, sl in ((jobs[0], du, slice(0, B)), (jobs[1], dp, slice(B, 2 * B)), (jobs[2], dn, slice(2 * B, 3 * B))):
             j.update(dY=dY, dpre=dpre[sl], dact=dact[sl], dRows=drows[sl])
         ops.towers_bwd(jobs[:1], D, H, drop_p, g_mlp[:Pu])
@@ -515,7 +612,16 @@ class ShardedBPRTrainer:
         self._mark("towers_bwd")
 
         # steps 4-5: row gradients (sample order → bucket order) back to the owning shards, deterministic segment sums there
-        if padded:
+        if p2p:
+            # the exchange plan is computed locally (bucket + slot of every request); the gradient rows and the plan's row list are
+            # WRITTEN into the owners' receive buckets over NVLink; the barrier makes them visible before the owners' segment sums
+            C = self.capacity(3 * B)
+            slot, send_rows = ops.route_padded(user_ids.contiguous(), item_ids, W, self._nu_by_rank, C, self.overflow)
+            g_buf, r_buf, g_ptrs, r_ptrs, _ = self._p2p_buckets(3 * B)
+            ops.push_rows_sharded(g_ptrs, r_ptrs, self.rank, C, drows, slot, send_rows)
+            self._barrier(1)
+            g_rows, rt.recv_rows = g_buf, r_buf
+        elif padded:
             g_pad = torch.empty(W * C + 1, D, **f32)               # empty slots are skipped at the owner (their row is -1);
             g_pad.index_copy_(0, rt.inv, drows)                    # row W·C collects the overflowed requests and is not sent
             if W == 1:
@@ -534,20 +640,33 @@ class ShardedBPRTrainer:
         self._mark("grad_exchange")
         uq, ug, n_uq = ops.scatter_rows(rows_sc, g_rows, max(self.table.shape[0], 1), -1)
         self._mark("scatter")
-        if W > 1:
-            dist.all_reduce(g_mlp, group=self.group)                       # Σ over ranks of (1/W)-scaled local gradients
-        # step 6: global gradient norm and mean loss, on the device.  Table shards are disjoint → their Σg² add up; the MLP
-        # gradient is replicated → counted once (on rank 0).
-        segs = [(ug, n_uq, D)]
-        if self.rank == 0:
-            segs.append((g_mlp, None, 0))
-        ops.sumsq(self.opt, segs)
         opt64, opt32 = self.opt.view(torch.float64), self.opt.view(torch.float32)
-        red = torch.cat([opt64[_OPT_SUMSQ_F64:_OPT_SUMSQ_F64 + 1], loss.to(torch.float64) / W])
-        if W > 1:
-            dist.all_reduce(red, group=self.group)
-        opt64[_OPT_SUMSQ_F64:_OPT_SUMSQ_F64 + 1].copy_(red[0:1])
-        opt32[_OPT_LOSS_F32:_OPT_LOSS_F32 + 1].copy_(red[1:2].to(torch.float32))
+        if sym_red:
+            # peer-memory reductions (every rank adds all ranks' buffers in rank order: identical everywhere, no broadcast, no NCCL):
+            # the MLP gradients were complete before barrier 1; the scalars need one more barrier after the local segment sums
+            gm, sc, gm_ptrs, sc_ptrs, _ = self._mlp_sym
+            g_red = torch.empty(gm.numel(), **f32)
+            ops.allreduce_oneshot(gm_ptrs, gm.numel(), g_red)
+            g_mlp = g_red[:Pu + Pi]
+            ops.sumsq(self.opt, [(ug, n_uq, D)])                           # Σg² of this rank's shard rows
+            ops.scalars_publish(self.opt, loss, 1.0 / W, sc)
+            self._barrier(2)
+            ops.scalars_reduce(sc_ptrs, self.opt)                          # opt.sumsq = Σ over shards, opt.loss = global mean loss
+            ops.sumsq(self.opt, [(g_mlp, None, 0)])                        # + the (replicated) MLP gradient, counted once
+        else:
+            if W > 1:
+                dist.all_reduce(g_mlp, group=self.group)                   # Σ over ranks of (1/W)-scaled local gradients
+            # step 6: global gradient norm and mean loss, on the device.  Table shards are disjoint → their Σg² add up; the MLP
+            # gradient is replicated → counted once (on rank 0).
+            segs = [(ug, n_uq, D)]
+            if self.rank == 0:
+                segs.append((g_mlp, None, 0))
+            ops.sumsq(self.opt, segs)
+            red = torch.cat([opt64[_OPT_SUMSQ_F64:_OPT_SUMSQ_F64 + 1], loss.to(torch.float64) / W])
+            if W > 1:
+                dist.all_reduce(red, group=self.group)
+            opt64[_OPT_SUMSQ_F64:_OPT_SUMSQ_F64 + 1].copy_(red[0:1])
+            opt32[_OPT_LOSS_F32:_OPT_LOSS_F32 + 1].copy_(red[1:2].to(torch.float32))
         ops.grad_norm_clip(self.opt)
         self._mark("allreduce_norm_clip")
 

@@ -67,6 +67,21 @@ assert tr_g._graph is not None
 fe, fg = tr_e.full_state(), tr_g.full_state()
 pad_param_diff = max(float((fe[k] - fg[k]).abs().max()) for k in O.PARAM_KEYS)
 tr_g.close()          # a live graph with NCCL nodes would hang destroy_process_group()
+# … and through the peer-memory exchange (rows read from / gradients written to the owners' shards over NVLink, two cross-GPU
+# barriers per step, symmetric memory): eager steps, capture, replays
+tr_e2 = ShardedBPRTrainer(NU, NI, D, H, adam_mode="dense", device=dev, init={k: torch.from_numpy(v) for k, v in P.items()}, lr=1e-2)
+tr_p = ShardedBPRTrainer(NU, NI, D, H, adam_mode="dense", device=dev, init={k: torch.from_numpy(v) for k, v in P.items()}, lr=1e-2,
+                         exchange="p2p", capacity_factor=1.5, use_cuda_graph=True)
+p2p_diff = 0.0
+for s in range(5):
+    b = [torch.from_numpy(a).to(dev) for a in batch(rank, s)]
+    le, lp = float(tr_e2.step(*b)), float(tr_p.step(*b))
+    p2p_diff = max(p2p_diff, abs(le - lp))
+tr_p.check_exchange(); tr_p.check_ids()
+assert tr_p._graph is not None
+fe2, fp = tr_e2.full_state(), tr_p.full_state()
+p2p_param_diff = max(float((fe2[k] - fp[k]).abs().max()) for k in O.PARAM_KEYS)
+tr_p.close()
 # sharded retrieval
 g = torch.Generator().manual_seed(0)
 x = torch.nn.functional.normalize(torch.randn(20000, 64, generator=g), dim=-1)
@@ -83,11 +98,13 @@ def batch2(r, s):
     rng = np.random.default_rng(77 * s + r)
     return (rng.integers(0, 401, 256), rng.integers(0, 301, 256), (rng.random((256, 18)) < .2).astype(np.float32),
             rng.integers(0, 301, 256), (rng.random((256, 18)) < .2).astype(np.float32))
-dp_losses = [float(dp.step_host(*batch2(rank, s))) for s in range(3)]
+dp_losses = [float(dp.step_host(*batch2(rank, s))) for s in range(4)]      # 2 eager + capture (incl. the all-reduce) + replay
 dp_state = {k: v.detach().cpu().numpy() for k, v in m.state_dict().items()}
+assert dp._graph is not None
+dp.close()            # the captured step holds an NCCL node: release it before destroy_process_group()
 if rank == 0:
     S2 = O.AdamState(); dp_ref = []
-    for st in range(3):
+    for st in range(4):
         parts = [batch2(r, st) for r in range(world)]
         gb = tuple(np.concatenate([p[k] for p in parts]) for k in range(5))
         dp_ref.append(float(O.train_step(P2, S2, gb, lr=1e-2)[0]))
@@ -103,19 +120,22 @@ if rank == 0:
     s_ref, i_ref = V.flat_search(q.numpy(), x.numpy(), 100)
     V.assert_topk_equivalent(s.cpu().numpy(), i.cpu().numpy(), s_ref, i_ref)
     print("RESULT " + json.dumps({"losses": losses, "ref": ref, "max_param_err": err, "dp_losses": dp_losses, "dp_ref": dp_ref,
-                                  "dp_err": dp_err, "pad_diff": pad_diff, "pad_param_diff": pad_param_diff}))
+                                  "dp_err": dp_err, "pad_diff": pad_diff, "pad_param_diff": pad_param_diff,
+                                  "p2p_diff": p2p_diff, "p2p_param_diff": p2p_param_diff}))
 dist.barrier(); dist.destroy_process_group()
 '''
 
 
-def test_sharded_world1_padded_graph_equals_exact(golden):
-    """exchange='padded' + use_cuda_graph (the whole step one graph replay) against the exact exchange, world 1."""
+@pytest.mark.parametrize("exchange", ["padded", "p2p"])
+def test_sharded_world1_padded_graph_equals_exact(golden, exchange):
+    """exchange='padded' / 'p2p' + use_cuda_graph (the whole step one graph replay) against the exact exchange, world 1 (p2p at
+    world 1 runs the same gather / push kernels on local pointers, without barriers)."""
     from recommendit_b200.sharded import ShardedBPRTrainer
     g = golden("tt_d128")
     nu, ni, D, H = (int(v) for v in g["meta"][:4])
     init = {k: torch.from_numpy(g["init/" + k]) for k in O.PARAM_KEYS}
     a = ShardedBPRTrainer(nu, ni, D, H, adam_mode="rows", device="cuda", init=init, lr=float(g["lr"]))
-    b = ShardedBPRTrainer(nu, ni, D, H, adam_mode="rows", device="cuda", init=init, lr=float(g["lr"]), exchange="padded",
+    b = ShardedBPRTrainer(nu, ni, D, H, adam_mode="rows", device="cuda", init=init, lr=float(g["lr"]), exchange=exchange,
                           use_cuda_graph=True)
     for s in range(5):
         batch = [dev(x) for x in batch_from_golden(g, s % 2)]
@@ -145,6 +165,7 @@ def test_sharded_world2_nccl_matches_single_process_oracle(tmp_path):
     assert np.allclose(r["dp_losses"], r["dp_ref"], atol=2e-5), r
     assert r["dp_err"] <= 0.5 * 1e-2, r
     assert r["pad_diff"] <= 1e-6 and r["pad_param_diff"] <= 1e-6, r
+    assert r["p2p_diff"] <= 1e-6 and r["p2p_param_diff"] <= 1e-6, r
 
 
 @pytest.mark.parametrize("world,n_u,n_i", [(1, 100, 200), (2, 8192, 16384), (8, 5000, 10001), (3, 0, 77), (64, 300, 0)])
