@@ -20,6 +20,8 @@
 // mode 2 = 3xTF32 (hi/lo split of both operands of both MMAs, fp32-grade), mode 1 = single TF32 (stated fast mode).
 // The tensor core's fp32 accumulation is not round-to-nearest over long chains (see tower_tc.cu), so every Y tile starts
 // a fresh TMEM accumulation that is flushed into fp32 registers.  D = 64 only (the production width).
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "umma.cuh"
 
@@ -356,13 +358,13 @@ template <bool PASS_I>
 __global__ void __launch_bounds__(256) inbatch_finish_kernel(const float* __restrict__ acc_part, const double* __restrict__ r_part,
                                                              float* __restrict__ r_total, const float* __restrict__ other,
                                                              const float* __restrict__ cen, float* __restrict__ out, int B, int Bp,
-                                                             int split) {
+                                                             int split, int nq) {
     const int idx = blockIdx.x * 256 + threadIdx.x;
     const int row = idx >> 4, c4 = idx & 15;
     if (row >= B) return;
     // rs = row sum of this pass's G: r_i in pass U; the column sum q_j = Σ_i G_ij in pass I (whose diagonal term uses r_j)
     double rs = 0.0;
-    for (int s = 0; s < split * NQ; ++s) rs += r_part[(long long)s * Bp + row];
+    for (int s = 0; s < split * nq; ++s) rs += r_part[(long long)s * Bp + row];
     const float q = (float)rs;
     float r = q;
     if (!PASS_I) { if (c4 == 0) r_total[row] = r; }
@@ -418,6 +420,324 @@ __global__ void colsum_final_kernel(const float* __restrict__ part, int B, float
     cen[which * DD + d] = a / (float)B;
 }
 
+// ================================================================================================================ //
+// TMEM-operand, TMA-fed form of the same two passes (default; RB200_INBATCH_TS=0 selects the kernel above)
+//
+//   * the X tile [128 × 64] and the G tile [128 × 64] are the A operands of the two products and live in TMEM (thread = row =
+//     TMEM lane: the epilogue writes G where the tensor core reads it — no shared-memory staging, no transposes);
+//   * the streamed side comes from operand IMAGES built once per call by inbatch_images_kernel — per 64-row tile [Y hi | Y lo |
+//     (Y−c)ᵀ hi | (Y−c)ᵀ lo], 64 KB, already split and in the K-major UMMA layout — fetched by bulk asynchronous copies (TMA
+//     engine) into two 3-slot rings; no thread ever touches a Y element;
+//   * warp-specialised: warp 8 issues copies and MMAs, warps 0-7 run the epilogue (row × 32 columns per thread); every hand-off
+//     is an mbarrier.  Tensor queue: S(0) S(1) | GY(0) S(2) | GY(1) S(3) | … — the epilogue of tile t runs under GY(t−1) and
+//     S(t+1), so the tensor pipe (48 MMAs = 1536 issue cycles per tile) is the critical path, not the B² epilogue.
+//   TMEM (512 columns): X hi|lo [0,128) · S double-buffered [128,256) · G hi|lo [256,384) · acc [384,448).
+// ================================================================================================================ //
+constexpr int NT_EPI2 = 256, NT_TS = NT_EPI2 + 32;
+constexpr int IMG_HALF = YT * DD * 4;            // 16 KB: one of hi / lo of a [64 × 64] operand
+constexpr int IMG_PAIR = 2 * IMG_HALF;           // hi | lo
+constexpr int IMG_TILE = 2 * IMG_PAIR;           // Y pair, then centred-transposed pair: 64 KB per 64-row tile
+constexpr int NSLOT = 3;
+constexpr uint32_t TS_X_HI = 0, TS_X_LO = 64, TS_S = 128, TS_G_HI = 256, TS_G_LO = 320, TS_ACC = 384, TS_COLS = 512;
+constexpr int NQ2 = NT_EPI2 / 128;               // column halves of a tile
+constexpr size_t IB_TS_SMEM = (size_t)2 * NSLOT * IMG_PAIR;      // 192 KB
+
+// images of U (blockIdx.y = 0) and I (1): tile t → img[y][t]; rows past B are zero; cen == NULL: no centring (loss-only calls)
+__global__ void __launch_bounds__(256) inbatch_images_kernel(const float* __restrict__ U, const float* __restrict__ I, int B,
+                                                             const float* __restrict__ cen, unsigned char* __restrict__ img_u,
+                                                             unsigned char* __restrict__ img_i) {
+    const float* X = blockIdx.y ? I : U;
+    unsigned char* img = (blockIdx.y ? img_i : img_u) + (size_t)blockIdx.x * IMG_TILE;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int mq = tid & 15, sq = tid >> 4;          // 4 d-columns (4·mq…) × 4 y-rows (4·sq…)
+    const int y0 = blockIdx.x * YT;
+    const float4 c = cen ? __ldg(reinterpret_cast<const float4*>(cen + blockIdx.y * DD) + mq) : make_float4(0.f, 0.f, 0.f, 0.f);
+    float4 v[4], w[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const long long r = y0 + sq * 4 + i;
+        const bool ok = r < B;
+        v[i] = ok ? __ldg(reinterpret_cast<const float4*>(X + r * DD) + mq) : make_float4(0.f, 0.f, 0.f, 0.f);
+        w[i] = ok ? make_float4(v[i].x - c.x, v[i].y - c.y, v[i].z - c.z, v[i].w - c.w) : make_float4(0.f, 0.f, 0.f, 0.f);
+        put4<2>(img, img + IMG_HALF, YT, sq * 4 + i, mq * 4, v[i]);
+    }
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {                    // transposed, lane-rotated (conflict-free in shared memory; harmless here)
+        const int e = (t + (lane >> 1)) & 3;
+        put4<2>(img + IMG_PAIR, img + IMG_PAIR + IMG_HALF, DD, mq * 4 + e, sq * 4,
+                make_float4(sel4(w[0], e), sel4(w[1], e), sel4(w[2], e), sel4(w[3], e)));
+    }
+}
+
+template <int MODE>
+__device__ __forceinline__ void st16_split(uint32_t hi_addr, uint32_t lo_addr, const float* x) {
+    float hi[16], lo[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) { hi[i] = umma::tf32_hi(x[i]); lo[i] = x[i] - hi[i]; }
+    umma::tmem_st16(hi_addr, hi);
+    if (MODE == 2) umma::tmem_st16(lo_addr, lo);
+}
+
+// D[tmem] = A[tmem, 128 lanes × 64 columns: hi at a_hi, lo at a_lo] · B[64 × 64]ᵀ (shared-memory image: hi, then lo); one thread
+template <int MODE>
+__device__ __forceinline__ void issue_ts64(uint32_t d, uint32_t a_hi, uint32_t a_lo, const unsigned char* b_img) {
+    const uint32_t idesc = umma::idesc_tf32(128, 64);
+    constexpr uint32_t lbo = (64 / 8) * 128;
+    const uint64_t dbh = umma::smem_desc(umma::smem_u32(b_img), lbo, 128), dbl = umma::smem_desc(umma::smem_u32(b_img + IMG_HALF), lbo, 128);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const uint64_t ob = (uint64_t)((2 * j * lbo) >> 4);
+        if (MODE == 2) {
+            umma::mma_tf32_ts(d, a_lo + 8 * j, dbh + ob, idesc, j > 0);
+            umma::mma_tf32_ts(d, a_hi + 8 * j, dbl + ob, idesc, true);
+            umma::mma_tf32_ts(d, a_hi + 8 * j, dbh + ob, idesc, true);
+        } else {
+            umma::mma_tf32_ts(d, a_hi + 8 * j, dbh + ob, idesc, j > 0);
+        }
+    }
+}
+
+struct IbTsParams {
+    const float* X;                      // row-side embeddings [B × 64]
+    const unsigned char* yimg;           // images of the streamed side (IMG_TILE per 64-row tile)
+    const float* diag;
+    int B, split, tiles_per_split, Bp;
+    float g;
+    float* acc_part; double* r_part; double* loss_part;
+    int* err_flag;
+};
+
+template <int MODE, bool PASS_I, bool WITH_GRAD>
+__global__ void __launch_bounds__(NT_TS, 1) inbatch_ts_kernel(const IbTsParams p) {
+    extern __shared__ __align__(1024) unsigned char smem[];
+    unsigned char* ybuf = smem;                              // [NSLOT][IMG_PAIR]   Y images (B operand of S = X·Yᵀ)
+    unsigned char* ytbuf = smem + NSLOT * IMG_PAIR;          // [NSLOT][IMG_PAIR]   (Y−c)ᵀ images (B operand of acc = G·(Y−c))
+    __shared__ __align__(8) uint64_t bar_yfull[NSLOT], bar_ytfull[NSLOT], bar_s[2], bar_gy, bar_e, bar_x;
+    __shared__ uint32_t tmem_slot;
+    __shared__ int dead;
+    __shared__ double red[NT_EPI2 / 32];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if (warp == 0) umma::tmem_alloc(&tmem_slot, TS_COLS);
+    if (tid == NT_EPI2) {
+        for (int i = 0; i < NSLOT; ++i) { umma::mbar_init(&bar_yfull[i], 1); umma::mbar_init(&bar_ytfull[i], 1); }
+        umma::mbar_init(&bar_s[0], 1); umma::mbar_init(&bar_s[1], 1); umma::mbar_init(&bar_gy, 1);
+        umma::mbar_init(&bar_e, NT_EPI2); umma::mbar_init(&bar_x, NT_EPI2);
+        umma::fence_mbar_init();
+        dead = 0;
+    }
+    umma::fence_before_sync();
+    __syncthreads();
+    umma::fence_after_sync();
+    const uint32_t tmem = tmem_slot;
+    const int B = p.B;
+    const int xt = blockIdx.x / p.split, part = blockIdx.x - xt * p.split;
+    const int x0 = xt * XT;
+    const int t_begin = part * p.tiles_per_split;
+    const int n_ytiles = (B + YT - 1) / YT;
+    int t_end = t_begin + p.tiles_per_split;
+    if (t_end > n_ytiles) t_end = n_ytiles;
+    const int nt = t_end - t_begin;
+    constexpr uint32_t Y_COPY = MODE == 2 ? IMG_PAIR : IMG_HALF;
+
+    if (warp == NT_EPI2 / 32) {
+        // ================================ copy + MMA issuer ================================================= //
+        const unsigned char* img0 = p.yimg + (size_t)t_begin * IMG_TILE;
+        if (umma::elect_one()) {
+            for (int j = 0; j < NSLOT && j < nt; ++j) {
+                umma::mbar_expect_tx(&bar_yfull[j], Y_COPY);
+                umma::bulk_g2s(ybuf + j * IMG_PAIR, img0 + (size_t)j * IMG_TILE, Y_COPY, &bar_yfull[j]);
+            }
+            if (WITH_GRAD) {
+                for (int j = 0; j < 2 && j < nt; ++j) {
+                    umma::mbar_expect_tx(&bar_ytfull[j], Y_COPY);
+                    umma::bulk_g2s(ytbuf + j * IMG_PAIR, img0 + (size_t)j * IMG_TILE + IMG_PAIR, Y_COPY, &bar_ytfull[j]);
+                }
+            }
+        }
+        __syncwarp();
+        bool ok = umma::mbar_wait(&bar_x, 0u);                 // X tile staged in TMEM
+        umma::fence_after_sync();
+        for (int j = 0; j < 2 && j < nt && ok; ++j) {
+            ok = umma::mbar_wait(&bar_yfull[j], 0u);
+            if (ok && umma::elect_one()) {
+                issue_ts64<MODE>(tmem + TS_S + j * YT, tmem + TS_X_HI, tmem + TS_X_LO, ybuf + j * IMG_PAIR);
+                umma::commit(&bar_s[j]);
+            }
+            __syncwarp();
+        }
+        for (int i = 0; i < nt && ok; ++i) {
+            // tile i consumed: S(i) read (and, with gradients, GY(i−1) drained and G(i) stored) — everything this iteration
+            // overwrites or reads is implied by it
+            ok = umma::mbar_wait(&bar_e, (uint32_t)(i & 1));
+            if (!ok) break;
+            umma::fence_after_sync();
+            if (WITH_GRAD) {
+                if (i + 2 < nt && umma::elect_one()) {
+                    const int sl = (i + 2) % NSLOT;
+                    umma::mbar_expect_tx(&bar_ytfull[sl], Y_COPY);
+                    umma::bulk_g2s(ytbuf + sl * IMG_PAIR, img0 + (size_t)(i + 2) * IMG_TILE + IMG_PAIR, Y_COPY, &bar_ytfull[sl]);
+                }
+                __syncwarp();
+                ok = umma::mbar_wait(&bar_ytfull[i % NSLOT], (uint32_t)((i / NSLOT) & 1));
+                if (!ok) break;
+                if (umma::elect_one()) {
+                    issue_ts64<MODE>(tmem + TS_ACC, tmem + TS_G_HI, tmem + TS_G_LO, ytbuf + (i % NSLOT) * IMG_PAIR);
+                    umma::commit(&bar_gy);
+                }
+                __syncwarp();
+            }
+            if (i + 2 < nt) {
+                ok = umma::mbar_wait(&bar_yfull[(i + 2) % NSLOT], (uint32_t)(((i + 2) / NSLOT) & 1));
+                if (!ok) break;
+                if (umma::elect_one()) {
+                    issue_ts64<MODE>(tmem + TS_S + (i & 1) * YT, tmem + TS_X_HI, tmem + TS_X_LO, ybuf + ((i + 2) % NSLOT) * IMG_PAIR);
+                    umma::commit(&bar_s[i & 1]);
+                }
+                __syncwarp();
+            }
+            if (i + 3 < nt && umma::elect_one()) {
+                const int sl = i % NSLOT;                      // held Y(i): S(i) completed before the epilogue of tile i read it
+                umma::mbar_expect_tx(&bar_yfull[sl], Y_COPY);
+                umma::bulk_g2s(ybuf + sl * IMG_PAIR, img0 + (size_t)(i + 3) * IMG_TILE, Y_COPY, &bar_yfull[sl]);
+            }
+            __syncwarp();
+        }
+        if (!ok && lane == 0) { dead = 1; if (p.err_flag) atomicOr(p.err_flag, 2); }
+    } else {
+        // ================================ epilogue warps ==================================================== //
+        const int r_own = ((warp & 3) << 5) + lane, half = warp >> 2;
+        const uint32_t lane_off = (uint32_t)((warp & 3) * 32) << 16;
+        const int gi = x0 + r_own;                   // this thread's global X row
+        {   // the X tile → TMEM (A operand of every S product of this CTA): this thread's row, 32 of its 64 columns
+            float xv[32];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (gi < B) v = __ldg(reinterpret_cast<const float4*>(p.X + (long long)gi * DD + half * 32) + q);
+                xv[q * 4] = v.x; xv[q * 4 + 1] = v.y; xv[q * 4 + 2] = v.z; xv[q * 4 + 3] = v.w;
+            }
+            st16_split<MODE>(tmem + lane_off + TS_X_HI + half * 32, tmem + lane_off + TS_X_LO + half * 32, xv);
+            st16_split<MODE>(tmem + lane_off + TS_X_HI + half * 32 + 16, tmem + lane_off + TS_X_LO + half * 32 + 16, xv + 16);
+            umma::tmem_st_wait();
+            umma::fence_before_sync();
+            umma::mbar_arrive(&bar_x);
+        }
+        Bar w_s0{&bar_s[0], 0u, &dead, p.err_flag}, w_s1{&bar_s[1], 0u, &dead, p.err_flag}, w_gy{&bar_gy, 0u, &dead, p.err_flag};
+        const float d_own = (!PASS_I && gi < B) ? __ldg(p.diag + gi) : 0.f;
+        float acc[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) acc[i] = 0.f;
+        float r_hi = 0.f, r_lo = 0.f, loss_hi = 0.f, loss_lo = 0.f;
+        for (int i = 0; i < nt; ++i) {
+            const int y0 = (t_begin + i) * YT;
+            float dq[32];                            // S_jj of this thread's columns (pass I; diag is padded with zeros)
+            if (PASS_I) {
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    const float4 v = __ldg(reinterpret_cast<const float4*>(p.diag + y0 + half * 32) + q);
+                    dq[q * 4] = v.x; dq[q * 4 + 1] = v.y; dq[q * 4 + 2] = v.z; dq[q * 4 + 3] = v.w;
+                }
+            }
+            if (i & 1) w_s1.wait(); else w_s0.wait();          // S(i) complete
+            umma::fence_after_sync();
+            float s[32];
+#pragma unroll
+            for (int c = 0; c < 32; ++c) s[c] = 0.f;
+            if (!dead) umma::tmem_ld32(tmem + lane_off + TS_S + (i & 1) * YT + half * 32, s);
+            if (!WITH_GRAD) { umma::fence_before_sync(); umma::mbar_arrive(&bar_e); }
+            float tile_loss = 0.f, tile_r = 0.f;
+            const bool clean = y0 + YT <= B && x0 + XT <= B && (y0 + YT <= x0 || y0 >= x0 + XT);
+            if (clean) {
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    float prod = 1.f;
+#pragma unroll
+                    for (int c = h * 16; c < h * 16 + 16; ++c) {
+                        const float x = s[c] - (PASS_I ? dq[c] : d_own);
+                        const float ex = __expf(-fabsf(x));
+                        const float inv = rcp_approx(1.f + ex);
+                        s[c] = p.g * (x >= 0.f ? inv : ex * inv);
+                        tile_r += s[c];
+                        if (!PASS_I) { tile_loss += fmaxf(x, 0.f); prod *= 1.f + ex; }      // Π(1+e) ≤ 2¹⁶: one log per 16 scores
+                    }
+                    if (!PASS_I) tile_loss += __logf(prod);
+                }
+            } else {
+#pragma unroll
+                for (int c = 0; c < 32; ++c) {
+                    const int gj = y0 + half * 32 + c;
+                    const float x = s[c] - (PASS_I ? dq[c] : d_own);
+                    const bool valid = gi < B && gj < B && gi != gj;
+                    const float ex = __expf(-fabsf(x));
+                    const float inv = rcp_approx(1.f + ex);
+                    s[c] = valid ? p.g * (x >= 0.f ? inv : ex * inv) : 0.f;
+                    tile_r += s[c];
+                    if (!PASS_I) tile_loss += valid ? fmaxf(x, 0.f) + __logf(1.f + ex) : 0.f;
+                }
+            }
+            two_sum(r_hi, r_lo, tile_r);
+            if (!PASS_I) two_sum(loss_hi, loss_lo, tile_loss);
+            if (WITH_GRAD) {
+                if (i > 0) {                         // GY(i−1) finished under this epilogue: drain it; the G columns are free again
+                    w_gy.wait();
+                    umma::fence_after_sync();
+                    if (!dead) {
+                        float f[32];
+                        umma::tmem_ld32(tmem + lane_off + TS_ACC + half * 32, f);
+#pragma unroll
+                        for (int c = 0; c < 32; ++c) acc[c] += f[c];
+                    }
+                }
+                st16_split<MODE>(tmem + lane_off + TS_G_HI + half * 32, tmem + lane_off + TS_G_LO + half * 32, s);
+                st16_split<MODE>(tmem + lane_off + TS_G_HI + half * 32 + 16, tmem + lane_off + TS_G_LO + half * 32 + 16, s + 16);
+                umma::tmem_st_wait();
+                umma::fence_before_sync();
+                umma::mbar_arrive(&bar_e);           // G(i) ready → GY(i), S(i+2)
+            }
+        }
+        if (WITH_GRAD && nt > 0) {
+            w_gy.wait();
+            umma::fence_after_sync();
+            if (!dead) {
+                float f[32];
+                umma::tmem_ld32(tmem + lane_off + TS_ACC + half * 32, f);
+#pragma unroll
+                for (int c = 0; c < 32; ++c) acc[c] += f[c];
+            }
+        }
+        if (WITH_GRAD) {
+            float* dst = p.acc_part + ((long long)part * p.Bp + gi) * DD + half * 32;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) *reinterpret_cast<float4*>(dst + q * 4) = make_float4(acc[q * 4], acc[q * 4 + 1], acc[q * 4 + 2], acc[q * 4 + 3]);
+            p.r_part[((long long)part * NQ2 + half) * p.Bp + gi] = (double)r_hi + (double)r_lo;
+        }
+        if (!PASS_I) {
+            const double loss_sum = rb_warp_sum_d((double)loss_hi + (double)loss_lo);
+            if (lane == 0) red[warp] = loss_sum;
+        }
+    }
+    umma::fence_before_sync();
+    __syncthreads();
+    if (!PASS_I && tid == 0) {
+        double tsum = 0.0;
+        for (int w = 0; w < NT_EPI2 / 32; ++w) tsum += red[w];
+        p.loss_part[blockIdx.x] = tsum;
+    }
+    if (warp == 0) umma::tmem_free(tmem, TS_COLS);
+}
+
+template <int MODE, bool PASS_I, bool WITH_GRAD>
+int launch_ts(const IbTsParams& p, int grid, cudaStream_t st) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        RB_CUDA(cudaFuncSetAttribute(inbatch_ts_kernel<MODE, PASS_I, WITH_GRAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)IB_TS_SMEM));
+        attr_set = true;
+    }
+    inbatch_ts_kernel<MODE, PASS_I, WITH_GRAD><<<grid, NT_TS, IB_TS_SMEM, st>>>(p);
+    RB_LAUNCH_CHECK("inbatch_ts_kernel");
+    return RB200_OK;
+}
+
 struct IbPlan { int n_xt, n_yt, split, tps, Bp, grid; };
 IbPlan plan(int B) {
     IbPlan pl;
@@ -452,8 +772,8 @@ int launch(const IbParams& p, int grid, cudaStream_t st) {
 size_t rb_inbatch_tc_workspace_bytes(int B, int D) {
     if (D != DD || B < 1) return 0;
     const IbPlan pl = plan(B);
-    return 256 * 10 + sizeof(float) * ((size_t)2 * B + YT + 2 * DD + 2 * CM_BLOCKS * DD) + sizeof(int) + sizeof(float) * (size_t)pl.split * pl.Bp * DD +
-           sizeof(double) * ((size_t)pl.split * NQ * pl.Bp + pl.grid);
+    return 256 * 12 + sizeof(float) * ((size_t)2 * B + YT + 2 * DD + 2 * CM_BLOCKS * DD) + sizeof(int) + sizeof(float) * (size_t)pl.split * pl.Bp * DD +
+           sizeof(double) * ((size_t)pl.split * NQ * pl.Bp + pl.grid) + (size_t)2 * pl.n_yt * IMG_TILE;
 }
 
 int rb_inbatch_tc(const float* U, const float* I, int B, int D, int mode, float* loss, float* dU, float* dI,
@@ -472,14 +792,17 @@ int rb_inbatch_tc(const float* U, const float* I, int B, int D, int mode, float*
     float* acc_part = ar.take<float>((size_t)pl.split * pl.Bp * DD);
     double* r_part = ar.take<double>((size_t)pl.split * NQ * pl.Bp);
     double* loss_part = ar.take<double>(pl.grid);
+    unsigned char* img_u = ar.take<unsigned char>((size_t)pl.n_yt * IMG_TILE);
+    unsigned char* img_i = ar.take<unsigned char>((size_t)pl.n_yt * IMG_TILE);
     if (!workspace || !ar.ok()) return rb_set_error(RB200_ERR_WORKSPACE, "bpr_inbatch: workspace too small (%zu given)", workspace_bytes);
+    static int use_ts = -1;                 // RB200_INBATCH_TS=0: the shared-memory-operand kernel of round 1
+    if (use_ts < 0) { const char* e = getenv("RB200_INBATCH_TS"); use_ts = (e && atoi(e) == 0) ? 0 : 1; }
     rowdot64_kernel<<<(Bd + 7) / 8, 256, 0, st>>>(U, I, B, Bd, diag);
     RB_LAUNCH_CHECK("rowdot64_kernel");
     const double denom = (double)B * (double)(B - 1);
     IbParams p{};
     p.diag = diag; p.B = B; p.split = pl.split; p.tiles_per_split = pl.tps; p.g = (float)((double)grad_scale / denom);
-    p.acc_part = acc_part; p.r_part = r_part; p.loss_part = loss_part; p.Bp = pl.Bp; p.err_flag = nullptr;
-    (void)err;
+    p.acc_part = acc_part; p.r_part = r_part; p.loss_part = loss_part; p.Bp = pl.Bp; p.err_flag = err;
     const bool grad = dU != nullptr;
     int rc;
     if (grad) {
@@ -488,6 +811,30 @@ int rb_inbatch_tc(const float* U, const float* I, int B, int D, int mode, float*
         colsum_final_kernel<<<1, 128, 0, st>>>(cen_part, B, cen);
         RB_LAUNCH_CHECK("colsum_final_kernel");
     }
+    const int fgrid = (B * 16 + 255) / 256;
+    if (use_ts) {
+        inbatch_images_kernel<<<dim3(pl.n_yt, 2), 256, 0, st>>>(U, I, B, grad ? cen : nullptr, img_u, img_i);
+        RB_LAUNCH_CHECK("inbatch_images_kernel");
+        IbTsParams q{};
+        q.diag = diag; q.B = B; q.split = pl.split; q.tiles_per_split = pl.tps; q.Bp = pl.Bp; q.g = p.g;
+        q.acc_part = acc_part; q.r_part = r_part; q.loss_part = loss_part; q.err_flag = err;
+        RB_CUDA(cudaMemsetAsync(err, 0, sizeof(int), st));
+        q.X = U; q.yimg = img_i;
+        if (mode == 2) rc = grad ? launch_ts<2, false, true>(q, pl.grid, st) : launch_ts<2, false, false>(q, pl.grid, st);
+        else rc = grad ? launch_ts<1, false, true>(q, pl.grid, st) : launch_ts<1, false, false>(q, pl.grid, st);
+        if (rc) return rc;
+        inbatch_loss_kernel<<<1, 32, 0, st>>>(loss_part, pl.grid, 1.0 / denom, loss);
+        RB_LAUNCH_CHECK("inbatch_loss_kernel");
+        if (!grad) return RB200_OK;
+        inbatch_finish_kernel<false><<<fgrid, 256, 0, st>>>(acc_part, r_part, r_total, I, cen + DD, dU, B, pl.Bp, pl.split, NQ2);
+        RB_LAUNCH_CHECK("inbatch_finish_kernel");
+        q.X = I; q.yimg = img_u;
+        rc = mode == 2 ? launch_ts<2, true, true>(q, pl.grid, st) : launch_ts<1, true, true>(q, pl.grid, st);
+        if (rc) return rc;
+        inbatch_finish_kernel<true><<<fgrid, 256, 0, st>>>(acc_part, r_part, r_total, U, cen, dI, B, pl.Bp, pl.split, NQ2);
+        RB_LAUNCH_CHECK("inbatch_finish_kernel");
+        return RB200_OK;
+    }
     p.X = U; p.Y = I; p.ycen = cen + DD;
     if (mode == 2) rc = grad ? launch<2, false, true>(p, pl.grid, st) : launch<2, false, false>(p, pl.grid, st);
     else rc = grad ? launch<1, false, true>(p, pl.grid, st) : launch<1, false, false>(p, pl.grid, st);
@@ -495,13 +842,12 @@ int rb_inbatch_tc(const float* U, const float* I, int B, int D, int mode, float*
     inbatch_loss_kernel<<<1, 32, 0, st>>>(loss_part, pl.grid, 1.0 / denom, loss);
     RB_LAUNCH_CHECK("inbatch_loss_kernel");
     if (!grad) return RB200_OK;
-    const int fgrid = (B * 16 + 255) / 256;
-    inbatch_finish_kernel<false><<<fgrid, 256, 0, st>>>(acc_part, r_part, r_total, I, cen + DD, dU, B, pl.Bp, pl.split);
+    inbatch_finish_kernel<false><<<fgrid, 256, 0, st>>>(acc_part, r_part, r_total, I, cen + DD, dU, B, pl.Bp, pl.split, NQ);
     RB_LAUNCH_CHECK("inbatch_finish_kernel");
     p.X = I; p.Y = U; p.ycen = cen;
     rc = mode == 2 ? launch<2, true, true>(p, pl.grid, st) : launch<1, true, true>(p, pl.grid, st);
     if (rc) return rc;
-    inbatch_finish_kernel<true><<<fgrid, 256, 0, st>>>(acc_part, r_part, r_total, U, cen, dI, B, pl.Bp, pl.split);
+    inbatch_finish_kernel<true><<<fgrid, 256, 0, st>>>(acc_part, r_part, r_total, U, cen, dI, B, pl.Bp, pl.split, NQ);
     RB_LAUNCH_CHECK("inbatch_finish_kernel");
     return RB200_OK;
 }

@@ -117,3 +117,17 @@ def test_inbatch_full_batch_properties():
     lhs = U.astype(np.float64).T @ dU.astype(np.float64)
     rhs = dI.astype(np.float64).T @ I.astype(np.float64)
     assert rel_l2(lhs, rhs) <= 1e-5
+
+
+def test_shared_memory_operand_kernel_stays_selectable():
+    """RB200_INBATCH_TS=0 selects round 1's shared-memory-operand kernel (thread-staged Y tiles): the parity cases of this file
+    again on it (the selector is read once per process, hence the subprocess)."""
+    import os
+    import subprocess
+    import sys
+    if os.environ.get("RB200_INBATCH_TS") == "0":
+        pytest.skip("already inside the RB200_INBATCH_TS=0 run")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "pytest", "-x", "-q", "-m", "gpu", "tests/test_gpu_inbatch_tc.py", "-k", "not selectable"],
+                       cwd=root, env=dict(os.environ, RB200_INBATCH_TS="0"), capture_output=True, text=True, timeout=1200)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
