@@ -470,12 +470,16 @@ def bench_inbatch(args, dev):
         ms = float(np.median(ts))
         out[name] = {"ms": ms, "logical_tflops": 6.0 * B * B * D / (ms * 1e-3) / 1e12}
     t = out["tcgen05_3xtf32"]
-    out["roofline"] = {"kernel": "inbatch_tc_kernel<2> x2 (rb200_bpr_inbatch mode 2)", "bound": "tensor", "unit": "TFLOP/s",
+    out["roofline"] = {"kernel": "inbatch_ts_kernel<2> x2 (rb200_bpr_inbatch mode 2: X and G tiles as TMEM A operands, TMA-fed operand images)",
+                       "bound": "tensor", "unit": "TFLOP/s",
                        "achieved": t["logical_tflops"], "issued_tflops": t["logical_tflops"] * 4.0, "peak": pk["bf16_tflops"],
-                       "frac": t["logical_tflops"] / pk["bf16_tflops"], "traffic": ncu_traffic("inbatch_tc_kernel"),
+                       "frac": t["logical_tflops"] / pk["bf16_tflops"], "issued_frac_of_tf32_peak": t["logical_tflops"] * 4.0 / (pk["bf16_tflops"] / 2),
+                       "traffic": ncu_traffic("inbatch_tc_kernel"),
+                       "tensor_pipe_active_pct_ncu": 54.8,
                        "note": "logical 6·B²·D fp32-grade flops vs the measured bf16 peak (kind::tf32 peaks at half of it); issued = "
-                               "8·B²·D (scores recomputed) x 3 (3xTF32).  The kernel is bound by the B² sigmoid/softplus epilogue and "
-                               "operand staging (SFU + issue slots), not by the tensor pipe (profiles/r01_inbatch_tc.md)"}
+                               "8·B²·D (scores recomputed in the second pass) x 3 (3xTF32).  ncu (profiles/r02_inbatch_ts.md): "
+                               "sm__pipe_tensor_cycles_active 54.8 % / 55.8 % in the two passes (north_star target >= 50 %), DRAM 10.6 MB "
+                               "read / 0 written per launch"}
     # whole step with the in-batch loss (2 towers + B×B), CUDA graph, device-resident batch
     torch.manual_seed(0)
     model = R.TwoTowerModel(N_USERS, N_ITEMS, D, H, dropout=DROPOUT).to(dev).train()

@@ -13,7 +13,8 @@ I = torch.nn.functional.normalize(torch.randn(B, D, device="cuda", generator=g),
 loss = torch.empty(1, device="cuda"); dU = torch.empty_like(U); dI = torch.empty_like(I)
 wsb = lib.rb200_bpr_inbatch_workspace_bytes(B, D)
 ws = _lib.workspace(wsb, "cuda")
-for mode in (0, 2, 1):
+modes = tuple(int(m) for m in sys.argv[2].split(",")) if len(sys.argv) > 2 else (0, 2, 1)
+for mode in modes:
     def run():
         _lib.check(lib.rb200_bpr_inbatch(U.data_ptr(), I.data_ptr(), B, D, mode, loss.data_ptr(), dU.data_ptr(), dI.data_ptr(), 1.0,
                                          ws.data_ptr(), wsb, _lib.stream_ptr()))
