@@ -145,6 +145,15 @@ def bench_c4(K: int, W: int, dev, rank: int, world: int, B: int = 8192, strong_g
             t = torch.tensor([stages[k] for k in keys], dtype=torch.float64, device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             stages = {k: float(v) for k, v in zip(keys, t.tolist())}
+    # the same boundaries INSIDE a graph replay (device timestamps): no host launch time in these
+    stages_g = None
+    if with_stages:
+        stages_g = tr.profile_stages_graph(*resident[0])
+        if _dist_on():
+            keys = sorted(stages_g)
+            t = torch.tensor([stages_g[k] for k in keys], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            stages_g = {k: float(v) for k, v in zip(keys, t.tolist())}
 
     # strong scaling: fixed global batch
     Bs = strong_global // world
@@ -183,11 +192,13 @@ def bench_c4(K: int, W: int, dev, rank: int, world: int, B: int = 8192, strong_g
             "exchange": {"all_to_all_bytes_per_rank_per_step": int(a2a_bytes), "mlp_allreduce_bytes": mlp_floats * 4,
                          "nvlink_GBps_if_alone": None}}
     if stages:
-        tw = stages.get("towers_fwd", 0.0) + stages.get("towers_bwd", 0.0)
+        src = stages_g or stages
+        tw = src.get("towers_fwd", 0.0) + src.get("towers_bwd", 0.0)
         roof["towers"] = {"kernel": "tower_fwd_ts_kernel<128> + tower_bwd_data_ts_kernel<128> + tower_bwd_weights_ts_kernel<128,*> (tcgen05 3xTF32)",
                           "bound": "tensor", "unit": "TFLOP/s", "ms": tw, "achieved": tower_flops / (tw * 1e-3) / 1e12 if tw else None,
                           "peak": pk["bf16_tflops"], "frac": tower_flops / (tw * 1e-3) / 1e12 / pk["bf16_tflops"] if tw else None,
-                          "share_of_step_eager": tw / max(sum(stages.values()), 1e-9)}
+                          "share_of_step": tw / max(sum(src.values()), 1e-9),
+                          "timed": "device timestamps inside a graph replay" if stages_g else "eager phases"}
         comm = stages.get("route_gather_exchange", 0.0) + stages.get("grad_exchange", 0.0) + stages.get("allreduce_norm_clip", 0.0)
         roof["exchange"]["phases_with_collectives_ms_eager"] = comm
     return {
@@ -201,7 +212,7 @@ def bench_c4(K: int, W: int, dev, rank: int, world: int, B: int = 8192, strong_g
                 "ms_per_step": e2e_s / Ke * 1e3, "steps": Ke,
                 "api": "per step: batch (ids + genres) from pinned host memory -> device, ShardedBPRTrainer.step, loss.item() "
                        "(host synchronisation every step), wall clock, max over ranks"},
-        "gpu_launches": launches * K, "launches_per_step": launches, "stage_ms_eager": stages, "roofline": roof, "clocks": clocks,
+        "gpu_launches": launches * K, "launches_per_step": launches, "stage_ms_eager": stages, "stage_ms_graph": stages_g, "roofline": roof, "clocks": clocks,
         "final_loss": float(loss), "c4_strong": strong,
     }
 
@@ -426,7 +437,7 @@ def _run(args):
         "ms_per_step": c4["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic", "config": c4["config"], "config_detail": c4["config_detail"], "e2e": c4["e2e"],
         "gpu_launches": c4["gpu_launches"],
-        "launches_per_step": c4["launches_per_step"], "stage_ms_eager": c4["stage_ms_eager"], "roofline": c4["roofline"],
+        "launches_per_step": c4["launches_per_step"], "stage_ms_eager": c4["stage_ms_eager"], "stage_ms_graph": c4["stage_ms_graph"], "roofline": c4["roofline"],
         "clocks": c4["clocks"], "final_loss": c4["final_loss"], "c4_strong": c4["c4_strong"], "parity": parity,
         "scaling_basis": "C4 efficiency at N GPUs = value(N) / (N x c4.value of the N=1 line): bench.py --gpus 1 runs this same function at "
                          "world 1 with the same per-rank batch and reports it as its `c4` object (its headline stays C2, the "

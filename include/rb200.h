@@ -43,6 +43,9 @@ size_t rb200_sizeof(int which);
 /* kernels of this library launched so far by this process (host-side count; cub's internal launches
  * and graph replays are not included) */
 uint64_t rb200_launch_count(void);
+/* measurement aid: a one-thread kernel on `stream` writes the device's %globaltimer (ns) to out[idx] (device memory).
+ * Capturable, so phase boundaries can be timed inside a CUDA-graph replay (bench_sharded.py's stage table). */
+int rb200_stamp(uint64_t* out, int idx, void* stream);
 
 /* ------------------------------------------------------------------------------------------ *
  * Towers — src/models/two_tower.py:39-42 (UserTower.forward) and :68-72 (ItemTower.forward)

@@ -1,12 +1,19 @@
 """CPU restatement of the threshold-pruned exhaustive search (rb200_flat_search's round loop, csrc/ivf.cu + csrc/flat_scan_tc.cu)
 — TEST INFRASTRUCTURE ONLY.  It restates the ALGORITHM, not the arithmetic: scores come from the same fp32 matmul as
 ``ivf_oracle.flat_search``; what is checked (tests/test_oracle_flat_rounds.py) is that pruning by the running k-th best score with a
-strict comparison, row ranges growing by a factor of four, a bounded survivor list and the redo-on-overflow rule return exactly the
+strict comparison, row ranges growing by a factor of four (eight for at most 128 queries), a bounded survivor list and the
+redo-on-overflow rule return exactly the
 exhaustive top-k (faiss IndexFlatIP semantics: score descending, earlier row first on equal scores) for any row order.
 """
 import numpy as np
 
-PREFIX, GROWTH, CAP_K, CAP_MIN = 8192, 4, 7, 3584       # the constants of csrc/ivf.cu
+PREFIX, GROWTH, CAP_K, CAP_MIN = 8192, 4, 7, 3584       # the constants of csrc/ivf.cu (more than 128 queries)
+GROWTH_SMALL, CAP_K_SMALL = 8, 16                       # at most 128 queries: flat_growth / flat_cap in csrc/ivf.cu
+
+
+def constants_for(nq):
+    """(growth, cap_k) rb200_flat_search uses for a batch of nq queries"""
+    return (GROWTH_SMALL, CAP_K_SMALL) if nq <= 128 else (GROWTH, CAP_K)
 
 
 def _topk_rows(scores, rows, k):
@@ -15,12 +22,15 @@ def _topk_rows(scores, rows, k):
     return scores[order], rows[order]
 
 
-def flat_search_rounds(q, x, k, prefix=PREFIX, growth=GROWTH, cap=None):
+def flat_search_rounds(q, x, k, prefix=PREFIX, growth=None, cap=None):
     """→ (scores [nq, k], rows [nq, k], overflowed: bool).  -FLT_MAX / -1 padded when k > rows."""
     q, x = np.asarray(q, np.float32), np.asarray(x, np.float32)
     nq, n = q.shape[0], x.shape[0]
+    g_auto, cap_k = constants_for(nq)
+    if growth is None:
+        growth = g_auto
     if cap is None:
-        cap = (max(CAP_K * k, CAP_MIN) + 511) // 512 * 512
+        cap = (max(cap_k * k, CAP_MIN) + 511) // 512 * 512
     out_s = np.full((nq, k), -np.finfo(np.float32).max, np.float32)
     out_i = np.full((nq, k), -1, np.int64)
     n0 = min(n, prefix)

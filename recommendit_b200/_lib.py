@@ -87,6 +87,7 @@ SIGNATURES = {
     "rb200_sm_count": (I, []),
     "rb200_sizeof": (SZ, [I]),
     "rb200_launch_count": (U64, []),
+    "rb200_stamp": (I, [P, I, P]),
     "rb200_tower_fwd": (I, [C.POINTER(TowerJob), I, I, I, F, U64, U64, P, I, P, P, SZ, P]),
     "rb200_tower_fwd_workspace_bytes": (SZ, [I, I, I, I, I]),
     "rb200_tower_img_bytes": (SZ, [I, I, I]),

@@ -34,6 +34,19 @@ extern "C" const char* rb200_last_error(void) { return g_err; }
 extern "C" int rb200_sm_count(void) { return rb_sm_count(); }
 extern "C" uint64_t rb200_launch_count(void) { return g_rb_launches; }
 
+// one thread: out[idx] = %globaltimer (ns).  A capturable timestamp: phase boundaries INSIDE a CUDA-graph replay, where events cannot go
+__global__ void stamp_kernel(unsigned long long* out, int idx) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    out[idx] = t;
+}
+extern "C" int rb200_stamp(uint64_t* out, int idx, void* stream) {
+    RB_REQUIRE(out && idx >= 0, "stamp: bad arguments");
+    stamp_kernel<<<1, 1, 0, (cudaStream_t)stream>>>((unsigned long long*)out, idx);
+    RB_LAUNCH_CHECK("stamp_kernel");
+    return RB200_OK;
+}
+
 // sizeof() of the ABI structs, so that foreign-language bindings can verify their mirrors.
 extern "C" size_t rb200_sizeof(int which) {
     switch (which) {

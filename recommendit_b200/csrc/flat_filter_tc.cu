@@ -1,0 +1,245 @@
+// Exhaustive inner-product scan for MANY queries (more than 128; BASELINE cfg 5: 4096 queries against 12.5 M rows per GPU) — the round
+// kernel of rb200_flat_search where the scan is bound by the tensor pipe.  One-pass TF32 FILTER + exact re-score of the survivors:
+//
+//   * only the hi images of rows and queries are multiplied (1 MMA per logical MMA instead of the 3 of 3xTF32): the accumulator holds
+//     S̃ = Σ hi(q_i)·hi(x_i) with |S − S̃| ≤ (2ε + ε²)·Σ|q_i||x_i| ≤ 2⁻¹⁰·(1 + 2⁻¹²)·‖q‖‖x‖ (ε = 2⁻¹¹: round-to-nearest tf32 split; the fp32
+//     accumulation error is four orders of magnitude smaller).  A score survives when S̃ > thr[q] − qmarg[q]·max‖x‖ with
+//     qmarg[q] = 1.5·2⁻¹⁰·‖q‖ (flat_qimage_kernel) and max‖x‖ over the CTA's rows: no row that could beat the threshold is lost, a few per
+//     cent more survive, and the host loop re-scores every survivor in fp32 (flat_rescore_kernel) before the select — same ids;
+//   * database-stationary: a CTA owns 2 × 128 rows, written once into TMEM as the A operands (hi image, lane = row, column = k; TS-mode
+//     MMAs: the tensor core reads only the query operand from shared memory), and the whole query set streams past in blocks of 128
+//     queries — M128 × N128 × K8 MMAs, 8 per (tile, block) unit, from a pre-split image (2 MB at nq = 4096, L2-resident) by one bulk
+//     copy per block into a 4-slot ring;
+//   * THREE special warps.  ncu on the previous form (one warp issuing copies and the MMAs of both tiles, N = 64) showed the tensor pipe
+//     30 % active with the epilogue warps waiting on the MMAs 41 % of the time and the issuing warp's samples spread evenly over its
+//     ≈ 250 instructions per 64-query chunk: a single in-order warp needs ≈ 7 cycles per instruction, so the ISSUER bounded the kernel.
+//     Now: warp 16 = copy producer, warps 17 and 18 = one MMA issuer per tile (≈ 100 instructions per 128-query unit each, half the MMAs
+//     per query at N = 128), warps 0-15 = epilogue (8 per tile: TMEM lane quadrant × 64-query half);
+//   * a ring of three accumulators [128 × 128] in TMEM (384 columns + 2 × 64 for the rows = 512) shared by the units in issue order;
+//     hand-offs through mbarriers only (copy → MMA: expect_tx; MMA → epilogue and MMA → slot reuse: tcgen05.commit; epilogue → MMA: arrive);
+//   * thresholds of all queries, already lowered by the margin at this CTA's largest row norm, staged in shared memory once per CTA;
+//     survivors through per-warp shared-memory buffers (survivors.cuh).
+// D = 64, at most 8192 queries per call (the staged thresholds: 32 KB).
+#include <stdlib.h>
+
+#include "common.cuh"
+#include "survivors.cuh"
+#include "umma.cuh"
+
+namespace {
+
+constexpr int VT = 128, QB = 128, DD = 64, TILES = 2, NSLOT = 4, NACC = 3, EW = 16;
+constexpr int Q_SLOT = QB * DD * 4;              // hi image of one 128-query block: 32 KB
+constexpr int Q_BLK = 2 * Q_SLOT;                // [hi | lo] per block in the image (flat_qimage_kernel with 128-row blocks)
+constexpr int MAX_Q = 8192;
+constexpr int CAPW = 256;
+constexpr int NT_F = (EW + 3) * 32;
+constexpr size_t SMEM_F = (size_t)NSLOT * Q_SLOT + (size_t)EW * WarpSurvivors<CAPW>::BYTES + (size_t)MAX_Q * 4;
+
+__global__ void __launch_bounds__(NT_F, 1)
+flat_filter_tc_kernel(const float* __restrict__ x, long long n_rows, const unsigned char* __restrict__ qimg, int n_blocks,
+                      const float* __restrict__ thr, const float* __restrict__ qmarg, int* __restrict__ count,
+                      float* __restrict__ cand_s, long long stride, int kprev, int* __restrict__ cand_r, int cap, int* __restrict__ flags) {
+    extern __shared__ __align__(1024) unsigned char smem[];
+    unsigned char* qbuf = smem;                                  // [NSLOT][Q_SLOT]
+    unsigned char* surv_mem = qbuf + NSLOT * Q_SLOT;             // [EW][WarpSurvivors<CAPW>::BYTES]
+    float* th_sm = reinterpret_cast<float*>(surv_mem + EW * WarpSurvivors<CAPW>::BYTES);     // [n_blocks·128] effective thresholds
+    __shared__ __align__(8) uint64_t bar_qfull[NSLOT], bar_qfree[NSLOT], bar_done[TILES][NACC], bar_free[TILES][NACC];
+    __shared__ uint32_t tmem_slot;
+    __shared__ float nrm_s[TILES * 4];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const long long row0 = (long long)blockIdx.x * (TILES * VT);
+    constexpr uint32_t ACC_COLS = NACC * QB, TM_COLS = 512;      // then per tile the hi image of its rows, 64 columns
+    static_assert(ACC_COLS + TILES * DD <= TM_COLS, "TMEM budget");
+
+    if (warp == 0) umma::tmem_alloc(&tmem_slot, TM_COLS);
+    if (tid == EW * 32) {
+        for (int i = 0; i < NSLOT; ++i) { umma::mbar_init(&bar_qfull[i], 1); umma::mbar_init(&bar_qfree[i], TILES); }
+        for (int i = 0; i < NACC; ++i) {
+            umma::mbar_init(&bar_done[0][i], 1); umma::mbar_init(&bar_done[1][i], 1);
+            umma::mbar_init(&bar_free[0][i], 256); umma::mbar_init(&bar_free[1][i], 256);
+        }
+        umma::fence_mbar_init();
+        for (int i = 0; i < NSLOT && i < n_blocks; ++i) {        // the first query blocks are on their way while the rows are staged
+            umma::mbar_expect_tx(&bar_qfull[i], Q_SLOT);
+            umma::bulk_g2s(qbuf + i * Q_SLOT, qimg + (size_t)i * Q_BLK, Q_SLOT, &bar_qfull[i]);
+        }
+    }
+    // ---- rows → TMEM (warps 0-7: thread = one row, 16 independent 16-byte loads, hi image, 4 tcgen05.st of 16 columns) ---------- //
+    const bool stager = warp < TILES * 4;
+    const long long srow = row0 + (warp >> 2) * VT + ((warp & 3) << 5) + lane;
+    float4 vv[DD / 4];
+    if (stager) {
+#pragma unroll
+        for (int i = 0; i < DD / 4; ++i)
+            vv[i] = srow < n_rows ? __ldcs(reinterpret_cast<const float4*>(x + srow * DD) + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+        float ss[4] = {0.f, 0.f, 0.f, 0.f};                      // max ‖x‖ over the CTA's rows: the unit of the queries' margins
+#pragma unroll
+        for (int i = 0; i < DD / 4; ++i)
+            ss[i & 3] = fmaf(vv[i].x, vv[i].x, fmaf(vv[i].y, vv[i].y, fmaf(vv[i].z, vv[i].z, fmaf(vv[i].w, vv[i].w, ss[i & 3]))));
+        const uint32_t mx = __reduce_max_sync(0xffffffffu, __float_as_uint((ss[0] + ss[1]) + (ss[2] + ss[3])));     // ≥ 0: bits order like values
+        if (lane == 0) nrm_s[warp] = sqrtf(__uint_as_float(mx)) * 1.0001f;
+    }
+    umma::fence_before_sync();
+    __syncthreads();                                             // TMEM base address, barriers and norms published
+    umma::fence_after_sync();
+    const uint32_t tmem = tmem_slot;
+    if (stager) {
+        const uint32_t a_base = tmem + ((uint32_t)((warp & 3) * 32) << 16) + ACC_COLS + (uint32_t)(warp >> 2) * DD;
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+            float hi[16];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                float4 h, l;
+                umma::split4(vv[g * 4 + i], h, l);
+                hi[4 * i] = h.x; hi[4 * i + 1] = h.y; hi[4 * i + 2] = h.z; hi[4 * i + 3] = h.w;
+            }
+            umma::tmem_st16(a_base + g * 16, hi);
+        }
+        umma::tmem_st_wait();
+    }
+    if (warp < EW) {                                             // effective thresholds of all queries (epilogue warps only use them)
+        float nxmax = 0.f;
+#pragma unroll
+        for (int i = 0; i < TILES * 4; ++i) nxmax = fmaxf(nxmax, nrm_s[i]);
+        for (int i = tid; i < n_blocks * QB; i += EW * 32) th_sm[i] = fmaf(-__ldg(qmarg + i), nxmax, __ldg(thr + i));
+    }
+    umma::fence_before_sync();
+    __syncthreads();                                             // rows in TMEM, thresholds staged
+    umma::fence_after_sync();
+
+    if (warp == EW) {
+        // ================================ copy producer ================================ //
+        bool ok = true;
+        for (int c = NSLOT; c < n_blocks && ok; ++c) {
+            const int sl = c % NSLOT;
+            ok = umma::mbar_wait(&bar_qfree[sl], ((c / NSLOT) - 1) & 1);
+            if (!ok && lane == 0) atomicCAS(flags + 2, 0, (1 << 24) | (warp << 16) | c);
+            if (ok && umma::elect_one()) {
+                umma::mbar_expect_tx(&bar_qfull[sl], Q_SLOT);
+                umma::bulk_g2s(qbuf + sl * Q_SLOT, qimg + (size_t)c * Q_BLK, Q_SLOT, &bar_qfull[sl]);
+            }
+            __syncwarp();
+        }
+        if (!ok && lane == 0) atomicOr(flags + 1, 4);
+    } else if (warp > EW) {
+        // ================================ MMA issuer of tile t (a converged warp, one elected lane) ================================ //
+        const int t = warp - EW - 1;
+        const uint32_t idesc = umma::idesc_tf32(VT, QB);
+        constexpr uint32_t lbo_b = (QB / 8) * 128;
+        const uint32_t q_s = umma::smem_u32(qbuf), a_t = tmem + ACC_COLS + (uint32_t)t * DD;
+        // Unit u = 2c + t uses accumulator a = u % 3 for the k-th time, k = u / 3; the uses of an accumulator alternate between the two
+        // tiles.  Its previous use (k − 1, the OTHER tile's) is released on bar_free[1 − t][a], a barrier that counts only that tile's
+        // releases: the ((k − 1) / 2)-th; completions go to bar_done[t][a], this tile's (k / 2)-th.  With ONE barrier per accumulator
+        // for both tiles every waiter would see only every other phase, and a one-bit parity cannot tell phase k from phase k − 2:
+        // a warp running ahead passes the wait two uses early (seen as wrong scores and dead-locks while this kernel was written).
+        int a = t, k = 0;
+        bool ok = true;
+        for (int c = 0; c < n_blocks; ++c) {
+            const int sl = c % NSLOT;
+            ok = umma::mbar_wait(&bar_qfull[sl], (c / NSLOT) & 1);
+            if (!ok && lane == 0) atomicCAS(flags + 2, 0, (2 << 24) | (warp << 16) | c);
+            if (ok && k >= 1) {
+                ok = umma::mbar_wait(&bar_free[1 - t][a], ((k - 1) >> 1) & 1);
+                if (!ok && lane == 0) atomicCAS(flags + 2, 0, (3 << 24) | (warp << 16) | c);
+            }
+            if (!ok) break;
+            umma::fence_after_sync();
+            if (umma::elect_one()) {
+                const uint64_t db = umma::smem_desc(q_s + sl * Q_SLOT, lbo_b, 128);
+                const uint32_t acc = tmem + (uint32_t)a * QB;
+#pragma unroll
+                for (int j = 0; j < DD / 8; ++j)
+                    umma::mma_tf32_ts(acc, a_t + 8 * j, db + (uint64_t)((2 * j * lbo_b) >> 4), idesc, j > 0);
+                umma::commit(&bar_done[t][a]);                   // → epilogue of this unit
+                umma::commit(&bar_qfree[sl]);                    // → (with the other tile's) slot sl may be refilled
+            }
+            __syncwarp();
+            a += 2;
+            if (a >= NACC) { a -= NACC; ++k; }
+        }
+        if (!ok && lane == 0) atomicOr(flags + 1, 1);
+    } else {
+        // ================================ epilogue warps (8 per tile) ================================ //
+        const int t = warp >> 3, wq = warp & 7;
+        const int r_own = ((wq & 3) << 5) + lane, half = wq >> 2;
+        const uint32_t lane_off = (uint32_t)((wq & 3) * 32) << 16;
+        const long long row = row0 + t * VT + r_own;
+        WarpSurvivors<CAPW> surv;
+        surv.init(surv_mem + warp * WarpSurvivors<CAPW>::BYTES, lane);
+        int a = t, k = 0;
+        for (int c = 0; c < n_blocks; ++c) {
+            if (!umma::mbar_wait(&bar_done[t][a], (k >> 1) & 1)) {
+                atomicOr(flags + 1, 2);
+                if (lane == 0) atomicCAS(flags + 2, 0, (4 << 24) | (warp << 16) | c);
+                break;
+            }
+            umma::fence_after_sync();
+#pragma unroll
+            for (int blk = 0; blk < 2; ++blk) {
+                const int q0 = c * QB + half * 64 + blk * 32;
+                const uint32_t acc = tmem + lane_off + (uint32_t)a * QB + half * 64 + blk * 32;
+                float s[32];
+                umma::tmem_ld32(acc, s);
+                // branch-free: one predicate-accumulating compare per score decides whether the warp has any survivor at all; only
+                // then is the per-score mask built and handed to the warp's survivor buffer
+                bool any = false;
+#pragma unroll
+                for (int j4 = 0; j4 < 8; ++j4) {
+                    const float4 t4 = *reinterpret_cast<const float4*>(th_sm + q0 + j4 * 4);
+                    any = any || (s[j4 * 4] > t4.x) || (s[j4 * 4 + 1] > t4.y) || (s[j4 * 4 + 2] > t4.z) || (s[j4 * 4 + 3] > t4.w);
+                }
+                if (row >= n_rows) any = false;
+                if (__any_sync(0xffffffffu, any)) {
+                    uint32_t m = 0;
+#pragma unroll
+                    for (int j4 = 0; j4 < 8; ++j4) {
+                        const float4 t4 = *reinterpret_cast<const float4*>(th_sm + q0 + j4 * 4);
+                        m |= (s[j4 * 4] > t4.x ? 1u : 0u) << (j4 * 4);
+                        m |= (s[j4 * 4 + 1] > t4.y ? 1u : 0u) << (j4 * 4 + 1);
+                        m |= (s[j4 * 4 + 2] > t4.z ? 1u : 0u) << (j4 * 4 + 2);
+                        m |= (s[j4 * 4 + 3] > t4.w ? 1u : 0u) << (j4 * 4 + 3);
+                    }
+                    if (row >= n_rows) m = 0;
+                    surv.add_block(m, acc, q0, (int)(row - 0), count, cand_s, stride, kprev, cand_r, cap, flags);   // S̃, replaced by flat_rescore_kernel
+                }
+            }
+            umma::fence_before_sync();
+            umma::mbar_arrive(&bar_free[t][a]);                  // the accumulator may be overwritten by the unit three later (the other tile's)
+            a += 2;
+            if (a >= NACC) { a -= NACC; ++k; }
+        }
+        surv.flush(count, cand_s, stride, kprev, cand_r, cap, flags);
+    }
+    umma::fence_before_sync();
+    __syncthreads();
+    if (warp == 0) umma::tmem_free(tmem, TM_COLS);
+}
+
+}  // namespace
+
+// does a round over nq queries use the one-pass filter (its survivors then need rb_flat_rescore)?  RB200_FLAT_FILTER=0: 3xTF32 scores
+// straight from flat_scan_tc_kernel (testing knob).  The query image is then laid out in 128-query blocks (rb_flat_qimage block_rows).
+bool rb_flat_filtered(int nq) {
+    static int on = -1;
+    if (on < 0) { const char* e = getenv("RB200_FLAT_FILTER"); on = e ? atoi(e) : 1; }
+    return on && nq > 128 && nq <= MAX_Q;
+}
+
+// one round: rows [0, n_rows) of x (the caller offsets x) against n_blocks·128 queries (image in 128-query blocks), thr / qmarg / count
+// [n_blocks·128]
+int rb_flat_filter_tc(const float* x, long long n_rows, const unsigned char* qimg, int n_blocks, const float* thr, const float* qmarg, int* count,
+                      float* cand_s, long long stride, int kprev, int* cand_r, int cap, int* flags, cudaStream_t st) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        RB_CUDA(cudaFuncSetAttribute(flat_filter_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_F));
+        attr_set = true;
+    }
+    const long long n_cta = (n_rows + TILES * VT - 1) / (TILES * VT);
+    RB_REQUIRE(n_rows >= 1 && n_rows < (1ll << 31) && n_blocks >= 1 && n_blocks * QB <= MAX_Q, "flat_filter: 1..2^31 rows, at most 8192 queries");
+    flat_filter_tc_kernel<<<(unsigned)n_cta, NT_F, SMEM_F, st>>>(x, n_rows, qimg, n_blocks, thr, qmarg, count, cand_s, stride, kprev, cand_r, cap,
+                                                                  flags);
+    RB_LAUNCH_CHECK("flat_filter_tc_kernel");
+    return RB200_OK;
+}

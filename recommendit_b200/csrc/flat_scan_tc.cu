@@ -15,64 +15,90 @@
 // tile is accumulated in TMEM, double-buffered.  Warp-specialised: warp 8 issues the copies and the MMAs (one thread), warps 0-7
 // stage the rows once and then run the epilogues — the MMAs of chunk c+1 run under the epilogue of chunk c, and hand-offs go
 // through mbarriers only (copy → MMA: expect_tx; MMA → epilogue and MMA → slot reuse: tcgen05.commit; epilogue → MMA: arrive).
+// FILTER (the default for more than two query chunks): a ONE-pass TF32 filter instead of 3xTF32.  Only the hi images of rows and
+// queries are multiplied (1 MMA per logical MMA instead of 3), so the accumulator holds S̃ = Σ hi(q_i)·hi(x_i) with
+// |S − S̃| ≤ (2ε + ε²)·Σ|q_i||x_i| ≤ 2⁻¹⁰·(1 + 2⁻¹²)·‖q‖‖x‖ (ε = 2⁻¹¹: round-to-nearest tf32 split; fp32 accumulation error is four
+// orders of magnitude smaller).  A score survives when S̃ > thr[q] − qmarg[q]·max‖x‖ with qmarg[q] = 1.5·2⁻¹⁰·‖q‖ (flat_qimage_kernel)
+// and max‖x‖ taken over the CTA's rows: no row that could beat the threshold is lost, a few per cent more survive (the score density at
+// the k-th best of N rows is ≈ k·z/(N·σ) per unit score), and the host loop re-scores every survivor in fp32 (flat_rescore_kernel)
+// before the select — same ids, a third of the MMAs.  With a third of the tensor work per unit the epilogue gets one warp set PER TILE
+// (16 epilogue warps at TILES = 2) so that a warp sees every other unit.
 // D = 64.  <TILES 2, NSLOT 3>: 224 KB of shared memory, 256 TMEM columns, 1 CTA per SM (many query chunks: tensor-bound);
 // <TILES 1, NSLOT 1>: 96 KB, 2 CTAs per SM (one or two query chunks: the scan is bound by reading the rows).
 #include <stdlib.h>
 
 #include "common.cuh"
+#include "survivors.cuh"
 #include "umma.cuh"
 
 namespace {
 
-constexpr int VT = 128, QT = 64, DD = 64, NT_EPI = 256, NT_F = NT_EPI + 32;
+constexpr int VT = 128, QT = 64, DD = 64;
 constexpr int V_BYTES = VT * DD * 4;             // one half (hi or lo) of one tile: 32 KB
 constexpr int Q_HALF = QT * DD * 4;              // 16 KB
 constexpr int Q_IMG = 2 * Q_HALF;                // hi image then lo image of one 64-query chunk: 32 KB
-template <int TILES, int NSLOT, bool A_TMEM> constexpr size_t flat_smem() { return (A_TMEM ? 0 : (size_t)TILES * 2 * V_BYTES) + (size_t)NSLOT * Q_IMG; }
+constexpr int TH_SM_CHUNKS = 128;                // the filter stages the thresholds of up to 8192 queries in shared memory (32 KB)
 
 // q [nq, 64] fp32 → per chunk of 64 queries [hi | lo], each in the K-major core-matrix layout of umma.cuh; rows past nq are zero
-__global__ void __launch_bounds__(256) flat_qimage_kernel(const float* __restrict__ q, int nq, int n_chunks, unsigned char* __restrict__ qimg) {
-    const int i = blockIdx.x * 256 + threadIdx.x;                // (row, 16-byte chunk)
-    if (i >= n_chunks * QT * (DD / 4)) return;
+// qmarg[r] = FILTER_C·‖q_r‖ (0 for the padding rows): the filter's per-query safety margin per unit of row norm
+constexpr float FILTER_C = 1.5f / 1024.f;
+// blk = rows per image block: 64 (flat_scan_tc / flat_stream_tc) or 128 (flat_filter_tc): block b = [hi | lo] of rows [b·blk, (b+1)·blk)
+__global__ void __launch_bounds__(256) flat_qimage_kernel(const float* __restrict__ q, int nq, int blk, unsigned char* __restrict__ qimg,
+                                                          float* __restrict__ qmarg) {
+    const int i = blockIdx.x * 256 + threadIdx.x;                // (row, 16-byte chunk); grid covers the padded rows × 16 exactly
     const int r = i >> 4, c4 = i & 15;
     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
     if (r < nq) v = __ldg(reinterpret_cast<const float4*>(q + (long long)r * DD) + c4);
+    float ss = fmaf(v.x, v.x, fmaf(v.y, v.y, fmaf(v.z, v.z, v.w * v.w)));
+#pragma unroll
+    for (int o = 8; o >= 1; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+    if (c4 == 0) qmarg[r] = FILTER_C * sqrtf(ss) * 1.0001f;
     float4 hi, lo;
     umma::split4(v, hi, lo);
-    unsigned char* base = qimg + (size_t)(r / QT) * Q_IMG;
-    const uint32_t off = umma::kmajor_offset(QT, r % QT, c4 * 4);
+    const size_t half_bytes = (size_t)blk * DD * 4;
+    unsigned char* base = qimg + (size_t)(r / blk) * 2 * half_bytes;
+    const uint32_t off = umma::kmajor_offset(blk, r % blk, c4 * 4);
     *reinterpret_cast<float4*>(base + off) = hi;
-    *reinterpret_cast<float4*>(base + Q_HALF + off) = lo;
+    *reinterpret_cast<float4*>(base + half_bytes + off) = lo;
 }
 
-template <int TILES, int NSLOT, bool A_TMEM>
-__global__ void __launch_bounds__(NT_F, 1) flat_scan_tc_kernel(const float* __restrict__ x, long long n_rows,
-                                                               const unsigned char* __restrict__ qimg, int n_chunks,
-                                                               const float* __restrict__ thr, int* __restrict__ count,
-                                                               float* __restrict__ cand_s, long long stride, int kprev,
-                                                               int* __restrict__ cand_r, int cap, int* __restrict__ flags) {
+template <int TILES, int NSLOT, bool A_TMEM, bool FILTER>
+__global__ void __launch_bounds__((FILTER ? 8 * TILES : 8) * 32 + 32, 1)
+flat_scan_tc_kernel(const float* __restrict__ x, long long n_rows, const unsigned char* __restrict__ qimg, int n_chunks,
+                    const float* __restrict__ thr, const float* __restrict__ qmarg, int* __restrict__ count,
+                    float* __restrict__ cand_s, long long stride, int kprev, int* __restrict__ cand_r, int cap, int* __restrict__ flags) {
+    static_assert(!FILTER || A_TMEM, "the one-pass filter keeps the rows in TMEM");
+    constexpr int EW = FILTER ? 8 * TILES : 8;                   // epilogue warps (FILTER: one set of 8 per tile); warp EW = copy + MMA issuer
+    constexpr int QSLOT = FILTER ? Q_HALF : Q_IMG;               // the filter multiplies the hi images only
+    constexpr int A_COLS = FILTER ? DD : 2 * DD;                 // TMEM columns of one tile's row image(s)
     extern __shared__ __align__(1024) unsigned char smem[];
     unsigned char* v_hi = smem;                                  // [TILES][V_BYTES]
     unsigned char* v_lo = smem + TILES * V_BYTES;
-    unsigned char* qbuf = smem + (A_TMEM ? 0 : 2 * TILES * V_BYTES);      // [NSLOT][Q_IMG]
-    __shared__ __align__(8) uint64_t bar_qfull[NSLOT], bar_qfree[NSLOT], bar_m[2 * TILES], bar_accfree[2 * TILES];   // per (buffer, tile) unit
+    unsigned char* qbuf = smem + (A_TMEM ? 0 : 2 * TILES * V_BYTES);      // [NSLOT][QSLOT]
+    constexpr int CAPW = TILES == 1 ? 128 : 256;                 // survivor buffer entries per epilogue warp (survivors.cuh)
+    unsigned char* surv_mem = qbuf + NSLOT * QSLOT;              // [EW][WarpSurvivors<CAPW>::BYTES]
+    float* th_sm = reinterpret_cast<float*>(surv_mem + EW * WarpSurvivors<CAPW>::BYTES);     // FILTER: [n_chunks·64] effective thresholds
+    constexpr int NBUF = FILTER ? 3 : 2;                         // accumulator buffers per tile (the filter's epilogue is the critical path)
+    __shared__ __align__(8) uint64_t bar_qfull[NSLOT], bar_qfree[NSLOT], bar_m[NBUF * TILES], bar_accfree[NBUF * TILES];   // per (buffer, tile) unit
     __shared__ uint32_t tmem_slot;
     __shared__ int dead;
+    __shared__ float nrm_s[TILES * 4];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const long long row0 = (long long)blockIdx.x * (TILES * VT);
-    // TMEM columns: [2 buffers][TILES] accumulators of 64, then (A_TMEM) per tile the hi and the lo image of the rows, 64 columns each
-    constexpr uint32_t ACC_COLS = 2 * TILES * QT, TM_COLS = A_TMEM ? ACC_COLS + TILES * 2 * DD : ACC_COLS;
-    static_assert(TM_COLS == 128 || TM_COLS == 256 || TM_COLS == 512, "TMEM allocations are powers of two");
+    // TMEM columns: [NBUF buffers][TILES] accumulators of 64, then (A_TMEM) per tile the hi (and the lo) image of the rows, 64 columns each
+    constexpr uint32_t ACC_COLS = NBUF * TILES * QT, USED_COLS = A_TMEM ? ACC_COLS + TILES * A_COLS : ACC_COLS;
+    constexpr uint32_t TM_COLS = USED_COLS <= 128 ? 128 : USED_COLS <= 256 ? 256 : 512;
+    static_assert(USED_COLS <= 512, "TMEM budget");
 
     if (warp == 0) umma::tmem_alloc(&tmem_slot, TM_COLS);
-    if (tid == NT_EPI) {
+    if (tid == EW * 32) {
         for (int i = 0; i < NSLOT; ++i) { umma::mbar_init(&bar_qfull[i], 1); umma::mbar_init(&bar_qfree[i], 1); }
-        for (int i = 0; i < 2 * TILES; ++i) { umma::mbar_init(&bar_m[i], 1); umma::mbar_init(&bar_accfree[i], NT_EPI); }
+        for (int i = 0; i < NBUF * TILES; ++i) { umma::mbar_init(&bar_m[i], 1); umma::mbar_init(&bar_accfree[i], 256); }
         umma::fence_mbar_init();
         dead = 0;
         for (int i = 0; i < NSLOT && i < n_chunks; ++i) {        // the first query chunks are on their way while the rows are staged
-            umma::mbar_expect_tx(&bar_qfull[i], Q_IMG);
-            umma::bulk_g2s(qbuf + i * Q_IMG, qimg + (size_t)i * Q_IMG, Q_IMG, &bar_qfull[i]);
+            umma::mbar_expect_tx(&bar_qfull[i], QSLOT);
+            umma::bulk_g2s(qbuf + i * QSLOT, qimg + (size_t)i * Q_IMG, QSLOT, &bar_qfull[i]);
         }
     }
     // ---- stage the database rows (warps 0-7): all loads of a thread are issued before the first is used.  A warp covers 8 rows ×
@@ -88,12 +114,19 @@ __global__ void __launch_bounds__(NT_F, 1) flat_scan_tc_kernel(const float* __re
 #pragma unroll
             for (int i = 0; i < DD / 4; ++i)
                 vv[i] = row < n_rows ? __ldcs(reinterpret_cast<const float4*>(x + row * DD) + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+            if (FILTER) {                                        // max ‖x‖ over the CTA's rows: the unit of the queries' margins
+                float ss = 0.f;
+#pragma unroll
+                for (int i = 0; i < DD / 4; ++i) ss = fmaf(vv[i].x, vv[i].x, fmaf(vv[i].y, vv[i].y, fmaf(vv[i].z, vv[i].z, fmaf(vv[i].w, vv[i].w, ss))));
+                const uint32_t mx = __reduce_max_sync(0xffffffffu, __float_as_uint(ss));     // ss ≥ 0: the bit patterns order like the values
+                if (lane == 0) nrm_s[warp] = sqrtf(__uint_as_float(mx)) * 1.0001f;
+            }
         }
         umma::fence_before_sync();
         __syncthreads();                                         // TMEM base address published (tmem_slot)
         umma::fence_after_sync();
         if (stager) {
-            const uint32_t a_base = tmem_slot + ((uint32_t)((warp & 3) * 32) << 16) + ACC_COLS + (uint32_t)(warp >> 2) * 2 * DD;
+            const uint32_t a_base = tmem_slot + ((uint32_t)((warp & 3) * 32) << 16) + ACC_COLS + (uint32_t)(warp >> 2) * A_COLS;
 #pragma unroll
             for (int g = 0; g < 4; ++g) {
                 float hi[16], lo[16];
@@ -105,11 +138,11 @@ __global__ void __launch_bounds__(NT_F, 1) flat_scan_tc_kernel(const float* __re
                     lo[4 * i] = l.x; lo[4 * i + 1] = l.y; lo[4 * i + 2] = l.z; lo[4 * i + 3] = l.w;
                 }
                 umma::tmem_st16(a_base + g * 16, hi);
-                umma::tmem_st16(a_base + DD + g * 16, lo);
+                if (!FILTER) umma::tmem_st16(a_base + DD + g * 16, lo);
             }
             umma::tmem_st_wait();
         }
-    } else if (warp < NT_EPI / 32) {
+    } else if (warp < 8) {
         const int r8 = lane & 7, c4l = lane >> 3;
         float4 vv[8 * TILES];
 #pragma unroll
@@ -136,7 +169,7 @@ __global__ void __launch_bounds__(NT_F, 1) flat_scan_tc_kernel(const float* __re
     umma::fence_after_sync();
     const uint32_t tmem = tmem_slot;
 
-    if (warp == NT_EPI / 32) {
+    if (warp == EW) {
         // ================================ copy + MMA issuer (one thread) ================================ //
         // The whole warp walks the loop (warp-uniform control flow and operands); single instructions are issued by one elected lane.
         const uint32_t idesc = umma::idesc_tf32(VT, QT);
@@ -145,30 +178,32 @@ __global__ void __launch_bounds__(NT_F, 1) flat_scan_tc_kernel(const float* __re
         uint32_t ph_full = 0, ph_free = 0, ph_acc = 0;          // one phase bit per barrier (bit i = barrier i)
         bool ok = true;
         for (int c = 0; c < n_chunks && ok; ++c) {
-            const int b = c & 1, sl = c % NSLOT;
+            const int b = c % NBUF, sl = c % NSLOT;
             ok = umma::mbar_wait(&bar_qfull[sl], (ph_full >> sl) & 1);
             ph_full ^= 1u << sl;
             if (!ok) break;
             // descriptors differ only in the start address field (bits 0-13, in 16-byte units)
-            const uint64_t dbh = umma::smem_desc(q_s + sl * Q_IMG, lbo_b, 128);
-            const uint64_t dbl = umma::smem_desc(q_s + sl * Q_IMG + Q_HALF, lbo_b, 128);
-            // one unit = (chunk, tile): 24 MMAs into its own accumulator, its own completion barrier — the epilogue of tile 0
-            // starts while the MMAs of tile 1 run, and an accumulator is needed again only four units later
+            const uint64_t dbh = umma::smem_desc(q_s + sl * QSLOT, lbo_b, 128);
+            const uint64_t dbl = umma::smem_desc(q_s + sl * QSLOT + (FILTER ? 0 : Q_HALF), lbo_b, 128);
+            // one unit = (chunk, tile): 24 MMAs (8 in the filter) into its own accumulator, its own completion barrier — the epilogue
+            // of tile 0 starts while the MMAs of tile 1 run, and an accumulator is needed again only four units later
 #pragma unroll
             for (int t = 0; t < TILES; ++t) {
                 const int un = b * TILES + t;
-                if (c >= 2) { ok = ok && umma::mbar_wait(&bar_accfree[un], (ph_acc >> un) & 1); ph_acc ^= 1u << un; }
+                if (c >= NBUF) { ok = ok && umma::mbar_wait(&bar_accfree[un], (ph_acc >> un) & 1); ph_acc ^= 1u << un; }
                 if (!ok) break;
                 umma::fence_after_sync();
                 if (umma::elect_one()) {
                     const uint32_t acc = tmem + (uint32_t)un * QT;
-                    const uint32_t a_hi = tmem + ACC_COLS + (uint32_t)t * 2 * DD, a_lo = a_hi + DD;
+                    const uint32_t a_hi = tmem + ACC_COLS + (uint32_t)t * A_COLS, a_lo = a_hi + DD;
                     const uint64_t dah = A_TMEM ? 0 : umma::smem_desc(v_hi_s + t * V_BYTES, lbo_a, 128);
                     const uint64_t dal = A_TMEM ? 0 : umma::smem_desc(v_lo_s + t * V_BYTES, lbo_a, 128);
 #pragma unroll
                     for (int j = 0; j < DD / 8; ++j) {
                         const uint64_t oa = (uint64_t)((2 * j * lbo_a) >> 4), ob = (uint64_t)((2 * j * lbo_b) >> 4);
-                        if (A_TMEM) {
+                        if (FILTER) {
+                            umma::mma_tf32_ts(acc, a_hi + 8 * j, dbh + ob, idesc, j > 0);
+                        } else if (A_TMEM) {
                             umma::mma_tf32_ts(acc, a_lo + 8 * j, dbh + ob, idesc, j > 0);
                             umma::mma_tf32_ts(acc, a_hi + 8 * j, dbl + ob, idesc, true);
                             umma::mma_tf32_ts(acc, a_hi + 8 * j, dbh + ob, idesc, true);
@@ -193,8 +228,8 @@ __global__ void __launch_bounds__(NT_F, 1) flat_scan_tc_kernel(const float* __re
                 ok = umma::mbar_wait(&bar_qfree[s2], (ph_free >> s2) & 1);
                 ph_free ^= 1u << s2;
                 if (ok && umma::elect_one()) {
-                    umma::mbar_expect_tx(&bar_qfull[s2], Q_IMG);
-                    umma::bulk_g2s(qbuf + s2 * Q_IMG, qimg + (size_t)(cc + NSLOT) * Q_IMG, Q_IMG, &bar_qfull[s2]);
+                    umma::mbar_expect_tx(&bar_qfull[s2], QSLOT);
+                    umma::bulk_g2s(qbuf + s2 * QSLOT, qimg + (size_t)(cc + NSLOT) * Q_IMG, QSLOT, &bar_qfull[s2]);
                 }
                 __syncwarp();
             }
@@ -202,19 +237,48 @@ __global__ void __launch_bounds__(NT_F, 1) flat_scan_tc_kernel(const float* __re
         if (!ok && lane == 0) { dead = 1; atomicOr(flags + 1, 1); }
     } else {
         // ================================ epilogue warps ================================ //
-        const int r_own = ((warp & 3) << 5) + lane, half = warp >> 2;
-        const uint32_t lane_off = (uint32_t)((warp & 3) * 32) << 16;
+        const int wq = warp & 7;                                 // FILTER: warps 8t … 8t+7 own tile t; otherwise every warp walks all tiles
+        const int r_own = ((wq & 3) << 5) + lane, half = wq >> 2;
+        const uint32_t lane_off = (uint32_t)((wq & 3) * 32) << 16;
+        const int t_begin = FILTER ? (warp >> 3) : 0, t_end = FILTER ? t_begin + 1 : TILES;
+        float nxmax = 0.f;
+        if (FILTER) {
+#pragma unroll
+            for (int i = 0; i < TILES * 4; ++i) nxmax = fmaxf(nxmax, nrm_s[i]);
+        }
+        WarpSurvivors<CAPW> surv;
+        surv.init(surv_mem + warp * WarpSurvivors<CAPW>::BYTES, lane);
+        // FILTER: the thresholds of ALL queries, already lowered by each query's margin at this CTA's largest row norm, are staged in
+        // shared memory once (a global load per chunk sat on the epilogue's per-chunk latency chain, which bounds this kernel)
+        const bool th_staged = FILTER && n_chunks <= TH_SM_CHUNKS;
+        if (th_staged) {
+            for (int i = tid; i < n_chunks * QT; i += EW * 32) th_sm[i] = fmaf(-__ldg(qmarg + i), nxmax, __ldg(thr + i));
+            asm volatile("bar.sync 1, %0;" ::"n"(EW * 32) : "memory");
+        }
         uint32_t ph_m = 0;
         for (int c = 0; c < n_chunks; ++c) {
-            const int b = c & 1;
+            const int b = c % NBUF;
             float4 th4[8];                                       // thresholds of this thread's 32 queries (uniform loads)
+            if (th_staged) {
 #pragma unroll
-            for (int i = 0; i < 8; ++i) th4[i] = __ldg(reinterpret_cast<const float4*>(thr + (long long)c * QT + half * 32) + i);
+                for (int i = 0; i < 8; ++i) th4[i] = *reinterpret_cast<const float4*>(th_sm + c * QT + half * 32 + i * 4);
+            } else {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) th4[i] = __ldg(reinterpret_cast<const float4*>(thr + (long long)c * QT + half * 32) + i);
+                if (FILTER) {                                    // lowered by the query's margin at this CTA's largest row norm
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const float4 m = __ldg(reinterpret_cast<const float4*>(qmarg + (long long)c * QT + half * 32) + i);
+                        th4[i].x = fmaf(-m.x, nxmax, th4[i].x); th4[i].y = fmaf(-m.y, nxmax, th4[i].y);
+                        th4[i].z = fmaf(-m.z, nxmax, th4[i].z); th4[i].w = fmaf(-m.w, nxmax, th4[i].w);
+                    }
+                }
+            }
             const float* th = reinterpret_cast<const float*>(th4);
             const int q0 = c * QT + half * 32;
             bool alive = true;
 #pragma unroll
-            for (int t = 0; t < TILES; ++t) {
+            for (int t = t_begin; t < t_end; ++t) {
                 const int un = b * TILES + t;
                 if (!umma::mbar_wait(&bar_m[un], (ph_m >> un) & 1)) { atomicOr(flags + 1, 2); alive = false; break; }
                 ph_m ^= 1u << un;
@@ -225,9 +289,7 @@ __global__ void __launch_bounds__(NT_F, 1) flat_scan_tc_kernel(const float* __re
                 const long long row = row0 + t * VT + r_own;
                 // branch-free (a branch per score made the epilogue the bottleneck: 64 reconvergence regions per chunk,
                 // instruction-fetch bound).  One predicate-accumulating compare per score decides whether the warp has any
-                // survivor at all; only then is the per-score mask built.  Survivors are rare, so their columns are walked in a
-                // warp-uniform loop and the score is re-read from TMEM (one column for the 32 lanes) instead of indexing
-                // registers dynamically.
+                // survivor at all; only then is the per-score mask built and handed to the warp's survivor buffer (survivors.cuh).
                 bool any = false;
 #pragma unroll
                 for (int j = 0; j < 32; ++j) any = any || (s[j] > th[j]);
@@ -237,46 +299,66 @@ __global__ void __launch_bounds__(NT_F, 1) flat_scan_tc_kernel(const float* __re
 #pragma unroll
                     for (int j = 0; j < 32; ++j) m |= (s[j] > th[j] ? 1u : 0u) << j;
                     if (row >= n_rows) m = 0;
-                    uint32_t u = __reduce_or_sync(0xffffffffu, m);
-                    while (u) {
-                        const int j = __ffs(u) - 1;
-                        u &= u - 1;
-                        const float v = umma::tmem_ld1(acc + j);
-                        if ((m >> j) & 1u) {
-                            const int pos = atomicAdd(count + q0 + j, 1);
-                            if (pos < cap) {
-                                cand_s[(long long)(q0 + j) * stride + kprev + pos] = v;
-                                cand_r[(long long)(q0 + j) * cap + pos] = (int)row;
-                            } else {
-                                flags[0] = 1;                    // survivor list full: the caller redoes the search on the chunked path
-                            }
-                        }
-                    }
+                    surv.add_block(m, acc, q0, (int)row, count, cand_s, stride, kprev, cand_r, cap, flags);   // FILTER: S̃, replaced by flat_rescore_kernel
                 }
                 umma::fence_before_sync();
                 umma::mbar_arrive(&bar_accfree[un]);             // this accumulator may be overwritten by chunk c + 2
             }
             if (!alive) break;
         }
+        surv.flush(count, cand_s, stride, kprev, cand_r, cap, flags);
     }
     umma::fence_before_sync();
     __syncthreads();
     if (warp == 0) umma::tmem_free(tmem, TM_COLS);
 }
 
-template <int TILES, int NSLOT, bool A_TMEM>
-int launch_flat_scan(const float* x, long long n_rows, const unsigned char* qimg, int n_chunks, const float* thr, int* count,
+// exact fp32 scores of the filter's survivors: 16 lanes per (query, survivor) — lane i holds the i-th 16-byte chunk of the query and of
+// the row, four fused multiply-adds, then a fixed xor-shuffle tree (deterministic).  grid (ceil(cap / 128), nq), 256 threads.
+__global__ void __launch_bounds__(256) flat_rescore_kernel(const float* __restrict__ q, const float* __restrict__ x, const int* __restrict__ count,
+                                                           const int* __restrict__ cand_r, int cap, float* __restrict__ cand_s,
+                                                           long long stride, int kprev) {
+    const int qi = blockIdx.y;
+    const int n = min(__ldg(count + qi), cap);
+    const int p0 = blockIdx.x * 128;
+    if (p0 >= n) return;
+    const int g = threadIdx.x >> 4, l = threadIdx.x & 15;
+    const float4 qv = __ldg(reinterpret_cast<const float4*>(q + (long long)qi * DD) + l);
+    float4 xv[8];
+    int rows[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int p = p0 + i * 16 + g;
+        rows[i] = p < n ? __ldg(cand_r + (long long)qi * cap + p) : -1;
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+        xv[i] = rows[i] >= 0 ? __ldg(reinterpret_cast<const float4*>(x + (long long)rows[i] * DD) + l) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        float d = fmaf(qv.w, xv[i].w, fmaf(qv.z, xv[i].z, fmaf(qv.y, xv[i].y, qv.x * xv[i].x)));
+#pragma unroll
+        for (int o = 8; o >= 1; o >>= 1) d += __shfl_xor_sync(0xffffffffu, d, o);
+        if (l == 0 && rows[i] >= 0) cand_s[(long long)qi * stride + kprev + p0 + i * 16 + g] = d;
+    }
+}
+
+template <int TILES, int NSLOT, bool A_TMEM, bool FILTER>
+int launch_flat_scan(const float* x, long long n_rows, const unsigned char* qimg, int n_chunks, const float* thr, const float* qmarg, int* count,
                      float* cand_s, long long stride, int kprev, int* cand_r, int cap, int* flags, cudaStream_t st) {
     static bool attr_set = false;
-    constexpr size_t smem = flat_smem<TILES, NSLOT, A_TMEM>();
+    constexpr int EWARPS = FILTER ? 8 * TILES : 8;
+    constexpr size_t smem = (A_TMEM ? 0 : (size_t)TILES * 2 * V_BYTES) + (size_t)NSLOT * (FILTER ? Q_HALF : Q_IMG)
+                            + (size_t)EWARPS * WarpSurvivors<(TILES == 1 ? 128 : 256)>::BYTES + (FILTER ? (size_t)TH_SM_CHUNKS * QT * 4 : 0);
+    constexpr int NTHR = EWARPS * 32 + 32;
     if (!attr_set) {
-        RB_CUDA(cudaFuncSetAttribute(flat_scan_tc_kernel<TILES, NSLOT, A_TMEM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        RB_CUDA(cudaFuncSetAttribute(flat_scan_tc_kernel<TILES, NSLOT, A_TMEM, FILTER>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_set = true;
     }
     const long long n_cta = (n_rows + TILES * VT - 1) / (TILES * VT);
     RB_REQUIRE(n_rows >= 1 && n_rows < (1ll << 31) && n_cta < (1ll << 31), "flat_scan: a round holds at most 2^31 rows");
-    flat_scan_tc_kernel<TILES, NSLOT, A_TMEM><<<(unsigned)n_cta, NT_F, smem, st>>>(x, n_rows, qimg, n_chunks, thr, count, cand_s, stride,
-                                                                                 kprev, cand_r, cap, flags);
+    flat_scan_tc_kernel<TILES, NSLOT, A_TMEM, FILTER><<<(unsigned)n_cta, NTHR, smem, st>>>(x, n_rows, qimg, n_chunks, thr, qmarg, count, cand_s,
+                                                                                         stride, kprev, cand_r, cap, flags);
     RB_LAUNCH_CHECK("flat_scan_tc_kernel");
     return RB200_OK;
 }
@@ -284,20 +366,30 @@ int launch_flat_scan(const float* x, long long n_rows, const unsigned char* qimg
 }  // namespace
 
 // one round: rows [0, n_rows) of x (the caller offsets x) against n_chunks·64 queries (image), thresholds thr[n_chunks·64]
-int rb_flat_scan_tc(const float* x, long long n_rows, const unsigned char* qimg, int n_chunks, const float* thr, int* count,
+int rb_flat_scan_tc(const float* x, long long n_rows, const unsigned char* qimg, int n_chunks, const float* thr, const float* qmarg, int* count,
                     float* cand_s, long long stride, int kprev, int* cand_r, int cap, int* flags, cudaStream_t st) {
     static int variant = -1;                // RB200_FLAT_VARIANT: 0 = rows in shared memory (SS MMAs), 1 = rows in TMEM (TS MMAs)
     if (variant < 0) { const char* e = getenv("RB200_FLAT_VARIANT"); variant = e ? atoi(e) : 1; }
     if (n_chunks <= 2)
-        return launch_flat_scan<1, 1, false>(x, n_rows, qimg, n_chunks, thr, count, cand_s, stride, kprev, cand_r, cap, flags, st);
+        return launch_flat_scan<1, 1, false, false>(x, n_rows, qimg, n_chunks, thr, qmarg, count, cand_s, stride, kprev, cand_r, cap, flags, st);
     if (variant == 1)
-        return launch_flat_scan<2, 4, true>(x, n_rows, qimg, n_chunks, thr, count, cand_s, stride, kprev, cand_r, cap, flags, st);
-    return launch_flat_scan<2, 3, false>(x, n_rows, qimg, n_chunks, thr, count, cand_s, stride, kprev, cand_r, cap, flags, st);
+        return launch_flat_scan<2, 4, true, false>(x, n_rows, qimg, n_chunks, thr, qmarg, count, cand_s, stride, kprev, cand_r, cap, flags, st);
+    return launch_flat_scan<2, 2, false, false>(x, n_rows, qimg, n_chunks, thr, qmarg, count, cand_s, stride, kprev, cand_r, cap, flags, st);
 }
 
-int rb_flat_qimage(const float* q, int nq, int n_chunks, unsigned char* qimg, cudaStream_t st) {
-    const int n = n_chunks * QT * (DD / 4);
-    flat_qimage_kernel<<<(n + 255) / 256, 256, 0, st>>>(q, nq, n_chunks, qimg);
+// survivors of a filtered round → their fp32 scores (x = the round's first row, as passed to rb_flat_scan_tc)
+int rb_flat_rescore(const float* q, int nq, const float* x, const int* count, const int* cand_r, int cap, float* cand_s, long long stride,
+                    int kprev, cudaStream_t st) {
+    flat_rescore_kernel<<<dim3((cap + 127) / 128, nq), 256, 0, st>>>(q, x, count, cand_r, cap, cand_s, stride, kprev);
+    RB_LAUNCH_CHECK("flat_rescore_kernel");
+    return RB200_OK;
+}
+
+// nq_pad: rows of the image (a multiple of 128; rows past nq are zero), block_rows: 64 or 128
+int rb_flat_qimage(const float* q, int nq, int nq_pad, int block_rows, unsigned char* qimg, float* qmarg, cudaStream_t st) {
+    RB_REQUIRE((block_rows == 64 || block_rows == 128) && nq_pad % 128 == 0 && nq_pad >= nq, "flat_qimage: bad padding");
+    const int n = nq_pad * (DD / 4);
+    flat_qimage_kernel<<<n / 256, 256, 0, st>>>(q, nq, block_rows, qimg, qmarg);
     RB_LAUNCH_CHECK("flat_qimage_kernel");
     return RB200_OK;
 }

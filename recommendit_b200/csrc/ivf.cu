@@ -26,9 +26,19 @@ int rb_list_scan_tc(const float* q, int D, const float* list_vecs, const int64_t
 int rb_gemm_nt_tc(const float* A, int M, const float* B, int N, int K, int mode, float* C, long long ldc, int* err_flag,
                   cudaStream_t st);
 // threshold-pruned exhaustive scan (flat_scan_tc.cu)
-int rb_flat_scan_tc(const float* x, long long n_rows, const unsigned char* qimg, int n_chunks, const float* thr, int* count,
+int rb_flat_scan_tc(const float* x, long long n_rows, const unsigned char* qimg, int n_chunks, const float* thr, const float* qmarg, int* count,
                     float* cand_s, long long stride, int kprev, int* cand_r, int cap, int* flags, cudaStream_t st);
-int rb_flat_qimage(const float* q, int nq, int n_chunks, unsigned char* qimg, cudaStream_t st);
+int rb_flat_qimage(const float* q, int nq, int nq_pad, int block_rows, unsigned char* qimg, float* qmarg, cudaStream_t st);
+// one-pass TF32 filter for 129 … 8192 queries (flat_filter_tc.cu: N = 128 MMAs, one issuer warp per tile)
+bool rb_flat_filtered(int nq);
+int rb_flat_filter_tc(const float* x, long long n_rows, const unsigned char* qimg, int n_blocks, const float* thr, const float* qmarg, int* count,
+                      float* cand_s, long long stride, int kprev, int* cand_r, int cap, int* flags, cudaStream_t st);
+// streaming round kernel for at most 128 queries (flat_stream_tc.cu: persistent, tensor-map TMA, one-pass filter)
+bool rb_flat_streamed(int n_chunks);
+int rb_flat_stream_tc(const float* x, long long n_rows, const unsigned char* qimg, int n_chunks, const float* thr, const float* qmarg, int* count,
+                      float* cand_s, long long stride, int kprev, int* cand_r, int cap, int* flags, cudaStream_t st);
+int rb_flat_rescore(const float* q, int nq, const float* x, const int* count, const int* cand_r, int cap, float* cand_s, long long stride,
+                    int kprev, cudaStream_t st);
 
 namespace {
 
@@ -946,8 +956,14 @@ static long long flat_chunk_rows(int nq, int64_t n) {
 // [seen, 4·seen) against thr[q] = the k-th best score over [0, seen), so it is expected to leave 3·k survivors per query;
 // the survivor lists hold FLAT_CAP_K·k (at least 3584) entries — if one ever fills up (a database sorted by score towards a
 // query), the search is redone on the chunked path, which has no such limit.
-constexpr int FLAT_GROWTH = 4, FLAT_CAP_K = 7, FLAT_CAP_MIN = 3584;
-static int flat_cap(int k) { const int c = FLAT_CAP_K * k; return ((c < FLAT_CAP_MIN ? FLAT_CAP_MIN : c) + 511) / 512 * 512; }
+// At most 128 queries (the scan is bound by reading the rows and a round's fixed cost — prep, re-score, select, launch gaps ≈ 30 us —
+// is what is left to save): rounds grow ×8 (7·k expected survivors, lists of 16·k), four rounds instead of six over 12.5 M rows.
+constexpr int FLAT_CAP_MIN = 3584;
+static int flat_growth(int nq) { return nq <= 128 ? 8 : 4; }
+static int flat_cap(int k, int nq) {
+    const int c = (nq <= 128 ? 16 : 7) * k;
+    return ((c < FLAT_CAP_MIN ? FLAT_CAP_MIN : c) + 511) / 512 * 512;
+}
 static bool flat_use_rounds(int D, int64_t n, long long chunk) {
     static int off = -1;
     if (off < 0) { const char* e = getenv("RB200_FLAT_CHUNKED"); off = (e && atoi(e)) ? 1 : 0; }     // testing knob: chunked path only
@@ -957,10 +973,10 @@ static bool flat_use_rounds(int D, int64_t n, long long chunk) {
 
 extern "C" size_t rb200_flat_search_workspace_bytes(int nq, int64_t n, int k) {
     const long long chunk = flat_chunk_rows(nq, n);
-    const long long cap = flat_cap(k), wide = chunk > cap ? chunk : cap;
-    const size_t nq_pad = ((size_t)nq + 63) / 64 * 64;
+    const long long cap = flat_cap(k, nq), wide = chunk > cap ? chunk : cap;
+    const size_t nq_pad = ((size_t)nq + 127) / 128 * 128;
     return 256 * 12 + sizeof(float) * (size_t)nq * (size_t)(wide + k) + (sizeof(float) + sizeof(int64_t)) * (size_t)nq * k
-           + nq_pad * 64 * 8 + nq_pad * 8 + sizeof(long long) * (size_t)nq + sizeof(int) * (size_t)nq * cap + 64;
+           + nq_pad * 64 * 8 + nq_pad * 12 + sizeof(long long) * (size_t)nq + sizeof(int) * (size_t)nq * cap + 64;
 }
 
 __global__ void copy_prev_kernel(const float* __restrict__ prev_scores, int nq, int k, float* __restrict__ cand, long long stride) {
@@ -1016,9 +1032,9 @@ extern "C" int rb200_flat_search(const float* q, int nq, const float* x, int64_t
     RB_REQUIRE(q && x && out_scores && out_ids && nq >= 1 && n >= 1 && k >= 1 && k <= 2048, "flat_search: bad arguments (k must be 1..2048)");
     cudaStream_t st = (cudaStream_t)stream;
     const long long chunk = flat_chunk_rows(nq, n);
-    const int cap = flat_cap(k);
+    const int cap = flat_cap(k, nq), growth = flat_growth(nq);
     const long long stride = (chunk > cap ? chunk : cap) + k;
-    const int n_qchunks = (nq + 63) / 64, nq_pad = n_qchunks * 64;
+    const int n_qchunks = (nq + 63) / 64, nq_pad = (nq + 127) / 128 * 128;     // 64-query chunks of the scan / stream kernels; padded rows
     RbArena ar(workspace, workspace_bytes);
     float* cand = ar.take<float>((size_t)nq * stride);
     float* tmp_scores = ar.take<float>((size_t)nq * k);
@@ -1026,6 +1042,7 @@ extern "C" int rb200_flat_search(const float* q, int nq, const float* x, int64_t
     unsigned char* qimg = ar.take<unsigned char>((size_t)nq_pad * 64 * 8);
     float* thr = ar.take<float>(nq_pad);
     int* count = ar.take<int>(nq_pad);
+    float* qmarg = ar.take<float>(nq_pad);
     long long* lens = ar.take<long long>(nq);
     int* cand_r = ar.take<int>((size_t)nq * cap);
     int* flags = ar.take<int>(4);
@@ -1040,15 +1057,22 @@ extern "C" int rb200_flat_search(const float* q, int nq, const float* x, int64_t
     if ((rc = flat_chunked_range(q, nq, x, D, 0, n0, chunk, stride, k, id_base, cand, bufS, bufI, cur, st))) return rc;
     if (rounds) {
         RB_CUDA(cudaMemsetAsync(flags, 0, 4 * sizeof(int), st));
-        if ((rc = rb_flat_qimage(q, nq, n_qchunks, qimg, st))) return rc;
+        const bool streamed = rb_flat_streamed(n_qchunks);     // ≤ 128 queries: the scan is bound by reading the rows
+        const bool filter_tc = !streamed && rb_flat_filtered(nq);     // 129 … 8192 queries: bound by the tensor pipe
+        const bool filtered = streamed || filter_tc;           // one-pass TF32 filter: survivors are re-scored in fp32 before the select
+        if ((rc = rb_flat_qimage(q, nq, nq_pad, filter_tc ? 128 : 64, qimg, qmarg, st))) return rc;
         const long long rstride = (long long)k + cap;
         for (long long seen = n0; seen < n;) {
-            const long long upto = (n / FLAT_GROWTH >= seen) ? seen * FLAT_GROWTH : n;
+            const long long upto = (n / growth >= seen) ? seen * growth : n;
             const long long rows = (upto < n ? upto : n) - seen;
             flat_round_prep_kernel<<<(unsigned)(((long long)nq_pad * k + NT - 1) / NT), NT, 0, st>>>(bufS[cur], nq, nq_pad, k, cand, rstride,
                                                                                                   thr, count);
             RB_LAUNCH_CHECK("flat_round_prep_kernel");
-            if ((rc = rb_flat_scan_tc(x + seen * D, rows, qimg, n_qchunks, thr, count, cand, rstride, k, cand_r, cap, flags, st))) return rc;
+            rc = streamed    ? rb_flat_stream_tc(x + seen * D, rows, qimg, n_qchunks, thr, qmarg, count, cand, rstride, k, cand_r, cap, flags, st)
+                 : filter_tc ? rb_flat_filter_tc(x + seen * D, rows, qimg, nq_pad / 128, thr, qmarg, count, cand, rstride, k, cand_r, cap, flags, st)
+                             : rb_flat_scan_tc(x + seen * D, rows, qimg, n_qchunks, thr, qmarg, count, cand, rstride, k, cand_r, cap, flags, st);
+            if (rc) return rc;
+            if (filtered && (rc = rb_flat_rescore(q, nq, x + seen * D, count, cand_r, cap, cand, rstride, k, st))) return rc;
             flat_round_lens_kernel<<<(nq + NT - 1) / NT, NT, 0, st>>>(count, nq, k, cap, lens);
             RB_LAUNCH_CHECK("flat_round_lens_kernel");
             ResolveSurv res{bufI[cur], k, cand_r, cap, id_base + seen};
@@ -1060,7 +1084,7 @@ extern "C" int rb200_flat_search(const float* q, int nq, const float* x, int64_t
         int h[4] = {0, 0, 0, 0};
         RB_CUDA(cudaMemcpyAsync(h, flags, sizeof(h), cudaMemcpyDeviceToHost, st));
         RB_CUDA(cudaStreamSynchronize(st));
-        RB_REQUIRE(h[1] == 0, "flat_search: tensor-core pipeline timed out (flag %d)", h[1]);
+        RB_REQUIRE(h[1] == 0, "flat_search: tensor-core pipeline timed out (flag %d, first wait 0x%x)", h[1], h[2]);
         if (h[0]) {            // a survivor list overflowed: redo everything on the chunked path (exact for any row order)
             cur = -1;
             if ((rc = flat_chunked_range(q, nq, x, D, 0, n, chunk, stride, k, id_base, cand, bufS, bufI, cur, st))) return rc;

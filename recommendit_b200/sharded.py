@@ -519,12 +519,52 @@ class ShardedBPRTrainer:
         return self._static_loss
 
     _marks = None
+    _stamp_buf = None
+    _stamp_names: Optional[list] = None
 
     def _mark(self, name: str) -> None:
-        if self._marks is not None:
+        if self._stamp_buf is not None:                            # device timestamps: capturable (profile_stages_graph)
+            i = len(self._stamp_names)
+            self._stamp_names.append(name)
+            check(self.ops.lib.rb200_stamp(self._stamp_buf.data_ptr(), i, stream_ptr()), "stamp")
+        elif self._marks is not None:
             e = torch.cuda.Event(enable_timing=True)
             e.record()
             self._marks.append((name, e))
+
+    def profile_stages_graph(self, user_ids, pos_ids, pos_genres, neg_ids, neg_genres, reps: int = 9) -> Dict[str, float]:
+        """Phase times INSIDE a CUDA-graph replay of the step (ms, median of ``reps`` replays): the step is captured once more with
+        a one-thread ``%globaltimer`` kernel at every phase boundary (``rb200_stamp``; ≈ 2 us each, which the sum includes).  Unlike
+        :meth:`profile_stages` no host launch time is in these numbers.  The replays are real optimiser steps.  Collective over
+        the ranks (every rank must call it)."""
+        batch = [b.clone() for b in (user_ids, pos_ids, pos_genres, neg_ids, neg_genres)]
+        self._stamp_buf = torch.zeros(64, dtype=torch.int64, device=self.dev)
+        try:
+            self._stamp_names = []
+            self._mark("begin")
+            self._step(*batch)                                     # eager once: allocator warm-up for the stamped variant
+            torch.cuda.synchronize(self.dev)
+            self._stamp_names = []
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self._mark("begin")
+                self._step(*batch)
+            self.steps -= 1
+            names = list(self._stamp_names)
+            acc: Dict[str, list] = {}
+            for rep in range(reps + 2):
+                g.replay()
+                self.steps += 1
+                torch.cuda.synchronize(self.dev)
+                if rep < 2:
+                    continue
+                t = self._stamp_buf[:len(names)].tolist()
+                for i in range(1, len(names)):
+                    acc.setdefault(names[i], []).append((t[i] - t[i - 1]) * 1e-6)
+            del g
+        finally:
+            self._stamp_buf, self._stamp_names = None, None
+        return {k: float(sorted(v)[len(v) // 2]) for k, v in acc.items()}
 
     def profile_stages(self, user_ids, pos_ids, pos_genres, neg_ids, neg_genres, reps: int = 5) -> Dict[str, float]:
         """Time between CUDA events at the phase boundaries of EAGER steps (ms, median of ``reps`` after one untimed step that
@@ -556,6 +596,7 @@ class ShardedBPRTrainer:
             # The barrier orders this read after every rank's Adam of the previous step.
             item_ids = torch.cat([pos_ids, neg_ids])
             self._barrier(0)
+            self._mark("barrier0")
             rows = ops.gather_rows_sharded(self._shard_ptrs, self._nu_host, user_ids.contiguous(), item_ids, self.n_user_rows,
                                            self.n_item_rows, D, self.err_flag)
             if getattr(self, "_ident", None) is None or self._ident.numel() != 3 * B:
@@ -617,8 +658,10 @@ class ShardedBPRTrainer:
             # WRITTEN into the owners' receive buckets over NVLink; the barrier makes them visible before the owners' segment sums
             C = self.capacity(3 * B)
             slot, send_rows = ops.route_padded(user_ids.contiguous(), item_ids, W, self._nu_by_rank, C, self.overflow)
+            self._mark("route_plan")
             g_buf, r_buf, g_ptrs, r_ptrs, _ = self._p2p_buckets(3 * B)
             ops.push_rows_sharded(g_ptrs, r_ptrs, self.rank, C, drows, slot, send_rows)
+            self._mark("push_rows")
             self._barrier(1)
             g_rows, rt.recv_rows = g_buf, r_buf
         elif padded:
@@ -648,9 +691,12 @@ class ShardedBPRTrainer:
             g_red = torch.empty(gm.numel(), **f32)
             ops.allreduce_oneshot(gm_ptrs, gm.numel(), g_red)
             g_mlp = g_red[:Pu + Pi]
+            self._mark("mlp_allreduce")
             ops.sumsq(self.opt, [(ug, n_uq, D)])                           # Σg² of this rank's shard rows
             ops.scalars_publish(self.opt, loss, 1.0 / W, sc)
+            self._mark("sumsq_publish")
             self._barrier(2)
+            self._mark("barrier2")
             ops.scalars_reduce(sc_ptrs, self.opt)                          # opt.sumsq = Σ over shards, opt.loss = global mean loss
             ops.sumsq(self.opt, [(g_mlp, None, 0)])                        # + the (replicated) MLP gradient, counted once
         else:

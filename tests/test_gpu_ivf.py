@@ -152,6 +152,22 @@ def test_flat_search_pruned_rounds_match_oracle(n, k, nq):
     V.assert_topk_equivalent(s.cpu().numpy(), ids.cpu().numpy(), s_ref, np.where(i_ref >= 0, i_ref + 7, -1))
 
 
+@pytest.mark.parametrize("n,k,nq", [(200000, 100, 300), (120000, 500, 193)])
+def test_flat_search_filter_margin_scales_with_the_norms(n, k, nq):
+    """The one-pass TF32 filter of the pruned rounds (more than 128 queries) lowers each threshold by 1.5·2⁻¹⁰·‖q‖·max‖x‖: rows and
+    queries of very different lengths (0.05 … 20) must still give the oracle's ids — a margin in absolute score units would lose
+    winners among the long rows."""
+    import recommendit_b200 as R
+    x, rng = _data(n, 64, 1, seed=n % 977)
+    x = np.ascontiguousarray(x * np.exp(rng.uniform(np.log(0.05), np.log(20.0), (n, 1))).astype(np.float32))
+    q = V.normalize_rows(rng.standard_normal((nq, 64)).astype(np.float32))
+    q = np.ascontiguousarray(q * np.exp(rng.uniform(np.log(0.1), np.log(8.0), (nq, 1))).astype(np.float32))
+    s, ids = R.flat_search(torch.from_numpy(q).cuda(), torch.from_numpy(x).cuda(), k)
+    s_ref, i_ref = V.flat_search_c(q, x, k)
+    qn = np.linalg.norm(q, axis=1, keepdims=True)
+    V.assert_topk_equivalent(s.cpu().numpy() / qn / 20.0, ids.cpu().numpy(), s_ref / qn / 20.0, i_ref)
+
+
 def test_flat_search_pruned_rounds_survive_an_adversarial_row_order_and_duplicates():
     """A database sorted by ascending score towards the queries makes every later row beat the running threshold: the survivor
     lists overflow and the search must come back exact (redone on the chunked path).  Duplicated rows give exact-score ties."""

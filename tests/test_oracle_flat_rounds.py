@@ -23,6 +23,18 @@ def test_pruned_rounds_equal_exhaustive_search_on_random_rows():
     assert not of and np.array_equal(i, ei) and np.array_equal(s, es)
 
 
+def test_both_growth_regimes_are_exact():
+    """more than 128 queries: rounds ×4, lists of 7·k; at most 128: rounds ×8, lists of 16·k (csrc/ivf.cu flat_growth / flat_cap)"""
+    assert FR.constants_for(128) == (8, 16) and FR.constants_for(129) == (4, 7)
+    rng = np.random.default_rng(7)
+    x = V.normalize_rows(rng.standard_normal((9000, 16)).astype(np.float32))
+    for nq in (5, 130):
+        q = V.normalize_rows(rng.standard_normal((nq, 16)).astype(np.float32))
+        s, i, of = FR.flat_search_rounds(q, x, 30, prefix=128)
+        es, ei = _exact(q, x, 30)
+        assert not of and np.array_equal(i, ei) and np.array_equal(s, es)
+
+
 def test_exact_ties_go_to_the_earlier_row_across_rounds():
     rng = np.random.default_rng(1)
     x = V.normalize_rows(rng.standard_normal((3000, 8)).astype(np.float32))
