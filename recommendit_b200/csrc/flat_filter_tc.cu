@@ -17,9 +17,14 @@
 //     per query at N = 128), warps 0-15 = epilogue (8 per tile: TMEM lane quadrant × 64-query half);
 //   * a ring of three accumulators [128 × 128] in TMEM (384 columns + 2 × 64 for the rows = 512) shared by the units in issue order;
 //     hand-offs through mbarriers only (copy → MMA: expect_tx; MMA → epilogue and MMA → slot reuse: tcgen05.commit; epilogue → MMA: arrive);
-//   * thresholds of all queries, already lowered by the margin at this CTA's largest row norm, staged in shared memory once per CTA;
-//     survivors through per-warp shared-memory buffers (survivors.cuh).
-// D = 64, at most 8192 queries per call (the staged thresholds: 32 KB).
+//   * THE COMPARISON RUNS ON THE TENSOR CORE.  With the thresholds in shared memory the epilogue needed a load and a predicate-chained
+//     compare per score (ncu: 40 % of the kernel's instructions, 1 200 issue cycles per 128-query block against 1 024 of MMAs).  Instead
+//     every unit gets a ninth K step, an SS-mode MMA of a constant [128 × 8] A tile (n, 1, 1, 0 …; n = this CTA's largest row norm rounded
+//     UP to tf32) with the k = 64 … 71 rows of the query image (m_q, −t_hi, −t_lo, 0 …; m_q = the query's margin rounded up, t_hi + t_lo =
+//     its threshold, rewritten every round by flat_filter_ext_kernel): the accumulator holds S̃ + m_q·n − thr_q and a score survives iff
+//     it is POSITIVE — a 3-input integer max tree over the raw bits (16 instructions per 32 scores, no dependency chain, no loads);
+//   * survivors through per-warp shared-memory buffers (survivors.cuh).
+// D = 64, 129 … 65 536 queries per call.
 #include <stdlib.h>
 
 #include "common.cuh"
@@ -29,12 +34,32 @@
 namespace {
 
 constexpr int VT = 128, QB = 128, DD = 64, TILES = 2, NSLOT = 4, NACC = 3, EW = 16;
-constexpr int Q_SLOT = QB * DD * 4;              // hi image of one 128-query block: 32 KB
-constexpr int Q_BLK = 2 * Q_SLOT;                // [hi | lo] per block in the image (flat_qimage_kernel with 128-row blocks)
-constexpr int MAX_Q = 8192;
+constexpr int Q_HI = QB * DD * 4;                // hi image of one 128-query block: 32 KB
+constexpr int Q_EXT = QB * 8 * 4;                // its threshold rows k = 64 … 71: 4 KB, contiguous behind the hi image (K-major core matrices)
+constexpr int Q_SLOT = Q_HI + Q_EXT;
+constexpr int Q_BLK = 2 * Q_HI;                  // stride of a block in the image (flat_qimage_kernel with 128-row blocks, hi only)
+constexpr int MAX_Q = 65536;                     // survivors.cuh keeps the query in 16 bits
 constexpr int CAPW = 256;
 constexpr int NT_F = (EW + 3) * 32;
-constexpr size_t SMEM_F = (size_t)NSLOT * Q_SLOT + (size_t)EW * WarpSurvivors<CAPW>::BYTES + (size_t)MAX_Q * 4;
+constexpr size_t SMEM_F = (size_t)NSLOT * Q_SLOT + (size_t)EW * WarpSurvivors<CAPW>::BYTES + Q_EXT;
+
+// round a non-negative float UP to a tf32-representable value (the tensor core ignores the low 13 mantissa bits)
+__device__ __forceinline__ float tf32_up(float x) { return __uint_as_float((__float_as_uint(x) + 0x1FFFu) & 0xFFFFE000u); }
+
+// per round: rows k = 64 … 71 of every query's image = (margin rounded up, −thr_hi, −thr_lo, 0, 0, 0, 0, 0).  Padding queries carry
+// thr = FLT_MAX: −1e30 keeps their accumulators negative without an infinity inside the tensor core.
+__global__ void __launch_bounds__(256) flat_filter_ext_kernel(const float* __restrict__ thr, const float* __restrict__ qmarg, int nq_pad,
+                                                              unsigned char* __restrict__ qimg) {
+    const int r = blockIdx.x * 256 + threadIdx.x;
+    if (r >= nq_pad) return;
+    const float t = fminf(__ldg(thr + r), 1e30f);
+    const float th = umma::tf32_hi(t), tl = umma::tf32_hi(t - th);
+    unsigned char* ext = qimg + (size_t)(r / QB) * Q_BLK + Q_HI;
+    const int rr = r % QB;
+    const uint32_t off = (uint32_t)(((rr >> 3) << 7) + ((rr & 7) << 4));
+    *reinterpret_cast<float4*>(ext + off) = make_float4(tf32_up(__ldg(qmarg + r)), -th, -tl, 0.f);
+    *reinterpret_cast<float4*>(ext + (QB / 8) * 128 + off) = make_float4(0.f, 0.f, 0.f, 0.f);
+}
 
 __global__ void __launch_bounds__(NT_F, 1)
 flat_filter_tc_kernel(const float* __restrict__ x, long long n_rows, const unsigned char* __restrict__ qimg, int n_blocks,
@@ -43,7 +68,7 @@ flat_filter_tc_kernel(const float* __restrict__ x, long long n_rows, const unsig
     extern __shared__ __align__(1024) unsigned char smem[];
     unsigned char* qbuf = smem;                                  // [NSLOT][Q_SLOT]
     unsigned char* surv_mem = qbuf + NSLOT * Q_SLOT;             // [EW][WarpSurvivors<CAPW>::BYTES]
-    float* th_sm = reinterpret_cast<float*>(surv_mem + EW * WarpSurvivors<CAPW>::BYTES);     // [n_blocks·128] effective thresholds
+    unsigned char* a_ext = surv_mem + EW * WarpSurvivors<CAPW>::BYTES;      // [128 × 8] A tile of the threshold K step (K-major core matrices)
     __shared__ __align__(8) uint64_t bar_qfull[NSLOT], bar_qfree[NSLOT], bar_done[TILES][NACC], bar_free[TILES][NACC];
     __shared__ uint32_t tmem_slot;
     __shared__ float nrm_s[TILES * 4];
@@ -99,14 +124,17 @@ flat_filter_tc_kernel(const float* __restrict__ x, long long n_rows, const unsig
         }
         umma::tmem_st_wait();
     }
-    if (warp < EW) {                                             // effective thresholds of all queries (epilogue warps only use them)
+    if (tid < VT) {                                              // A tile of the threshold K step: row r = (max ‖x‖ of this CTA, 1, 1, 0, 0, 0, 0, 0)
         float nxmax = 0.f;
 #pragma unroll
         for (int i = 0; i < TILES * 4; ++i) nxmax = fmaxf(nxmax, nrm_s[i]);
-        for (int i = tid; i < n_blocks * QB; i += EW * 32) th_sm[i] = fmaf(-__ldg(qmarg + i), nxmax, __ldg(thr + i));
+        const uint32_t off = (uint32_t)(((tid >> 3) << 7) + ((tid & 7) << 4));
+        *reinterpret_cast<float4*>(a_ext + off) = make_float4(tf32_up(nxmax), 1.f, 1.f, 0.f);
+        *reinterpret_cast<float4*>(a_ext + (VT / 8) * 128 + off) = make_float4(0.f, 0.f, 0.f, 0.f);
     }
+    umma::fence_proxy_async();
     umma::fence_before_sync();
-    __syncthreads();                                             // rows in TMEM, thresholds staged
+    __syncthreads();                                             // rows in TMEM, threshold tile staged
     umma::fence_after_sync();
 
     if (warp == EW) {
@@ -129,6 +157,7 @@ flat_filter_tc_kernel(const float* __restrict__ x, long long n_rows, const unsig
         const uint32_t idesc = umma::idesc_tf32(VT, QB);
         constexpr uint32_t lbo_b = (QB / 8) * 128;
         const uint32_t q_s = umma::smem_u32(qbuf), a_t = tmem + ACC_COLS + (uint32_t)t * DD;
+        const uint64_t da_ext = umma::smem_desc(umma::smem_u32(a_ext), (VT / 8) * 128, 128);
         // Unit u = 2c + t uses accumulator a = u % 3 for the k-th time, k = u / 3; the uses of an accumulator alternate between the two
         // tiles.  Its previous use (k − 1, the OTHER tile's) is released on bar_free[1 − t][a], a barrier that counts only that tile's
         // releases: the ((k − 1) / 2)-th; completions go to bar_done[t][a], this tile's (k / 2)-th.  With ONE barrier per accumulator
@@ -152,6 +181,7 @@ flat_filter_tc_kernel(const float* __restrict__ x, long long n_rows, const unsig
 #pragma unroll
                 for (int j = 0; j < DD / 8; ++j)
                     umma::mma_tf32_ts(acc, a_t + 8 * j, db + (uint64_t)((2 * j * lbo_b) >> 4), idesc, j > 0);
+                umma::mma_tf32(acc, da_ext, db + (uint64_t)((2 * (DD / 8) * lbo_b) >> 4), idesc, true);     // + m_q·n − thr_q
                 umma::commit(&bar_done[t][a]);                   // → epilogue of this unit
                 umma::commit(&bar_qfree[sl]);                    // → (with the other tile's) slot sl may be refilled
             }
@@ -182,27 +212,24 @@ flat_filter_tc_kernel(const float* __restrict__ x, long long n_rows, const unsig
                 const uint32_t acc = tmem + lane_off + (uint32_t)a * QB + half * 64 + blk * 32;
                 float s[32];
                 umma::tmem_ld32(acc, s);
-                // branch-free: one predicate-accumulating compare per score decides whether the warp has any survivor at all; only
-                // then is the per-score mask built and handed to the warp's survivor buffer
-                bool any = false;
+                // survive ⇔ accumulator > 0 ⇔ its bit pattern is a positive integer: a 3-input max tree decides whether the warp has any
+                // survivor at all; only then is the per-score mask built and handed to the warp's survivor buffer
+                int mx[11];
 #pragma unroll
-                for (int j4 = 0; j4 < 8; ++j4) {
-                    const float4 t4 = *reinterpret_cast<const float4*>(th_sm + q0 + j4 * 4);
-                    any = any || (s[j4 * 4] > t4.x) || (s[j4 * 4 + 1] > t4.y) || (s[j4 * 4 + 2] > t4.z) || (s[j4 * 4 + 3] > t4.w);
-                }
-                if (row >= n_rows) any = false;
-                if (__any_sync(0xffffffffu, any)) {
-                    uint32_t m = 0;
+                for (int i = 0; i < 10; ++i) mx[i] = __vimax3_s32(__float_as_int(s[3 * i]), __float_as_int(s[3 * i + 1]), __float_as_int(s[3 * i + 2]));
+                mx[10] = max(__float_as_int(s[30]), __float_as_int(s[31]));
+                const int m3a = __vimax3_s32(mx[0], mx[1], mx[2]), m3b = __vimax3_s32(mx[3], mx[4], mx[5]), m3c = __vimax3_s32(mx[6], mx[7], mx[8]);
+                const int top = __vimax3_s32(__vimax3_s32(m3a, m3b, m3c), mx[9], mx[10]);
+                if (__any_sync(0xffffffffu, top > 0 && row < n_rows)) {
+                    uint32_t nm = 0;                             // bit j = score j NOT positive: sign bit of (b − 1) | b, shifted in from the top
 #pragma unroll
-                    for (int j4 = 0; j4 < 8; ++j4) {
-                        const float4 t4 = *reinterpret_cast<const float4*>(th_sm + q0 + j4 * 4);
-                        m |= (s[j4 * 4] > t4.x ? 1u : 0u) << (j4 * 4);
-                        m |= (s[j4 * 4 + 1] > t4.y ? 1u : 0u) << (j4 * 4 + 1);
-                        m |= (s[j4 * 4 + 2] > t4.z ? 1u : 0u) << (j4 * 4 + 2);
-                        m |= (s[j4 * 4 + 3] > t4.w ? 1u : 0u) << (j4 * 4 + 3);
+                    for (int j = 31; j >= 0; --j) {
+                        const int bj = __float_as_int(s[j]);
+                        nm = __funnelshift_l((uint32_t)((bj - 1) | bj), nm, 1);
                     }
+                    uint32_t m = ~nm;
                     if (row >= n_rows) m = 0;
-                    surv.add_block(m, acc, q0, (int)(row - 0), count, cand_s, stride, kprev, cand_r, cap, flags);   // S̃, replaced by flat_rescore_kernel
+                    surv.add_block(m, acc, q0, (int)row, count, cand_s, stride, kprev, cand_r, cap, flags);   // value replaced by flat_rescore_kernel
                 }
             }
             umma::fence_before_sync();
@@ -227,8 +254,15 @@ bool rb_flat_filtered(int nq) {
     return on && nq > 128 && nq <= MAX_Q;
 }
 
-// one round: rows [0, n_rows) of x (the caller offsets x) against n_blocks·128 queries (image in 128-query blocks), thr / qmarg / count
-// [n_blocks·128]
+// start of a filtered round (after thr has been written): the threshold rows of the query image
+int rb_flat_filter_thresholds(const float* thr, const float* qmarg, int nq_pad, unsigned char* qimg, cudaStream_t st) {
+    flat_filter_ext_kernel<<<(nq_pad + 255) / 256, 256, 0, st>>>(thr, qmarg, nq_pad, qimg);
+    RB_LAUNCH_CHECK("flat_filter_ext_kernel");
+    return RB200_OK;
+}
+
+// one round: rows [0, n_rows) of x (the caller offsets x) against n_blocks·128 queries (image in 128-query blocks with this round's
+// threshold rows: rb_flat_filter_thresholds), count [n_blocks·128]
 int rb_flat_filter_tc(const float* x, long long n_rows, const unsigned char* qimg, int n_blocks, const float* thr, const float* qmarg, int* count,
                       float* cand_s, long long stride, int kprev, int* cand_r, int cap, int* flags, cudaStream_t st) {
     static bool attr_set = false;
@@ -237,7 +271,7 @@ int rb_flat_filter_tc(const float* x, long long n_rows, const unsigned char* qim
         attr_set = true;
     }
     const long long n_cta = (n_rows + TILES * VT - 1) / (TILES * VT);
-    RB_REQUIRE(n_rows >= 1 && n_rows < (1ll << 31) && n_blocks >= 1 && n_blocks * QB <= MAX_Q, "flat_filter: 1..2^31 rows, at most 8192 queries");
+    RB_REQUIRE(n_rows >= 1 && n_rows < (1ll << 31) && n_blocks >= 1 && n_blocks * QB <= MAX_Q, "flat_filter: 1..2^31 rows, at most 65536 queries");
     flat_filter_tc_kernel<<<(unsigned)n_cta, NT_F, SMEM_F, st>>>(x, n_rows, qimg, n_blocks, thr, qmarg, count, cand_s, stride, kprev, cand_r, cap,
                                                                   flags);
     RB_LAUNCH_CHECK("flat_filter_tc_kernel");

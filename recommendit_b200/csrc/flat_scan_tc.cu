@@ -59,7 +59,7 @@ __global__ void __launch_bounds__(256) flat_qimage_kernel(const float* __restric
     unsigned char* base = qimg + (size_t)(r / blk) * 2 * half_bytes;
     const uint32_t off = umma::kmajor_offset(blk, r % blk, c4 * 4);
     *reinterpret_cast<float4*>(base + off) = hi;
-    *reinterpret_cast<float4*>(base + half_bytes + off) = lo;
+    if (blk == 64) *reinterpret_cast<float4*>(base + half_bytes + off) = lo;      // 128-row blocks (the filter): hi only, threshold rows behind it
 }
 
 template <int TILES, int NSLOT, bool A_TMEM, bool FILTER>

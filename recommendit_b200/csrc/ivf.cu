@@ -31,6 +31,7 @@ int rb_flat_scan_tc(const float* x, long long n_rows, const unsigned char* qimg,
 int rb_flat_qimage(const float* q, int nq, int nq_pad, int block_rows, unsigned char* qimg, float* qmarg, cudaStream_t st);
 // one-pass TF32 filter for 129 … 8192 queries (flat_filter_tc.cu: N = 128 MMAs, one issuer warp per tile)
 bool rb_flat_filtered(int nq);
+int rb_flat_filter_thresholds(const float* thr, const float* qmarg, int nq_pad, unsigned char* qimg, cudaStream_t st);
 int rb_flat_filter_tc(const float* x, long long n_rows, const unsigned char* qimg, int n_blocks, const float* thr, const float* qmarg, int* count,
                       float* cand_s, long long stride, int kprev, int* cand_r, int cap, int* flags, cudaStream_t st);
 // streaming round kernel for at most 128 queries (flat_stream_tc.cu: persistent, tensor-map TMA, one-pass filter)
@@ -1068,6 +1069,7 @@ extern "C" int rb200_flat_search(const float* q, int nq, const float* x, int64_t
             flat_round_prep_kernel<<<(unsigned)(((long long)nq_pad * k + NT - 1) / NT), NT, 0, st>>>(bufS[cur], nq, nq_pad, k, cand, rstride,
                                                                                                   thr, count);
             RB_LAUNCH_CHECK("flat_round_prep_kernel");
+            if (filter_tc && (rc = rb_flat_filter_thresholds(thr, qmarg, nq_pad, qimg, st))) return rc;
             rc = streamed    ? rb_flat_stream_tc(x + seen * D, rows, qimg, n_qchunks, thr, qmarg, count, cand, rstride, k, cand_r, cap, flags, st)
                  : filter_tc ? rb_flat_filter_tc(x + seen * D, rows, qimg, nq_pad / 128, thr, qmarg, count, cand, rstride, k, cand_r, cap, flags, st)
                              : rb_flat_scan_tc(x + seen * D, rows, qimg, n_qchunks, thr, qmarg, count, cand, rstride, k, cand_r, cap, flags, st);
