@@ -159,6 +159,13 @@ int rb200_scatter_rows(const int64_t* ids, const float* rows, int B, int D, int6
                        int64_t padding_idx, float* dense_grad, int64_t* uniq_ids, float* uniq_grads,
                        int* n_uniq, int* row_slot, void* workspace, size_t workspace_bytes,
                        void* stream);
+/* The same result in two phases: rb200_scatter_plan needs only the ids (sort, segment heads, compact id list: uniq_ids / n_uniq /
+ * row_slot) and may run on another stream before the gradient rows exist; rb200_scatter_apply then adds the rows up.  Both use the
+ * same workspace (rb200_scatter_workspace_bytes), which must stay untouched in between.  n_rows < 2^31. */
+int rb200_scatter_plan(const int64_t* ids, int B, int64_t n_rows, int64_t padding_idx, int64_t* uniq_ids, int* n_uniq,
+                       int* row_slot, void* workspace, size_t workspace_bytes, void* stream);
+int rb200_scatter_apply(const float* rows, int B, int D, int64_t n_rows, float* dense_grad, const int64_t* uniq_ids,
+                        float* uniq_grads, const int* n_uniq, void* workspace, size_t workspace_bytes, void* stream);
 int rb200_scatter_reset_slots(const int64_t* uniq_ids, const int* n_uniq, int max_uniq, int* row_slot,
                               void* stream);
 /* row_slot[uniq_ids[i]] = i for i < n_uniq[0] (when the compact list was produced without a slot map) */
@@ -236,6 +243,11 @@ int rb200_gather_rows_sharded(const void* const* shard_ptrs, const int64_t* user
 int rb200_push_rows_sharded(void* const* grad_bucket_ptrs, void* const* row_bucket_ptrs, int world, int rank, int64_t capacity,
                             const float* drows, const int64_t* slot_of_sample, int64_t n, int D, const int64_t* send_rows,
                             void* stream);
+/* The plan's row list alone (send_rows [world·capacity] → the owners' row buckets; rb200_push_rows_sharded then takes
+ * send_rows = NULL and row_bucket_ptrs may hold NULLs): it depends only on the ids, so it can be sent at the start of the step and
+ * the owners run rb200_scatter_plan on it under the towers.  Ends with a system-scope fence. */
+int rb200_push_row_lists_sharded(void* const* row_bucket_ptrs, int world, int rank, int64_t capacity, const int64_t* send_rows,
+                                 void* stream);
 /* Reductions of the same step over peer memory ("ncclAllReduce of MLP grads and of {norm², loss}"),
  * deterministic and identical on every rank: each rank reads all ranks' buffers and adds them in rank order.
  *   allreduce_oneshot: out[i] = Σ_k src_ptrs[k][i] (n floats, n % 4 == 0; HOST array of `world` device pointers).

@@ -100,11 +100,14 @@ SIGNATURES = {
     "rb200_bpr_inbatch": (I, [P, P, I, I, I, P, P, P, F, P, SZ, P]),
     "rb200_scatter_workspace_bytes": (SZ, [I, I64]),
     "rb200_scatter_rows": (I, [P, P, I, I, I64, I64, P, P, P, P, P, P, SZ, P]),
+    "rb200_scatter_plan": (I, [P, I, I64, I64, P, P, P, P, SZ, P]),
+    "rb200_scatter_apply": (I, [P, I, I, I64, P, P, P, P, P, SZ, P]),
     "rb200_scatter_reset_slots": (I, [P, P, I, P, P]),
     "rb200_scatter_set_slots": (I, [P, P, I, P, P]),
     "rb200_gather_rows": (I, [P, P, I64, I, I64, P, P]),
     "rb200_gather_rows_sharded": (I, [P, P, I, P, I64, P, I64, I64, I64, I, P, P, P]),
     "rb200_push_rows_sharded": (I, [P, P, I, I, I64, P, P, I64, I, P, P]),
+    "rb200_push_row_lists_sharded": (I, [P, I, I, I64, P, P]),
     "rb200_allreduce_oneshot": (I, [P, I, I64, P, P]),
     "rb200_sharded_scalars_publish": (I, [P, P, F, P, P]),
     "rb200_sharded_scalars_reduce": (I, [P, I, P, P]),

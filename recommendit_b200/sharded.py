@@ -178,12 +178,19 @@ class CudaOps:
         return out
 
     def push_rows_sharded(self, grad_ptrs: List[int], row_ptrs: List[int], rank: int, capacity: int, drows: torch.Tensor,
-                          slot: torch.Tensor, send_rows: torch.Tensor) -> None:
-        """gradient rows + the plan's row list → the owners' receive buckets through the peer pointers (``rb200_push_rows_sharded``)"""
+                          slot: torch.Tensor, send_rows: Optional[torch.Tensor]) -> None:
+        """gradient rows (+ the plan's row list unless ``send_rows`` is None: it then went ahead with :meth:`push_row_lists`) → the
+        owners' receive buckets through the peer pointers (``rb200_push_rows_sharded``)"""
         W = len(grad_ptrs)
         check(self.lib.rb200_push_rows_sharded((C.c_void_p * W)(*grad_ptrs), (C.c_void_p * W)(*row_ptrs), W, rank, capacity, ptr(drows),
                                                ptr(slot), drows.shape[0], drows.shape[1], ptr(send_rows), stream_ptr()),
               "rb200_push_rows_sharded")
+
+    def push_row_lists(self, row_ptrs: List[int], rank: int, capacity: int, send_rows: torch.Tensor) -> None:
+        """the plan's row list → the owners' row buckets (``rb200_push_row_lists_sharded``)"""
+        W = len(row_ptrs)
+        check(self.lib.rb200_push_row_lists_sharded((C.c_void_p * W)(*row_ptrs), W, rank, capacity, ptr(send_rows), stream_ptr()),
+              "rb200_push_row_lists_sharded")
 
     def allreduce_oneshot(self, src_ptrs: List[int], n: int, out: torch.Tensor) -> None:
         W = len(src_ptrs)
@@ -246,6 +253,25 @@ class CudaOps:
             check(self.lib.rb200_scatter_rows(ptr(ids), ptr(rows), B, D, n_rows, padding_row, None, ptr(uniq), ptr(ug), ptr(nu), None,
                                               ptr(ws), wsb, stream_ptr()), "rb200_scatter_rows")
         return uniq, ug, nu
+
+    def scatter_plan(self, ids: torch.Tensor, n_rows: int, padding_row: int):
+        """first phase of :meth:`scatter_rows` (needs only the ids) → (uniq_ids [cap], n_uniq [1] int32, workspace)"""
+        B = ids.numel()
+        uniq = torch.empty(max(B, 1), dtype=torch.int64, device=ids.device)
+        nu = torch.zeros(1, dtype=torch.int32, device=ids.device)
+        wsb = self.lib.rb200_scatter_workspace_bytes(B, n_rows)
+        ws = torch.empty(wsb, dtype=torch.uint8, device=ids.device)        # (not the shared scratch: it has to survive until apply)
+        check(self.lib.rb200_scatter_plan(ptr(ids), B, n_rows, padding_row, ptr(uniq), ptr(nu), None, ptr(ws), wsb, stream_ptr()),
+              "rb200_scatter_plan")
+        return uniq, nu, ws
+
+    def scatter_apply(self, rows: torch.Tensor, n_rows: int, uniq: torch.Tensor, nu: torch.Tensor, ws: torch.Tensor) -> torch.Tensor:
+        """second phase → uniq_grads [cap, D]"""
+        B, D = rows.shape
+        ug = torch.empty(max(B, 1), D, dtype=torch.float32, device=rows.device)
+        check(self.lib.rb200_scatter_apply(ptr(rows), B, D, n_rows, None, ptr(uniq), ptr(ug), ptr(nu), ptr(ws), ws.numel(), stream_ptr()),
+              "rb200_scatter_apply")
+        return ug
 
     def sumsq(self, opt: torch.Tensor, segs: List[Tuple[torch.Tensor, Optional[torch.Tensor], int]]) -> None:
         """opt.sumsq += Σ x² ; a segment is (tensor, count tensor or None, row_len)"""
@@ -444,6 +470,17 @@ class ShardedBPRTrainer:
             dist.all_to_all_single(recv_rows, send_rows[:W * C].contiguous(), group=self.group)
         return slot_s, recv_rows, C
 
+    _side = None
+
+    def _side_stream(self, i: int = 0):
+        """the step's side streams (forked from and joined to the step's stream with events: capturable)"""
+        if self._side is None:
+            # high priority: the exchange plan, the row lists and the sort of the received rows are many small kernels that must not
+            # queue behind the towers' CTAs.  (Running the user tower's backward on a second side stream was tried: the towers' phase
+            # shrank by 20 us but the replay period did not — C4 at world 1 0.273 -> 0.278 ms.)
+            self._side = [torch.cuda.Stream(device=self.dev, priority=-1)]
+        return self._side[i]
+
     def _barrier(self, channel: int) -> None:
         """cross-GPU barrier on the stream (symmetric-memory signal pads; capturable; traps after 60 s instead of hanging)"""
         if self._tab_hdl is not None:
@@ -597,6 +634,23 @@ class ShardedBPRTrainer:
             item_ids = torch.cat([pos_ids, neg_ids])
             self._barrier(0)
             self._mark("barrier0")
+            # Everything that depends only on the ids runs on a side stream under the gather and the towers: the exchange plan, the
+            # plan's row lists to the owners (their own barrier channel), and the owners' sort of the rows they are about to receive
+            # (first phase of the segment sum).  The gradient rows follow after the towers' backward.
+            side = self._side_stream()
+            main = torch.cuda.current_stream(dev)
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                C = self.capacity(3 * B)
+                slot, send_rows = ops.route_padded(user_ids.contiguous(), item_ids, W, self._nu_by_rank, C, self.overflow)
+                g_buf, r_buf, g_ptrs, r_ptrs, _ = self._p2p_buckets(3 * B)
+                ops.push_row_lists(r_ptrs, self.rank, C, send_rows)
+                self._barrier(3)
+                rows_sc = r_buf
+                if self.rank == 0:       # the global padding ids 0 live on rank 0 (local rows 0 and n_user_local): no gradient
+                    nu0 = self.user_table.shape[0]
+                    rows_sc = torch.where((rows_sc == 0) | (rows_sc == nu0), torch.full_like(rows_sc, -1), rows_sc)
+                uq, n_uq, scat_ws = ops.scatter_plan(rows_sc, max(self.table.shape[0], 1), -1)
             rows = ops.gather_rows_sharded(self._shard_ptrs, self._nu_host, user_ids.contiguous(), item_ids, self.n_user_rows,
                                            self.n_item_rows, D, self.err_flag)
             if getattr(self, "_ident", None) is None or self._ident.numel() != 3 * B:
@@ -656,14 +710,12 @@ class ShardedBPRTrainer:
         if p2p:
             # the exchange plan is computed locally (bucket + slot of every request); the gradient rows and the plan's row list are
             # WRITTEN into the owners' receive buckets over NVLink; the barrier makes them visible before the owners' segment sums
-            C = self.capacity(3 * B)
-            slot, send_rows = ops.route_padded(user_ids.contiguous(), item_ids, W, self._nu_by_rank, C, self.overflow)
+            main.wait_stream(side)
             self._mark("route_plan")
-            g_buf, r_buf, g_ptrs, r_ptrs, _ = self._p2p_buckets(3 * B)
-            ops.push_rows_sharded(g_ptrs, r_ptrs, self.rank, C, drows, slot, send_rows)
+            ops.push_rows_sharded(g_ptrs, r_ptrs, self.rank, C, drows, slot, None)
             self._mark("push_rows")
             self._barrier(1)
-            g_rows, rt.recv_rows = g_buf, r_buf
+            g_rows = g_buf
         elif padded:
             g_pad = torch.empty(W * C + 1, D, **f32)               # empty slots are skipped at the owner (their row is -1);
             g_pad.index_copy_(0, rt.inv, drows)                    # row W·C collects the overflowed requests and is not sent
@@ -676,28 +728,35 @@ class ShardedBPRTrainer:
             g_rows = ops.gather_rows(drows, rt.perm)
             if W > 1:
                 g_rows = all_to_all_var(g_rows, rt.send_counts, rt.recv_counts, self.group)
-        rows_sc = rt.recv_rows
-        if self.rank == 0:       # the global padding ids 0 live on rank 0 (local rows 0 and n_user_local): no gradient
-            nu0 = self.user_table.shape[0]
-            rows_sc = torch.where((rows_sc == 0) | (rows_sc == nu0), torch.full_like(rows_sc, -1), rows_sc)
-        self._mark("grad_exchange")
-        uq, ug, n_uq = ops.scatter_rows(rows_sc, g_rows, max(self.table.shape[0], 1), -1)
+        if p2p:
+            self._mark("grad_exchange")
+            if sym_red:          # the MLP gradients of all ranks are complete (barrier 1): their reduction runs beside the segment sums
+                gm, sc, gm_ptrs, sc_ptrs, _ = self._mlp_sym
+                side.wait_stream(main)
+                with torch.cuda.stream(side):
+                    g_red = torch.empty(gm.numel(), **f32)
+                    ops.allreduce_oneshot(gm_ptrs, gm.numel(), g_red)
+            ug = ops.scatter_apply(g_rows, max(self.table.shape[0], 1), uq, n_uq, scat_ws)
+        else:
+            rows_sc = rt.recv_rows
+            if self.rank == 0:       # the global padding ids 0 live on rank 0 (local rows 0 and n_user_local): no gradient
+                nu0 = self.user_table.shape[0]
+                rows_sc = torch.where((rows_sc == 0) | (rows_sc == nu0), torch.full_like(rows_sc, -1), rows_sc)
+            self._mark("grad_exchange")
+            uq, ug, n_uq = ops.scatter_rows(rows_sc, g_rows, max(self.table.shape[0], 1), -1)
         self._mark("scatter")
         opt64, opt32 = self.opt.view(torch.float64), self.opt.view(torch.float32)
         if sym_red:
             # peer-memory reductions (every rank adds all ranks' buffers in rank order: identical everywhere, no broadcast, no NCCL):
             # the MLP gradients were complete before barrier 1; the scalars need one more barrier after the local segment sums
-            gm, sc, gm_ptrs, sc_ptrs, _ = self._mlp_sym
-            g_red = torch.empty(gm.numel(), **f32)
-            ops.allreduce_oneshot(gm_ptrs, gm.numel(), g_red)
-            g_mlp = g_red[:Pu + Pi]
-            self._mark("mlp_allreduce")
             ops.sumsq(self.opt, [(ug, n_uq, D)])                           # Σg² of this rank's shard rows
             ops.scalars_publish(self.opt, loss, 1.0 / W, sc)
             self._mark("sumsq_publish")
             self._barrier(2)
             self._mark("barrier2")
             ops.scalars_reduce(sc_ptrs, self.opt)                          # opt.sumsq = Σ over shards, opt.loss = global mean loss
+            main.wait_stream(side)                                         # the reduced MLP gradients
+            g_mlp = g_red[:Pu + Pi]
             ops.sumsq(self.opt, [(g_mlp, None, 0)])                        # + the (replicated) MLP gradient, counted once
         else:
             if W > 1:

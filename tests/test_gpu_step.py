@@ -385,3 +385,41 @@ def test_train_epoch_pipelined_equals_step_host_loop(golden):
     for (k, a), (_, b) in zip(m1.state_dict().items(), m2.state_dict().items()):
         assert torch.equal(a, b), k
     assert np.isnan(t2.train_epoch([]))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("B,n_rows,D,kind", [(37000, 700000, 128, "zipf"), (3000, 500, 64, "uniform"), (20000, 90000, 128, "empty_slots")])
+def test_scatter_plan_then_apply_equals_scatter_rows(B, n_rows, D, kind):
+    """Two-phase segment sum (rb200_scatter_plan on the ids — on another stream, before the rows exist — then rb200_scatter_apply):
+    bit-identical to rb200_scatter_rows, including empty slots (id -1: the padded exchange's unused bucket slots) and popular ids."""
+    from recommendit_b200 import _lib
+    lib = _lib.load()
+    rng = np.random.default_rng(B)
+    ids = (rng.zipf(1.05, B) - 1) % n_rows if kind == "zipf" else rng.integers(0, n_rows, B)
+    if kind == "empty_slots":
+        ids[rng.random(B) < 0.5] = -1
+    d_ids = dev(ids)
+    wsb = lib.rb200_scatter_workspace_bytes(B, n_rows)
+    uq1 = torch.empty(B, dtype=torch.int64, device="cuda"); ug1 = torch.full((B, D), float("nan"), device="cuda")
+    nu1 = torch.zeros(1, dtype=torch.int32, device="cuda")
+    uq2 = torch.empty_like(uq1); ug2 = torch.full((B, D), float("nan"), device="cuda"); nu2 = torch.zeros_like(nu1)
+    ws1, ws2 = _lib.workspace(wsb, "cuda"), _lib.workspace(wsb, "cuda")
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):                                          # the plan: ids only, side stream
+        _lib.check(lib.rb200_scatter_plan(d_ids.data_ptr(), B, n_rows, -1, uq2.data_ptr(), nu2.data_ptr(), None, ws2.data_ptr(), wsb,
+                                          _lib.stream_ptr()))
+    rows = rng.standard_normal((B, D)).astype(np.float32)                  # the rows come later
+    d_rows = dev(rows)
+    _lib.check(lib.rb200_scatter_rows(d_ids.data_ptr(), d_rows.data_ptr(), B, D, n_rows, -1, None, uq1.data_ptr(), ug1.data_ptr(),
+                                      nu1.data_ptr(), None, ws1.data_ptr(), wsb, _lib.stream_ptr()))
+    torch.cuda.current_stream().wait_stream(side)
+    _lib.check(lib.rb200_scatter_apply(d_rows.data_ptr(), B, D, n_rows, None, uq2.data_ptr(), ug2.data_ptr(), nu2.data_ptr(), ws2.data_ptr(),
+                                       wsb, _lib.stream_ptr()))
+    n1, n2 = int(nu1.item()), int(nu2.item())
+    assert n1 == n2 == len(np.unique(ids[ids >= 0]))
+    assert torch.equal(uq1[:n1], uq2[:n2]) and torch.equal(ug1[:n1], ug2[:n2])
+    exp = np.zeros((n_rows, D), np.float64)
+    np.add.at(exp, ids[ids >= 0], rows[ids >= 0].astype(np.float64))
+    got = ug2[:n2].cpu().numpy()
+    np.testing.assert_allclose(got, exp[uq2[:n2].cpu().numpy()], rtol=0, atol=5e-4 if kind == "zipf" else 1e-5)
