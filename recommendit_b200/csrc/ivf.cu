@@ -287,33 +287,67 @@ __global__ void __launch_bounds__(NT) probe_finish_kernel(const int64_t* __restr
     if (lane == 0) totals[q] = running;
 }
 
-__global__ void pair_keys_kernel(const int* __restrict__ probes, long long n_pairs, int nlist, int* __restrict__ keys,
-                                 int* __restrict__ vals) {
+// One block: list_qstart = exclusive scan of the per-list probe counts (n_lists + 1 entries), cand_off = exclusive scan of the per-query
+// candidate totals (nq + 1 entries), out2 = {Σ, max} of the totals — the plan's two cub scans, a memset and a reduction in one launch.
+constexpr int PS_NT = 1024;
+__global__ void __launch_bounds__(PS_NT) plan_scans_kernel(const int* __restrict__ list_qcount, int n_lists, int* __restrict__ list_qstart,
+                                                           const long long* __restrict__ totals, int nq, long long* __restrict__ cand_off,
+                                                           long long* __restrict__ out2) {
+    __shared__ long long wsum[PS_NT / 32];
+    __shared__ long long s_carry, s_max;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    long long vmax = 0;
+    for (int pass = 0; pass < 2; ++pass) {
+        const int n = pass == 0 ? n_lists : nq;
+        if (tid == 0) s_carry = 0;
+        __syncthreads();
+        for (int base = 0; base < n + 1; base += PS_NT) {
+            const int i = base + tid;
+            long long v = 0;
+            if (i < n) v = pass == 0 ? (long long)list_qcount[i] : totals[i];
+            if (pass == 1) vmax = v > vmax ? v : vmax;
+            long long incl = v;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const long long t = __shfl_up_sync(RB_FULL_MASK, incl, o);
+                if (lane >= o) incl += t;
+            }
+            if (lane == 31) wsum[warp] = incl;
+            __syncthreads();
+            long long before = s_carry;
+            for (int w = 0; w < warp; ++w) before += wsum[w];
+            if (i < n + 1) {
+                if (pass == 0) list_qstart[i] = (int)(before + incl - v);
+                else cand_off[i] = before + incl - v;
+            }
+            __syncthreads();
+            if (tid == PS_NT - 1) s_carry = before + incl;
+            __syncthreads();
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { const long long om = __shfl_xor_sync(RB_FULL_MASK, vmax, o); vmax = om > vmax ? om : vmax; }
+    if (lane == 0) wsum[warp] = vmax;
+    __syncthreads();
+    if (tid == 0) {
+        long long m = 0;
+        for (int w = 0; w < PS_NT / 32; ++w) m = wsum[w] > m ? wsum[w] : m;
+        out2[0] = s_carry;          // carry of the second pass = Σ totals
+        out2[1] = m;
+    }
+}
+
+// (list, query) pairs grouped by list without a sort: pair i of list l goes to one of the list's slots [list_qstart[l], list_qstart[l+1]),
+// handed out by counting the list's counter down.  The order of a list's pairs is arbitrary (it only decides which query sits in which
+// column of the scan's MMAs: every candidate's destination comes from cand_base, so the results do not depend on it).
+__global__ void pair_scatter_kernel(const int* __restrict__ probes, long long n_pairs, const int* __restrict__ list_qstart,
+                                    int* __restrict__ list_qcount, int* __restrict__ pair_qp) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_pairs) return;
     const int l = probes[i];
-    keys[i] = l >= 0 ? l : nlist;     // invalid probes sort to the end
-    vals[i] = (int)i;
-}
-
-// Σ and max of the per-query candidate counts (one block; integer arithmetic, order-independent)
-__global__ void __launch_bounds__(NT) reduce_totals_kernel(const long long* __restrict__ totals, int nq, long long* __restrict__ out2) {
-    __shared__ long long ssum[NT / 32], smax[NT / 32];
-    long long s = 0, m = 0;
-    for (int i = threadIdx.x; i < nq; i += NT) { const long long t = totals[i]; s += t; m = t > m ? t : m; }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        s += __shfl_xor_sync(RB_FULL_MASK, s, o);
-        const long long om = __shfl_xor_sync(RB_FULL_MASK, m, o);
-        m = om > m ? om : m;
-    }
-    if ((threadIdx.x & 31) == 0) { ssum[threadIdx.x >> 5] = s; smax[threadIdx.x >> 5] = m; }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        s = 0; m = 0;
-        for (int w = 0; w < NT / 32; ++w) { s += ssum[w]; m = smax[w] > m ? smax[w] : m; }
-        out2[0] = s; out2[1] = m;
-    }
+    if (l < 0) return;
+    const int slot = atomicSub(list_qcount + l, 1) - 1;
+    pair_qp[list_qstart[l] + slot] = (int)i;
 }
 
 // ------------------------------------------------------------------------------------------ //
@@ -760,19 +794,9 @@ __global__ void __launch_bounds__(NT) merge_gather_kernel(const float* __restric
 
 struct PlanLayout {
     float* coarse; int* probes; int* cand_base; long long* totals; long long* cand_off; long long* tot2;
-    int* list_qcount; int* list_qstart; int* pair_keys; int* pair_vals; int* pair_keys_sorted; int* pair_qp;
+    int* list_qcount; int* list_qstart; int* pair_qp;
     float* probe_scores; int64_t* probe_ids;
-    char* temp; size_t temp_bytes;
 };
-size_t plan_temp_bytes(int nq, int nlist, int nprobe) {
-    size_t a = 0, b = 0, c = 0;
-    const long long np = (long long)nq * nprobe;
-    cub::DeviceRadixSort::SortPairs(nullptr, a, (const int*)nullptr, (int*)nullptr, (const int*)nullptr, (int*)nullptr, (int)np);
-    cub::DeviceScan::ExclusiveSum(nullptr, b, (const int*)nullptr, (int*)nullptr, nlist + 1);
-    cub::DeviceScan::ExclusiveSum(nullptr, c, (const long long*)nullptr, (long long*)nullptr, nq + 1);
-    size_t m = a > b ? a : b;
-    return m > c ? m : c;
-}
 bool carve_plan(RbArena& ar, int nq, int nlist, int nprobe, PlanLayout& L) {
     const size_t np = (size_t)nq * nprobe;
     L.coarse = ar.take<float>((size_t)nq * nlist);
@@ -780,11 +804,8 @@ bool carve_plan(RbArena& ar, int nq, int nlist, int nprobe, PlanLayout& L) {
     L.totals = ar.take<long long>((size_t)nq + 1); L.cand_off = ar.take<long long>((size_t)nq + 1);
     L.tot2 = ar.take<long long>(2);
     L.list_qcount = ar.take<int>((size_t)nlist + 2); L.list_qstart = ar.take<int>((size_t)nlist + 2);
-    L.pair_keys = ar.take<int>(np); L.pair_vals = ar.take<int>(np);
-    L.pair_keys_sorted = ar.take<int>(np); L.pair_qp = ar.take<int>(np);
+    L.pair_qp = ar.take<int>(np);
     L.probe_scores = ar.take<float>(np); L.probe_ids = ar.take<int64_t>(np);
-    L.temp_bytes = plan_temp_bytes(nq, nlist, nprobe);
-    L.temp = ar.take<char>(L.temp_bytes);
     return ar.ok();
 }
 
@@ -854,8 +875,8 @@ extern "C" int rb200_ivf_build(const float* x, int64_t n, int D, const int32_t* 
 
 extern "C" size_t rb200_ivf_plan_workspace_bytes(int nq, int nlist, int nprobe) {
     const size_t np = (size_t)nq * nprobe;
-    return 256 * 18 + sizeof(float) * ((size_t)nq * nlist + np) + sizeof(int64_t) * np + sizeof(int) * (6 * np + 2 * ((size_t)nlist + 2)) +
-           sizeof(long long) * (2 * ((size_t)nq + 1) + 2) + plan_temp_bytes(nq, nlist, nprobe);
+    return 256 * 18 + sizeof(float) * ((size_t)nq * nlist + np) + sizeof(int64_t) * np + sizeof(int) * (3 * np + 2 * ((size_t)nlist + 2)) +
+           sizeof(long long) * (2 * ((size_t)nq + 1) + 2);
 }
 
 extern "C" int rb200_ivf_search_plan(const float* q, int nq, int D, const float* centroids, int nlist, int nprobe,
@@ -882,19 +903,14 @@ extern "C" int rb200_ivf_search_plan(const float* q, int nq, int D, const float*
     probe_finish_kernel<<<(unsigned)(((long long)nq * 32 + NT - 1) / NT), NT, 0, st>>>(L.probe_ids, nq, nprobe, offsets, L.probes, L.cand_base, L.totals,
                                                          L.list_qcount);
     RB_LAUNCH_CHECK("probe_finish_kernel");
+    // the (list, query) pairs grouped by list: a counting sort on the per-list probe counts of probe_finish_kernel — one scan launch
+    // (lists and per-query candidate offsets together) and one scatter, instead of cub's radix sort + two scans + a reduction
+    // (54 of the plan's 193 us in profiles/r01_launches_ivf_v7.csv)
     const long long np = (long long)nq * nprobe;
-    pair_keys_kernel<<<(unsigned)((np + NT - 1) / NT), NT, 0, st>>>(L.probes, np, nlist, L.pair_keys, L.pair_vals);
-    RB_LAUNCH_CHECK("pair_keys_kernel");
-    size_t tb = L.temp_bytes;
-    RB_CUDA(cub::DeviceRadixSort::SortPairs(L.temp, tb, (const int*)L.pair_keys, L.pair_keys_sorted, (const int*)L.pair_vals,
-                                            L.pair_qp, (int)np, 0, key_bits_i32(nlist + 1), st));
-    tb = L.temp_bytes;
-    RB_CUDA(cub::DeviceScan::ExclusiveSum(L.temp, tb, (const int*)L.list_qcount, L.list_qstart, nlist + 1, st));
-    RB_CUDA(cudaMemsetAsync(L.totals + nq, 0, sizeof(long long), st));
-    tb = L.temp_bytes;
-    RB_CUDA(cub::DeviceScan::ExclusiveSum(L.temp, tb, (const long long*)L.totals, L.cand_off, nq + 1, st));
-    reduce_totals_kernel<<<1, NT, 0, st>>>(L.totals, nq, L.tot2);
-    RB_LAUNCH_CHECK("reduce_totals_kernel");
+    plan_scans_kernel<<<1, PS_NT, 0, st>>>(L.list_qcount, nlist, L.list_qstart, L.totals, nq, L.cand_off, L.tot2);
+    RB_LAUNCH_CHECK("plan_scans_kernel");
+    pair_scatter_kernel<<<(unsigned)((np + NT - 1) / NT), NT, 0, st>>>(L.probes, np, L.list_qstart, L.list_qcount, L.pair_qp);
+    RB_LAUNCH_CHECK("pair_scatter_kernel");
     if (!total_candidates_host) return RB200_OK;      // asynchronous form (CUDA-graph capturable): the caller sizes by upper bounds
     long long h[2] = {0, 0};
     RB_CUDA(cudaMemcpyAsync(h, L.tot2, sizeof(h), cudaMemcpyDeviceToHost, st));
