@@ -621,7 +621,8 @@ def make_flat_shard(dev, rows: int, seed: int):
 
 def bench_flat(args, dev, rows: int = 12_500_000, nqs=(4096, 64), reps: int = 3):
     """BASELINE C5, the work of ONE of its 8 shards: exhaustive inner-product top-500 over 12.5 M x 64 rows (100 M / 8) —
-    rb200_flat_search = first exact chunk, then threshold-pruned tcgen05 rounds (csrc/flat_scan_tc.cu).  The N>1 line adds the
+    rb200_flat_search = first exact chunk, then threshold-pruned tcgen05 rounds (more than 128 queries: csrc/flat_filter_tc.cu, one-pass
+    TF32 filter + exact re-score of the survivors; at most 128: csrc/flat_stream_tc.cu, tensor-map TMA stream).  The N>1 line adds the
     all-gather + merge across shards."""
     import recommendit_b200 as R
     pk = peaks()
@@ -656,20 +657,27 @@ def bench_flat(args, dev, rows: int = 12_500_000, nqs=(4096, 64), reps: int = 3)
                "prefix_1M_parity": {"ok": parity_ok, "ids_identical_frac": float(same.float().mean()),
                                     "ids_differing_are_score_ties_within": 4e-7, "max_score_diff": float((s1.double() - ref.values).abs().max()),
                                     "rule": "ids identical except exact/rounding-level score ties (north_star); scores within 2e-6"}}
-        if nq >= 1024:
-            ent["roofline"] = {"kernel": "flat_scan_tc_kernel (3xTF32: 3 MMAs per logical MMA)", "bound": "tensor", "unit": "TFLOP/s",
-                               "achieved": flops / (t * 1e-3) / 1e12, "issued_tflops": 3 * flops / (t * 1e-3) / 1e12,
+        if nq > 128:
+            issued = flops * 9.0 / 8.0                        # 8 K steps of scores + 1 K step that subtracts the threshold
+            ent["roofline"] = {"kernel": "flat_filter_tc_kernel (one-pass TF32 filter, N = 128 MMAs, threshold compared on the tensor core; "
+                                         "survivors re-scored in fp32 by flat_rescore_kernel)",
+                               "bound": "tensor", "unit": "TFLOP/s",
+                               "achieved": flops / (t * 1e-3) / 1e12, "issued_tflops": issued / (t * 1e-3) / 1e12,
                                "peak": pk["bf16_tflops"], "frac": flops / (t * 1e-3) / 1e12 / pk["bf16_tflops"],
-                               "traffic": ncu_traffic("flat_scan_tc_kernel"), "traffic_note": "per launch; ncu --set full of the 786 432-row round of a 2 M-row search "
-                               "(profiles/r01_flat_scan_tc.md): dram read 245.8 MB + write 12.1 MB for 201 MB of rows — the shard is "
-                               "read once; tensor pipe 56.7 % active",
-                               "note": "logical 2·nq·N·D flops vs the measured bf16 peak; kind::tf32 peaks at half of it and 3xTF32 "
-                                       "issues 3 MMAs per logical one, so 1/6 of the bf16 peak is this kernel's ceiling"}
+                               "frac_of_tf32_peak": flops / (t * 1e-3) / 1e12 / (pk["bf16_tflops"] / 2.0),
+                               "traffic": ncu_traffic("flat_filter_tc_kernel"),
+                               "traffic_note": "per launch of the largest round (6.29 M rows = 1.61 GB of the 12.5 M-row shard): "
+                                               "profiles/r02_flat_filter.md",
+                               "note": "logical 2·nq·N·D flops of the WHOLE search (all rounds, re-score and selects included in the time) "
+                                       "vs the measured bf16 peak; kind::tf32 peaks at half of it (frac_of_tf32_peak)"}
         else:
             by = rows * 64 * 4.0
-            ent["roofline"] = {"kernel": "flat_scan_tc_kernel", "bound": "hbm", "unit": "GB/s", "achieved": by / (t * 1e-3) / 1e9,
-                               "peak": pk["hbm_gbs"], "frac": by / (t * 1e-3) / 1e9 / pk["hbm_gbs"], "traffic": ncu_traffic("flat_scan_tc_kernel_small_nq"),
-                               "note": "the shard is read once per batch: N·D·4 bytes"}
+            ent["roofline"] = {"kernel": "flat_stream_tc_kernel (persistent, tensor-map TMA, one-pass TF32 filter)", "bound": "hbm", "unit": "GB/s",
+                               "achieved": by / (t * 1e-3) / 1e9,
+                               "peak": pk["hbm_gbs"], "frac": by / (t * 1e-3) / 1e9 / pk["hbm_gbs"], "traffic": ncu_traffic("flat_stream_tc_kernel"),
+                               "traffic_note": "per launch of the largest round (8.31 M rows = 2.13 GB): profiles/r02_flat_stream.md",
+                               "note": "the shard is read once per batch: N·D·4 bytes over the time of the WHOLE search (four rounds, "
+                                       "re-score and selects included)"}
         out[f"nq{nq}"] = ent
     del x
     torch.cuda.empty_cache()

@@ -53,7 +53,7 @@ flat_stream_tc_kernel(const __grid_constant__ CUtensorMap xmap, long long n_rows
     extern __shared__ __align__(1024) unsigned char smem[];
     unsigned char* stages = smem;                                // [NST][STAGE_BYTES], 1024-byte aligned atoms
     unsigned char* qbuf = smem + NST * STAGE_BYTES;              // [NCH][Q_HALF]
-    unsigned char* surv_mem = qbuf + NCH * Q_HALF;               // [8][WarpSurvivors<CAPW>::BYTES] (survivors.cuh)
+    unsigned char* surv_mem = qbuf + NCH * Q_HALF;               // [8][WarpSurvivors<CAPW, false>::BYTES] (survivors.cuh)
     __shared__ __align__(8) uint64_t bar_full[NST], bar_empty[NST], bar_done[NACC], bar_free[NACC], bar_q;
     __shared__ uint32_t tmem_slot;
     __shared__ volatile int dead;                                // a barrier wait timed out: every role stops waiting (flags[1] tells the host)
@@ -131,8 +131,8 @@ flat_stream_tc_kernel(const __grid_constant__ CUtensorMap xmap, long long n_rows
         const int grp = warp >> 2, wq = warp & 3;
         const int r_own = (wq << 5) + lane;
         const uint32_t lane_off = (uint32_t)(wq * 32) << 16;
-        WarpSurvivors<CAPW> surv;
-        surv.init(surv_mem + warp * WarpSurvivors<CAPW>::BYTES, lane);
+        WarpSurvivors<CAPW, false> surv;
+        surv.init(surv_mem + warp * WarpSurvivors<CAPW, false>::BYTES, lane);
         for (int i = grp; i < n_mine; i += 2) {
             const int st = i % NST, a = i % NACC;
             const long long row = ((long long)blockIdx.x + (long long)i * gridDim.x) * VT + r_own;
@@ -217,7 +217,7 @@ template <int NCH>
 int launch_flat_stream(const CUtensorMap& map, long long n_rows, int n_tiles, const unsigned char* qimg, const float* thr, const float* qmarg,
                        int* count, float* cand_s, long long stride, int kprev, int* cand_r, int cap, int* flags, cudaStream_t st) {
     static bool attr_set = false;
-    constexpr size_t smem = (size_t)NST * STAGE_BYTES + (size_t)NCH * Q_HALF + 8 * (size_t)WarpSurvivors<CAPW>::BYTES;
+    constexpr size_t smem = (size_t)NST * STAGE_BYTES + (size_t)NCH * Q_HALF + 8 * (size_t)WarpSurvivors<CAPW, false>::BYTES;
     if (!attr_set) {
         RB_CUDA(cudaFuncSetAttribute(flat_stream_tc_kernel<NCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_set = true;

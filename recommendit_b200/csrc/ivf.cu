@@ -32,6 +32,7 @@ int rb_flat_qimage(const float* q, int nq, int nq_pad, int block_rows, unsigned 
 // one-pass TF32 filter for 129 … 8192 queries (flat_filter_tc.cu: N = 128 MMAs, one issuer warp per tile)
 bool rb_flat_filtered(int nq);
 int rb_flat_filter_thresholds(const float* thr, const float* qmarg, int nq_pad, unsigned char* qimg, cudaStream_t st);
+int rb_flat_filter_image(const float* q, int nq, int nq_pad, unsigned char* qimg, float* qmarg, cudaStream_t st);
 int rb_flat_filter_tc(const float* x, long long n_rows, const unsigned char* qimg, int n_blocks, const float* thr, const float* qmarg, int* count,
                       float* cand_s, long long stride, int kprev, int* cand_r, int cap, int* flags, cudaStream_t st);
 // streaming round kernel for at most 128 queries (flat_stream_tc.cu: persistent, tensor-map TMA, one-pass filter)
@@ -1077,7 +1078,7 @@ extern "C" int rb200_flat_search(const float* q, int nq, const float* x, int64_t
         const bool streamed = rb_flat_streamed(n_qchunks);     // ≤ 128 queries: the scan is bound by reading the rows
         const bool filter_tc = !streamed && rb_flat_filtered(nq);     // 129 … 8192 queries: bound by the tensor pipe
         const bool filtered = streamed || filter_tc;           // one-pass TF32 filter: survivors are re-scored in fp32 before the select
-        if ((rc = rb_flat_qimage(q, nq, nq_pad, filter_tc ? 128 : 64, qimg, qmarg, st))) return rc;
+        if ((rc = filter_tc ? rb_flat_filter_image(q, nq, nq_pad, qimg, qmarg, st) : rb_flat_qimage(q, nq, nq_pad, 64, qimg, qmarg, st))) return rc;
         const long long rstride = (long long)k + cap;
         for (long long seen = n0; seen < n;) {
             const long long upto = (n / growth >= seen) ? seen * growth : n;

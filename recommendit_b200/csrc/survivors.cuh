@@ -14,7 +14,10 @@
 #include "common.cuh"
 #include "umma.cuh"
 
-template <int CAPW>
+// VAL = false: the filter kernels — their accumulator holds an approximate (and threshold-shifted) score that flat_rescore_kernel replaces
+// anyway, so only (query, row) are kept: no score has to be re-read from TMEM and the epilogue can release its accumulator as soon as the
+// scores are in registers.
+template <int CAPW, bool VAL = true>
 struct WarpSurvivors {
     float* sc;                 // [CAPW] scores
     int* rw;                   // [CAPW] rows (relative to the round's first row)
@@ -49,7 +52,7 @@ struct WarpSurvivors {
                 const int e = e0 + i * 32 + lane;
                 if (qv[i] >= 0) {
                     if (pos[i] < cap) {
-                        cand_s[(long long)qv[i] * stride + kprev + pos[i]] = sc[e];
+                        if (VAL) cand_s[(long long)qv[i] * stride + kprev + pos[i]] = sc[e];
                         cand_r[(long long)qv[i] * cap + pos[i]] = rw[e];
                     } else {
                         flags[0] = 1;      // survivor list full: the caller redoes the search on the chunked path
@@ -74,11 +77,11 @@ struct WarpSurvivors {
             while (u) {
                 const int j = __ffs(u) - 1;
                 u &= u - 1;
-                const float v = umma::tmem_ld1(acc + j);
+                const float v = VAL ? umma::tmem_ld1(acc + j) : 0.f;
                 if ((m >> j) & 1u) {
                     const int pos = atomicAdd(count + q0 + j, 1);
                     if (pos < cap) {
-                        cand_s[(long long)(q0 + j) * stride + kprev + pos] = v;
+                        if (VAL) cand_s[(long long)(q0 + j) * stride + kprev + pos] = v;
                         cand_r[(long long)(q0 + j) * cap + pos] = row;
                     } else {
                         flags[0] = 1;
@@ -92,12 +95,12 @@ struct WarpSurvivors {
         while (u) {
             const int j = __ffs(u) - 1;
             u &= u - 1;
-            const float v = umma::tmem_ld1(acc + j);
+            const float v = VAL ? umma::tmem_ld1(acc + j) : 0.f;
             const bool mine = (m >> j) & 1u;
             const uint32_t b = __ballot_sync(0xffffffffu, mine);
             if (mine) {
                 const int idx = fill + __popc(b & lt);
-                sc[idx] = v;
+                if (VAL) sc[idx] = v;
                 rw[idx] = row;
                 qq[idx] = (unsigned short)(q0 + j);
             }

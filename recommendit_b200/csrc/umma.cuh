@@ -130,6 +130,30 @@ __device__ __forceinline__ void mma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, ui
         : "memory");
 }
 
+// ---- kind::f16 with bf16 operands (fp32 accumulate): M×N×16 per instruction.  A 16-byte chunk of a K-major core-matrix row holds 8
+// consecutive k; a TMEM A operand packs two consecutive k per 32-bit column (low half = even k), 8 columns per instruction.
+__host__ __device__ constexpr uint32_t idesc_bf16(int M, int N) {
+    return (1u << 4) /*c = F32*/ | (1u << 7) /*a = BF16*/ | (1u << 10) /*b = BF16*/ | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ void mma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, bool accumulate) {
+    const uint32_t acc = accumulate ? 1u : 0u, z = 0u;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, {%5, %6, %7, %8}, p;\n\t}"
+        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(acc), "r"(z), "r"(z), "r"(z), "r"(z)
+        : "memory");
+}
+__device__ __forceinline__ void mma_bf16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, bool accumulate) {
+    const uint32_t acc = accumulate ? 1u : 0u, z = 0u;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, {%5, %6, %7, %8}, p;\n\t}"
+        ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(acc), "r"(z), "r"(z), "r"(z), "r"(z)
+        : "memory");
+}
+
 // registers → 16 consecutive 32-bit columns of this thread's lane (no wait: follow the last store with tmem_st_wait)
 __device__ __forceinline__ void tmem_st16(uint32_t taddr, const float (&v)[16]) {
     asm volatile(
