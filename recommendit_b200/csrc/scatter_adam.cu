@@ -287,13 +287,36 @@ __global__ void __launch_bounds__(LS_THREADS) long_segments_kernel(const SegPara
             for (int li = 0; li < nl; ++li) {
                 const int sg = list[li];
                 const int beg = J.seg_start[sg], end = J.seg_start[sg + 1];
-                for (int c = lane; c < D4; c += 32) {
-                    float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
-                    for (int k = beg + 1 + warp; k < end; k += 32) {       // (row `beg` was taken by segment_sum2_kernel)
-                        const float4 v = __ldg(rows + (long long)__ldg(J.pos + k) * D4 + c);
-                        a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+                // warp w owns rows beg+1+w, beg+1+w+32, … (row `beg` was taken by segment_sum2_kernel).  Their positions are fetched 32 at a
+                // time (one per lane) and handed round by shuffles, and four row reads are in flight per lane with one partial sum each
+                // (i mod 4; added as (a0 + a1) + (a2 + a3)): a 5 900-row segment — the hottest user of a 65 536-sample Zipf batch, all of it
+                // on one rank of the sharded step — took 66 us with one dependent pos → row chain per warp.
+                const int n_mine = end > beg + 1 + warp ? (end - (beg + 1 + warp) + 31) / 32 : 0;      // rows of this warp
+                for (int c0 = 0; c0 < D4; c0 += 32) {                   // (every lane walks the loop: the shuffles below are warp-wide)
+                    const int c = c0 + lane;
+                    const bool col = c < D4;
+                    float4 a4[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) a4[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    for (int i0 = 0; i0 < n_mine; i0 += 32) {
+                        const int ki = i0 + lane;
+                        const int pk = ki < n_mine ? __ldg(J.pos + beg + 1 + warp + 32 * ki) : 0;
+                        const int lim = min(32, n_mine - i0);
+                        for (int j0 = 0; j0 < lim; j0 += 4) {
+                            float4 v[4];
+#pragma unroll
+                            for (int u = 0; u < 4; ++u) {
+                                const int pj = __shfl_sync(0xffffffffu, pk, (j0 + u) & 31);
+                                v[u] = (col && j0 + u < lim) ? __ldg(rows + (long long)pj * D4 + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+                            }
+#pragma unroll
+                            for (int u = 0; u < 4; ++u) { a4[u].x += v[u].x; a4[u].y += v[u].y; a4[u].z += v[u].z; a4[u].w += v[u].w; }
+                        }
                     }
-                    *reinterpret_cast<float4*>(&part[warp][c * 4]) = a;
+                    float4 a;
+                    a.x = (a4[0].x + a4[1].x) + (a4[2].x + a4[3].x); a.y = (a4[0].y + a4[1].y) + (a4[2].y + a4[3].y);
+                    a.z = (a4[0].z + a4[1].z) + (a4[2].z + a4[3].z); a.w = (a4[0].w + a4[1].w) + (a4[2].w + a4[3].w);
+                    if (col) *reinterpret_cast<float4*>(&part[warp][c * 4]) = a;
                 }
                 __syncthreads();
                 for (int d = tid; d < D; d += LS_THREADS) {
@@ -1106,58 +1129,74 @@ extern "C" int rb200_gather_rows(const float* table, const int64_t* rows, int64_
 struct PeerTables { const float* table[RB200_MAX_PEERS]; long long user_rows[RB200_MAX_PEERS]; };
 struct PeerBuckets { float* grads[RB200_MAX_PEERS]; int64_t* rows[RB200_MAX_PEERS]; };
 
-// out[r] = shard[owner(id_r)][local_row(id_r)], requests in sample order [user ids | item ids]; one warp per 32 float4 of a row
+// out[r] = shard[owner(id_r)][local_row(id_r)], requests in sample order [user ids | item ids].  One warp per request, four requests
+// in flight per warp (a peer read over NVLink takes ≈ 2 us); the per-request arithmetic (owner = id mod world, local row = id / world)
+// is done once per request, not once per 16 bytes.
 __global__ void __launch_bounds__(NT) gather_rows_sharded_kernel(const PeerTables P, int world, const int64_t* __restrict__ user_ids,
                                                                  long long n_u, const int64_t* __restrict__ item_ids, long long n_i,
                                                                  long long n_user_rows, long long n_item_rows, int D4,
                                                                  float* __restrict__ out, int* __restrict__ err_flag) {
-    // Four independent 16-byte reads in flight per thread: a peer read over NVLink takes ≈ 2 us, and with one outstanding read per
-    // thread the 8-GPU gather ran at ≈ 320 GB/s (timestamps inside the step's graph replay).
-    const long long total = (n_u + n_i) * D4, stride = (long long)gridDim.x * NT;
-    for (long long i0 = (long long)blockIdx.x * NT + threadIdx.x; i0 < total; i0 += 4 * stride) {
+    const int lane = threadIdx.x & 31;
+    const long long n = n_u + n_i, n_warps = (long long)gridDim.x * (NT / 32);
+    for (long long r0 = (long long)blockIdx.x * (NT / 32) + (threadIdx.x >> 5); r0 < n; r0 += 4 * n_warps) {
         const float4* src[4];
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
-            const long long i = i0 + u * stride;
+            const long long r = r0 + u * n_warps;
             src[u] = nullptr;
-            if (i < total) {
-                const long long r = i / D4;
-                const int c = (int)(i - r * D4);
+            if (r < n) {
                 const bool is_user = r < n_u;
                 long long id = is_user ? user_ids[r] : item_ids[r - n_u];
                 if ((unsigned long long)id >= (unsigned long long)(is_user ? n_user_rows : n_item_rows)) {
-                    if (err_flag && c == 0) atomicOr(err_flag, 1);
+                    if (err_flag && lane == 0) atomicOr(err_flag, 1);
                     id = 0;
                 }
                 const int owner = (int)(id % world);
                 const long long local = id / world + (is_user ? 0 : P.user_rows[owner]);
-                src[u] = reinterpret_cast<const float4*>(P.table[owner]) + local * D4 + c;
+                src[u] = reinterpret_cast<const float4*>(P.table[owner]) + local * D4;
             }
         }
-        float4 v[4];
-        // (plain loads, not the read-only path: the source may be peer memory that other GPUs rewrite between steps)
+        for (int c = lane; c < D4; c += 32) {
+            float4 v[4];
+            // (plain loads, not the read-only path: the source may be peer memory that other GPUs rewrite between steps)
 #pragma unroll
-        for (int u = 0; u < 4; ++u) if (src[u]) v[u] = *src[u];
+            for (int u = 0; u < 4; ++u) if (src[u]) v[u] = src[u][c];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) if (src[u]) reinterpret_cast<float4*>(out)[i0 + u * stride] = v[u];
+            for (int u = 0; u < 4; ++u) if (src[u]) reinterpret_cast<float4*>(out)[(r0 + u * n_warps) * D4 + c] = v[u];
+        }
     }
 }
 
 // gradient rows (sample order) → bucket (this rank) of their owner's receive buffer, at the slot the exchange plan assigned;
-// the plan's row list (owner-local row per slot, -1 = empty) goes with them.  Requests that overflowed their bucket (slot ==
-// world·C) are dropped (counted by the plan).
+// the plan's row list (owner-local row per slot, -1 = empty) goes with them unless it went ahead (send_rows NULL).  Requests that
+// overflowed their bucket (slot == world·C) are dropped (counted by the plan).  One warp per row, four rows in flight per warp.
 __global__ void __launch_bounds__(NT) push_rows_sharded_kernel(const PeerBuckets P, int world, int rank, long long C,
                                                                const float* __restrict__ drows, const int64_t* __restrict__ slot_of_sample,
                                                                long long n, int D4, const int64_t* __restrict__ send_rows) {
-    const long long total = n * D4, stride = (long long)gridDim.x * NT;
-    for (long long i = (long long)blockIdx.x * NT + threadIdx.x; i < total; i += stride) {
-        const long long r = i / D4;
-        const int c = (int)(i - r * D4);
-        const long long slot = slot_of_sample[r];
-        if (slot >= (long long)world * C) continue;
-        const int owner = (int)(slot / C);
-        const long long off = slot - (long long)owner * C;
-        reinterpret_cast<float4*>(P.grads[owner])[((long long)rank * C + off) * D4 + c] = __ldg(reinterpret_cast<const float4*>(drows) + i);
+    const int lane = threadIdx.x & 31;
+    const long long n_warps = (long long)gridDim.x * (NT / 32), stride = (long long)gridDim.x * NT;
+    for (long long r0 = (long long)blockIdx.x * (NT / 32) + (threadIdx.x >> 5); r0 < n; r0 += 4 * n_warps) {
+        float4* dst[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const long long r = r0 + u * n_warps;
+            dst[u] = nullptr;
+            if (r < n) {
+                const long long slot = slot_of_sample[r];
+                if (slot < (long long)world * C) {
+                    const int owner = (int)(slot / C);
+                    const long long off = slot - (long long)owner * C;
+                    dst[u] = reinterpret_cast<float4*>(P.grads[owner]) + ((long long)rank * C + off) * D4;
+                }
+            }
+        }
+        for (int c = lane; c < D4; c += 32) {
+            float4 v[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) if (dst[u]) v[u] = __ldg(reinterpret_cast<const float4*>(drows) + (r0 + u * n_warps) * D4 + c);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) if (dst[u]) dst[u][c] = v[u];
+        }
     }
     if (send_rows)
         for (long long j = (long long)blockIdx.x * NT + threadIdx.x; j < (long long)world * C; j += stride) {
@@ -1165,7 +1204,9 @@ __global__ void __launch_bounds__(NT) push_rows_sharded_kernel(const PeerBuckets
             const long long off = j - (long long)owner * C;
             P.rows[owner][(long long)rank * C + off] = send_rows[j];
         }
-    __threadfence_system();          // peer writes ordered before the cross-GPU barrier that follows on the stream
+    // No fence here: the cross-GPU barrier that follows on the stream is a later kernel (its release at system scope is ordered after
+    // this kernel's writes by the kernel boundary, and the peers' acquire makes them visible).  A __threadfence_system() per thread
+    // cost this kernel most of its time (12.6 MB in 20 us at world 1).
 }
 // the plan's row list alone (it depends only on the ids: sent at the start of the step, so that the owners sort their received rows
 // under the towers)

@@ -767,11 +767,13 @@ class ShardedBPRTrainer:
             if self.rank == 0:
                 segs.append((g_mlp, None, 0))
             ops.sumsq(self.opt, segs)
-            red = torch.cat([opt64[_OPT_SUMSQ_F64:_OPT_SUMSQ_F64 + 1], loss.to(torch.float64) / W])
             if W > 1:
+                red = torch.cat([opt64[_OPT_SUMSQ_F64:_OPT_SUMSQ_F64 + 1], loss.to(torch.float64) / W])
                 dist.all_reduce(red, group=self.group)
-            opt64[_OPT_SUMSQ_F64:_OPT_SUMSQ_F64 + 1].copy_(red[0:1])
-            opt32[_OPT_LOSS_F32:_OPT_LOSS_F32 + 1].copy_(red[1:2].to(torch.float32))
+                opt64[_OPT_SUMSQ_F64:_OPT_SUMSQ_F64 + 1].copy_(red[0:1])
+                opt32[_OPT_LOSS_F32:_OPT_LOSS_F32 + 1].copy_(red[1:2].to(torch.float32))
+            else:
+                opt32[_OPT_LOSS_F32:_OPT_LOSS_F32 + 1].copy_(loss)          # one process: the sum of squares is already complete
         ops.grad_norm_clip(self.opt)
         self._mark("allreduce_norm_clip")
 
