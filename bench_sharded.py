@@ -273,10 +273,14 @@ def parity_c5(dev, rank: int, world: int):
     dist.all_gather(parts, x)
     s1, i1 = flat_search(q, torch.cat(parts), k, 0)
     same_ids = (i == i1)
-    # a differing id is acceptable only where the two scores at that rank are equal (an exact tie)
-    tie_ok = same_ids | (s == s1)
+    # A differing id is acceptable only where the two scores at that rank tie at rounding level (4e-7: bench.py's rule for the C5
+    # prefix check).  Exact equality cannot be asked for: a row inside a search's exact prefix (its first 8192 rows) is scored by the
+    # 3xTF32 GEMM, a row met in a pruned round by the fp32 re-score of the survivors — the same (query, row) pair can differ in the
+    # last bits between the sharded search (rows 50 000 … 58 191 open the second shard's prefix) and the unsharded one.
+    tie_ok = same_ids | ((s - s1).abs() <= 4e-7)
     return {"what": f"sharded_flat_search over {world} x {rows} rows vs rb200_flat_search over the concatenated {world * rows} rows, "
                     f"{nq} queries, top-{k}", "ids_equal_frac": float(same_ids.float().mean()),
+            "rule": "ids identical except where the scores at that rank tie within 4e-7 (fp32 rounding of a 64-term dot product)",
             "max_score_diff": float((s - s1).abs().max()), "ok": bool(tie_ok.all().item() and float((s - s1).abs().max()) <= 2e-6)}
 
 
