@@ -1,0 +1,178 @@
+"""Build the round-2 evidence files under profiles/ from the scratch captures in gpurun_out/ (tools; run once per capture set).
+Launch lists: `ncu --metrics gpu__time_duration.sum --clock-control none --csv`; full captures: `ncu --set full --clock-control none
+--import-source on`.  Per-launch times of a launch list are serialised and cold-cache: shares, not absolutes (README of profiles)."""
+import csv, io, json, shutil, subprocess, sys
+from pathlib import Path
+ROOT = Path(__file__).resolve().parents[1]
+G, P = ROOT / "gpurun_out", ROOT / "profiles"
+
+
+def load(f):
+    lines = [l for l in open(f) if not l.startswith("==")]
+    rows = list(csv.DictReader(lines))
+    return [(r["Kernel Name"].replace("<unnamed>::", "").replace("void ", "").split("(")[0][:90], float(r["Metric Value"]) / 1000.0,
+             r["Grid Size"], r["Block Size"]) for r in rows]
+
+
+def table(rows, title):
+    tot = sum(r[1] for r in rows)
+    out = [f"### {title}\n", "| kernel | us | share | grid | block |", "|---|---:|---:|---|---|"]
+    for n, t, g, b in rows:
+        out.append(f"| `{n}` | {t:.2f} | {100 * t / tot:.1f} % | {g} | {b} |")
+    out.append(f"| **sum** | **{tot:.1f}** | | | |\n")
+    return "\n".join(out)
+
+
+def agg_table(rows, title):
+    agg, cnt = {}, {}
+    for n, t, g, b in rows:
+        agg[n] = agg.get(n, 0.0) + t; cnt[n] = cnt.get(n, 0) + 1
+    tot = sum(agg.values())
+    out = [f"### {title}\n", "| kernel | launches | us (sum) | share |", "|---|---:|---:|---:|"]
+    for n, t in sorted(agg.items(), key=lambda kv: -kv[1]):
+        out.append(f"| `{n}` | {cnt[n]} | {t:.1f} | {100 * t / tot:.1f} % |")
+    out.append(f"| **sum** | {len(rows)} | **{tot:.1f}** | |\n")
+    return "\n".join(out)
+
+
+def ncu_raw(rep):
+    raw = subprocess.run(["ncu", "-i", str(rep), "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(io.StringIO(raw)))
+    return rows[0], rows[1], rows[2:]
+
+
+KEYS = [("gpu__time_duration.sum", "time"), ("dram__bytes_read.sum", "dram read"), ("dram__bytes_write.sum", "dram write"),
+        ("gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "dram % of peak"),
+        ("sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active", "tensor pipe active %"),
+        ("smsp__issue_active.avg.pct_of_peak_sustained_active", "issue active %"),
+        ("sm__warps_active.avg.pct_of_peak_sustained_active", "warps active %"),
+        ("l1tex__m_xbar2l1tex_read_bytes.sum.per_second", "L2 -> SM read"),
+        ("launch__registers_per_thread", "regs"), ("launch__grid_size", "grid"), ("launch__block_size", "block"),
+        ("sm__inst_executed.sum", "warp instructions")]
+
+
+def ncu_table(rep, title):
+    hdr, units, rows = ncu_raw(rep)
+    idx = {h: i for i, h in enumerate(hdr)}
+    ks = [(k, n) for k, n in KEYS if k in idx]
+    out = [f"### {title}\n", "| kernel | " + " | ".join(n for _, n in ks) + " |", "|---|" + "---:|" * len(ks)]
+    for r in rows:
+        def fmt(k):
+            v, u = r[idx[k]], units[idx[k]]
+            try:
+                return f"{float(v):.4g} {u}".strip()
+            except ValueError:
+                return f"{v} {u}".strip()
+        out.append(f"| `{r[idx['Kernel Name']][:70]}` | " + " | ".join(fmt(k) for k, _ in ks) + " |")
+    return "\n".join(out) + "\n"
+
+
+def lines_table(rep, kre, top=14):
+    txt = subprocess.run([sys.executable, str(ROOT / "tools" / "ncu_lines.py"), str(rep), kre, str(top)], capture_output=True, text=True).stdout
+    return txt
+
+
+def last_call(rows, marker, back=0, nth_from_end=1):
+    idx = [i for i, n in enumerate(rows) if marker in n[0]]
+    s = idx[-nth_from_end] - back
+    e = idx[-nth_from_end + 1] - back if nth_from_end > 1 else len(rows)
+    return rows[s:e]
+
+
+if __name__ == "__main__":
+    for f in ("r2f_launches_c2.csv", "r2f_launches_c4.csv", "r2f_launches_ivf.csv", "r2f_launches_flat4096.csv", "r2f_launches_flat64.csv"):
+        shutil.copy(G / f, P / f.replace("r2f_", "r02_"))
+    # ---- C2 step ----
+    c2 = load(G / "r2f_launches_c2.csv")
+    step = last_call(c2, "block_sort_segments", 0, 2)
+    (P / "r02_launches_c2.md").write_text(
+        "# r02 — C2 training step (batch 8192, D = 64, H = 128), launch list of one eager step\n\n"
+        "Command: `ncu --metrics gpu__time_duration.sum --clock-control none --csv python tools/c2_step_probe.py eager 3` (the plain run "
+        "exited 0 first: `eager C2 step: 0.1309 ms`; the bench times the same kernels as ONE graph replay: 0.1247 ms).  "
+        "`block_sort_segments_kernel`, `finalize_sum_kernel` and the user tower's backward run on a side stream inside the graph.\n\n"
+        + table(step, "one step (stream order of the capture)") +
+        "\nCritical path (main stream): prep + fwd + loss + item-tower bwd (data, weights) + grad_finish + adam ≈ 112 us of kernels + ≈ 1–2 us "
+        "per launch boundary.\n")
+    # ---- C4 step ----
+    c4 = load(G / "r2f_launches_c4.csv")
+    idx = [i for i, n in enumerate(c4) if "route" in n[0] and "hist" in n[0]] or [i for i, n in enumerate(c4) if "route" in n[0]]
+    step4 = c4[idx[-1] - 0:] if idx else c4[-40:]
+    tl = {}
+    for name, f in (("world 1", "r2_tl_n1_v7.log"), ("2 GPUs", "r2_tl_n2_v3.log"), ("8 GPUs", "r2_tl_n8_v3.log")):
+        try:
+            tl[name] = json.loads(open(G / f).read().strip().splitlines()[-1])
+        except Exception:
+            pass
+    keys = ["barrier0", "route_gather_exchange", "towers_fwd", "loss", "towers_bwd", "route_plan", "push_rows", "grad_exchange", "scatter",
+            "sumsq_publish", "barrier2", "allreduce_norm_clip", "adam"]
+    t = ["### phases of one graph replay (device `%globaltimer` stamps between the phases, max over ranks, us)\n",
+         "| phase | " + " | ".join(tl) + " |", "|---|" + "---:|" * len(tl)]
+    for k in keys:
+        t.append(f"| {k} | " + " | ".join(f"{1e3 * v['stage_ms_graph'].get(k, 0.0):.1f}" for v in tl.values()) + " |")
+    t.append("| **ms per step (no stamps)** | " + " | ".join(f"**{v['ms_per_step']:.3f}**" for v in tl.values()) + " |")
+    t.append("| samples/s (all ranks) | " + " | ".join(f"{v['value'] / 1e6:.1f} M" for v in tl.values()) + " |\n")
+    (P / "r02_c4_step.md").write_text(
+        "# r02 — C4 sharded step (10 M x 1 M rows, D = 128, 8192 samples per rank, exchange = p2p)\n\n"
+        "`tools/c4_timeline.py` (= `bench_sharded.bench_c4`): the step is ONE CUDA-graph replay; a one-thread kernel (`rb200_stamp`) "
+        "records `%globaltimer` at every phase boundary of the main stream.  `route_plan` is now only the join with the side stream that "
+        "computes the exchange plan, pushes the row lists and sorts the received rows under the towers; `scatter` is the segment sum "
+        "alone.  `barrier*` / `grad_exchange` are cross-GPU barriers (they include waiting for the slowest rank: under Zipf(1.05) users "
+        "the rank that owns the hottest ids has the longest segment sums).\n\n" + "\n".join(t) +
+        "\n(The 2-GPU column was measured one commit earlier than the other two: before the warp-per-row push kernel and the long-segment "
+        "change.)  Efficiency of the weak-scaling curve = value(N) / (N x value(1)).  Before this round's changes the same table read "
+        "0.362 / 0.393 / 0.457 ms per step (profiles of the previous session: gpurun_out/r2_tl_n*.log).\n\n"
+        + agg_table(last_call(c4, "gather_rows_sharded", 12), "launch list of one EAGER step at world 1 (ncu, serialised; includes the side stream's kernels)") +
+        "\nCommand: `ncu --metrics gpu__time_duration.sum --clock-control none --csv python tools/c4_step_probe.py eager` "
+        "(plain run first: 0.636 ms per eager step, host-bound; the graph replay of the same kernels: 0.261 ms).\n")
+    # ---- IVF ----
+    ivf = load(G / "r2f_launches_ivf.csv")
+    batch = last_call(ivf, "gemm_nt_tc", 0)
+    (P / "r02_ivf.md").write_text(
+        "# r02 — C3 IVF search (1 M x 64, nlist 4096, nprobe 32, top-500, 4096 queries per batch)\n\n"
+        "Bench: 0.670 ms per batch device-timed (0.719 at the start of the round).  The plan's cub radix sort + two scans + reduction "
+        "(54 us in `profiles/r01_launches_ivf_v7.csv`) are now `plan_scans_kernel` + `pair_scatter_kernel`.\n\n"
+        + table(batch, "launch list of one batch (`ncu --metrics gpu__time_duration.sum --clock-control none --csv python tools/ivf_probe.py 3`)")
+        + ncu_table(G / "r2_prof_ivf.ncu-rep", "`ncu --set full` of the probe select, the list scan and the final select (per launch)")
+        + "\nReading: the database is read once (261 MB for 256 MB of rows); the scan writes 103 MB of candidate scores that the select "
+          "reads back (138 MB).  Both kernels are latency-bound (warps active 22 % / 47 %): in the list scan 27 % of the stall samples sit "
+          "at the block barrier behind the dependent loads (tile table -> offsets -> pairs -> query rows) — a persistent, prefetching form "
+          "is the next step (DESIGN.md §10).\n\n" + lines_table(G / "r2_prof_ivf.ncu-rep", "list_scan_tc", 10))
+    # ---- flat filter ----
+    f4 = load(G / "r2f_launches_flat4096.csv")
+    idx = [i for i, n in enumerate(f4) if "flat_filter_image" in n[0]]
+    search = f4[idx[-2] - 3: idx[-1] - 3]
+    (P / "r02_flat_filter.md").write_text(
+        "# r02 — exhaustive top-500, one C5 shard (12.5 M x 64 rows), 4096 queries: `flat_filter_tc_kernel`\n\n"
+        "`python tools/flat_prof.py 12500000 4096`: 12.1–12.6 ms per batch (37.5 ms at the end of round 1, 27.4 at the start of this "
+        "session).  Steps of this session (ms per batch): per-warp survivor buffers 24.3 -> thresholds staged / 3 accumulators 23.2 -> "
+        "new kernel (N = 128 MMAs, copy producer + one issuer warp per tile) 18.4 -> threshold comparison on the tensor core 14.9 -> "
+        "bf16 operands 14.1 -> accumulators released right after the TMEM loads 12.6.\n\n"
+        + agg_table(search, "launch list of one search (ncu, serialised)")
+        + ncu_table(G / "r2f_prof_filter.ncu-rep", "`ncu --set full` of the largest round (6.29 M rows x 4096 queries, 24 576 CTAs)")
+        + "\nEarlier captures of the same round, same command (`-k regex:flat_filter_tc -s 4 -c 1`): tf32 operands + thresholds in shared "
+          "memory 7.56 ms, tensor pipe 39.9 %; tf32 + threshold on the tensor core 5.82 ms, 58.5 %; the previous kernel "
+          "(`flat_scan_tc_kernel<2,8,1,1>`, one warp issuing copies and MMAs for both tiles, N = 64) 9.94 ms, 30.1 % — there the issuing "
+          "warp's samples were spread evenly over ≈ 250 instructions per 64-query chunk (≈ 7 cycles each): the issuer, not the tensor "
+          "pipe, bounded the kernel.\n\n" + lines_table(G / "r2f_prof_filter.ncu-rep", "flat_filter_tc", 12))
+    # ---- flat stream ----
+    f64 = load(G / "r2f_launches_flat64.csv")
+    idx = [i for i, n in enumerate(f64) if "flat_qimage" in n[0]]
+    search = f64[idx[-2] - 3: idx[-1] - 3]
+    (P / "r02_flat_stream.md").write_text(
+        "# r02 — exhaustive top-500, one C5 shard (12.5 M x 64 rows = 3.2 GB), 64 queries: `flat_stream_tc_kernel`\n\n"
+        "`python tools/flat_prof.py 12500000 64`: 1.10–1.12 ms per batch = 2.9 TB/s of rows = 44 % of the measured HBM peak (2.1 ms = 23 % "
+        "with the per-tile CTAs of round 1; nq = 1: 0.82 ms).  Four rounds (x8) after the exact 8192-row prefix.\n\n"
+        + table(search, "launch list of one search (ncu, serialised)")
+        + ncu_table(G / "r2f_prof_stream.ncu-rep", "`ncu --set full` of the four rounds (57 344 / 458 752 / 3.67 M / 8.31 M rows)")
+        + "\nThe two large rounds run at 3.2 and 5.0 TB/s of DRAM reads; the small ones pay a fixed cost (survivor flushes of all CTAs "
+          "contend on the 64 per-query counters; ≈ 7·k survivors per query per round whatever its size).\n\n"
+        + lines_table(G / "r2f_prof_stream.ncu-rep", "flat_stream_tc", 10))
+    # ---- towers ----
+    (P / "r02_towers_c2.md").write_text(
+        "# r02 — C2 tower kernels (`csrc/tower_ts.cu`: activations as the TMEM A operand), `ncu --set full`\n\n"
+        "Command: `ncu --set full --clock-control none --import-source on -k regex:tower python tools/c2_step_probe.py eager 2` "
+        "(previous session of this round).\n\n" + ncu_table(G / "r2_prof_towers.ncu-rep", "per launch")
+        + "\nDRAM traffic of the backward stage (four launches): 60.6 MB; forward: 3.9 MB (tables and weights are L2-resident).  The "
+          "kernels are latency-bound at batch 8192: one 128-sample tile per CTA, 1 CTA per SM (197–221 KB of shared memory for the "
+          "weight images), 192 forward tiles on 148 SMs = two waves.\n")
+    print("profiles written")
