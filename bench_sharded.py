@@ -78,9 +78,10 @@ def _parallelism(world: int, cap: int) -> str:
     if EXCHANGE == "p2p":
         return (f"row-sharded x{world}, peer-memory exchange over NVLink/NVSwitch (torch symmetric memory): every rank READS the rows it "
                 f"needs straight from the owners' shards and WRITES its row gradients into the owners' receive buckets ({cap} rows per "
-                f"rank pair = {CAPACITY_FACTOR}x the mean) — one kernel each, two cross-GPU barriers per step, no collective on the row "
-                "path; NCCL all-reduce only for the MLP gradients (273 KB) and {sum g^2, loss}; no host synchronisation: the whole step "
-                "is ONE CUDA-graph replay")
+                f"rank pair = {CAPACITY_FACTOR}x the mean) — one kernel each; the MLP gradients (273 KB) and {{sum g^2, loss}} are reduced by "
+                "one-shot peer reads in rank order; the exchange plan, the row lists and the owners' sort of the received rows run on a "
+                "side stream under the gather and the towers; four cross-GPU barriers per step, NO NCCL inside the step, no host "
+                "synchronisation: the whole step is ONE CUDA-graph replay")
     return (f"row-sharded x{world}: NCCL all-to-all of ids / rows / row gradients + all-reduce of the MLP gradients "
             f"and of {{sum g^2, loss}}; fixed-capacity exchange buckets ({cap} rows per rank pair = "
             f"{CAPACITY_FACTOR}x the mean), no host synchronisation: the whole step incl. the collectives is ONE "
@@ -384,7 +385,7 @@ def _run(args):
     # ---- secondary: C2, data-parallel replicas (tables of 2.6 MB: replicating them is the natural layout) --------------- #
     torch.manual_seed(0)
     model = R.TwoTowerModel(N_USERS, N_ITEMS, D, H, dropout=DROPOUT).to(dev).train()
-    tr = R.DataParallelBPRTrainer(model, lr=1e-3, weight_decay=1e-5, max_norm=1.0, use_cuda_graph=True)
+    tr = R.DataParallelBPRTrainer(model, lr=1e-3, weight_decay=1e-5, max_norm=1.0, use_cuda_graph=True, allreduce="p2p")
     K2 = min(K, 50)
     nb = min(K2 + W + 2, 24)
     batches, _ = synth_batches(nb, seed=100 + rank)
@@ -451,8 +452,9 @@ def _run(args):
                   "e2e": {"value": world * B * K2 / dp_e2e, "unit": "samples/s", "h2d_bytes_per_step": pinned[0].numel(), "d2h_bytes_per_step": 4},
                   "launches_per_step": int(dp_launches), "replicas_in_sync": in_sync, "final_loss": float(dp_loss),
                   "config": {"workload": f"C2 x{world}: batch 8192 PER RANK, ML-1M-shape tables replicated, dense Adam, dropout 0.1",
-                             "parallelism": f"data parallel x{world}: one NCCL all-reduce of the dense gradients per step ({ar_bytes} B), "
-                                            "captured with both halves of the step in ONE CUDA graph"}},
+                             "parallelism": f"data parallel x{world}: one all-reduce of the dense gradients per step ({ar_bytes} B) as a two-shot "
+                                            "kernel over peer memory between two cross-GPU barriers (rb200_allreduce_twoshot, torch symmetric "
+                                            "memory; no NCCL in the step), captured with both halves of the step in ONE CUDA graph"}},
         "c5": {"metric": "flat_top500_qps", "value": nq5 / ms5 * 1e3, "unit": "queries/s", "ms_per_batch": ms5,
                "logical_tflops_all_gpus": 2.0 * nq5 * rows5 * world * 64 / (ms5 * 1e-3) / 1e12,
                "ranks_agree": bool((lo5 == hi5).item()), "shards_in_result": shards_hit,

@@ -255,6 +255,11 @@ int rb200_push_row_lists_sharded(void* const* row_bucket_ptrs, int world, int ra
  *   scalars_reduce:    st->sumsq = Σ_k (slot_k[0] + slot_k[1]) in fp64, st->loss = Σ_k slot_k[2].
  * The caller orders them with cross-GPU barriers (publish → barrier → reduce). */
 int rb200_allreduce_oneshot(const void* const* src_ptrs, int world, int64_t n, float* out, void* stream);
+/* Two-shot all-reduce IN PLACE over peer memory (the data-parallel step: one buffer of dense gradients per rank, mapped into every
+ * process): rank r sums slice r of all ranks' buffers in rank order and writes the sum into slice r of every rank's buffer — all
+ * ranks end up with bit-identical sums.  buf_ptrs: HOST array of the `world` device pointers; n floats, n % 4 == 0.  The caller puts
+ * a cross-GPU barrier before (all buffers complete) and after (all slices delivered).  Replaces ncclAllReduce inside the step. */
+int rb200_allreduce_twoshot(void* const* buf_ptrs, int world, int rank, int64_t n, void* stream);
 /* (rb200_sharded_scalars_publish / _reduce are declared below, after rb200_opt_state) */
 
 /* ------------------------------------------------------------------------------------------ *

@@ -109,6 +109,7 @@ SIGNATURES = {
     "rb200_push_rows_sharded": (I, [P, P, I, I, I64, P, P, I64, I, P, P]),
     "rb200_push_row_lists_sharded": (I, [P, I, I, I64, P, P]),
     "rb200_allreduce_oneshot": (I, [P, I, I64, P, P]),
+    "rb200_allreduce_twoshot": (I, [P, I, I, I64, P]),
     "rb200_sharded_scalars_publish": (I, [P, P, F, P, P]),
     "rb200_sharded_scalars_reduce": (I, [P, I, P, P]),
     "rb200_sample_batch": (I, [P, P, I64, P, P, P, I64, I, U64, I64, I64, I64, I64, P, P, P, P]),

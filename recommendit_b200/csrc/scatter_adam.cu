@@ -1235,6 +1235,34 @@ __global__ void __launch_bounds__(NT) allreduce_oneshot_kernel(const PeerSrc P, 
         reinterpret_cast<float4*>(out)[i] = a;
     }
 }
+// Two-shot all-reduce IN PLACE over peer memory (the data-parallel step's dense gradients: 2.7 MB at the reference's sizes): rank r owns
+// slice r of the buffer — it reads that slice from every rank (ascending rank order: every element is summed by exactly one rank, in
+// the same order whatever the rank count, so all ranks end up with bit-identical sums), and writes the sum back into slice r of EVERY
+// rank's buffer.  No other rank reads or writes slice r, so the reduction is in place; the caller puts a cross-GPU barrier before
+// (all buffers complete) and after (all slices delivered).  Per rank (W − 1)/W · n floats cross NVLink in each direction.
+struct PeerRW { float* p[RB200_MAX_PEERS]; };
+__global__ void __launch_bounds__(NT) allreduce_twoshot_kernel(const PeerRW P, int world, int rank, long long n4) {
+    const long long per = (n4 + world - 1) / world, beg = per * rank, end = beg + per < n4 ? beg + per : n4;
+    const long long stride = (long long)gridDim.x * NT;
+    for (long long i0 = beg + (long long)blockIdx.x * NT + threadIdx.x; i0 < end; i0 += 2 * stride) {
+        const long long i1 = i0 + stride;
+        const bool two = i1 < end;
+        float4 a = *(reinterpret_cast<const float4*>(P.p[0]) + i0), b = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (two) b = *(reinterpret_cast<const float4*>(P.p[0]) + i1);
+        for (int k = 1; k < world; ++k) {
+            const float4 v = *(reinterpret_cast<const float4*>(P.p[k]) + i0);
+            float4 w = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (two) w = *(reinterpret_cast<const float4*>(P.p[k]) + i1);
+            a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+            b.x += w.x; b.y += w.y; b.z += w.z; b.w += w.w;
+        }
+        for (int k = 0; k < world; ++k) {
+            reinterpret_cast<float4*>(P.p[k])[i0] = a;
+            if (two) reinterpret_cast<float4*>(P.p[k])[i1] = b;
+        }
+    }
+}
+
 // this rank's {Σg² of its table-shard gradients (fp64 as a hi/lo float pair), loss·scale} → its 4-float slot (peer-readable)
 __global__ void scalars_publish_kernel(const rb200_opt_state* st, const float* loss, float scale, float* slot) {
     if (threadIdx.x == 0 && blockIdx.x == 0) {
@@ -1264,6 +1292,17 @@ extern "C" int rb200_allreduce_oneshot(const void* const* src_ptrs, int world, i
     for (int k = 0; k < world; ++k) { RB_REQUIRE(src_ptrs[k], "allreduce_oneshot: NULL pointer of rank %d", k); P.p[k] = (const float*)src_ptrs[k]; }
     allreduce_oneshot_kernel<<<stream_grid(n / 4), NT, 0, (cudaStream_t)stream>>>(P, world, n / 4, out);
     RB_LAUNCH_CHECK("allreduce_oneshot_kernel");
+    return RB200_OK;
+}
+
+extern "C" int rb200_allreduce_twoshot(void* const* buf_ptrs, int world, int rank, int64_t n, void* stream) {
+    RB_REQUIRE(buf_ptrs && world >= 1 && world <= RB200_MAX_PEERS && rank >= 0 && rank < world && n >= 4 && n % 4 == 0,
+               "allreduce_twoshot: n must be a multiple of 4, 1..%d ranks", RB200_MAX_PEERS);
+    PeerRW P{};
+    for (int k = 0; k < world; ++k) { RB_REQUIRE(buf_ptrs[k], "allreduce_twoshot: NULL pointer of rank %d", k); P.p[k] = (float*)buf_ptrs[k]; }
+    const long long per = (n / 4 + world - 1) / world;
+    allreduce_twoshot_kernel<<<stream_grid((per + 1) / 2), NT, 0, (cudaStream_t)stream>>>(P, world, rank, n / 4);
+    RB_LAUNCH_CHECK("allreduce_twoshot_kernel");
     return RB200_OK;
 }
 

@@ -362,7 +362,8 @@ class DataParallelBPRTrainer(FusedBPRTrainer):
     (MLPs + both tables, 2.7 MB at the reference's sizes) between the two halves of the step:
 
         rb200_bpr_step (… → dense gradients in `dp_grads`, loss gradient scaled by 1/world)
-        torch.distributed.all_reduce(dp_grads)                                   # NCCL over NVLink
+        torch.distributed.all_reduce(dp_grads)                                   # NCCL over NVLink (allreduce="nccl"), or
+        barrier; rb200_allreduce_twoshot; barrier                                # peer memory, no NCCL (allreduce="p2p")
         rb200_bpr_apply (Σg² → clip → Adam on every parameter, as torch.optim.Adam on dense grads does)
 
     — all three captured in ONE CUDA graph after two eager steps (call ``close()`` before ``destroy_process_group()``).
@@ -370,8 +371,10 @@ class DataParallelBPRTrainer(FusedBPRTrainer):
     The result equals the single-process step on the concatenated global batch (mean loss over world·B samples).
     Parameters are broadcast from rank 0 at construction.  Huge tables use ``sharded.ShardedBPRTrainer`` instead."""
 
-    def __init__(self, model: TwoTowerModel, group=None, **kw):
+    def __init__(self, model: TwoTowerModel, group=None, allreduce: str = "nccl", **kw):
         import torch.distributed as dist
+        if allreduce not in ("nccl", "p2p"):
+            raise ValueError("allreduce must be 'nccl' or 'p2p'")
         self.dist = dist
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
@@ -388,7 +391,18 @@ class DataParallelBPRTrainer(FusedBPRTrainer):
             self._flatten()
         n = self.lib.rb200_bpr_dp_grad_floats(self.D, self.H, self.E, model.n_users + 1, model.n_items + 1)
         # dense gradients + one trailing float for the loss (pre-scaled by 1/world on the device): ONE all-reduce per step
-        self._dp_buf = torch.zeros(n + 4, dtype=torch.float32, device=self.dev)
+        self._dp_hdl, self._dp_ptrs = None, None
+        n_buf = (n + 4 + 3) // 4 * 4
+        if self.world > 1 and allreduce == "p2p":
+            # the buffer lives in symmetric memory (one NVLink / NVSwitch box): the all-reduce is a two-shot kernel over peer memory
+            # between two cross-GPU barriers (rb200_allreduce_twoshot) instead of ncclAllReduce
+            import torch.distributed._symmetric_memory as symm_mem
+            self._dp_buf = symm_mem.empty(n_buf, dtype=torch.float32, device=self.dev)
+            self._dp_buf.zero_()
+            self._dp_hdl = symm_mem.rendezvous(self._dp_buf, group if group is not None else dist.group.WORLD)
+            self._dp_ptrs = [int(p) for p in self._dp_hdl.buffer_ptrs]
+        else:
+            self._dp_buf = torch.zeros(n_buf, dtype=torch.float32, device=self.dev)
         self.dp_grads = self._dp_buf[:n]
         self.loss_sum = self._dp_buf[n:n + 1]
         self._eager_dp = 0
@@ -416,7 +430,13 @@ class DataParallelBPRTrainer(FusedBPRTrainer):
     def _whole(self) -> None:
         self._phase(0)
         if self.world > 1:
-            self.dist.all_reduce(self._dp_buf, group=self.group)
+            if self._dp_hdl is not None:
+                self._dp_hdl.barrier(channel=0, timeout_ms=60000)          # every rank's gradients are complete
+                check(self.lib.rb200_allreduce_twoshot((C.c_void_p * self.world)(*self._dp_ptrs), self.world, self.rank,
+                                                       self._dp_buf.numel(), stream_ptr()), "rb200_allreduce_twoshot")
+                self._dp_hdl.barrier(channel=1, timeout_ms=60000)          # every slice has been delivered everywhere
+            else:
+                self.dist.all_reduce(self._dp_buf, group=self.group)
         self._phase(1)
 
     def step(self, masks=None) -> torch.Tensor:

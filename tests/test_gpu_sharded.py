@@ -102,6 +102,15 @@ dp_losses = [float(dp.step_host(*batch2(rank, s))) for s in range(4)]      # 2 e
 dp_state = {k: v.detach().cpu().numpy() for k, v in m.state_dict().items()}
 assert dp._graph is not None
 dp.close()            # the captured step holds an NCCL node: release it before destroy_process_group()
+# the same replicas with the all-reduce done over peer memory (two-shot kernel between two cross-GPU barriers, no NCCL in the step)
+m2 = R.TwoTowerModel(400, 300, 64, 128, dropout=0.0)
+m2.load_state_dict({k: torch.from_numpy(v) for k, v in O.init_params(400, 300, 64, 128, seed=9).items()}); m2.to(dev).train()
+dp2 = R.DataParallelBPRTrainer(m2, lr=1e-2, use_cuda_graph=True, allreduce="p2p")
+dp2_losses = [float(dp2.step_host(*batch2(rank, s))) for s in range(4)]
+assert dp2._graph is not None and dp2._dp_hdl is not None
+dp2_diff = max(abs(a - b) for a, b in zip(dp_losses, dp2_losses))
+dp2_param_diff = max(float((v.detach().cpu() - torch.from_numpy(dp_state[k])).abs().max()) for k, v in m2.state_dict().items())
+dp2.close()
 if rank == 0:
     S2 = O.AdamState(); dp_ref = []
     for st in range(4):
@@ -121,7 +130,8 @@ if rank == 0:
     V.assert_topk_equivalent(s.cpu().numpy(), i.cpu().numpy(), s_ref, i_ref)
     print("RESULT " + json.dumps({"losses": losses, "ref": ref, "max_param_err": err, "dp_losses": dp_losses, "dp_ref": dp_ref,
                                   "dp_err": dp_err, "pad_diff": pad_diff, "pad_param_diff": pad_param_diff,
-                                  "p2p_diff": p2p_diff, "p2p_param_diff": p2p_param_diff}))
+                                  "p2p_diff": p2p_diff, "p2p_param_diff": p2p_param_diff,
+                                  "dp2_diff": dp2_diff, "dp2_param_diff": dp2_param_diff}))
 dist.barrier(); dist.destroy_process_group()
 '''
 
@@ -166,6 +176,8 @@ def test_sharded_world2_nccl_matches_single_process_oracle(tmp_path):
     assert r["dp_err"] <= 0.5 * 1e-2, r
     assert r["pad_diff"] <= 1e-6 and r["pad_param_diff"] <= 1e-6, r
     assert r["p2p_diff"] <= 1e-6 and r["p2p_param_diff"] <= 1e-6, r
+    # peer-memory all-reduce of the data-parallel replicas vs the NCCL one (different summation orders of two addends: equal here)
+    assert r["dp2_diff"] <= 1e-6 and r["dp2_param_diff"] <= 2e-5, r
 
 
 @pytest.mark.parametrize("world,n_u,n_i", [(1, 100, 200), (2, 8192, 16384), (8, 5000, 10001), (3, 0, 77), (64, 300, 0)])
