@@ -4,9 +4,12 @@ import numpy as np
 import pytest
 import torch
 
+from pathlib import Path
+
 from oracle import ivf_oracle as V
 
 pytestmark = pytest.mark.gpu
+ROOT = Path(__file__).resolve().parents[1]
 
 
 def _data(n, d, nlist, seed, skew=False):
@@ -340,3 +343,29 @@ def test_real_faiss_cross_check(tmp_path):
     fi2.nprobe = 5
     fs2, fids2 = fi2.search(q, 50)
     V.assert_topk_equivalent(fs2, fids2, fs, fids)
+
+
+@pytest.mark.parametrize("env", [{"RB200_FLAT_FILTER_TF32": "1"}, {"RB200_FLAT_FILTER": "0"}, {"RB200_FLAT_STREAM": "0"},
+                                 {"RB200_FLAT_FILTER": "0", "RB200_FLAT_VARIANT": "0"}])
+def test_flat_search_kernel_variants_behind_the_tuning_knobs(env):
+    """The pruned rounds have one default kernel per batch size (bf16 filter above 128 queries, TMA stream up to 128); the other
+    forms stay reachable through environment knobs read once per process — tf32 filter, 3xTF32 scan with the rows in TMEM or in
+    shared memory, per-tile CTAs for small batches.  Each runs in its own process against the fp64 top-k of a library matmul."""
+    import os, subprocess, sys
+    code = r'''
+import sys, torch
+sys.path.insert(0, %r)
+import recommendit_b200 as R
+g = torch.Generator(device="cuda").manual_seed(3)
+x = torch.nn.functional.normalize(torch.randn(150001, 64, device="cuda", generator=g), dim=-1)
+for nq in (40, 333):
+    q = torch.nn.functional.normalize(torch.randn(nq, 64, device="cuda", generator=g), dim=-1)
+    s, i = R.flat_search(q, x, 200)
+    ref = torch.topk(q.double() @ x.double().T, 200, dim=1)
+    same = i == ref.indices
+    near = (s.double() - ref.values).abs() <= 4e-7
+    assert bool((same | near).all()) and float((s.double() - ref.values).abs().max()) <= 2e-6, (nq, float(same.float().mean()))
+print("VARIANT-OK")
+''' % str(ROOT)
+    out = subprocess.run([sys.executable, "-c", code], env={**os.environ, **env}, capture_output=True, text=True, timeout=300)
+    assert "VARIANT-OK" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
