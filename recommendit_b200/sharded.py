@@ -166,12 +166,14 @@ class CudaOps:
         return out
 
     def gather_rows_sharded(self, shard_ptrs: List[int], user_rows_by_rank: List[int], user_ids: torch.Tensor, item_ids: torch.Tensor,
-                            n_user_rows: int, n_item_rows: int, D: int, err_flag: Optional[torch.Tensor]) -> torch.Tensor:
+                            n_user_rows: int, n_item_rows: int, D: int, err_flag: Optional[torch.Tensor],
+                            out: Optional[torch.Tensor] = None) -> torch.Tensor:
         """out[r] = the row of request r (sample order [users | items]) read straight from its owner's shard through the peer
         pointers (``rb200_gather_rows_sharded``): no id exchange, no owner-side gather, no row exchange"""
         W = len(shard_ptrs)
         n = user_ids.numel() + item_ids.numel()
-        out = torch.empty(n, D, dtype=torch.float32, device=user_ids.device)
+        if out is None:
+            out = torch.empty(n, D, dtype=torch.float32, device=user_ids.device)
         check(self.lib.rb200_gather_rows_sharded((C.c_void_p * W)(*shard_ptrs), (C.c_int64 * W)(*user_rows_by_rank), W, ptr(user_ids),
                                                  user_ids.numel(), ptr(item_ids), item_ids.numel(), n_user_rows, n_item_rows, D, ptr(out),
                                                  ptr(err_flag), stream_ptr()), "rb200_gather_rows_sharded")
@@ -478,7 +480,7 @@ class ShardedBPRTrainer:
             # high priority: the exchange plan, the row lists and the sort of the received rows are many small kernels that must not
             # queue behind the towers' CTAs.  (Running the user tower's backward on a second side stream was tried: the towers' phase
             # shrank by 20 us but the replay period did not — C4 at world 1 0.273 -> 0.278 ms.)
-            self._side = [torch.cuda.Stream(device=self.dev, priority=-1)]
+            self._side = [torch.cuda.Stream(device=self.dev, priority=-1), torch.cuda.Stream(device=self.dev)]
         return self._side[i]
 
     def _barrier(self, channel: int) -> None:
@@ -651,8 +653,20 @@ class ShardedBPRTrainer:
                     nu0 = self.user_table.shape[0]
                     rows_sc = torch.where((rows_sc == 0) | (rows_sc == nu0), torch.full_like(rows_sc, -1), rows_sc)
                 uq, n_uq, scat_ws = ops.scatter_plan(rows_sc, max(self.table.shape[0], 1), -1)
-            rows = ops.gather_rows_sharded(self._shard_ptrs, self._nu_host, user_ids.contiguous(), item_ids, self.n_user_rows,
-                                           self.n_item_rows, D, self.err_flag)
+            split_fwd = W > 1      # several GPUs: the item rows cross NVLink on a second side stream under the user tower's forward
+            if split_fwd:
+                rows = torch.empty(3 * B, D, **f32)
+                none = user_ids[:0]
+                side2 = self._side_stream(1)
+                side2.wait_stream(main)
+                with torch.cuda.stream(side2):
+                    ops.gather_rows_sharded(self._shard_ptrs, self._nu_host, none, item_ids, self.n_user_rows, self.n_item_rows, D,
+                                            self.err_flag, out=rows[B:])
+                ops.gather_rows_sharded(self._shard_ptrs, self._nu_host, user_ids.contiguous(), none, self.n_user_rows, self.n_item_rows, D,
+                                        self.err_flag, out=rows[:B])
+            else:
+                rows = ops.gather_rows_sharded(self._shard_ptrs, self._nu_host, user_ids.contiguous(), item_ids, self.n_user_rows,
+                                               self.n_item_rows, D, self.err_flag)
             if getattr(self, "_ident", None) is None or self._ident.numel() != 3 * B:
                 self._ident = torch.arange(3 * B, dtype=torch.int64, device=dev)
             rt = Route(perm=None, inv=self._ident, local_rows=None, send_counts=None, recv_rows=None)
@@ -687,9 +701,15 @@ class ShardedBPRTrainer:
             dict(table=rows, ids=inv_n, extra=neg_genres, W1=iW1, b1=ib1, W2=iW2, b2=ib2, out=out[2 * B:], hid=hid[2 * B:], denom=den[2 * B:]),
         ]
         drop_p = self.dropout
-        if drop_p > 0.0:
-            # masks keyed by (seed of this rank; optimizer step read on the device, so a graph replay draws new ones)
-            ops.towers_fwd(jobs, D, H, drop_p, self.seed + 7919 * self.rank, 0, self.opt.data_ptr() + OptState.step.offset)
+        # masks keyed by (seed of this rank; optimizer step read on the device, so a graph replay draws new ones)
+        seed_r, step_dev = self.seed + 7919 * self.rank, self.opt.data_ptr() + OptState.step.offset
+        if p2p and split_fwd:
+            # user tower as soon as its rows are here, item towers when theirs have arrived (own launch: own mask stream)
+            ops.towers_fwd(jobs[:1], D, H, drop_p, seed_r if drop_p > 0.0 else 0, 0, step_dev if drop_p > 0.0 else None)
+            main.wait_stream(side2)
+            ops.towers_fwd(jobs[1:], D, H, drop_p, seed_r + 1000003 if drop_p > 0.0 else 0, 0, step_dev if drop_p > 0.0 else None)
+        elif drop_p > 0.0:
+            ops.towers_fwd(jobs, D, H, drop_p, seed_r, 0, step_dev)
         else:
             ops.towers_fwd(jobs, D, H, 0.0, 0, 0)
         self._mark("towers_fwd")
