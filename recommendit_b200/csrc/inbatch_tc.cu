@@ -385,11 +385,17 @@ __global__ void __launch_bounds__(256) inbatch_finish_kernel(const float* __rest
     reinterpret_cast<float4*>(out + (long long)row * DD)[c4] = a;
 }
 
-__global__ void inbatch_loss_kernel(const double* __restrict__ partials, int n, double scale, float* __restrict__ out) {
+// err: the tensor-core kernels' time-out flag — a pipeline that gave up (wrong descriptor, heavy preemption) must not pass garbage
+// on as a result: the loss becomes NaN
+__global__ void inbatch_loss_kernel(const double* __restrict__ partials, int n, double scale, float* __restrict__ out, const int* __restrict__ err) {
     double t = 0.0;
     for (int i = threadIdx.x; i < n; i += 32) t += partials[i];
     t = rb_warp_sum_d(t);
-    if (threadIdx.x == 0) out[0] = (float)(t * scale);
+    if (threadIdx.x == 0) out[0] = (err && *err) ? __int_as_float(0x7fc00000) : (float)(t * scale);
+}
+// after the gradient pass: a time-out there also poisons the loss
+__global__ void inbatch_poison_kernel(const int* __restrict__ err, float* __restrict__ loss) {
+    if (*err) loss[0] = __int_as_float(0x7fc00000);
 }
 
 // column means of U (blockIdx.y = 0) and I (1): fixed-order partial sums over CM_BLOCKS row ranges, then one small block
@@ -812,18 +818,18 @@ int rb_inbatch_tc(const float* U, const float* I, int B, int D, int mode, float*
         RB_LAUNCH_CHECK("colsum_final_kernel");
     }
     const int fgrid = (B * 16 + 255) / 256;
+    RB_CUDA(cudaMemsetAsync(err, 0, sizeof(int), st));
     if (use_ts) {
         inbatch_images_kernel<<<dim3(pl.n_yt, 2), 256, 0, st>>>(U, I, B, grad ? cen : nullptr, img_u, img_i);
         RB_LAUNCH_CHECK("inbatch_images_kernel");
         IbTsParams q{};
         q.diag = diag; q.B = B; q.split = pl.split; q.tiles_per_split = pl.tps; q.Bp = pl.Bp; q.g = p.g;
         q.acc_part = acc_part; q.r_part = r_part; q.loss_part = loss_part; q.err_flag = err;
-        RB_CUDA(cudaMemsetAsync(err, 0, sizeof(int), st));
         q.X = U; q.yimg = img_i;
         if (mode == 2) rc = grad ? launch_ts<2, false, true>(q, pl.grid, st) : launch_ts<2, false, false>(q, pl.grid, st);
         else rc = grad ? launch_ts<1, false, true>(q, pl.grid, st) : launch_ts<1, false, false>(q, pl.grid, st);
         if (rc) return rc;
-        inbatch_loss_kernel<<<1, 32, 0, st>>>(loss_part, pl.grid, 1.0 / denom, loss);
+        inbatch_loss_kernel<<<1, 32, 0, st>>>(loss_part, pl.grid, 1.0 / denom, loss, err);
         RB_LAUNCH_CHECK("inbatch_loss_kernel");
         if (!grad) return RB200_OK;
         inbatch_finish_kernel<false><<<fgrid, 256, 0, st>>>(acc_part, r_part, r_total, I, cen + DD, dU, B, pl.Bp, pl.split, NQ2);
@@ -833,13 +839,15 @@ int rb_inbatch_tc(const float* U, const float* I, int B, int D, int mode, float*
         if (rc) return rc;
         inbatch_finish_kernel<true><<<fgrid, 256, 0, st>>>(acc_part, r_part, r_total, U, cen, dI, B, pl.Bp, pl.split, NQ2);
         RB_LAUNCH_CHECK("inbatch_finish_kernel");
+        inbatch_poison_kernel<<<1, 1, 0, st>>>(err, loss);
+        RB_LAUNCH_CHECK("inbatch_poison_kernel");
         return RB200_OK;
     }
     p.X = U; p.Y = I; p.ycen = cen + DD;
     if (mode == 2) rc = grad ? launch<2, false, true>(p, pl.grid, st) : launch<2, false, false>(p, pl.grid, st);
     else rc = grad ? launch<1, false, true>(p, pl.grid, st) : launch<1, false, false>(p, pl.grid, st);
     if (rc) return rc;
-    inbatch_loss_kernel<<<1, 32, 0, st>>>(loss_part, pl.grid, 1.0 / denom, loss);
+    inbatch_loss_kernel<<<1, 32, 0, st>>>(loss_part, pl.grid, 1.0 / denom, loss, err);
     RB_LAUNCH_CHECK("inbatch_loss_kernel");
     if (!grad) return RB200_OK;
     inbatch_finish_kernel<false><<<fgrid, 256, 0, st>>>(acc_part, r_part, r_total, I, cen + DD, dU, B, pl.Bp, pl.split, NQ);
@@ -849,5 +857,7 @@ int rb_inbatch_tc(const float* U, const float* I, int B, int D, int mode, float*
     if (rc) return rc;
     inbatch_finish_kernel<true><<<fgrid, 256, 0, st>>>(acc_part, r_part, r_total, U, cen, dI, B, pl.Bp, pl.split, NQ);
     RB_LAUNCH_CHECK("inbatch_finish_kernel");
+    inbatch_poison_kernel<<<1, 1, 0, st>>>(err, loss);
+    RB_LAUNCH_CHECK("inbatch_poison_kernel");
     return RB200_OK;
 }

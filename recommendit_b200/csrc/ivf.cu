@@ -797,6 +797,7 @@ struct PlanLayout {
     float* coarse; int* probes; int* cand_base; long long* totals; long long* cand_off; long long* tot2;
     int* list_qcount; int* list_qstart; int* pair_qp;
     float* probe_scores; int64_t* probe_ids;
+    int* tc_err;               // set by the tcgen05 coarse GEMM when one of its bounded barrier waits times out
 };
 bool carve_plan(RbArena& ar, int nq, int nlist, int nprobe, PlanLayout& L) {
     const size_t np = (size_t)nq * nprobe;
@@ -807,6 +808,7 @@ bool carve_plan(RbArena& ar, int nq, int nlist, int nprobe, PlanLayout& L) {
     L.list_qcount = ar.take<int>((size_t)nlist + 2); L.list_qstart = ar.take<int>((size_t)nlist + 2);
     L.pair_qp = ar.take<int>(np);
     L.probe_scores = ar.take<float>(np); L.probe_ids = ar.take<int64_t>(np);
+    L.tc_err = ar.take<int>(4);
     return ar.ok();
 }
 
@@ -876,7 +878,7 @@ extern "C" int rb200_ivf_build(const float* x, int64_t n, int D, const int32_t* 
 
 extern "C" size_t rb200_ivf_plan_workspace_bytes(int nq, int nlist, int nprobe) {
     const size_t np = (size_t)nq * nprobe;
-    return 256 * 18 + sizeof(float) * ((size_t)nq * nlist + np) + sizeof(int64_t) * np + sizeof(int) * (3 * np + 2 * ((size_t)nlist + 2)) +
+    return 256 * 19 + sizeof(float) * ((size_t)nq * nlist + np) + sizeof(int64_t) * np + sizeof(int) * (3 * np + 2 * ((size_t)nlist + 2)) +
            sizeof(long long) * (2 * ((size_t)nq + 1) + 2);
 }
 
@@ -891,7 +893,8 @@ extern "C" int rb200_ivf_search_plan(const float* q, int nq, int D, const float*
     PlanLayout L;
     if (!plan_ws || !carve_plan(ar, nq, nlist, nprobe, L)) return rb_set_error(RB200_ERR_WORKSPACE, "ivf_search_plan: workspace too small");
     {   // coarse quantizer q·Cᵀ on the tensor cores (3xTF32, fp32 accumulate in TMEM)
-        int rc = rb_gemm_nt_tc(q, nq, centroids, nlist, D, 2, L.coarse, nlist, nullptr, st);
+        RB_CUDA(cudaMemsetAsync(L.tc_err, 0, sizeof(int), st));
+        int rc = rb_gemm_nt_tc(q, nq, centroids, nlist, D, 2, L.coarse, nlist, L.tc_err, st);
         if (rc) return rc;
     }
     RB_CUDA(cudaMemsetAsync(L.list_qcount, 0, sizeof(int) * ((size_t)nlist + 2), st));
@@ -914,8 +917,12 @@ extern "C" int rb200_ivf_search_plan(const float* q, int nq, int D, const float*
     RB_LAUNCH_CHECK("pair_scatter_kernel");
     if (!total_candidates_host) return RB200_OK;      // asynchronous form (CUDA-graph capturable): the caller sizes by upper bounds
     long long h[2] = {0, 0};
+    int tc_err = 0;
     RB_CUDA(cudaMemcpyAsync(h, L.tot2, sizeof(h), cudaMemcpyDeviceToHost, st));
+    RB_CUDA(cudaMemcpyAsync(&tc_err, L.tc_err, sizeof(int), cudaMemcpyDeviceToHost, st));
     RB_CUDA(cudaStreamSynchronize(st));
+    // (the synchronous form is where a timed-out tensor-core pipeline can be reported: garbage probe lists must not pass as a result)
+    RB_REQUIRE(tc_err == 0, "ivf_search_plan: the coarse-quantizer GEMM's tensor-core pipeline timed out (flag %d)", tc_err);
     *total_candidates_host = h[0];
     *max_candidates_host = h[1];
     return RB200_OK;

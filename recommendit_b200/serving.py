@@ -30,11 +30,20 @@ class UserRecommender:
         self.lib = _lib.load()
         self.model, self.index = model.eval(), index
         self.dev = _lib.require_cuda(model.user_tower.embedding.weight, index.index.centroids)
-        st = index.index
-        self.k = min(int(k), st.ntotal)
-        self.nprobe = max(1, min(int(st.nprobe), st.nlist))
+        self._k_asked = int(k)
         self._id_pinned = torch.zeros(1, dtype=torch.int64).pin_memory()
         self._id_dev = torch.zeros(1, dtype=torch.int64, device=self.dev)
+        self._stream = torch.cuda.Stream(self.dev)
+        self._graph = None
+        self._captured_sig = None
+        self._captured_refs = None
+        self._size_buffers()
+
+    def _size_buffers(self) -> None:
+        """result / plan / candidate buffers for the index as it is now (construction, and again when the index was rebuilt)"""
+        st = self.index.index
+        self.k = min(self._k_asked, st.ntotal)
+        self.nprobe = max(1, min(int(st.nprobe), st.nlist))
         self._q = torch.empty(1, st.d, dtype=torch.float32, device=self.dev)
         self._scores = torch.empty(1, self.k, dtype=torch.float32, device=self.dev)
         self._ids = torch.empty(1, self.k, dtype=torch.int64, device=self.dev)
@@ -45,9 +54,15 @@ class UserRecommender:
         self._max_cand = self.nprobe * max(st.max_list_len, 1)           # upper bound: no read-back needed
         self._ws_bytes = self.lib.rb200_ivf_search_workspace_bytes(self._max_cand)
         self._ws = torch.empty(max(self._ws_bytes, 256), dtype=torch.uint8, device=self.dev)
-        self._stream = torch.cuda.Stream(self.dev)
-        self._graph = None
-        self._nprobe_captured = None
+
+    def _signature(self):
+        """Everything the captured graph has baked in: the device addresses of the model's parameters and of the index arrays, and the
+        sizes the workspaces were carved for.  A rebuilt index (``build_ivf_index`` again), ``model.to()`` or a re-flattened parameter
+        block moves them; replaying the old graph would then read freed memory."""
+        st = self.index.index
+        tensors = [p for p in self.model.user_tower.parameters()] + [st.centroids, st.offsets, st.list_vecs, st.tile_list, st.tile_idx,
+                                                                     self.index._list_item_ids]
+        return tuple(int(t.data_ptr()) for t in tensors) + (id(st), int(st.max_list_len), int(st.ntotal), int(st.nlist), int(st.d)), tensors
 
     def _enqueue(self) -> None:
         st = self.index.index
@@ -75,6 +90,10 @@ class UserRecommender:
             raise IndexError(f"user id {user_id} is outside the embedding table [0, {self.model.n_users}] (torch would raise "
                              "'index out of range in self')")
         self._id_pinned[0] = int(user_id)
+        sig, refs = self._signature()
+        if self._graph is not None and sig != self._captured_sig:
+            self._graph = None                                        # parameters or index arrays moved: size and capture again
+            self._size_buffers()
         with torch.cuda.device(self.dev), torch.cuda.stream(self._stream):
             if self._graph is None:
                 self._enqueue()                                       # eager once: kernel attributes, allocator
@@ -83,6 +102,7 @@ class UserRecommender:
                 with torch.cuda.graph(g, stream=self._stream):
                     self._enqueue()
                 self._graph = g
+                self._captured_sig, self._captured_refs = sig, refs   # (strong references: the captured addresses stay valid)
             self._graph.replay()
             self._stream.synchronize()
         s, ids = self._scores_pinned.numpy()[0], self._ids_pinned.numpy()[0]

@@ -128,6 +128,18 @@ def test_graph_captured_request_equals_the_two_drop_in_calls(d, nlist, nprobe):
     s_ref, i_ref = index.search(model.get_user_embedding(17, dev), 500)
     s, i = rec.recommend(17)
     assert np.array_equal(i, i_ref) and np.array_equal(s, s_ref)
+    # a rebuilt index (new device arrays behind the same FAISSIndex) and a moved parameter block are noticed: the request is captured
+    # again instead of replaying addresses that no longer hold the data
+    old_ptr = index.index.list_vecs.data_ptr()
+    keep_alive = index.index                                   # (keeps the old arrays allocated so that the new ones get new addresses)
+    index.build_ivf_index(emb[::-1].copy(), item_ids[::-1])
+    assert index.index.list_vecs.data_ptr() != old_ptr
+    model.user_tower.embedding.weight.data = model.user_tower.embedding.weight.data.clone()
+    for u in (5, 17):
+        s_ref, i_ref = index.search(model.get_user_embedding(u, dev), 500)
+        s, i = rec.recommend(u)
+        assert np.array_equal(i, i_ref) and np.array_equal(s, s_ref), u
+    del keep_alive
     index.set_n_probe(max(1, nprobe // 2))
     if nprobe // 2 >= 1 and nprobe // 2 != nprobe:
         with pytest.raises(RB200Error, match="n_probe changed"):
