@@ -606,6 +606,13 @@ def bench_hbm_kernels(dev):
     n_u = int(nuq.item())
     add("scatter_rows", ms, big_b * (4 * D4 + 8) + n_u * (4 * D4 + 8),
         f"deterministic sorted-segment sum of {big_b} gradient rows into {n_u} unique rows (radix sort of (id, sample) pairs included)")
+    # the two phases apart (rb200_scatter_plan needs only the ids: the steps run it on a side stream under the towers; what is left on
+    # the critical path is rb200_scatter_apply — rows in, unique rows out)
+    _lib.check(lib.rb200_scatter_plan(ids2.data_ptr(), big_b, rows, 0, uq.data_ptr(), nuq.data_ptr(), None, ws.data_ptr(), wsb, sp()))
+    ms_apply = timeit(lambda: _lib.check(lib.rb200_scatter_apply(grads.data_ptr(), big_b, D4, rows, None, uq.data_ptr(), ugr.data_ptr(),
+                                                                 nuq.data_ptr(), ws.data_ptr(), wsb, sp())))
+    add("scatter_apply", ms_apply, big_b * (4 * D4 + 4) + n_u * (4 * D4),
+        f"second phase alone (segment sums of {big_b} rows into {n_u} unique rows; the id sort is rb200_scatter_plan, off the critical path)")
     return res
 
 
