@@ -557,6 +557,46 @@ class ShardedBPRTrainer:
         self.steps += 1
         return self._static_loss
 
+    def train_epoch(self, batches) -> float:
+        """The reference's ``train_epoch`` loop (``train_embeddings.py:170-199``) over this rank's batches, given as 5-tuples of PINNED
+        host tensors ``(user_ids, pos_ids, pos_genres, neg_ids, neg_genres)`` of one shape: batch i+1 travels host → device on a copy
+        stream into the other of two staging sets while step i runs, every step's loss goes device → host into a pinned array
+        (4 bytes, asynchronous), and the host synchronises ONCE, at the end.  Returns the mean of the steps' global mean losses.
+        Collective over the ranks (every rank passes the same number of batches)."""
+        n = len(batches)
+        if n == 0:
+            return 0.0
+        main = torch.cuda.current_stream(self.dev)
+        if getattr(self, "_copy_stream", None) is None:
+            self._copy_stream = torch.cuda.Stream(device=self.dev)
+        cs = self._copy_stream
+        stage = [[torch.empty(t.shape, dtype=t.dtype, device=self.dev) for t in batches[0]] for _ in range(2)]
+        copied = [torch.cuda.Event() for _ in range(2)]
+        consumed = [torch.cuda.Event() for _ in range(2)]
+        losses = torch.empty(n, dtype=torch.float32).pin_memory()
+
+        def upload(i: int) -> None:
+            s = i % 2
+            with torch.cuda.stream(cs):
+                if i >= 2:
+                    cs.wait_event(consumed[s])                     # step i − 2 has taken this staging set
+                else:
+                    cs.wait_stream(main)
+                for dst, src in zip(stage[s], batches[i]):
+                    dst.copy_(src, non_blocking=True)
+                copied[s].record(cs)
+
+        upload(0)
+        for i in range(n):
+            if i + 1 < n:
+                upload(i + 1)
+            main.wait_event(copied[i % 2])
+            loss = self.step(*stage[i % 2])                        # (copies the staging set into the captured step's inputs, replays)
+            consumed[i % 2].record(main)
+            losses[i:i + 1].copy_(loss, non_blocking=True)
+        torch.cuda.synchronize(self.dev)
+        return float(losses.mean())
+
     _marks = None
     _stamp_buf = None
     _stamp_names: Optional[list] = None

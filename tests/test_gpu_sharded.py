@@ -158,6 +158,25 @@ def test_sharded_world1_padded_graph_equals_exact(golden, exchange):
         assert float((fa[k] - fb[k]).abs().max()) <= 1e-6, k
 
 
+def test_sharded_train_epoch_from_pinned_batches_equals_step_by_step(golden):
+    """ShardedBPRTrainer.train_epoch — batch i+1 uploaded on a copy stream under step i, losses read back asynchronously, one host
+    synchronisation — must walk the same trajectory as calling step() on device batches one by one."""
+    from recommendit_b200.sharded import ShardedBPRTrainer
+    g = golden("tt_d128")
+    nu, ni, D, H = (int(v) for v in g["meta"][:4])
+    init = {k: torch.from_numpy(g["init/" + k]) for k in O.PARAM_KEYS}
+    mk = lambda: ShardedBPRTrainer(nu, ni, D, H, adam_mode="rows", device="cuda", init=init, lr=float(g["lr"]), exchange="p2p",
+                                   use_cuda_graph=True)
+    a, b = mk(), mk()
+    host = [[torch.from_numpy(np.ascontiguousarray(x)).pin_memory() for x in batch_from_golden(g, s % 2)] for s in range(7)]
+    step_losses = [float(a.step(*[t.cuda() for t in hb])) for hb in host]
+    mean = b.train_epoch(host)
+    assert abs(mean - float(np.mean(np.asarray(step_losses, np.float32)))) <= 1e-6, (mean, step_losses)
+    fa, fb = a.full_state(), b.full_state()
+    for k in O.PARAM_KEYS:
+        assert torch.equal(fa[k], fb[k]), k
+
+
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
 def test_sharded_world2_nccl_matches_single_process_oracle(tmp_path):
     import json
