@@ -287,6 +287,10 @@ int rb200_opt_begin_step(rb200_opt_state* st, void* stream);
 /* peer-memory reduction of the step's scalars, see rb200_allreduce_oneshot above */
 int rb200_sharded_scalars_publish(const rb200_opt_state* st, const float* loss, float scale, float* slot, void* stream);
 int rb200_sharded_scalars_reduce(const void* const* slot_ptrs, int world, rb200_opt_state* st, void* stream);
+/* scalars_reduce + the sum of squares of the replicated dense gradient (n floats, counted once) + the clip coefficient, in one
+ * launch: st->sumsq = Σ_k slot_k.sumsq + Σ dense_grad², st->loss = Σ_k slot_k.loss, st->total_norm, st->clip_coef. */
+int rb200_sharded_scalars_finish(const void* const* slot_ptrs, int world, const float* dense_grad, int64_t n, rb200_opt_state* st,
+                                 void* stream);
 /* sumsq += Σ x² over up to 4 segments.  A segment is n floats at x; when `count` (device int) is
  * set the length is count[0]*row_len instead (compact unique-row gradients) and n is only the
  * capacity used to size the grid.  Deterministic (fixed partition, fixed-order fp64 finalisation). */
@@ -308,6 +312,11 @@ int rb200_adam_table_dense(float* w, float* m, float* v, int64_t n_rows, int D, 
 int rb200_adam_rows(float* w, float* m, float* v, int D, const int64_t* uniq_ids,
                     const float* uniq_grads, const int* n_uniq, int max_uniq,
                     const rb200_opt_state* st, void* stream);
+/* rb200_adam_rows on a table (shard) and rb200_adam_dense on up to two dense blocks (n0 / n1 floats, 16-byte aligned, may be 0) in ONE
+ * launch — the optimizer of the row-sharded step. */
+int rb200_adam_rows_dense2(float* w, float* m, float* v, int D, const int64_t* uniq_ids, const float* uniq_grads, const int* n_uniq,
+                           int max_uniq, float* w0, const float* g0, float* m0, float* v0, int64_t n0, float* w1, const float* g1,
+                           float* m1, float* v1, int64_t n1, const rb200_opt_state* st, void* stream);
 
 /* ------------------------------------------------------------------------------------------ *
  * The whole training step of src/training/train_embeddings.py:183-192 as ONE host call:

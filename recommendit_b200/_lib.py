@@ -112,6 +112,8 @@ SIGNATURES = {
     "rb200_allreduce_twoshot": (I, [P, I, I, I64, P]),
     "rb200_sharded_scalars_publish": (I, [P, P, F, P, P]),
     "rb200_sharded_scalars_reduce": (I, [P, I, P, P]),
+    "rb200_sharded_scalars_finish": (I, [P, I, P, I64, P, P]),
+    "rb200_adam_rows_dense2": (I, [P, P, P, I, P, P, P, I, P, P, P, P, I64, P, P, P, P, I64, P, P]),
     "rb200_sample_batch": (I, [P, P, I64, P, P, P, I64, I, U64, I64, I64, I64, I64, P, P, P, P]),
     "rb200_sample_batch_dev": (I, [P, I, P, P, P, P, P]),
     "rb200_route_plan_workspace_bytes": (SZ, [I64, I]),

@@ -1286,6 +1286,49 @@ __global__ void scalars_reduce_kernel(const PeerSrc P, int world, rb200_opt_stat
     }
 }
 
+// The tail of the sharded step's norm in ONE launch (one block): Σ over the ranks' published {Σg², loss} slots (rank order), plus the
+// sum of squares of the replicated MLP gradient (n floats; fp64, fixed order: per-thread strided, shuffle tree, warp order), then
+// total_norm and clip_coef — scalars_reduce + sumsq_accumulate + grad_norm_clip before.
+constexpr int SF_NT = 1024;
+__global__ void __launch_bounds__(SF_NT) scalars_finish_kernel(const PeerSrc P, int world, const float* __restrict__ g, long long n,
+                                                               rb200_opt_state* st) {
+    __shared__ double wpart[SF_NT / 32];
+    double a = 0.0;
+    for (long long i = threadIdx.x; i < n; i += SF_NT) { const double x = (double)g[i]; a += x * x; }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+    if ((threadIdx.x & 31) == 0) wpart[threadIdx.x >> 5] = a;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double s = 0.0;
+        float l = 0.f;
+        for (int k = 0; k < world; ++k) {
+            const volatile float* q = P.p[k];
+            s += (double)q[0] + (double)q[1];
+            l += q[2];
+        }
+        double mlp = 0.0;
+        for (int w = 0; w < SF_NT / 32; ++w) mlp += wpart[w];
+        s += mlp;
+        st->sumsq = s;
+        st->loss = l;
+        float tn;
+        st->clip_coef = clip_from_sumsq(s, st->max_norm, &tn);
+        st->total_norm = tn;
+    }
+}
+
+extern "C" int rb200_sharded_scalars_finish(const void* const* slot_ptrs, int world, const float* dense_grad, int64_t n, rb200_opt_state* st,
+                                            void* stream) {
+    RB_REQUIRE(slot_ptrs && st && world >= 1 && world <= RB200_MAX_PEERS && n >= 0 && (n == 0 || dense_grad), "sharded_scalars_finish: 1..%d ranks",
+               RB200_MAX_PEERS);
+    PeerSrc P{};
+    for (int k = 0; k < world; ++k) { RB_REQUIRE(slot_ptrs[k], "sharded_scalars_finish: NULL pointer of rank %d", k); P.p[k] = (const float*)slot_ptrs[k]; }
+    scalars_finish_kernel<<<1, SF_NT, 0, (cudaStream_t)stream>>>(P, world, dense_grad, (long long)n, st);
+    RB_LAUNCH_CHECK("scalars_finish_kernel");
+    return RB200_OK;
+}
+
 extern "C" int rb200_allreduce_oneshot(const void* const* src_ptrs, int world, int64_t n, float* out, void* stream) {
     RB_REQUIRE(src_ptrs && out && world >= 1 && world <= RB200_MAX_PEERS && n >= 4 && n % 4 == 0, "allreduce_oneshot: n must be a multiple of 4, 1..%d ranks", RB200_MAX_PEERS);
     PeerSrc P{};
@@ -1446,6 +1489,60 @@ extern "C" int rb200_adam_rows(float* w, float* m, float* v, int D, const int64_
     return RB200_OK;
 }
 
+// The sharded step's optimizer in ONE launch: Adam on the touched rows of the table shard and on up to two dense parameter blocks (the
+// replicated MLPs) — three launches before, at ≈ 3 us of launch boundary each inside the step's graph.
+__global__ void __launch_bounds__(NT) adam_rows_dense2_kernel(float* __restrict__ w, float* __restrict__ m, float* __restrict__ v, int D4,
+                                                              const int64_t* __restrict__ uniq_ids, const float* __restrict__ uniq_grads,
+                                                              const int* __restrict__ n_uniq, const AdamDenseParams dp,
+                                                              const rb200_opt_state* __restrict__ st) {
+    const AdamK k = load_adam(st);
+    const long long stride = (long long)gridDim.x * NT;
+    const long long n4 = (long long)n_uniq[0] * D4;
+    for (long long i = (long long)blockIdx.x * NT + threadIdx.x; i < n4; i += stride) {
+        const long long u = i / D4;
+        const int c = (int)(i - u * D4);
+        const long long o = __ldg(uniq_ids + u) * D4 + c;
+        const float4 gv = __ldg(reinterpret_cast<const float4*>(uniq_grads) + i);
+        float4 wv = reinterpret_cast<float4*>(w)[o], mv = reinterpret_cast<float4*>(m)[o], vv = reinterpret_cast<float4*>(v)[o];
+        adam4(wv, gv, mv, vv, k);
+        reinterpret_cast<float4*>(w)[o] = wv; reinterpret_cast<float4*>(m)[o] = mv; reinterpret_cast<float4*>(v)[o] = vv;
+    }
+    for (int j = 0; j < dp.n_jobs; ++j) {
+        const AdamDenseJob& J = dp.job[j];
+        const long long d4 = J.n >> 2;
+        for (long long i = (long long)blockIdx.x * NT + threadIdx.x; i < d4; i += stride) {
+            float4 wv = reinterpret_cast<float4*>(J.w)[i], mv = reinterpret_cast<float4*>(J.m)[i], vv = reinterpret_cast<float4*>(J.v)[i];
+            const float4 gv = __ldg(reinterpret_cast<const float4*>(J.g) + i);
+            adam4(wv, gv, mv, vv, k);
+            reinterpret_cast<float4*>(J.w)[i] = wv; reinterpret_cast<float4*>(J.m)[i] = mv; reinterpret_cast<float4*>(J.v)[i] = vv;
+        }
+        for (long long i = d4 * 4 + (long long)blockIdx.x * NT + threadIdx.x; i < J.n; i += stride) {
+            float wv = J.w[i], mv = J.m[i], vv = J.v[i];
+            adam1(wv, __ldg(J.g + i), mv, vv, k);
+            J.w[i] = wv; J.m[i] = mv; J.v[i] = vv;
+        }
+    }
+}
+
+extern "C" int rb200_adam_rows_dense2(float* w, float* m, float* v, int D, const int64_t* uniq_ids, const float* uniq_grads, const int* n_uniq,
+                                      int max_uniq, float* w0, const float* g0, float* m0, float* v0, int64_t n0, float* w1, const float* g1,
+                                      float* m1, float* v1, int64_t n1, const rb200_opt_state* st, void* stream) {
+    RB_REQUIRE(w && m && v && st && uniq_ids && uniq_grads && n_uniq && D >= 4 && D % 4 == 0 && max_uniq >= 0, "adam_rows_dense2: bad arguments");
+    RB_REQUIRE(n0 >= 0 && n1 >= 0 && (n0 == 0 || (w0 && g0 && m0 && v0)) && (n1 == 0 || (w1 && g1 && m1 && v1)), "adam_rows_dense2: bad dense blocks");
+    auto al = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+    RB_REQUIRE((n0 == 0 || (al(w0) && al(g0) && al(m0) && al(v0))) && (n1 == 0 || (al(w1) && al(g1) && al(m1) && al(v1))),
+               "adam_rows_dense2: the dense blocks must be 16-byte aligned");
+    AdamDenseParams dp{};
+    if (n0 > 0) dp.job[dp.n_jobs++] = AdamDenseJob{w0, g0, m0, v0, (long long)n0};
+    if (n1 > 0) dp.job[dp.n_jobs++] = AdamDenseJob{w1, g1, m1, v1, (long long)n1};
+    long long work = (long long)max_uniq * (D / 4);
+    if (n0 / 4 > work) work = n0 / 4;
+    if (n1 / 4 > work) work = n1 / 4;
+    if (work <= 0) return RB200_OK;
+    adam_rows_dense2_kernel<<<stream_grid(work), NT, 0, (cudaStream_t)stream>>>(w, m, v, D / 4, uniq_ids, uniq_grads, n_uniq, dp, st);
+    RB_LAUNCH_CHECK("adam_rows_dense2_kernel");
+    return RB200_OK;
+}
 
 // ---- fused-step helpers: two tensors per launch ------------------------------------------------------------------ //
 int rb_adam_dense2(float* w0, const float* g0, float* m0, float* v0, long long n0, float* w1, const float* g1, float* m1, float* v1,

@@ -201,6 +201,21 @@ class CudaOps:
     def scalars_publish(self, opt: torch.Tensor, loss: torch.Tensor, scale: float, slot: torch.Tensor) -> None:
         check(self.lib.rb200_sharded_scalars_publish(ptr(opt), ptr(loss), scale, ptr(slot), stream_ptr()), "rb200_sharded_scalars_publish")
 
+    def scalars_finish(self, slot_ptrs: List[int], dense_grad: torch.Tensor, opt: torch.Tensor) -> None:
+        """scalars_reduce + Σ dense_grad² + the clip coefficient in one launch (``rb200_sharded_scalars_finish``)"""
+        W = len(slot_ptrs)
+        check(self.lib.rb200_sharded_scalars_finish((C.c_void_p * W)(*slot_ptrs), W, ptr(dense_grad), dense_grad.numel(), ptr(opt),
+                                                    stream_ptr()), "rb200_sharded_scalars_finish")
+
+    def adam_rows_dense2(self, w, m, v, uniq, ug, nu, dense, opt) -> None:
+        """Adam on the touched rows of ``w`` and on the dense blocks ``dense = [(w, g, m, v), …]`` (at most two) in one launch"""
+        d = list(dense) + [(None, None, None, None)] * (2 - len(dense))
+        n = [0 if t[0] is None else t[0].numel() for t in d]
+        check(self.lib.rb200_adam_rows_dense2(ptr(w), ptr(m), ptr(v), w.shape[1], ptr(uniq), ptr(ug), ptr(nu), uniq.numel(),
+                                              ptr(d[0][0]), ptr(d[0][1]), ptr(d[0][2]), ptr(d[0][3]), n[0],
+                                              ptr(d[1][0]), ptr(d[1][1]), ptr(d[1][2]), ptr(d[1][3]), n[1], ptr(opt), stream_ptr()),
+              "rb200_adam_rows_dense2")
+
     def scalars_reduce(self, slot_ptrs: List[int], opt: torch.Tensor) -> None:
         W = len(slot_ptrs)
         check(self.lib.rb200_sharded_scalars_reduce((C.c_void_p * W)(*slot_ptrs), W, ptr(opt), stream_ptr()), "rb200_sharded_scalars_reduce")
@@ -814,10 +829,10 @@ class ShardedBPRTrainer:
             self._mark("sumsq_publish")
             self._barrier(2)
             self._mark("barrier2")
-            ops.scalars_reduce(sc_ptrs, self.opt)                          # opt.sumsq = Σ over shards, opt.loss = global mean loss
             main.wait_stream(side)                                         # the reduced MLP gradients
             g_mlp = g_red[:Pu + Pi]
-            ops.sumsq(self.opt, [(g_mlp, None, 0)])                        # + the (replicated) MLP gradient, counted once
+            # opt.sumsq = Σ over shards + the (replicated) MLP gradient counted once, opt.loss = global mean loss, clip coefficient
+            ops.scalars_finish(sc_ptrs, g_mlp, self.opt)
         else:
             if W > 1:
                 dist.all_reduce(g_mlp, group=self.group)                   # Σ over ranks of (1/W)-scaled local gradients
@@ -834,15 +849,22 @@ class ShardedBPRTrainer:
                 opt32[_OPT_LOSS_F32:_OPT_LOSS_F32 + 1].copy_(red[1:2].to(torch.float32))
             else:
                 opt32[_OPT_LOSS_F32:_OPT_LOSS_F32 + 1].copy_(loss)          # one process: the sum of squares is already complete
-        ops.grad_norm_clip(self.opt)
+        if not sym_red:
+            ops.grad_norm_clip(self.opt)
         self._mark("allreduce_norm_clip")
 
-        ops.adam_dense(self.user_mlp, g_mlp[:Pu], self.state["user_mlp"], self.state_v["user_mlp"], self.opt)
-        ops.adam_dense(self.item_mlp, g_mlp[Pu:], self.state["item_mlp"], self.state_v["item_mlp"], self.opt)
-        if self.adam_mode == "dense":
-            ops.adam_table_dense(self.table, self.state["table"], self.state_v["table"], uq, ug, n_uq, self.slot, self.opt)
-        else:
-            ops.adam_rows(self.table, self.state["table"], self.state_v["table"], uq, ug, n_uq, self.opt)
+        mlp_aligned = Pu % 4 == 0 and all(t.data_ptr() % 16 == 0 for t in (self.user_mlp, self.item_mlp, g_mlp))
+        if self.adam_mode == "dense" or not mlp_aligned:
+            ops.adam_dense(self.user_mlp, g_mlp[:Pu], self.state["user_mlp"], self.state_v["user_mlp"], self.opt)
+            ops.adam_dense(self.item_mlp, g_mlp[Pu:], self.state["item_mlp"], self.state_v["item_mlp"], self.opt)
+            if self.adam_mode == "dense":
+                ops.adam_table_dense(self.table, self.state["table"], self.state_v["table"], uq, ug, n_uq, self.slot, self.opt)
+            else:
+                ops.adam_rows(self.table, self.state["table"], self.state_v["table"], uq, ug, n_uq, self.opt)
+        else:                   # touched rows of the shard + both MLP blocks: one launch
+            ops.adam_rows_dense2(self.table, self.state["table"], self.state_v["table"], uq, ug, n_uq,
+                                 [(self.user_mlp, g_mlp[:Pu], self.state["user_mlp"], self.state_v["user_mlp"]),
+                                  (self.item_mlp, g_mlp[Pu:], self.state["item_mlp"], self.state_v["item_mlp"])], self.opt)
         self._mark("adam")
         self.steps += 1
         return opt32[_OPT_LOSS_F32:_OPT_LOSS_F32 + 1].clone()
