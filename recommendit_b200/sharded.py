@@ -854,7 +854,7 @@ class ShardedBPRTrainer:
         self._mark("allreduce_norm_clip")
 
         mlp_aligned = Pu % 4 == 0 and all(t.data_ptr() % 16 == 0 for t in (self.user_mlp, self.item_mlp, g_mlp))
-        if self.adam_mode == "dense" or not mlp_aligned:
+        if self.adam_mode == "dense" or not mlp_aligned or not hasattr(ops, "adam_rows_dense2"):     # (stand-in ops of the CPU tests)
             ops.adam_dense(self.user_mlp, g_mlp[:Pu], self.state["user_mlp"], self.state_v["user_mlp"], self.opt)
             ops.adam_dense(self.item_mlp, g_mlp[Pu:], self.state["item_mlp"], self.state_v["item_mlp"], self.opt)
             if self.adam_mode == "dense":
