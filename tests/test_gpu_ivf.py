@@ -369,3 +369,20 @@ print("VARIANT-OK")
 ''' % str(ROOT)
     out = subprocess.run([sys.executable, "-c", code], env={**os.environ, **env}, capture_output=True, text=True, timeout=300)
     assert "VARIANT-OK" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
+
+
+@pytest.mark.parametrize("nlist,nprobe", [(1024, 8), (64, 32), (700, 5)])
+def test_probe_selection_with_equal_coarse_scores_prefers_the_lower_list(nlist, nprobe):
+    """Coarse-quantizer ties: with identical centroids every coarse score is the same, `index.add` puts every vector into list 0
+    (lowest-index tie rule) and a search must probe lists 0 … nprobe−1 — so it sees list 0 and returns the exhaustive result."""
+    import recommendit_b200 as R
+    rng = np.random.default_rng(nlist)
+    x = V.normalize_rows(rng.standard_normal((3000, 64)).astype(np.float32))
+    c = V.normalize_rows(rng.standard_normal((1, 64)).astype(np.float32))
+    cen = np.repeat(c, nlist, axis=0).copy()
+    idx = R.FAISSIndex(64, nlist, nprobe)
+    idx.build_ivf_index(x, list(range(1, 3001)), centroids=cen)
+    q = V.normalize_rows(rng.standard_normal((37, 64)).astype(np.float32))
+    s, ids = idx.batch_search(q, 50)
+    s_ref, i_ref = V.flat_search(q, x, 50)
+    V.assert_topk_equivalent(s, ids, s_ref, i_ref + 1)
