@@ -20,6 +20,9 @@
 #include "common.cuh"
 
 // tcgen05 score product (gemm_tc.cu): C[M,N] = A[M,K]·B[N,K]ᵀ, mode 2 = 3xTF32 (fp32-grade)
+int rb_list_scan_pipe(const float* q, int D, const float* list_vecs, const int64_t* offsets, const int* pair_qp, const long long* pair_dst,
+                      const int* list_qstart, int nprobe, float* cand, long long total_candidates, const int* tile_list, const int* tile_idx,
+                      long long n_tiles, int* err_flag, cudaStream_t st);
 int rb_list_scan_tc(const float* q, int D, const float* list_vecs, const int64_t* offsets, const int* pair_qp, const int* list_qstart,
                     int nprobe, const int* cand_base, const long long* cand_off, float* cand, const int* tile_list,
                     const int* tile_idx, long long n_tiles, cudaStream_t st);
@@ -341,14 +344,19 @@ __global__ void __launch_bounds__(PS_NT) plan_scans_kernel(const int* __restrict
 // (list, query) pairs grouped by list without a sort: pair i of list l goes to one of the list's slots [list_qstart[l], list_qstart[l+1]),
 // handed out by counting the list's counter down.  The order of a list's pairs is arbitrary (it only decides which query sits in which
 // column of the scan's MMAs: every candidate's destination comes from cand_base, so the results do not depend on it).
-__global__ void pair_scatter_kernel(const int* __restrict__ probes, long long n_pairs, const int* __restrict__ list_qstart,
-                                    int* __restrict__ list_qcount, int* __restrict__ pair_qp) {
+// pair_dst: where the pair's candidate scores start in the candidate buffer (cand_off of its query + cand_base of the probe) — the
+// scan then finds a chunk's destinations with one load instead of a pair → query → offset chain.
+__global__ void pair_scatter_kernel(const int* __restrict__ probes, long long n_pairs, int nprobe, const int* __restrict__ list_qstart,
+                                    int* __restrict__ list_qcount, const long long* __restrict__ cand_off, const int* __restrict__ cand_base,
+                                    int* __restrict__ pair_qp, long long* __restrict__ pair_dst) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_pairs) return;
     const int l = probes[i];
     if (l < 0) return;
     const int slot = atomicSub(list_qcount + l, 1) - 1;
-    pair_qp[list_qstart[l] + slot] = (int)i;
+    const int pos = list_qstart[l] + slot;
+    pair_qp[pos] = (int)i;
+    pair_dst[pos] = cand_off[i / nprobe] + cand_base[i];
 }
 
 // ------------------------------------------------------------------------------------------ //
@@ -795,7 +803,7 @@ __global__ void __launch_bounds__(NT) merge_gather_kernel(const float* __restric
 
 struct PlanLayout {
     float* coarse; int* probes; int* cand_base; long long* totals; long long* cand_off; long long* tot2;
-    int* list_qcount; int* list_qstart; int* pair_qp;
+    int* list_qcount; int* list_qstart; int* pair_qp; long long* pair_dst;
     float* probe_scores; int64_t* probe_ids;
     int* tc_err;               // set by the tcgen05 coarse GEMM when one of its bounded barrier waits times out
 };
@@ -806,7 +814,7 @@ bool carve_plan(RbArena& ar, int nq, int nlist, int nprobe, PlanLayout& L) {
     L.totals = ar.take<long long>((size_t)nq + 1); L.cand_off = ar.take<long long>((size_t)nq + 1);
     L.tot2 = ar.take<long long>(2);
     L.list_qcount = ar.take<int>((size_t)nlist + 2); L.list_qstart = ar.take<int>((size_t)nlist + 2);
-    L.pair_qp = ar.take<int>(np);
+    L.pair_qp = ar.take<int>(np); L.pair_dst = ar.take<long long>(np);
     L.probe_scores = ar.take<float>(np); L.probe_ids = ar.take<int64_t>(np);
     L.tc_err = ar.take<int>(4);
     return ar.ok();
@@ -878,7 +886,7 @@ extern "C" int rb200_ivf_build(const float* x, int64_t n, int D, const int32_t* 
 
 extern "C" size_t rb200_ivf_plan_workspace_bytes(int nq, int nlist, int nprobe) {
     const size_t np = (size_t)nq * nprobe;
-    return 256 * 19 + sizeof(float) * ((size_t)nq * nlist + np) + sizeof(int64_t) * np + sizeof(int) * (3 * np + 2 * ((size_t)nlist + 2)) +
+    return 256 * 20 + sizeof(float) * ((size_t)nq * nlist + np) + sizeof(int64_t) * 2 * np + sizeof(int) * (3 * np + 2 * ((size_t)nlist + 2)) +
            sizeof(long long) * (2 * ((size_t)nq + 1) + 2);
 }
 
@@ -913,7 +921,8 @@ extern "C" int rb200_ivf_search_plan(const float* q, int nq, int D, const float*
     const long long np = (long long)nq * nprobe;
     plan_scans_kernel<<<1, PS_NT, 0, st>>>(L.list_qcount, nlist, L.list_qstart, L.totals, nq, L.cand_off, L.tot2);
     RB_LAUNCH_CHECK("plan_scans_kernel");
-    pair_scatter_kernel<<<(unsigned)((np + NT - 1) / NT), NT, 0, st>>>(L.probes, np, L.list_qstart, L.list_qcount, L.pair_qp);
+    pair_scatter_kernel<<<(unsigned)((np + NT - 1) / NT), NT, 0, st>>>(L.probes, np, nprobe, L.list_qstart, L.list_qcount, L.cand_off,
+                                                                       L.cand_base, L.pair_qp, L.pair_dst);
     RB_LAUNCH_CHECK("pair_scatter_kernel");
     if (!total_candidates_host) return RB200_OK;      // asynchronous form (CUDA-graph capturable): the caller sizes by upper bounds
     long long h[2] = {0, 0};
@@ -948,9 +957,12 @@ extern "C" int rb200_ivf_search_run(const float* q, int nq, int D, int nlist, in
     float* cand = ar.take<float>((size_t)(total_candidates > 0 ? total_candidates : 1));
     if (!workspace || !ar.ok()) return rb_set_error(RB200_ERR_WORKSPACE, "ivf_search_run: workspace too small");
     if (total_candidates > 0 && max_list_len > 0) {
-        // D = 64 with a tile table: tcgen05 kernel (ivf_scan_tc.cu); otherwise the FFMA tile kernel
-        const int tc = rb_list_scan_tc(q, D, list_vecs, offsets, L.pair_qp, L.list_qstart, nprobe, L.cand_base, L.cand_off, cand,
-                                       tile_list, tile_idx, n_tiles, st);
+        // D = 64 with a tile table: the persistent, prefetching tcgen05 kernel (ivf_scan_tc.cu); RB200_IVF_PIPE=0: one CTA per tile
+        int tc = rb_list_scan_pipe(q, D, list_vecs, offsets, L.pair_qp, L.pair_dst, L.list_qstart, nprobe, cand, total_candidates, tile_list,
+                                   tile_idx, n_tiles, L.tc_err, st);
+        if (tc > 0)                 // (otherwise the FFMA tile kernel below)
+            tc = rb_list_scan_tc(q, D, list_vecs, offsets, L.pair_qp, L.list_qstart, nprobe, L.cand_base, L.cand_off, cand,
+                                 tile_list, tile_idx, n_tiles, st);
         if (tc < 0) return tc;
         if (tc != 0) {
             dim3 g((unsigned)((max_list_len + TT - 1) / TT), nlist);

@@ -5,6 +5,8 @@
 // the radix-sorted (list, query) pairs — are gathered in chunks of 64 as the B operand; S[128 vectors × 64 queries] is
 // accumulated in TMEM by tcgen05.mma and written to the compact candidate buffer (for a fixed query, the 32 lanes of a
 // warp hold 32 consecutive vectors → 128-byte stores).  D = 64.  96 KB of shared memory → 2 CTAs per SM.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "umma.cuh"
 
@@ -148,6 +150,289 @@ __global__ void __launch_bounds__(NT_SC, 2) list_scan_tc_kernel(const float* __r
     if (warp == 0) umma::tmem_free(tmem, QT);
 }
 
+// ------------------------------------------------------------------------------------------------------------------------ //
+// The same scan as a PERSISTENT, WARP-SPECIALISED kernel.  ncu on list_scan_tc_kernel (profiles/r02_ivf.md): warps active 22 %, 27 % of
+// the stall samples at the block barrier behind four dependent global round trips per work item (tile table → offsets / query range →
+// (list, query) pairs → query rows and destinations), and every unit — a 128-vector tile against a chunk of ≤ 64 probing queries; the
+// chunks beyond the first of a popular list are 40 % of the units on the bench's skewed index — ran load → stage → MMA → store as one
+// serial chain with two CTAs per SM to overlap.  (A first persistent form that only took the dependent chains off the main warps
+// measured the same 270 us per batch: the chain stage → MMA → store itself, ≈ 4.4 us per unit, was the bound.)
+//
+// One CTA per SM walks the tile table with stride gridDim.x and, per tile, the chunks of the queries that probe its list:
+//   * descriptor warp — owns every dependent chain: tile entry two tiles ahead and list geometry one tile ahead (registers), then per
+//     chunk one load of the pairs and of their destinations (pair_dst, precomputed by the plan) → a unit descriptor (query rows,
+//     destinations, tile geometry) in a ring of four shared-memory slots;
+//   * sixteen loader warps — global loads of unit u+2 go out (two register sets) before unit u+1 is staged: vector tile (when the tile
+//     changes; two shared-memory buffers) and query chunk (two buffers), hi/lo split, K-major operand layout;
+//   * one MMA warp — 24 tcgen05.mma per unit (3xTF32) with descriptors built once, two accumulators in TMEM;
+//   * eight epilogue warps — TMEM → candidate buffer (128-byte stores per (warp, query)).
+// Hand-offs through mbarriers only; every barrier has one waiting role that sees its phases in order.
+// Measured (device timestamps per role, one CTA): ≈ 3 us per unit — the loaders wait ≈ 1.6 us for the vector tile they requested a unit
+// earlier and the epilogue needs ≈ 2 us for its 32 stores per thread: the SM's load/store path, shared by the loaders' 16-byte gathers
+// and the 256 misaligned 128-byte candidate stores of a unit, is what bounds the kernel now (C3 batch 0.67 → 0.63 ms; a third query
+// buffer / accumulator and an L2 prefetch of the tiles changed nothing).  Next: the vector tile by tensor-map TMA (off the LSU).
+struct UnitDesc {
+    long long v0;              // first vector (row of list_vecs) of the tile
+    int nv;                    // vectors in the tile (≤ 128)
+    int new_tile;              // the vector tile has to be staged (first chunk of the tile)
+    int last;                  // last chunk of the tile (its vector buffer is free once these MMAs are done)
+    int valid;                 // 0: end of this CTA's work
+    unsigned dst[QT];          // per query of the chunk: where its scores for this tile start in cand (0xFFFFFFFF: no query)
+    int qrow[QT];              // per query of the chunk: its row in q (−1: none)
+};
+constexpr unsigned NO_DST = 0xFFFFFFFFu;
+constexpr int NQB = 3, NACC = 3;                            // query-chunk buffers and accumulators: with two of each the hand-off loop
+                                                            // stage → MMA → free (≈ 3 us) bounded the kernel at 1.6 us per unit
+constexpr int RING = 4, N_LOAD = 16, N_EPI = 8;            // (eight loader warps were busy 84 % of the time: staging bounded the kernel)
+constexpr int VPT = 64 / N_LOAD, QPT = 32 / N_LOAD;        // 16-byte pieces of the vector tile / the query chunk per loader thread
+constexpr int W_MMA = N_LOAD + N_EPI, W_DESC = W_MMA + 1, NT_PIPE = (W_DESC + 1) * 32;
+constexpr int N_BARS = 2 * RING + 2 * NQB + 2 + 2 * NACC;
+// 224 KB of operands + the descriptor ring + the barriers: everything in the dynamic block (a static block next to a 1024-byte aligned
+// dynamic one is padded to 1 KB, which would not fit the 227 KB any more)
+constexpr size_t PIPE_SMEM = 2 * (2 * V_BYTES) + NQB * (2 * Q_BYTES) + RING * sizeof(UnitDesc) + N_BARS * 8 + 16;
+
+__global__ void __launch_bounds__(NT_PIPE, 1) list_scan_pipe_kernel(const float* __restrict__ q, const float* __restrict__ list_vecs,
+                                                                    const int64_t* __restrict__ offsets, const int* __restrict__ pair_qp,
+                                                                    const long long* __restrict__ pair_dst,
+                                                                    const int* __restrict__ list_qstart, int nprobe, float* __restrict__ cand,
+                                                                    const int* __restrict__ tile_list, const int* __restrict__ tile_idx,
+                                                                    int n_tiles, int* __restrict__ err_flag) {
+    extern __shared__ __align__(1024) unsigned char smem[];
+    unsigned char* vbuf = smem;                                  // [2][hi V_BYTES | lo V_BYTES]
+    unsigned char* qbuf = smem + 4 * V_BYTES;                    // [NQB][hi Q_BYTES | lo Q_BYTES]
+    UnitDesc* ring = reinterpret_cast<UnitDesc*>(qbuf + NQB * 2 * Q_BYTES);
+    uint64_t* bar_full = reinterpret_cast<uint64_t*>(ring + RING);
+    uint64_t* bar_empty = bar_full + RING;
+    uint64_t* bar_sfull = bar_empty + RING;
+    uint64_t* bar_qfree = bar_sfull + NQB;
+    uint64_t* bar_vfree = bar_qfree + NQB;
+    uint64_t* bar_done = bar_vfree + 2;
+    uint64_t* bar_free = bar_done + NACC;
+    uint32_t* tmem_slot_p = reinterpret_cast<uint32_t*>(bar_free + NACC);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if (warp == 0) umma::tmem_alloc(tmem_slot_p, 4 * QT);
+    if (tid == 32) {
+        for (int i = 0; i < RING; ++i) { umma::mbar_init(&bar_full[i], 1); umma::mbar_init(&bar_empty[i], N_LOAD + 1 + N_EPI); }
+        for (int i = 0; i < NQB; ++i) { umma::mbar_init(&bar_sfull[i], N_LOAD); umma::mbar_init(&bar_qfree[i], 1); }
+        for (int i = 0; i < NACC; ++i) { umma::mbar_init(&bar_done[i], 1); umma::mbar_init(&bar_free[i], N_EPI); }
+        for (int i = 0; i < 2; ++i) umma::mbar_init(&bar_vfree[i], 1);
+        umma::fence_mbar_init();
+    }
+    umma::fence_before_sync();
+    __syncthreads();
+    umma::fence_after_sync();
+    const uint32_t tmem = *tmem_slot_p;
+    bool ok = true;
+
+    if (warp == W_DESC) {
+        // ================================ descriptor warp ================================ //
+        const int G = (int)gridDim.x;
+        int slot = 0, uses = 0;                                  // uses: descriptors written so far (slot = uses % RING)
+        auto publish = [&](bool okk) -> bool {                   // wait until the slot is free (its previous unit has been consumed)
+            if (uses >= RING && okk) okk = umma::mbar_wait(&bar_empty[slot], ((uses / RING) - 1) & 1);
+            return okk;
+        };
+        // software pipeline over this CTA's tile entries: entry e+2G's (tile, list) and entry e+G's list geometry are in flight while
+        // the chunks of entry e are described
+        const int e0 = (int)blockIdx.x;
+        int ti1 = 1, l1 = 0, ti2 = 1, l2 = 0;                    // entries e+G and e+2G (ti odd = nothing to do)
+        long long lb1 = 0, le1 = 0; int qs1 = 0, qe1 = 0;
+        int ti0 = 1, l0 = 0; long long lb0 = 0, le0 = 0; int qs0 = 0, qe0 = 0;
+        if (e0 < n_tiles) { ti0 = __ldg(tile_idx + e0); l0 = __ldg(tile_list + e0); }
+        if (e0 + G < n_tiles) { ti1 = __ldg(tile_idx + e0 + G); l1 = __ldg(tile_list + e0 + G); }
+        if (!(ti0 & 1)) { lb0 = __ldg(offsets + l0); le0 = __ldg(offsets + l0 + 1); qs0 = __ldg(list_qstart + l0); qe0 = __ldg(list_qstart + l0 + 1); }
+        for (int e = e0; e < n_tiles && ok; e += G) {
+            if (e + 2 * G < n_tiles) { ti2 = __ldg(tile_idx + e + 2 * G); l2 = __ldg(tile_list + e + 2 * G); } else ti2 = 1;
+            if (e + G < n_tiles && !(ti1 & 1)) {
+                lb1 = __ldg(offsets + l1); le1 = __ldg(offsets + l1 + 1); qs1 = __ldg(list_qstart + l1); qe1 = __ldg(list_qstart + l1 + 1);
+            }
+            const long long v0 = lb0 + (long long)ti0 * 64;
+            if (!(ti0 & 1) && v0 < le0 && qs0 < qe0) {
+                const int nv = (int)min((long long)VT, le0 - v0);
+                for (int p0 = qs0; p0 < qe0 && ok; p0 += QT) {
+                    int qp[2]; long long pd[2];                  // this chunk's pairs first (the only dependent loads of a unit), then the slot
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        const int pi = p0 + h * 32 + lane;
+                        qp[h] = pi < qe0 ? __ldg(pair_qp + pi) : -1;
+                        pd[h] = pi < qe0 ? __ldg(pair_dst + pi) : -1;
+                    }
+                    ok = publish(ok);
+                    if (!ok) break;
+                    UnitDesc& u = ring[slot];
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        u.qrow[h * 32 + lane] = qp[h] >= 0 ? qp[h] / nprobe : -1;
+                        u.dst[h * 32 + lane] = qp[h] >= 0 ? (unsigned)(pd[h] + (v0 - lb0)) : NO_DST;
+                    }
+                    if (p0 == qs0) {
+                        // the tile's rows on their way into L2 (this warp runs ≈ 3 units ahead of the loaders' reads: the database is
+                        // read once per batch, so every tile is an HBM miss otherwise — the loaders' first use of a row was 28 % of the
+                        // kernel's stall samples)
+                        const char* vp = reinterpret_cast<const char*>(list_vecs + v0 * DD);
+                        const int n_lines = nv * DD * 4 / 128;
+                        for (int ln = lane; ln < n_lines; ln += 32) asm volatile("prefetch.global.L2 [%0];" ::"l"(vp + (size_t)ln * 128));
+                    }
+                    if (lane == 0) { u.v0 = v0; u.nv = nv; u.new_tile = p0 == qs0; u.last = p0 + QT >= qe0; u.valid = 1; }
+                    __syncwarp();
+                    if (lane == 0) { __threadfence_block(); umma::mbar_arrive(&bar_full[slot]); }
+                    ++uses; slot = uses % RING;
+                }
+            }
+            ti0 = ti1; l0 = l1; lb0 = lb1; le0 = le1; qs0 = qs1; qe0 = qe1;
+            ti1 = ti2; l1 = l2;
+        }
+        ok = publish(ok);                                        // end marker
+        if (ok && lane == 0) { ring[slot].valid = 0; __threadfence_block(); umma::mbar_arrive(&bar_full[slot]); }
+        if (!ok && lane == 0 && err_flag) atomicOr(err_flag, 4);
+    } else if (warp < N_LOAD) {
+        // ================================ loader warps ================================ //
+        const int r8 = lane & 7, c4l = lane >> 3;
+        float4 qvA[QPT], vvA[VPT], qvB[QPT], vvB[VPT];
+        // this thread's pieces: (row, 16-byte column) of the tile and their K-major shared-memory offsets, fixed for the whole kernel
+        int vrow[VPT], vc4[VPT], qrow_i[QPT], qc4[QPT];
+        uint32_t voff[VPT], qoff[QPT];
+#pragma unroll
+        for (int i = 0; i < VPT; ++i) {
+            const int uu = warp * VPT + i;
+            vrow[i] = (uu >> 2) * 8 + r8; vc4[i] = (uu & 3) * 4 + c4l;
+            voff[i] = umma::kmajor_offset(VT, vrow[i], vc4[i] * 4);
+        }
+#pragma unroll
+        for (int i = 0; i < QPT; ++i) {
+            const int uu = warp * QPT + i;
+            qrow_i[i] = (uu >> 2) * 8 + r8; qc4[i] = (uu & 3) * 4 + c4l;
+            qoff[i] = umma::kmajor_offset(QT, qrow_i[i], qc4[i] * 4);
+        }
+        auto load_unit = [&](const UnitDesc& u, float4 (&qv)[QPT], float4 (&vv)[VPT]) {
+            if (u.new_tile) {
+#pragma unroll
+                for (int i = 0; i < VPT; ++i)
+                    vv[i] = vrow[i] < u.nv ? __ldg(reinterpret_cast<const float4*>(list_vecs + (u.v0 + vrow[i]) * DD) + vc4[i]) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+#pragma unroll
+            for (int i = 0; i < QPT; ++i) {
+                const int qr = u.qrow[qrow_i[i]];
+                qv[i] = qr >= 0 ? __ldg(reinterpret_cast<const float4*>(q + (long long)qr * DD) + qc4[i]) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        };
+        auto put = [&](unsigned char* hi_base, unsigned char* lo_base, uint32_t off, const float4& v) {
+            float4 hi, lo;
+            umma::split4(v, hi, lo);
+            *reinterpret_cast<float4*>(hi_base + off) = hi;
+            *reinterpret_cast<float4*>(lo_base + off) = lo;
+        };
+        int n_tile = -1;                                         // tiles started so far − 1: the vector buffer of the current tile is n_tile & 1
+        // unit u: descriptor in ring[u % RING]; stage it from the given register set
+        auto stage_unit = [&](int u, const float4 (&qv)[QPT], const float4 (&vv)[VPT]) {
+            const UnitDesc& d = ring[u % RING];
+            const int qb = u % NQB;
+            if (d.new_tile) {
+                ++n_tile;
+                const int vb = n_tile & 1;
+                if (n_tile >= 2 && ok) ok = umma::mbar_wait(&bar_vfree[vb], ((n_tile >> 1) - 1) & 1);
+                unsigned char* vh = vbuf + vb * 2 * V_BYTES;
+#pragma unroll
+                for (int i = 0; i < VPT; ++i) put(vh, vh + V_BYTES, voff[i], vv[i]);
+            }
+            if (u >= NQB && ok) ok = umma::mbar_wait(&bar_qfree[qb], ((u / NQB) - 1) & 1);
+            unsigned char* qh = qbuf + qb * 2 * Q_BYTES;
+#pragma unroll
+            for (int i = 0; i < QPT; ++i) put(qh, qh + Q_BYTES, qoff[i], qv[i]);
+            umma::fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) { umma::mbar_arrive(&bar_sfull[qb]); umma::mbar_arrive(&bar_empty[u % RING]); }
+        };
+        auto desc_ready = [&](int u) -> bool {                   // descriptor of unit u present and valid
+            if (ok) ok = umma::mbar_wait(&bar_full[u % RING], (u / RING) & 1);
+            return ok && ring[u % RING].valid;
+        };
+        // two register sets: the loads of unit u+1 are in flight while unit u is staged
+        bool vA = desc_ready(0), vB = false;
+        if (vA) load_unit(ring[0], qvA, vvA);
+        for (int u = 0; vA; u += 2) {
+            vB = desc_ready(u + 1);
+            if (vB) load_unit(ring[(u + 1) % RING], qvB, vvB);
+            stage_unit(u, qvA, vvA);
+            if (!vB) break;
+            vA = desc_ready(u + 2);
+            if (vA) load_unit(ring[(u + 2) % RING], qvA, vvA);
+            stage_unit(u + 1, qvB, vvB);
+        }
+        if (!ok && lane == 0 && err_flag) atomicOr(err_flag, 8);
+    } else if (warp == W_MMA) {
+        // ================================ MMA warp ================================ //
+        const uint32_t idesc = umma::idesc_tf32(VT, QT);
+        const uint32_t lbo_a = (VT / 8) * 128, lbo_b = (QT / 8) * 128;
+        const uint32_t v_s = umma::smem_u32(vbuf), q_s = umma::smem_u32(qbuf);
+        int n_tile = -1;
+        for (int u = 0; ok; ++u) {
+            ok = umma::mbar_wait(&bar_full[u % RING], (u / RING) & 1);
+            if (!ok) break;
+            const UnitDesc& d = ring[u % RING];
+            if (!d.valid) break;
+            const int new_tile = d.new_tile, last = d.last;
+            if (new_tile) ++n_tile;
+            const int vb = n_tile & 1, qb = u % NQB, a = u % NACC;
+            ok = umma::mbar_wait(&bar_sfull[qb], (u / NQB) & 1);
+            if (ok && u >= NACC) ok = umma::mbar_wait(&bar_free[a], ((u / NACC) - 1) & 1);
+            if (!ok) break;
+            umma::fence_after_sync();
+            if (umma::elect_one()) {
+                const uint64_t dah = umma::smem_desc(v_s + vb * 2 * V_BYTES, lbo_a, 128), dal = umma::smem_desc(v_s + vb * 2 * V_BYTES + V_BYTES, lbo_a, 128);
+                const uint64_t dbh = umma::smem_desc(q_s + qb * 2 * Q_BYTES, lbo_b, 128), dbl = umma::smem_desc(q_s + qb * 2 * Q_BYTES + Q_BYTES, lbo_b, 128);
+                const uint32_t acc = tmem + (uint32_t)a * QT;
+#pragma unroll
+                for (int j = 0; j < DD / 8; ++j) {
+                    const uint64_t oa = (uint64_t)((2 * j * lbo_a) >> 4), ob = (uint64_t)((2 * j * lbo_b) >> 4);
+                    umma::mma_tf32(acc, dal + oa, dbh + ob, idesc, j > 0);
+                    umma::mma_tf32(acc, dah + oa, dbl + ob, idesc, true);
+                    umma::mma_tf32(acc, dah + oa, dbh + ob, idesc, true);
+                }
+                umma::commit(&bar_done[a]);                      // → epilogue of this unit
+                umma::commit(&bar_qfree[qb]);                    // → the query buffer may be refilled
+                if (last) umma::commit(&bar_vfree[vb]);          // → so may the vector buffer, when this was the tile's last chunk
+                umma::mbar_arrive(&bar_empty[u % RING]);
+            }
+            __syncwarp();
+        }
+        if (!ok && lane == 0 && err_flag) atomicOr(err_flag, 1);
+    } else {
+        // ================================ epilogue warps ================================ //
+        const int ew = warp - N_LOAD;
+        const int r_own = ((ew & 3) << 5) + lane, half = ew >> 2;
+        const uint32_t lane_off = (uint32_t)((ew & 3) * 32) << 16;
+        for (int u = 0; ok; ++u) {
+            ok = umma::mbar_wait(&bar_full[u % RING], (u / RING) & 1);
+            if (!ok) break;
+            const UnitDesc& d = ring[u % RING];
+            if (!d.valid) break;
+            const int a = u % NACC;
+            ok = umma::mbar_wait(&bar_done[a], (u / NACC) & 1);
+            if (!ok) break;
+            umma::fence_after_sync();
+            float s[32];
+            umma::tmem_ld32(tmem + lane_off + (uint32_t)a * QT + half * 32, s);
+            umma::fence_before_sync();
+            __syncwarp();
+            if (lane == 0) umma::mbar_arrive(&bar_free[a]);      // the scores are in registers: the accumulator goes back to the MMA warp
+            if (r_own < d.nv) {
+#pragma unroll
+                for (int c = 0; c < 32; ++c) {
+                    const unsigned dd = d.dst[half * 32 + c];
+                    if (dd != NO_DST) __stcs(cand + (size_t)dd + r_own, s[c]);
+                }
+            }
+            __syncwarp();
+            if (lane == 0) umma::mbar_arrive(&bar_empty[u % RING]);
+        }
+        if (!ok && lane == 0 && err_flag) atomicOr(err_flag, 2);
+    }
+    umma::fence_before_sync();
+    __syncthreads();
+    if (warp == 0) umma::tmem_free(tmem, 4 * QT);
+}
+
 }  // namespace
 
 // returns 1 when this kernel does not cover the shape (caller uses the FFMA kernel)
@@ -163,5 +448,26 @@ int rb_list_scan_tc(const float* q, int D, const float* list_vecs, const int64_t
     list_scan_tc_kernel<<<(unsigned)n_tiles, NT_SC, SC_SMEM, st>>>(q, list_vecs, offsets, pair_qp, list_qstart, nprobe, cand_base,
                                                                    cand_off, cand, tile_list, tile_idx, nullptr);
     RB_LAUNCH_CHECK("list_scan_tc_kernel");
+    return RB200_OK;
+}
+
+// returns 1 when this kernel does not cover the shape or is switched off (RB200_IVF_PIPE=0: one CTA per tile, list_scan_tc_kernel)
+int rb_list_scan_pipe(const float* q, int D, const float* list_vecs, const int64_t* offsets, const int* pair_qp, const long long* pair_dst,
+                      const int* list_qstart, int nprobe, float* cand, long long total_candidates, const int* tile_list, const int* tile_idx,
+                      long long n_tiles, int* err_flag, cudaStream_t st) {
+    static int on = -1;
+    if (on < 0) { const char* e = getenv("RB200_IVF_PIPE"); on = e ? atoi(e) : 1; }
+    // (the unit descriptors keep candidate offsets in 32 bits)
+    if (!on || D != DD || !tile_list || !tile_idx || n_tiles <= 0 || n_tiles >= (1ll << 31) || total_candidates >= 0xFFFFFFFFll) return 1;
+    static bool attr_set = false;
+    if (!attr_set) {
+        RB_CUDA(cudaFuncSetAttribute(list_scan_pipe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PIPE_SMEM));
+        attr_set = true;
+    }
+    long long grid = rb_sm_count();
+    if (grid > n_tiles) grid = n_tiles;
+    list_scan_pipe_kernel<<<(unsigned)grid, NT_PIPE, PIPE_SMEM, st>>>(q, list_vecs, offsets, pair_qp, pair_dst, list_qstart, nprobe, cand,
+                                                                      tile_list, tile_idx, (int)n_tiles, err_flag);
+    RB_LAUNCH_CHECK("list_scan_pipe_kernel");
     return RB200_OK;
 }
