@@ -294,51 +294,53 @@ __global__ void __launch_bounds__(NT) probe_finish_kernel(const int64_t* __restr
 // One block: list_qstart = exclusive scan of the per-list probe counts (n_lists + 1 entries), cand_off = exclusive scan of the per-query
 // candidate totals (nq + 1 entries), out2 = {Σ, max} of the totals — the plan's two cub scans, a memset and a reduction in one launch.
 constexpr int PS_NT = 1024;
+// block-wide exclusive scan of n values (+ the total at index n): thread t owns a contiguous run of ceil((n+1)/PS_NT) elements — its
+// loads are independent of each other and of the block's one shuffle / shared-memory round (a chunked scan paid a dependent global
+// round trip and three barriers per 1024 elements: 15.6 us for the plan's two 4097-element scans)
+template <typename TIn, typename TOut>
+__device__ __forceinline__ long long block_excl_scan(const TIn* __restrict__ in, int n, TOut* __restrict__ out, long long* wsum /*[PS_NT/32 + 1]*/,
+                                                     long long* vmax) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int per = (n + 1 + PS_NT - 1) / PS_NT;
+    const int i0 = tid * per, i1 = min(i0 + per, n);              // inputs [i0, i1) (index n has no input: it receives the total)
+    long long local = 0, mx = 0;
+    for (int i = i0; i < i1; ++i) { const long long v = (long long)in[i]; local += v; mx = v > mx ? v : mx; }
+    long long incl = local;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const long long t = __shfl_up_sync(RB_FULL_MASK, incl, o);
+        if (lane >= o) incl += t;
+    }
+    __syncthreads();                                             // (wsum may still be read by a previous call)
+    if (lane == 31) wsum[warp] = incl;
+    __syncthreads();
+    long long before = incl - local, total = 0;
+    for (int w = 0; w < PS_NT / 32; ++w) { const long long c = wsum[w]; if (w < warp) before += c; total += c; }
+    long long run = before;
+    for (int i = i0; i < min(i0 + per, n + 1); ++i) {
+        out[i] = (TOut)run;
+        if (i < n) run += (long long)in[i];
+    }
+    if (vmax) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) { const long long om = __shfl_xor_sync(RB_FULL_MASK, mx, o); mx = om > mx ? om : mx; }
+        __syncthreads();
+        if (lane == 0) wsum[warp] = mx;
+        __syncthreads();
+        long long m = 0;
+        for (int w = 0; w < PS_NT / 32; ++w) m = wsum[w] > m ? wsum[w] : m;
+        *vmax = m;
+    }
+    return total;
+}
 __global__ void __launch_bounds__(PS_NT) plan_scans_kernel(const int* __restrict__ list_qcount, int n_lists, int* __restrict__ list_qstart,
                                                            const long long* __restrict__ totals, int nq, long long* __restrict__ cand_off,
                                                            long long* __restrict__ out2) {
     __shared__ long long wsum[PS_NT / 32];
-    __shared__ long long s_carry, s_max;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     long long vmax = 0;
-    for (int pass = 0; pass < 2; ++pass) {
-        const int n = pass == 0 ? n_lists : nq;
-        if (tid == 0) s_carry = 0;
-        __syncthreads();
-        for (int base = 0; base < n + 1; base += PS_NT) {
-            const int i = base + tid;
-            long long v = 0;
-            if (i < n) v = pass == 0 ? (long long)list_qcount[i] : totals[i];
-            if (pass == 1) vmax = v > vmax ? v : vmax;
-            long long incl = v;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const long long t = __shfl_up_sync(RB_FULL_MASK, incl, o);
-                if (lane >= o) incl += t;
-            }
-            if (lane == 31) wsum[warp] = incl;
-            __syncthreads();
-            long long before = s_carry;
-            for (int w = 0; w < warp; ++w) before += wsum[w];
-            if (i < n + 1) {
-                if (pass == 0) list_qstart[i] = (int)(before + incl - v);
-                else cand_off[i] = before + incl - v;
-            }
-            __syncthreads();
-            if (tid == PS_NT - 1) s_carry = before + incl;
-            __syncthreads();
-        }
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) { const long long om = __shfl_xor_sync(RB_FULL_MASK, vmax, o); vmax = om > vmax ? om : vmax; }
-    if (lane == 0) wsum[warp] = vmax;
-    __syncthreads();
-    if (tid == 0) {
-        long long m = 0;
-        for (int w = 0; w < PS_NT / 32; ++w) m = wsum[w] > m ? wsum[w] : m;
-        out2[0] = s_carry;          // carry of the second pass = Σ totals
-        out2[1] = m;
-    }
+    block_excl_scan<int, int>(list_qcount, n_lists, list_qstart, wsum, nullptr);
+    const long long total = block_excl_scan<long long, long long>(totals, nq, cand_off, wsum, &vmax);
+    if (threadIdx.x == 0) { out2[0] = total; out2[1] = vmax; }
 }
 
 // (list, query) pairs grouped by list without a sort: pair i of list l goes to one of the list's slots [list_qstart[l], list_qstart[l+1]),

@@ -126,17 +126,26 @@ if __name__ == "__main__":
         "(plain run first: 0.636 ms per eager step, host-bound; the graph replay of the same kernels: 0.261 ms).\n")
     # ---- IVF ----
     ivf = load(G / "r2f_launches_ivf.csv")
-    batch = last_call(ivf, "gemm_nt_tc", 0)
+    i_scan = max(i for i, n in enumerate(ivf) if "list_scan_pipe" in n[0])
+    i_beg = max(i for i, n in enumerate(ivf[:i_scan]) if "gemm_nt_tc" in n[0])
+    i_end = min(i for i, n in enumerate(ivf) if i > i_beg and "ResolveIvf" in n[0])
+    batch = [n for n in ivf[i_beg:i_end + 1] if not n[0].startswith("at::")]       # (the bench's L2 flush between plan and run left out)
     (P / "r02_ivf.md").write_text(
         "# r02 — C3 IVF search (1 M x 64, nlist 4096, nprobe 32, top-500, 4096 queries per batch)\n\n"
-        "Bench: 0.670 ms per batch device-timed (0.719 at the start of the round).  The plan's cub radix sort + two scans + reduction "
-        "(54 us in `profiles/r01_launches_ivf_v7.csv`) are now `plan_scans_kernel` + `pair_scatter_kernel`.\n\n"
+        "Bench: 0.624–0.630 ms per batch device-timed (0.719 at the start of the round).  Two changes: the plan's cub radix sort + two "
+        "scans + reduction (54 us in `profiles/r01_launches_ivf_v7.csv`) became `plan_scans_kernel` + `pair_scatter_kernel` (0.719 -> "
+        "0.672 ms), and the list scan became the persistent, warp-specialised `list_scan_pipe_kernel` (0.672 -> 0.628 ms).\n\n"
         + table(batch, "launch list of one batch (`ncu --metrics gpu__time_duration.sum --clock-control none --csv python tools/ivf_probe.py 3`)")
-        + ncu_table(G / "r2_prof_ivf.ncu-rep", "`ncu --set full` of the probe select, the list scan and the final select (per launch)")
-        + "\nReading: the database is read once (261 MB for 256 MB of rows); the scan writes 103 MB of candidate scores that the select "
-          "reads back (138 MB).  Both kernels are latency-bound (warps active 22 % / 47 %): in the list scan 27 % of the stall samples sit "
-          "at the block barrier behind the dependent loads (tile table -> offsets -> pairs -> query rows) — a persistent, prefetching form "
-          "is the next step (DESIGN.md §10).\n\n" + lines_table(G / "r2_prof_ivf.ncu-rep", "list_scan_tc", 10))
+        + ncu_table(G / "r2f_prof_ivf.ncu-rep", "`ncu --set full` of the probe select, the list scan and the final select (per launch)")
+        + "\nReading: the database is read once (262 MB for 256 MB of rows); the scan writes ~100 MB of candidate scores that the select "
+          "reads back (138 MB).  History of the scan kernel (same command): one CTA per tile (`list_scan_tc_kernel`, earlier capture "
+          "`gpurun_out/r2_prof_ivf.ncu-rep`) 271 us, warps active 22 %, 27 % of the stall samples at the block barrier behind four "
+          "dependent global round trips; persistent with a descriptor warp but serial stage -> MMA -> store per unit: 260–270 us (the "
+          "chain itself, not the loads, was the bound); warp-specialised with 8 loader warps: 260 us, the loaders 84 % busy; 16 loader "
+          "warps + hoisted operand offsets: 213 us.  Device timestamps per role (one CTA, `%globaltimer`): ~3 us per unit — the loaders "
+          "wait ~1.6 us for the vector tile requested one unit earlier, the epilogue spends ~2 us on its 32 stores per thread (256 "
+          "misaligned 128-byte stores per unit): the SM's load/store path is the bound now; a third query buffer / accumulator and an L2 "
+          "prefetch of the tiles changed nothing.\n\n" + lines_table(G / "r2f_prof_ivf.ncu-rep", "list_scan_pipe", 10))
     # ---- flat filter ----
     f4 = load(G / "r2f_launches_flat4096.csv")
     idx = [i for i, n in enumerate(f4) if "flat_filter_image" in n[0]]
