@@ -399,6 +399,7 @@ def _run(args):
     torch.manual_seed(0)
     model = R.TwoTowerModel(N_USERS, N_ITEMS, D, H, dropout=DROPOUT).to(dev).train()
     tr = R.DataParallelBPRTrainer(model, lr=1e-3, weight_decay=1e-5, max_norm=1.0, use_cuda_graph=True, allreduce="p2p")
+    dp_multimem = bool(getattr(tr, "_dp_mc", 0))
     K2 = min(K, 50)
     nb = min(K2 + W + 2, 24)
     batches, _ = synth_batches(nb, seed=100 + rank)
@@ -465,9 +466,11 @@ def _run(args):
                   "e2e": {"value": world * B * K2 / dp_e2e, "unit": "samples/s", "h2d_bytes_per_step": pinned[0].numel(), "d2h_bytes_per_step": 4},
                   "launches_per_step": int(dp_launches), "replicas_in_sync": in_sync, "final_loss": float(dp_loss),
                   "config": {"workload": f"C2 x{world}: batch 8192 PER RANK, ML-1M-shape tables replicated, dense Adam, dropout 0.1",
-                             "parallelism": f"data parallel x{world}: one all-reduce of the dense gradients per step ({ar_bytes} B) as a two-shot "
-                                            "kernel over peer memory between two cross-GPU barriers (rb200_allreduce_twoshot, torch symmetric "
-                                            "memory; no NCCL in the step), captured with both halves of the step in ONE CUDA graph"}},
+                             "parallelism": f"data parallel x{world}: one all-reduce of the dense gradients per step ({ar_bytes} B) over peer "
+                                            "memory between two cross-GPU barriers (torch symmetric memory; no NCCL in the step) — "
+                                            + ("reduced inside the NVSwitch (rb200_allreduce_multimem: multimem.ld_reduce / multimem.st)"
+                                               if dp_multimem else "two-shot kernel (rb200_allreduce_twoshot)")
+                                            + ", captured with both halves of the step in ONE CUDA graph"}},
         "c5": {"metric": "flat_top500_qps", "value": nq5 / ms5 * 1e3, "unit": "queries/s", "ms_per_batch": ms5,
                "logical_tflops_all_gpus": 2.0 * nq5 * rows5 * world * 64 / (ms5 * 1e-3) / 1e12,
                "ranks_agree": bool((lo5 == hi5).item()), "shards_in_result": shards_hit,

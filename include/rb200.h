@@ -260,6 +260,10 @@ int rb200_allreduce_oneshot(const void* const* src_ptrs, int world, int64_t n, f
  * ranks end up with bit-identical sums.  buf_ptrs: HOST array of the `world` device pointers; n floats, n % 4 == 0.  The caller puts
  * a cross-GPU barrier before (all buffers complete) and after (all slices delivered).  Replaces ncclAllReduce inside the step. */
 int rb200_allreduce_twoshot(void* const* buf_ptrs, int world, int rank, int64_t n, void* stream);
+/* The same reduction inside the NVSwitch (NVLS multicast): multicast_ptr = the multicast address of the ranks' buffers (torch symmetric
+ * memory: handle.multicast_ptr; 0 when the fabric has no multicast support — use the two-shot form then).  Rank r reduces slice r with
+ * multimem.ld_reduce and broadcasts the sum with multimem.st.  Same barriers around it. */
+int rb200_allreduce_multimem(void* multicast_ptr, int world, int rank, int64_t n, void* stream);
 /* (rb200_sharded_scalars_publish / _reduce are declared below, after rb200_opt_state) */
 
 /* ------------------------------------------------------------------------------------------ *

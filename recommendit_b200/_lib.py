@@ -110,6 +110,7 @@ SIGNATURES = {
     "rb200_push_row_lists_sharded": (I, [P, I, I, I64, P, P]),
     "rb200_allreduce_oneshot": (I, [P, I, I64, P, P]),
     "rb200_allreduce_twoshot": (I, [P, I, I, I64, P]),
+    "rb200_allreduce_multimem": (I, [P, I, I, I64, P]),
     "rb200_sharded_scalars_publish": (I, [P, P, F, P, P]),
     "rb200_sharded_scalars_reduce": (I, [P, I, P, P]),
     "rb200_sharded_scalars_finish": (I, [P, I, P, I64, P, P]),

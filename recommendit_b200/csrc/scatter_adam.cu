@@ -1338,6 +1338,32 @@ extern "C" int rb200_allreduce_oneshot(const void* const* src_ptrs, int world, i
     return RB200_OK;
 }
 
+// The same all-reduce through the NVSwitch's multicast object (NVLS): rank r reads slice r ONCE through the multicast address with the
+// reduction done inside the switch (multimem.ld_reduce) and stores the sum once through the same address, which the switch delivers to
+// every rank (multimem.st) — per rank n/W floats each way instead of (W − 1)/W · n.  One reduction per element, broadcast to all: every
+// rank holds the same bits.  Same barriers around it as the two-shot form.
+__global__ void __launch_bounds__(NT) allreduce_multimem_kernel(float* __restrict__ mc, int world, int rank, long long n4) {
+    const long long per = (n4 + world - 1) / world, beg = per * rank, end = beg + per < n4 ? beg + per : n4;
+    const long long stride = (long long)gridDim.x * NT;
+    for (long long i = beg + (long long)blockIdx.x * NT + threadIdx.x; i < end; i += stride) {
+        float4 v;
+        float* p = mc + i * 4;
+        asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0, %1, %2, %3}, [%4];"
+                     : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
+        asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};"
+                     ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+    }
+}
+
+extern "C" int rb200_allreduce_multimem(void* multicast_ptr, int world, int rank, int64_t n, void* stream) {
+    RB_REQUIRE(multicast_ptr && world >= 1 && world <= RB200_MAX_PEERS && rank >= 0 && rank < world && n >= 4 && n % 4 == 0,
+               "allreduce_multimem: n must be a multiple of 4, 1..%d ranks, a multicast address", RB200_MAX_PEERS);
+    const long long per = (n / 4 + world - 1) / world;
+    allreduce_multimem_kernel<<<stream_grid(per), NT, 0, (cudaStream_t)stream>>>((float*)multicast_ptr, world, rank, n / 4);
+    RB_LAUNCH_CHECK("allreduce_multimem_kernel");
+    return RB200_OK;
+}
+
 extern "C" int rb200_allreduce_twoshot(void* const* buf_ptrs, int world, int rank, int64_t n, void* stream) {
     RB_REQUIRE(buf_ptrs && world >= 1 && world <= RB200_MAX_PEERS && rank >= 0 && rank < world && n >= 4 && n % 4 == 0,
                "allreduce_twoshot: n must be a multiple of 4, 1..%d ranks", RB200_MAX_PEERS);

@@ -391,7 +391,7 @@ class DataParallelBPRTrainer(FusedBPRTrainer):
             self._flatten()
         n = self.lib.rb200_bpr_dp_grad_floats(self.D, self.H, self.E, model.n_users + 1, model.n_items + 1)
         # dense gradients + one trailing float for the loss (pre-scaled by 1/world on the device): ONE all-reduce per step
-        self._dp_hdl, self._dp_ptrs = None, None
+        self._dp_hdl, self._dp_ptrs, self._dp_mc = None, None, 0
         n_buf = (n + 4 + 3) // 4 * 4
         if self.world > 1 and allreduce == "p2p":
             # the buffer lives in symmetric memory (one NVLink / NVSwitch box): the all-reduce is a two-shot kernel over peer memory
@@ -401,6 +401,10 @@ class DataParallelBPRTrainer(FusedBPRTrainer):
             self._dp_buf.zero_()
             self._dp_hdl = symm_mem.rendezvous(self._dp_buf, group if group is not None else dist.group.WORLD)
             self._dp_ptrs = [int(p) for p in self._dp_hdl.buffer_ptrs]
+            # NVLS: the reduction inside the switch when the fabric offers a multicast object (RB200_DP_MULTIMEM=0: two-shot kernel)
+            import os
+            mc = int(getattr(self._dp_hdl, "multicast_ptr", 0) or 0)
+            self._dp_mc = mc if os.environ.get("RB200_DP_MULTIMEM", "1") != "0" else 0
         else:
             self._dp_buf = torch.zeros(n_buf, dtype=torch.float32, device=self.dev)
         self.dp_grads = self._dp_buf[:n]
@@ -432,8 +436,12 @@ class DataParallelBPRTrainer(FusedBPRTrainer):
         if self.world > 1:
             if self._dp_hdl is not None:
                 self._dp_hdl.barrier(channel=0, timeout_ms=60000)          # every rank's gradients are complete
-                check(self.lib.rb200_allreduce_twoshot((C.c_void_p * self.world)(*self._dp_ptrs), self.world, self.rank,
-                                                       self._dp_buf.numel(), stream_ptr()), "rb200_allreduce_twoshot")
+                if self._dp_mc:
+                    check(self.lib.rb200_allreduce_multimem(self._dp_mc, self.world, self.rank, self._dp_buf.numel(), stream_ptr()),
+                          "rb200_allreduce_multimem")
+                else:
+                    check(self.lib.rb200_allreduce_twoshot((C.c_void_p * self.world)(*self._dp_ptrs), self.world, self.rank,
+                                                           self._dp_buf.numel(), stream_ptr()), "rb200_allreduce_twoshot")
                 self._dp_hdl.barrier(channel=1, timeout_ms=60000)          # every slice has been delivered everywhere
             else:
                 self.dist.all_reduce(self._dp_buf, group=self.group)

@@ -111,6 +111,19 @@ assert dp2._graph is not None and dp2._dp_hdl is not None
 dp2_diff = max(abs(a - b) for a, b in zip(dp_losses, dp2_losses))
 dp2_param_diff = max(float((v.detach().cpu() - torch.from_numpy(dp_state[k])).abs().max()) for k, v in m2.state_dict().items())
 dp2.close()
+# … and with the in-switch reduction switched off (two-shot kernel; where the fabric has no multicast object dp2 already used it)
+import os
+os.environ["RB200_DP_MULTIMEM"] = "0"
+m3 = R.TwoTowerModel(400, 300, 64, 128, dropout=0.0)
+m3.load_state_dict({k: torch.from_numpy(v) for k, v in O.init_params(400, 300, 64, 128, seed=9).items()}); m3.to(dev).train()
+dp3 = R.DataParallelBPRTrainer(m3, lr=1e-2, use_cuda_graph=True, allreduce="p2p")
+dp3_losses = [float(dp3.step_host(*batch2(rank, s))) for s in range(4)]
+assert dp3._dp_mc == 0
+dp3_diff = max(abs(a - b) for a, b in zip(dp_losses, dp3_losses))
+dp3_param_diff = max(float((v.detach().cpu() - torch.from_numpy(dp_state[k])).abs().max()) for k, v in m3.state_dict().items())
+dp_multimem_used = bool(dp2._dp_mc)
+dp3.close()
+del os.environ["RB200_DP_MULTIMEM"]
 if rank == 0:
     S2 = O.AdamState(); dp_ref = []
     for st in range(4):
@@ -131,7 +144,8 @@ if rank == 0:
     print("RESULT " + json.dumps({"losses": losses, "ref": ref, "max_param_err": err, "dp_losses": dp_losses, "dp_ref": dp_ref,
                                   "dp_err": dp_err, "pad_diff": pad_diff, "pad_param_diff": pad_param_diff,
                                   "p2p_diff": p2p_diff, "p2p_param_diff": p2p_param_diff,
-                                  "dp2_diff": dp2_diff, "dp2_param_diff": dp2_param_diff}))
+                                  "dp2_diff": dp2_diff, "dp2_param_diff": dp2_param_diff, "dp3_diff": dp3_diff,
+                                  "dp3_param_diff": dp3_param_diff, "dp_multimem_used": dp_multimem_used}))
 dist.barrier(); dist.destroy_process_group()
 '''
 
@@ -197,6 +211,7 @@ def test_sharded_world2_nccl_matches_single_process_oracle(tmp_path):
     assert r["p2p_diff"] <= 1e-6 and r["p2p_param_diff"] <= 1e-6, r
     # peer-memory all-reduce of the data-parallel replicas vs the NCCL one (different summation orders of two addends: equal here)
     assert r["dp2_diff"] <= 1e-6 and r["dp2_param_diff"] <= 2e-5, r
+    assert r["dp3_diff"] <= 1e-6 and r["dp3_param_diff"] <= 2e-5, r          # (dp2: multimem where available, dp3: two-shot)
 
 
 @pytest.mark.parametrize("world,n_u,n_i", [(1, 100, 200), (2, 8192, 16384), (8, 5000, 10001), (3, 0, 77), (64, 300, 0)])
