@@ -61,3 +61,50 @@ def flat_search_rounds(q, x, k, prefix=PREFIX, growth=None, cap=None):
         m = len(best[i][0])
         out_s[i, :m], out_i[i, :m] = best[i]
     return out_s, out_i, overflow
+
+
+# ---------------------------------------------------------------------------------------------------------------- #
+# The one-pass FILTER of the pruned rounds (csrc/flat_filter_tc.cu, csrc/flat_stream_tc.cu), restated: operands rounded to bf16
+# (round-to-nearest-even, both rows and queries) or to tf32 (rows truncated / queries rounded), products accumulated in fp32 and a
+# score kept when  S~ + margin_q * max||x|| - thr_q > 0  with max||x|| over the rows of a CTA (256 rows) or of a tile (128 rows).
+# What the tests check on the CPU: the kept set is a SUPERSET of {S > thr} for any scale of rows and queries (no true winner can be
+# lost), and it is not much larger.
+# ---------------------------------------------------------------------------------------------------------------- #
+def _bf16_rn(a):
+    """float32 -> the nearest bfloat16 (ties to even), returned as float32"""
+    u = np.asarray(a, np.float32).view(np.uint32).astype(np.uint64)
+    r = (u + 0x7FFF + ((u >> 16) & 1)) & 0xFFFF0000
+    return r.astype(np.uint32).view(np.float32)
+
+
+def _tf32_rn(a):
+    """float32 -> tf32 by adding half an ulp to the magnitude and truncating (umma::tf32_hi)"""
+    u = np.asarray(a, np.float32).view(np.uint32).astype(np.uint64)
+    return ((u + 0x1000) & 0xFFFFE000).astype(np.uint32).view(np.float32)
+
+
+def _tf32_trunc(a):
+    """what kind::tf32 does to a raw fp32 operand: the low 13 mantissa bits are ignored"""
+    return (np.asarray(a, np.float32).view(np.uint32) & np.uint32(0xFFFFE000)).view(np.float32)
+
+
+FILTER = {                      # format -> (row rounding, query rounding, margin constant C: margin_q = C * ||q||, rows per norm block)
+    "bf16": (_bf16_rn, _bf16_rn, 1.5 / 256.0, 256),             # flat_filter_tc_kernel<true>   (more than 128 queries)
+    "tf32": (_tf32_rn, _tf32_rn, 1.5 / 1024.0, 256),            # flat_filter_tc_kernel<false>
+    "stream": (_tf32_trunc, _tf32_rn, 2.0 / 1024.0, 128),       # flat_stream_tc_kernel (raw rows by TMA, margin 2^-9, per-tile norm)
+}
+
+
+def filter_keep(q, x, thr, fmt="bf16"):
+    """-> boolean [nq, n]: the scores the filter lets through (they are re-scored in fp32 afterwards)"""
+    rx, rq, cm, blk = FILTER[fmt]
+    q, x = np.asarray(q, np.float32), np.asarray(x, np.float32)
+    s_approx = (rq(q).astype(np.float32) @ rx(x).astype(np.float32).T).astype(np.float32)
+    qn = np.linalg.norm(q.astype(np.float64), axis=1) * 1.0001
+    xn = np.linalg.norm(x.astype(np.float64), axis=1) * 1.0001
+    n = x.shape[0]
+    nmax = np.empty(n)
+    for b in range(0, n, blk):
+        nmax[b:b + blk] = xn[b:b + blk].max()
+    margin = (cm * qn)[:, None] * nmax[None, :]
+    return s_approx.astype(np.float64) + margin - np.asarray(thr, np.float64)[:, None] > 0.0

@@ -1,5 +1,6 @@
 """The threshold-pruned round algorithm of rb200_flat_search, restated on the CPU, against the plain exhaustive search — CPU."""
 import numpy as np
+import pytest
 
 from oracle import flat_rounds_oracle as FR
 from oracle import ivf_oracle as V
@@ -67,3 +68,30 @@ def test_expected_survivors_per_round_are_about_growth_minus_one_times_k():
     thr = -np.sort(-s[:, :seen], axis=1)[:, k - 1]
     surv = (s[:, seen:] > thr[:, None]).sum(1)
     assert 2.0 * k < surv.mean() < 4.0 * k
+
+
+@pytest.mark.parametrize("fmt", ["bf16", "tf32", "stream"])
+@pytest.mark.parametrize("scale", ["unit", "wild"])
+def test_filter_margin_never_loses_a_row_that_beats_the_threshold(fmt, scale):
+    """The one-pass filters of the pruned rounds (bf16 / tf32 products + a margin in units of ||q||·max||x||): every score above its
+    query's threshold in fp32 arithmetic passes the filter, whatever the scale of rows and queries, and the filter lets through only
+    a little more than that (the survivors are re-scored in fp32, so extra ones cost time, not correctness)."""
+    rng = np.random.default_rng({"bf16": 1, "tf32": 2, "stream": 3}[fmt])
+    n, nq, d, k = 6000, 24, 64, 100
+    x = V.normalize_rows(rng.standard_normal((n, d)).astype(np.float32))
+    q = V.normalize_rows(rng.standard_normal((nq, d)).astype(np.float32))
+    if scale == "wild":
+        x = (x * np.exp(rng.uniform(np.log(0.05), np.log(20.0), (n, 1)))).astype(np.float32)
+        q = (q * np.exp(rng.uniform(np.log(0.1), np.log(8.0), (nq, 1)))).astype(np.float32)
+    s = (q.astype(np.float64) @ x.astype(np.float64).T)
+    s32 = (q @ x.T).astype(np.float32)
+    thr = -np.sort(-s32, axis=1)[:, k - 1]                       # each query's k-th best score: the hardest threshold to keep exact
+    keep = FR.filter_keep(q, x, thr, fmt)
+    must = s32 > thr[:, None]
+    assert not (must & ~keep).any()                              # no winner lost
+    # scores a whole margin below the threshold never pass (the filter is a filter)
+    _, _, cm, _ = FR.FILTER[fmt]
+    bound = 2.6 * cm * np.linalg.norm(q, axis=1)[:, None] * np.linalg.norm(x, axis=1).max()
+    assert not (keep & (s < thr[:, None] - bound)).any()
+    if scale == "unit":
+        assert keep.sum() <= must.sum() + nq * (40 if fmt == "bf16" else 12)      # a few per cent of k extra per query
