@@ -408,7 +408,7 @@ def bench_ivf(args, dev):
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
         _lib.check(lib.rb200_ivf_search_run(q.data_ptr(), nq, d, nlist, nprobe, st.offsets.data_ptr(), st.list_ids.data_ptr(),
-                                            st.list_vecs.data_ptr(), st.max_list_len, st.tile_list.data_ptr(), st.tile_idx.data_ptr(),
+                                            st.list_vecs.data_ptr(), st.list_vecs.shape[0], st.max_list_len, st.tile_list.data_ptr(), st.tile_idx.data_ptr(),
                                             st.tile_list.numel(), k, plan.data_ptr(), pb, tot.value, mx.value,
                                             so.data_ptr(), io.data_ptr(), ws.data_ptr(), ws.numel(), _lib.stream_ptr()))
         b.record(); torch.cuda.synchronize(dev)

@@ -435,9 +435,10 @@ int rb200_ivf_search_plan(const float* q, int nq, int D, const float* centroids,
                           int64_t* total_candidates_host, int64_t* max_candidates_host, void* stream);
 size_t rb200_ivf_search_workspace_bytes(int64_t total_candidates);
 /* tile_list / tile_idx (optional, int32 [n_tiles]): the index's table of (list, 64-vector tile) work items — one CTA per
- * non-empty tile instead of a (max tiles) × nlist grid full of empty CTAs.  It depends only on `offsets`; build it once. */
+ * non-empty tile instead of a (max tiles) × nlist grid full of empty CTAs.  It depends only on `offsets`; build it once.
+ * n_vectors: rows of list_vecs (= offsets[nlist]; the D = 64 scan fetches vector tiles with a tensor map over [n_vectors, D]). */
 int rb200_ivf_search_run(const float* q, int nq, int D, int nlist, int nprobe, const int64_t* offsets,
-                         const int64_t* list_ids, const float* list_vecs, int64_t max_list_len,
+                         const int64_t* list_ids, const float* list_vecs, int64_t n_vectors, int64_t max_list_len,
                          const int32_t* tile_list, const int32_t* tile_idx, int n_tiles, int k,
                          void* plan_ws, size_t plan_ws_bytes, int64_t total_candidates,
                          int64_t max_candidates, float* out_scores, int64_t* out_ids, void* workspace,

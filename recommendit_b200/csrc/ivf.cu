@@ -20,7 +20,7 @@
 #include "common.cuh"
 
 // tcgen05 score product (gemm_tc.cu): C[M,N] = A[M,K]·B[N,K]ᵀ, mode 2 = 3xTF32 (fp32-grade)
-int rb_list_scan_pipe(const float* q, int D, const float* list_vecs, const int64_t* offsets, const int* pair_qp, const long long* pair_dst,
+int rb_list_scan_pipe(const float* q, int D, const float* list_vecs, long long n_vectors, const int64_t* offsets, const int* pair_qp, const long long* pair_dst,
                       const int* list_qstart, int nprobe, float* cand, long long total_candidates, const int* tile_list, const int* tile_idx,
                       long long n_tiles, int* err_flag, cudaStream_t st);
 int rb_list_scan_tc(const float* q, int D, const float* list_vecs, const int64_t* offsets, const int* pair_qp, const int* list_qstart,
@@ -944,13 +944,13 @@ extern "C" size_t rb200_ivf_search_workspace_bytes(int64_t total_candidates) {
 }
 
 extern "C" int rb200_ivf_search_run(const float* q, int nq, int D, int nlist, int nprobe, const int64_t* offsets,
-                                    const int64_t* list_ids, const float* list_vecs, int64_t max_list_len,
+                                    const int64_t* list_ids, const float* list_vecs, int64_t n_vectors, int64_t max_list_len,
                                     const int32_t* tile_list, const int32_t* tile_idx, int n_tiles, int k,
                                     void* plan_ws, size_t plan_ws_bytes, int64_t total_candidates, int64_t max_candidates,
                                     float* out_scores, int64_t* out_ids, void* workspace, size_t workspace_bytes,
                                     void* stream) {
     RB_REQUIRE(q && offsets && list_ids && list_vecs && out_scores && out_ids, "ivf_search_run: NULL pointer");
-    RB_REQUIRE(nq >= 1 && k >= 1 && k <= 2048 && nprobe >= 1 && max_list_len >= 0, "ivf_search_run: bad sizes (k must be 1..2048)");
+    RB_REQUIRE(nq >= 1 && k >= 1 && k <= 2048 && nprobe >= 1 && max_list_len >= 0 && n_vectors >= 0, "ivf_search_run: bad sizes (k must be 1..2048)");
     cudaStream_t st = (cudaStream_t)stream;
     RbArena pa(plan_ws, plan_ws_bytes);
     PlanLayout L;
@@ -960,7 +960,7 @@ extern "C" int rb200_ivf_search_run(const float* q, int nq, int D, int nlist, in
     if (!workspace || !ar.ok()) return rb_set_error(RB200_ERR_WORKSPACE, "ivf_search_run: workspace too small");
     if (total_candidates > 0 && max_list_len > 0) {
         // D = 64 with a tile table: the persistent, prefetching tcgen05 kernel (ivf_scan_tc.cu); RB200_IVF_PIPE=0: one CTA per tile
-        int tc = rb_list_scan_pipe(q, D, list_vecs, offsets, L.pair_qp, L.pair_dst, L.list_qstart, nprobe, cand, total_candidates, tile_list,
+        int tc = rb_list_scan_pipe(q, D, list_vecs, n_vectors, offsets, L.pair_qp, L.pair_dst, L.list_qstart, nprobe, cand, total_candidates, tile_list,
                                    tile_idx, n_tiles, L.tc_err, st);
         if (tc > 0)                 // (otherwise the FFMA tile kernel below)
             tc = rb_list_scan_tc(q, D, list_vecs, offsets, L.pair_qp, L.list_qstart, nprobe, L.cand_base, L.cand_off, cand,

@@ -5,6 +5,7 @@
 // the radix-sorted (list, query) pairs — are gathered in chunks of 64 as the B operand; S[128 vectors × 64 queries] is
 // accumulated in TMEM by tcgen05.mma and written to the compact candidate buffer (for a fixed query, the 32 lanes of a
 // warp hold 32 consecutive vectors → 128-byte stores).  D = 64.  96 KB of shared memory → 2 CTAs per SM.
+#include <cuda.h>
 #include <stdlib.h>
 
 #include "common.cuh"
@@ -181,17 +182,23 @@ struct UnitDesc {
     int qrow[QT];              // per query of the chunk: its row in q (−1: none)
 };
 constexpr unsigned NO_DST = 0xFFFFFFFFu;
-constexpr int NQB = 3, NACC = 3;                            // query-chunk buffers and accumulators: with two of each the hand-off loop
-                                                            // stage → MMA → free (≈ 3 us) bounded the kernel at 1.6 us per unit
+constexpr int NQB = 2, NACC = 3;                            // query-chunk buffers and accumulators
+constexpr int RAW_BYTES = VT * DD * 4;                      // a vector tile as it arrives by TMA: two 128-byte-swizzled [128 × 32] atoms
 constexpr int RING = 4, N_LOAD = 16, N_EPI = 8;            // (eight loader warps were busy 84 % of the time: staging bounded the kernel)
 constexpr int VPT = 64 / N_LOAD, QPT = 32 / N_LOAD;        // 16-byte pieces of the vector tile / the query chunk per loader thread
 constexpr int W_MMA = N_LOAD + N_EPI, W_DESC = W_MMA + 1, NT_PIPE = (W_DESC + 1) * 32;
-constexpr int N_BARS = 2 * RING + 2 * NQB + 2 + 2 * NACC;
+constexpr int N_BARS = 2 * RING + 2 * NQB + 2 + 2 * NACC + 2;
 // 224 KB of operands + the descriptor ring + the barriers: everything in the dynamic block (a static block next to a 1024-byte aligned
 // dynamic one is padded to 1 KB, which would not fit the 227 KB any more)
-constexpr size_t PIPE_SMEM = 2 * (2 * V_BYTES) + NQB * (2 * Q_BYTES) + RING * sizeof(UnitDesc) + N_BARS * 8 + 16;
+constexpr size_t PIPE_SMEM = 2 * (2 * V_BYTES) + NQB * (2 * Q_BYTES) + RAW_BYTES + RING * sizeof(UnitDesc) + N_BARS * 8 + 16;
 
-__global__ void __launch_bounds__(NT_PIPE, 1) list_scan_pipe_kernel(const float* __restrict__ q, const float* __restrict__ list_vecs,
+__device__ __forceinline__ void tma_rows_2d(void* dst_smem, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                 ::"r"(umma::smem_u32(dst_smem)), "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(umma::smem_u32(bar))
+                 : "memory");
+}
+
+__global__ void __launch_bounds__(NT_PIPE, 1) list_scan_pipe_kernel(const __grid_constant__ CUtensorMap vmap, const float* __restrict__ q,
                                                                     const int64_t* __restrict__ offsets, const int* __restrict__ pair_qp,
                                                                     const long long* __restrict__ pair_dst,
                                                                     const int* __restrict__ list_qstart, int nprobe, float* __restrict__ cand,
@@ -200,7 +207,8 @@ __global__ void __launch_bounds__(NT_PIPE, 1) list_scan_pipe_kernel(const float*
     extern __shared__ __align__(1024) unsigned char smem[];
     unsigned char* vbuf = smem;                                  // [2][hi V_BYTES | lo V_BYTES]
     unsigned char* qbuf = smem + 4 * V_BYTES;                    // [NQB][hi Q_BYTES | lo Q_BYTES]
-    UnitDesc* ring = reinterpret_cast<UnitDesc*>(qbuf + NQB * 2 * Q_BYTES);
+    unsigned char* raw = qbuf + NQB * 2 * Q_BYTES;               // [2 atoms][128 rows × 128 B], SWIZZLE_128B (1024-byte aligned)
+    UnitDesc* ring = reinterpret_cast<UnitDesc*>(raw + RAW_BYTES);
     uint64_t* bar_full = reinterpret_cast<uint64_t*>(ring + RING);
     uint64_t* bar_empty = bar_full + RING;
     uint64_t* bar_sfull = bar_empty + RING;
@@ -208,7 +216,9 @@ __global__ void __launch_bounds__(NT_PIPE, 1) list_scan_pipe_kernel(const float*
     uint64_t* bar_vfree = bar_qfree + NQB;
     uint64_t* bar_done = bar_vfree + 2;
     uint64_t* bar_free = bar_done + NACC;
-    uint32_t* tmem_slot_p = reinterpret_cast<uint32_t*>(bar_free + NACC);
+    uint64_t* bar_rawfull = bar_free + NACC;
+    uint64_t* bar_rawfree = bar_rawfull + 1;
+    uint32_t* tmem_slot_p = reinterpret_cast<uint32_t*>(bar_rawfree + 1);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     if (warp == 0) umma::tmem_alloc(tmem_slot_p, 4 * QT);
     if (tid == 32) {
@@ -216,6 +226,7 @@ __global__ void __launch_bounds__(NT_PIPE, 1) list_scan_pipe_kernel(const float*
         for (int i = 0; i < NQB; ++i) { umma::mbar_init(&bar_sfull[i], N_LOAD); umma::mbar_init(&bar_qfree[i], 1); }
         for (int i = 0; i < NACC; ++i) { umma::mbar_init(&bar_done[i], 1); umma::mbar_init(&bar_free[i], N_EPI); }
         for (int i = 0; i < 2; ++i) umma::mbar_init(&bar_vfree[i], 1);
+        umma::mbar_init(bar_rawfull, 1); umma::mbar_init(bar_rawfree, N_LOAD);
         umma::fence_mbar_init();
     }
     umma::fence_before_sync();
@@ -227,7 +238,7 @@ __global__ void __launch_bounds__(NT_PIPE, 1) list_scan_pipe_kernel(const float*
     if (warp == W_DESC) {
         // ================================ descriptor warp ================================ //
         const int G = (int)gridDim.x;
-        int slot = 0, uses = 0;                                  // uses: descriptors written so far (slot = uses % RING)
+        int slot = 0, uses = 0, n_tma = 0;                       // uses: descriptors written so far (slot = uses % RING); tiles requested
         auto publish = [&](bool okk) -> bool {                   // wait until the slot is free (its previous unit has been consumed)
             if (uses >= RING && okk) okk = umma::mbar_wait(&bar_empty[slot], ((uses / RING) - 1) & 1);
             return okk;
@@ -265,18 +276,26 @@ __global__ void __launch_bounds__(NT_PIPE, 1) list_scan_pipe_kernel(const float*
                         u.qrow[h * 32 + lane] = qp[h] >= 0 ? qp[h] / nprobe : -1;
                         u.dst[h * 32 + lane] = qp[h] >= 0 ? (unsigned)(pd[h] + (v0 - lb0)) : NO_DST;
                     }
-                    if (p0 == qs0) {
-                        // the tile's rows on their way into L2 (this warp runs ≈ 3 units ahead of the loaders' reads: the database is
-                        // read once per batch, so every tile is an HBM miss otherwise — the loaders' first use of a row was 28 % of the
-                        // kernel's stall samples)
-                        const char* vp = reinterpret_cast<const char*>(list_vecs + v0 * DD);
-                        const int n_lines = nv * DD * 4 / 128;
-                        for (int ln = lane; ln < n_lines; ln += 32) asm volatile("prefetch.global.L2 [%0];" ::"l"(vp + (size_t)ln * 128));
-                    }
                     if (lane == 0) { u.v0 = v0; u.nv = nv; u.new_tile = p0 == qs0; u.last = p0 + QT >= qe0; u.valid = 1; }
                     __syncwarp();
                     if (lane == 0) { __threadfence_block(); umma::mbar_arrive(&bar_full[slot]); }
                     ++uses; slot = uses % RING;
+                    if (p0 == qs0) {
+                        // The tile's rows by tensor-map TMA into the raw buffer (off the SM's load/store path, where the loaders' 16-byte
+                        // gathers queued behind the epilogue's stores), as soon as the loaders have taken the previous tile out of it —
+                        // AFTER the descriptor is out: the loaders look one descriptor ahead before they stage (and free the raw
+                        // buffer of) the current unit, so waiting here first would dead-lock.  Rows past the tile belong to the next
+                        // list (or are zero-filled past the table): their scores are not stored.
+                        if (n_tma >= 1 && ok) ok = umma::mbar_wait(bar_rawfree, (n_tma - 1) & 1);
+                        if (!ok) break;
+                        if (umma::elect_one()) {
+                            umma::mbar_expect_tx(bar_rawfull, RAW_BYTES);
+                            tma_rows_2d(raw, &vmap, 0, (int)v0, bar_rawfull);
+                            tma_rows_2d(raw + RAW_BYTES / 2, &vmap, 32, (int)v0, bar_rawfull);
+                        }
+                        __syncwarp();
+                        ++n_tma;
+                    }
                 }
             }
             ti0 = ti1; l0 = l1; lb0 = lb1; le0 = le1; qs0 = qs1; qe0 = qe1;
@@ -288,15 +307,17 @@ __global__ void __launch_bounds__(NT_PIPE, 1) list_scan_pipe_kernel(const float*
     } else if (warp < N_LOAD) {
         // ================================ loader warps ================================ //
         const int r8 = lane & 7, c4l = lane >> 3;
-        float4 qvA[QPT], vvA[VPT], qvB[QPT], vvB[VPT];
-        // this thread's pieces: (row, 16-byte column) of the tile and their K-major shared-memory offsets, fixed for the whole kernel
-        int vrow[VPT], vc4[VPT], qrow_i[QPT], qc4[QPT];
-        uint32_t voff[VPT], qoff[QPT];
+        float4 qvA[QPT], qvB[QPT];
+        // this thread's pieces: (row, 16-byte column) of the tile, where they sit in the swizzled raw tile and their K-major
+        // shared-memory offsets in the operand buffers — fixed for the whole kernel
+        int qrow_i[QPT], qc4[QPT];
+        uint32_t voff[VPT], roff[VPT], qoff[QPT];
 #pragma unroll
         for (int i = 0; i < VPT; ++i) {
             const int uu = warp * VPT + i;
-            vrow[i] = (uu >> 2) * 8 + r8; vc4[i] = (uu & 3) * 4 + c4l;
-            voff[i] = umma::kmajor_offset(VT, vrow[i], vc4[i] * 4);
+            const int vrow = (uu >> 2) * 8 + r8, vc4 = (uu & 3) * 4 + c4l;
+            voff[i] = umma::kmajor_offset(VT, vrow, vc4 * 4);
+            roff[i] = (uint32_t)((vc4 >> 3) * (RAW_BYTES / 2) + vrow * 128 + (((vc4 & 7) ^ (vrow & 7)) << 4));
         }
 #pragma unroll
         for (int i = 0; i < QPT; ++i) {
@@ -304,12 +325,7 @@ __global__ void __launch_bounds__(NT_PIPE, 1) list_scan_pipe_kernel(const float*
             qrow_i[i] = (uu >> 2) * 8 + r8; qc4[i] = (uu & 3) * 4 + c4l;
             qoff[i] = umma::kmajor_offset(QT, qrow_i[i], qc4[i] * 4);
         }
-        auto load_unit = [&](const UnitDesc& u, float4 (&qv)[QPT], float4 (&vv)[VPT]) {
-            if (u.new_tile) {
-#pragma unroll
-                for (int i = 0; i < VPT; ++i)
-                    vv[i] = vrow[i] < u.nv ? __ldg(reinterpret_cast<const float4*>(list_vecs + (u.v0 + vrow[i]) * DD) + vc4[i]) : make_float4(0.f, 0.f, 0.f, 0.f);
-            }
+        auto load_unit = [&](const UnitDesc& u, float4 (&qv)[QPT]) {
 #pragma unroll
             for (int i = 0; i < QPT; ++i) {
                 const int qr = u.qrow[qrow_i[i]];
@@ -324,7 +340,7 @@ __global__ void __launch_bounds__(NT_PIPE, 1) list_scan_pipe_kernel(const float*
         };
         int n_tile = -1;                                         // tiles started so far − 1: the vector buffer of the current tile is n_tile & 1
         // unit u: descriptor in ring[u % RING]; stage it from the given register set
-        auto stage_unit = [&](int u, const float4 (&qv)[QPT], const float4 (&vv)[VPT]) {
+        auto stage_unit = [&](int u, const float4 (&qv)[QPT]) {
             const UnitDesc& d = ring[u % RING];
             const int qb = u % NQB;
             if (d.new_tile) {
@@ -332,8 +348,11 @@ __global__ void __launch_bounds__(NT_PIPE, 1) list_scan_pipe_kernel(const float*
                 const int vb = n_tile & 1;
                 if (n_tile >= 2 && ok) ok = umma::mbar_wait(&bar_vfree[vb], ((n_tile >> 1) - 1) & 1);
                 unsigned char* vh = vbuf + vb * 2 * V_BYTES;
+                if (ok) ok = umma::mbar_wait(bar_rawfull, n_tile & 1);          // the tile has landed
 #pragma unroll
-                for (int i = 0; i < VPT; ++i) put(vh, vh + V_BYTES, voff[i], vv[i]);
+                for (int i = 0; i < VPT; ++i) put(vh, vh + V_BYTES, voff[i], *reinterpret_cast<const float4*>(raw + roff[i]));
+                __syncwarp();
+                if (lane == 0) umma::mbar_arrive(bar_rawfree);                  // this warp has taken its pieces out of the raw tile
             }
             if (u >= NQB && ok) ok = umma::mbar_wait(&bar_qfree[qb], ((u / NQB) - 1) & 1);
             unsigned char* qh = qbuf + qb * 2 * Q_BYTES;
@@ -349,15 +368,15 @@ __global__ void __launch_bounds__(NT_PIPE, 1) list_scan_pipe_kernel(const float*
         };
         // two register sets: the loads of unit u+1 are in flight while unit u is staged
         bool vA = desc_ready(0), vB = false;
-        if (vA) load_unit(ring[0], qvA, vvA);
+        if (vA) load_unit(ring[0], qvA);
         for (int u = 0; vA; u += 2) {
             vB = desc_ready(u + 1);
-            if (vB) load_unit(ring[(u + 1) % RING], qvB, vvB);
-            stage_unit(u, qvA, vvA);
+            if (vB) load_unit(ring[(u + 1) % RING], qvB);
+            stage_unit(u, qvA);
             if (!vB) break;
             vA = desc_ready(u + 2);
-            if (vA) load_unit(ring[(u + 2) % RING], qvA, vvA);
-            stage_unit(u + 1, qvB, vvB);
+            if (vA) load_unit(ring[(u + 2) % RING], qvA);
+            stage_unit(u + 1, qvB);
         }
         if (!ok && lane == 0 && err_flag) atomicOr(err_flag, 8);
     } else if (warp == W_MMA) {
@@ -451,14 +470,40 @@ int rb_list_scan_tc(const float* q, int D, const float* list_vecs, const int64_t
     return RB200_OK;
 }
 
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_tiled_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess && qres == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)p;
+    }
+    return fn;
+}
+
 // returns 1 when this kernel does not cover the shape or is switched off (RB200_IVF_PIPE=0: one CTA per tile, list_scan_tc_kernel)
-int rb_list_scan_pipe(const float* q, int D, const float* list_vecs, const int64_t* offsets, const int* pair_qp, const long long* pair_dst,
+int rb_list_scan_pipe(const float* q, int D, const float* list_vecs, long long n_vectors, const int64_t* offsets, const int* pair_qp, const long long* pair_dst,
                       const int* list_qstart, int nprobe, float* cand, long long total_candidates, const int* tile_list, const int* tile_idx,
                       long long n_tiles, int* err_flag, cudaStream_t st) {
     static int on = -1;
     if (on < 0) { const char* e = getenv("RB200_IVF_PIPE"); on = e ? atoi(e) : 1; }
     // (the unit descriptors keep candidate offsets in 32 bits)
     if (!on || D != DD || !tile_list || !tile_idx || n_tiles <= 0 || n_tiles >= (1ll << 31) || total_candidates >= 0xFFFFFFFFll) return 1;
+    if (n_vectors < 1 || n_vectors >= (1ll << 31) || (reinterpret_cast<uintptr_t>(list_vecs) & 15)) return 1;
+    EncodeTiledFn enc = encode_tiled_fn();
+    if (!enc) return 1;
+    CUtensorMap vmap;
+    {
+        const cuuint64_t dims[2] = {(cuuint64_t)DD, (cuuint64_t)n_vectors};
+        const cuuint64_t strides[1] = {(cuuint64_t)DD * 4};
+        const cuuint32_t box[2] = {32, (cuuint32_t)VT};
+        const cuuint32_t estr[2] = {1, 1};
+        const CUresult r = enc(&vmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)list_vecs, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                               CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        RB_REQUIRE(r == CUDA_SUCCESS, "list_scan_pipe: cuTensorMapEncodeTiled failed (%d)", (int)r);
+    }
     static bool attr_set = false;
     if (!attr_set) {
         RB_CUDA(cudaFuncSetAttribute(list_scan_pipe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PIPE_SMEM));
@@ -466,7 +511,7 @@ int rb_list_scan_pipe(const float* q, int D, const float* list_vecs, const int64
     }
     long long grid = rb_sm_count();
     if (grid > n_tiles) grid = n_tiles;
-    list_scan_pipe_kernel<<<(unsigned)grid, NT_PIPE, PIPE_SMEM, st>>>(q, list_vecs, offsets, pair_qp, pair_dst, list_qstart, nprobe, cand,
+    list_scan_pipe_kernel<<<(unsigned)grid, NT_PIPE, PIPE_SMEM, st>>>(vmap, q, offsets, pair_qp, pair_dst, list_qstart, nprobe, cand,
                                                                       tile_list, tile_idx, (int)n_tiles, err_flag);
     RB_LAUNCH_CHECK("list_scan_pipe_kernel");
     return RB200_OK;

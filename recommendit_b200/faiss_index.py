@@ -155,7 +155,7 @@ class _IVFState:
         scores = torch.empty(nq, k, dtype=torch.float32, device=q.device)
         rows = torch.empty(nq, k, dtype=torch.int64, device=q.device)
         check(lib.rb200_ivf_search_run(ptr(q), nq, self.d, self.nlist, nprobe, ptr(self.offsets), ptr(ids_src),
-                                       ptr(self.list_vecs), self.max_list_len, ptr(self.tile_list), ptr(self.tile_idx),
+                                       ptr(self.list_vecs), self.list_vecs.shape[0], self.max_list_len, ptr(self.tile_list), ptr(self.tile_idx),
                                        self.tile_list.numel(), k, ptr(plan), pb, total.value, mx.value,
                                        ptr(scores), ptr(rows), ptr(ws), wb, stream_ptr()), "rb200_ivf_search_run")
         return scores, rows

@@ -73,7 +73,7 @@ class UserRecommender:
         check(self.lib.rb200_ivf_search_plan(ptr(self._q), 1, st.d, ptr(st.centroids), st.nlist, self.nprobe, ptr(st.offsets),
                                              ptr(self._plan), self._plan_bytes, None, None, stream_ptr()), "rb200_ivf_search_plan")
         check(self.lib.rb200_ivf_search_run(ptr(self._q), 1, st.d, st.nlist, self.nprobe, ptr(st.offsets), ptr(self.index._list_item_ids),
-                                            ptr(st.list_vecs), st.max_list_len, ptr(st.tile_list), ptr(st.tile_idx),
+                                            ptr(st.list_vecs), st.list_vecs.shape[0], st.max_list_len, ptr(st.tile_list), ptr(st.tile_idx),
                                             st.tile_list.numel(), self.k, ptr(self._plan), self._plan_bytes, self._max_cand,
                                             self._max_cand, ptr(self._scores), ptr(self._ids), ptr(self._ws), self._ws_bytes,
                                             stream_ptr()), "rb200_ivf_search_run")
