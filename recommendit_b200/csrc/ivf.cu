@@ -480,12 +480,18 @@ template <> __device__ long long resolve_id<ResolveSurv>(const ResolveSurv& r, i
 
 constexpr int SORT_CAP = 2048;   // winners + boundary bucket must fit the in-CTA sort (falls back to radix select otherwise)
 constexpr int NBK = 1024;        // value-range buckets of the fast path (fine enough that top-500 + boundary bucket ≤ 512 usually)
+constexpr int RANK_MAX = 512;    // fullest bucket for which the winners are ordered by in-bucket ranks instead of the bitonic sort
 
 // Per-query top-k (one CTA per query).
-//   fast path : value-range bucket select — min/max of the scores, 256 linear buckets over [min, max] (well spread even
-//               though cosine scores share their leading float bits), locate the bucket b* that holds the k-th score,
-//               compact every candidate in buckets ≥ b* (winners + boundary bucket), bitonic-sort that small set by
-//               (score desc, candidate position asc) and emit the first k.
+//   fast path : value-range bucket select — min/max of the scores, NBK linear buckets over [min, max] (well spread even
+//               though cosine scores share their leading float bits), locate the bucket b* that holds the k-th score.
+//               The buckets are already an order: the histogram becomes, in place, each bucket's first output position
+//               (suffix sums from the top), every candidate in buckets ≥ b* takes a slot inside its bucket's range, and its
+//               exact place is its rank by (score desc, candidate position asc) among the few entries of the same bucket —
+//               written straight to the output when < k.  No sort: the 45-step bitonic network over 512 (key, position)
+//               pairs was ≈ 40 % of this kernel's instructions and the separate counting pass another ≈ 8 %.
+//               (A bucket with more than RANK_MAX entries — heavily duplicated scores — takes the older form: compact
+//               winners + boundary bucket, bitonic-sort that set, emit the first k.)
 //   fallback  : exact MSB-first radix select (many equal scores / boundary bucket too large).
 // Bitonic sort of NT·EPT entries, descending by (key, then ascending position): EPT consecutive entries per thread as 64-bit
 // composites (key, inverted position) in registers; strides < EPT are register swaps, strides < 32·EPT warp shuffles, only the
@@ -553,7 +559,7 @@ __global__ void __launch_bounds__(NT) select_topk_kernel(const float* __restrict
     __shared__ int hist_f[NBK];           // fast path: NBK linear buckets over [min, max]
     __shared__ int wsum[2][NT / 32];
     __shared__ uint32_t s_prefix;
-    __shared__ int s_a, s_b, s_count;
+    __shared__ int s_a, s_b, s_c, s_count;
     const int q = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const float* src = cand + (cand_off ? cand_off[q] : (long long)q * fixed_stride);
     const int n = counts ? (int)counts[q] : fixed_count;
@@ -576,8 +582,10 @@ __global__ void __launch_bounds__(NT) select_topk_kernel(const float* __restrict
         src = cache;
         have_range = true;
     }
+    res.stage(q, aux, tid, NT);      // resolver copies its per-query tables into shared memory (no dependent global chains); every
+                                     // path below passes a block barrier before it resolves ids
     int m = 0;                       // number of entries placed in skey/sidx
-    bool done = false;
+    bool done = false, emitted = false;
     if (n <= SORT_CAP && n <= 2 * k) {
         // small input: sort everything
         for (int i = tid; i < n; i += NT) { skey[i] = f2key(src[i]); sidx[i] = i; }
@@ -603,37 +611,68 @@ __global__ void __launch_bounds__(NT) select_topk_kernel(const float* __restrict
             atomicAdd(&hist_f[b], 1);
         }
         __syncthreads();
+        constexpr int PB = NBK / NT;
+        int part = 0, suf = 0, any_big = 0;
         {
             // boundary bucket b* = largest b with count(bucket ≥ b) ≥ k, found with a block-wide suffix sum
-            constexpr int PB = NBK / NT;
-            int part = 0;
+            int hmax = 0;
 #pragma unroll
-            for (int c = 0; c < PB; ++c) part += hist_f[tid * PB + c];
-            int suf = part;                              // Σ over lanes ≥ lane (within the warp)
+            for (int c = 0; c < PB; ++c) { const int h = hist_f[tid * PB + c]; part += h; hmax = max(hmax, h); }
+            suf = part;                                  // Σ over lanes ≥ lane (within the warp)
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) {
                 const int t = __shfl_down_sync(RB_FULL_MASK, suf, o);
                 if (lane + o < 32) suf += t;
             }
             if (lane == 0) wsum[0][warp] = suf;
-            __syncthreads();
+            any_big = __syncthreads_or(hmax > RANK_MAX);
             for (int w = warp + 1; w < NT / 32; ++w) suf += wsum[0][w];
             if (suf >= k && suf - part < k) {            // the boundary lies inside this thread's PB buckets
                 int cum = suf - part, b = tid * PB + PB - 1;
                 for (; b > tid * PB; --b) { if (cum + hist_f[b] >= k) break; cum += hist_f[b]; }
-                s_a = b; s_b = cum + hist_f[b];
+                s_a = b; s_b = cum + hist_f[b]; s_c = hist_f[b];
             }
         }
         __syncthreads();
         const int bstar = s_a, m_fast = s_b;
-        if (m_fast <= SORT_CAP && scale > 0.f) {
+        auto bucket_of = [&](float v) { return min(NBK - 1, (int)((v - lo) * scale)); };
+        if (m_fast <= SORT_CAP && scale > 0.f && !any_big) {
+            // hist_f[b] := entries in buckets > b = first output position of bucket b (each thread converts the PB buckets it summed;
+            // nobody reads the counts any more).  The scatter's atomicAdd then hands out the slots of the bucket's range and leaves
+            // hist_f[b] at the range's end, which is the beginning of bucket b − 1's.
+            int excl = suf - part;
+#pragma unroll
+            for (int c = PB - 1; c >= 0; --c) { const int h = hist_f[tid * PB + c]; hist_f[tid * PB + c] = excl; excl += h; }
+            __syncthreads();
+            for (int i = tid; i < n; i += NT) {
+                const float v = src[i];
+                const int b = bucket_of(v);
+                if (b >= bstar) { const int slot = atomicAdd(&hist_f[b], 1); skey[slot] = f2key(v); sidx[slot] = i; }
+            }
+            __syncthreads();
+            for (int j = tid; j < m_fast; j += NT) {
+                const uint32_t kj = skey[j]; const int ij = sidx[j];
+                const int b = bucket_of(key2f(kj));
+                const int beg = b == NBK - 1 ? 0 : hist_f[b + 1], end = hist_f[b];
+                int pos = beg;
+                for (int t = beg; t < end; ++t) {
+                    const uint32_t kt = skey[t]; const int it = sidx[t];
+                    pos += (kt > kj || (kt == kj && it < ij)) ? 1 : 0;
+                }
+                if (pos < k) {                           // (the boundary bucket's tail falls off the end)
+                    out_scores[(long long)q * k + pos] = key2f(kj);
+                    out_ids[(long long)q * k + pos] = resolve_id<R>(res, q, ij);
+                }
+            }
+            done = true; emitted = true;
+        } else if (m_fast <= SORT_CAP && scale > 0.f) {
             // compaction without a per-iteration atomic (measured: the ballot + atomicAdd loop was 29 % of the kernel): every
             // thread counts its own survivors, one block-wide exclusive scan places them, a second pass writes them.  The
             // order of the survivors is irrelevant (they are sorted by (score, position) below).
             // Entries above the boundary bucket are certainly among the k best; of the c_b entries IN the boundary bucket only the
             // best r = k − (count above) are.  When that makes exactly k <= 512 entries the final sort runs on 512 instead of
             // 1024 slots, so the boundary bucket (a handful of entries) is cut by exact rank first.
-            const int c_b = hist_f[bstar], n_above = m_fast - c_b, r_keep = k - n_above;
+            const int c_b = s_c, n_above = m_fast - c_b, r_keep = k - n_above;
             const bool cut = m_fast > 512 && k <= 512 && c_b <= 512;
             int cnt_a = 0, cnt_b = 0;
             for (int i = tid; i < n; i += NT) {
@@ -721,6 +760,7 @@ __global__ void __launch_bounds__(NT) select_topk_kernel(const float* __restrict
         }
         m = k;
     }
+    if (emitted) return;             // (block-uniform)
     // ---- bitonic sort of the m collected entries, descending by (key, then ascending position) ---------------- //
     int sort_n = 2;
     while (sort_n < m) sort_n <<= 1;
@@ -742,8 +782,6 @@ __global__ void __launch_bounds__(NT) select_topk_kernel(const float* __restrict
             }
         }
     }
-    __syncthreads();
-    res.stage(q, aux, tid, NT);          // resolver copies its per-query tables into shared memory (no dependent global chains)
     __syncthreads();
     const int n_out = m < k ? m : k;
     for (int j = tid; j < k; j += NT) {
