@@ -343,7 +343,7 @@ def ivf_roofline(scan_bytes, run_ms, n, d, nq, k, n_cand, pk):
     fraction of peak computed from it (2.7 in round 1) is not a roofline statement; it is kept as `query_major`."""
     phys = n * (4 * d + 8) + 2 * n_cand * 4 + nq * k * 12
     traffic = ncu_traffic("list_scan_tc_kernel+select_topk_kernel")
-    return {"kernel": "list_scan_tc_kernel + select_topk_kernel<ResolveIvf> (rb200_ivf_search_run)", "bound": "hbm", "unit": "GB/s",
+    return {"kernel": "list_scan_pipe_kernel + select_topk_kernel<ResolveIvf> (rb200_ivf_search_run)", "bound": "hbm", "unit": "GB/s",
             "achieved": phys / (run_ms * 1e-3) / 1e9, "peak": pk["hbm_gbs"], "frac": phys / (run_ms * 1e-3) / 1e9 / pk["hbm_gbs"],
             "peak_source": pk["source"], "algorithmic_bytes": phys, "ms": run_ms, "traffic": traffic,
             "definition": "list-major: database read once (N·(4·D+8)) + candidate scores written and read once (2·4·candidates) + results",

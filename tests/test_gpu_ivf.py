@@ -115,6 +115,30 @@ def test_exact_ties_follow_scan_order():
     np.testing.assert_array_equal(s, s_ref)
 
 
+@pytest.mark.parametrize("dup", [300, 700])
+def test_many_equal_scores_keep_scan_order(dup):
+    """`dup` copies of one vector give `dup` equal best scores, all in one value bucket of the top-k select: up to 512 entries per
+    bucket the winners are placed by their rank inside the bucket, above that by the bitonic path — scan order either way."""
+    import recommendit_b200 as R
+    rng = np.random.default_rng(dup)
+    n, d, k = 3000, 32, 500
+    x = V.normalize_rows(rng.standard_normal((n, d)).astype(np.float32))
+    where = rng.choice(n, dup, replace=False)
+    x[where] = x[where[0]]
+    c = V.normalize_rows(rng.standard_normal((2, d)).astype(np.float32))
+    idx = R.FAISSIndex(d, 2, 2)
+    idx.build_ivf_index(x, list(range(n)), centroids=c)
+    q = x[where[:1]].copy()
+    s, ids = idx.batch_search(q, k)
+    xn = V.normalize_rows(x)
+    off, order = V.build_lists(V.assign(xn, c), 2)
+    s_ref, i_ref = V.ivf_search(V.normalize_rows(q), c, off, order, xn, 2, k)
+    m = min(dup, k)
+    assert ids[0, :m].tolist() == i_ref[0, :m].tolist()
+    assert len(set(np.asarray(s)[0, :m].tolist())) == 1
+    V.assert_topk_equivalent(s, ids, s_ref, i_ref, rtol=1e-5, atol=1e-5)
+
+
 def test_gpu_kmeans_trains_a_usable_quantizer():
     """index.train is not bit-reproducible against FAISS (nor required to be); check the objective instead."""
     import recommendit_b200 as R
