@@ -478,7 +478,9 @@ template <> __device__ long long resolve_id<ResolveSurv>(const ResolveSurv& r, i
     return r.row_base + r.rows[(long long)q * r.cap + (c - r.kprev)];
 }
 
-constexpr int SORT_CAP = 2048;   // winners + boundary bucket must fit the in-CTA sort (falls back to radix select otherwise)
+constexpr int SORT_CAP = 2048;   // winners + boundary bucket must fit the in-CTA buffer (falls back to radix select otherwise); the buffer
+                                 // of a launch is sized by its k (sort_cap: a power of two ≥ 4·k in 256 … SORT_CAP) — the coarse
+                                 // quantizer's top-nprobe select keeps 8 CTAs per SM that way instead of 6
 constexpr int NBK = 1024;        // value-range buckets of the fast path (fine enough that top-500 + boundary bucket ≤ 512 usually)
 constexpr int RANK_MAX = 512;    // fullest bucket for which the winners are ordered by in-bucket ranks instead of the bitonic sort
 
@@ -548,12 +550,12 @@ __device__ __forceinline__ void reg_bitonic_sort(uint32_t* skey, int* sidx, int 
 template <typename R>
 __global__ void __launch_bounds__(NT) select_topk_kernel(const float* __restrict__ cand, const long long* __restrict__ cand_off,
                                                          long long fixed_stride, const long long* __restrict__ counts,
-                                                         int fixed_count, int k, int cache_cap, R res,
+                                                         int fixed_count, int k, int cache_cap, int sort_cap, R res,
                                                          float* __restrict__ out_scores, int64_t* __restrict__ out_ids) {
     extern __shared__ __align__(16) unsigned char sm_raw[];
-    uint32_t* skey = reinterpret_cast<uint32_t*>(sm_raw);           // [SORT_CAP]
-    int* sidx = reinterpret_cast<int*>(skey + SORT_CAP);            // [SORT_CAP]
-    float* cache = reinterpret_cast<float*>(sidx + SORT_CAP);       // [cache_cap]
+    uint32_t* skey = reinterpret_cast<uint32_t*>(sm_raw);           // [sort_cap]
+    int* sidx = reinterpret_cast<int*>(skey + sort_cap);            // [sort_cap]
+    float* cache = reinterpret_cast<float*>(sidx + sort_cap);       // [cache_cap]
     int* aux = reinterpret_cast<int*>(cache + cache_cap);           // [res.aux_ints()] per-query lookup tables of the resolver
     __shared__ int hist[256];
     __shared__ int hist_f[NBK];           // fast path: NBK linear buckets over [min, max]
@@ -586,7 +588,7 @@ __global__ void __launch_bounds__(NT) select_topk_kernel(const float* __restrict
                                      // path below passes a block barrier before it resolves ids
     int m = 0;                       // number of entries placed in skey/sidx
     bool done = false, emitted = false;
-    if (n <= SORT_CAP && n <= 2 * k) {
+    if (n <= sort_cap && n <= 2 * k) {
         // small input: sort everything
         for (int i = tid; i < n; i += NT) { skey[i] = f2key(src[i]); sidx[i] = i; }
         m = n; done = true;
@@ -636,7 +638,7 @@ __global__ void __launch_bounds__(NT) select_topk_kernel(const float* __restrict
         __syncthreads();
         const int bstar = s_a, m_fast = s_b;
         auto bucket_of = [&](float v) { return min(NBK - 1, (int)((v - lo) * scale)); };
-        if (m_fast <= SORT_CAP && scale > 0.f && !any_big) {
+        if (m_fast <= sort_cap && scale > 0.f && !any_big) {
             // hist_f[b] := entries in buckets > b = first output position of bucket b (each thread converts the PB buckets it summed;
             // nobody reads the counts any more).  The scatter's atomicAdd then hands out the slots of the bucket's range and leaves
             // hist_f[b] at the range's end, which is the beginning of bucket b − 1's.
@@ -665,7 +667,7 @@ __global__ void __launch_bounds__(NT) select_topk_kernel(const float* __restrict
                 }
             }
             done = true; emitted = true;
-        } else if (m_fast <= SORT_CAP && scale > 0.f) {
+        } else if (m_fast <= sort_cap && scale > 0.f) {
             // compaction without a per-iteration atomic (measured: the ballot + atomicAdd loop was 29 % of the kernel): every
             // thread counts its own survivors, one block-wide exclusive scan places them, a second pass writes them.  The
             // order of the survivors is irrelevant (they are sorted by (score, position) below).
@@ -690,7 +692,7 @@ __global__ void __launch_bounds__(NT) select_topk_kernel(const float* __restrict
             int pa = inc_a - cnt_a, pb = inc_b - cnt_b;
             for (int w = 0; w < warp; ++w) { pa += wsum[0][w]; pb += wsum[1][w]; }
             // boundary entries: behind the others (plain compaction) or parked at the end of the sort buffer (exact cut)
-            const int b_base = cut ? SORT_CAP - c_b : n_above;
+            const int b_base = cut ? sort_cap - c_b : n_above;
             for (int i = tid; i < n; i += NT) {
                 const float v = src[i];
                 const int b = min(NBK - 1, (int)((v - lo) * scale));
@@ -808,13 +810,15 @@ int launch_select(const float* cand, const long long* cand_off, long long fixed_
     if (!cap_max) { const char* e = getenv("RB200_SELECT_CACHE"); cap_max = e ? atoi(e) : 8192; if (cap_max < 1024) cap_max = 1024; }
     int cache_cap = (int)(max_count < cap_max ? max_count : cap_max);
     if (cache_cap < 0) cache_cap = 0;
-    const size_t smem = (size_t)SORT_CAP * 8 + (size_t)cache_cap * 4 + (size_t)res.aux_ints() * 4 + 16;
+    int sort_cap = 256;
+    while (sort_cap < 4 * k && sort_cap < SORT_CAP) sort_cap <<= 1;
+    const size_t smem = (size_t)sort_cap * 8 + (size_t)cache_cap * 4 + (size_t)res.aux_ints() * 4 + 16;
     static size_t attr_smem = 0;
     if (smem > attr_smem) {
         RB_CUDA(cudaFuncSetAttribute(select_topk_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem > 48 * 1024 ? smem : 48 * 1024)));
         attr_smem = smem;
     }
-    select_topk_kernel<R><<<nq, NT, smem, st>>>(cand, cand_off, fixed_stride, counts, fixed_count, k, cache_cap, res, out_scores,
+    select_topk_kernel<R><<<nq, NT, smem, st>>>(cand, cand_off, fixed_stride, counts, fixed_count, k, cache_cap, sort_cap, res, out_scores,
                                                 out_ids);
     RB_LAUNCH_CHECK("select_topk_kernel");
     return RB200_OK;
