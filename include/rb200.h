@@ -428,12 +428,16 @@ int rb200_ivf_build(const float* x, int64_t n, int D, const int32_t* assign, int
  *                          back (CUDA-graph capturable) and the caller sizes rb200_ivf_search_run by the
  *                          upper bounds total = nq·nprobe·max_list_len, max = nprobe·max_list_len.
  *   rb200_ivf_search_run   list-major scan into the candidate buffer + per-query top-k.
+ *   rb200_ivf_search_status  SYNCHRONISES the stream and reports a timed-out tensor-core pipeline of the searches that
+ *                          used this plan workspace since its last rb200_ivf_search_plan (RB200_ERR_INVALID + message);
+ *                          the host-facing search calls it before it hands results out.
  * out_scores [nq,k] (-FLT_MAX padding), out_ids [nq,k] internal row numbers (-1 padding); k <= 2048. */
 size_t rb200_ivf_plan_workspace_bytes(int nq, int nlist, int nprobe);
 int rb200_ivf_search_plan(const float* q, int nq, int D, const float* centroids, int nlist, int nprobe,
                           const int64_t* offsets, void* plan_ws, size_t plan_ws_bytes,
                           int64_t* total_candidates_host, int64_t* max_candidates_host, void* stream);
 size_t rb200_ivf_search_workspace_bytes(int64_t total_candidates);
+int rb200_ivf_search_status(const void* plan_ws, size_t plan_ws_bytes, int nq, int nlist, int nprobe, void* stream);
 /* tile_list / tile_idx (optional, int32 [n_tiles]): the index's table of (list, 64-vector tile) work items — one CTA per
  * non-empty tile instead of a (max tiles) × nlist grid full of empty CTAs.  It depends only on `offsets`; build it once.
  * n_vectors: rows of list_vecs (= offsets[nlist]; the D = 64 scan fetches vector tiles with a tensor map over [n_vectors, D]). */

@@ -143,6 +143,7 @@ SIGNATURES = {
     "rb200_ivf_plan_workspace_bytes": (SZ, [I, I, I]),
     "rb200_ivf_search_plan": (I, [P, I, I, P, I, I, P, P, SZ, C.POINTER(I64), C.POINTER(I64), P]),
     "rb200_ivf_search_workspace_bytes": (SZ, [I64]),
+    "rb200_ivf_search_status": (I, [P, SZ, I, I, I, P]),
     "rb200_ivf_search_run": (I, [P, I, I, I, I, P, P, P, I64, I64, P, P, I, I, P, SZ, I64, I64, P, P, P, SZ, P]),
     "rb200_flat_search_workspace_bytes": (SZ, [I, I64, I]),
     "rb200_flat_search": (I, [P, I, P, I64, I, I, I64, P, P, P, SZ, P]),

@@ -981,6 +981,18 @@ extern "C" int rb200_ivf_search_plan(const float* q, int nq, int D, const float*
     return RB200_OK;
 }
 
+extern "C" int rb200_ivf_search_status(const void* plan_ws, size_t plan_ws_bytes, int nq, int nlist, int nprobe, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    RbArena pa(const_cast<void*>(plan_ws), plan_ws_bytes);
+    PlanLayout L;
+    if (!plan_ws || !carve_plan(pa, nq, nlist, nprobe, L)) return rb_set_error(RB200_ERR_WORKSPACE, "ivf_search_status: plan workspace too small");
+    int flag = 0;
+    RB_CUDA(cudaMemcpyAsync(&flag, L.tc_err, sizeof(int), cudaMemcpyDeviceToHost, st));
+    RB_CUDA(cudaStreamSynchronize(st));
+    RB_REQUIRE(flag == 0, "ivf_search: the list scan's tensor-core pipeline timed out (flag %d): the results are not valid", flag);
+    return RB200_OK;
+}
+
 extern "C" size_t rb200_ivf_search_workspace_bytes(int64_t total_candidates) {
     return 256 + sizeof(float) * (size_t)(total_candidates > 0 ? total_candidates : 1);
 }

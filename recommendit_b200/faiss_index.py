@@ -158,6 +158,8 @@ class _IVFState:
                                        ptr(self.list_vecs), self.list_vecs.shape[0], self.max_list_len, ptr(self.tile_list), ptr(self.tile_idx),
                                        self.tile_list.numel(), k, ptr(plan), pb, total.value, mx.value,
                                        ptr(scores), ptr(rows), ptr(ws), wb, stream_ptr()), "rb200_ivf_search_run")
+        # every caller of this form hands the results to the host next: a timed-out tensor-core pipeline must not pass as a result
+        check(lib.rb200_ivf_search_status(ptr(plan), pb, nq, self.nlist, nprobe, stream_ptr()), "rb200_ivf_search_status")
         return scores, rows
 
     def search(self, queries: np.ndarray, k: int) -> Tuple[np.ndarray, np.ndarray]:
