@@ -491,7 +491,9 @@ int rb_list_scan_pipe(const float* q, int D, const float* list_vecs, long long n
     if (on < 0) { const char* e = getenv("RB200_IVF_PIPE"); on = e ? atoi(e) : 1; }
     // (the unit descriptors keep candidate offsets in 32 bits)
     if (!on || D != DD || !tile_list || !tile_idx || n_tiles <= 0 || n_tiles >= (1ll << 31) || total_candidates >= 0xFFFFFFFFll) return 1;
-    if (n_vectors < 1 || n_vectors >= (1ll << 31) || (reinterpret_cast<uintptr_t>(list_vecs) & 15)) return 1;
+    // (the tensor map: int32 row coordinates, a 16-byte aligned base, at least one full box of rows — smaller indexes take the
+    //  one-CTA-per-tile kernel, where speed does not matter)
+    if (n_vectors < VT || n_vectors >= (1ll << 31) || (reinterpret_cast<uintptr_t>(list_vecs) & 15)) return 1;
     EncodeTiledFn enc = encode_tiled_fn();
     if (!enc) return 1;
     CUtensorMap vmap;
@@ -502,7 +504,7 @@ int rb_list_scan_pipe(const float* q, int D, const float* list_vecs, long long n
         const cuuint32_t estr[2] = {1, 1};
         const CUresult r = enc(&vmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)list_vecs, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                                CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-        RB_REQUIRE(r == CUDA_SUCCESS, "list_scan_pipe: cuTensorMapEncodeTiled failed (%d)", (int)r);
+        if (r != CUDA_SUCCESS) return 1;                        // (not fatal: the other list-scan kernel needs no tensor map)
     }
     static bool attr_set = false;
     if (!attr_set) {
