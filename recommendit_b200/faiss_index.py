@@ -158,14 +158,23 @@ class _IVFState:
                                        ptr(self.list_vecs), self.list_vecs.shape[0], self.max_list_len, ptr(self.tile_list), ptr(self.tile_idx),
                                        self.tile_list.numel(), k, ptr(plan), pb, total.value, mx.value,
                                        ptr(scores), ptr(rows), ptr(ws), wb, stream_ptr()), "rb200_ivf_search_run")
-        # every caller of this form hands the results to the host next: a timed-out tensor-core pipeline must not pass as a result
-        check(lib.rb200_ivf_search_status(ptr(plan), pb, nq, self.nlist, nprobe, stream_ptr()), "rb200_ivf_search_status")
+        self._last_plan = (plan, pb, nq, nprobe)          # for check_last_search()
         return scores, rows
+
+    def check_last_search(self) -> None:
+        """SYNCHRONISES the stream and raises if a tensor-core pipeline of the last ``search_device`` timed out (garbage must not
+        pass as a result).  The host-facing searches call it where they wait for their device→host copies anyway."""
+        last = getattr(self, "_last_plan", None)
+        if last is None:
+            return
+        plan, pb, nq, nprobe = last
+        check(_lib.load().rb200_ivf_search_status(ptr(plan), pb, nq, self.nlist, nprobe, stream_ptr()), "rb200_ivf_search_status")
 
     def search(self, queries: np.ndarray, k: int) -> Tuple[np.ndarray, np.ndarray]:
         """faiss-style ``index.search(x, k)`` on host arrays (already normalised)."""
         q = torch.as_tensor(np.ascontiguousarray(queries, dtype=np.float32), device=self.centroids.device)
         s, r = self.search_device(q, k)
+        self.check_last_search()
         return s.cpu().numpy(), r.cpu().numpy()
 
 
@@ -232,7 +241,7 @@ class FAISSIndex:
             hr = torch.empty(r.shape, dtype=r.dtype, pin_memory=True)
             hs.copy_(s, non_blocking=True)
             hr.copy_(r, non_blocking=True)
-            torch.cuda.current_stream().synchronize()
+            st.check_last_search()                       # (synchronises the stream: the copies have landed)
             return hs.numpy(), hr.numpy()
 
     def search(self, query_vector: np.ndarray, k: int = 500) -> Tuple[np.ndarray, np.ndarray]:

@@ -984,6 +984,7 @@ class ShardedIVFIndex:
         st = self.local.index
         kk = min(k, max(st.ntotal, 1))
         s, i = st.search_device(queries, kk, id_table=self.local._list_item_ids)
+        st.check_last_search()
         if kk < k:                                               # a shard with fewer than k rows: pad to the common width
             pad_s = torch.full((s.shape[0], k - kk), -3.4028234663852886e38, dtype=s.dtype, device=s.device)
             pad_i = torch.full((s.shape[0], k - kk), -1, dtype=i.dtype, device=i.device)

@@ -168,6 +168,7 @@ class _OracleIVF:
             s, r = V.ivf_search(q.numpy(), cen, off, order, xn, self.nprobe, k)
             return torch.from_numpy(s), torch.from_numpy(np.where(r >= 0, ids[np.maximum(r, 0)], -1))
         st.search_device = search_device
+        st.check_last_search = lambda: None          # (the device index reads its tensor-core error flag here)
         self.index, self._list_item_ids = st, None
 
     def set_n_probe(self, n):
