@@ -350,7 +350,8 @@ def ivf_roofline(scan_bytes, run_ms, n, d, nq, k, n_cand, pk):
             "query_major": {"algorithmic_bytes": scan_bytes, "GBps_equivalent": scan_bytes / (run_ms * 1e-3) / 1e9,
                             "note": "SURVEY.md §8d's per-query figure nq·Σ_probed len·(4·D+8): what a query-major scan would read; "
                                     "reported for comparison with CPU FAISS-style scans, not as a fraction of peak"},
-            "note": "the pair is latency / SM-bound, not HBM-bound (profiles/r01_ncu_full_v2.md: DRAM traffic is 1.4x the database)"}
+            "note": "the pair is latency / SM-bound, not HBM-bound (profiles/r02_ivf.md: DRAM traffic is 1.4x the database; the list scan is bound by the SM's "
+                    "load/store path, the select by its passes over shared memory)"}
 
 
 def bench_ivf(args, dev):
